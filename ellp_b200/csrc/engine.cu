@@ -1,0 +1,723 @@
+// engine.cu -- host driver of the device-resident pivot loop + the C ABI of include/ellp_b200.h.
+//
+// The host only launches kernels and reads back the 16-byte index-level status; every number of the
+// iteration (B^-1, x, y, d, reduced costs, ratios) stays in HBM.  No CPU fallback exists: without a
+// CUDA device ellp_b200_create() fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "engine.hpp"
+#include "kernels.cuh"
+
+using namespace ellp;
+
+#define CUDA_TRY(expr)                                                                           \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                      \
+            return ELLP_E_CUDA;                                                                  \
+        }                                                                                        \
+    } while (0)
+
+#define LAUNCH(kernel, grid, block, ...)                                                         \
+    do {                                                                                         \
+        kernel<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__);                                \
+        ctx->launches++;                                                                         \
+    } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Arena {
+    size_t off = 0;
+    char* base = nullptr;
+    template <class T> T* take(size_t count) {
+        off = align_up(off, 256);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+struct ellp_b200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    char* arena = nullptr;
+    size_t arena_bytes = 0;
+    bool resident = false;
+    int solver = ELLP_PRIMAL;
+    DevLP lp{};
+    int KS = 1, kc = 64;
+    bool binv_valid = false;
+    uint64_t pivots_since_refactor = 0;
+    PivotState* d_st = nullptr;
+    PivotState* h_st = nullptr;  // pinned
+    int64_t trace_cap = 0;
+    double dual_obj0 = 0.;
+    std::vector<cudaEvent_t> ev;  // profile=1: pairs around rank-1 launches
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // tuning (ellp_b200_set_tuning)
+    int rank1_cols_per_cta = 64;
+    int rank1_stream_min_mb = 96;  // evict-first policy when the updated matrix is larger than this
+};
+
+namespace {
+
+int set_err(ellp_b200_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+int ensure_arena(ellp_b200_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->arena_bytes) return ELLP_OK;
+    if (ctx->arena) {
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaFree(ctx->arena));
+        ctx->arena = nullptr;
+        ctx->arena_bytes = 0;
+    }
+    bytes = align_up(bytes + (bytes >> 3), (size_t)1 << 21);
+    CUDA_TRY(cudaMalloc(&ctx->arena, bytes));
+    ctx->arena_bytes = bytes;
+    return ELLP_OK;
+}
+
+void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap) {
+    const size_t ld = (size_t)lp.ld, m = (size_t)lp.m, n = (size_t)lp.n, nN = (size_t)lp.nN;
+    lp.A = a.take<double>(ld * n);
+    lp.c = a.take<double>(n);
+    lp.b = a.take<double>(std::max<size_t>(m, 1));
+    lp.lb = a.take<double>(n);
+    lp.ub = a.take<double>(n);
+    lp.kind = a.take<uint8_t>(n);
+    lp.x = a.take<double>(n);
+    lp.Bv = a.take<int32_t>(std::max<size_t>(m, 1));
+    lp.Nv = a.take<int32_t>(std::max<size_t>(nN, 1));
+    lp.Ns = a.take<uint8_t>(std::max<size_t>(nN, 1));
+    lp.y = a.take<double>(ld);
+    lp.d = a.take<double>(n);
+    lp.G = a.take<double>(ld * 2 * m);
+    lp.Binv = lp.G ? lp.G + ld * m : nullptr;
+    lp.cB = a.take<double>(ld);
+    lp.u = a.take<double>(ld);
+    lp.rN = a.take<double>(std::max<size_t>(nN, 1));
+    lp.key = a.take<double>(std::max<size_t>(nN, 1));
+    lp.dcol = a.take<double>(ld);
+    lp.rho = a.take<double>(ld);
+    lp.prow = a.take<double>(2 * m + 8);
+    lp.part = a.take<double>((size_t)KS * ld);
+    lp.lam = a.take<double>(std::max<size_t>(m, 1));
+    lp.trace = trace_cap > 0 ? a.take<ellp_trace_rec>((size_t)trace_cap) : nullptr;
+}
+
+const char* dev_err_message(int e) {
+    switch (e) {
+        case kErrNaNPricing: return "NaN detected";
+        case kErrLambdaNegative: return "assertion failed: lambda >= 0.";
+        case kErrFlipFree: return "pivot should have been unbounded";
+        case kErrNaNDualRatio: return "called `Option::unwrap()` on a `None` value (partial_cmp)";
+        case kErrSingular: return "invalid B, A_B is not invertible";
+        default: return "unknown device error";
+    }
+}
+
+int read_state(ellp_b200_ctx* ctx) {
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_st, ctx->d_st, sizeof(PivotState), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return ELLP_OK;
+}
+
+int write_state(ellp_b200_ctx* ctx) {
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_st, ctx->h_st, sizeof(PivotState), cudaMemcpyHostToDevice, ctx->stream));
+    return ELLP_OK;
+}
+
+void launch_rank1(ellp_b200_ctx* ctx, double* E, int64_t ld, int R, int C, const double* alpha, const double* prow,
+                  const PivotState* st, int r_fixed) {
+    if (C <= 0 || R <= 0) return;
+    const int cpc = std::max(kColsInFlight, ctx->rank1_cols_per_cta);
+    dim3 grid((unsigned)((R + 2 * kRank1Threads - 1) / (2 * kRank1Threads)), (unsigned)((C + cpc - 1) / cpc));
+    const bool stream = (double)ld * C * 8.0 > (double)ctx->rank1_stream_min_mb * 1048576.0;
+    if (stream) LAUNCH(k_rank1<true>, grid, kRank1Threads, E, ld, R, C, alpha, prow, st, r_fixed, cpc);
+    else LAUNCH(k_rank1<false>, grid, kRank1Threads, E, ld, R, C, alpha, prow, st, r_fixed, cpc);
+}
+
+int gemv_grid(int ncols) { return std::max(1, std::min((ncols + 7) / 8, 148 * 32)); }
+
+// Gauss-Jordan refactorisation of B^-1 from the current basis (see kernels.cuh).
+int refactor(ellp_b200_ctx* ctx, uint64_t* count) {
+    DevLP& lp = ctx->lp;
+    const int m = lp.m;
+    // preserve the iteration's index-level state around the factorisation
+    if (int rc = read_state(ctx)) return rc;
+    PivotState saved = *ctx->h_st;
+    LAUNCH(k_gj_init, 2 * m, 256, lp);
+    for (int k = 0; k < m; ++k) {
+        LAUNCH(k_gj_pivot, 1, 1024, lp, k, ctx->d_st);
+        const int cols = 2 * m - k;
+        LAUNCH(k_gj_swap_gather, (cols + 255) / 256, 256, lp, k, ctx->d_st);
+        launch_rank1(ctx, lp.G + (int64_t)k * lp.ld, lp.ld, m, cols, lp.dcol, lp.prow, ctx->d_st, 0);
+    }
+    if (int rc = read_state(ctx)) return rc;
+    const int err = ctx->h_st->err;
+    *ctx->h_st = saved;
+    ctx->h_st->err = 0;
+    if (int rc = write_state(ctx)) return rc;
+    if (err == kErrSingular) return set_err(ctx, ELLP_E_ELLP, dev_err_message(err));
+    ctx->binv_valid = true;
+    ctx->pivots_since_refactor = 0;
+    if (count) ++*count;
+    return ELLP_OK;
+}
+
+void launch_primal_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, bool profile, size_t* ev_used) {
+    DevLP& lp = ctx->lp;
+    PivotState* st = ctx->d_st;
+    const int m = lp.m, nN = lp.nN;
+    // BTRAN u = B^-T c_B  (primal :184-187)
+    LAUNCH(k_gemv_t<EPI_PLAIN>, gemv_grid(m), 256, lp.Binv, lp.ld, (const int32_t*)nullptr, m, lp.cB, lp.u,
+           (const double*)nullptr, (const uint8_t*)nullptr, (double*)nullptr, st, 1);
+    // pricing r = c_N - A_N^T u + Dantzig keys  (primal :189, :253-270)
+    LAUNCH(k_gemv_t<EPI_PRIMAL_PRICE>, gemv_grid(nN), 256, lp.A, lp.ld, lp.Nv, nN, lp.u, lp.rN, lp.c, lp.Ns, lp.key, st, 0);
+    LAUNCH(k_select_primal, 1, 32, lp.key, lp.rN, lp.Nv, lp.Ns, nN, o->tie_rule, st);
+    // FTRAN d = B^-1 a_q  (primal :295)
+    dim3 fg((unsigned)((lp.ld + 255) / 256), (unsigned)ctx->KS);
+    LAUNCH(k_ftran_partial, fg, 128, lp.Binv, lp.ld, m, lp.A, st, lp.part, ctx->kc);
+    LAUNCH(k_ratio_primal, 1, 1024, lp, ctx->KS, o->tie_rule, st);
+    LAUNCH(k_gather_row, (m + 255) / 256, 256, lp.Binv, lp.ld, m, st, lp.prow, 1);
+    if (profile && *ev_used + 2 <= ctx->ev.size()) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
+    launch_rank1(ctx, lp.Binv, lp.ld, m, m, lp.dcol, lp.prow, st, 0);
+    if (profile && (*ev_used & 1)) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
+}
+
+void launch_dual_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, bool profile, size_t* ev_used) {
+    DevLP& lp = ctx->lp;
+    PivotState* st = ctx->d_st;
+    const int m = lp.m, nN = lp.nN;
+    LAUNCH(k_dual_leaving, 1, 1024, lp, st);                                                  // dual :200-236
+    LAUNCH(k_gather_row, (m + 255) / 256, 256, lp.Binv, lp.ld, m, st, lp.rho, 0);             // rho = e_r^T B^-1 (:248-253)
+    LAUNCH(k_gemv_t<EPI_PLAIN>, gemv_grid(nN), 256, lp.A, lp.ld, lp.Nv, nN, lp.rho, lp.rN,  // alpha = A_N^T rho (:255)
+           (const double*)nullptr, (const uint8_t*)nullptr, (double*)nullptr, st, 0);
+    LAUNCH(k_select_dual, 1, 1024, lp, st);                                                   // :257-289
+    dim3 fg((unsigned)((lp.ld + 255) / 256), (unsigned)ctx->KS);
+    LAUNCH(k_ftran_partial, fg, 128, lp.Binv, lp.ld, m, lp.A, st, lp.part, ctx->kc);          // :294
+    LAUNCH(k_dual_update, 1, 1024, lp, ctx->KS, st);                                          // :296-333
+    if (profile && *ev_used + 2 <= ctx->ev.size()) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
+    launch_rank1(ctx, lp.Binv, lp.ld, m, m, lp.dcol, lp.prow, st, 0);
+    if (profile && (*ev_used & 1)) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
+}
+
+double host_dual_obj(const ellp_std_form* sf, const double* y, const double* d) {  // standard_form.rs:52-68
+    double o = 0.;
+    for (int i = 0; i < sf->m; ++i) o += sf->b[i] * y[i];
+    for (int i = 0; i < sf->n; ++i) {
+        switch (sf->kind[i]) {
+            case ELLP_FREE: break;
+            case ELLP_LOWER: o += sf->lb[i] * d[i]; break;
+            case ELLP_UPPER: o += sf->ub[i] * d[i]; break;
+            case ELLP_TWOSIDED: o += (d[i] > 0.) ? sf->lb[i] * d[i] : sf->ub[i] * d[i]; break;
+            default: o += sf->lb[i] * d[i];
+        }
+    }
+    return o;
+}
+
+}  // namespace
+
+// solve_trivial_problem (solvers/trivial/solve_trivial_problem.rs:5-96), host side: O(n) scalar work.
+int ellp::host_solve_trivial(const ellp_std_form* sf, ellp_point* pt, bool minimize) {
+    int nN = 0;
+    for (int i = 0; i < sf->n; ++i) {
+        const double c_i = sf->c[i];
+        auto push = [&](int side) {
+            if (pt->N) { pt->N[nN] = i; pt->N_side[nN] = (uint8_t)side; }
+            ++nN;
+        };
+        switch (sf->kind[i]) {
+            case ELLP_FREE:
+                push(ELLP_NB_FREE);
+                if (c_i != 0.) { pt->nN = nN; return ELLP_UNBOUNDED; }
+                pt->x[i] = 0.;
+                break;
+            case ELLP_LOWER:
+                push(ELLP_NB_LOWER);
+                if (c_i > 0.) { if (minimize) pt->x[i] = sf->lb[i]; else { pt->nN = nN; return ELLP_UNBOUNDED; } }
+                else if (minimize) pt->x[i] = sf->lb[i];
+                else { if (c_i != 0.) { pt->nN = nN; return ELLP_UNBOUNDED; } pt->x[i] = sf->lb[i]; }
+                break;
+            case ELLP_UPPER:
+                push(ELLP_NB_UPPER);
+                if (c_i > 0.) { if (minimize) { pt->nN = nN; return ELLP_UNBOUNDED; } pt->x[i] = sf->ub[i]; }
+                else if (minimize) { if (c_i != 0.) { pt->nN = nN; return ELLP_UNBOUNDED; } pt->x[i] = sf->ub[i]; }
+                else pt->x[i] = sf->ub[i];
+                break;
+            case ELLP_TWOSIDED:
+                if ((c_i > 0.) == minimize) { push(ELLP_NB_LOWER); pt->x[i] = sf->lb[i]; }
+                else { push(ELLP_NB_UPPER); pt->x[i] = sf->ub[i]; }
+                break;
+            default:
+                push(ELLP_NB_LOWER);
+                pt->x[i] = sf->lb[i];
+        }
+    }
+    pt->nN = nN;
+    return ELLP_OPTIMAL;
+}
+
+extern "C" {
+
+const char* ellp_b200_version(void) { return "ellp_b200 0.1 (sm_100a)"; }
+
+int ellp_b200_create(int device, ellp_b200_ctx** out) {
+    if (!out) return ELLP_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return ELLP_E_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return ELLP_E_CUDA;
+    auto* ctx = new ellp_b200_ctx();
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&ctx->d_st, sizeof(PivotState)) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_st, sizeof(PivotState)) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        delete ctx;
+        return ELLP_E_CUDA;
+    }
+    std::memset(ctx->h_st, 0, sizeof(PivotState));
+    *out = ctx;
+    return ELLP_OK;
+}
+
+void ellp_b200_destroy(ellp_b200_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto e : ctx->ev) cudaEventDestroy(e);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->d_st) cudaFree(ctx->d_st);
+    if (ctx->h_st) cudaFreeHost(ctx->h_st);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* ellp_b200_last_error(const ellp_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+void ellp_b200_set_error_(ellp_b200_ctx* ctx, const char* msg) { if (ctx) ctx->err = msg ? msg : ""; }
+uint64_t ellp_b200_launch_count(const ellp_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void ellp_b200_reset_launch_count(ellp_b200_ctx* ctx) { if (ctx) ctx->launches = 0; }
+
+int ellp_b200_set_tuning(ellp_b200_ctx* ctx, const char* key, int value) {
+    if (!ctx || !key) return ELLP_E_ARG;
+    if (!std::strcmp(key, "rank1_cols_per_cta")) ctx->rank1_cols_per_cta = value;
+    else if (!std::strcmp(key, "rank1_stream_min_mb")) ctx->rank1_stream_min_mb = value;
+    else return set_err(ctx, ELLP_E_ARG, std::string("unknown tuning key ") + key);
+    return ELLP_OK;
+}
+
+void ellp_b200_default_opts(ellp_opts* o) {
+    std::memset(o, 0, sizeof(*o));
+    o->max_iter = 1000;  // {Primal,Dual}SimplexSolver::default() (primal :19-23, dual :20-24)
+    o->tie_rule = ELLP_TIES_REFERENCE;
+    o->engine = ELLP_ENGINE_AUTO;
+}
+
+int ellp_b200_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_point* pt, int solver, const ellp_opts* o) {
+    if (!ctx || !sf || !pt) return ELLP_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int m = sf->m, n = sf->n;
+    if (m <= 0 || n < m) return set_err(ctx, ELLP_E_ARG, "upload needs 0 < m <= n");
+    DevLP lp{};
+    lp.m = m;
+    lp.n = n;
+    lp.nN = n - m;
+    lp.ld = (int64_t)align_up((size_t)m, 4);
+    int kc = std::max(64, (m + 63) / 64);
+    kc = std::min(kc, kFtranMaxKc);
+    const int KS = (m + kc - 1) / kc;
+    const int64_t tcap = (o && o->trace) ? o->trace_cap : 0;
+    Arena probe;
+    carve(probe, lp, KS, tcap);
+    if (int rc = ensure_arena(ctx, probe.off + 256)) return rc;
+    Arena a;
+    a.base = ctx->arena;
+    carve(a, lp, KS, tcap);
+    cudaStream_t s = ctx->stream;
+    // zero the padded scratch once (padding rows must stay zero)
+    CUDA_TRY(cudaMemsetAsync(lp.cB, 0, (size_t)((char*)lp.lam - (char*)lp.cB), s));
+    CUDA_TRY(cudaMemsetAsync(lp.y, 0, sizeof(double) * lp.ld, s));
+    if (lp.ld == m) {
+        CUDA_TRY(cudaMemcpyAsync((void*)lp.A, sf->A, sizeof(double) * (size_t)m * n, cudaMemcpyHostToDevice, s));
+    } else {
+        CUDA_TRY(cudaMemsetAsync((void*)lp.A, 0, sizeof(double) * (size_t)lp.ld * n, s));
+        CUDA_TRY(cudaMemcpy2DAsync((void*)lp.A, sizeof(double) * lp.ld, sf->A, sizeof(double) * m, sizeof(double) * m, n,
+                                   cudaMemcpyHostToDevice, s));
+    }
+    CUDA_TRY(cudaMemcpyAsync((void*)lp.c, sf->c, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync((void*)lp.b, sf->b, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync((void*)lp.lb, sf->lb, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync((void*)lp.ub, sf->ub, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync((void*)lp.kind, sf->kind, (size_t)n, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(lp.x, pt->x, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(lp.Bv, pt->B, sizeof(int32_t) * m, cudaMemcpyHostToDevice, s));
+    if (lp.nN > 0) {
+        CUDA_TRY(cudaMemcpyAsync(lp.Nv, pt->N, sizeof(int32_t) * lp.nN, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(lp.Ns, pt->N_side, (size_t)lp.nN, cudaMemcpyHostToDevice, s));
+    }
+    ctx->dual_obj0 = 0.;
+    if (solver == ELLP_DUAL) {
+        if (!pt->y || !pt->d) return set_err(ctx, ELLP_E_ARG, "dual solve needs y and d");
+        CUDA_TRY(cudaMemcpyAsync(lp.y, pt->y, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(lp.d, pt->d, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+        ctx->dual_obj0 = host_dual_obj(sf, pt->y, pt->d);
+    }
+    ctx->lp = lp;
+    ctx->KS = KS;
+    ctx->kc = kc;
+    ctx->trace_cap = tcap;
+    ctx->solver = solver;
+    ctx->resident = true;
+    ctx->binv_valid = false;
+    // host buffers are only borrowed for the duration of the call
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return ELLP_OK;
+}
+
+int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
+    if (!ctx || !o || !res) return ELLP_E_ARG;
+    if (!ctx->resident) return set_err(ctx, ELLP_E_ARG, "no LP resident: call ellp_b200_upload first");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    DevLP& lp = ctx->lp;
+    const uint64_t launches0 = ctx->launches;
+    std::memset(res, 0, sizeof(*res));
+    PivotState& h = *ctx->h_st;
+    std::memset(&h, 0, sizeof(h));
+    h.status = kRunning;
+    h.max_iter = o->max_iter;
+    h.phase_tag = o->phase_tag;
+    h.trace_cap = (o->trace && lp.trace) ? std::min<int64_t>(o->trace_cap, ctx->trace_cap) : 0;
+    h.obj = ctx->dual_obj0;
+    if (o->max_iter == 0) h.status = ELLP_MAXITER;  // primal :163 (iter=1 > 0), dual :191 (0 >= 0)
+    if (int rc = write_state(ctx)) return rc;
+    const bool profile = o->profile != 0;
+    if (profile && ctx->ev.size() < 8192) {
+        const size_t old = ctx->ev.size();
+        ctx->ev.resize(8192);
+        for (size_t i = old; i < ctx->ev.size(); ++i) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
+    }
+    size_t ev_used = 0;
+    if (!ctx->binv_valid) {
+        if (int rc = refactor(ctx, &res->refactors)) return rc;
+    }
+    LAUNCH(k_init_cB, (int)((lp.ld + 255) / 256), 256, lp);
+    if (ctx->solver == ELLP_PRIMAL) LAUNCH(k_obj_dot, 1, 1024, lp.c, lp.x, lp.n, ctx->d_st);
+    int check_every = o->check_every > 0 ? o->check_every : (lp.m >= 2048 ? 1 : 8);
+    int refactor_every = o->refactor_every > 0 ? o->refactor_every : (lp.m <= 512 ? 100 : 0);
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    int rc_loop = ELLP_OK;
+    while (h.status == kRunning) {
+        int batch = check_every;
+        if (refactor_every > 0) batch = (int)std::min<uint64_t>(batch, std::max<uint64_t>(1, refactor_every - ctx->pivots_since_refactor));
+        for (int k = 0; k < batch; ++k) {
+            if (ctx->solver == ELLP_PRIMAL) launch_primal_iteration(ctx, o, profile, &ev_used);
+            else launch_dual_iteration(ctx, o, profile, &ev_used);
+        }
+        const uint64_t before = h.pivots;
+        if ((rc_loop = read_state(ctx))) break;
+        ctx->pivots_since_refactor += h.pivots - before;
+        if (h.status != kRunning) break;
+        if (refactor_every > 0 && ctx->pivots_since_refactor >= (uint64_t)refactor_every) {
+            if ((rc_loop = refactor(ctx, &res->refactors))) break;
+        }
+    }
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (rc_loop) return rc_loop;
+    CUDA_TRY(cudaGetLastError());
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    res->ms_device = ms;
+    if (profile) {
+        for (size_t i = 0; i + 1 < ev_used; i += 2) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, ctx->ev[i], ctx->ev[i + 1]) == cudaSuccess) { res->ms_rank1 += t; res->n_rank1++; }
+        }
+    }
+    res->status = h.status;
+    res->iters = h.pivots;
+    res->trace_len = h.trace_len;
+    res->launches = ctx->launches - launches0;
+    res->obj = h.obj;
+    if (o->trace && h.trace_cap > 0) {
+        const int64_t nrec = std::min<int64_t>(h.trace_len, h.trace_cap);
+        if (nrec > 0) CUDA_TRY(cudaMemcpy(o->trace, lp.trace, sizeof(ellp_trace_rec) * (size_t)nrec, cudaMemcpyDeviceToHost));
+    }
+    if (h.err) {
+        const int code = (h.err == kErrSingular) ? ELLP_E_ELLP : ELLP_E_PANIC;
+        return set_err(ctx, code, dev_err_message(h.err));
+    }
+    return ELLP_OK;
+}
+
+int ellp_b200_download(ellp_b200_ctx* ctx, ellp_point* pt) {
+    if (!ctx || !pt || !ctx->resident) return ELLP_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    DevLP& lp = ctx->lp;
+    cudaStream_t s = ctx->stream;
+    CUDA_TRY(cudaMemcpyAsync(pt->x, lp.x, sizeof(double) * lp.n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(pt->B, lp.Bv, sizeof(int32_t) * lp.m, cudaMemcpyDeviceToHost, s));
+    if (lp.nN > 0) {
+        CUDA_TRY(cudaMemcpyAsync(pt->N, lp.Nv, sizeof(int32_t) * lp.nN, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(pt->N_side, lp.Ns, (size_t)lp.nN, cudaMemcpyDeviceToHost, s));
+    }
+    if (ctx->solver == ELLP_DUAL && pt->y && pt->d) {
+        CUDA_TRY(cudaMemcpyAsync(pt->y, lp.y, sizeof(double) * lp.m, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(pt->d, lp.d, sizeof(double) * lp.n, cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return ELLP_OK;
+}
+
+static int solve_with_initial(ellp_b200_ctx* ctx, const ellp_std_form* sf, ellp_point* pt, const ellp_opts* o,
+                              ellp_result* res, int solver) {
+    if (!ctx || !sf || !pt || !o || !res) return ELLP_E_ARG;
+    std::memset(res, 0, sizeof(*res));
+    const int m = sf->m, n = sf->n;
+    if (m == 0) {  // primal :118-122 / dual :132-136
+        if (pt->nB != 0) return set_err(ctx, ELLP_E_PANIC, "assertion failed: B.is_empty()");
+        res->status = ellp::host_solve_trivial(sf, pt, true);
+        double obj = 0.;
+        for (int i = 0; i < n; ++i) obj += sf->c[i] * pt->x[i];
+        res->obj = obj;
+        return ELLP_OK;
+    }
+    if (solver == ELLP_DUAL) {  // dual :139-151
+        for (int j = 0; j < pt->nN; ++j) {
+            const double d_i = pt->d[pt->N[j]];
+            const int side = pt->N_side[j];
+            const bool infeasible = side == ELLP_NB_LOWER ? d_i < -kEps : (side == ELLP_NB_UPPER ? d_i > kEps : std::fabs(d_i) > kEps);
+            if (infeasible) return set_err(ctx, ELLP_E_PANIC, "initial point of dual phase 2 is dual infeasible");
+        }
+    }
+    char buf[160];
+    if (pt->nB != m) {  // primal :124-130 / dual :153-159
+        std::snprintf(buf, sizeof buf, "invalid B, has %d elements but %d expected", pt->nB, m);
+        return set_err(ctx, ELLP_E_ELLP, buf);
+    }
+    if (n < m) return set_err(ctx, ELLP_E_PANIC, "called `Option::unwrap()` on a `None` value");  // checked_sub
+    if (pt->nN != n - m) {  // primal :134-140 / dual :163-169
+        std::snprintf(buf, sizeof buf, "invalid N, has %d elements but %d expected", pt->nN, n - m);
+        return set_err(ctx, ELLP_E_ELLP, buf);
+    }
+    if (n == m) {  // N empty: primal :149-151 / dual :175-177 (Optimal without any further check)
+        res->status = ELLP_OPTIMAL;
+        double obj = 0.;
+        for (int i = 0; i < n; ++i) obj += sf->c[i] * pt->x[i];
+        res->obj = solver == ELLP_PRIMAL ? obj : host_dual_obj(sf, pt->y, pt->d);
+        return ELLP_OK;
+    }
+    if (int rc = ellp_b200_upload(ctx, sf, pt, solver, o)) return rc;
+    int rc = ellp_b200_run(ctx, o, res);
+    if (rc) return rc;
+    if ((rc = ellp_b200_download(ctx, pt))) return rc;
+    if (solver == ELLP_PRIMAL) {  // StandardForm::obj (standard_form.rs:47-50)
+        double obj = 0.;
+        for (int i = 0; i < n; ++i) obj += sf->c[i] * pt->x[i];
+        res->obj = obj;
+    } else {
+        res->obj = host_dual_obj(sf, pt->y, pt->d);
+    }
+    return ELLP_OK;
+}
+
+int ellp_b200_primal_solve_with_initial(ellp_b200_ctx* ctx, const ellp_std_form* sf, ellp_point* pt, const ellp_opts* o,
+                                        ellp_result* res) {
+    return solve_with_initial(ctx, sf, pt, o, res, ELLP_PRIMAL);
+}
+
+int ellp_b200_dual_solve_with_initial(ellp_b200_ctx* ctx, const ellp_std_form* sf, ellp_point* pt, const ellp_opts* o,
+                                      ellp_result* res) {
+    return solve_with_initial(ctx, sf, pt, o, res, ELLP_DUAL);
+}
+
+// ---- kernel-level entry points -------------------------------------------------------------------
+int ellp_b200_dev_alloc(ellp_b200_ctx* ctx, uint64_t bytes, void** dptr) {
+    if (!ctx || !dptr) return ELLP_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMalloc(dptr, bytes));
+    return ELLP_OK;
+}
+int ellp_b200_dev_free(ellp_b200_ctx* ctx, void* dptr) {
+    if (!ctx) return ELLP_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaFree(dptr));
+    return ELLP_OK;
+}
+int ellp_b200_h2d(ellp_b200_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
+    if (!ctx) return ELLP_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return ELLP_OK;
+}
+int ellp_b200_d2h(ellp_b200_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
+    if (!ctx) return ELLP_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return ELLP_OK;
+}
+int ellp_b200_sync(ellp_b200_ctx* ctx) {
+    if (!ctx) return ELLP_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaGetLastError());
+    return ELLP_OK;
+}
+int ellp_b200_dev_fill_uniform(ellp_b200_ctx* ctx, double* dptr, uint64_t count, uint64_t seed, uint64_t offset, double lo,
+                               double hi) {
+    if (!ctx) return ELLP_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    LAUNCH(k_fill_uniform, 148 * 8, 256, dptr, count, seed, offset, lo, hi);
+    CUDA_TRY(cudaGetLastError());
+    return ELLP_OK;
+}
+
+__global__ void k_gather_row_plain(const double* __restrict__ E, int64_t ld, int64_t C, int64_t r, const double* __restrict__ alpha,
+                                   double* __restrict__ out) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < C) out[j] = E[j * ld + r] / alpha[r];
+}
+
+int ellp_b200_rank1_update_dev(ellp_b200_ctx* ctx, double* E, int64_t R, int64_t C, int64_t ld, const double* alpha, int64_t r,
+                               int32_t reps, float* ms_avg) {
+    if (!ctx || !E || !alpha || R <= 0 || C <= 0 || ld < R || r < 0 || r >= R || reps < 1) return ELLP_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    double* prow = nullptr;
+    double* apad = nullptr;
+    const int64_t Rp = (int64_t)align_up((size_t)R, 2);
+    CUDA_TRY(cudaMalloc(&prow, sizeof(double) * C));
+    CUDA_TRY(cudaMalloc(&apad, sizeof(double) * Rp));
+    CUDA_TRY(cudaMemsetAsync(apad, 0, sizeof(double) * Rp, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(apad, alpha, sizeof(double) * R, cudaMemcpyDeviceToDevice, ctx->stream));
+    LAUNCH(k_gather_row_plain, (unsigned)((C + 255) / 256), 256, E, ld, C, r, alpha, prow);
+    const bool vec = (ld % 2 == 0) && ((reinterpret_cast<uintptr_t>(E) & 15) == 0);
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int k = 0; k < reps; ++k) {
+        if (vec) {
+            launch_rank1(ctx, E, ld, (int)R, (int)C, apad, prow, nullptr, (int)r);
+        } else {
+            dim3 grid((unsigned)((R + 255) / 256), (unsigned)std::min<int64_t>(C, 1024));
+            LAUNCH(k_rank1_scalar, grid, 256, E, ld, (int)R, (int)C, apad, prow, (int)r);
+        }
+    }
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaGetLastError());
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (ms_avg) *ms_avg = ms / (float)reps;
+    cudaFree(prow);
+    cudaFree(apad);
+    return ELLP_OK;
+}
+
+int ellp_b200_rank1_update(ellp_b200_ctx* ctx, double* E, int64_t R, int64_t C, int64_t ld, const double* alpha, int64_t r) {
+    if (!ctx || !E || !alpha || R <= 0 || C <= 0 || ld < R) return ELLP_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    double* dE = nullptr;
+    double* da = nullptr;
+    CUDA_TRY(cudaMalloc(&dE, sizeof(double) * ld * C));
+    CUDA_TRY(cudaMalloc(&da, sizeof(double) * R));
+    CUDA_TRY(cudaMemcpy(dE, E, sizeof(double) * ld * C, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(da, alpha, sizeof(double) * R, cudaMemcpyHostToDevice));
+    int rc = ellp_b200_rank1_update_dev(ctx, dE, R, C, ld, da, r, 1, nullptr);
+    if (rc == ELLP_OK) CUDA_TRY(cudaMemcpy(E, dE, sizeof(double) * ld * C, cudaMemcpyDeviceToHost));
+    cudaFree(dE);
+    cudaFree(da);
+    return rc;
+}
+
+int ellp_b200_gemv_t(ellp_b200_ctx* ctx, const double* M, int64_t R, int64_t C, int64_t ld, const int32_t* cols, int64_t ncols,
+                     const double* v, double* y) {
+    if (!ctx || !M || !v || !y || R <= 0 || C <= 0 || ld < R || ncols <= 0) return ELLP_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int64_t ldp = (int64_t)align_up((size_t)R, 4);
+    double *dM = nullptr, *dv = nullptr, *dy = nullptr;
+    int32_t* dc = nullptr;
+    CUDA_TRY(cudaMalloc(&dM, sizeof(double) * ldp * C));
+    CUDA_TRY(cudaMalloc(&dv, sizeof(double) * ldp));
+    CUDA_TRY(cudaMalloc(&dy, sizeof(double) * ncols));
+    CUDA_TRY(cudaMemset(dM, 0, sizeof(double) * ldp * C));
+    CUDA_TRY(cudaMemset(dv, 0, sizeof(double) * ldp));
+    CUDA_TRY(cudaMemcpy2D(dM, sizeof(double) * ldp, M, sizeof(double) * ld, sizeof(double) * R, C, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dv, v, sizeof(double) * R, cudaMemcpyHostToDevice));
+    if (cols) {
+        CUDA_TRY(cudaMalloc(&dc, sizeof(int32_t) * ncols));
+        CUDA_TRY(cudaMemcpy(dc, cols, sizeof(int32_t) * ncols, cudaMemcpyHostToDevice));
+    }
+    LAUNCH(k_gemv_t<EPI_PLAIN>, gemv_grid((int)ncols), 256, dM, ldp, dc, (int)ncols, dv, dy, (const double*)nullptr,
+           (const uint8_t*)nullptr, (double*)nullptr, (PivotState*)nullptr, 0);
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(y, dy, sizeof(double) * ncols, cudaMemcpyDeviceToHost));
+    cudaFree(dM); cudaFree(dv); cudaFree(dy);
+    if (dc) cudaFree(dc);
+    return ELLP_OK;
+}
+
+int ellp_b200_gemv_n(ellp_b200_ctx* ctx, const double* M, int64_t R, int64_t C, int64_t ld, const double* v, double* y) {
+    if (!ctx || !M || !v || !y || R <= 0 || C <= 0 || ld < R) return ELLP_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int64_t ldp = (int64_t)align_up((size_t)R, 4);
+    int kc = std::min(kFtranMaxKc, std::max(64, (int)((C + 63) / 64)));
+    const int KS = (int)((C + kc - 1) / kc);
+    double *dM = nullptr, *dv = nullptr, *dy = nullptr, *dp = nullptr;
+    CUDA_TRY(cudaMalloc(&dM, sizeof(double) * ldp * C));
+    CUDA_TRY(cudaMalloc(&dv, sizeof(double) * C));
+    CUDA_TRY(cudaMalloc(&dy, sizeof(double) * R));
+    CUDA_TRY(cudaMalloc(&dp, sizeof(double) * ldp * KS));
+    CUDA_TRY(cudaMemset(dM, 0, sizeof(double) * ldp * C));
+    CUDA_TRY(cudaMemcpy2D(dM, sizeof(double) * ldp, M, sizeof(double) * ld, sizeof(double) * R, C, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dv, v, sizeof(double) * C, cudaMemcpyHostToDevice));
+    dim3 grid((unsigned)((ldp + 255) / 256), (unsigned)KS);
+    LAUNCH(k_gemv_n_partial, grid, 128, dM, ldp, (int)R, (int)C, dv, dp, kc);
+    LAUNCH(k_sum_partials, (unsigned)((R + 255) / 256), 256, dp, ldp, (int)R, KS, dy);
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(y, dy, sizeof(double) * R, cudaMemcpyDeviceToHost));
+    cudaFree(dM); cudaFree(dv); cudaFree(dy); cudaFree(dp);
+    return ELLP_OK;
+}
+
+int ellp_b200_invert(ellp_b200_ctx* ctx, const double* Bmat, int64_t m, double* Binv) {
+    if (!ctx || !Bmat || !Binv || m <= 0) return ELLP_E_ARG;
+    // run the resident-LP refactorisation on an LP whose A is Bmat and whose basis is 0..m-1
+    std::vector<double> zeros((size_t)m, 0.0);
+    std::vector<uint8_t> kind((size_t)m, ELLP_LOWER);
+    std::vector<int32_t> B((size_t)m);
+    for (int64_t i = 0; i < m; ++i) B[i] = (int32_t)i;
+    ellp_std_form sf{(int32_t)m, (int32_t)m, Bmat, zeros.data(), zeros.data(), kind.data(), zeros.data(), zeros.data()};
+    std::vector<double> x((size_t)m, 0.0);
+    ellp_point pt{x.data(), B.data(), nullptr, nullptr, nullptr, nullptr, (int32_t)m, 0};
+    ellp_opts o;
+    ellp_b200_default_opts(&o);
+    if (int rc = ellp_b200_upload(ctx, &sf, &pt, ELLP_PRIMAL, &o)) return rc;
+    std::memset(ctx->h_st, 0, sizeof(PivotState));
+    if (int rc = write_state(ctx)) return rc;
+    if (int rc = refactor(ctx, nullptr)) return rc;
+    const DevLP& lp = ctx->lp;
+    CUDA_TRY(cudaMemcpy2D(Binv, sizeof(double) * m, lp.Binv, sizeof(double) * lp.ld, sizeof(double) * m, m, cudaMemcpyDeviceToHost));
+    return ELLP_OK;
+}
+
+}  // extern "C"

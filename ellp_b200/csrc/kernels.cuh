@@ -1,0 +1,811 @@
+// kernels.cuh -- hand-written sm_100a kernels of the simplex pivot loop (all fp64, device resident).
+//
+// Kernel <-> reference map (paths relative to the reference repo):
+//   k_gemv_t<EPI_PLAIN>         BTRAN  u = A_B^-T c_B      primal_simplex_solver.rs:184-187
+//                               pivot row alpha = A_N^T rho dual_simplex_solver.rs:255
+//   k_gemv_t<EPI_PRIMAL_PRICE>  r = c_N - A_N^T u + keys    primal_simplex_solver.rs:189, :253-270
+//   k_select_primal             Dantzig max_by fold         primal_simplex_solver.rs:271-292
+//   k_ftran_partial             B^-1 a_q (split-K GEMV)     primal :295, dual :294
+//   k_ratio_primal              ratio fold, step, apply     primal :296-434, :205-232
+//   k_dual_leaving              first infeasible basic      dual :200-236
+//   k_select_dual               min-ratio entering          dual :257-289
+//   k_dual_update               d, y, x, obj, swap          dual :296-333
+//   k_gather_row / k_rank1      replace `A_B.clone().lu()`  primal :173, dual :241
+//   k_gj_*                      basis refactorisation (Gauss-Jordan with the LU's pivot rule)
+//
+// Compiled with -fmad=false: products and sums round separately exactly where the reference's
+// Rust does; fused multiply-adds appear only where written as fma().
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include "device_types.cuh"
+
+namespace ellp {
+
+struct DevLP {
+    int32_t m, n, nN;
+    int64_t ld;  // leading dimension of A, Binv, G (m rounded up to a multiple of 4; padding rows are zero)
+    const double* A;
+    const double* c;
+    const double* b;
+    const double* lb;
+    const double* ub;
+    const uint8_t* kind;
+    double* x;
+    int32_t* Bv;
+    int32_t* Nv;
+    uint8_t* Ns;
+    double* y;
+    double* d;
+    double* G;     // ld x 2m Gauss-Jordan workspace [A_B | I]
+    double* Binv;  // = G + m*ld
+    double* cB;    // ld (padding zero)
+    double* u;     // ld
+    double* rN;    // nN: reduced costs (primal) / pivot row alpha (dual)
+    double* key;   // nN
+    double* dcol;  // ld: B^-1 a_q (un-negated)
+    double* rho;   // ld: row r of B^-1
+    double* prow;  // 2m: scaled pivot row consumed by k_rank1
+    double* part;  // KS x ld split-K partial sums
+    double* lam;   // m
+    ellp_trace_rec* trace;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+__device__ __forceinline__ double2 ld_f64x2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ double2 ld_f64x2_stream(const double* p) { return __ldcs(reinterpret_cast<const double2*>(p)); }
+__device__ __forceinline__ void st_f64x2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
+__device__ __forceinline__ void st_f64x2_stream(double* p, double2 v) { __stcs(reinterpret_cast<double2*>(p), v); }
+
+// ------------------------------------------------------------------------------------------------
+// K1/K5 (transpose form): one warp per column, 16-byte coalesced loads, 4 loads in flight per lane,
+// warp-shuffle reduction.  len2 = ld/2 double2 elements per column (padding rows are zero in M and v).
+// ------------------------------------------------------------------------------------------------
+enum { EPI_PLAIN = 0, EPI_PRIMAL_PRICE = 1 };
+
+__device__ __forceinline__ double warp_col_dot(const double* __restrict__ col, const double* __restrict__ v, int len2, int lane) {
+    const double2* c2 = reinterpret_cast<const double2*>(col);
+    const double2* v2 = reinterpret_cast<const double2*>(v);
+    double s0 = 0., s1 = 0., s2 = 0., s3 = 0.;
+    int k = lane;
+    for (; k + 96 < len2; k += 128) {
+        const double2 a0 = __ldcs(c2 + k), a1 = __ldcs(c2 + k + 32), a2 = __ldcs(c2 + k + 64), a3 = __ldcs(c2 + k + 96);
+        const double2 b0 = __ldg(v2 + k), b1 = __ldg(v2 + k + 32), b2 = __ldg(v2 + k + 64), b3 = __ldg(v2 + k + 96);
+        s0 = fma(a0.x, b0.x, s0); s0 = fma(a0.y, b0.y, s0);
+        s1 = fma(a1.x, b1.x, s1); s1 = fma(a1.y, b1.y, s1);
+        s2 = fma(a2.x, b2.x, s2); s2 = fma(a2.y, b2.y, s2);
+        s3 = fma(a3.x, b3.x, s3); s3 = fma(a3.y, b3.y, s3);
+    }
+    for (; k < len2; k += 32) {
+        const double2 a0 = __ldcs(c2 + k);
+        const double2 b0 = __ldg(v2 + k);
+        s0 = fma(a0.x, b0.x, s0); s0 = fma(a0.y, b0.y, s0);
+    }
+    return warp_sum((s0 + s1) + (s2 + s3));
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(256) k_gemv_t(const double* __restrict__ M, int64_t ld, const int32_t* __restrict__ cols,
+                                                int ncols, const double* __restrict__ v, double* __restrict__ out,
+                                                const double* __restrict__ c, const uint8_t* __restrict__ Ns,
+                                                double* __restrict__ key, PivotState* st, int clear_update) {
+    if (st) {
+        if (clear_update && blockIdx.x == 0 && threadIdx.x == 0) st->do_update = 0;
+        if (st->status != kRunning) return;
+    }
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int len2 = (int)(ld >> 1);
+    for (int j = blockIdx.x * warps_per_block + (threadIdx.x >> 5); j < ncols; j += gridDim.x * warps_per_block) {
+        const int col = cols ? cols[j] : j;
+        const double dot = warp_col_dot(M + (int64_t)col * ld, v, len2, lane);
+        if (lane == 0) {
+            if (EPI == EPI_PLAIN) {
+                out[j] = dot;
+            } else {
+                // r_j = c_j - a_j^T u (primal :189) and the Dantzig key (primal :258-269); -1 marks "not a candidate"
+                const double r = c[col] - dot;
+                const int side = Ns[j];
+                double k = -1.0;
+                if (!(fabs(r) < kEps)) {
+                    if (r > 0. && side == ELLP_NB_UPPER) k = r;
+                    else if (!(r > 0.) && side == ELLP_NB_LOWER) k = -r;
+                    else if (side == ELLP_NB_FREE) k = fabs(r);
+                }
+                out[j] = r;
+                key[j] = k;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dantzig selection.  tie_rule 0 reproduces Iterator::max_by over N in position order with the
+// reference's EPS-tolerant comparator (primal :271-286): the accumulator survives only when it
+// compares Greater.  One warp walks the keys 32 at a time; inside a chunk the lanes that would
+// change the accumulator are found with a ballot and applied in order, which is exactly the
+// sequential fold.  tie_rule 1 is the order-free form (max key, then largest variable index
+// within EPS of it).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_select_primal(const double* __restrict__ key, const double* __restrict__ rN,
+                                                      const int32_t* __restrict__ Nv, const uint8_t* __restrict__ Ns,
+                                                      int nN, int tie_rule, PivotState* st) {
+    if (st->status != kRunning) return;
+    const int lane = threadIdx.x;
+    const unsigned full = 0xffffffffu;
+    bool have = false;
+    double bk = 0.;
+    int bv = 0, bp = -1;
+    if (tie_rule == ELLP_TIES_REFERENCE) {
+        constexpr int U = 4;
+        for (int base = 0; base < nN; base += 32 * U) {
+            double k[U];
+            int v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int j = base + u * 32 + lane;
+                k[u] = (j < nN) ? __ldcg(key + j) : -1.0;
+                v[u] = (j < nN) ? __ldcg(Nv + j) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool cand = (k[u] != -1.0);
+                unsigned rem = __ballot_sync(full, cand);
+                while (rem) {
+                    bool eff = false;
+                    if (cand && ((rem >> lane) & 1u)) {
+                        if (!have) eff = true;
+                        else if (fabs(bk - k[u]) >= kEps) eff = (k[u] > bk);
+                        else eff = (v[u] > bv);
+                    }
+                    const unsigned msk = __ballot_sync(full, eff);
+                    if (!msk) break;
+                    const int f = __ffs(msk) - 1;
+                    bk = __shfl_sync(full, k[u], f);
+                    bv = __shfl_sync(full, v[u], f);
+                    bp = base + u * 32 + f;
+                    have = true;
+                    rem &= (f == 31) ? 0u : (full << (f + 1));
+                }
+            }
+        }
+    } else {
+        double kmax = -CUDART_INF;
+        for (int j = lane; j < nN; j += 32) {
+            const double k = __ldcg(key + j);
+            if (k != -1.0 && k > kmax) kmax = k;
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) kmax = fmax(kmax, __shfl_xor_sync(full, kmax, off));
+        int bestv = -1, bestp = -1;
+        for (int j = lane; j < nN; j += 32) {
+            const double k = __ldcg(key + j);
+            if (k != -1.0 && (kmax - k < kEps)) {
+                const int v = __ldcg(Nv + j);
+                if (v > bestv) { bestv = v; bestp = j; }
+            }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const int ov = __shfl_xor_sync(full, bestv, off), op = __shfl_xor_sync(full, bestp, off);
+            if (ov > bestv) { bestv = ov; bestp = op; }
+        }
+        bv = bestv;
+        bp = bestp;
+    }
+    if (lane == 0) {
+        if (bp < 0) {
+            st->status = ELLP_OPTIMAL;  // primal :289-292
+        } else {
+            st->q_pos = bp;
+            st->q_var = bv;
+            st->q_side = Ns[bp];
+            st->rq = rN[bp];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5 FTRAN: alpha = B^-1 a_q with B^-1 column-major: each thread owns two rows (one 16-byte load per
+// column), a CTA owns 256 rows x kc columns; partial sums go to part[ks][row] and are added in a
+// fixed order by the consumer (k_ratio_primal / k_dual_update) => bitwise deterministic.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFtranMaxKc = 512;
+
+__global__ void __launch_bounds__(128) k_ftran_partial(const double* __restrict__ Binv, int64_t ld, int m,
+                                                       const double* __restrict__ A, const PivotState* st,
+                                                       double* __restrict__ part, int kc) {
+    if (st->status != kRunning) return;
+    __shared__ double vs[kFtranMaxKc];
+    const int k0 = blockIdx.y * kc;
+    const int kn = min(kc, m - k0);
+    const double* acol = A + (int64_t)st->q_var * ld;
+    for (int t = threadIdx.x; t < kn; t += blockDim.x) vs[t] = acol[k0 + t];
+    __syncthreads();
+    const int64_t row = (int64_t)blockIdx.x * 256 + 2 * threadIdx.x;
+    if (row >= ld) return;
+    double ax = 0., ay = 0.;
+    const double* p = Binv + row + (int64_t)k0 * ld;
+    int k = 0;
+    for (; k + 4 <= kn; k += 4) {
+        const double2 e0 = ld_f64x2(p + (int64_t)(k + 0) * ld), e1 = ld_f64x2(p + (int64_t)(k + 1) * ld);
+        const double2 e2 = ld_f64x2(p + (int64_t)(k + 2) * ld), e3 = ld_f64x2(p + (int64_t)(k + 3) * ld);
+        ax = fma(e0.x, vs[k + 0], ax); ay = fma(e0.y, vs[k + 0], ay);
+        ax = fma(e1.x, vs[k + 1], ax); ay = fma(e1.y, vs[k + 1], ay);
+        ax = fma(e2.x, vs[k + 2], ax); ay = fma(e2.y, vs[k + 2], ay);
+        ax = fma(e3.x, vs[k + 3], ax); ay = fma(e3.y, vs[k + 3], ay);
+    }
+    for (; k < kn; ++k) {
+        const double2 e0 = ld_f64x2(p + (int64_t)k * ld);
+        ax = fma(e0.x, vs[k], ax); ay = fma(e0.y, vs[k], ay);
+    }
+    st_f64x2(part + (int64_t)blockIdx.y * ld + row, make_double2(ax, ay));
+}
+
+// generic y = M v on host-supplied device data (kernel-level entry point ellp_b200_gemv_n)
+__global__ void __launch_bounds__(128) k_gemv_n_partial(const double* __restrict__ M, int64_t ld, int R, int C,
+                                                        const double* __restrict__ v, double* __restrict__ part, int kc) {
+    __shared__ double vs[kFtranMaxKc];
+    const int k0 = blockIdx.y * kc;
+    const int kn = min(kc, C - k0);
+    for (int t = threadIdx.x; t < kn; t += blockDim.x) vs[t] = v[k0 + t];
+    __syncthreads();
+    const int64_t row = (int64_t)blockIdx.x * 256 + 2 * threadIdx.x;
+    if (row >= ld) return;
+    double ax = 0., ay = 0.;
+    const double* p = M + row + (int64_t)k0 * ld;
+    for (int k = 0; k < kn; ++k) {
+        const double2 e0 = ld_f64x2(p + (int64_t)k * ld);
+        ax = fma(e0.x, vs[k], ax); ay = fma(e0.y, vs[k], ay);
+    }
+    st_f64x2(part + (int64_t)blockIdx.y * ld + row, make_double2(ax, ay));
+}
+
+__global__ void k_sum_partials(const double* __restrict__ part, int64_t ld, int R, int KS, double* __restrict__ y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    double a = 0.;
+    for (int ks = 0; ks < KS; ++ks) a += part[(int64_t)ks * ld + i];
+    y[i] = a;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 primal: bounded ratio test (primal :305-400), step (:402-434) and pivot application (:205-232)
+// in one single-CTA kernel.  tie_rule 0 reproduces the sequential scan with its (lambda, new_basic,
+// new_basic_index) state exactly -- including the stale-index behaviour of :379-399.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double primal_ratio(int kind, double lb, double ub, double x_i, double d_i) {
+    switch (kind) {
+        case ELLP_FREE: return CUDART_INF;
+        case ELLP_LOWER:
+            if (d_i > 0.) return CUDART_INF;
+            return (x_i > lb) ? (lb - x_i) / d_i : 0.;
+        case ELLP_UPPER:
+            if (d_i > 0.) return (x_i < ub) ? (ub - x_i) / d_i : 0.;
+            return CUDART_INF;
+        case ELLP_TWOSIDED:
+            if (d_i > 0.) return (x_i < ub) ? (ub - x_i) / d_i : 0.;
+            return (x_i < lb) ? (lb - x_i) / d_i : 0.;  // primal :359 (sic)
+        default: return 0.;                              // Fixed
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_ratio_primal(DevLP lp, int KS, int tie_rule, PivotState* st) {
+    if (st->status != kRunning) return;
+    __shared__ double s_lambda;
+    __shared__ int s_nb;
+    const int tid = threadIdx.x;
+    const int m = lp.m;
+    const int q_var = st->q_var;
+    const bool at_lower = (st->q_side == ELLP_NB_LOWER);
+    // alpha = sum of split-K partials (fixed order); d = -alpha when entering from its lower bound (:296-300)
+    for (int i = tid; i < m; i += blockDim.x) {
+        double a = 0.;
+        for (int ks = 0; ks < KS; ++ks) a += lp.part[(int64_t)ks * lp.ld + i];
+        lp.dcol[i] = a;
+        const double d_i = at_lower ? -a : a;
+        double lam = -1.0;  // -1 = skipped (|d_i| < EPS, :321)
+        if (!(fabs(d_i) < kEps)) {
+            const int var = lp.Bv[i];
+            lam = primal_ratio(lp.kind[var], lp.lb[var], lp.ub[var], lp.x[var], d_i);
+        }
+        lp.lam[i] = lam;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        const unsigned full = 0xffffffffu;
+        const int lane = tid;
+        double lambda;
+        {
+            const int kq = lp.kind[q_var];  // :305-311
+            lambda = (kq == ELLP_TWOSIDED) ? (lp.ub[q_var] - lp.lb[q_var]) : (kq == ELLP_FIXED ? 0. : CUDART_INF);
+        }
+        int nb = -1;
+        if (tie_rule == ELLP_TIES_REFERENCE) {
+            bool have_nbi = false;
+            int nbi = 0;
+            constexpr int U = 4;
+            for (int base = 0; base < m; base += 32 * U) {
+                double l[U];
+                int v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = base + u * 32 + lane;
+                    l[u] = (i < m) ? lp.lam[i] : -1.0;
+                    v[u] = (i < m) ? lp.Bv[i] : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool cand = (l[u] != -1.0);
+                    unsigned rem = __ballot_sync(full, cand);
+                    while (rem) {
+                        int eff = 0;  // 1 strict (:379), 2 tie accepted (:387-399)
+                        if (cand && ((rem >> lane) & 1u)) {
+                            if (l[u] < lambda - kEps) eff = 1;
+                            else if (fabs(l[u] - lambda) < kEps && (!have_nbi || v[u] < nbi)) eff = 2;
+                        }
+                        const unsigned msk = __ballot_sync(full, eff != 0);
+                        if (!msk) break;
+                        const int f = __ffs(msk) - 1;
+                        const int kind_f = __shfl_sync(full, eff, f);
+                        lambda = __shfl_sync(full, l[u], f);
+                        nb = base + u * 32 + f;
+                        if (kind_f == 2) { have_nbi = true; nbi = __shfl_sync(full, v[u], f); }
+                        rem &= (f == 31) ? 0u : (full << (f + 1));
+                    }
+                }
+            }
+        } else {
+            double lmin = CUDART_INF;
+            for (int i = lane; i < m; i += 32) {
+                const double l = lp.lam[i];
+                if (l != -1.0 && l < lmin) lmin = l;
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) lmin = fmin(lmin, __shfl_xor_sync(full, lmin, off));
+            if (lmin < lambda + kEps && lmin < CUDART_INF) {
+                int bestv = 0x7fffffff, bestp = -1;
+                for (int i = lane; i < m; i += 32) {
+                    const double l = lp.lam[i];
+                    if (l != -1.0 && (l - lmin < kEps)) {
+                        const int v = lp.Bv[i];
+                        if (v < bestv) { bestv = v; bestp = i; }
+                    }
+                }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const int ov = __shfl_xor_sync(full, bestv, off), op = __shfl_xor_sync(full, bestp, off);
+                    if (ov < bestv) { bestv = ov; bestp = op; }
+                }
+                nb = bestp;
+                lambda = lp.lam[nb];
+            }
+        }
+        if (lane == 0) { s_lambda = lambda; s_nb = nb; }
+    }
+    __syncthreads();
+    const double lambda = s_lambda;
+    const int nb = s_nb;
+    if (!(lambda >= 0.)) {  // :402 assert!(lambda >= 0.)
+        if (tid == 0) { st->err = kErrLambdaNegative; st->status = ELLP_UNBOUNDED; st->do_update = 0; }
+        return;
+    }
+    if (isinf(lambda)) {  // :404-406
+        if (tid == 0) { st->status = ELLP_UNBOUNDED; st->do_update = 0; }
+        return;
+    }
+    if (lambda > 0.) {  // :408-417
+        for (int i = tid; i < m; i += blockDim.x) {
+            const double a = lp.dcol[i];
+            const double d_i = at_lower ? -a : a;
+            const int var = lp.Bv[i];
+            lp.x[var] = lp.x[var] + lambda * d_i;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (lambda > 0.) lp.x[q_var] = at_lower ? lp.x[q_var] + lambda : lp.x[q_var] - lambda;
+        const int q_pos = st->q_pos;
+        const int64_t t = st->trace_len;
+        int leave_var = -1;
+        if (nb >= 0) {  // :208-221
+            const double a = lp.dcol[nb];
+            const double d_nb = at_lower ? -a : a;
+            leave_var = lp.Bv[nb];
+            lp.Bv[nb] = q_var;
+            lp.Nv[q_pos] = leave_var;
+            lp.Ns[q_pos] = (d_nb > 0.) ? ELLP_NB_UPPER : ELLP_NB_LOWER;
+            lp.cB[nb] = lp.c[q_var];
+            st->r_pos = nb;
+            st->leave_var = leave_var;
+            st->alpha_r = a;
+            st->do_update = 1;
+        } else {  // :223-231 bound flip
+            const int side = lp.Ns[q_pos];
+            if (side == ELLP_NB_LOWER) lp.Ns[q_pos] = ELLP_NB_UPPER;
+            else if (side == ELLP_NB_UPPER) lp.Ns[q_pos] = ELLP_NB_LOWER;
+            else { st->err = kErrFlipFree; st->status = ELLP_UNBOUNDED; }
+            st->r_pos = -1;
+            st->do_update = 0;
+        }
+        if (lp.trace && t < st->trace_cap) {
+            ellp_trace_rec rec;
+            rec.phase = st->phase_tag;
+            rec.iter = (int32_t)st->pivots;
+            rec.entering = q_var;
+            rec.leaving = leave_var;
+            rec.step = lambda;
+            rec.obj = st->obj;
+            lp.trace[t] = rec;
+        }
+        st->trace_len = t + 1;
+        st->step = lambda;
+        st->obj = st->obj + st->rq * (at_lower ? lambda : -lambda);
+        st->pivots += 1;
+        if (st->status == kRunning && st->pivots >= st->max_iter) st->status = ELLP_MAXITER;  // :163-166 at the next loop head
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pivot row of E: out[j] = E[r, j] (mode 0, dual rho) or E[r, j] / alpha_r (mode 1, feeds k_rank1)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_gather_row(const double* __restrict__ E, int64_t ld, int C, const PivotState* st, double* __restrict__ out,
+                             int mode) {
+    if (mode == 0) { if (st->status != kRunning) return; }
+    else if (!st->do_update) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= C) return;
+    const double e = E[(int64_t)j * ld + st->r_pos];
+    out[j] = (mode == 0) ? e : e / st->alpha_r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: rank-1 row reduction  E[r,j] = p_j ; E[i,j] = fma(-alpha_i, p_j, E[i,j])   (p_j = E_old[r,j]/alpha_r)
+// HBM-bound read-modify-write stream: 16 B of traffic per element, 2 flops.
+//   - a thread owns two consecutive rows (one 16-byte access per column), a CTA 2*blockDim rows;
+//     its -alpha pair lives in registers for the whole CTA lifetime
+//   - kColsInFlight columns are loaded before any is stored => kColsInFlight x 16 B in flight/thread
+//   - STREAM=true uses evict-first loads/stores (tableau much larger than L2); false keeps the
+//     default policy so a basis inverse that fits the 126 MB L2 stays resident between pivots
+// ------------------------------------------------------------------------------------------------
+constexpr int kRank1Threads = 256;
+constexpr int kColsInFlight = 8;
+
+template <bool STREAM>
+__global__ void __launch_bounds__(kRank1Threads) k_rank1(double* __restrict__ E, int64_t ld, int R, int C,
+                                                         const double* __restrict__ alpha, const double* __restrict__ prow,
+                                                         const PivotState* st, int r_fixed, int cols_per_cta) {
+    int r = r_fixed;
+    if (st) {
+        if (!st->do_update) return;
+        r = st->r_pos;
+    }
+    const int64_t row = ((int64_t)blockIdx.x * kRank1Threads + threadIdx.x) * 2;
+    if (row >= R) return;
+    const int c0 = blockIdx.y * cols_per_cta;
+    const int c1 = min(C, c0 + cols_per_cta);
+    double2 na = ld_f64x2(alpha + row);
+    na.x = -na.x;
+    na.y = (row + 1 < R) ? -na.y : 0.;  // a padding row (ld > R) is never modified: fma(0, p, e) == e for finite p
+    const bool r0 = (row == r), r1 = (row + 1 == r);
+    double* base = E + row;
+    int j = c0;
+    for (; j + kColsInFlight <= c1; j += kColsInFlight) {
+        double2 e[kColsInFlight];
+        double p[kColsInFlight];
+#pragma unroll
+        for (int u = 0; u < kColsInFlight; ++u)
+            e[u] = STREAM ? ld_f64x2_stream(base + (int64_t)(j + u) * ld) : ld_f64x2(base + (int64_t)(j + u) * ld);
+#pragma unroll
+        for (int u = 0; u < kColsInFlight; ++u) p[u] = __ldg(prow + j + u);
+#pragma unroll
+        for (int u = 0; u < kColsInFlight; ++u) {
+            e[u].x = r0 ? p[u] : fma(na.x, p[u], e[u].x);
+            e[u].y = r1 ? p[u] : fma(na.y, p[u], e[u].y);
+            if (STREAM) st_f64x2_stream(base + (int64_t)(j + u) * ld, e[u]);
+            else st_f64x2(base + (int64_t)(j + u) * ld, e[u]);
+        }
+    }
+    for (; j < c1; ++j) {
+        double2 e = ld_f64x2(base + (int64_t)j * ld);
+        const double p = __ldg(prow + j);
+        e.x = r0 ? p : fma(na.x, p, e.x);
+        e.y = r1 ? p : fma(na.y, p, e.y);
+        st_f64x2(base + (int64_t)j * ld, e);
+    }
+}
+
+// scalar variant for matrices whose leading dimension is odd (kernel-level entry point only)
+__global__ void k_rank1_scalar(double* __restrict__ E, int64_t ld, int R, int C, const double* __restrict__ alpha,
+                               const double* __restrict__ prow, int r) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    const double na = -alpha[i];
+    for (int j = blockIdx.y; j < C; j += gridDim.y) {
+        const double p = prow[j];
+        double* e = E + (int64_t)j * ld + i;
+        *e = (i == r) ? p : fma(na, p, *e);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dual simplex kernels
+// ------------------------------------------------------------------------------------------------
+// dual :200-236 -- first basis position (in B order) whose variable violates its bound by more than EPS
+__global__ void __launch_bounds__(1024) k_dual_leaving(DevLP lp, PivotState* st) {
+    if (threadIdx.x == 0) st->do_update = 0;
+    if (st->status != kRunning) return;
+    __shared__ int s_min[32];
+    const int tid = threadIdx.x;
+    int best = 0x7fffffff;
+    for (int i = tid; i < lp.m; i += blockDim.x) {
+        const int var = lp.Bv[i];
+        const double x_i = lp.x[var];
+        const int kind = lp.kind[var];
+        bool viol = false;
+        if (kind == ELLP_LOWER) viol = x_i < lp.lb[var] - kEps;
+        else if (kind == ELLP_UPPER) viol = x_i > lp.ub[var] + kEps;
+        else if (kind == ELLP_TWOSIDED) viol = (x_i > lp.ub[var] + kEps) || (x_i < lp.lb[var] - kEps);
+        if (viol) { best = i; break; }  // i increases monotonically per thread
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
+    if ((tid & 31) == 0) s_min[tid >> 5] = best;
+    __syncthreads();
+    if (tid < 32) {
+        best = (tid < (blockDim.x >> 5)) ? s_min[tid] : 0x7fffffff;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
+        if (tid == 0) {
+            if (best == 0x7fffffff) {
+                st->status = ELLP_OPTIMAL;  // :243-246
+            } else {
+                const int var = lp.Bv[best];
+                const double x_i = lp.x[var];
+                const int kind = lp.kind[var];
+                double delta;
+                int side;
+                if (kind == ELLP_LOWER) { delta = x_i - lp.lb[var]; side = ELLP_NB_LOWER; }
+                else if (kind == ELLP_UPPER) { delta = x_i - lp.ub[var]; side = ELLP_NB_UPPER; }
+                else if (x_i > lp.ub[var] + kEps) { delta = x_i - lp.ub[var]; side = ELLP_NB_UPPER; }
+                else { delta = x_i - lp.lb[var]; side = ELLP_NB_LOWER; }
+                st->r_pos = best;
+                st->leave_var = var;
+                st->delta = delta;
+                st->new_side = side;
+            }
+        }
+    }
+}
+
+// dual :257-289 -- entering = first minimum of d_j / alpha~_j over eligible nonbasics (exact compare,
+// first in N-position order on equality) == lexicographic min of (ratio, position): order-free.
+__global__ void __launch_bounds__(1024) k_select_dual(DevLP lp, PivotState* st) {
+    if (st->status != kRunning) return;
+    __shared__ double s_t[32];
+    __shared__ int s_p[32];
+    __shared__ int s_nan;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_nan = 0;
+    __syncthreads();
+    const bool neg = st->delta < 0.;
+    double bt = 0.;
+    int bp = 0x7fffffff;
+    for (int j = tid; j < lp.nN; j += blockDim.x) {
+        double a = lp.rN[j];
+        if (neg) a = -a;
+        const int side = lp.Ns[j];
+        const bool keep = (side == ELLP_NB_LOWER) ? (a > kEps) : (side == ELLP_NB_UPPER ? (a < -kEps) : true);
+        if (keep) {
+            const double t = lp.d[lp.Nv[j]] / a;
+            if (t != t) s_nan = 1;
+            if (bp == 0x7fffffff || t < bt) { bt = t; bp = j; }  // j increases per thread: keeps the first minimum
+        }
+    }
+    const unsigned full = 0xffffffffu;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const double ot = __shfl_xor_sync(full, bt, off);
+        const int op = __shfl_xor_sync(full, bp, off);
+        if (op != 0x7fffffff && (bp == 0x7fffffff || ot < bt || (ot == bt && op < bp))) { bt = ot; bp = op; }
+    }
+    if ((tid & 31) == 0) { s_t[tid >> 5] = bt; s_p[tid >> 5] = bp; }
+    __syncthreads();
+    if (tid < 32) {
+        const int nw = blockDim.x >> 5;
+        bt = (tid < nw) ? s_t[tid] : 0.;
+        bp = (tid < nw) ? s_p[tid] : 0x7fffffff;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const double ot = __shfl_xor_sync(full, bt, off);
+            const int op = __shfl_xor_sync(full, bp, off);
+            if (op != 0x7fffffff && (bp == 0x7fffffff || ot < bt || (ot == bt && op < bp))) { bt = ot; bp = op; }
+        }
+        if (tid == 0) {
+            if (s_nan) { st->err = kErrNaNDualRatio; st->status = ELLP_INFEASIBLE; }
+            else if (bp == 0x7fffffff) st->status = ELLP_INFEASIBLE;  // :281-284 dual unbounded
+            else {
+                st->q_pos = bp;
+                st->q_var = lp.Nv[bp];
+                st->q_side = lp.Ns[bp];
+                st->theta_d = neg ? -bt : bt;  // :286-289
+            }
+        }
+    }
+}
+
+// dual :294-333
+__global__ void __launch_bounds__(1024) k_dual_update(DevLP lp, int KS, PivotState* st) {
+    if (st->status != kRunning) return;
+    const int tid = threadIdx.x;
+    const int m = lp.m;
+    const int r_pos = st->r_pos, q_pos = st->q_pos, q_var = st->q_var, leave_var = st->leave_var;
+    const double theta_d = st->theta_d, delta = st->delta;
+    for (int i = tid; i < m; i += blockDim.x) {  // alpha_q = B^-1 a_q
+        double a = 0.;
+        for (int ks = 0; ks < KS; ++ks) a += lp.part[(int64_t)ks * lp.ld + i];
+        lp.dcol[i] = a;
+    }
+    for (int j = tid; j < lp.nN; j += blockDim.x) {  // :298-300
+        const int var = lp.Nv[j];
+        lp.d[var] = lp.d[var] - theta_d * lp.rN[j];
+    }
+    for (int i = tid; i < m; i += blockDim.x) lp.y[i] = lp.y[i] + theta_d * lp.rho[i];  // :304
+    __syncthreads();
+    const double alpha_r = lp.dcol[r_pos];
+    const double theta_p = delta / alpha_r;  // :306
+    for (int i = tid; i < m; i += blockDim.x) {  // :310-312
+        const int var = lp.Bv[i];
+        lp.x[var] = lp.x[var] - theta_p * lp.dcol[i];
+    }
+    for (int j = tid; j < m; j += blockDim.x) lp.prow[j] = lp.rho[j] / alpha_r;  // scaled pivot row for k_rank1
+    __syncthreads();
+    if (tid == 0) {
+        lp.d[leave_var] = -theta_d;  // :296 (leaving variable is not in N, so the order vs :298 is immaterial)
+        lp.d[q_var] = 0.;            // :302
+        lp.x[q_var] = lp.x[q_var] + theta_p;  // :314
+        const int64_t t = st->trace_len;
+        if (lp.trace && t < st->trace_cap) {
+            ellp_trace_rec rec;
+            rec.phase = st->phase_tag;
+            rec.iter = (int32_t)st->pivots;
+            rec.entering = q_var;
+            rec.leaving = leave_var;
+            rec.step = theta_p;
+            rec.obj = st->obj;
+            lp.trace[t] = rec;
+        }
+        st->trace_len = t + 1;
+        st->obj = st->obj + theta_d * delta;  // :316
+        lp.Bv[r_pos] = q_var;                 // :322-323
+        lp.Nv[q_pos] = leave_var;
+        lp.Ns[q_pos] = (uint8_t)st->new_side;
+        lp.cB[r_pos] = lp.c[q_var];
+        st->alpha_r = alpha_r;
+        st->step = theta_p;
+        st->do_update = 1;
+        st->pivots += 1;
+        if (st->pivots >= st->max_iter) st->status = ELLP_MAXITER;  // :191-194 at the next loop head
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Refactorisation: Gauss-Jordan on G = [A_B | I] with the pivot rule of the reference's LU (first
+// max |a| at or below the diagonal), so the pivots equal the U_kk the reference tests against EPS
+// (primal :175-179).  Each elimination step is one k_rank1 launch on the ld x (2m - k) trailing block.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_gj_init(DevLP lp) {
+    const int j = blockIdx.x;  // column of G
+    const int m = lp.m;
+    for (int64_t i = threadIdx.x; i < lp.ld; i += blockDim.x) {
+        double v;
+        if (j < m) v = (i < m) ? lp.A[(int64_t)lp.Bv[j] * lp.ld + i] : 0.;
+        else v = (i == j - m) ? 1. : 0.;
+        lp.G[(int64_t)j * lp.ld + i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_gj_pivot(DevLP lp, int k, PivotState* st) {
+    if (st->err) return;
+    __shared__ double s_v[32];
+    __shared__ int s_i[32];
+    const int tid = threadIdx.x;
+    const double* col = lp.G + (int64_t)k * lp.ld;
+    double bv = -1.;
+    int bi = 0x7fffffff;
+    for (int i = k + tid; i < lp.m; i += blockDim.x) {
+        const double v = fabs(col[i]);
+        if (v > bv) { bv = v; bi = i; }  // strict: first max per thread
+    }
+    const unsigned full = 0xffffffffu;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const double ov = __shfl_xor_sync(full, bv, off);
+        const int oi = __shfl_xor_sync(full, bi, off);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((tid & 31) == 0) { s_v[tid >> 5] = bv; s_i[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid < 32) {
+        const int nw = blockDim.x >> 5;
+        bv = (tid < nw) ? s_v[tid] : -1.;
+        bi = (tid < nw) ? s_i[tid] : 0x7fffffff;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const double ov = __shfl_xor_sync(full, bv, off);
+            const int oi = __shfl_xor_sync(full, bi, off);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (tid == 0) {
+            s_i[0] = bi;
+            st->gj_piv = bi;
+            st->r_pos = k;
+            st->alpha_r = col[bi];
+            st->do_update = 1;
+            if (!(bv >= kEps)) { st->err = kErrSingular; st->do_update = 0; }  // |U_kk| < EPS
+        }
+    }
+    __syncthreads();
+    const int p = s_i[0];
+    if (st->err) return;
+    // pivot column after the row swap k <-> p (padding rows stay zero)
+    for (int64_t i = tid; i < lp.ld; i += blockDim.x) {
+        const int64_t src = (i == k) ? p : ((i == p) ? k : i);
+        lp.dcol[i] = (i < lp.m) ? col[src] : 0.;
+    }
+}
+
+__global__ void k_gj_swap_gather(DevLP lp, int k, const PivotState* st) {
+    if (st->err) return;
+    const int j = k + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= 2 * lp.m) return;
+    const int p = st->gj_piv;
+    double* col = lp.G + (int64_t)j * lp.ld;
+    const double a = col[k], b = col[p];
+    if (p != k) { col[k] = b; col[p] = a; }
+    lp.prow[j - k] = b / st->alpha_r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__global__ void k_init_cB(DevLP lp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < lp.ld) lp.cB[i] = (i < lp.m) ? lp.c[lp.Bv[i]] : 0.;
+}
+
+__global__ void __launch_bounds__(1024) k_obj_dot(const double* __restrict__ c, const double* __restrict__ x, int n, PivotState* st) {
+    __shared__ double s[32];
+    double a = 0.;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a = fma(c[i], x[i], a);
+    a = warp_sum(a);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        a = (threadIdx.x < (blockDim.x >> 5)) ? s[threadIdx.x] : 0.;
+        a = warp_sum(a);
+        if (threadIdx.x == 0) st->obj = a;
+    }
+}
+
+// counter-based U(lo,hi): splitmix64(seed + golden*(offset+i)) -> 53-bit mantissa
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+__global__ void k_fill_uniform(double* __restrict__ out, uint64_t count, uint64_t seed, uint64_t offset, double lo, double hi) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t h = splitmix64(seed * 0x2545f4914f6cdd1dull + offset + i);
+        const double u = (double)(h >> 11) * (1.0 / 9007199254740992.0);
+        out[i] = lo + (hi - lo) * u;
+    }
+}
+
+}  // namespace ellp

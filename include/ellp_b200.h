@@ -1,0 +1,217 @@
+/*
+ * ellp_b200.h -- C ABI of the B200-native simplex pivoting engine.
+ *
+ * Drop-in boundary for the hot path of kehlert/ellp (paths relative to the reference repo):
+ *   PrimalSimplexSolver::solve_with_initial   src/solvers/primal/primal_simplex_solver.rs:95-236 (+ pivot :238-435)
+ *   DualSimplexSolver::solve_with_initial     src/solvers/dual/dual_simplex_solver.rs:110-335
+ * plus the two-phase drivers around them (primal :32-93, dual :33-108) and kernel-level entry
+ * points used by the parity tests and the roofline bench.
+ *
+ * Conventions
+ *  - plain C, plain pointers and sizes; every pointer is caller-owned and only borrowed for the
+ *    duration of the call; matrices are column-major with lda = m exactly like
+ *    nalgebra::DMatrix<f64>::as_slice() (standard_form.rs:27-34), so a Rust caller passes its
+ *    buffers without copying.
+ *  - one opaque ctx per (host thread, CUDA device); a ctx is not thread-safe, different ctxs are
+ *    independent.
+ *  - no aborts: every panic!/assert!/Err(EllPError) of the reference becomes a negative return
+ *    code and a message retrievable with ellp_b200_last_error(); the messages of the reference's
+ *    Err values are preserved verbatim (primal :125-129,:135-139,:176-178; dual :154-158,:164-168).
+ *  - there is NO CPU fallback: without a CUDA device ellp_b200_create() fails with ELLP_E_CUDA.
+ */
+#ifndef ELLP_B200_H
+#define ELLP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- encodings (values cross the ABI) ------------------------------------------------------ */
+/* Bound                     src/problem.rs:190-197 */
+enum { ELLP_FREE = 0, ELLP_LOWER = 1, ELLP_UPPER = 2, ELLP_TWOSIDED = 3, ELLP_FIXED = 4 };
+/* NonbasicBound             src/standard_form.rs:205-210 */
+enum { ELLP_NB_LOWER = 0, ELLP_NB_UPPER = 1, ELLP_NB_FREE = 2 };
+/* ConstraintOp              src/problem.rs:298-303 */
+enum { ELLP_LTE = 0, ELLP_EQ = 1, ELLP_GTE = 2 };
+/* SolutionStatus / SolverResult   src/solver.rs:6-12,27-33 */
+enum { ELLP_OPTIMAL = 0, ELLP_INFEASIBLE = 1, ELLP_UNBOUNDED = 2, ELLP_MAXITER = 3 };
+/* return codes */
+enum {
+    ELLP_OK = 0,
+    ELLP_E_ELLP = -1,    /* the reference would return Err(EllPError(msg)) */
+    ELLP_E_PANIC = -2,   /* the reference would panic!/assert! (message preserved) */
+    ELLP_E_CUDA = -3,    /* CUDA runtime / no device / out of memory */
+    ELLP_E_ARG = -4      /* malformed arguments */
+};
+enum { ELLP_PRIMAL = 0, ELLP_DUAL = 1 };
+/* tie rules: 0 reproduces the reference's sequential folds (primal :271-286, :379-399) exactly,
+ * 1 is the order-free form of SURVEY appendix A.1/A.2 (needed when columns are sharded). */
+enum { ELLP_TIES_REFERENCE = 0, ELLP_TIES_CANONICAL = 1 };
+/* engines: explicit basis inverse (revised simplex) or full tableau (column-shardable) */
+enum { ELLP_ENGINE_AUTO = 0, ELLP_ENGINE_REVISED = 1, ELLP_ENGINE_TABLEAU = 2 };
+
+typedef struct ellp_b200_ctx ellp_b200_ctx;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int  ellp_b200_create(int device, ellp_b200_ctx** out);
+void ellp_b200_destroy(ellp_b200_ctx* ctx);
+const char* ellp_b200_last_error(const ellp_b200_ctx* ctx);
+const char* ellp_b200_version(void);
+/* number of kernels this library launched on ctx since creation / since the last reset */
+uint64_t ellp_b200_launch_count(const ellp_b200_ctx* ctx);
+void     ellp_b200_reset_launch_count(ellp_b200_ctx* ctx);
+
+/* ---- the hot-path boundary: solve_with_initial ---------------------------------------------- */
+/* StandardForm{c, A, b, bounds}   src/standard_form.rs:27-34 */
+typedef struct {
+    int32_t m, n;          /* rows(), cols() */
+    const double* A;       /* m x n, column-major, lda = m */
+    const double* c;       /* n */
+    const double* b;       /* m */
+    const uint8_t* kind;   /* n, ELLP_FREE.. */
+    const double* lb;      /* n: Lower/TwoSided lower bound, Fixed value */
+    const double* ub;      /* n: Upper/TwoSided upper bound */
+} ellp_std_form;
+
+/* Point{x, N, B} (+ y, d of DualFeasiblePoint)   src/standard_form.rs:20-25, dual_problem.rs:11-16 */
+typedef struct {
+    double*  x;        /* n, in/out */
+    int32_t* B;        /* nB, in/out: variable index per basis position */
+    int32_t* N;        /* nN, in/out: variable index per nonbasic position */
+    uint8_t* N_side;   /* nN, in/out: ELLP_NB_* */
+    double*  y;        /* m, in/out, dual only (may be NULL for primal) */
+    double*  d;        /* n, in/out, dual only (may be NULL for primal) */
+    int32_t  nB, nN;   /* lengths supplied (checked like primal :124-140 / dual :153-169) */
+} ellp_point;
+
+typedef struct {
+    int32_t phase, iter;       /* phase: 0 primal ph1, 1 primal ph2, 2 dual ph1, 3 dual ph2 */
+    int32_t entering, leaving; /* variable indices; leaving = -1 for a bound flip */
+    double  step;              /* primal lambda / dual theta_primal */
+    double  obj;               /* running objective before the pivot */
+} ellp_trace_rec;
+
+typedef struct {
+    uint64_t max_iter;        /* solver.max_iter: Default = 1000, new(None) = UINT64_MAX */
+    int32_t  tie_rule;        /* ELLP_TIES_* */
+    int32_t  engine;          /* ELLP_ENGINE_* */
+    int32_t  refactor_every;  /* rebuild the basis inverse every k pivots (0 = library default) */
+    int32_t  check_every;     /* host reads the 16-byte status every k iterations (0 = default) */
+    int32_t  phase_tag;       /* value stored in trace records */
+    int32_t  profile;         /* 1: record CUDA events around every rank-1 update launch */
+    ellp_trace_rec* trace;    /* optional caller buffer */
+    int64_t  trace_cap;
+} ellp_opts;
+
+typedef struct {
+    int32_t  status;          /* ELLP_OPTIMAL.. */
+    uint64_t iters;           /* pivots performed (basis changes + bound flips) */
+    double   obj;             /* primal: c.x ; dual: dual_obj(y, d) */
+    int64_t  trace_len;
+    uint64_t launches;        /* kernels launched by this call */
+    double   ms_device;       /* device time of the iteration loop (CUDA events on the ctx stream) */
+    double   ms_rank1;        /* with profile=1: summed device time of the rank-1 update launches */
+    uint64_t n_rank1;         /* with profile=1: number of rank-1 update launches timed */
+    uint64_t refactors;
+} ellp_result;
+
+void ellp_b200_default_opts(ellp_opts* o);
+
+/* Replaces PrimalSimplexSolver::solve_with_initial (primal_simplex_solver.rs:95-236):
+ * uploads (std_form, point), pivots on the device until Optimal / Unbounded / MaxIter, writes the
+ * final x, B, N back.  pt->y/pt->d are ignored. */
+int ellp_b200_primal_solve_with_initial(ellp_b200_ctx*, const ellp_std_form*, ellp_point*, const ellp_opts*, ellp_result*);
+/* Replaces DualSimplexSolver::solve_with_initial (dual_simplex_solver.rs:110-335). */
+int ellp_b200_dual_solve_with_initial(ellp_b200_ctx*, const ellp_std_form*, ellp_point*, const ellp_opts*, ellp_result*);
+
+/* The same call split in three so a caller can keep the LP resident in HBM between calls
+ * (bench.py times `run` for the device-resident number and the one-shot call for e2e). */
+int ellp_b200_upload(ellp_b200_ctx*, const ellp_std_form*, const ellp_point*, int solver /*ELLP_PRIMAL|ELLP_DUAL*/, const ellp_opts*);
+int ellp_b200_run(ellp_b200_ctx*, const ellp_opts*, ellp_result*);      /* continues from the resident point */
+int ellp_b200_download(ellp_b200_ctx*, ellp_point*);
+
+/* ---- two-phase drivers: {Primal,Dual}SimplexSolver::solve ------------------------------------ */
+/* A Problem as built by Problem::add_var / add_constraint (src/problem.rs:19-106); constraints in
+ * CSR over variable ids. */
+typedef struct {
+    int32_t nvars, ncons;
+    const double*  obj;      /* nvars */
+    const uint8_t* kind;     /* nvars */
+    const double*  lb;       /* nvars */
+    const double*  ub;       /* nvars */
+    const int64_t* var_id;   /* nvars, or NULL => id = position */
+    const int32_t* row_ptr;  /* ncons + 1 */
+    const int64_t* col_id;   /* nnz: variable ids */
+    const double*  coef;     /* nnz */
+    const uint8_t* op;       /* ncons: ELLP_LTE.. */
+    const double*  rhs;      /* ncons */
+} ellp_problem_desc;
+
+typedef struct {
+    int32_t  status;          /* SolverResult: ELLP_OPTIMAL.. */
+    double   obj;             /* Solution::obj() (solver.rs:47-49) or MaxIter{obj} */
+    double*  x;               /* caller buffer, nvars: Solution::x() (solver.rs:51-53) */
+    uint64_t iters[4];        /* pivots per phase, index = trace phase id */
+    int32_t  used_primal_fallback;   /* dual_simplex_solver.rs:50-67 */
+    int64_t  trace_len;
+    uint64_t launches;
+    double   ms_device;
+} ellp_solution;
+
+/* PrimalSimplexSolver::solve (primal :32-93) / DualSimplexSolver::solve (dual :33-108): standard
+ * form + phase construction on the host (standard_form.rs:78-191, primal_problem.rs:80-291,
+ * dual_problem.rs:89-404), both phases pivoted on the device. */
+int ellp_b200_solve(ellp_b200_ctx*, const ellp_problem_desc*, int solver, const ellp_opts*, ellp_solution*);
+
+/* parse_mps (src/parse_mps.rs:23-66) with deterministic FILE order; returns a handle whose
+ * description can be passed to ellp_b200_solve. */
+typedef struct ellp_b200_model ellp_b200_model;
+int  ellp_b200_parse_mps(const char* text, ellp_b200_model** out, char* err256);
+void ellp_b200_model_free(ellp_b200_model*);
+void ellp_b200_model_desc(const ellp_b200_model*, ellp_problem_desc* out);
+
+/* Host-side stages, exposed for stage-by-stage comparison with the oracle.
+ * which: 0 = Option<StandardForm>::from(Problem), 1 = PrimalPhase1, 2 = DualPhase1. */
+typedef struct ellp_b200_stage ellp_b200_stage;
+int  ellp_b200_stage_new(const ellp_problem_desc*, int which, ellp_b200_stage** out, int* infeasible, char* err256);
+void ellp_b200_stage_free(ellp_b200_stage*);
+void ellp_b200_stage_dims(const ellp_b200_stage*, int32_t* m, int32_t* n, int32_t* nx, int32_t* nB, int32_t* nN,
+                          int32_t* len_c, int32_t* len_bounds);
+void ellp_b200_stage_copy(const ellp_b200_stage*, double* A, double* c, double* b, uint8_t* kind, double* lb,
+                          double* ub, double* x, int32_t* B, int32_t* N, uint8_t* N_side, double* y, double* d);
+
+/* ---- kernel-level entry points (unit parity + roofline) -------------------------------------- */
+/* device buffers owned by the ctx */
+int ellp_b200_dev_alloc(ellp_b200_ctx*, uint64_t bytes, void** dptr);
+int ellp_b200_dev_free(ellp_b200_ctx*, void* dptr);
+int ellp_b200_h2d(ellp_b200_ctx*, void* dst, const void* src, uint64_t bytes);
+int ellp_b200_d2h(ellp_b200_ctx*, void* dst, const void* src, uint64_t bytes);
+int ellp_b200_sync(ellp_b200_ctx*);
+/* fills a device array with U(lo,hi) doubles from a counter-based generator (splitmix64 of
+ * seed + element index): lets the large synthetic LPs be built in HBM without crossing PCIe */
+int ellp_b200_dev_fill_uniform(ellp_b200_ctx*, double* dptr, uint64_t count, uint64_t seed, uint64_t offset, double lo, double hi);
+
+/* K3: rank-1 row reduction of E (R x C, column-major, ld >= R, DEVICE pointers):
+ *   p_j = E[r,j] / alpha[r];  E[r,j] = p_j;  E[i,j] = fma(-alpha[i], p_j, E[i,j])  (i != r)
+ * replaces the per-iteration `A_B.clone().lu()` of the reference (primal :173, dual :241).
+ * reps launches are timed with CUDA events on the ctx stream; *ms_avg receives the mean. */
+int ellp_b200_rank1_update_dev(ellp_b200_ctx*, double* E, int64_t R, int64_t C, int64_t ld, const double* alpha,
+                               int64_t r, int32_t reps, float* ms_avg);
+/* same on host buffers (copies in, one update, copies out) */
+int ellp_b200_rank1_update(ellp_b200_ctx*, double* E, int64_t R, int64_t C, int64_t ld, const double* alpha, int64_t r);
+
+/* K1/K5: y[j] = dot(M[:, cols[j]], v) for j < ncols (cols == NULL => identity); host buffers */
+int ellp_b200_gemv_t(ellp_b200_ctx*, const double* M, int64_t R, int64_t C, int64_t ld, const int32_t* cols,
+                     int64_t ncols, const double* v, double* y);
+/* K5: y = M v (FTRAN form, M column-major R x C); host buffers */
+int ellp_b200_gemv_n(ellp_b200_ctx*, const double* M, int64_t R, int64_t C, int64_t ld, const double* v, double* y);
+/* K4: explicit inverse of a dense m x m matrix (column-major, host buffers); returns ELLP_E_ELLP
+ * "invalid B, A_B is not invertible" when a pivot is below EPS (primal :175-179). */
+int ellp_b200_invert(ellp_b200_ctx*, const double* Bmat, int64_t m, double* Binv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ELLP_B200_H */

@@ -1,0 +1,180 @@
+"""CPU-side checks of the product library: it loads, exports every symbol the header declares, refuses
+to run without a GPU (no CPU fallback), and its host layer (standard form, phase builders, MPS reader)
+agrees with the oracle stage by stage.  No kernel is launched here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import problems as P
+from ellp_b200 import _native as N
+from ellp_b200.problem import Bound, ConstraintOp, EllPError, Problem
+from ellp_b200.solver import parse_mps
+from oracle import binding as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_cuda():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "ellp_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(ellp_b200_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 30
+    lib = C.CDLL(N.LIB_PATH)
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, f"declared in include/ellp_b200.h but not exported: {missing}"
+    assert N.lib.ellp_b200_version().decode().startswith("ellp_b200")
+
+
+def test_no_cpu_fallback_without_a_device():
+    if _has_cuda():
+        pytest.skip("a CUDA device is present")
+    h = C.c_void_p()
+    assert N.lib.ellp_b200_create(0, C.byref(h)) == N.E_CUDA
+    with pytest.raises(N.NativeError):
+        N.Context(0)
+
+
+def _stage(problem, which):
+    arr = problem.to_arrays()
+    desc, _keep = N.problem_desc(arr)
+    h = C.c_void_p()
+    infeasible = C.c_int(0)
+    err = C.create_string_buffer(256)
+    rc = N.lib.ellp_b200_stage_new(C.byref(desc), which, C.byref(h), C.byref(infeasible), err)
+    assert rc == N.OK, err.value
+    if infeasible.value:
+        return None
+    try:
+        dims = [C.c_int32() for _ in range(7)]
+        N.lib.ellp_b200_stage_dims(h, *[C.byref(v) for v in dims])
+        m, n, nx, nB, nN, lc, lb_ = [v.value for v in dims]
+        A = np.zeros((m, n), order="F"); c = np.zeros(max(lc, 1)); b = np.zeros(max(m, 1))
+        kind = np.zeros(max(lb_, 1), dtype=np.uint8); lb = np.zeros(max(lb_, 1)); ub = np.zeros(max(lb_, 1))
+        x = np.zeros(max(nx, 1)); B = np.zeros(max(nB, 1), dtype=np.int32); Nn = np.zeros(max(nN, 1), dtype=np.int32)
+        Ns = np.zeros(max(nN, 1), dtype=np.uint8); y = np.zeros(max(m, 1)); d = np.zeros(max(n, 1))
+        N.lib.ellp_b200_stage_copy(h, N.ptr(A), N.ptr(c), N.ptr(b), N.ptr(kind), N.ptr(lb), N.ptr(ub), N.ptr(x), N.ptr(B),
+                                   N.ptr(Nn), N.ptr(Ns), N.ptr(y) if which == 2 else None, N.ptr(d) if which == 2 else None)
+        return dict(m=m, n=n, A=A, c=c[:lc], b=b[:m], kind=kind[:lb_], lb=lb[:lb_], ub=ub[:lb_], x=x[:nx], B=B[:nB],
+                    N=Nn[:nN], N_side=Ns[:nN], y=y[:m], d=d[:n])
+    finally:
+        N.lib.ellp_b200_stage_free(h)
+
+
+ALL = [(f.__name__, f) for f in P.GOLDEN] + [(n, (lambda n=n: P.netlib(n))) for n in P.NETLIB]
+
+
+@pytest.mark.parametrize("which", [0, 1, 2], ids=["standard_form", "primal_phase1", "dual_phase1"])
+@pytest.mark.parametrize("name,make", ALL, ids=[a for a, _ in ALL])
+def test_host_stages_match_oracle(name, make, which):
+    prob, _ = make()
+    try:
+        ref = O.stage(prob, which)
+    except O.OracleError:
+        pytest.skip("reference panics while building this stage")
+    got = _stage(prob, which)
+    if ref is None:
+        assert got is None
+        return
+    assert got is not None
+    assert (got["m"], got["n"]) == (ref.m, ref.n)
+    np.testing.assert_array_equal(got["A"], ref.A)      # same arithmetic, same order => bit-exact
+    np.testing.assert_array_equal(got["c"], ref.c)
+    np.testing.assert_array_equal(got["b"], ref.b)
+    np.testing.assert_array_equal(got["kind"], ref.kind)
+    # lb/ub are only meaningful for the kinds that carry them
+    for j, k in enumerate(ref.kind):
+        if k in (1, 3, 4):
+            assert got["lb"][j] == ref.lb[j]
+        if k in (2, 3):
+            assert got["ub"][j] == ref.ub[j]
+    if which:
+        np.testing.assert_array_equal(got["B"], ref.B)
+        np.testing.assert_array_equal(got["N"], ref.N)
+        np.testing.assert_array_equal(got["N_side"], ref.N_side)
+        np.testing.assert_allclose(got["x"], ref.x, rtol=0, atol=0)
+    if which == 2 and ref.m:
+        np.testing.assert_array_equal(got["y"], ref.y)
+        np.testing.assert_array_equal(got["d"], ref.d)
+
+
+@pytest.mark.parametrize("name", P.NETLIB)
+def test_mps_reader_round_trips_netlib_fixtures(name):
+    text = P.netlib_mps_text(name)
+    got = parse_mps(text)
+    want, _ = P.netlib(name)
+    a, b = got.to_arrays(), want.to_arrays()
+    for k in ("nvars", "ncons"):
+        assert a[k] == b[k]
+    for k in ("obj", "kind", "lb", "ub", "row_ptr", "col_id", "coef", "op", "rhs"):
+        np.testing.assert_array_equal(a[k], b[k])
+
+
+def test_mps_reader_small_example_and_errors():
+    # same shape as the reference's unit test (src/parse_mps.rs:565-643): 3 variables, 3 rows, bounds
+    text = """NAME TEST
+ROWS
+ N COST
+ L LIM1
+ G LIM2
+ E MYEQN
+COLUMNS
+ X COST 1.0
+ X LIM1 1.0
+ X LIM2 1.0
+ Y COST 2.0
+ Y LIM1 1.0
+ Y MYEQN -1.0
+ Z COST -1.0
+ Z MYEQN 1.0
+RHS
+ RHS LIM1 4.0
+ RHS LIM2 1.0
+ MYEQN 7.0
+BOUNDS
+ UP BND X 4.0
+ LO BND Y -1.0
+ UP BND Y 1.0
+ FR BND Z
+ENDATA
+"""
+    p = parse_mps(text)
+    assert [v.obj_coeff for v in p.variables] == [1.0, 2.0, -1.0]
+    assert p.variables[0].bound == Bound.Upper(4.0)
+    assert p.variables[1].bound == Bound.TwoSided(-1.0, 1.0)
+    assert p.variables[2].bound == Bound.Free()
+    assert [(int(c.op), c.rhs) for c in p.constraints] == [(0, 4.0), (2, 1.0), (1, 7.0)]
+    assert [(int(v), a) for v, a in p.constraints[2].coeffs] == [(1, -1.0), (2, 1.0)]
+    with pytest.raises(EllPError, match="expected 'ROWS'"):
+        parse_mps("NAME T\nROWZ\n")
+    with pytest.raises(EllPError, match="could not find the row"):
+        parse_mps("NAME T\nROWS\n N C\nCOLUMNS\n X NOPE 1.0\nRHS\nENDATA\n")
+    with pytest.raises(EllPError, match="should not specify rhs value for the objective"):
+        parse_mps("NAME T\nROWS\n N C\n L R\nCOLUMNS\n X R 1.0\nRHS\n B C 1.0\nENDATA\n")
+
+
+def test_problem_builder_matches_reference_unit_tests():
+    # src/problem.rs:372-429
+    p = Problem.new()
+    x = p.add_var(1.0, Bound.TwoSided(0.0, 1.0), "x")
+    assert p.variables[0].name == "x" and p.variables[0].bound == Bound.TwoSided(0.0, 1.0)
+    with pytest.raises(EllPError):
+        p.add_var(1.0, Bound.TwoSided(1.0, 0.0), "bad")
+    with pytest.raises(EllPError):
+        p.add_var(1.0, Bound.Lower(float("inf")), "inf")
+    with pytest.raises(EllPError):
+        p.add_var(1.0, Bound.Free(), "x")  # duplicate name
+    with pytest.raises(EllPError):
+        from ellp_b200.problem import VariableId
+        p.add_constraint([(VariableId(99), 1.0)], ConstraintOp.Eq, 0.0)
+    p.add_constraint([(x, 2.0)], ConstraintOp.Lte, 1.0)
+    assert p.is_feasible([0.5]) and not p.is_feasible([0.75]) and not p.is_feasible([0.1, 0.2])
