@@ -64,7 +64,7 @@ struct ellp_b200_ctx {
     std::vector<cudaEvent_t> ev;  // profile=1: pairs around rank-1 launches
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // tuning (ellp_b200_set_tuning)
-    int rank1_cols_per_cta = 64;
+    int rank1_cols_per_cta = 8;
     int rank1_stream_min_mb = 96;  // evict-first policy when the updated matrix is larger than this
 };
 
