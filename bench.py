@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py -- simplex pivots/s of the B200 pivot loop on the dense LP of BASELINE.json configs[4].
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--pivots P]
+
+A "step" = one pass of the hot path over one batch of synthetic input = P simplex pivots of the same dense LP
+(`min -c.x, Ax <= b, x >= 0`, A ~ U(0,1); standard form m x (n_struct + m), slack starting basis; built in HBM by a
+counter-based generator).  `value` times steps with the tableau resident in HBM (each step continues pivoting where
+the previous one stopped); `e2e` times the reference-facing C-ABI call ellp_b200_primal_solve_with_initial on HOST
+buffers (H2D of the whole standard form + P pivots + D2H of the point, every step).  N > 1: the tableau is
+column-sharded, one rank per GPU (torchrun), see ellp_b200/sharded.py.
+
+`--impl reference` times the reference's own CPU algorithm (the oracle port of ellp's PrimalSimplexSolver::
+solve_with_initial: a fresh dense LU per pivot, single thread like the reference) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[4]: "synthetic dense LP 32768x65536 fp64, tableau column-sharded ... at 1/2/4/8 B200"
+    "dense_tableau_32768x65536": dict(m=32768, ns=32768, pivots=20, sample_m=1024, sample_pivots=3),
+    # north_star target size: "for a 16384x32768 dense LP, the row-reduction kernel sustains >= 70% of HBM bandwidth"
+    "dense_tableau_16384x32768": dict(m=16384, ns=16384, pivots=40, sample_m=1024, sample_pivots=3),
+    "dense_tableau_4096x12288": dict(m=4096, ns=8192, pivots=200, sample_m=512, sample_pivots=6),
+    "dense_tableau_tiny": dict(m=256, ns=256, pivots=20, sample_m=128, sample_pivots=4),
+}
+DEFAULT_WORKLOAD = "dense_tableau_32768x65536"
+SEED = 0
+METRIC = "simplex pivots/sec (fp64)"
+UNIT = "pivots/s"
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs
+def cpu_reference_sample(wl: dict, pivots: int):
+    """ellp's own algorithm (oracle port) on the same generator at size sample_m x 2*sample_m, `pivots` pivots."""
+    import bench_lp
+    from oracle import binding as O
+    ms = wl["sample_m"]
+    ratio = wl["ns"] / wl["m"]
+    lp = bench_lp.dense_lp(ms, int(ms * ratio), SEED)
+    O.lib()
+    t0 = time.perf_counter()
+    r = O.solve_with_initial(O.PRIMAL, lp["m"], lp["n"], lp["A"], lp["c"], lp["b"], lp["kind"], lp["lb"], lp["ub"], lp["x"],
+                             lp["B"], lp["N"], lp["N_side"], max_iter=pivots)
+    dt = time.perf_counter() - t0
+    assert r.status == O.MAXITER, r.status_name
+    return pivots / dt, dt, f"{pivots} pivots of the same generator at {lp['m']}x{lp['n']} (a full-size pivot needs a " \
+                            f"{wl['m']}^3 dense LU: ~{(wl['m'] / ms) ** 3 * dt / pivots:.0f} s extrapolated)"
+
+
+def run_reference(args, wl, name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    P = wl["sample_pivots"]
+    for _ in range(args.warmup):
+        cpu_reference_sample(wl, P)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, _, sample = cpu_reference_sample(wl, P)
+    dt = time.perf_counter() - t0
+    value = args.steps * P / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "m": wl["m"], "n": wl["m"] + wl["ns"]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args, wl, name):
+    import torch
+    from ellp_b200 import _native as N
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from ellp_b200 import sharded
+        return sharded.bench_main(args, wl, name, METRIC, UNIT, SEED, ClockSampler, measured_peak, cpu_reference_sample)
+
+    torch.cuda.set_device(local_rank)
+    ctx = N.Context(local_rank)
+    m, ns, P = wl["m"], wl["ns"], (args.pivots or wl["pivots"])
+    n = m + ns
+    o = N.default_opts(P, engine=N.ENGINE_TABLEAU, check_every=min(P, 16), profile=True)
+    ctx.check(N.lib.ellp_b200_generate_dense(ctx.h, m, ns, SEED, C.byref(o)))
+
+    def step():
+        res = N.Result()
+        ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(o), C.byref(res)))
+        assert res.status == N.MAXITER and res.iters == P, (res.status, res.iters)
+        return res
+
+    for _ in range(args.warmup):
+        step()
+    ctx.check(N.lib.ellp_b200_sync(ctx.h))
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = ctx.launch_count()
+    t0 = time.perf_counter()
+    dev_ms = rank1_ms = 0.0
+    n_rank1 = 0
+    for _ in range(args.steps):
+        r = step()
+        dev_ms += r.ms_device; rank1_ms += r.ms_rank1; n_rank1 += r.n_rank1
+    ctx.check(N.lib.ellp_b200_sync(ctx.h))
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    launches = ctx.launch_count() - launches0
+    clk = clocks.stop()
+    value = args.steps * P / dt
+
+    # roofline of the dominant kernel (K3 rank-1 update of the m x n tableau): algorithmic bytes per launch
+    peak, peak_src = measured_peak()
+    alg_bytes = 16.0 * m * n + 8.0 * (m + n)
+    k3_ms = rank1_ms / max(n_rank1, 1)
+    achieved = alg_bytes / (k3_ms * 1e-3) / 1e9 if n_rank1 else None
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "k3_ncu_traffic.json")) as f:
+            traffic = json.load(f).get(name)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_rank1<true> (rank-1 tableau row reduction)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "frac_of_8TBs_nominal": (achieved / 8000.0) if achieved else None,
+                "traffic": traffic, "peak_source": peak_src, "ms_per_launch": k3_ms, "launches_timed": n_rank1,
+                "algorithmic_bytes_per_launch": alg_bytes, "share_of_step_device_time": (rank1_ms / dev_ms) if dev_ms else None}
+
+    # ---- e2e: the C-ABI boundary on HOST buffers (H2D + pivots + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        A_h = torch.empty(m * n, dtype=torch.float64, pin_memory=True)
+        small = torch.empty(5 * n + m, dtype=torch.float64, pin_memory=True).numpy()
+        c_h, b_h, lb_h, ub_h, x0 = small[:n], small[n:n + m], small[n + m:2 * n + m], small[2 * n + m:3 * n + m], small[3 * n + m:4 * n + m]
+        kind_h = np.zeros(n, dtype=np.uint8)
+        A_np = A_h.numpy()
+        ctx.check(N.lib.ellp_b200_generate_dense(ctx.h, m, ns, SEED, C.byref(o)))
+        ctx.check(N.lib.ellp_b200_download_std_form(ctx.h, N.ptr(A_np), N.ptr(c_h), N.ptr(b_h), N.ptr(kind_h), N.ptr(lb_h), N.ptr(ub_h)))
+        x0[:] = 0.0
+        x0[ns:] = b_h
+        B0 = np.arange(ns, n, dtype=np.int32); N0 = np.arange(ns, dtype=np.int32); Ns0 = np.zeros(ns, dtype=np.uint8)
+        sf = N.StdForm(m, n, N.ptr(A_np), N.ptr(c_h), N.ptr(b_h), N.ptr(kind_h), N.ptr(lb_h), N.ptr(ub_h))
+        oe = N.default_opts(P, engine=N.ENGINE_TABLEAU, check_every=min(P, 16))
+        xs = torch.empty(n, dtype=torch.float64, pin_memory=True).numpy()
+
+        def e2e_step():
+            xs[:] = x0
+            B, Nv, Ns = B0.copy(), N0.copy(), Ns0.copy()
+            pt = N.Point(N.ptr(xs), N.ptr(B), N.ptr(Nv), N.ptr(Ns), None, None, m, ns)
+            res = N.Result()
+            ctx.check(N.lib.ellp_b200_primal_solve_with_initial(ctx.h, C.byref(sf), C.byref(pt), C.byref(oe), C.byref(res)))
+            assert res.status == N.MAXITER and res.iters == P
+            return res.obj
+
+        for _ in range(min(args.warmup, 3)):
+            e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            obj = e2e_step()
+        torch.cuda.synchronize()
+        dte = time.perf_counter() - t0
+        h2d = 8 * m * n + 8 * (3 * n + m) + n + 8 * n + 4 * m + 4 * ns + ns
+        d2h = 8 * n + 4 * m + 4 * ns + ns + 120 * ((P + 15) // 16)
+        e2e = {"value": args.steps * P / dte, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": 1e3 * dte / args.steps, "api": "ellp_b200_primal_solve_with_initial (host buffers, pinned)",
+               "objective_after_step": obj}
+        del A_h
+
+    cpu = None
+    if not args.no_cpu:
+        v, dtc, sample = cpu_reference_sample(wl, max(6, wl["sample_pivots"] * 4))
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample, "seconds": dtc,
+               "host_cores_available": os.cpu_count()}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "m": m, "n": n, "pivots_per_step": P, "engine": "tableau (B^-1 A resident, in place)",
+                       "tie_rule": "reference folds", "l2": f"tableau {8.0 * m * n / 1e9:.1f} GB >> 126 MB L2 (no flush needed)",
+                       "baseline_config": "BASELINE.json configs[4]" if name == DEFAULT_WORKLOAD else "north_star / smaller variant"},
+            "device_ms_per_step": dev_ms / args.steps, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
+            "cpu_baseline": cpu, "e2e": e2e}
+    print(json.dumps(line), flush=True)
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--pivots", type=int, default=0, help="pivots per step (0 = workload default)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl, args.workload)
+    else:
+        run_ours(args, wl, args.workload)
+
+
+if __name__ == "__main__":
+    main()

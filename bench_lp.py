@@ -1,0 +1,38 @@
+"""Numpy twin of the device LP generator (ellp_b200/csrc/kernels.cuh: k_gen_dense_cols / k_gen_dense_vectors).
+
+Used by tests (bit-for-bit check against the device) and by bench.py's CPU legs, which must not touch the GPU library.
+    min -c.x  s.t.  A x + s = b, x, s >= 0;   A ~ U(0,1) m x ns,  b_i ~ U(1,2) * ns/4,  c_j ~ U(0.5,1.5)
+(SURVEY.md 8(d), configs 4/5).  Starting point: slack basis.
+"""
+import numpy as np
+
+_MASK = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _splitmix64(z):
+    with np.errstate(over="ignore"):
+        z = z + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def _uniform01(seed, idx):
+    with np.errstate(over="ignore"):
+        h = _splitmix64(np.uint64(seed) * np.uint64(0x2545F4914F6CDD1D) + idx.astype(np.uint64))
+    return (h >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def dense_lp(m: int, ns: int, seed: int) -> dict:
+    n = ns + m
+    A = np.zeros((m, n), order="F")
+    idx = np.arange(m * ns, dtype=np.uint64)
+    A[:, :ns] = _uniform01(seed, idx).reshape((m, ns), order="F")
+    A[:, ns:] = np.eye(m)
+    c = np.zeros(n)
+    c[:ns] = -(0.5 + _uniform01(seed + 1, np.arange(ns, dtype=np.uint64)))
+    b = (1.0 + _uniform01(seed + 2, np.arange(m, dtype=np.uint64))) * (ns * 0.25)
+    x = np.zeros(n)
+    x[ns:] = b
+    return dict(m=m, n=n, A=A, c=c, b=b, kind=np.ones(n, dtype=np.uint8), lb=np.zeros(n), ub=np.zeros(n), x=x,
+                B=np.arange(ns, n, dtype=np.int32), N=np.arange(ns, dtype=np.int32), N_side=np.zeros(ns, dtype=np.uint8))

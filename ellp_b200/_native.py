@@ -18,6 +18,7 @@ OK, E_ELLP, E_PANIC, E_CUDA, E_ARG = 0, -1, -2, -3, -4
 OPTIMAL, INFEASIBLE, UNBOUNDED, MAXITER = 0, 1, 2, 3
 PRIMAL, DUAL = 0, 1
 TIES_REFERENCE, TIES_CANONICAL = 0, 1
+ENGINE_AUTO, ENGINE_REVISED, ENGINE_TABLEAU = 0, 1, 2
 U64_MAX = 2**64 - 1
 
 TRACE_DTYPE = np.dtype([("phase", "<i4"), ("iter", "<i4"), ("entering", "<i4"), ("leaving", "<i4"),
@@ -93,6 +94,8 @@ def _load():
         "ellp_b200_d2h": (C.c_int, [vp, vp, vp, u64]),
         "ellp_b200_sync": (C.c_int, [vp]),
         "ellp_b200_dev_fill_uniform": (C.c_int, [vp, vp, u64, u64, u64, C.c_double, C.c_double]),
+        "ellp_b200_generate_dense": (C.c_int, [vp, i32, i32, u64, C.POINTER(Opts)]),
+        "ellp_b200_download_std_form": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
         "ellp_b200_rank1_update_dev": (C.c_int, [vp, vp, i64, i64, i64, vp, i64, i32, C.POINTER(C.c_float)]),
         "ellp_b200_rank1_update": (C.c_int, [vp, vp, i64, i64, i64, vp, i64]),
         "ellp_b200_gemv_t": (C.c_int, [vp, vp, i64, i64, i64, vp, i64, vp, vp]),
@@ -153,7 +156,7 @@ class Context:
 
 
 def default_opts(max_iter: Optional[int] = 1000, tie_rule: int = TIES_REFERENCE, refactor_every: int = 0,
-                 check_every: int = 0, profile: bool = False) -> Opts:
+                 check_every: int = 0, profile: bool = False, engine: int = ENGINE_AUTO) -> Opts:
     o = Opts()
     lib.ellp_b200_default_opts(C.byref(o))
     o.max_iter = U64_MAX if max_iter is None else int(max_iter)
@@ -161,6 +164,7 @@ def default_opts(max_iter: Optional[int] = 1000, tie_rule: int = TIES_REFERENCE,
     o.refactor_every = refactor_every
     o.check_every = check_every
     o.profile = 1 if profile else 0
+    o.engine = engine
     return o
 
 

@@ -56,6 +56,8 @@ struct ellp_b200_ctx {
     DevLP lp{};
     int KS = 1, kc = 64;
     bool binv_valid = false;
+    bool tableau = false;  // ELLP_ENGINE_TABLEAU resident
+    int* d_flag = nullptr;
     uint64_t pivots_since_refactor = 0;
     PivotState* d_st = nullptr;
     PivotState* h_st = nullptr;  // pinned
@@ -89,7 +91,7 @@ int ensure_arena(ellp_b200_ctx* ctx, size_t bytes) {
     return ELLP_OK;
 }
 
-void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap) {
+void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap, bool tableau) {
     const size_t ld = (size_t)lp.ld, m = (size_t)lp.m, n = (size_t)lp.n, nN = (size_t)lp.nN;
     lp.A = a.take<double>(ld * n);
     lp.c = a.take<double>(n);
@@ -103,16 +105,25 @@ void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap) {
     lp.Ns = a.take<uint8_t>(std::max<size_t>(nN, 1));
     lp.y = a.take<double>(ld);
     lp.d = a.take<double>(n);
-    lp.G = a.take<double>(ld * 2 * m);
-    lp.Binv = lp.G ? lp.G + ld * m : nullptr;
+    if (tableau) {  // T overwrites A in place; no basis inverse is kept
+        lp.G = nullptr;
+        lp.Binv = nullptr;
+        lp.T = const_cast<double*>(lp.A);
+        lp.dj = a.take<double>(n);
+    } else {
+        lp.G = a.take<double>(ld * 2 * m);
+        lp.Binv = lp.G ? lp.G + ld * m : nullptr;
+        lp.T = nullptr;
+        lp.dj = nullptr;
+    }
     lp.cB = a.take<double>(ld);
     lp.u = a.take<double>(ld);
     lp.rN = a.take<double>(std::max<size_t>(nN, 1));
     lp.key = a.take<double>(std::max<size_t>(nN, 1));
     lp.dcol = a.take<double>(ld);
     lp.rho = a.take<double>(ld);
-    lp.prow = a.take<double>(2 * m + 8);
-    lp.part = a.take<double>((size_t)KS * ld);
+    lp.prow = a.take<double>((tableau ? n : 2 * m) + 8);
+    lp.part = a.take<double>(tableau ? 8 : (size_t)KS * ld);
     lp.lam = a.take<double>(std::max<size_t>(m, 1));
     lp.trace = trace_cap > 0 ? a.take<ellp_trace_rec>((size_t)trace_cap) : nullptr;
 }
@@ -140,30 +151,50 @@ int write_state(ellp_b200_ctx* ctx) {
 }
 
 void launch_rank1(ellp_b200_ctx* ctx, double* E, int64_t ld, int R, int C, const double* alpha, const double* prow,
-                  const PivotState* st, int r_fixed) {
+                  const PivotState* st, int r_fixed, double* dj = nullptr) {
     if (C <= 0 || R <= 0) return;
     const int cpc = std::max(kColsInFlight, ctx->rank1_cols_per_cta);
     dim3 grid((unsigned)((R + 2 * kRank1Threads - 1) / (2 * kRank1Threads)), (unsigned)((C + cpc - 1) / cpc));
     const bool stream = (double)ld * C * 8.0 > (double)ctx->rank1_stream_min_mb * 1048576.0;
-    if (stream) LAUNCH(k_rank1<true>, grid, kRank1Threads, E, ld, R, C, alpha, prow, st, r_fixed, cpc);
-    else LAUNCH(k_rank1<false>, grid, kRank1Threads, E, ld, R, C, alpha, prow, st, r_fixed, cpc);
+    if (stream) LAUNCH(k_rank1<true>, grid, kRank1Threads, E, ld, R, C, alpha, prow, st, r_fixed, cpc, dj);
+    else LAUNCH(k_rank1<false>, grid, kRank1Threads, E, ld, R, C, alpha, prow, st, r_fixed, cpc, dj);
 }
 
 int gemv_grid(int ncols) { return std::max(1, std::min((ncols + 7) / 8, 148 * 32)); }
 
-// Gauss-Jordan refactorisation of B^-1 from the current basis (see kernels.cuh).
+// Gauss-Jordan refactorisation (see kernels.cuh).  Revised engine: B^-1 from the current basis on G = [A_B | I].
+// Tableau engine: T = B^-1 A built in place (skipped when the basis columns already are the identity), then the
+// reduced-cost row d = c - c_B^T T.
 int refactor(ellp_b200_ctx* ctx, uint64_t* count) {
     DevLP& lp = ctx->lp;
     const int m = lp.m;
     // preserve the iteration's index-level state around the factorisation
     if (int rc = read_state(ctx)) return rc;
     PivotState saved = *ctx->h_st;
-    LAUNCH(k_gj_init, 2 * m, 256, lp);
-    for (int k = 0; k < m; ++k) {
-        LAUNCH(k_gj_pivot, 1, 1024, lp, k, ctx->d_st);
-        const int cols = 2 * m - k;
-        LAUNCH(k_gj_swap_gather, (cols + 255) / 256, 256, lp, k, ctx->d_st);
-        launch_rank1(ctx, lp.G + (int64_t)k * lp.ld, lp.ld, m, cols, lp.dcol, lp.prow, ctx->d_st, 0);
+    if (!ctx->tableau) {
+        LAUNCH(k_gj_init, 2 * m, 256, lp);
+        for (int k = 0; k < m; ++k) {
+            LAUNCH(k_gj_pivot, 1, 1024, lp.G, lp.ld, m, (const int32_t*)nullptr, k, lp.dcol, ctx->d_st);
+            const int cols = 2 * m - k;
+            LAUNCH(k_gj_swap_gather, (cols + 255) / 256, 256, lp.G, lp.ld, k, 2 * m, k, lp.prow, ctx->d_st);
+            launch_rank1(ctx, lp.G + (int64_t)k * lp.ld, lp.ld, m, cols, lp.dcol, lp.prow, ctx->d_st, 0);
+        }
+    } else {
+        CUDA_TRY(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+        LAUNCH(k_check_identity_basis, m, 256, lp.T, lp.ld, m, lp.Bv, ctx->d_flag);
+        int mismatch = 0;
+        CUDA_TRY(cudaMemcpyAsync(&mismatch, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (mismatch) {
+            for (int k = 0; k < m; ++k) {
+                LAUNCH(k_gj_pivot, 1, 1024, lp.T, lp.ld, m, (const int32_t*)lp.Bv, k, lp.dcol, ctx->d_st);
+                LAUNCH(k_gj_swap_gather, (lp.n + 255) / 256, 256, lp.T, lp.ld, 0, lp.n, k, lp.prow, ctx->d_st);
+                launch_rank1(ctx, lp.T, lp.ld, m, lp.n, lp.dcol, lp.prow, ctx->d_st, 0);
+            }
+        }
+        LAUNCH(k_init_cB, (int)((lp.ld + 255) / 256), 256, lp);
+        LAUNCH(k_gemv_t<EPI_REDCOST>, gemv_grid(lp.n), 256, lp.T, lp.ld, (const int32_t*)nullptr, lp.n, lp.cB, lp.dj, lp.c,
+               (const uint8_t*)nullptr, (double*)nullptr, (PivotState*)nullptr, 0);
     }
     if (int rc = read_state(ctx)) return rc;
     const int err = ctx->h_st->err;
@@ -175,6 +206,20 @@ int refactor(ellp_b200_ctx* ctx, uint64_t* count) {
     ctx->pivots_since_refactor = 0;
     if (count) ++*count;
     return ELLP_OK;
+}
+
+// tableau engine, primal: 5 launches per pivot, the rank-1 update of T is >99 % of the bytes
+void launch_tableau_primal_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, bool profile, size_t* ev_used) {
+    DevLP& lp = ctx->lp;
+    PivotState* st = ctx->d_st;
+    const int m = lp.m, nN = lp.nN, n = lp.n;
+    LAUNCH(k_price_tab, (nN + 255) / 256, 256, lp.dj, lp.Nv, lp.Ns, nN, lp.rN, lp.key, st);     // primal :189, :253-270
+    LAUNCH(k_select_primal, 1, 32, lp.key, lp.rN, lp.Nv, lp.Ns, nN, o->tie_rule, st);           // :271-292
+    LAUNCH(k_ratio_primal, 1, 1024, lp, 0, o->tie_rule, st);                                    // :295-434, :205-232
+    LAUNCH(k_gather_row, (n + 255) / 256, 256, lp.T, lp.ld, n, st, lp.prow, 1);
+    if (profile && *ev_used + 2 <= ctx->ev.size()) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
+    launch_rank1(ctx, lp.T, lp.ld, m, n, lp.dcol, lp.prow, st, 0, lp.dj);
+    if (profile && (*ev_used & 1)) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
 }
 
 void launch_primal_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, bool profile, size_t* ev_used) {
@@ -285,7 +330,7 @@ int ellp_b200_create(int device, ellp_b200_ctx** out) {
     auto* ctx = new ellp_b200_ctx();
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc(&ctx->d_st, sizeof(PivotState)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_st, sizeof(PivotState)) != cudaSuccess || cudaMalloc(&ctx->d_flag, sizeof(int)) != cudaSuccess ||
         cudaMallocHost(&ctx->h_st, sizeof(PivotState)) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
         delete ctx;
@@ -305,6 +350,7 @@ void ellp_b200_destroy(ellp_b200_ctx* ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->d_st) cudaFree(ctx->d_st);
+    if (ctx->d_flag) cudaFree(ctx->d_flag);
     if (ctx->h_st) cudaFreeHost(ctx->h_st);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -344,12 +390,15 @@ int ellp_b200_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_poi
     kc = std::min(kc, kFtranMaxKc);
     const int KS = (m + kc - 1) / kc;
     const int64_t tcap = (o && o->trace) ? o->trace_cap : 0;
+    const bool tableau = o && o->engine == ELLP_ENGINE_TABLEAU;
+    if (tableau && solver != ELLP_PRIMAL)
+        return set_err(ctx, ELLP_E_ARG, "ELLP_ENGINE_TABLEAU implements the primal path only; use ELLP_ENGINE_REVISED for the dual");
     Arena probe;
-    carve(probe, lp, KS, tcap);
+    carve(probe, lp, KS, tcap, tableau);
     if (int rc = ensure_arena(ctx, probe.off + 256)) return rc;
     Arena a;
     a.base = ctx->arena;
-    carve(a, lp, KS, tcap);
+    carve(a, lp, KS, tcap, tableau);
     cudaStream_t s = ctx->stream;
     // zero the padded scratch once (padding rows must stay zero)
     CUDA_TRY(cudaMemsetAsync(lp.cB, 0, (size_t)((char*)lp.lam - (char*)lp.cB), s));
@@ -385,8 +434,61 @@ int ellp_b200_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_poi
     ctx->trace_cap = tcap;
     ctx->solver = solver;
     ctx->resident = true;
+    ctx->tableau = tableau;
     ctx->binv_valid = false;
     // host buffers are only borrowed for the duration of the call
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return ELLP_OK;
+}
+
+int ellp_b200_generate_dense(ellp_b200_ctx* ctx, int32_t m, int32_t n_struct, uint64_t seed, const ellp_opts* o) {
+    if (!ctx || !o || m <= 0 || n_struct <= 0 || (m % 4) != 0) return set_err(ctx, ELLP_E_ARG, "generate_dense needs m % 4 == 0");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    DevLP lp{};
+    lp.m = m;
+    lp.n = n_struct + m;
+    lp.nN = n_struct;
+    lp.ld = m;
+    int kc = std::min(kFtranMaxKc, std::max(64, (m + 63) / 64));
+    const int KS = (m + kc - 1) / kc;
+    const int64_t tcap = o->trace ? o->trace_cap : 0;
+    const bool tableau = o->engine == ELLP_ENGINE_TABLEAU;
+    Arena probe;
+    carve(probe, lp, KS, tcap, tableau);
+    if (int rc = ensure_arena(ctx, probe.off + 256)) return rc;
+    Arena a;
+    a.base = ctx->arena;
+    carve(a, lp, KS, tcap, tableau);
+    CUDA_TRY(cudaMemsetAsync(lp.cB, 0, (size_t)((char*)lp.lam - (char*)lp.cB), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(lp.y, 0, sizeof(double) * lp.ld, ctx->stream));
+    LAUNCH(k_gen_dense_cols, 148 * 16, 256, const_cast<double*>(lp.A), lp.ld, m, (int64_t)n_struct, (int64_t)0, (int64_t)lp.n, seed);
+    LAUNCH(k_gen_dense_vectors, 148 * 2, 256, lp, (int64_t)n_struct, seed);
+    ctx->lp = lp;
+    ctx->KS = KS;
+    ctx->kc = kc;
+    ctx->trace_cap = tcap;
+    ctx->solver = ELLP_PRIMAL;
+    ctx->resident = true;
+    ctx->tableau = tableau;
+    ctx->binv_valid = false;
+    ctx->dual_obj0 = 0.;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaGetLastError());
+    return ELLP_OK;
+}
+
+/* copies the resident standard form + point to caller (host) buffers: used to obtain host copies of generated LPs */
+int ellp_b200_download_std_form(ellp_b200_ctx* ctx, double* A, double* c, double* b, uint8_t* kind, double* lb, double* ub) {
+    if (!ctx || !ctx->resident) return ELLP_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const DevLP& lp = ctx->lp;
+    cudaStream_t s = ctx->stream;
+    if (A) CUDA_TRY(cudaMemcpy2DAsync(A, sizeof(double) * lp.m, lp.A, sizeof(double) * lp.ld, sizeof(double) * lp.m, lp.n, cudaMemcpyDeviceToHost, s));
+    if (c) CUDA_TRY(cudaMemcpyAsync(c, lp.c, sizeof(double) * lp.n, cudaMemcpyDeviceToHost, s));
+    if (b) CUDA_TRY(cudaMemcpyAsync(b, lp.b, sizeof(double) * lp.m, cudaMemcpyDeviceToHost, s));
+    if (kind) CUDA_TRY(cudaMemcpyAsync(kind, lp.kind, (size_t)lp.n, cudaMemcpyDeviceToHost, s));
+    if (lb) CUDA_TRY(cudaMemcpyAsync(lb, lp.lb, sizeof(double) * lp.n, cudaMemcpyDeviceToHost, s));
+    if (ub) CUDA_TRY(cudaMemcpyAsync(ub, lp.ub, sizeof(double) * lp.n, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return ELLP_OK;
 }
@@ -420,14 +522,15 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
     LAUNCH(k_init_cB, (int)((lp.ld + 255) / 256), 256, lp);
     if (ctx->solver == ELLP_PRIMAL) LAUNCH(k_obj_dot, 1, 1024, lp.c, lp.x, lp.n, ctx->d_st);
     int check_every = o->check_every > 0 ? o->check_every : (lp.m >= 2048 ? 1 : 8);
-    int refactor_every = o->refactor_every > 0 ? o->refactor_every : (lp.m <= 512 ? 100 : 0);
+    int refactor_every = o->refactor_every > 0 ? o->refactor_every : ((lp.m <= 512 && !ctx->tableau) ? 100 : 0);
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
     int rc_loop = ELLP_OK;
     while (h.status == kRunning) {
         int batch = check_every;
         if (refactor_every > 0) batch = (int)std::min<uint64_t>(batch, std::max<uint64_t>(1, refactor_every - ctx->pivots_since_refactor));
         for (int k = 0; k < batch; ++k) {
-            if (ctx->solver == ELLP_PRIMAL) launch_primal_iteration(ctx, o, profile, &ev_used);
+            if (ctx->tableau) launch_tableau_primal_iteration(ctx, o, profile, &ev_used);
+            else if (ctx->solver == ELLP_PRIMAL) launch_primal_iteration(ctx, o, profile, &ev_used);
             else launch_dual_iteration(ctx, o, profile, &ev_used);
         }
         const uint64_t before = h.pivots;

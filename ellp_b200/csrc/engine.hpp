@@ -8,4 +8,4 @@ namespace ellp {
 int host_solve_trivial(const ellp_std_form* sf, ellp_point* pt, bool minimize);
 }  // namespace ellp
 
-extern "C" int ellp_b200_set_tuning(ellp_b200_ctx* ctx, const char* key, int value);
+

@@ -49,6 +49,9 @@ struct DevLP {
     double* part;  // KS x ld split-K partial sums
     double* lam;   // m
     ellp_trace_rec* trace;
+    // tableau engine (ELLP_ENGINE_TABLEAU): T = B^-1 A lives in the buffer of A (in place), dj = reduced costs
+    double* T;     // ld x n, nullptr for the revised engine
+    double* dj;    // n
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -66,7 +69,7 @@ __device__ __forceinline__ void st_f64x2_stream(double* p, double2 v) { __stcs(r
 // K1/K5 (transpose form): one warp per column, 16-byte coalesced loads, 4 loads in flight per lane,
 // warp-shuffle reduction.  len2 = ld/2 double2 elements per column (padding rows are zero in M and v).
 // ------------------------------------------------------------------------------------------------
-enum { EPI_PLAIN = 0, EPI_PRIMAL_PRICE = 1 };
+enum { EPI_PLAIN = 0, EPI_PRIMAL_PRICE = 1, EPI_REDCOST = 2 };
 
 __device__ __forceinline__ double warp_col_dot(const double* __restrict__ col, const double* __restrict__ v, int len2, int lane) {
     const double2* c2 = reinterpret_cast<const double2*>(col);
@@ -107,6 +110,8 @@ __global__ void __launch_bounds__(256) k_gemv_t(const double* __restrict__ M, in
         if (lane == 0) {
             if (EPI == EPI_PLAIN) {
                 out[j] = dot;
+            } else if (EPI == EPI_REDCOST) {
+                out[j] = c[col] - dot;  // d_j = c_j - c_B^T (B^-1 a_j): reduced-cost row of a fresh tableau
             } else {
                 // r_j = c_j - a_j^T u (primal :189) and the Dantzig key (primal :258-269); -1 marks "not a candidate"
                 const double r = c[col] - dot;
@@ -304,9 +309,14 @@ __global__ void __launch_bounds__(1024) k_ratio_primal(DevLP lp, int KS, int tie
     const int q_var = st->q_var;
     const bool at_lower = (st->q_side == ELLP_NB_LOWER);
     // alpha = sum of split-K partials (fixed order); d = -alpha when entering from its lower bound (:296-300)
+    // KS > 0: revised engine, alpha = sum of split-K partials; KS == 0: tableau engine, alpha = T[:, q] (copied out
+    // because k_rank1 overwrites that column); KS < 0: alpha already sits in dcol (column-sharded tableau)
+    const double* tcol = (KS == 0) ? lp.T + (int64_t)q_var * lp.ld : nullptr;
     for (int i = tid; i < m; i += blockDim.x) {
         double a = 0.;
-        for (int ks = 0; ks < KS; ++ks) a += lp.part[(int64_t)ks * lp.ld + i];
+        if (KS > 0) { for (int ks = 0; ks < KS; ++ks) a += lp.part[(int64_t)ks * lp.ld + i]; }
+        else if (KS == 0) a = tcol[i];
+        else a = lp.dcol[i];
         lp.dcol[i] = a;
         const double d_i = at_lower ? -a : a;
         double lam = -1.0;  // -1 = skipped (|d_i| < EPS, :321)
@@ -479,16 +489,23 @@ constexpr int kColsInFlight = 8;
 template <bool STREAM>
 __global__ void __launch_bounds__(kRank1Threads) k_rank1(double* __restrict__ E, int64_t ld, int R, int C,
                                                          const double* __restrict__ alpha, const double* __restrict__ prow,
-                                                         const PivotState* st, int r_fixed, int cols_per_cta) {
+                                                         const PivotState* st, int r_fixed, int cols_per_cta,
+                                                         double* __restrict__ dj) {
     int r = r_fixed;
     if (st) {
         if (!st->do_update) return;
         r = st->r_pos;
     }
-    const int64_t row = ((int64_t)blockIdx.x * kRank1Threads + threadIdx.x) * 2;
-    if (row >= R) return;
     const int c0 = blockIdx.y * cols_per_cta;
     const int c1 = min(C, c0 + cols_per_cta);
+    // tableau engine: the reduced-cost row is one more row of the same rank-1 update,
+    // d_j -= d_q * p_j; the first row-block of every column group carries it (C extra doubles in total)
+    if (dj != nullptr && blockIdx.x == 0) {
+        const double nrq = -st->rq;
+        for (int j = c0 + threadIdx.x; j < c1; j += kRank1Threads) dj[j] = fma(nrq, __ldg(prow + j), dj[j]);
+    }
+    const int64_t row = ((int64_t)blockIdx.x * kRank1Threads + threadIdx.x) * 2;
+    if (row >= R) return;
     double2 na = ld_f64x2(alpha + row);
     na.x = -na.x;
     na.y = (row + 1 < R) ? -na.y : 0.;  // a padding row (ld > R) is never modified: fma(0, p, e) == e for finite p
@@ -710,15 +727,19 @@ __global__ void k_gj_init(DevLP lp) {
     }
 }
 
-__global__ void __launch_bounds__(1024) k_gj_pivot(DevLP lp, int k, PivotState* st) {
+// M: ld x ncols working matrix; pcol: column whose entries at rows >= k are searched for the pivot
+// (k itself for [A_B | I]; the basis column Bv[k] when a tableau is built in place)
+__global__ void __launch_bounds__(1024) k_gj_pivot(double* __restrict__ M, int64_t ld, int m, const int32_t* __restrict__ pcol_of,
+                                                   int k, double* __restrict__ dcol, PivotState* st) {
     if (st->err) return;
     __shared__ double s_v[32];
     __shared__ int s_i[32];
     const int tid = threadIdx.x;
-    const double* col = lp.G + (int64_t)k * lp.ld;
+    const int pc = pcol_of ? pcol_of[k] : k;
+    const double* col = M + (int64_t)pc * ld;
     double bv = -1.;
     int bi = 0x7fffffff;
-    for (int i = k + tid; i < lp.m; i += blockDim.x) {
+    for (int i = k + tid; i < m; i += blockDim.x) {
         const double v = fabs(col[i]);
         if (v > bv) { bv = v; bi = i; }  // strict: first max per thread
     }
@@ -745,30 +766,64 @@ __global__ void __launch_bounds__(1024) k_gj_pivot(DevLP lp, int k, PivotState* 
             s_i[0] = bi;
             st->gj_piv = bi;
             st->r_pos = k;
-            st->alpha_r = col[bi];
             st->do_update = 1;
-            if (!(bv >= kEps)) { st->err = kErrSingular; st->do_update = 0; }  // |U_kk| < EPS
+            if (!(bv >= kEps)) { st->err = kErrSingular; st->do_update = 0; s_i[0] = -1; }  // |U_kk| < EPS
+            else st->alpha_r = col[bi];
         }
     }
     __syncthreads();
     const int p = s_i[0];
-    if (st->err) return;
+    if (p < 0) return;
     // pivot column after the row swap k <-> p (padding rows stay zero)
-    for (int64_t i = tid; i < lp.ld; i += blockDim.x) {
+    for (int64_t i = tid; i < ld; i += blockDim.x) {
         const int64_t src = (i == k) ? p : ((i == p) ? k : i);
-        lp.dcol[i] = (i < lp.m) ? col[src] : 0.;
+        dcol[i] = (i < m) ? col[src] : 0.;
     }
 }
 
-__global__ void k_gj_swap_gather(DevLP lp, int k, const PivotState* st) {
+// swaps rows k and p of columns [c_begin, c_end) and emits the scaled pivot row prow[j - c_begin] = M[k, j] / pivot
+__global__ void k_gj_swap_gather(double* __restrict__ M, int64_t ld, int c_begin, int c_end, int k, double* __restrict__ prow,
+                                 const PivotState* st) {
     if (st->err) return;
-    const int j = k + blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= 2 * lp.m) return;
+    const int j = c_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= c_end) return;
     const int p = st->gj_piv;
-    double* col = lp.G + (int64_t)j * lp.ld;
+    double* col = M + (int64_t)j * ld;
     const double a = col[k], b = col[p];
     if (p != k) { col[k] = b; col[p] = a; }
-    lp.prow[j - k] = b / st->alpha_r;
+    prow[j - c_begin] = b / st->alpha_r;
+}
+
+// tableau engine: is column Bv[i] of T exactly e_i for every i (slack / identity starting basis)?
+__global__ void k_check_identity_basis(const double* __restrict__ T, int64_t ld, int m, const int32_t* __restrict__ Bv,
+                                       int* __restrict__ mismatch) {
+    const int i = blockIdx.x;
+    const double* col = T + (int64_t)Bv[i] * ld;
+    bool bad = false;
+    for (int k = threadIdx.x; k < m; k += blockDim.x) {
+        const double want = (k == i) ? 1. : 0.;
+        if (col[k] != want) bad = true;
+    }
+    if (bad) *mismatch = 1;
+}
+
+// tableau engine pricing: reduced costs are a maintained row, so the Dantzig keys are a pure O(n - m) pass
+__global__ void k_price_tab(const double* __restrict__ dj, const int32_t* __restrict__ Nv, const uint8_t* __restrict__ Ns, int nN,
+                            double* __restrict__ rN, double* __restrict__ key, PivotState* st) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->do_update = 0;
+    if (st->status != kRunning) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nN) return;
+    const double r = dj[Nv[j]];
+    const int side = Ns[j];
+    double k = -1.0;
+    if (!(fabs(r) < kEps)) {  // primal :258-269
+        if (r > 0. && side == ELLP_NB_UPPER) k = r;
+        else if (!(r > 0.) && side == ELLP_NB_LOWER) k = -r;
+        else if (side == ELLP_NB_FREE) k = fabs(r);
+    }
+    rN[j] = r;
+    key[j] = k;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -806,6 +861,55 @@ __global__ void k_fill_uniform(double* __restrict__ out, uint64_t count, uint64_
         const double u = (double)(h >> 11) * (1.0 / 9007199254740992.0);
         out[i] = lo + (hi - lo) * u;
     }
+}
+
+
+// ---- synthetic dense LP built directly in HBM (bench workloads) ----------------------------
+//   min -c.x  s.t.  A x + s = b, x, s >= 0      A ~ U(0,1) m x ns,  b_i ~ U(1,2) * ns/4,  c_j ~ U(0.5,1.5)
+// columns [0, ns) structural, [ns, ns+m) slack (identity); starting point = slack basis (primal feasible).
+// col_lo/col_hi select the locally stored column range (column sharding); element values depend only on the
+// GLOBAL (row, column) index so every sharding sees the same LP.
+__global__ void k_gen_dense_cols(double* __restrict__ A, int64_t ld, int m, int64_t ns, int64_t col_lo, int64_t col_hi, uint64_t seed) {
+    const int64_t ncol = col_hi - col_lo;
+    const int64_t total = ncol * ld;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t jl = e / ld, i = e - jl * ld;
+        const int64_t j = col_lo + jl;
+        double v = 0.;
+        if (i < m) {
+            if (j < ns) {
+                const uint64_t h = splitmix64(seed * 0x2545f4914f6cdd1dull + (uint64_t)(j * m + i));
+                v = (double)(h >> 11) * (1.0 / 9007199254740992.0);
+            } else {
+                v = (j - ns == i) ? 1. : 0.;
+            }
+        }
+        A[e] = v;
+    }
+}
+
+__global__ void k_gen_dense_vectors(DevLP lp, int64_t ns, uint64_t seed) {
+    const int m = lp.m, n = lp.n;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        double cj = 0., xj = 0.;
+        if (j < ns) {
+            const uint64_t h = splitmix64((seed + 1) * 0x2545f4914f6cdd1dull + (uint64_t)j);
+            cj = -(0.5 + (double)(h >> 11) * (1.0 / 9007199254740992.0));
+        } else {
+            const uint64_t h = splitmix64((seed + 2) * 0x2545f4914f6cdd1dull + (uint64_t)(j - ns));
+            xj = (1.0 + (double)(h >> 11) * (1.0 / 9007199254740992.0)) * ((double)ns * 0.25);
+            const int i = (int)(j - ns);
+            const_cast<double*>(lp.b)[i] = xj;
+            lp.Bv[i] = (int32_t)j;
+        }
+        const_cast<double*>(lp.c)[j] = cj;
+        const_cast<double*>(lp.lb)[j] = 0.;
+        const_cast<double*>(lp.ub)[j] = 0.;
+        const_cast<uint8_t*>(lp.kind)[j] = ELLP_LOWER;
+        lp.x[j] = xj;
+        if (j < ns) { lp.Nv[j] = (int32_t)j; lp.Ns[j] = ELLP_NB_LOWER; }
+    }
+    (void)m;
 }
 
 }  // namespace ellp

@@ -82,13 +82,15 @@ class _GpuSimplexSolver:
     _solver = N.PRIMAL
 
     def __init__(self, max_iter: Optional[int] = 1000, *, ctx: Optional[N.Context] = None,
-                 tie_rule: int = N.TIES_REFERENCE, refactor_every: int = 0, check_every: int = 0, trace_cap: int = 0):
+                 tie_rule: int = N.TIES_REFERENCE, refactor_every: int = 0, check_every: int = 0, trace_cap: int = 0,
+                 engine: int = N.ENGINE_AUTO):
         self.max_iter = max_iter
         self._ctx = ctx
         self.tie_rule = tie_rule
         self.refactor_every = refactor_every
         self.check_every = check_every
         self.trace_cap = trace_cap
+        self.engine = engine
 
     @classmethod
     def default(cls, **kw):  # Default::default(): max_iter = 1000
@@ -103,7 +105,7 @@ class _GpuSimplexSolver:
         return self._ctx or default_context()
 
     def _opts(self):
-        o = N.default_opts(self.max_iter, self.tie_rule, self.refactor_every, self.check_every)
+        o = N.default_opts(self.max_iter, self.tie_rule, self.refactor_every, self.check_every, engine=self.engine)
         tr = None
         if self.trace_cap:
             tr = np.zeros(self.trace_cap, dtype=N.TRACE_DTYPE)

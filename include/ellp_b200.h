@@ -132,6 +132,16 @@ int ellp_b200_upload(ellp_b200_ctx*, const ellp_std_form*, const ellp_point*, in
 int ellp_b200_run(ellp_b200_ctx*, const ellp_opts*, ellp_result*);      /* continues from the resident point */
 int ellp_b200_download(ellp_b200_ctx*, ellp_point*);
 
+/* Builds the synthetic dense LP of the bench configs directly in HBM (never crosses PCIe) and leaves it resident:
+ *   min -c.x  s.t.  A x + s = b, x, s >= 0;  A ~ U(0,1) m x n_struct, b_i ~ U(1,2)*n_struct/4, c_j ~ U(0.5,1.5)
+ * standard form m x (n_struct + m), starting point = slack basis.  Values come from a counter-based generator
+ * (splitmix64 of seed and the global element index).  o->engine selects the resident representation. */
+int ellp_b200_generate_dense(ellp_b200_ctx*, int32_t m, int32_t n_struct, uint64_t seed, const ellp_opts* o);
+/* copies the resident standard form to host buffers (any pointer may be NULL) */
+int ellp_b200_download_std_form(ellp_b200_ctx*, double* A, double* c, double* b, uint8_t* kind, double* lb, double* ub);
+/* tuning knobs: "rank1_cols_per_cta", "rank1_stream_min_mb" */
+int ellp_b200_set_tuning(ellp_b200_ctx*, const char* key, int value);
+
 /* ---- two-phase drivers: {Primal,Dual}SimplexSolver::solve ------------------------------------ */
 /* A Problem as built by Problem::add_var / add_constraint (src/problem.rs:19-106); constraints in
  * CSR over variable ids. */

@@ -254,3 +254,61 @@ def test_invert_matches_numpy(env, m):
     inv = np.zeros((m, m), order="F")
     ctx.check(N.lib.ellp_b200_invert(ctx.h, N.ptr(Bm), m, N.ptr(inv)))
     np.testing.assert_allclose(inv @ Bm, np.eye(m), atol=1e-8 * np.linalg.cond(Bm))
+
+
+# ---------------------------------------------------------------- tableau engine (column-shardable representation)
+@pytest.mark.parametrize("seed,m,n,tie", [(0, 24, 40, 0), (1, 64, 128, 0), (2, 64, 128, 1), (3, 132, 190, 0)])
+def test_tableau_engine_matches_oracle_trace(env, seed, m, n, tie):
+    O, S, N = env["O"], env["S"], env["N"]
+    A, b, c = _dense_lp(seed, m, n)
+    Af, cf, kind, lb, ub, x0, B0, N0, Ns0 = _slack_start_primal(A, b, c)
+    xo, Bo, No, Nso = x0.copy(), B0.copy(), N0.copy(), Ns0.copy()
+    ref = O.solve_with_initial(O.PRIMAL, m, n + m, Af, cf, b, kind, lb, ub, xo, Bo, No, Nso, max_iter=None, mode=tie, trace_cap=20000)
+    xg, Bg, Ng, Nsg = x0.copy(), B0.copy(), N0.copy(), Ns0.copy()
+    sol = S.GpuPrimalSimplexSolver.new(None, ctx=env["ctx"], trace_cap=20000, tie_rule=tie, engine=N.ENGINE_TABLEAU)
+    res, trace = sol.solve_with_initial(m, n + m, Af, cf, b, kind, lb, ub, xg, Bg, Ng, Nsg)
+    assert res.status == ref.status == O.OPTIMAL
+    assert res.iters == len(ref.trace)
+    assert (trace["entering"] == ref.trace["entering"]).all() and (trace["leaving"] == ref.trace["leaving"]).all()
+    np.testing.assert_array_equal(Bg, Bo)
+    np.testing.assert_allclose(xg, xo, rtol=1e-9, atol=1e-9)
+    assert _rel(res.obj, ref.obj) < 1e-9
+
+
+@pytest.mark.parametrize("make", P.GOLDEN + [lambda n=n: P.netlib(n) for n in P.NETLIB],
+                         ids=[f.__name__ for f in P.GOLDEN] + P.NETLIB)
+def test_tableau_engine_two_phase_primal(env, make):
+    # non-identity starting bases (phase 2 restarts from phase 1's basis): the tableau is rebuilt by Gauss-Jordan
+    prob, exp = make()
+    N, S = env["N"], env["S"]
+    res = S.GpuPrimalSimplexSolver.default(ctx=env["ctx"], engine=N.ENGINE_TABLEAU).solve(prob)
+    obj = res.solution.obj() if res.is_optimal else float("nan")
+    x = res.solution.x() if res.is_optimal else []
+    P.check_expectation(exp, res.kind, obj, x)
+    ref = env["O"].solve(prob, env["O"].PRIMAL, 1000, env["O"].MODE_EXACT)
+    assert res.kind == ref.status_name
+    if res.is_optimal:
+        assert _rel(obj, ref.obj) < 1e-9
+        assert res.iters == ref.iters
+
+
+def test_generated_dense_lp_matches_numpy_twin_and_oracle(env):
+    """The bench LP is generated in HBM; its numpy twin (bench_lp.py) must produce the same bits, and a short
+    budget of pivots must follow the oracle's pivot sequence."""
+    import bench_lp
+    N, O, ctx = env["N"], env["O"], env["ctx"]
+    m, ns, seed, K = 64, 96, 5, 40
+    o = N.default_opts(K, engine=N.ENGINE_TABLEAU)
+    tr = np.zeros(K, dtype=N.TRACE_DTYPE); o.trace = N.ptr(tr); o.trace_cap = K
+    ctx.check(N.lib.ellp_b200_generate_dense(ctx.h, m, ns, seed, C.byref(o)))
+    n = ns + m
+    A = np.zeros((m, n), order="F"); c = np.zeros(n); b = np.zeros(m); kind = np.zeros(n, dtype=np.uint8); lb = np.zeros(n); ub = np.zeros(n)
+    ctx.check(N.lib.ellp_b200_download_std_form(ctx.h, N.ptr(A), N.ptr(c), N.ptr(b), N.ptr(kind), N.ptr(lb), N.ptr(ub)))
+    lp = bench_lp.dense_lp(m, ns, seed)
+    assert A.tobytes() == lp["A"].tobytes() and c.tobytes() == lp["c"].tobytes() and b.tobytes() == lp["b"].tobytes()
+    res = N.Result()
+    ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(o), C.byref(res)))
+    assert res.status == N.MAXITER and res.iters == K
+    ref = O.solve_with_initial(O.PRIMAL, m, n, lp["A"], lp["c"], lp["b"], lp["kind"], lp["lb"], lp["ub"], lp["x"].copy(),
+                               lp["B"].copy(), lp["N"].copy(), lp["N_side"].copy(), max_iter=K, trace_cap=K)
+    assert (tr["entering"] == ref.trace["entering"]).all() and (tr["leaving"] == ref.trace["leaving"]).all()
