@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <dlfcn.h>
 #include <limits>
 #include <string>
 #include <vector>
@@ -28,6 +29,12 @@ using namespace ellp;
 #define LAUNCH(kernel, grid, block, ...)                                                         \
     do {                                                                                         \
         kernel<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__);                                \
+        ctx->launches++;                                                                         \
+    } while (0)
+
+#define LAUNCH_SMEM(kernel, grid, block, smem, ...)                                              \
+    do {                                                                                         \
+        kernel<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);                           \
         ctx->launches++;                                                                         \
     } while (0)
 
@@ -57,6 +64,12 @@ struct ellp_b200_ctx {
     int KS = 1, kc = 64;
     bool binv_valid = false;
     bool tableau = false;  // ELLP_ENGINE_TABLEAU resident
+    // column sharding (one rank per GPU)
+    bool sharded = false;
+    int rank = 0, nranks = 1;
+    void* nccl_comm = nullptr;
+    double* sendcol = nullptr;  // ld doubles staged for the pivot-column all-reduce (inside the arena)
+    uint8_t* d_sides = nullptr; // n_glob bytes: colstat of every column (gathered) / scatter source
     int* d_flag = nullptr;
     uint64_t pivots_since_refactor = 0;
     PivotState* d_st = nullptr;
@@ -69,6 +82,48 @@ struct ellp_b200_ctx {
     int rank1_cols_per_cta = 8;
     int rank1_stream_min_mb = 96;  // evict-first policy when the updated matrix is larger than this
 };
+
+// ---- NCCL, bound at run time (torch ships libnccl.so.2; the library must also load on boxes without it) -----------
+namespace nccl {
+struct UniqueId { char internal[128]; };
+typedef void* Comm;
+enum { kUint8 = 1, kFloat64 = 8, kSum = 0 };
+struct Api {
+    void* handle = nullptr;
+    int (*GetUniqueId)(UniqueId*) = nullptr;
+    int (*CommInitRank)(Comm*, int, UniqueId, int) = nullptr;
+    int (*CommDestroy)(Comm) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, Comm, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static Api api;
+static bool load(const char* path, std::string* err) {
+    if (api.handle) return true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h && path && *path) h = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { *err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+    api.handle = h;
+    api.GetUniqueId = (int (*)(UniqueId*))dlsym(h, "ncclGetUniqueId");
+    api.CommInitRank = (int (*)(Comm*, int, UniqueId, int))dlsym(h, "ncclCommInitRank");
+    api.CommDestroy = (int (*)(Comm))dlsym(h, "ncclCommDestroy");
+    api.AllGather = (int (*)(const void*, void*, size_t, int, Comm, cudaStream_t))dlsym(h, "ncclAllGather");
+    api.AllReduce = (int (*)(const void*, void*, size_t, int, int, Comm, cudaStream_t))dlsym(h, "ncclAllReduce");
+    api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.AllReduce) { *err = "libnccl.so.2 lacks required symbols"; api.handle = nullptr; return false; }
+    return true;
+}
+}  // namespace nccl
+
+#define NCCL_TRY(expr)                                                                                       \
+    do {                                                                                                     \
+        int r__ = (expr);                                                                                    \
+        if (r__ != 0) {                                                                                      \
+            ctx->err = std::string(#expr) + ": " + (nccl::api.GetErrorString ? nccl::api.GetErrorString(r__) : "nccl error"); \
+            return ELLP_E_CUDA;                                                                              \
+        }                                                                                                    \
+    } while (0)
 
 namespace {
 
@@ -91,20 +146,23 @@ int ensure_arena(ellp_b200_ctx* ctx, size_t bytes) {
     return ELLP_OK;
 }
 
-void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap, bool tableau) {
-    const size_t ld = (size_t)lp.ld, m = (size_t)lp.m, n = (size_t)lp.n, nN = (size_t)lp.nN;
+void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap, bool tableau, bool sharded = false, int nranks = 1,
+           double** sendcol = nullptr, uint8_t** d_sides = nullptr) {
+    // n = locally stored columns (A / T, dj, key, prow); ng = length of the replicated per-variable vectors
+    const size_t ld = (size_t)lp.ld, m = (size_t)lp.m, n = (size_t)lp.n, ng = (size_t)lp.n_glob;
+    const size_t nN = sharded ? n : (size_t)lp.nN;
     lp.A = a.take<double>(ld * n);
-    lp.c = a.take<double>(n);
+    lp.c = a.take<double>(ng);
     lp.b = a.take<double>(std::max<size_t>(m, 1));
-    lp.lb = a.take<double>(n);
-    lp.ub = a.take<double>(n);
-    lp.kind = a.take<uint8_t>(n);
-    lp.x = a.take<double>(n);
+    lp.lb = a.take<double>(ng);
+    lp.ub = a.take<double>(ng);
+    lp.kind = a.take<uint8_t>(ng);
+    lp.x = a.take<double>(ng);
     lp.Bv = a.take<int32_t>(std::max<size_t>(m, 1));
     lp.Nv = a.take<int32_t>(std::max<size_t>(nN, 1));
     lp.Ns = a.take<uint8_t>(std::max<size_t>(nN, 1));
     lp.y = a.take<double>(ld);
-    lp.d = a.take<double>(n);
+    lp.d = a.take<double>(ng);
     if (tableau) {  // T overwrites A in place; no basis inverse is kept
         lp.G = nullptr;
         lp.Binv = nullptr;
@@ -126,6 +184,17 @@ void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap, bool tableau) {
     lp.part = a.take<double>(tableau ? 8 : (size_t)KS * ld);
     lp.lam = a.take<double>(std::max<size_t>(m, 1));
     lp.trace = trace_cap > 0 ? a.take<ellp_trace_rec>((size_t)trace_cap) : nullptr;
+    if (sharded) {
+        lp.colstat = a.take<uint8_t>(n);
+        lp.xchg = a.take<double>(64 + 4 * (size_t)nranks);
+        double* sc = a.take<double>(ld);
+        uint8_t* sd = a.take<uint8_t>(ng);
+        if (sendcol) *sendcol = sc;
+        if (d_sides) *d_sides = sd;
+    } else {
+        lp.colstat = nullptr;
+        lp.xchg = nullptr;
+    }
 }
 
 const char* dev_err_message(int e) {
@@ -180,11 +249,13 @@ int refactor(ellp_b200_ctx* ctx, uint64_t* count) {
             launch_rank1(ctx, lp.G + (int64_t)k * lp.ld, lp.ld, m, cols, lp.dcol, lp.prow, ctx->d_st, 0);
         }
     } else {
-        CUDA_TRY(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
-        LAUNCH(k_check_identity_basis, m, 256, lp.T, lp.ld, m, lp.Bv, ctx->d_flag);
         int mismatch = 0;
-        CUDA_TRY(cudaMemcpyAsync(&mismatch, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (!ctx->sharded) {  // a sharded tableau is only accepted with an identity starting basis (checked at upload)
+            CUDA_TRY(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+            LAUNCH(k_check_identity_basis, m, 256, lp.T, lp.ld, m, lp.Bv, ctx->d_flag);
+            CUDA_TRY(cudaMemcpyAsync(&mismatch, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        }
         if (mismatch) {
             for (int k = 0; k < m; ++k) {
                 LAUNCH(k_gj_pivot, 1, 1024, lp.T, lp.ld, m, (const int32_t*)lp.Bv, k, lp.dcol, ctx->d_st);
@@ -193,7 +264,7 @@ int refactor(ellp_b200_ctx* ctx, uint64_t* count) {
             }
         }
         LAUNCH(k_init_cB, (int)((lp.ld + 255) / 256), 256, lp);
-        LAUNCH(k_gemv_t<EPI_REDCOST>, gemv_grid(lp.n), 256, lp.T, lp.ld, (const int32_t*)nullptr, lp.n, lp.cB, lp.dj, lp.c,
+        LAUNCH(k_gemv_t<EPI_REDCOST>, gemv_grid(lp.n), 256, lp.T, lp.ld, (const int32_t*)nullptr, lp.n, lp.cB, lp.dj, lp.c + lp.col_lo,
                (const uint8_t*)nullptr, (double*)nullptr, (PivotState*)nullptr, 0);
     }
     if (int rc = read_state(ctx)) return rc;
@@ -214,12 +285,32 @@ void launch_tableau_primal_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, boo
     PivotState* st = ctx->d_st;
     const int m = lp.m, nN = lp.nN, n = lp.n;
     LAUNCH(k_price_tab, (nN + 255) / 256, 256, lp.dj, lp.Nv, lp.Ns, nN, lp.rN, lp.key, st);     // primal :189, :253-270
-    LAUNCH(k_select_primal, 1, 32, lp.key, lp.rN, lp.Nv, lp.Ns, nN, o->tie_rule, st);           // :271-292
-    LAUNCH(k_ratio_primal, 1, 1024, lp, 0, o->tie_rule, st);                                    // :295-434, :205-232
+    LAUNCH_SMEM(k_select_primal, 1, kScanThreads, kScanSmemBytes, lp.key, lp.rN, lp.Nv, lp.Ns, nN, o->tie_rule, st);           // :271-292
+    LAUNCH_SMEM(k_ratio_primal, 1, kScanThreads, kScanSmemBytes, lp, 0, o->tie_rule, st);                                    // :295-434, :205-232
     LAUNCH(k_gather_row, (n + 255) / 256, 256, lp.T, lp.ld, n, st, lp.prow, 1);
     if (profile && *ev_used + 2 <= ctx->ev.size()) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
     launch_rank1(ctx, lp.T, lp.ld, m, n, lp.dcol, lp.prow, st, 0, lp.dj);
     if (profile && (*ev_used & 1)) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
+}
+
+// column-sharded tableau: 7 kernels + 3 NCCL collectives per pivot, no host involvement
+int launch_sharded_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, bool profile, size_t* ev_used) {
+    DevLP& lp = ctx->lp;
+    PivotState* st = ctx->d_st;
+    const int m = lp.m, n = lp.n, G = ctx->nranks;
+    LAUNCH(k_price_shard, (n + 255) / 256, 256, lp, st);
+    LAUNCH(k_shard_local_max, 1, 1024, lp, st);
+    NCCL_TRY(nccl::api.AllGather(lp.xchg + 0, lp.xchg + 16, 1, nccl::kFloat64, ctx->nccl_comm, ctx->stream));
+    LAUNCH(k_shard_pick, 1, 1024, lp, G, st);
+    NCCL_TRY(nccl::api.AllGather(lp.xchg + 8, lp.xchg + 32, 3, nccl::kFloat64, ctx->nccl_comm, ctx->stream));
+    LAUNCH(k_shard_stage_column, (int)((lp.ld + 255) / 256), 256, lp, G, st, ctx->sendcol);
+    NCCL_TRY(nccl::api.AllReduce(ctx->sendcol, lp.dcol, (size_t)lp.ld, nccl::kFloat64, nccl::kSum, ctx->nccl_comm, ctx->stream));
+    LAUNCH_SMEM(k_ratio_primal, 1, kScanThreads, kScanSmemBytes, lp, -1, o->tie_rule, st);
+    LAUNCH(k_gather_row, (n + 255) / 256, 256, lp.T, lp.ld, n, st, lp.prow, 1);
+    if (profile && *ev_used + 2 <= ctx->ev.size()) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
+    launch_rank1(ctx, lp.T, lp.ld, m, n, lp.dcol, lp.prow, st, 0, lp.dj);
+    if (profile && (*ev_used & 1)) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
+    return ELLP_OK;
 }
 
 void launch_primal_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, bool profile, size_t* ev_used) {
@@ -231,11 +322,11 @@ void launch_primal_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, bool profil
            (const double*)nullptr, (const uint8_t*)nullptr, (double*)nullptr, st, 1);
     // pricing r = c_N - A_N^T u + Dantzig keys  (primal :189, :253-270)
     LAUNCH(k_gemv_t<EPI_PRIMAL_PRICE>, gemv_grid(nN), 256, lp.A, lp.ld, lp.Nv, nN, lp.u, lp.rN, lp.c, lp.Ns, lp.key, st, 0);
-    LAUNCH(k_select_primal, 1, 32, lp.key, lp.rN, lp.Nv, lp.Ns, nN, o->tie_rule, st);
+    LAUNCH_SMEM(k_select_primal, 1, kScanThreads, kScanSmemBytes, lp.key, lp.rN, lp.Nv, lp.Ns, nN, o->tie_rule, st);
     // FTRAN d = B^-1 a_q  (primal :295)
     dim3 fg((unsigned)((lp.ld + 255) / 256), (unsigned)ctx->KS);
     LAUNCH(k_ftran_partial, fg, 128, lp.Binv, lp.ld, m, lp.A, st, lp.part, ctx->kc);
-    LAUNCH(k_ratio_primal, 1, 1024, lp, ctx->KS, o->tie_rule, st);
+    LAUNCH_SMEM(k_ratio_primal, 1, kScanThreads, kScanSmemBytes, lp, ctx->KS, o->tie_rule, st);
     LAUNCH(k_gather_row, (m + 255) / 256, 256, lp.Binv, lp.ld, m, st, lp.prow, 1);
     if (profile && *ev_used + 2 <= ctx->ev.size()) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
     launch_rank1(ctx, lp.Binv, lp.ld, m, m, lp.dcol, lp.prow, st, 0);
@@ -337,6 +428,11 @@ int ellp_b200_create(int device, ellp_b200_ctx** out) {
         return ELLP_E_CUDA;
     }
     std::memset(ctx->h_st, 0, sizeof(PivotState));
+    if (cudaFuncSetAttribute(k_select_primal, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(k_ratio_primal, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmemBytes) != cudaSuccess) {
+        ellp_b200_destroy(ctx);
+        return ELLP_E_CUDA;
+    }
     *out = ctx;
     return ELLP_OK;
 }
@@ -345,6 +441,7 @@ void ellp_b200_destroy(ellp_b200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->nccl_comm && nccl::api.CommDestroy) nccl::api.CommDestroy(ctx->nccl_comm);
     for (auto e : ctx->ev) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -385,6 +482,8 @@ int ellp_b200_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_poi
     lp.m = m;
     lp.n = n;
     lp.nN = n - m;
+    lp.n_glob = n;
+    lp.col_lo = 0;
     lp.ld = (int64_t)align_up((size_t)m, 4);
     int kc = std::max(64, (m + 63) / 64);
     kc = std::min(kc, kFtranMaxKc);
@@ -435,6 +534,7 @@ int ellp_b200_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_poi
     ctx->solver = solver;
     ctx->resident = true;
     ctx->tableau = tableau;
+    ctx->sharded = false;
     ctx->binv_valid = false;
     // host buffers are only borrowed for the duration of the call
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -448,6 +548,8 @@ int ellp_b200_generate_dense(ellp_b200_ctx* ctx, int32_t m, int32_t n_struct, ui
     lp.m = m;
     lp.n = n_struct + m;
     lp.nN = n_struct;
+    lp.n_glob = lp.n;
+    lp.col_lo = 0;
     lp.ld = m;
     int kc = std::min(kFtranMaxKc, std::max(64, (m + 63) / 64));
     const int KS = (m + kc - 1) / kc;
@@ -470,6 +572,7 @@ int ellp_b200_generate_dense(ellp_b200_ctx* ctx, int32_t m, int32_t n_struct, ui
     ctx->solver = ELLP_PRIMAL;
     ctx->resident = true;
     ctx->tableau = tableau;
+    ctx->sharded = false;
     ctx->binv_valid = false;
     ctx->dual_obj0 = 0.;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -484,13 +587,127 @@ int ellp_b200_download_std_form(ellp_b200_ctx* ctx, double* A, double* c, double
     const DevLP& lp = ctx->lp;
     cudaStream_t s = ctx->stream;
     if (A) CUDA_TRY(cudaMemcpy2DAsync(A, sizeof(double) * lp.m, lp.A, sizeof(double) * lp.ld, sizeof(double) * lp.m, lp.n, cudaMemcpyDeviceToHost, s));
-    if (c) CUDA_TRY(cudaMemcpyAsync(c, lp.c, sizeof(double) * lp.n, cudaMemcpyDeviceToHost, s));
+    if (c) CUDA_TRY(cudaMemcpyAsync(c, lp.c, sizeof(double) * lp.n_glob, cudaMemcpyDeviceToHost, s));
     if (b) CUDA_TRY(cudaMemcpyAsync(b, lp.b, sizeof(double) * lp.m, cudaMemcpyDeviceToHost, s));
-    if (kind) CUDA_TRY(cudaMemcpyAsync(kind, lp.kind, (size_t)lp.n, cudaMemcpyDeviceToHost, s));
-    if (lb) CUDA_TRY(cudaMemcpyAsync(lb, lp.lb, sizeof(double) * lp.n, cudaMemcpyDeviceToHost, s));
-    if (ub) CUDA_TRY(cudaMemcpyAsync(ub, lp.ub, sizeof(double) * lp.n, cudaMemcpyDeviceToHost, s));
+    if (kind) CUDA_TRY(cudaMemcpyAsync(kind, lp.kind, (size_t)lp.n_glob, cudaMemcpyDeviceToHost, s));
+    if (lb) CUDA_TRY(cudaMemcpyAsync(lb, lp.lb, sizeof(double) * lp.n_glob, cudaMemcpyDeviceToHost, s));
+    if (ub) CUDA_TRY(cudaMemcpyAsync(ub, lp.ub, sizeof(double) * lp.n_glob, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return ELLP_OK;
+}
+
+
+// ---- column sharding: one rank per GPU ---------------------------------------------------------------------------
+int ellp_b200_comm_unique_id(const char* nccl_path, void* out128) {
+    std::string err;
+    if (!out128 || !nccl::load(nccl_path, &err)) return ELLP_E_CUDA;
+    nccl::UniqueId id;
+    if (nccl::api.GetUniqueId(&id) != 0) return ELLP_E_CUDA;
+    std::memcpy(out128, id.internal, 128);
+    return ELLP_OK;
+}
+
+int ellp_b200_comm_init(ellp_b200_ctx* ctx, const char* nccl_path, const void* id128, int rank, int nranks) {
+    if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return ELLP_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    std::string err;
+    if (!nccl::load(nccl_path, &err)) return set_err(ctx, ELLP_E_CUDA, err);
+    nccl::UniqueId id;
+    std::memcpy(id.internal, id128, 128);
+    NCCL_TRY(nccl::api.CommInitRank(&ctx->nccl_comm, nranks, id, rank));
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    return ELLP_OK;
+}
+
+static int sharded_prepare(ellp_b200_ctx* ctx, int32_t m, int32_t n_glob, const ellp_opts* o, DevLP* out) {
+    if (!ctx->nccl_comm) return set_err(ctx, ELLP_E_ARG, "call ellp_b200_comm_init first");
+    if (n_glob % ctx->nranks != 0) return set_err(ctx, ELLP_E_ARG, "column sharding needs n divisible by the number of ranks");
+    if (m % 4 != 0) return set_err(ctx, ELLP_E_ARG, "column sharding needs m % 4 == 0");
+    DevLP lp{};
+    lp.m = m;
+    lp.n_glob = n_glob;
+    lp.n = n_glob / ctx->nranks;
+    lp.col_lo = ctx->rank * lp.n;
+    lp.nN = lp.n;
+    lp.ld = m;
+    const int64_t tcap = o->trace ? o->trace_cap : 0;
+    Arena probe;
+    carve(probe, lp, 1, tcap, true, true, ctx->nranks);
+    if (int rc = ensure_arena(ctx, probe.off + 256)) return rc;
+    Arena a;
+    a.base = ctx->arena;
+    carve(a, lp, 1, tcap, true, true, ctx->nranks, &ctx->sendcol, &ctx->d_sides);
+    CUDA_TRY(cudaMemsetAsync(lp.cB, 0, (size_t)((char*)lp.lam - (char*)lp.cB), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(lp.y, 0, sizeof(double) * lp.ld, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(lp.xchg, 0, sizeof(double) * (64 + 4 * (size_t)ctx->nranks), ctx->stream));
+    ctx->KS = 1;
+    ctx->kc = 64;
+    ctx->trace_cap = tcap;
+    ctx->solver = ELLP_PRIMAL;
+    ctx->tableau = true;
+    ctx->sharded = true;
+    ctx->dual_obj0 = 0.;
+    *out = lp;
+    return ELLP_OK;
+}
+
+static int sharded_finish_init(ellp_b200_ctx* ctx) {
+    // reduced-cost row of the local columns (the starting basis is the identity, so T = A)
+    DevLP& lp = ctx->lp;
+    LAUNCH(k_init_cB, (int)((lp.ld + 255) / 256), 256, lp);
+    LAUNCH(k_gemv_t<EPI_REDCOST>, gemv_grid(lp.n), 256, lp.T, lp.ld, (const int32_t*)nullptr, lp.n, lp.cB, lp.dj, lp.c + lp.col_lo,
+           (const uint8_t*)nullptr, (double*)nullptr, (PivotState*)nullptr, 0);
+    ctx->resident = true;
+    ctx->binv_valid = true;
+    ctx->pivots_since_refactor = 0;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaGetLastError());
+    return ELLP_OK;
+}
+
+int ellp_b200_sharded_generate_dense(ellp_b200_ctx* ctx, int32_t m, int32_t n_struct, uint64_t seed, const ellp_opts* o) {
+    if (!ctx || !o || m <= 0 || n_struct <= 0) return ELLP_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    DevLP lp{};
+    if (int rc = sharded_prepare(ctx, m, n_struct + m, o, &lp)) return rc;
+    LAUNCH(k_gen_dense_cols, 148 * 16, 256, const_cast<double*>(lp.A), lp.ld, m, (int64_t)n_struct, (int64_t)lp.col_lo,
+           (int64_t)(lp.col_lo + lp.n), seed);
+    LAUNCH(k_gen_dense_vectors, 148 * 2, 256, lp, (int64_t)n_struct, seed);
+    ctx->lp = lp;
+    return sharded_finish_init(ctx);
+}
+
+int ellp_b200_sharded_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_point* pt, const ellp_opts* o) {
+    if (!ctx || !sf || !pt || !o) return ELLP_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int m = sf->m, ng = sf->n;
+    if (pt->nB != m || pt->nN != ng - m) return set_err(ctx, ELLP_E_ARG, "sharded upload: B / N lengths do not match the standard form");
+    DevLP lp{};
+    if (int rc = sharded_prepare(ctx, m, ng, o, &lp)) return rc;
+    cudaStream_t s = ctx->stream;
+    // sf->A is THIS RANK's column block [col_lo, col_lo + n) (m x n, lda = m); the vectors are global
+    CUDA_TRY(cudaMemcpyAsync((void*)lp.A, sf->A, sizeof(double) * (size_t)m * lp.n, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync((void*)lp.c, sf->c, sizeof(double) * ng, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync((void*)lp.b, sf->b, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync((void*)lp.lb, sf->lb, sizeof(double) * ng, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync((void*)lp.ub, sf->ub, sizeof(double) * ng, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync((void*)lp.kind, sf->kind, (size_t)ng, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(lp.x, pt->x, sizeof(double) * ng, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(lp.Bv, pt->B, sizeof(int32_t) * m, cudaMemcpyHostToDevice, s));
+    std::vector<uint8_t> sides((size_t)ng, kColBasic);
+    for (int j = 0; j < pt->nN; ++j) sides[pt->N[j]] = pt->N_side[j];
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_sides, sides.data(), (size_t)ng, cudaMemcpyHostToDevice, s));
+    LAUNCH(k_shard_init, (lp.n + 255) / 256, 256, lp, ctx->d_sides);
+    ctx->lp = lp;
+    // the in-place tableau needs an identity starting basis: every rank checks the basis columns it owns
+    CUDA_TRY(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), s));
+    LAUNCH(k_check_identity_shard, m, 128, lp, ctx->d_flag);
+    int mismatch = 0;
+    CUDA_TRY(cudaMemcpyAsync(&mismatch, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (mismatch) return set_err(ctx, ELLP_E_ARG, "sharded tableau: the starting basis must be the identity (slack basis)");
+    return sharded_finish_init(ctx);
 }
 
 int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
@@ -520,19 +737,23 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
         if (int rc = refactor(ctx, &res->refactors)) return rc;
     }
     LAUNCH(k_init_cB, (int)((lp.ld + 255) / 256), 256, lp);
-    if (ctx->solver == ELLP_PRIMAL) LAUNCH(k_obj_dot, 1, 1024, lp.c, lp.x, lp.n, ctx->d_st);
+    if (ctx->solver == ELLP_PRIMAL) LAUNCH(k_obj_dot, 1, 1024, lp.c, lp.x, lp.n_glob, ctx->d_st);
     int check_every = o->check_every > 0 ? o->check_every : (lp.m >= 2048 ? 1 : 8);
     int refactor_every = o->refactor_every > 0 ? o->refactor_every : ((lp.m <= 512 && !ctx->tableau) ? 100 : 0);
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
     int rc_loop = ELLP_OK;
     while (h.status == kRunning) {
         int batch = check_every;
+        // never enqueue more iterations than the pivot budget still allows (they would be no-op launches)
+        if (o->max_iter - h.pivots < (uint64_t)batch) batch = (int)std::max<uint64_t>(1, o->max_iter - h.pivots);
         if (refactor_every > 0) batch = (int)std::min<uint64_t>(batch, std::max<uint64_t>(1, refactor_every - ctx->pivots_since_refactor));
         for (int k = 0; k < batch; ++k) {
-            if (ctx->tableau) launch_tableau_primal_iteration(ctx, o, profile, &ev_used);
+            if (ctx->sharded) { if ((rc_loop = launch_sharded_iteration(ctx, o, profile, &ev_used))) break; }
+            else if (ctx->tableau) launch_tableau_primal_iteration(ctx, o, profile, &ev_used);
             else if (ctx->solver == ELLP_PRIMAL) launch_primal_iteration(ctx, o, profile, &ev_used);
             else launch_dual_iteration(ctx, o, profile, &ev_used);
         }
+        if (rc_loop) break;
         const uint64_t before = h.pivots;
         if ((rc_loop = read_state(ctx))) break;
         ctx->pivots_since_refactor += h.pivots - before;
@@ -575,6 +796,18 @@ int ellp_b200_download(ellp_b200_ctx* ctx, ellp_point* pt) {
     CUDA_TRY(cudaSetDevice(ctx->device));
     DevLP& lp = ctx->lp;
     cudaStream_t s = ctx->stream;
+    if (ctx->sharded) {  // x and B are replicated; N is rebuilt from the gathered per-column status (ascending variable index)
+        CUDA_TRY(cudaMemcpyAsync(pt->x, lp.x, sizeof(double) * lp.n_glob, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(pt->B, lp.Bv, sizeof(int32_t) * lp.m, cudaMemcpyDeviceToHost, s));
+        NCCL_TRY(nccl::api.AllGather(lp.colstat, ctx->d_sides, (size_t)lp.n, nccl::kUint8, ctx->nccl_comm, s));
+        std::vector<uint8_t> sides((size_t)lp.n_glob);
+        CUDA_TRY(cudaMemcpyAsync(sides.data(), ctx->d_sides, (size_t)lp.n_glob, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        int k = 0;
+        for (int j = 0; j < lp.n_glob && k < pt->nN; ++j)
+            if (sides[j] != kColBasic) { pt->N[k] = j; pt->N_side[k] = sides[j]; ++k; }
+        return ELLP_OK;
+    }
     CUDA_TRY(cudaMemcpyAsync(pt->x, lp.x, sizeof(double) * lp.n, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(pt->B, lp.Bv, sizeof(int32_t) * lp.m, cudaMemcpyDeviceToHost, s));
     if (lp.nN > 0) {

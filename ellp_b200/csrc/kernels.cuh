@@ -52,7 +52,15 @@ struct DevLP {
     // tableau engine (ELLP_ENGINE_TABLEAU): T = B^-1 A lives in the buffer of A (in place), dj = reduced costs
     double* T;     // ld x n, nullptr for the revised engine
     double* dj;    // n
+    // column-sharded tableau: this rank stores global columns [col_lo, col_lo + n); x / kind / lb / ub / c are
+    // replicated with n_glob entries, Bv holds GLOBAL variable indices, colstat replaces the N list
+    int32_t n_glob;
+    int32_t col_lo;
+    uint8_t* colstat;  // n local entries: ELLP_NB_* or kColBasic; nullptr when not sharded
+    double* xchg;      // small exchange buffers: [0] local max key | [8..8+3) candidate | [16..16+G) gathered max | [32..32+3G) gathered candidates
 };
+
+constexpr uint8_t kColBasic = 3;
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -137,62 +145,88 @@ __global__ void __launch_bounds__(256) k_gemv_t(const double* __restrict__ M, in
 // sequential fold.  tie_rule 1 is the order-free form (max key, then largest variable index
 // within EPS of it).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_select_primal(const double* __restrict__ key, const double* __restrict__ rN,
-                                                      const int32_t* __restrict__ Nv, const uint8_t* __restrict__ Ns,
-                                                      int nN, int tie_rule, PivotState* st) {
+constexpr int kScanTile = 4096;                          // (value, tag) pairs per shared-memory tile
+constexpr int kScanSmemBytes = 2 * kScanTile * (8 + 4);  // double-buffered
+constexpr int kScanThreads = 1024;
+
+// Warps 1..31 stream (value, tag) tiles from global into shared memory while warp 0 folds the previous tile.
+__device__ __forceinline__ void scan_load_tile(const double* __restrict__ val, const int32_t* __restrict__ tag, int n, int tile,
+                                               double* sval, int* stag, int first_thread) {
+    const int base = tile * kScanTile;
+    for (int t = threadIdx.x - first_thread; t < kScanTile; t += kScanThreads - first_thread) {
+        const int i = base + t;
+        sval[t] = (i < n) ? __ldcg(val + i) : -1.0;
+        stag[t] = (i < n) ? __ldcg(tag + i) : 0;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_select_primal(const double* __restrict__ key, const double* __restrict__ rN,
+                                                                const int32_t* __restrict__ Nv, const uint8_t* __restrict__ Ns,
+                                                                int nN, int tie_rule, PivotState* st) {
     if (st->status != kRunning) return;
-    const int lane = threadIdx.x;
+    extern __shared__ __align__(16) unsigned char scan_smem[];
+    double* sval[2] = {reinterpret_cast<double*>(scan_smem), reinterpret_cast<double*>(scan_smem) + kScanTile};
+    int* stag[2] = {reinterpret_cast<int*>(scan_smem + 2 * kScanTile * 8), reinterpret_cast<int*>(scan_smem + 2 * kScanTile * 8) + kScanTile};
+    __shared__ double s_red[32];
+    __shared__ int s_redi[32], s_redp[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned full = 0xffffffffu;
     bool have = false;
     double bk = 0.;
     int bv = 0, bp = -1;
     if (tie_rule == ELLP_TIES_REFERENCE) {
-        constexpr int U = 4;
-        for (int base = 0; base < nN; base += 32 * U) {
-            double k[U];
-            int v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int j = base + u * 32 + lane;
-                k[u] = (j < nN) ? __ldcg(key + j) : -1.0;
-                v[u] = (j < nN) ? __ldcg(Nv + j) : 0;
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const bool cand = (k[u] != -1.0);
-                unsigned rem = __ballot_sync(full, cand);
-                while (rem) {
-                    bool eff = false;
-                    if (cand && ((rem >> lane) & 1u)) {
-                        if (!have) eff = true;
-                        else if (fabs(bk - k[u]) >= kEps) eff = (k[u] > bk);
-                        else eff = (v[u] > bv);
+        const int ntiles = (nN + kScanTile - 1) / kScanTile;
+        scan_load_tile(key, Nv, nN, 0, sval[0], stag[0], 0);
+        __syncthreads();
+        for (int t = 0; t < ntiles; ++t) {
+            if (warp == 0) {
+                const double* sk = sval[t & 1];
+                const int* sv = stag[t & 1];
+                for (int c = 0; c < kScanTile; c += 32) {
+                    const double k = sk[c + lane];
+                    const int v = sv[c + lane];
+                    const bool cand = (k != -1.0);
+                    unsigned rem = __ballot_sync(full, cand);
+                    while (rem) {
+                        bool eff = false;
+                        if (cand && ((rem >> lane) & 1u)) {
+                            if (!have) eff = true;
+                            else if (fabs(bk - k) >= kEps) eff = (k > bk);
+                            else eff = (v > bv);
+                        }
+                        const unsigned msk = __ballot_sync(full, eff);
+                        if (!msk) break;
+                        const int f = __ffs(msk) - 1;
+                        bk = __shfl_sync(full, k, f);
+                        bv = __shfl_sync(full, v, f);
+                        bp = t * kScanTile + c + f;
+                        have = true;
+                        rem &= (f == 31) ? 0u : (full << (f + 1));
                     }
-                    const unsigned msk = __ballot_sync(full, eff);
-                    if (!msk) break;
-                    const int f = __ffs(msk) - 1;
-                    bk = __shfl_sync(full, k[u], f);
-                    bv = __shfl_sync(full, v[u], f);
-                    bp = base + u * 32 + f;
-                    have = true;
-                    rem &= (f == 31) ? 0u : (full << (f + 1));
                 }
+            } else if (t + 1 < ntiles) {
+                scan_load_tile(key, Nv, nN, t + 1, sval[(t + 1) & 1], stag[(t + 1) & 1], 32);
             }
+            __syncthreads();
         }
     } else {
-        double kmax = -CUDART_INF;
-        for (int j = lane; j < nN; j += 32) {
-            const double k = __ldcg(key + j);
-            if (k != -1.0 && k > kmax) kmax = k;
-        }
+        // order-free rule: max key, then the largest variable index within EPS of it
+        double kmax = -1.0;
+        for (int j = tid; j < nN; j += kScanThreads) kmax = fmax(kmax, __ldcg(key + j));
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) kmax = fmax(kmax, __shfl_xor_sync(full, kmax, off));
+        if (lane == 0) s_red[warp] = kmax;
+        __syncthreads();
+        kmax = s_red[0];
+        for (int w = 1; w < 32; ++w) kmax = fmax(kmax, s_red[w]);
         int bestv = -1, bestp = -1;
-        for (int j = lane; j < nN; j += 32) {
-            const double k = __ldcg(key + j);
-            if (k != -1.0 && (kmax - k < kEps)) {
-                const int v = __ldcg(Nv + j);
-                if (v > bestv) { bestv = v; bestp = j; }
+        if (kmax != -1.0) {
+            for (int j = tid; j < nN; j += kScanThreads) {
+                const double k = __ldcg(key + j);
+                if (k != -1.0 && (kmax - k < kEps)) {
+                    const int v = __ldcg(Nv + j);
+                    if (v > bestv) { bestv = v; bestp = j; }
+                }
             }
         }
 #pragma unroll
@@ -200,10 +234,16 @@ __global__ void __launch_bounds__(32) k_select_primal(const double* __restrict__
             const int ov = __shfl_xor_sync(full, bestv, off), op = __shfl_xor_sync(full, bestp, off);
             if (ov > bestv) { bestv = ov; bestp = op; }
         }
-        bv = bestv;
-        bp = bestp;
+        if (lane == 0) { s_redi[warp] = bestv; s_redp[warp] = bestp; }
+        __syncthreads();
+        if (tid == 0) {
+            bv = -1;
+            bp = -1;
+            for (int w = 0; w < 32; ++w)
+                if (s_redp[w] >= 0 && s_redi[w] > bv) { bv = s_redi[w]; bp = s_redp[w]; }
+        }
     }
-    if (lane == 0) {
+    if (tid == 0) {
         if (bp < 0) {
             st->status = ELLP_OPTIMAL;  // primal :289-292
         } else {
@@ -327,9 +367,14 @@ __global__ void __launch_bounds__(1024) k_ratio_primal(DevLP lp, int KS, int tie
         lp.lam[i] = lam;
     }
     __syncthreads();
-    if (tid < 32) {
+    {
+        extern __shared__ __align__(16) unsigned char scan_smem[];
+        double* sval[2] = {reinterpret_cast<double*>(scan_smem), reinterpret_cast<double*>(scan_smem) + kScanTile};
+        int* stag[2] = {reinterpret_cast<int*>(scan_smem + 2 * kScanTile * 8), reinterpret_cast<int*>(scan_smem + 2 * kScanTile * 8) + kScanTile};
+        __shared__ double s_red[32];
+        __shared__ int s_redi[32], s_redp[32];
         const unsigned full = 0xffffffffu;
-        const int lane = tid;
+        const int lane = tid & 31, warp = tid >> 5;
         double lambda;
         {
             const int kq = lp.kind[q_var];  // :305-311
@@ -339,64 +384,81 @@ __global__ void __launch_bounds__(1024) k_ratio_primal(DevLP lp, int KS, int tie
         if (tie_rule == ELLP_TIES_REFERENCE) {
             bool have_nbi = false;
             int nbi = 0;
-            constexpr int U = 4;
-            for (int base = 0; base < m; base += 32 * U) {
-                double l[U];
-                int v[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int i = base + u * 32 + lane;
-                    l[u] = (i < m) ? lp.lam[i] : -1.0;
-                    v[u] = (i < m) ? lp.Bv[i] : 0;
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const bool cand = (l[u] != -1.0);
-                    unsigned rem = __ballot_sync(full, cand);
-                    while (rem) {
-                        int eff = 0;  // 1 strict (:379), 2 tie accepted (:387-399)
-                        if (cand && ((rem >> lane) & 1u)) {
-                            if (l[u] < lambda - kEps) eff = 1;
-                            else if (fabs(l[u] - lambda) < kEps && (!have_nbi || v[u] < nbi)) eff = 2;
+            const int ntiles = (m + kScanTile - 1) / kScanTile;
+            scan_load_tile(lp.lam, lp.Bv, m, 0, sval[0], stag[0], 0);
+            __syncthreads();
+            for (int t = 0; t < ntiles; ++t) {
+                if (warp == 0) {
+                    const double* sl = sval[t & 1];
+                    const int* sv = stag[t & 1];
+                    for (int c = 0; c < kScanTile; c += 32) {
+                        const double l = sl[c + lane];
+                        const int v = sv[c + lane];
+                        // lambda_i = +inf never changes the state (:379, :387), so it is not a candidate here
+                        const bool cand = (l != -1.0) && (l < CUDART_INF);
+                        unsigned rem = __ballot_sync(full, cand);
+                        while (rem) {
+                            int eff = 0;  // 1 strict (:379), 2 tie accepted (:387-399)
+                            if (cand && ((rem >> lane) & 1u)) {
+                                if (l < lambda - kEps) eff = 1;
+                                else if (fabs(l - lambda) < kEps && (!have_nbi || v < nbi)) eff = 2;
+                            }
+                            const unsigned msk = __ballot_sync(full, eff != 0);
+                            if (!msk) break;
+                            const int f = __ffs(msk) - 1;
+                            const int kind_f = __shfl_sync(full, eff, f);
+                            lambda = __shfl_sync(full, l, f);
+                            nb = t * kScanTile + c + f;
+                            if (kind_f == 2) { have_nbi = true; nbi = __shfl_sync(full, v, f); }
+                            rem &= (f == 31) ? 0u : (full << (f + 1));
                         }
-                        const unsigned msk = __ballot_sync(full, eff != 0);
-                        if (!msk) break;
-                        const int f = __ffs(msk) - 1;
-                        const int kind_f = __shfl_sync(full, eff, f);
-                        lambda = __shfl_sync(full, l[u], f);
-                        nb = base + u * 32 + f;
-                        if (kind_f == 2) { have_nbi = true; nbi = __shfl_sync(full, v[u], f); }
-                        rem &= (f == 31) ? 0u : (full << (f + 1));
                     }
+                } else if (t + 1 < ntiles) {
+                    scan_load_tile(lp.lam, lp.Bv, m, t + 1, sval[(t + 1) & 1], stag[(t + 1) & 1], 32);
                 }
+                __syncthreads();
             }
+            if (tid == 0) { s_lambda = lambda; s_nb = nb; }
         } else {
             double lmin = CUDART_INF;
-            for (int i = lane; i < m; i += 32) {
+            for (int i = tid; i < m; i += blockDim.x) {
                 const double l = lp.lam[i];
                 if (l != -1.0 && l < lmin) lmin = l;
             }
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) lmin = fmin(lmin, __shfl_xor_sync(full, lmin, off));
-            if (lmin < lambda + kEps && lmin < CUDART_INF) {
-                int bestv = 0x7fffffff, bestp = -1;
-                for (int i = lane; i < m; i += 32) {
+            if (lane == 0) s_red[warp] = lmin;
+            __syncthreads();
+            lmin = s_red[0];
+            for (int w = 1; w < 32; ++w) lmin = fmin(lmin, s_red[w]);
+            int bestv = 0x7fffffff, bestp = -1;
+            const bool basic_wins = (lmin < lambda + kEps && lmin < CUDART_INF);
+            if (basic_wins) {
+                for (int i = tid; i < m; i += blockDim.x) {
                     const double l = lp.lam[i];
                     if (l != -1.0 && (l - lmin < kEps)) {
                         const int v = lp.Bv[i];
                         if (v < bestv) { bestv = v; bestp = i; }
                     }
                 }
+            }
 #pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
-                    const int ov = __shfl_xor_sync(full, bestv, off), op = __shfl_xor_sync(full, bestp, off);
-                    if (ov < bestv) { bestv = ov; bestp = op; }
-                }
-                nb = bestp;
-                lambda = lp.lam[nb];
+            for (int off = 16; off >= 1; off >>= 1) {
+                const int ov = __shfl_xor_sync(full, bestv, off), op = __shfl_xor_sync(full, bestp, off);
+                if (ov < bestv) { bestv = ov; bestp = op; }
+            }
+            if (lane == 0) { s_redi[warp] = bestv; s_redp[warp] = bestp; }
+            __syncthreads();
+            if (tid == 0) {
+                bestv = 0x7fffffff;
+                bestp = -1;
+                for (int w = 0; w < 32; ++w)
+                    if (s_redp[w] >= 0 && s_redi[w] < bestv) { bestv = s_redi[w]; bestp = s_redp[w]; }
+                if (basic_wins && bestp >= 0) { nb = bestp; lambda = lp.lam[nb]; }
+                s_lambda = lambda;
+                s_nb = nb;
             }
         }
-        if (lane == 0) { s_lambda = lambda; s_nb = nb; }
     }
     __syncthreads();
     const double lambda = s_lambda;
@@ -426,20 +488,31 @@ __global__ void __launch_bounds__(1024) k_ratio_primal(DevLP lp, int KS, int tie
         if (nb >= 0) {  // :208-221
             const double a = lp.dcol[nb];
             const double d_nb = at_lower ? -a : a;
+            const uint8_t side_new = (d_nb > 0.) ? ELLP_NB_UPPER : ELLP_NB_LOWER;
             leave_var = lp.Bv[nb];
             lp.Bv[nb] = q_var;
-            lp.Nv[q_pos] = leave_var;
-            lp.Ns[q_pos] = (d_nb > 0.) ? ELLP_NB_UPPER : ELLP_NB_LOWER;
+            if (lp.colstat) {  // sharded: the owners of the two columns record the swap
+                if (q_var >= lp.col_lo && q_var < lp.col_lo + lp.n) lp.colstat[q_var - lp.col_lo] = kColBasic;
+                if (leave_var >= lp.col_lo && leave_var < lp.col_lo + lp.n) lp.colstat[leave_var - lp.col_lo] = side_new;
+            } else {
+                lp.Nv[q_pos] = leave_var;
+                lp.Ns[q_pos] = side_new;
+            }
             lp.cB[nb] = lp.c[q_var];
             st->r_pos = nb;
             st->leave_var = leave_var;
             st->alpha_r = a;
             st->do_update = 1;
         } else {  // :223-231 bound flip
-            const int side = lp.Ns[q_pos];
-            if (side == ELLP_NB_LOWER) lp.Ns[q_pos] = ELLP_NB_UPPER;
-            else if (side == ELLP_NB_UPPER) lp.Ns[q_pos] = ELLP_NB_LOWER;
+            const int side = st->q_side;
+            uint8_t flipped = ELLP_NB_FREE;
+            if (side == ELLP_NB_LOWER) flipped = ELLP_NB_UPPER;
+            else if (side == ELLP_NB_UPPER) flipped = ELLP_NB_LOWER;
             else { st->err = kErrFlipFree; st->status = ELLP_UNBOUNDED; }
+            if (flipped != ELLP_NB_FREE) {
+                if (lp.colstat) { if (q_var >= lp.col_lo && q_var < lp.col_lo + lp.n) lp.colstat[q_var - lp.col_lo] = flipped; }
+                else lp.Ns[q_pos] = flipped;
+            }
             st->r_pos = -1;
             st->do_update = 0;
         }
@@ -827,6 +900,127 @@ __global__ void k_price_tab(const double* __restrict__ dj, const int32_t* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
+// Column-sharded tableau (one rank per GPU).  Per pivot: local Dantzig keys -> all-gather of the local maxima ->
+// local candidate under the order-free rule (largest variable index within EPS of the GLOBAL maximum) ->
+// all-gather of the candidates -> every rank derives the same entering variable; its owner contributes the pivot
+// column to an all-reduce (the others contribute zeros) -> replicated ratio test -> local rank-1 update.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_price_shard(DevLP lp, PivotState* st) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->do_update = 0;
+    if (st->status != kRunning) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= lp.n) return;
+    const int side = lp.colstat[j];
+    double k = -1.0;
+    if (side != kColBasic) {
+        const double r = lp.dj[j];
+        if (!(fabs(r) < kEps)) {
+            if (r > 0. && side == ELLP_NB_UPPER) k = r;
+            else if (!(r > 0.) && side == ELLP_NB_LOWER) k = -r;
+            else if (side == ELLP_NB_FREE) k = fabs(r);
+        }
+    }
+    lp.key[j] = k;
+}
+
+__device__ __forceinline__ double block_max_1024(double v, double* s) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    v = (threadIdx.x < (blockDim.x >> 5)) ? s[threadIdx.x] : -1.0;
+    if (threadIdx.x < 32) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+        if (threadIdx.x == 0) s[0] = v;
+    }
+    __syncthreads();
+    return s[0];
+}
+
+__global__ void __launch_bounds__(1024) k_shard_local_max(DevLP lp, const PivotState* st) {
+    __shared__ double s[32];
+    if (st->status != kRunning) return;
+    double v = -1.0;
+    for (int j = threadIdx.x; j < lp.n; j += blockDim.x) v = fmax(v, lp.key[j]);
+    v = block_max_1024(v, s);
+    if (threadIdx.x == 0) lp.xchg[0] = v;
+}
+
+// xchg[16..16+G): gathered local maxima.  Candidate = largest local variable index with key > K* - EPS.
+__global__ void __launch_bounds__(1024) k_shard_pick(DevLP lp, int G, PivotState* st) {
+    __shared__ double s[32];
+    __shared__ int s_i[32];
+    if (st->status != kRunning) return;
+    double kmax = -1.0;
+    for (int g = 0; g < G; ++g) kmax = fmax(kmax, lp.xchg[16 + g]);
+    if (kmax == -1.0) {  // no candidate on any rank: optimal (primal :289-292); identical decision on every rank
+        __syncthreads();
+        if (threadIdx.x == 0) st->status = ELLP_OPTIMAL;
+        return;
+    }
+    int best = -1;
+    for (int j = threadIdx.x; j < lp.n; j += blockDim.x) {
+        const double k = lp.key[j];
+        if (k != -1.0 && (kmax - k < kEps)) best = max(best, j);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, off));
+    if ((threadIdx.x & 31) == 0) s_i[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = (threadIdx.x < (blockDim.x >> 5)) ? s_i[threadIdx.x] : -1;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, off));
+        if (threadIdx.x == 0) {
+            lp.xchg[8] = (best >= 0) ? (double)(lp.col_lo + best) : -1.0;
+            lp.xchg[9] = (best >= 0) ? lp.dj[best] : 0.;
+            lp.xchg[10] = (best >= 0) ? (double)lp.colstat[best] : 0.;
+        }
+    }
+    (void)s;
+}
+
+// xchg[32..32+3G): gathered candidates.  Every rank derives the same winner; the owner stages its pivot column.
+__global__ void k_shard_stage_column(DevLP lp, int G, PivotState* st, double* __restrict__ sendcol) {
+    if (st->status != kRunning) return;
+    double qv = -1.0, rq = 0., side = 0.;
+    for (int g = 0; g < G; ++g) {
+        const double v = lp.xchg[32 + 3 * g];
+        if (v > qv) { qv = v; rq = lp.xchg[32 + 3 * g + 1]; side = lp.xchg[32 + 3 * g + 2]; }
+    }
+    const int q_var = (int)qv;
+    const bool mine = (q_var >= lp.col_lo && q_var < lp.col_lo + lp.n);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < lp.ld) sendcol[i] = mine ? lp.T[(int64_t)(q_var - lp.col_lo) * lp.ld + i] : 0.;
+    if (i == 0) {
+        st->q_var = q_var;
+        st->q_pos = -1;
+        st->q_side = (int)side;
+        st->rq = rq;
+    }
+}
+
+// every rank checks the basis columns it owns: column Bv[i] must be e_i
+__global__ void k_check_identity_shard(DevLP lp, int* __restrict__ mismatch) {
+    const int i = blockIdx.x;
+    const int var = lp.Bv[i];
+    if (var < lp.col_lo || var >= lp.col_lo + lp.n) return;
+    const double* col = lp.T + (int64_t)(var - lp.col_lo) * lp.ld;
+    bool bad = false;
+    for (int k = threadIdx.x; k < lp.m; k += blockDim.x) {
+        const double want = (k == i) ? 1. : 0.;
+        if (col[k] != want) bad = true;
+    }
+    if (bad) *mismatch = 1;
+}
+
+__global__ void k_shard_init(DevLP lp, const uint8_t* __restrict__ side_of_var /* n_glob: ELLP_NB_* or kColBasic */) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < lp.n) lp.colstat[j] = side_of_var[lp.col_lo + j];
+}
+
+// ------------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------------
 __global__ void k_init_cB(DevLP lp) {
@@ -889,7 +1083,7 @@ __global__ void k_gen_dense_cols(double* __restrict__ A, int64_t ld, int m, int6
 }
 
 __global__ void k_gen_dense_vectors(DevLP lp, int64_t ns, uint64_t seed) {
-    const int m = lp.m, n = lp.n;
+    const int m = lp.m, n = lp.n_glob;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         double cj = 0., xj = 0.;
         if (j < ns) {
@@ -907,7 +1101,8 @@ __global__ void k_gen_dense_vectors(DevLP lp, int64_t ns, uint64_t seed) {
         const_cast<double*>(lp.ub)[j] = 0.;
         const_cast<uint8_t*>(lp.kind)[j] = ELLP_LOWER;
         lp.x[j] = xj;
-        if (j < ns) { lp.Nv[j] = (int32_t)j; lp.Ns[j] = ELLP_NB_LOWER; }
+        if (j < ns && lp.colstat == nullptr) { lp.Nv[j] = (int32_t)j; lp.Ns[j] = ELLP_NB_LOWER; }
+        if (lp.colstat != nullptr && j >= lp.col_lo && j < lp.col_lo + lp.n) lp.colstat[j - lp.col_lo] = (j < ns) ? (uint8_t)ELLP_NB_LOWER : kColBasic;
     }
     (void)m;
 }

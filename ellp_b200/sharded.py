@@ -1,0 +1,187 @@
+"""Column-sharded tableau: one process per GPU, launched with torchrun (reference config: BASELINE.json configs[4]).
+
+torch.distributed is only the plumbing (rendezvous, shipping the NCCL unique id, max-over-ranks of the timings);
+the per-pivot exchange -- two 8..24-byte all-gathers for the arg-select and one all-reduce that broadcasts the pivot
+column from its owner -- is issued by libellp_b200.so on its own stream through NCCL (include/ellp_b200.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import time
+from typing import Tuple
+
+import numpy as np
+
+from . import _native as N
+
+
+def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Global column range [lo, hi) stored by `rank` (equal blocks; n must be divisible by world)."""
+    if n % world != 0:
+        raise ValueError(f"column sharding needs n ({n}) divisible by the number of ranks ({world})")
+    w = n // world
+    return rank * w, (rank + 1) * w
+
+
+def owner_of(col: int, n: int, world: int) -> int:
+    return col // (n // world)
+
+
+def pick_entering(local_max_keys, candidates, eps: float = 1e-10):
+    """Host restatement of the device protocol (k_shard_pick / k_shard_stage_column), used by the CPU tests.
+
+    local_max_keys[g]: largest Dantzig key on rank g (-1 when it has no candidate).
+    candidates[g]: (var, rq, side) = rank g's largest variable index whose key is within eps of the GLOBAL maximum,
+    or (-1, 0, 0).  Returns (var, rq, side) of the entering variable or None when no rank has a candidate.
+    """
+    kmax = max(local_max_keys)
+    if kmax == -1.0:
+        return None
+    best = max(candidates, key=lambda c: c[0])
+    return best if best[0] >= 0 else None
+
+
+def nccl_library_path() -> str:
+    try:
+        import nvidia.nccl as pkg  # torch's bundled NCCL
+        p = os.path.join(os.path.dirname(pkg.__file__), "lib", "libnccl.so.2")
+        if os.path.exists(p):
+            return p
+    except Exception:
+        pass
+    return "libnccl.so.2"
+
+
+def init_comm(ctx: N.Context, rank: int, world: int):
+    """Creates the library's NCCL communicator; the 128-byte unique id travels over torch.distributed."""
+    import torch
+    import torch.distributed as dist
+    path = nccl_library_path().encode()
+    buf = (C.c_ubyte * 128)()
+    if rank == 0:
+        rc = N.lib.ellp_b200_comm_unique_id(path, C.cast(buf, C.c_void_p))
+        if rc != N.OK:
+            raise N.NativeError(rc, "ncclGetUniqueId failed")
+    t = torch.tensor(list(buf), dtype=torch.uint8)
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.broadcast(t, src=0)
+    raw = bytes(t.cpu().tolist())
+    idbuf = (C.c_ubyte * 128).from_buffer_copy(raw)
+    ctx.check(N.lib.ellp_b200_comm_init(ctx.h, path, C.cast(idbuf, C.c_void_p), rank, world))
+
+
+def bench_main(args, wl, name, METRIC, UNIT, SEED, ClockSampler, measured_peak, cpu_reference_sample):
+    """bench.py body for N > 1 (strong scaling: the same LP, columns split over the ranks)."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ["WORLD_SIZE"])
+    rank = int(os.environ["RANK"])
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = N.Context(local_rank)
+    init_comm(ctx, rank, world)
+    m, ns, P = wl["m"], wl["ns"], (args.pivots or wl["pivots"])
+    n = m + ns
+    lo, hi = shard_range(n, world, rank)
+    # order-free tie rule: the arg-select is a reduction over ranks
+    o = N.default_opts(P, engine=N.ENGINE_TABLEAU, tie_rule=N.TIES_CANONICAL, check_every=min(P, 16), profile=True)
+    ctx.check(N.lib.ellp_b200_sharded_generate_dense(ctx.h, m, ns, SEED, C.byref(o)))
+
+    def step():
+        res = N.Result()
+        ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(o), C.byref(res)))
+        assert res.status == N.MAXITER and res.iters == P, (res.status, res.iters)
+        return res
+
+    def barrier():
+        ctx.check(N.lib.ellp_b200_sync(ctx.h))
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = ctx.launch_count()
+    t0 = time.perf_counter()
+    dev_ms = rank1_ms = 0.0
+    n_rank1 = 0
+    for _ in range(args.steps):
+        r = step()
+        dev_ms += r.ms_device; rank1_ms += r.ms_rank1; n_rank1 += r.n_rank1
+    ctx.check(N.lib.ellp_b200_sync(ctx.h))
+    torch.cuda.synchronize()
+    dt_local = time.perf_counter() - t0
+    launches = ctx.launch_count() - launches0
+    clk = clocks.stop()
+    tt = torch.tensor([dt_local, dev_ms, rank1_ms / max(n_rank1, 1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt, dev_ms_max, k3_ms = [float(v) for v in tt.cpu()]
+    value = args.steps * P / dt
+
+    # e2e: every rank uploads ITS column block from pinned host memory, pivots, downloads the point
+    e2e = None
+    if not args.no_e2e:
+        nloc = hi - lo
+        A_h = torch.empty(m * nloc, dtype=torch.float64, pin_memory=True).numpy()
+        c_h = np.zeros(n); b_h = np.zeros(m); lb_h = np.zeros(n); ub_h = np.zeros(n); kind_h = np.zeros(n, dtype=np.uint8)
+        ctx.check(N.lib.ellp_b200_sharded_generate_dense(ctx.h, m, ns, SEED, C.byref(o)))
+        ctx.check(N.lib.ellp_b200_download_std_form(ctx.h, N.ptr(A_h), N.ptr(c_h), N.ptr(b_h), N.ptr(kind_h), N.ptr(lb_h), N.ptr(ub_h)))
+        x0 = np.zeros(n); x0[ns:] = b_h
+        B0 = np.arange(ns, n, dtype=np.int32); N0 = np.arange(ns, dtype=np.int32); Ns0 = np.zeros(ns, dtype=np.uint8)
+        sf = N.StdForm(m, n, N.ptr(A_h), N.ptr(c_h), N.ptr(b_h), N.ptr(kind_h), N.ptr(lb_h), N.ptr(ub_h))
+        oe = N.default_opts(P, engine=N.ENGINE_TABLEAU, tie_rule=N.TIES_CANONICAL, check_every=min(P, 16))
+
+        def e2e_step():
+            x, B, Nv, Ns = x0.copy(), B0.copy(), N0.copy(), Ns0.copy()
+            pt = N.Point(N.ptr(x), N.ptr(B), N.ptr(Nv), N.ptr(Ns), None, None, m, ns)
+            ctx.check(N.lib.ellp_b200_sharded_upload(ctx.h, C.byref(sf), C.byref(pt), C.byref(oe)))
+            res = N.Result()
+            ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(oe), C.byref(res)))
+            ctx.check(N.lib.ellp_b200_download(ctx.h, C.byref(pt)))
+            assert res.status == N.MAXITER and res.iters == P
+            return float(np.dot(c_h, x))
+
+        for _ in range(min(args.warmup, 3)):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            obj = e2e_step()
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dte = float(te.cpu()[0])
+        h2d = 8 * m * nloc + 8 * (3 * n + m) + n + 8 * n + 4 * m + n
+        d2h = 8 * n + 4 * m + n
+        e2e = {"value": args.steps * P / dte, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+               "ms_per_step": 1e3 * dte / args.steps, "api": "ellp_b200_sharded_upload + ellp_b200_run + ellp_b200_download (host buffers)",
+               "objective_after_step": obj}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        nloc = hi - lo
+        alg_bytes = 16.0 * m * nloc + 8.0 * (m + nloc)
+        achieved = alg_bytes / (k3_ms * 1e-3) / 1e9 if k3_ms > 0 else None
+        roofline = {"bound": "hbm", "kernel": "k_rank1<true> on the local column shard", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src, "ms_per_launch": k3_ms,
+                    "algorithmic_bytes_per_launch": alg_bytes, "note": "per GPU; max over ranks of the mean launch time"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": name, "m": m, "n": n, "pivots_per_step": P, "engine": "tableau, column-sharded",
+                           "columns_per_gpu": nloc, "tie_rule": "order-free (canonical)",
+                           "exchange": "2 x ncclAllGather (8 B, 24 B per rank) + 1 x ncclAllReduce (m doubles) per pivot",
+                           "l2": f"local shard {8.0 * m * nloc / 1e9:.2f} GB >> 126 MB L2"},
+                "device_ms_per_step": dev_ms_max / args.steps, "gpu_launches": int(launches) * world, "clocks": clk,
+                "roofline": roofline, "cpu_baseline": None, "e2e": e2e}
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()

@@ -142,6 +142,20 @@ int ellp_b200_download_std_form(ellp_b200_ctx*, double* A, double* c, double* b,
 /* tuning knobs: "rank1_cols_per_cta", "rank1_stream_min_mb" */
 int ellp_b200_set_tuning(ellp_b200_ctx*, const char* key, int value);
 
+/* ---- column-sharded tableau: one process per GPU (BASELINE.json configs[4]) ----------------------------------
+ * Rank g stores global columns [g*n/G, (g+1)*n/G) of the tableau and of the reduced-cost row; x, the basis list and
+ * the bounds are replicated.  Per pivot: local pricing, two tiny NCCL all-gathers (arg-select with the order-free
+ * tie rule), an NCCL all-reduce that broadcasts the pivot column from its owner, a replicated ratio test, and the
+ * local rank-1 update.  Requires n % G == 0, m % 4 == 0 and an identity (slack) starting basis.
+ * nccl_path: full path of libnccl.so.2 (may be NULL when the process already loaded it, e.g. through torch). */
+int ellp_b200_comm_unique_id(const char* nccl_path, void* out128);  /* rank 0; ship the 128 bytes to the other ranks */
+int ellp_b200_comm_init(ellp_b200_ctx*, const char* nccl_path, const void* id128, int rank, int nranks);
+int ellp_b200_sharded_generate_dense(ellp_b200_ctx*, int32_t m, int32_t n_struct, uint64_t seed, const ellp_opts* o);
+/* sf describes the GLOBAL standard form except that sf->A points at THIS RANK's column block (m x n/G, lda = m);
+ * pt is the global starting point.  Afterwards ellp_b200_run / ellp_b200_download work as in the single-GPU case
+ * (download rebuilds N in ascending variable order). */
+int ellp_b200_sharded_upload(ellp_b200_ctx*, const ellp_std_form* sf, const ellp_point* pt, const ellp_opts* o);
+
 /* ---- two-phase drivers: {Primal,Dual}SimplexSolver::solve ------------------------------------ */
 /* A Problem as built by Problem::add_var / add_constraint (src/problem.rs:19-106); constraints in
  * CSR over variable ids. */

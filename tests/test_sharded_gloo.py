@@ -1,0 +1,112 @@
+"""world_size-2 CPU test (gloo) of the N > 1 path's host logic: the column partition and the arg-select / pivot-column
+exchange protocol of the sharded tableau (ellp_b200/sharded.py), emulated on numpy shards and checked pivot for pivot
+against the oracle's order-free mode.  The CUDA kernels themselves are covered by tools/sharded_check.py on GPUs."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EPS = 1e-10
+
+
+def _worker(rank, world, port, m, ns, seed, K, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import bench_lp
+    from ellp_b200 import sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lp = bench_lp.dense_lp(m, ns, seed)
+    n = m + ns
+    lo, hi = sharded.shard_range(n, world, rank)
+    assert sharded.owner_of(lo, n, world) == rank and sharded.owner_of(hi - 1, n, world) == rank
+    T = lp["A"][:, lo:hi].copy()                       # local column block of the tableau (identity basis => T = A)
+    dj = lp["c"][lo:hi].copy()                         # local slice of the reduced-cost row (c_B = 0)
+    stat = np.where(np.arange(lo, hi) < ns, 0, 3).astype(np.uint8)  # 0 = at lower, 3 = basic
+    x, Bv = lp["x"].copy(), lp["B"].copy()
+    trace = []
+    for it in range(K):
+        key = np.where((stat == 0) & (dj < 0) & (np.abs(dj) >= EPS), -dj, -1.0)
+        kmax_loc = torch.tensor([key.max() if len(key) else -1.0], dtype=torch.float64)
+        g1 = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(g1, kmax_loc)
+        kmax = max(float(t) for t in g1)
+        cand = np.nonzero((key != -1.0) & (kmax - key < EPS))[0]
+        mine = (-1.0, 0.0, 0.0) if len(cand) == 0 else (float(lo + cand.max()), float(dj[cand.max()]), float(stat[cand.max()]))
+        g2 = [torch.zeros(3, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(g2, torch.tensor(mine, dtype=torch.float64))
+        win = sharded.pick_entering([float(t) for t in g1], [tuple(t.tolist()) for t in g2])
+        if win is None:
+            break
+        q, rq = int(win[0]), win[1]
+        col = torch.zeros(m, dtype=torch.float64)
+        if lo <= q < hi:
+            col = torch.from_numpy(T[:, q - lo].copy())
+        dist.all_reduce(col)                           # owner contributes the pivot column, the others zeros
+        alpha = col.numpy()
+        d = -alpha                                     # entering from its lower bound
+        lam = np.full(m, np.inf)
+        act = (np.abs(d) >= EPS) & (d < 0)
+        lam[act] = np.where(x[Bv[act]] > 0, (0 - x[Bv[act]]) / d[act], 0.0)
+        lmin = lam.min()
+        if not np.isfinite(lmin):
+            break
+        tie = np.nonzero(lam - lmin < EPS)[0]
+        r = tie[np.argmin(Bv[tie])]
+        lam_r = lam[r]
+        x[Bv] += lam_r * d
+        x[q] += lam_r
+        leave = int(Bv[r])
+        trace.append((q, leave))
+        prow = T[r, :] / alpha[r]
+        T -= np.outer(alpha, prow)
+        T[r, :] = prow
+        dj -= rq * prow
+        Bv[r] = q
+        if lo <= q < hi:
+            stat[q - lo] = 3
+        if lo <= leave < hi:
+            stat[leave - lo] = 0
+    ret[rank] = (trace, x, Bv)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("m,ns,seed,K", [(16, 48, 1, 40), (32, 96, 2, 60)])
+def test_sharded_protocol_matches_oracle_world2(m, ns, seed, K):
+    sys.path.insert(0, ROOT)
+    import bench_lp
+    from oracle import binding as O
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + (os.getpid() % 400)
+    mp.spawn(_worker, args=(world, port, m, ns, seed, K, ret), nprocs=world, join=True)
+    lp = bench_lp.dense_lp(m, ns, seed)
+    xo, Bo = lp["x"].copy(), lp["B"].copy()
+    ref = O.solve_with_initial(O.PRIMAL, m, m + ns, lp["A"], lp["c"], lp["b"], lp["kind"], lp["lb"], lp["ub"], xo, Bo,
+                               lp["N"].copy(), lp["N_side"].copy(), max_iter=K, mode=O.MODE_CANONICAL, trace_cap=K)
+    want = list(zip(ref.trace["entering"].tolist(), ref.trace["leaving"].tolist()))
+    for rank in range(world):
+        trace, x, Bv = ret[rank]
+        assert trace == want
+        np.testing.assert_array_equal(Bv, Bo)
+        np.testing.assert_allclose(x, xo, rtol=1e-9, atol=1e-9)
+
+
+def test_shard_range_partition():
+    from ellp_b200 import sharded
+    for world in (1, 2, 4, 8):
+        covered = []
+        for r in range(world):
+            lo, hi = sharded.shard_range(65536, world, r)
+            covered += [(lo, hi)]
+        assert covered[0][0] == 0 and covered[-1][1] == 65536
+        assert all(covered[i][1] == covered[i + 1][0] for i in range(world - 1))
+    with pytest.raises(ValueError):
+        sharded.shard_range(10, 4, 0)

@@ -1,0 +1,66 @@
+"""Run under torchrun with N ranks (one GPU each): the column-sharded tableau must pivot exactly like the oracle
+(order-free tie rule) and finish with the same point.  Prints SHARDED_CHECK_OK on rank 0."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench_lp  # noqa: E402
+from ellp_b200 import _native as N  # noqa: E402
+from ellp_b200 import sharded  # noqa: E402
+from oracle import binding as O  # noqa: E402
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+local = int(os.environ.get("LOCAL_RANK", rank))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ctx = N.Context(local)
+sharded.init_comm(ctx, rank, world)
+ok = True
+for (m, ns, seed, K) in [(64, 192, 3, 10**6), (256, 768, 4, 300)]:
+    n = m + ns
+    o = N.default_opts(K, engine=N.ENGINE_TABLEAU, tie_rule=N.TIES_CANONICAL, check_every=8)
+    tr = np.zeros(20000, dtype=N.TRACE_DTYPE); o.trace = N.ptr(tr); o.trace_cap = len(tr)
+    # (1) generated in HBM, sharded
+    ctx.check(N.lib.ellp_b200_sharded_generate_dense(ctx.h, m, ns, seed, C.byref(o)))
+    res = N.Result()
+    ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(o), C.byref(res)))
+    lp = bench_lp.dense_lp(m, ns, seed)
+    x, B, Nv, Ns = lp["x"].copy(), lp["B"].copy(), lp["N"].copy(), lp["N_side"].copy()
+    pt = N.Point(N.ptr(x), N.ptr(B), N.ptr(Nv), N.ptr(Ns), None, None, m, ns)
+    ctx.check(N.lib.ellp_b200_download(ctx.h, C.byref(pt)))
+    xo, Bo, No, Nso = lp["x"].copy(), lp["B"].copy(), lp["N"].copy(), lp["N_side"].copy()
+    ref = O.solve_with_initial(O.PRIMAL, m, n, lp["A"], lp["c"], lp["b"], lp["kind"], lp["lb"], lp["ub"], xo, Bo, No, Nso,
+                               max_iter=K, mode=O.MODE_CANONICAL, trace_cap=20000)
+    k = len(ref.trace)
+    good = (res.status == ref.status and res.iters == k and (tr["entering"][:k] == ref.trace["entering"]).all()
+            and (tr["leaving"][:k] == ref.trace["leaving"]).all() and np.array_equal(B, Bo)
+            and np.allclose(x, xo, rtol=1e-9, atol=1e-9) and set(Nv.tolist()) == set(No.tolist()))
+    # (2) the same LP uploaded from host buffers, each rank passing ITS column block
+    lo, hi = sharded.shard_range(n, world, rank)
+    Aloc = np.asfortranarray(lp["A"][:, lo:hi])
+    sf = N.StdForm(m, n, N.ptr(Aloc), N.ptr(lp["c"]), N.ptr(lp["b"]), N.ptr(lp["kind"]), N.ptr(lp["lb"]), N.ptr(lp["ub"]))
+    x2, B2, N2, Ns2 = lp["x"].copy(), lp["B"].copy(), lp["N"].copy(), lp["N_side"].copy()
+    pt2 = N.Point(N.ptr(x2), N.ptr(B2), N.ptr(N2), N.ptr(Ns2), None, None, m, ns)
+    tr2 = np.zeros(20000, dtype=N.TRACE_DTYPE); o.trace = N.ptr(tr2)
+    ctx.check(N.lib.ellp_b200_sharded_upload(ctx.h, C.byref(sf), C.byref(pt2), C.byref(o)))
+    res2 = N.Result()
+    ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(o), C.byref(res2)))
+    ctx.check(N.lib.ellp_b200_download(ctx.h, C.byref(pt2)))
+    good2 = (res2.iters == k and (tr2["entering"][:k] == ref.trace["entering"]).all() and np.array_equal(B2, Bo)
+             and np.allclose(x2, xo, rtol=1e-9, atol=1e-9))
+    print(f"rank {rank}: m={m} n={n} pivots={res.iters} oracle={k} status={res.status}/{ref.status} generated_ok={good} uploaded_ok={good2}", flush=True)
+    ok = ok and good and good2
+flag = torch.tensor([1 if ok else 0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0 and int(flag.item()) == 1:
+    print("SHARDED_CHECK_OK", flush=True)
+dist.barrier()
+ctx.close()
+dist.destroy_process_group()
+sys.exit(0 if int(flag.item()) == 1 else 1)
