@@ -232,7 +232,7 @@ def run_ours(args, wl, name):
 
     cpu = None
     if not args.no_cpu:
-        v, dtc, sample = cpu_reference_sample(wl, max(6, wl["sample_pivots"] * 4))
+        v, dtc, sample = cpu_reference_sample(wl, max(6, wl["sample_pivots"] * 20))
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample, "seconds": dtc,
                "host_cores_available": os.cpu_count()}
 
