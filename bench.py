@@ -35,6 +35,9 @@ WORKLOADS = {
     # north_star target size: "for a 16384x32768 dense LP, the row-reduction kernel sustains >= 70% of HBM bandwidth"
     "dense_tableau_16384x32768": dict(m=16384, ns=16384, pivots=40, sample_m=1024, sample_pivots=3),
     "dense_tableau_4096x12288": dict(m=4096, ns=8192, pivots=200, sample_m=512, sample_pivots=6),
+    # BASELINE.json configs[2] shape: dense 4096x8192 (Gte rows => standard form 4096x12288), DUAL simplex, revised engine
+    # (explicit basis inverse).  The entering/leaving rules are the reference's (steepest edge is not built yet).
+    "dense_revised_dual_4096x12288": dict(m=4096, ns=8192, pivots=200, sample_m=512, sample_pivots=6, dual=True),
     "dense_tableau_tiny": dict(m=256, ns=256, pivots=20, sample_m=128, sample_pivots=4),
 }
 DEFAULT_WORKLOAD = "dense_tableau_32768x65536"
@@ -96,11 +99,12 @@ def cpu_reference_sample(wl: dict, pivots: int):
     from oracle import binding as O
     ms = wl["sample_m"]
     ratio = wl["ns"] / wl["m"]
-    lp = bench_lp.dense_lp(ms, int(ms * ratio), SEED)
+    dual = bool(wl.get("dual"))
+    lp = bench_lp.dense_lp(ms, int(ms * ratio), SEED, 1 if dual else 0)
     O.lib()
     t0 = time.perf_counter()
-    r = O.solve_with_initial(O.PRIMAL, lp["m"], lp["n"], lp["A"], lp["c"], lp["b"], lp["kind"], lp["lb"], lp["ub"], lp["x"],
-                             lp["B"], lp["N"], lp["N_side"], max_iter=pivots)
+    r = O.solve_with_initial(O.DUAL if dual else O.PRIMAL, lp["m"], lp["n"], lp["A"], lp["c"], lp["b"], lp["kind"], lp["lb"],
+                             lp["ub"], lp["x"], lp["B"], lp["N"], lp["N_side"], lp.get("y"), lp.get("d"), max_iter=pivots)
     dt = time.perf_counter() - t0
     assert r.status == O.MAXITER, r.status_name
     return pivots / dt, dt, f"{pivots} pivots of the same generator at {lp['m']}x{lp['n']} (a full-size pivot needs a " \
@@ -144,8 +148,10 @@ def run_ours(args, wl, name):
     ctx = N.Context(local_rank)
     m, ns, P = wl["m"], wl["ns"], (args.pivots or wl["pivots"])
     n = m + ns
-    o = N.default_opts(P, engine=N.ENGINE_TABLEAU, check_every=min(P, 16), profile=True)
-    ctx.check(N.lib.ellp_b200_generate_dense(ctx.h, m, ns, SEED, C.byref(o)))
+    dual = bool(wl.get("dual"))
+    engine = N.ENGINE_REVISED if dual else N.ENGINE_TABLEAU
+    o = N.default_opts(P, engine=engine, check_every=min(P, 16), profile=True)
+    ctx.check(N.lib.ellp_b200_generate_dense_ex(ctx.h, m, ns, SEED, 1 if dual else 0, C.byref(o)))
 
     def step():
         res = N.Result()
@@ -175,7 +181,8 @@ def run_ours(args, wl, name):
 
     # roofline of the dominant kernel (K3 rank-1 update of the m x n tableau): algorithmic bytes per launch
     peak, peak_src = measured_peak()
-    alg_bytes = 16.0 * m * n + 8.0 * (m + n)
+    k3_cols = m if dual else n  # revised engine: K3 updates the m x m basis inverse; tableau engine: the m x n tableau
+    alg_bytes = 16.0 * m * k3_cols + 8.0 * (m + k3_cols)
     k3_ms = rank1_ms / max(n_rank1, 1)
     achieved = alg_bytes / (k3_ms * 1e-3) / 1e9 if n_rank1 else None
     traffic = None
@@ -184,7 +191,7 @@ def run_ours(args, wl, name):
             traffic = json.load(f).get(name)
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_rank1<true> (rank-1 tableau row reduction)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "k_rank1 (rank-1 row reduction of the %s)" % ("basis inverse" if dual else "tableau"), "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "frac_of_8TBs_nominal": (achieved / 8000.0) if achieved else None,
                 "traffic": traffic, "peak_source": peak_src, "ms_per_launch": k3_ms, "launches_timed": n_rank1,
                 "algorithmic_bytes_per_launch": alg_bytes, "share_of_step_device_time": (rank1_ms / dev_ms) if dev_ms else None}
@@ -197,21 +204,24 @@ def run_ours(args, wl, name):
         c_h, b_h, lb_h, ub_h, x0 = small[:n], small[n:n + m], small[n + m:2 * n + m], small[2 * n + m:3 * n + m], small[3 * n + m:4 * n + m]
         kind_h = np.zeros(n, dtype=np.uint8)
         A_np = A_h.numpy()
-        ctx.check(N.lib.ellp_b200_generate_dense(ctx.h, m, ns, SEED, C.byref(o)))
+        ctx.check(N.lib.ellp_b200_generate_dense_ex(ctx.h, m, ns, SEED, 1 if dual else 0, C.byref(o)))
         ctx.check(N.lib.ellp_b200_download_std_form(ctx.h, N.ptr(A_np), N.ptr(c_h), N.ptr(b_h), N.ptr(kind_h), N.ptr(lb_h), N.ptr(ub_h)))
         x0[:] = 0.0
-        x0[ns:] = b_h
+        x0[ns:] = -b_h if dual else b_h
+        y0 = np.zeros(m); d0 = c_h.copy()
         B0 = np.arange(ns, n, dtype=np.int32); N0 = np.arange(ns, dtype=np.int32); Ns0 = np.zeros(ns, dtype=np.uint8)
         sf = N.StdForm(m, n, N.ptr(A_np), N.ptr(c_h), N.ptr(b_h), N.ptr(kind_h), N.ptr(lb_h), N.ptr(ub_h))
-        oe = N.default_opts(P, engine=N.ENGINE_TABLEAU, check_every=min(P, 16))
+        oe = N.default_opts(P, engine=engine, check_every=min(P, 16))
         xs = torch.empty(n, dtype=torch.float64, pin_memory=True).numpy()
 
         def e2e_step():
             xs[:] = x0
             B, Nv, Ns = B0.copy(), N0.copy(), Ns0.copy()
-            pt = N.Point(N.ptr(xs), N.ptr(B), N.ptr(Nv), N.ptr(Ns), None, None, m, ns)
+            y, d = y0.copy(), d0.copy()
+            pt = N.Point(N.ptr(xs), N.ptr(B), N.ptr(Nv), N.ptr(Ns), N.ptr(y) if dual else None, N.ptr(d) if dual else None, m, ns)
             res = N.Result()
-            ctx.check(N.lib.ellp_b200_primal_solve_with_initial(ctx.h, C.byref(sf), C.byref(pt), C.byref(oe), C.byref(res)))
+            fn = N.lib.ellp_b200_dual_solve_with_initial if dual else N.lib.ellp_b200_primal_solve_with_initial
+            ctx.check(fn(ctx.h, C.byref(sf), C.byref(pt), C.byref(oe), C.byref(res)))
             assert res.status == N.MAXITER and res.iters == P
             return res.obj
 
@@ -226,7 +236,7 @@ def run_ours(args, wl, name):
         h2d = 8 * m * n + 8 * (3 * n + m) + n + 8 * n + 4 * m + 4 * ns + ns
         d2h = 8 * n + 4 * m + 4 * ns + ns + 120 * ((P + 15) // 16)
         e2e = {"value": args.steps * P / dte, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": 1e3 * dte / args.steps, "api": "ellp_b200_primal_solve_with_initial (host buffers, pinned)",
+               "ms_per_step": 1e3 * dte / args.steps, "api": "ellp_b200_%s_solve_with_initial (host buffers, pinned)" % ("dual" if dual else "primal"),
                "objective_after_step": obj}
         del A_h
 
@@ -239,8 +249,9 @@ def run_ours(args, wl, name):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "m": m, "n": n, "pivots_per_step": P, "engine": "tableau (B^-1 A resident, in place)",
-                       "tie_rule": "reference folds", "l2": f"tableau {8.0 * m * n / 1e9:.1f} GB >> 126 MB L2 (no flush needed)",
+            "config": {"workload": name, "m": m, "n": n, "pivots_per_step": P, "engine": "revised (explicit B^-1), dual simplex" if dual else "tableau (B^-1 A resident, in place)",
+                       "tie_rule": "reference folds", "l2": (f"A_N {8.0 * m * ns / 1e6:.0f} MB + B^-1 {8.0 * m * m / 1e6:.0f} MB streamed every pivot (> 126 MB L2, no flush)" if dual
+                              else f"tableau {8.0 * m * n / 1e9:.1f} GB >> 126 MB L2 (no flush needed)"),
                        "baseline_config": "BASELINE.json configs[4]" if name == DEFAULT_WORKLOAD else "north_star / smaller variant"},
             "device_ms_per_step": dev_ms / args.steps, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
             "cpu_baseline": cpu, "e2e": e2e}

@@ -23,7 +23,18 @@ def _uniform01(seed, idx):
     return (h >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
 
 
-def dense_lp(m: int, ns: int, seed: int) -> dict:
+def dense_lp(m: int, ns: int, seed: int, variant: int = 0) -> dict:
+    """variant 0: min -c.x, Ax + s = b (primal-feasible slack basis); variant 1: min c.x, Ax - s = b (dual-feasible)."""
+    if variant == 1:
+        lp = dense_lp(m, ns, seed, 0)
+        lp["A"][:, ns:] = 0.0  # off-diagonal zeros are +0.0 on the device, so do not negate an identity
+        np.fill_diagonal(lp["A"][:, ns:], -1.0)
+        lp["c"] = -lp["c"]
+        lp["c"][ns:] = 0.0
+        lp["x"][ns:] = -lp["b"]
+        lp["y"] = np.zeros(m)
+        lp["d"] = lp["c"].copy()
+        return lp
     n = ns + m
     A = np.zeros((m, n), order="F")
     idx = np.arange(m * ns, dtype=np.uint64)

@@ -40,6 +40,9 @@ struct PivotState {
     double delta;       // dual: x_r - violated bound
     double theta_d;     // dual step
     double rq;          // primal: reduced cost of the entering variable
+    long long lmin_bits; // primal ratio test: min finite ratio of this iteration (bits of a non-negative double; atomicMin)
+    int32_t do_step;    // 1 when x moves in this iteration (lambda > 0)
+    int32_t step_pad;
     int64_t trace_len;
     int64_t trace_cap;
     // Gauss-Jordan refactorisation scratch

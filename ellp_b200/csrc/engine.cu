@@ -286,8 +286,9 @@ void launch_tableau_primal_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, boo
     const int m = lp.m, nN = lp.nN, n = lp.n;
     LAUNCH(k_price_tab, (nN + 255) / 256, 256, lp.dj, lp.Nv, lp.Ns, nN, lp.rN, lp.key, st);     // primal :189, :253-270
     LAUNCH_SMEM(k_select_primal, 1, kScanThreads, kScanSmemBytes, lp.key, lp.rN, lp.Nv, lp.Ns, nN, o->tie_rule, st);           // :271-292
-    LAUNCH_SMEM(k_ratio_primal, 1, kScanThreads, kScanSmemBytes, lp, 0, o->tie_rule, st);                                    // :295-434, :205-232
-    LAUNCH(k_gather_row, (n + 255) / 256, 256, lp.T, lp.ld, n, st, lp.prow, 1);
+    LAUNCH(k_ratio_prep, (m + 255) / 256, 256, lp, 0, st);                                       // :295-367
+    LAUNCH_SMEM(k_ratio_pick, 1, kScanThreads, kScanSmemBytes, lp, o->tie_rule, st);             // :379-434, :205-232
+    LAUNCH(k_step_gather, (std::max(m, n) + 255) / 256, 256, lp, lp.T, n, st);                   // :408-417 + pivot row
     if (profile && *ev_used + 2 <= ctx->ev.size()) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
     launch_rank1(ctx, lp.T, lp.ld, m, n, lp.dcol, lp.prow, st, 0, lp.dj);
     if (profile && (*ev_used & 1)) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
@@ -305,8 +306,9 @@ int launch_sharded_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, bool profil
     NCCL_TRY(nccl::api.AllGather(lp.xchg + 8, lp.xchg + 32, 3, nccl::kFloat64, ctx->nccl_comm, ctx->stream));
     LAUNCH(k_shard_stage_column, (int)((lp.ld + 255) / 256), 256, lp, G, st, ctx->sendcol);
     NCCL_TRY(nccl::api.AllReduce(ctx->sendcol, lp.dcol, (size_t)lp.ld, nccl::kFloat64, nccl::kSum, ctx->nccl_comm, ctx->stream));
-    LAUNCH_SMEM(k_ratio_primal, 1, kScanThreads, kScanSmemBytes, lp, -1, o->tie_rule, st);
-    LAUNCH(k_gather_row, (n + 255) / 256, 256, lp.T, lp.ld, n, st, lp.prow, 1);
+    LAUNCH(k_ratio_prep, (m + 255) / 256, 256, lp, -1, st);
+    LAUNCH_SMEM(k_ratio_pick, 1, kScanThreads, kScanSmemBytes, lp, o->tie_rule, st);
+    LAUNCH(k_step_gather, (std::max(m, n) + 255) / 256, 256, lp, lp.T, n, st);
     if (profile && *ev_used + 2 <= ctx->ev.size()) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
     launch_rank1(ctx, lp.T, lp.ld, m, n, lp.dcol, lp.prow, st, 0, lp.dj);
     if (profile && (*ev_used & 1)) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
@@ -326,8 +328,9 @@ void launch_primal_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, bool profil
     // FTRAN d = B^-1 a_q  (primal :295)
     dim3 fg((unsigned)((lp.ld + 255) / 256), (unsigned)ctx->KS);
     LAUNCH(k_ftran_partial, fg, 128, lp.Binv, lp.ld, m, lp.A, st, lp.part, ctx->kc);
-    LAUNCH_SMEM(k_ratio_primal, 1, kScanThreads, kScanSmemBytes, lp, ctx->KS, o->tie_rule, st);
-    LAUNCH(k_gather_row, (m + 255) / 256, 256, lp.Binv, lp.ld, m, st, lp.prow, 1);
+    LAUNCH(k_ratio_prep, (m + 255) / 256, 256, lp, ctx->KS, st);
+    LAUNCH_SMEM(k_ratio_pick, 1, kScanThreads, kScanSmemBytes, lp, o->tie_rule, st);
+    LAUNCH(k_step_gather, (m + 255) / 256, 256, lp, lp.Binv, m, st);
     if (profile && *ev_used + 2 <= ctx->ev.size()) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
     launch_rank1(ctx, lp.Binv, lp.ld, m, m, lp.dcol, lp.prow, st, 0);
     if (profile && (*ev_used & 1)) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
@@ -429,7 +432,7 @@ int ellp_b200_create(int device, ellp_b200_ctx** out) {
     }
     std::memset(ctx->h_st, 0, sizeof(PivotState));
     if (cudaFuncSetAttribute(k_select_primal, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(k_ratio_primal, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmemBytes) != cudaSuccess) {
+        cudaFuncSetAttribute(k_ratio_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmemBytes) != cudaSuccess) {
         ellp_b200_destroy(ctx);
         return ELLP_E_CUDA;
     }
@@ -542,7 +545,12 @@ int ellp_b200_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_poi
 }
 
 int ellp_b200_generate_dense(ellp_b200_ctx* ctx, int32_t m, int32_t n_struct, uint64_t seed, const ellp_opts* o) {
-    if (!ctx || !o || m <= 0 || n_struct <= 0 || (m % 4) != 0) return set_err(ctx, ELLP_E_ARG, "generate_dense needs m % 4 == 0");
+    return ellp_b200_generate_dense_ex(ctx, m, n_struct, seed, 0, o);
+}
+
+int ellp_b200_generate_dense_ex(ellp_b200_ctx* ctx, int32_t m, int32_t n_struct, uint64_t seed, int32_t variant, const ellp_opts* o) {
+    if (!ctx || !o || m <= 0 || n_struct <= 0 || (m % 4) != 0 || variant < 0 || variant > 1)
+        return set_err(ctx, ELLP_E_ARG, "generate_dense needs m % 4 == 0 and variant in {0,1}");
     CUDA_TRY(cudaSetDevice(ctx->device));
     DevLP lp{};
     lp.m = m;
@@ -555,6 +563,7 @@ int ellp_b200_generate_dense(ellp_b200_ctx* ctx, int32_t m, int32_t n_struct, ui
     const int KS = (m + kc - 1) / kc;
     const int64_t tcap = o->trace ? o->trace_cap : 0;
     const bool tableau = o->engine == ELLP_ENGINE_TABLEAU;
+    if (tableau && variant == 1) return set_err(ctx, ELLP_E_ARG, "the dual variant needs ELLP_ENGINE_REVISED");
     Arena probe;
     carve(probe, lp, KS, tcap, tableau);
     if (int rc = ensure_arena(ctx, probe.off + 256)) return rc;
@@ -563,18 +572,19 @@ int ellp_b200_generate_dense(ellp_b200_ctx* ctx, int32_t m, int32_t n_struct, ui
     carve(a, lp, KS, tcap, tableau);
     CUDA_TRY(cudaMemsetAsync(lp.cB, 0, (size_t)((char*)lp.lam - (char*)lp.cB), ctx->stream));
     CUDA_TRY(cudaMemsetAsync(lp.y, 0, sizeof(double) * lp.ld, ctx->stream));
-    LAUNCH(k_gen_dense_cols, 148 * 16, 256, const_cast<double*>(lp.A), lp.ld, m, (int64_t)n_struct, (int64_t)0, (int64_t)lp.n, seed);
-    LAUNCH(k_gen_dense_vectors, 148 * 2, 256, lp, (int64_t)n_struct, seed);
+    LAUNCH(k_gen_dense_cols, 148 * 16, 256, const_cast<double*>(lp.A), lp.ld, m, (int64_t)n_struct, (int64_t)0, (int64_t)lp.n, seed,
+           variant == 0 ? 1.0 : -1.0);
+    LAUNCH(k_gen_dense_vectors, 148 * 2, 256, lp, (int64_t)n_struct, seed, (int)variant);
     ctx->lp = lp;
     ctx->KS = KS;
     ctx->kc = kc;
     ctx->trace_cap = tcap;
-    ctx->solver = ELLP_PRIMAL;
+    ctx->solver = variant == 0 ? ELLP_PRIMAL : ELLP_DUAL;
     ctx->resident = true;
     ctx->tableau = tableau;
     ctx->sharded = false;
     ctx->binv_valid = false;
-    ctx->dual_obj0 = 0.;
+    ctx->dual_obj0 = 0.;  // y = 0 and every bound is Lower(0): dual_obj(y, d) = 0
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(cudaGetLastError());
     return ELLP_OK;
@@ -672,8 +682,8 @@ int ellp_b200_sharded_generate_dense(ellp_b200_ctx* ctx, int32_t m, int32_t n_st
     DevLP lp{};
     if (int rc = sharded_prepare(ctx, m, n_struct + m, o, &lp)) return rc;
     LAUNCH(k_gen_dense_cols, 148 * 16, 256, const_cast<double*>(lp.A), lp.ld, m, (int64_t)n_struct, (int64_t)lp.col_lo,
-           (int64_t)(lp.col_lo + lp.n), seed);
-    LAUNCH(k_gen_dense_vectors, 148 * 2, 256, lp, (int64_t)n_struct, seed);
+           (int64_t)(lp.col_lo + lp.n), seed, 1.0);
+    LAUNCH(k_gen_dense_vectors, 148 * 2, 256, lp, (int64_t)n_struct, seed, 0);
     ctx->lp = lp;
     return sharded_finish_init(ctx);
 }
@@ -724,6 +734,7 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
     h.phase_tag = o->phase_tag;
     h.trace_cap = (o->trace && lp.trace) ? std::min<int64_t>(o->trace_cap, ctx->trace_cap) : 0;
     h.obj = ctx->dual_obj0;
+    h.lmin_bits = 0x7ff0000000000000ll;
     if (o->max_iter == 0) h.status = ELLP_MAXITER;  // primal :163 (iter=1 > 0), dual :191 (0 >= 0)
     if (int rc = write_state(ctx)) return rc;
     const bool profile = o->profile != 0;

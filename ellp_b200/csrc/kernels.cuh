@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) k_gemv_t(const double* __restrict__ M, in
                                                 const double* __restrict__ c, const uint8_t* __restrict__ Ns,
                                                 double* __restrict__ key, PivotState* st, int clear_update) {
     if (st) {
-        if (clear_update && blockIdx.x == 0 && threadIdx.x == 0) st->do_update = 0;
+        if (clear_update && blockIdx.x == 0 && threadIdx.x == 0) { st->do_update = 0; st->do_step = 0; }
         if (st->status != kRunning) return;
     }
     const int lane = threadIdx.x & 31;
@@ -174,7 +174,45 @@ __global__ void __launch_bounds__(kScanThreads) k_select_primal(const double* __
     bool have = false;
     double bk = 0.;
     int bv = 0, bp = -1;
+    if (tid == 0) st->lmin_bits = 0x7ff0000000000000ll;  // +inf: reset for this iteration's k_ratio_prep
+    bool fast = false;
     if (tie_rule == ELLP_TIES_REFERENCE) {
+        // Fast path (exact): let K* = max key.  If exactly one key lies within EPS of K* and none lies in the next EPS band,
+        // that element wins the fold whatever the order: it beats every other key strictly, and no other key can displace
+        // it or tie with it.  Ties / near-ties fall through to the sequential fold below.
+        double kmax = -1.0;
+        for (int j = tid; j < nN; j += kScanThreads) kmax = fmax(kmax, __ldcg(key + j));
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) kmax = fmax(kmax, __shfl_xor_sync(full, kmax, off));
+        if (lane == 0) s_red[warp] = kmax;
+        __syncthreads();
+        kmax = s_red[0];
+        for (int w = 1; w < 32; ++w) kmax = fmax(kmax, s_red[w]);
+        __syncthreads();
+        int nF = 0, nBand = 0, idxF = 0x7fffffff;
+        if (kmax != -1.0) {
+            for (int j = tid; j < nN; j += kScanThreads) {
+                const double k = __ldcg(key + j);
+                if (k == -1.0) continue;
+                if (kmax - k < kEps) { ++nF; idxF = min(idxF, j); }
+                else if (kmax - k < 2. * kEps) ++nBand;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            nF += __shfl_xor_sync(full, nF, off);
+            nBand += __shfl_xor_sync(full, nBand, off);
+            idxF = min(idxF, __shfl_xor_sync(full, idxF, off));
+        }
+        if (lane == 0) { s_redi[warp] = nF; s_redp[warp] = nBand; s_red[warp] = (double)idxF; }
+        __syncthreads();
+        nF = 0; nBand = 0; idxF = 0x7fffffff;
+        for (int w = 0; w < 32; ++w) { nF += s_redi[w]; nBand += s_redp[w]; idxF = min(idxF, (int)s_red[w]); }
+        __syncthreads();
+        if (kmax == -1.0) { fast = true; bp = -1; }
+        else if (nF == 1 && nBand == 0) { fast = true; bp = idxF; bv = Nv[idxF]; }
+    }
+    if (tie_rule == ELLP_TIES_REFERENCE && !fast) {
         const int ntiles = (nN + kScanTile - 1) / kScanTile;
         scan_load_tile(key, Nv, nN, 0, sval[0], stag[0], 0);
         __syncthreads();
@@ -209,7 +247,7 @@ __global__ void __launch_bounds__(kScanThreads) k_select_primal(const double* __
             }
             __syncthreads();
         }
-    } else {
+    } else if (tie_rule != ELLP_TIES_REFERENCE) {
         // order-free rule: max key, then the largest variable index within EPS of it
         double kmax = -1.0;
         for (int j = tid; j < nN; j += kScanThreads) kmax = fmax(kmax, __ldcg(key + j));
@@ -340,7 +378,45 @@ __device__ __forceinline__ double primal_ratio(int kind, double lb, double ub, d
     }
 }
 
-__global__ void __launch_bounds__(1024) k_ratio_primal(DevLP lp, int KS, int tie_rule, PivotState* st) {
+// K2a: pivot column, direction and the per-row ratios (primal :295-367), one row per thread over the whole grid.
+// KS > 0: revised engine, alpha = sum of split-K partials (fixed order); KS == 0: tableau engine, alpha = T[:, q]
+// (copied out because k_rank1 overwrites that column); KS < 0: alpha already sits in dcol (column-sharded tableau).
+__global__ void __launch_bounds__(256) k_ratio_prep(DevLP lp, int KS, PivotState* st) {
+    if (st->status != kRunning) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int q_var = st->q_var;
+    const bool at_lower = (st->q_side == ELLP_NB_LOWER);
+    double lam = -1.0;  // -1 = skipped (|d_i| < EPS, :321)
+    if (i < lp.m) {
+        double a = 0.;
+        if (KS > 0) { for (int ks = 0; ks < KS; ++ks) a += lp.part[(int64_t)ks * lp.ld + i]; }
+        else if (KS == 0) a = lp.T[(int64_t)q_var * lp.ld + i];
+        else a = lp.dcol[i];
+        lp.dcol[i] = a;
+        const double d_i = at_lower ? -a : a;  // :296-300
+        if (!(fabs(d_i) < kEps)) {
+            const int var = lp.Bv[i];
+            lam = primal_ratio(lp.kind[var], lp.lb[var], lp.ub[var], lp.x[var], d_i);
+        }
+        lp.lam[i] = lam;
+    }
+    // block minimum of the finite ratios -> one atomicMin per block (ratios are >= 0, so their bit patterns order like integers)
+    double v = (lam >= 0. && lam < CUDART_INF) ? lam : CUDART_INF;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, off));
+    __shared__ double s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) v = fmin(v, s[w]);
+        if (v < CUDART_INF) atomicMin(&st->lmin_bits, __double_as_longlong(v));
+    }
+}
+
+// K2b: the ratio fold (primal :305-400), the step decision (:402-434) and the pivot bookkeeping (:205-232), single CTA.
+// tie_rule 0 reproduces the sequential scan with its (lambda, new_basic, new_basic_index) state exactly -- including the
+// stale-index behaviour of :379-399 -- with an exact shortcut when the minimum is isolated.
+__global__ void __launch_bounds__(1024) k_ratio_pick(DevLP lp, int tie_rule, PivotState* st) {
     if (st->status != kRunning) return;
     __shared__ double s_lambda;
     __shared__ int s_nb;
@@ -348,24 +424,6 @@ __global__ void __launch_bounds__(1024) k_ratio_primal(DevLP lp, int KS, int tie
     const int m = lp.m;
     const int q_var = st->q_var;
     const bool at_lower = (st->q_side == ELLP_NB_LOWER);
-    // alpha = sum of split-K partials (fixed order); d = -alpha when entering from its lower bound (:296-300)
-    // KS > 0: revised engine, alpha = sum of split-K partials; KS == 0: tableau engine, alpha = T[:, q] (copied out
-    // because k_rank1 overwrites that column); KS < 0: alpha already sits in dcol (column-sharded tableau)
-    const double* tcol = (KS == 0) ? lp.T + (int64_t)q_var * lp.ld : nullptr;
-    for (int i = tid; i < m; i += blockDim.x) {
-        double a = 0.;
-        if (KS > 0) { for (int ks = 0; ks < KS; ++ks) a += lp.part[(int64_t)ks * lp.ld + i]; }
-        else if (KS == 0) a = tcol[i];
-        else a = lp.dcol[i];
-        lp.dcol[i] = a;
-        const double d_i = at_lower ? -a : a;
-        double lam = -1.0;  // -1 = skipped (|d_i| < EPS, :321)
-        if (!(fabs(d_i) < kEps)) {
-            const int var = lp.Bv[i];
-            lam = primal_ratio(lp.kind[var], lp.lb[var], lp.ub[var], lp.x[var], d_i);
-        }
-        lp.lam[i] = lam;
-    }
     __syncthreads();
     {
         extern __shared__ __align__(16) unsigned char scan_smem[];
@@ -381,7 +439,42 @@ __global__ void __launch_bounds__(1024) k_ratio_primal(DevLP lp, int KS, int tie
             lambda = (kq == ELLP_TWOSIDED) ? (lp.ub[q_var] - lp.lb[q_var]) : (kq == ELLP_FIXED ? 0. : CUDART_INF);
         }
         int nb = -1;
+        bool fast = false;
         if (tie_rule == ELLP_TIES_REFERENCE) {
+            // Fast path (exact): L = min(lambda0, min_i lambda_i).  If exactly one of {lambda0, lambda_i} lies below L + EPS and
+            // none lies in [L + EPS, L + 2 EPS), the fold ends on that element whatever happened before it: when it is reached
+            // the running lambda exceeds it by more than EPS (strict branch), and afterwards nothing is within EPS of it.
+            const double L = fmin(__longlong_as_double(st->lmin_bits), lambda);
+            int nF = 0, nBand = 0, idxF = 0x7fffffff;
+            if (L < CUDART_INF) {
+                for (int i = tid; i < m; i += blockDim.x) {
+                    const double l = lp.lam[i];
+                    if (l == -1.0) continue;
+                    if (l < L + kEps) { ++nF; idxF = min(idxF, i); }
+                    else if (l < L + 2. * kEps) ++nBand;
+                }
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                nF += __shfl_xor_sync(full, nF, off);
+                nBand += __shfl_xor_sync(full, nBand, off);
+                idxF = min(idxF, __shfl_xor_sync(full, idxF, off));
+            }
+            if (lane == 0) { s_redi[warp] = nF; s_redp[warp] = nBand; s_red[warp] = (double)idxF; }
+            __syncthreads();
+            nF = 0; nBand = 0; idxF = 0x7fffffff;
+            for (int w = 0; w < 32; ++w) { nF += s_redi[w]; nBand += s_redp[w]; idxF = min(idxF, (int)s_red[w]); }
+            __syncthreads();
+            const int f0 = (lambda < L + kEps) ? 1 : 0;
+            const int band0 = (!f0 && lambda < L + 2. * kEps) ? 1 : 0;
+            if (!(L < CUDART_INF)) { fast = true; }                               // nothing finite: lambda stays +inf (unbounded)
+            else if (nF + f0 == 1 && nBand + band0 == 0) {
+                fast = true;
+                if (!f0) { nb = idxF; lambda = lp.lam[idxF]; }                    // else: the entering variable's own bound flip
+            }
+            if (fast && tid == 0) { s_lambda = lambda; s_nb = nb; }
+        }
+        if (tie_rule == ELLP_TIES_REFERENCE && !fast) {
             bool have_nbi = false;
             int nbi = 0;
             const int ntiles = (m + kScanTile - 1) / kScanTile;
@@ -419,7 +512,7 @@ __global__ void __launch_bounds__(1024) k_ratio_primal(DevLP lp, int KS, int tie
                 __syncthreads();
             }
             if (tid == 0) { s_lambda = lambda; s_nb = nb; }
-        } else {
+        } else if (tie_rule != ELLP_TIES_REFERENCE) {
             double lmin = CUDART_INF;
             for (int i = tid; i < m; i += blockDim.x) {
                 const double l = lp.lam[i];
@@ -464,24 +557,15 @@ __global__ void __launch_bounds__(1024) k_ratio_primal(DevLP lp, int KS, int tie
     const double lambda = s_lambda;
     const int nb = s_nb;
     if (!(lambda >= 0.)) {  // :402 assert!(lambda >= 0.)
-        if (tid == 0) { st->err = kErrLambdaNegative; st->status = ELLP_UNBOUNDED; st->do_update = 0; }
+        if (tid == 0) { st->err = kErrLambdaNegative; st->status = ELLP_UNBOUNDED; st->do_update = 0; st->do_step = 0; }
         return;
     }
     if (isinf(lambda)) {  // :404-406
-        if (tid == 0) { st->status = ELLP_UNBOUNDED; st->do_update = 0; }
+        if (tid == 0) { st->status = ELLP_UNBOUNDED; st->do_update = 0; st->do_step = 0; }
         return;
     }
-    if (lambda > 0.) {  // :408-417
-        for (int i = tid; i < m; i += blockDim.x) {
-            const double a = lp.dcol[i];
-            const double d_i = at_lower ? -a : a;
-            const int var = lp.Bv[i];
-            lp.x[var] = lp.x[var] + lambda * d_i;
-        }
-    }
-    __syncthreads();
     if (tid == 0) {
-        if (lambda > 0.) lp.x[q_var] = at_lower ? lp.x[q_var] + lambda : lp.x[q_var] - lambda;
+        st->do_step = (lambda > 0.) ? 1 : 0;  // :408-417 is carried out by k_step_gather (x moves along d by lambda)
         const int q_pos = st->q_pos;
         const int64_t t = st->trace_len;
         int leave_var = -1;
@@ -545,6 +629,28 @@ __global__ void k_gather_row(const double* __restrict__ E, int64_t ld, int C, co
     if (j >= C) return;
     const double e = E[(int64_t)j * ld + st->r_pos];
     out[j] = (mode == 0) ? e : e / st->alpha_r;
+}
+
+// K2c: the primal step x_B += lambda d, x_q +-= lambda (primal :408-417) fused with the scaled pivot-row gather that feeds
+// k_rank1.  Runs after the bookkeeping of k_ratio_pick, so basis position r already holds the entering variable: the
+// leaving variable's value is updated through PivotState::leave_var.
+__global__ void k_step_gather(DevLP lp, const double* __restrict__ E, int C, PivotState* st) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (st->do_step) {
+        const double lambda = st->step;
+        const bool at_lower = (st->q_side == ELLP_NB_LOWER);
+        if (t < lp.m) {
+            const double a = lp.dcol[t];
+            const double d_i = at_lower ? -a : a;
+            const int var = (st->do_update && t == st->r_pos) ? st->leave_var : lp.Bv[t];
+            lp.x[var] = lp.x[var] + lambda * d_i;
+        }
+        if (t == 0) {
+            const int q = st->q_var;
+            lp.x[q] = at_lower ? lp.x[q] + lambda : lp.x[q] - lambda;
+        }
+    }
+    if (st->do_update && t < C) lp.prow[t] = E[(int64_t)t * lp.ld + st->r_pos] / st->alpha_r;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -883,7 +989,7 @@ __global__ void k_check_identity_basis(const double* __restrict__ T, int64_t ld,
 // tableau engine pricing: reduced costs are a maintained row, so the Dantzig keys are a pure O(n - m) pass
 __global__ void k_price_tab(const double* __restrict__ dj, const int32_t* __restrict__ Nv, const uint8_t* __restrict__ Ns, int nN,
                             double* __restrict__ rN, double* __restrict__ key, PivotState* st) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) st->do_update = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { st->do_update = 0; st->do_step = 0; }
     if (st->status != kRunning) return;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nN) return;
@@ -906,7 +1012,7 @@ __global__ void k_price_tab(const double* __restrict__ dj, const int32_t* __rest
 // column to an all-reduce (the others contribute zeros) -> replicated ratio test -> local rank-1 update.
 // ------------------------------------------------------------------------------------------------
 __global__ void k_price_shard(DevLP lp, PivotState* st) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) st->do_update = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { st->do_update = 0; st->do_step = 0; }
     if (st->status != kRunning) return;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= lp.n) return;
@@ -994,6 +1100,7 @@ __global__ void k_shard_stage_column(DevLP lp, int G, PivotState* st, double* __
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < lp.ld) sendcol[i] = mine ? lp.T[(int64_t)(q_var - lp.col_lo) * lp.ld + i] : 0.;
     if (i == 0) {
+        st->lmin_bits = 0x7ff0000000000000ll;
         st->q_var = q_var;
         st->q_pos = -1;
         st->q_side = (int)side;
@@ -1063,7 +1170,8 @@ __global__ void k_fill_uniform(double* __restrict__ out, uint64_t count, uint64_
 // columns [0, ns) structural, [ns, ns+m) slack (identity); starting point = slack basis (primal feasible).
 // col_lo/col_hi select the locally stored column range (column sharding); element values depend only on the
 // GLOBAL (row, column) index so every sharding sees the same LP.
-__global__ void k_gen_dense_cols(double* __restrict__ A, int64_t ld, int m, int64_t ns, int64_t col_lo, int64_t col_hi, uint64_t seed) {
+__global__ void k_gen_dense_cols(double* __restrict__ A, int64_t ld, int m, int64_t ns, int64_t col_lo, int64_t col_hi, uint64_t seed,
+                                 double slack_sign) {
     const int64_t ncol = col_hi - col_lo;
     const int64_t total = ncol * ld;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -1075,25 +1183,29 @@ __global__ void k_gen_dense_cols(double* __restrict__ A, int64_t ld, int m, int6
                 const uint64_t h = splitmix64(seed * 0x2545f4914f6cdd1dull + (uint64_t)(j * m + i));
                 v = (double)(h >> 11) * (1.0 / 9007199254740992.0);
             } else {
-                v = (j - ns == i) ? 1. : 0.;
+                v = (j - ns == i) ? slack_sign : 0.;
             }
         }
         A[e] = v;
     }
 }
 
-__global__ void k_gen_dense_vectors(DevLP lp, int64_t ns, uint64_t seed) {
+// variant 0: min -c.x, Ax + s = b (slack basis primal feasible); variant 1: min c.x, Ax - s = b (slack basis dual
+// feasible: x_B = -b < 0, y = 0, d = c >= 0) -- SURVEY 8(d) configs 4/5 and 3
+__global__ void k_gen_dense_vectors(DevLP lp, int64_t ns, uint64_t seed, int variant) {
     const int m = lp.m, n = lp.n_glob;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         double cj = 0., xj = 0.;
         if (j < ns) {
             const uint64_t h = splitmix64((seed + 1) * 0x2545f4914f6cdd1dull + (uint64_t)j);
-            cj = -(0.5 + (double)(h >> 11) * (1.0 / 9007199254740992.0));
+            cj = 0.5 + (double)(h >> 11) * (1.0 / 9007199254740992.0);
+            if (variant == 0) cj = -cj;
         } else {
             const uint64_t h = splitmix64((seed + 2) * 0x2545f4914f6cdd1dull + (uint64_t)(j - ns));
             xj = (1.0 + (double)(h >> 11) * (1.0 / 9007199254740992.0)) * ((double)ns * 0.25);
             const int i = (int)(j - ns);
             const_cast<double*>(lp.b)[i] = xj;
+            if (variant == 1) { xj = -xj; lp.y[i] = 0.; }
             lp.Bv[i] = (int32_t)j;
         }
         const_cast<double*>(lp.c)[j] = cj;
@@ -1101,6 +1213,7 @@ __global__ void k_gen_dense_vectors(DevLP lp, int64_t ns, uint64_t seed) {
         const_cast<double*>(lp.ub)[j] = 0.;
         const_cast<uint8_t*>(lp.kind)[j] = ELLP_LOWER;
         lp.x[j] = xj;
+        if (variant == 1) lp.d[j] = cj;
         if (j < ns && lp.colstat == nullptr) { lp.Nv[j] = (int32_t)j; lp.Ns[j] = ELLP_NB_LOWER; }
         if (lp.colstat != nullptr && j >= lp.col_lo && j < lp.col_lo + lp.n) lp.colstat[j - lp.col_lo] = (j < ns) ? (uint8_t)ELLP_NB_LOWER : kColBasic;
     }

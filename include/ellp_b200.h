@@ -137,6 +137,9 @@ int ellp_b200_download(ellp_b200_ctx*, ellp_point*);
  * standard form m x (n_struct + m), starting point = slack basis.  Values come from a counter-based generator
  * (splitmix64 of seed and the global element index).  o->engine selects the resident representation. */
 int ellp_b200_generate_dense(ellp_b200_ctx*, int32_t m, int32_t n_struct, uint64_t seed, const ellp_opts* o);
+/* variant 0: as above (primal feasible slack basis); variant 1: min c.x s.t. A x - s = b: the
+ * slack basis is dual feasible (x_B = -b, y = 0, d = c) and the resident solver is the dual one (revised engine). */
+int ellp_b200_generate_dense_ex(ellp_b200_ctx*, int32_t m, int32_t n_struct, uint64_t seed, int32_t variant, const ellp_opts* o);
 /* copies the resident standard form to host buffers (any pointer may be NULL) */
 int ellp_b200_download_std_form(ellp_b200_ctx*, double* A, double* c, double* b, uint8_t* kind, double* lb, double* ub);
 /* tuning knobs: "rank1_cols_per_cta", "rank1_stream_min_mb" */

@@ -325,3 +325,25 @@ def test_sharded_tableau_two_gpus_matches_single_gpu_and_oracle(env):
                           "--master-port", "29631", os.path.join(root, "tools", "sharded_check.py")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "SHARDED_CHECK_OK" in out.stdout
+
+
+def test_generated_dual_lp_matches_numpy_twin_and_oracle(env):
+    import bench_lp
+    N, O, ctx = env["N"], env["O"], env["ctx"]
+    m, ns, seed, K = 64, 128, 9, 60
+    o = N.default_opts(K, engine=N.ENGINE_REVISED)
+    tr = np.zeros(K, dtype=N.TRACE_DTYPE); o.trace = N.ptr(tr); o.trace_cap = K
+    ctx.check(N.lib.ellp_b200_generate_dense_ex(ctx.h, m, ns, seed, 1, C.byref(o)))
+    n = ns + m
+    A = np.zeros((m, n), order="F"); c = np.zeros(n); b = np.zeros(m)
+    ctx.check(N.lib.ellp_b200_download_std_form(ctx.h, N.ptr(A), N.ptr(c), N.ptr(b), None, None, None))
+    lp = bench_lp.dense_lp(m, ns, seed, 1)
+    assert A.tobytes() == lp["A"].tobytes() and c.tobytes() == lp["c"].tobytes() and b.tobytes() == lp["b"].tobytes()
+    res = N.Result()
+    ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(o), C.byref(res)))
+    ref = O.solve_with_initial(O.DUAL, m, n, lp["A"], lp["c"], lp["b"], lp["kind"], lp["lb"], lp["ub"], lp["x"].copy(),
+                               lp["B"].copy(), lp["N"].copy(), lp["N_side"].copy(), lp["y"].copy(), lp["d"].copy(),
+                               max_iter=K, trace_cap=K)
+    k = len(ref.trace)
+    assert res.status == ref.status and res.iters == k > 5
+    assert (tr["entering"][:k] == ref.trace["entering"]).all() and (tr["leaving"][:k] == ref.trace["leaving"]).all()
