@@ -39,6 +39,9 @@ WORKLOADS = {
     # (explicit basis inverse).  The entering/leaving rules are the reference's (steepest edge is not built yet).
     "dense_revised_dual_4096x12288": dict(m=4096, ns=8192, pivots=200, sample_m=512, sample_pivots=6, dual=True),
     "dense_tableau_tiny": dict(m=256, ns=256, pivots=20, sample_m=128, sample_pivots=4),
+    # BASELINE.json configs[3]: "batch of 65536 independent small LPs (64x128), sharded one shard per GPU at 1/2/4/8 B200"
+    "batch_small_lps_65536x64x128": dict(batch=True, nlp=65536, m=64, ns=128, sample_lps=150),
+    "batch_small_lps_tiny": dict(batch=True, nlp=600, m=64, ns=128, sample_lps=20),
 }
 DEFAULT_WORKLOAD = "dense_tableau_32768x65536"
 SEED = 0
@@ -130,6 +133,140 @@ def run_reference(args, wl, name):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ batch of small LPs
+def cpu_batch_sample(wl: dict, nlps: int):
+    """ellp's PrimalSimplexSolver::solve (oracle port, 1 thread) on the first `nlps` LPs of the batch."""
+    import bench_lp
+    from oracle import binding as O
+    O.lib()
+    probs = [bench_lp.batch_lp_problem_arrays(wl["m"], wl["ns"], SEED, k) for k in range(nlps)]
+    t0 = time.perf_counter()
+    piv = 0
+    for p in probs:
+        r = O.solve(p, O.PRIMAL, None, O.MODE_EXACT)
+        assert r.status == O.OPTIMAL
+        piv += sum(r.iters)
+    dt = time.perf_counter() - t0
+    return piv / dt, dt, f"PrimalSimplexSolver::solve on the first {nlps} LPs of the same batch ({piv} pivots, {nlps / dt:.1f} LPs/s)"
+
+
+def run_batch(args, wl, name):
+    """configs[3]: every rank solves its shard of the batch with the shared-memory kernel (K6); no collective."""
+    import torch
+    from ellp_b200 import _native as N
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        for _ in range(min(args.warmup, 1)):
+            cpu_batch_sample(wl, 5)
+        t0 = time.perf_counter(); piv = 0.0
+        per_step = max(4, wl["sample_lps"] // 8)
+        for _ in range(args.steps):
+            v, dts, sample = cpu_batch_sample(wl, per_step)
+            piv += v * dts
+        dt = time.perf_counter() - t0
+        value = piv / dt
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": name, "nlp": wl["nlp"], "m": wl["m"], "n_struct": wl["ns"]},
+                          "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+                          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = N.Context(local_rank)
+    m, ns = wl["m"], wl["ns"]
+    nlp = wl["nlp"] // world
+    first = rank * nlp
+    n0 = ns + m
+    o = N.default_opts(None)
+    ctx.check(N.lib.ellp_b200_batch_generate(ctx.h, nlp, m, ns, SEED, first, 0))
+    iters = np.zeros((nlp, 2), dtype=np.int32); status = np.zeros(nlp, dtype=np.int32)
+
+    def step():
+        res = N.BatchResult()
+        ctx.check(N.lib.ellp_b200_batch_run(ctx.h, C.byref(o), C.byref(res)))
+        return res.ms_device
+
+    def sync_all():
+        ctx.check(N.lib.ellp_b200_sync(ctx.h)); torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        step()
+    out = N.BatchResult(N.ptr(status), None, None, N.ptr(iters), None, None, 0, None, 0.0, 0, 0)
+    ctx.check(N.lib.ellp_b200_batch_download(ctx.h, C.byref(out)))
+    assert (status == N.OPTIMAL).all()
+    pivots_local = int(iters.sum())
+    sync_all()
+    clocks = ClockSampler(local_rank); clocks.start()
+    t0 = time.perf_counter(); dev_ms = 0.0
+    for _ in range(args.steps):
+        dev_ms += step()
+    ctx.check(N.lib.ellp_b200_sync(ctx.h)); torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    clk = clocks.stop()
+    # e2e: host buffers in, results out (ellp_b200_primal_solve_batch)
+    A_h = torch.empty(nlp * m * n0, dtype=torch.float64, pin_memory=True).numpy()
+    c_h = np.zeros(nlp * n0); b_h = np.zeros(nlp * m)
+    e2e = None
+    if not args.no_e2e:
+        kind_h = np.ones(nlp * n0, dtype=np.uint8); lb_h = np.zeros(nlp * n0); ub_h = np.zeros(nlp * n0)
+        ctx.check(N.lib.ellp_b200_batch_download_all(ctx.h, N.ptr(A_h), N.ptr(c_h), N.ptr(b_h)))
+        bt = N.Batch(nlp, m, n0, N.ptr(A_h), N.ptr(c_h), N.ptr(b_h), N.ptr(kind_h), N.ptr(lb_h), N.ptr(ub_h))
+        obj = np.zeros(nlp); st2 = np.zeros(nlp, dtype=np.int32); it2 = np.zeros((nlp, 2), dtype=np.int32); err2 = np.zeros(nlp, dtype=np.int32)
+        res = N.BatchResult(N.ptr(st2), N.ptr(obj), None, N.ptr(it2), N.ptr(err2), None, 0, None, 0.0, 0, 0)
+
+        def e2e_step():
+            ctx.check(N.lib.ellp_b200_primal_solve_batch(ctx.h, C.byref(bt), C.byref(o), C.byref(res)))
+            return int(res.pivots)
+
+        e2e_step()
+        sync_all()
+        t0 = time.perf_counter(); pe = 0
+        for _ in range(args.steps):
+            pe += e2e_step()
+        dte = time.perf_counter() - t0
+        e2e = dict(dt=dte, pivots=pe, h2d=8 * nlp * (m * n0 + 3 * n0 + m) + nlp * n0, d2h=nlp * (8 + 4 + 8 + 4))
+    vals = torch.tensor([dt, dev_ms, e2e["dt"] if e2e else 0.0], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(pivots_local), float(e2e["pivots"]) if e2e else 0.0], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    dt, dev_ms, dte = [float(v) for v in vals.cpu()]
+    pivots_total, pe_total = [float(v) for v in tot.cpu()]
+    if rank == 0:
+        value = args.steps * pivots_total / dt
+        cpu = None
+        if not args.no_cpu:
+            v, dtc, sample = cpu_batch_sample(wl, wl["sample_lps"])
+            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample, "seconds": dtc, "host_cores_available": os.cpu_count()}
+        peak, peak_src = measured_peak()
+        hbm_bytes = nlp * (8.0 * (m * n0 + 3 * n0 + m) + n0 + 8.0 * (n0 + m) + 4.0 * (m + n0) + n0 + 24)
+        smem_bytes_per_pivot = 16.0 * m * n0
+        roofline = {"bound": "hbm", "kernel": "k_batch_primal (tableau resident in shared memory; HBM only for loading the LP and storing the point)",
+                    "achieved": hbm_bytes * args.steps / (dev_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "traffic": None, "peak_source": peak_src,
+                    "frac": hbm_bytes * args.steps / (dev_ms * 1e-3) / 1e9 / peak,
+                    "note": "this kernel is shared-memory bound, not HBM bound: %.0f KB of shared-memory traffic per pivot, %.2f TB/s aggregate per GPU" % (
+                        smem_bytes_per_pivot / 1e3, smem_bytes_per_pivot * pivots_total / world * args.steps / (dev_ms * 1e-3) / 1e12)}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": name, "nlp": wl["nlp"], "lps_per_gpu": nlp, "m": m, "n_struct": ns, "std_form": f"{m}x{n0} (+{m} artificial columns in phase 1)",
+                           "pivots_per_step": pivots_total, "lps_per_s": args.steps * wl["nlp"] / dt, "engine": "K6 shared-memory condensed tableau, one CTA per LP",
+                           "l2": f"{8.0 * nlp * m * n0 / 1e9:.2f} GB of LP data per GPU per step (> 126 MB L2)"},
+                "device_ms_per_step": dev_ms / args.steps, "gpu_launches": args.steps * world, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+                "e2e": None if not e2e else {"value": pe_total / dte, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"] * world, "d2h_bytes_per_step": e2e["d2h"] * world,
+                                             "ms_per_step": 1e3 * dte / args.steps, "api": "ellp_b200_primal_solve_batch (host buffers, pinned)"}}
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.barrier(); dist.destroy_process_group()
+    ctx.close()
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -271,6 +408,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
+    if wl.get("batch"):
+        return run_batch(args, wl, args.workload)
     if args.impl == "reference":
         run_reference(args, wl, args.workload)
     else:

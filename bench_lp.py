@@ -47,3 +47,22 @@ def dense_lp(m: int, ns: int, seed: int, variant: int = 0) -> dict:
     x[ns:] = b
     return dict(m=m, n=n, A=A, c=c, b=b, kind=np.ones(n, dtype=np.uint8), lb=np.zeros(n), ub=np.zeros(n), x=x,
                 B=np.arange(ns, n, dtype=np.int32), N=np.arange(ns, dtype=np.int32), N_side=np.zeros(ns, dtype=np.uint8))
+
+
+def batch_lp(m: int, ns: int, seed: int, lpid: int) -> dict:
+    """Numpy twin of k_gen_batch (ellp_b200/csrc/batch.cuh): LP `lpid` of the configs[3] batch,
+    min -c.x, A x <= b, x >= 0.  Returns the structural data (A m x ns, c ns, b m)."""
+    idx = np.arange(m * ns, dtype=np.uint64)
+    A = _uniform01(seed + 3 * lpid, idx).reshape((m, ns), order="F")
+    c = -(0.5 + _uniform01(seed + 3 * lpid + 1, np.arange(ns, dtype=np.uint64)))
+    b = (1.0 + _uniform01(seed + 3 * lpid + 2, np.arange(m, dtype=np.uint64))) * (ns * 0.25)
+    return dict(A=A, c=c, b=b)
+
+
+def batch_lp_problem_arrays(m: int, ns: int, seed: int, lpid: int) -> dict:
+    """The same LP in the flat layout of Problem.to_arrays() (dense CSR rows, every variable Lower(0), rows Lte)."""
+    lp = batch_lp(m, ns, seed, lpid)
+    return dict(nvars=ns, ncons=m, obj=lp["c"].copy(), kind=np.ones(ns, dtype=np.uint8), lb=np.zeros(ns), ub=np.zeros(ns),
+                var_id=np.arange(ns, dtype=np.int64), row_ptr=(np.arange(m + 1, dtype=np.int32) * ns),
+                col_id=np.tile(np.arange(ns, dtype=np.int64), m), coef=np.ascontiguousarray(lp["A"]).reshape(-1),
+                op=np.zeros(m, dtype=np.uint8), rhs=lp["b"].copy())

@@ -47,6 +47,17 @@ class Result(C.Structure):
                 ("n_rank1", C.c_uint64), ("refactors", C.c_uint64)]
 
 
+class Batch(C.Structure):
+    _fields_ = [("nlp", C.c_int32), ("m", C.c_int32), ("n", C.c_int32), ("A", C.c_void_p), ("c", C.c_void_p), ("b", C.c_void_p),
+                ("kind", C.c_void_p), ("lb", C.c_void_p), ("ub", C.c_void_p)]
+
+
+class BatchResult(C.Structure):
+    _fields_ = [("status", C.c_void_p), ("obj", C.c_void_p), ("x", C.c_void_p), ("iters", C.c_void_p), ("err", C.c_void_p),
+                ("trace", C.c_void_p), ("trace_cap", C.c_int32), ("trace_len", C.c_void_p), ("ms_device", C.c_double),
+                ("launches", C.c_uint64), ("pivots", C.c_uint64)]
+
+
 class ProblemDesc(C.Structure):
     _fields_ = [("nvars", C.c_int32), ("ncons", C.c_int32), ("obj", C.c_void_p), ("kind", C.c_void_p),
                 ("lb", C.c_void_p), ("ub", C.c_void_p), ("var_id", C.c_void_p), ("row_ptr", C.c_void_p),
@@ -94,6 +105,13 @@ def _load():
         "ellp_b200_d2h": (C.c_int, [vp, vp, vp, u64]),
         "ellp_b200_sync": (C.c_int, [vp]),
         "ellp_b200_dev_fill_uniform": (C.c_int, [vp, vp, u64, u64, u64, C.c_double, C.c_double]),
+        "ellp_b200_primal_solve_batch": (C.c_int, [vp, C.POINTER(Batch), C.POINTER(Opts), C.POINTER(BatchResult)]),
+        "ellp_b200_batch_generate": (C.c_int, [vp, i32, i32, i32, u64, i64, i32]),
+        "ellp_b200_batch_upload": (C.c_int, [vp, C.POINTER(Batch), i32]),
+        "ellp_b200_batch_run": (C.c_int, [vp, C.POINTER(Opts), C.POINTER(BatchResult)]),
+        "ellp_b200_batch_download": (C.c_int, [vp, C.POINTER(BatchResult)]),
+        "ellp_b200_batch_download_lp": (C.c_int, [vp, i32, vp, vp, vp]),
+        "ellp_b200_batch_download_all": (C.c_int, [vp, vp, vp, vp]),
         "ellp_b200_comm_unique_id": (C.c_int, [C.c_char_p, vp]),
         "ellp_b200_comm_init": (C.c_int, [vp, C.c_char_p, vp, C.c_int, C.c_int]),
         "ellp_b200_sharded_generate_dense": (C.c_int, [vp, i32, i32, u64, C.POINTER(Opts)]),

@@ -14,6 +14,7 @@
 
 #include "engine.hpp"
 #include "kernels.cuh"
+#include "batch.cuh"
 
 using namespace ellp;
 
@@ -78,10 +79,20 @@ struct ellp_b200_ctx {
     double dual_obj0 = 0.;
     std::vector<cudaEvent_t> ev;  // profile=1: pairs around rank-1 launches
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // K6 batch of small LPs (device resident)
+    struct Batch {
+        int nlp = 0, m = 0, n0 = 0, nc = 0, ld = 0, trace_cap = 0;
+        double *A = nullptr, *c = nullptr, *b = nullptr, *lb = nullptr, *ub = nullptr, *x = nullptr, *obj = nullptr;
+        uint8_t *kind = nullptr, *Ns = nullptr;
+        int32_t *B = nullptr, *N = nullptr, *status = nullptr, *iters = nullptr, *err = nullptr, *trace_len = nullptr;
+        ellp_trace_rec* trace = nullptr;
+    } batch;
     // tuning (ellp_b200_set_tuning)
     int rank1_cols_per_cta = 8;
     int rank1_stream_min_mb = 96;  // evict-first policy when the updated matrix is larger than this
 };
+
+extern "C" { static void batch_free(ellp_b200_ctx* ctx); }
 
 // ---- NCCL, bound at run time (torch ships libnccl.so.2; the library must also load on boxes without it) -----------
 namespace nccl {
@@ -444,6 +455,7 @@ void ellp_b200_destroy(ellp_b200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    batch_free(ctx);
     if (ctx->nccl_comm && nccl::api.CommDestroy) nccl::api.CommDestroy(ctx->nccl_comm);
     for (auto e : ctx->ev) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -718,6 +730,154 @@ int ellp_b200_sharded_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const 
     CUDA_TRY(cudaStreamSynchronize(s));
     if (mismatch) return set_err(ctx, ELLP_E_ARG, "sharded tableau: the starting basis must be the identity (slack basis)");
     return sharded_finish_init(ctx);
+}
+
+// ---- K6: batches of independent small LPs ------------------------------------------------------------------------
+static void batch_free(ellp_b200_ctx* ctx) {
+    auto& B = ctx->batch;
+    void* ptrs[] = {B.A, B.c, B.b, B.lb, B.ub, B.x, B.obj, B.kind, B.Ns, B.B, B.N, B.status, B.iters, B.err, B.trace_len, B.trace};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    B = ellp_b200_ctx::Batch();
+}
+
+static int batch_alloc(ellp_b200_ctx* ctx, int nlp, int m, int n0, int trace_cap) {
+    batch_free(ctx);
+    auto& B = ctx->batch;
+    B.nlp = nlp; B.m = m; B.n0 = n0; B.nc = n0 + m; B.ld = (m % 2 == 0) ? m + 1 : m; B.trace_cap = trace_cap;
+    const size_t L = (size_t)nlp, nN = (size_t)n0;  // nc - m = n0 nonbasic positions
+    CUDA_TRY(cudaMalloc(&B.A, sizeof(double) * L * m * n0));
+    CUDA_TRY(cudaMalloc(&B.c, sizeof(double) * L * n0));
+    CUDA_TRY(cudaMalloc(&B.b, sizeof(double) * L * m));
+    CUDA_TRY(cudaMalloc(&B.lb, sizeof(double) * L * n0));
+    CUDA_TRY(cudaMalloc(&B.ub, sizeof(double) * L * n0));
+    CUDA_TRY(cudaMalloc(&B.kind, L * n0));
+    CUDA_TRY(cudaMalloc(&B.x, sizeof(double) * L * B.nc));
+    CUDA_TRY(cudaMalloc(&B.obj, sizeof(double) * L));
+    CUDA_TRY(cudaMalloc(&B.B, sizeof(int32_t) * L * m));
+    CUDA_TRY(cudaMalloc(&B.N, sizeof(int32_t) * L * nN));
+    CUDA_TRY(cudaMalloc(&B.Ns, L * nN));
+    CUDA_TRY(cudaMalloc(&B.status, sizeof(int32_t) * L));
+    CUDA_TRY(cudaMalloc(&B.iters, sizeof(int32_t) * 2 * L));
+    CUDA_TRY(cudaMalloc(&B.err, sizeof(int32_t) * L));
+    CUDA_TRY(cudaMalloc(&B.trace_len, sizeof(int32_t) * L));
+    if (trace_cap > 0) CUDA_TRY(cudaMalloc(&B.trace, sizeof(ellp_trace_rec) * L * trace_cap));
+    return ELLP_OK;
+}
+
+int ellp_b200_batch_generate(ellp_b200_ctx* ctx, int32_t nlp, int32_t m, int32_t n_struct, uint64_t seed, int64_t first_lp,
+                             int32_t trace_cap) {
+    if (!ctx || nlp <= 0 || m <= 0 || n_struct <= 0) return ELLP_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (int rc = batch_alloc(ctx, nlp, m, n_struct + m, trace_cap)) return rc;
+    auto& B = ctx->batch;
+    LAUNCH(k_gen_batch, 148 * 16, 256, B.A, B.c, B.b, B.kind, B.lb, B.ub, nlp, m, n_struct, seed, first_lp);
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaGetLastError());
+    return ELLP_OK;
+}
+
+int ellp_b200_batch_upload(ellp_b200_ctx* ctx, const ellp_batch* bt, int32_t trace_cap) {
+    if (!ctx || !bt || bt->nlp <= 0 || bt->m <= 0 || bt->n < bt->m) return ELLP_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (int rc = batch_alloc(ctx, bt->nlp, bt->m, bt->n, trace_cap)) return rc;
+    auto& B = ctx->batch;
+    const size_t L = (size_t)bt->nlp, m = (size_t)bt->m, n = (size_t)bt->n;
+    cudaStream_t s = ctx->stream;
+    CUDA_TRY(cudaMemcpyAsync(B.A, bt->A, sizeof(double) * L * m * n, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(B.c, bt->c, sizeof(double) * L * n, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(B.b, bt->b, sizeof(double) * L * m, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(B.lb, bt->lb, sizeof(double) * L * n, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(B.ub, bt->ub, sizeof(double) * L * n, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(B.kind, bt->kind, L * n, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return ELLP_OK;
+}
+
+int ellp_b200_batch_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_batch_result* res) {
+    if (!ctx || !o || !res) return ELLP_E_ARG;
+    auto& B = ctx->batch;
+    if (B.nlp <= 0) return set_err(ctx, ELLP_E_ARG, "no batch resident: call ellp_b200_batch_generate / ellp_b200_batch_upload first");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t smem = batch_smem_bytes(B.m, B.n0, B.ld);
+    if (smem > 227 * 1024) return set_err(ctx, ELLP_E_ARG, "LP too large for the shared-memory kernel (needs about (m+1)*n*8 bytes <= ~215 KB)");
+    CUDA_TRY(cudaFuncSetAttribute(k_batch_primal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BatchArgs a{};
+    a.nlp = B.nlp; a.m = B.m; a.n0 = B.n0; a.nc = B.nc; a.ld = B.ld;
+    a.mode = 0;
+    a.tie_rule = o->tie_rule;
+    a.trace_cap = B.trace_cap;
+    a.max_iter = o->max_iter;
+    a.A = B.A; a.c = B.c; a.b = B.b; a.kind = B.kind; a.lb = B.lb; a.ub = B.ub;
+    a.x = B.x; a.B = B.B; a.N = B.N; a.Ns = B.Ns;
+    a.status = B.status; a.obj = B.obj; a.iters = B.iters; a.err = B.err; a.trace = B.trace; a.trace_len = B.trace_len;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    int per_sm = 1;  // persistent CTAs: as many per SM as the shared-memory tableau allows (2 for 64 x 192)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_batch_primal, kBatchThreads, smem);
+    const int grid = std::min(B.nlp, sms * std::max(1, per_sm));
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    LAUNCH_SMEM(k_batch_primal, grid, kBatchThreads, smem, a);
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaGetLastError());
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    res->ms_device = ms;
+    res->launches = 1;
+    return ELLP_OK;
+}
+
+int ellp_b200_batch_download(ellp_b200_ctx* ctx, ellp_batch_result* res) {
+    if (!ctx || !res) return ELLP_E_ARG;
+    auto& B = ctx->batch;
+    if (B.nlp <= 0) return ELLP_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t L = (size_t)B.nlp;
+    cudaStream_t s = ctx->stream;
+    if (res->status) CUDA_TRY(cudaMemcpyAsync(res->status, B.status, sizeof(int32_t) * L, cudaMemcpyDeviceToHost, s));
+    if (res->obj) CUDA_TRY(cudaMemcpyAsync(res->obj, B.obj, sizeof(double) * L, cudaMemcpyDeviceToHost, s));
+    if (res->iters) CUDA_TRY(cudaMemcpyAsync(res->iters, B.iters, sizeof(int32_t) * 2 * L, cudaMemcpyDeviceToHost, s));
+    if (res->err) CUDA_TRY(cudaMemcpyAsync(res->err, B.err, sizeof(int32_t) * L, cudaMemcpyDeviceToHost, s));
+    if (res->x) CUDA_TRY(cudaMemcpyAsync(res->x, B.x, sizeof(double) * L * B.nc, cudaMemcpyDeviceToHost, s));
+    if (res->trace_len) CUDA_TRY(cudaMemcpyAsync(res->trace_len, B.trace_len, sizeof(int32_t) * L, cudaMemcpyDeviceToHost, s));
+    if (res->trace && B.trace) CUDA_TRY(cudaMemcpyAsync(res->trace, B.trace, sizeof(ellp_trace_rec) * L * B.trace_cap, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (res->iters) {
+        uint64_t p = 0;
+        for (size_t k = 0; k < 2 * L; ++k) p += (uint64_t)res->iters[k];
+        res->pivots = p;
+    }
+    return ELLP_OK;
+}
+
+int ellp_b200_batch_download_lp(ellp_b200_ctx* ctx, int32_t k, double* A, double* c, double* b) {
+    if (!ctx) return ELLP_E_ARG;
+    auto& B = ctx->batch;
+    if (k < 0 || k >= B.nlp) return ELLP_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (A) CUDA_TRY(cudaMemcpy(A, B.A + (size_t)k * B.m * B.n0, sizeof(double) * B.m * B.n0, cudaMemcpyDeviceToHost));
+    if (c) CUDA_TRY(cudaMemcpy(c, B.c + (size_t)k * B.n0, sizeof(double) * B.n0, cudaMemcpyDeviceToHost));
+    if (b) CUDA_TRY(cudaMemcpy(b, B.b + (size_t)k * B.m, sizeof(double) * B.m, cudaMemcpyDeviceToHost));
+    return ELLP_OK;
+}
+
+int ellp_b200_batch_download_all(ellp_b200_ctx* ctx, double* A, double* c, double* b) {
+    if (!ctx) return ELLP_E_ARG;
+    auto& B = ctx->batch;
+    if (B.nlp <= 0) return ELLP_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t L = (size_t)B.nlp;
+    if (A) CUDA_TRY(cudaMemcpy(A, B.A, sizeof(double) * L * B.m * B.n0, cudaMemcpyDeviceToHost));
+    if (c) CUDA_TRY(cudaMemcpy(c, B.c, sizeof(double) * L * B.n0, cudaMemcpyDeviceToHost));
+    if (b) CUDA_TRY(cudaMemcpy(b, B.b, sizeof(double) * L * B.m, cudaMemcpyDeviceToHost));
+    return ELLP_OK;
+}
+
+int ellp_b200_primal_solve_batch(ellp_b200_ctx* ctx, const ellp_batch* bt, const ellp_opts* o, ellp_batch_result* res) {
+    if (!ctx || !bt || !o || !res) return ELLP_E_ARG;
+    if (int rc = ellp_b200_batch_upload(ctx, bt, res->trace ? res->trace_cap : 0)) return rc;
+    if (int rc = ellp_b200_batch_run(ctx, o, res)) return rc;
+    return ellp_b200_batch_download(ctx, res);
 }
 
 int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {

@@ -194,3 +194,41 @@ def parse_mps(text: str) -> Problem:
         return p
     finally:
         N.lib.ellp_b200_model_free(h)
+
+
+@dataclass
+class BatchSolveResult:
+    status: np.ndarray      # SolverResult codes per LP (0 Optimal, 1 Infeasible, 2 Unbounded, 3 MaxIter, -1 not solved)
+    obj: np.ndarray
+    x: np.ndarray           # (nlp, n + m) standard-form points (incl. artificial columns)
+    iters: np.ndarray       # (nlp, 2) pivots of phase 1 / phase 2
+    err: np.ndarray
+    trace: Optional[np.ndarray]
+    trace_len: Optional[np.ndarray]
+    ms_device: float
+    pivots: int
+
+
+def primal_solve_batch(A, c, b, kind, lb, ub, max_iter: Optional[int] = 1000, tie_rule: int = N.TIES_REFERENCE,
+                       trace_cap: int = 0, ctx: Optional[N.Context] = None) -> BatchSolveResult:
+    """K6: PrimalSimplexSolver::solve (minus the standard-form step) for a batch of equally-shaped standard forms,
+    one CTA per LP, one launch (include/ellp_b200.h: ellp_b200_primal_solve_batch).
+    A: (nlp, m, n) with each LP column-major (i.e. pass np.asfortranarray per LP stacked) -- here given as (nlp, n, m)
+    C-contiguous = per-LP column-major; c, kind, lb, ub: (nlp, n); b: (nlp, m)."""
+    ctx = ctx or default_context()
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    nlp, n, m = A.shape  # (nlp, n, m) C-order == column-major m x n per LP
+    c = np.ascontiguousarray(c, dtype=np.float64); b = np.ascontiguousarray(b, dtype=np.float64)
+    kind = np.ascontiguousarray(kind, dtype=np.uint8); lb = np.ascontiguousarray(lb, dtype=np.float64); ub = np.ascontiguousarray(ub, dtype=np.float64)
+    bt = N.Batch(nlp, m, n, N.ptr(A), N.ptr(c), N.ptr(b), N.ptr(kind), N.ptr(lb), N.ptr(ub))
+    status = np.zeros(nlp, dtype=np.int32); obj = np.zeros(nlp); x = np.zeros((nlp, n + m)); iters = np.zeros((nlp, 2), dtype=np.int32)
+    err = np.zeros(nlp, dtype=np.int32)
+    tr = np.zeros((nlp, max(trace_cap, 1)), dtype=N.TRACE_DTYPE) if trace_cap else None
+    tl = np.zeros(nlp, dtype=np.int32)
+    res = N.BatchResult(N.ptr(status), N.ptr(obj), N.ptr(x), N.ptr(iters), N.ptr(err), N.ptr(tr) if trace_cap else None, trace_cap,
+                        N.ptr(tl), 0.0, 0, 0)
+    o = N.default_opts(max_iter, tie_rule)
+    rc = N.lib.ellp_b200_primal_solve_batch(ctx.h, C.byref(bt), C.byref(o), C.byref(res))
+    if rc != N.OK:
+        _raise(ctx, rc)
+    return BatchSolveResult(status, obj, x, iters, err, tr, tl, float(res.ms_device), int(res.pivots))

@@ -145,6 +145,38 @@ int ellp_b200_download_std_form(ellp_b200_ctx*, double* A, double* c, double* b,
 /* tuning knobs: "rank1_cols_per_cta", "rank1_stream_min_mb" */
 int ellp_b200_set_tuning(ellp_b200_ctx*, const char* key, int value);
 
+/* ---- K6: batches of independent small LPs (BASELINE.json configs[3]) -------------------------------------------
+ * Every LP of the batch has the same standard-form shape m x n and no Free variable; LP k sits at offset k*m*n (A,
+ * column-major, lda = m), k*n (c, kind, lb, ub), k*m (b).  One CTA per LP performs PrimalPhase1::from + phase 1 +
+ * verdict + PrimalPhase2::from + phase 2 (primal_problem.rs:95-141,234-291, primal_simplex_solver.rs:32-93) with the
+ * tableau resident in shared memory: one kernel launch for the whole batch.  Needs (m+1)*(n+m)*8 bytes <= ~210 KB.
+ * Multi-GPU: shard the batch over processes / GPUs; no collective is involved. */
+typedef struct {
+    int32_t nlp, m, n;
+    const double* A; const double* c; const double* b; const uint8_t* kind; const double* lb; const double* ub;
+} ellp_batch;
+typedef struct {
+    int32_t* status;      /* nlp: ELLP_OPTIMAL.. ; -1 = not solved (see err) */
+    double*  obj;         /* nlp: Solution::obj() (c.x over all standard-form columns) */
+    double*  x;           /* nlp * (n + m): standard-form point incl. the m artificial columns (may be NULL) */
+    int32_t* iters;       /* 2 * nlp: pivots of phase 1 and phase 2 */
+    int32_t* err;         /* nlp: 0, a device panic id, -100 = Free variable present (use ellp_b200_solve), 5 = singular */
+    ellp_trace_rec* trace;/* nlp * trace_cap or NULL */
+    int32_t  trace_cap;
+    int32_t* trace_len;   /* nlp or NULL */
+    double   ms_device;
+    uint64_t launches;
+    uint64_t pivots;      /* sum of iters */
+} ellp_batch_result;
+int ellp_b200_primal_solve_batch(ellp_b200_ctx*, const ellp_batch*, const ellp_opts*, ellp_batch_result*);  /* host buffers */
+/* device-resident variants (bench): synthetic batch of configs[3] built in HBM, LP ids first_lp .. first_lp+nlp-1 */
+int ellp_b200_batch_generate(ellp_b200_ctx*, int32_t nlp, int32_t m, int32_t n_struct, uint64_t seed, int64_t first_lp, int32_t trace_cap);
+int ellp_b200_batch_upload(ellp_b200_ctx*, const ellp_batch*, int32_t trace_cap);
+int ellp_b200_batch_run(ellp_b200_ctx*, const ellp_opts*, ellp_batch_result*);      /* fills ms_device, launches */
+int ellp_b200_batch_download(ellp_b200_ctx*, ellp_batch_result*);                   /* fills the non-NULL arrays, pivots */
+int ellp_b200_batch_download_lp(ellp_b200_ctx*, int32_t k, double* A, double* c, double* b);
+int ellp_b200_batch_download_all(ellp_b200_ctx*, double* A, double* c, double* b);   /* whole resident batch */
+
 /* ---- column-sharded tableau: one process per GPU (BASELINE.json configs[4]) ----------------------------------
  * Rank g stores global columns [g*n/G, (g+1)*n/G) of the tableau and of the reduced-cost row; x, the basis list and
  * the bounds are replicated.  Per pivot: local pricing, two tiny NCCL all-gathers (arg-select with the order-free

@@ -347,3 +347,74 @@ def test_generated_dual_lp_matches_numpy_twin_and_oracle(env):
     k = len(ref.trace)
     assert res.status == ref.status and res.iters == k > 5
     assert (tr["entering"][:k] == ref.trace["entering"]).all() and (tr["leaving"][:k] == ref.trace["leaving"]).all()
+
+
+# ---------------------------------------------------------------- K6: shared-memory batched kernel
+def _std_form_of(env, prob):
+    """Option<StandardForm>::from(Problem) through the product's host layer (ellp_b200_stage_new, which = 0)."""
+    N = env["N"]
+    arr = prob.to_arrays()
+    desc, _keep = N.problem_desc(arr)
+    h = C.c_void_p(); infeasible = C.c_int(0); err = C.create_string_buffer(256)
+    assert N.lib.ellp_b200_stage_new(C.byref(desc), 0, C.byref(h), C.byref(infeasible), err) == N.OK
+    assert not infeasible.value
+    dims = [C.c_int32() for _ in range(7)]
+    N.lib.ellp_b200_stage_dims(h, *[C.byref(v) for v in dims])
+    m, n = dims[0].value, dims[1].value
+    A = np.zeros((m, n), order="F"); c = np.zeros(n); b = np.zeros(m); kind = np.zeros(n, dtype=np.uint8); lb = np.zeros(n); ub = np.zeros(n)
+    N.lib.ellp_b200_stage_copy(h, N.ptr(A), N.ptr(c), N.ptr(b), N.ptr(kind), N.ptr(lb), N.ptr(ub), None, None, None, None, None, None)
+    N.lib.ellp_b200_stage_free(h)
+    return m, n, A, c, b, kind, lb, ub
+
+
+@pytest.mark.parametrize("name", P.NETLIB + ["small_prob_2", "small_prob_3", "small_prob_5", "small_prob_6", "beale_cycle",
+                                             "small_prob_unbounded_1", "two_variables_infeasible_with_bounds"])
+def test_batch_kernel_single_lp_follows_oracle_pivot_for_pivot(env, name):
+    """One launch solves the whole two-phase primal; same status, objective, point and pivot sequence as the oracle."""
+    S, O = env["S"], env["O"]
+    prob, exp = P.netlib(name) if name in P.NETLIB else P.GOLDEN_BY_NAME[name]()
+    m, n, A, c, b, kind, lb, ub = _std_form_of(env, prob)
+    r = S.primal_solve_batch(A.T[None].copy(), c[None], b[None], kind[None], lb[None], ub[None], 1000, trace_cap=4096, ctx=env["ctx"])
+    ref = O.solve(prob, O.PRIMAL, 1000, O.MODE_EXACT, trace_cap=4096)
+    assert r.err[0] == 0
+    assert r.status[0] == ref.status
+    assert list(r.iters[0]) == ref.iters[:2]
+    k = len(ref.trace)
+    assert r.trace_len[0] == k
+    assert (r.trace[0]["entering"][:k] == ref.trace["entering"]).all() and (r.trace[0]["leaving"][:k] == ref.trace["leaving"]).all()
+    if ref.status == O.OPTIMAL:
+        assert _rel(r.obj[0], ref.obj) < 1e-9
+        nv = len(prob.variables)
+        np.testing.assert_allclose(r.x[0][:nv], ref.x, rtol=1e-9, atol=1e-9)
+        P.check_expectation(exp, "Optimal", r.obj[0], r.x[0][:nv])
+
+
+def test_batch_kernel_generated_batch_matches_oracle(env):
+    """configs[3] generator at reduced count: every LP of the batch agrees with the oracle's solve() on the same LP
+    (status, objective 1e-9, pivot counts per phase)."""
+    from ellp_b200.problem import Bound, ConstraintOp, Problem
+    N, O, ctx = env["N"], env["O"], env["ctx"]
+    for (nlp, m, ns, seed) in [(40, 16, 24, 3), (300, 64, 128, 0)]:
+        ctx.check(N.lib.ellp_b200_batch_generate(ctx.h, nlp, m, ns, seed, 0, 0))
+        o = N.default_opts(None)
+        res = N.BatchResult()
+        ctx.check(N.lib.ellp_b200_batch_run(ctx.h, C.byref(o), C.byref(res)))
+        n0 = ns + m
+        status = np.zeros(nlp, dtype=np.int32); obj = np.zeros(nlp); x = np.zeros((nlp, n0 + m)); iters = np.zeros((nlp, 2), dtype=np.int32); err = np.zeros(nlp, dtype=np.int32)
+        out = N.BatchResult(N.ptr(status), N.ptr(obj), N.ptr(x), N.ptr(iters), N.ptr(err), None, 0, None, 0.0, 0, 0)
+        ctx.check(N.lib.ellp_b200_batch_download(ctx.h, C.byref(out)))
+        assert (err == 0).all() and (status == N.OPTIMAL).all()
+        assert out.pivots == iters.sum()
+        for k in ([0, 1, nlp - 1] if m == 64 else range(0, nlp, 7)):
+            A = np.zeros((m, n0), order="F"); c = np.zeros(n0); b = np.zeros(m)
+            ctx.check(N.lib.ellp_b200_batch_download_lp(ctx.h, k, N.ptr(A), N.ptr(c), N.ptr(b)))
+            p = Problem.new()
+            ids = [p.add_var(c[j], Bound.Lower(0.0)) for j in range(ns)]
+            for i in range(m):
+                p.add_constraint([(ids[j], A[i, j]) for j in range(ns)], ConstraintOp.Lte, b[i])
+            ref = O.solve(p, O.PRIMAL, None, O.MODE_EXACT)
+            assert ref.status == O.OPTIMAL
+            assert _rel(obj[k], ref.obj) < 1e-9
+            np.testing.assert_allclose(x[k][:ns], ref.x, rtol=1e-9, atol=1e-9)
+            assert list(iters[k]) == ref.iters[:2], (k, iters[k], ref.iters)
+        print(f"batch {nlp} x ({m}x{ns}): {res.ms_device:.3f} ms, {out.pivots} pivots, {out.pivots / res.ms_device / 1e3:.2f} M pivots/s")
