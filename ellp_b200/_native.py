@@ -124,6 +124,7 @@ def _load():
         "ellp_b200_gemv_t": (C.c_int, [vp, vp, i64, i64, i64, vp, i64, vp, vp]),
         "ellp_b200_gemv_n": (C.c_int, [vp, vp, i64, i64, i64, vp, vp]),
         "ellp_b200_invert": (C.c_int, [vp, vp, i64, vp]),
+        "ellp_b200_refactor_bench": (C.c_int, [vp, i32, u64, i32, i32, C.POINTER(C.c_float)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here == the .so does not export what the header declares

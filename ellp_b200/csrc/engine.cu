@@ -15,6 +15,7 @@
 #include "engine.hpp"
 #include "kernels.cuh"
 #include "batch.cuh"
+#include "refactor.cuh"
 
 using namespace ellp;
 
@@ -89,7 +90,8 @@ struct ellp_b200_ctx {
     } batch;
     // tuning (ellp_b200_set_tuning)
     int rank1_cols_per_cta = 8;
-    int rank1_stream_min_mb = 96;  // evict-first policy when the updated matrix is larger than this
+    int rank1_stream_min_mb = 96;
+    int refactor_mode = 0;        // 0 auto (blocked LU + DMMA for m >= 128, Gauss-Jordan below), 1 Gauss-Jordan, 2 blocked LU  // evict-first policy when the updated matrix is larger than this
 };
 
 extern "C" { static void batch_free(ellp_b200_ctx* ctx); }
@@ -194,6 +196,7 @@ void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap, bool tableau, bool sh
     lp.prow = a.take<double>((tableau ? n : 2 * m) + 8);
     lp.part = a.take<double>(tableau ? 8 : (size_t)KS * ld);
     lp.lam = a.take<double>(std::max<size_t>(m, 1));
+    lp.lu_piv = a.take<int32_t>(std::max<size_t>(m, 1));
     lp.trace = trace_cap > 0 ? a.take<ellp_trace_rec>((size_t)trace_cap) : nullptr;
     if (sharded) {
         lp.colstat = a.take<uint8_t>(n);
@@ -251,7 +254,33 @@ int refactor(ellp_b200_ctx* ctx, uint64_t* count) {
     // preserve the iteration's index-level state around the factorisation
     if (int rc = read_state(ctx)) return rc;
     PivotState saved = *ctx->h_st;
-    if (!ctx->tableau) {
+    const bool use_lu = !ctx->tableau && (ctx->refactor_mode == 2 || (ctx->refactor_mode == 0 && m >= 128));
+    if (use_lu) {
+        // K4: blocked partial-pivot LU of [A_B | I] with DMMA trailing updates, then the blocked back substitution (refactor.cuh)
+        LAUNCH(k_gj_init, 2 * m, 256, lp);
+        double* G = lp.G;
+        const int64_t ld = lp.ld;
+        const int ncols = 2 * m;
+        for (int k0 = 0; k0 < m; k0 += kPanel) {
+            const int nb = std::min(kPanel, m - k0), c0 = k0 + nb;
+            LAUNCH(k_lu_panel, 1, 1024, G, ld, m, k0, nb, lp.lu_piv, ctx->d_st);
+            LAUNCH(k_lu_swap_rows, (ncols - nb + 255) / 256, 256, G, ld, ncols, k0, nb, lp.lu_piv, ctx->d_st);
+            LAUNCH(k_lu_trsm_lower, (ncols - c0 + 127) / 128, 128, G, ld, ncols, k0, nb, c0, ctx->d_st);
+            const int M = m - c0, N = ncols - c0;
+            if (M > 0) {
+                dim3 grid((unsigned)((M + kGemmTile - 1) / kGemmTile), (unsigned)((N + kGemmTile - 1) / kGemmTile));
+                LAUNCH(k_dgemm_sub_dmma, grid, 256, G + (int64_t)c0 * ld + c0, G + (int64_t)k0 * ld + c0, G + (int64_t)c0 * ld + k0, ld, M, N, nb, ctx->d_st);
+            }
+        }
+        for (int k0 = ((m - 1) / kPanel) * kPanel; k0 >= 0; k0 -= kPanel) {
+            const int nb = std::min(kPanel, m - k0);
+            LAUNCH(k_lu_trsm_upper, (m + 127) / 128, 128, G, ld, ncols, k0, nb, m, ctx->d_st);
+            if (k0 > 0) {
+                dim3 grid((unsigned)((k0 + kGemmTile - 1) / kGemmTile), (unsigned)((m + kGemmTile - 1) / kGemmTile));
+                LAUNCH(k_dgemm_sub_dmma, grid, 256, G + (int64_t)m * ld, G + (int64_t)k0 * ld, G + (int64_t)m * ld + k0, ld, k0, m, nb, ctx->d_st);
+            }
+        }
+    } else if (!ctx->tableau) {
         LAUNCH(k_gj_init, 2 * m, 256, lp);
         for (int k = 0; k < m; ++k) {
             LAUNCH(k_gj_pivot, 1, 1024, lp.G, lp.ld, m, (const int32_t*)nullptr, k, lp.dcol, ctx->d_st);
@@ -477,6 +506,7 @@ int ellp_b200_set_tuning(ellp_b200_ctx* ctx, const char* key, int value) {
     if (!ctx || !key) return ELLP_E_ARG;
     if (!std::strcmp(key, "rank1_cols_per_cta")) ctx->rank1_cols_per_cta = value;
     else if (!std::strcmp(key, "rank1_stream_min_mb")) ctx->rank1_stream_min_mb = value;
+    else if (!std::strcmp(key, "refactor_mode")) ctx->refactor_mode = value;
     else return set_err(ctx, ELLP_E_ARG, std::string("unknown tuning key ") + key);
     return ELLP_OK;
 }
@@ -1204,6 +1234,36 @@ int ellp_b200_gemv_n(ellp_b200_ctx* ctx, const double* M, int64_t R, int64_t C, 
     CUDA_TRY(cudaMemcpy(y, dy, sizeof(double) * R, cudaMemcpyDeviceToHost));
     cudaFree(dM); cudaFree(dv); cudaFree(dy); cudaFree(dp);
     return ELLP_OK;
+}
+
+int ellp_b200_refactor_bench(ellp_b200_ctx* ctx, int32_t m, uint64_t seed, int32_t mode, int32_t reps, float* ms_avg) {
+    // times the refactorisation (K4) of a dense random m x m basis that never leaves HBM
+    if (!ctx || m <= 0 || (m % 4) != 0 || reps < 1) return ELLP_E_ARG;
+    ellp_opts o;
+    ellp_b200_default_opts(&o);
+    o.engine = ELLP_ENGINE_REVISED;
+    if (int rc = ellp_b200_generate_dense_ex(ctx, m, m, seed, 0, &o)) return rc;
+    std::vector<int32_t> B((size_t)m);
+    for (int i = 0; i < m; ++i) B[i] = i;  // basis = the m dense structural columns
+    CUDA_TRY(cudaMemcpy(ctx->lp.Bv, B.data(), sizeof(int32_t) * m, cudaMemcpyHostToDevice));
+    std::memset(ctx->h_st, 0, sizeof(PivotState));
+    if (int rc = write_state(ctx)) return rc;
+    const int saved = ctx->refactor_mode;
+    ctx->refactor_mode = mode;
+    int rc = refactor(ctx, nullptr);  // warm-up
+    float total = 0.f;
+    for (int k = 0; k < reps && rc == ELLP_OK; ++k) {
+        cudaEventRecord(ctx->ev0, ctx->stream);
+        rc = refactor(ctx, nullptr);
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        total += ms;
+    }
+    ctx->refactor_mode = saved;
+    if (ms_avg) *ms_avg = total / (float)reps;
+    return rc;
 }
 
 int ellp_b200_invert(ellp_b200_ctx* ctx, const double* Bmat, int64_t m, double* Binv) {

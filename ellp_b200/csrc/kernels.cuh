@@ -48,6 +48,7 @@ struct DevLP {
     double* prow;  // 2m: scaled pivot row consumed by k_rank1
     double* part;  // KS x ld split-K partial sums
     double* lam;   // m
+    int32_t* lu_piv;  // m: row pivots of the blocked LU refactorisation
     ellp_trace_rec* trace;
     // tableau engine (ELLP_ENGINE_TABLEAU): T = B^-1 A lives in the buffer of A (in place), dj = reduced costs
     double* T;     // ld x n, nullptr for the revised engine

@@ -269,6 +269,8 @@ int ellp_b200_gemv_n(ellp_b200_ctx*, const double* M, int64_t R, int64_t C, int6
 /* K4: explicit inverse of a dense m x m matrix (column-major, host buffers); returns ELLP_E_ELLP
  * "invalid B, A_B is not invertible" when a pivot is below EPS (primal :175-179). */
 int ellp_b200_invert(ellp_b200_ctx*, const double* Bmat, int64_t m, double* Binv);
+/* times K4 on a random dense m x m basis built in HBM; mode 1 = Gauss-Jordan, 2 = blocked LU + DMMA */
+int ellp_b200_refactor_bench(ellp_b200_ctx*, int32_t m, uint64_t seed, int32_t mode, int32_t reps, float* ms_avg);
 
 #ifdef __cplusplus
 }

@@ -418,3 +418,64 @@ def test_batch_kernel_generated_batch_matches_oracle(env):
             np.testing.assert_allclose(x[k][:ns], ref.x, rtol=1e-9, atol=1e-9)
             assert list(iters[k]) == ref.iters[:2], (k, iters[k], ref.iters)
         print(f"batch {nlp} x ({m}x{ns}): {res.ms_device:.3f} ms, {out.pivots} pivots, {out.pivots / res.ms_device / 1e3:.2f} M pivots/s")
+
+
+# ---------------------------------------------------------------- K4: blocked LU + DMMA refactorisation
+@pytest.mark.parametrize("m", [1, 2, 27, 33, 74, 128, 300, 513, 1000])
+def test_blocked_lu_dmma_inverse_matches_numpy_and_gauss_jordan(env, m):
+    N, ctx = env["N"], env["ctx"]
+    rng = np.random.default_rng(1000 + m)
+    Bm = np.asfortranarray(rng.standard_normal((m, m)) + 0.1 * np.eye(m))
+    inv_lu = np.zeros((m, m), order="F"); inv_gj = np.zeros((m, m), order="F")
+    try:
+        ctx.set_tuning("refactor_mode", 2)
+        ctx.check(N.lib.ellp_b200_invert(ctx.h, N.ptr(Bm), m, N.ptr(inv_lu)))
+        ctx.set_tuning("refactor_mode", 1)
+        ctx.check(N.lib.ellp_b200_invert(ctx.h, N.ptr(Bm), m, N.ptr(inv_gj)))
+    finally:
+        ctx.set_tuning("refactor_mode", 0)
+    tol = 1e-9 * np.linalg.cond(Bm)
+    np.testing.assert_allclose(inv_lu @ Bm, np.eye(m), atol=tol)
+    np.testing.assert_allclose(inv_lu, inv_gj, atol=tol, rtol=1e-7)
+
+
+def test_blocked_lu_detects_singular_basis_and_times_large_inverse(env):
+    import time
+    from ellp_b200.problem import EllPError
+    N, ctx = env["N"], env["ctx"]
+    m = 200
+    Bm = np.asfortranarray(np.random.default_rng(5).standard_normal((m, m)))
+    Bm[:, 77] = Bm[:, 3]  # rank deficient => a pivot below EPS
+    inv = np.zeros((m, m), order="F")
+    try:
+        ctx.set_tuning("refactor_mode", 2)
+        rc = N.lib.ellp_b200_invert(ctx.h, N.ptr(Bm), m, N.ptr(inv))
+        assert rc == N.E_ELLP and b"invalid B, A_B is not invertible" in N.lib.ellp_b200_last_error(ctx.h)
+        m = 2048
+        Bm = np.asfortranarray(np.random.default_rng(6).standard_normal((m, m)) + 3 * np.eye(m))
+        inv = np.zeros((m, m), order="F")
+        for mode, name in ((2, "blocked LU + DMMA"), (1, "Gauss-Jordan")):
+            ctx.set_tuning("refactor_mode", mode)
+            ctx.check(N.lib.ellp_b200_invert(ctx.h, N.ptr(Bm), m, N.ptr(inv)))
+            t0 = time.perf_counter()
+            ctx.check(N.lib.ellp_b200_invert(ctx.h, N.ptr(Bm), m, N.ptr(inv)))
+            dt = time.perf_counter() - t0
+            np.testing.assert_allclose(inv @ Bm, np.eye(m), atol=1e-8)
+            print(f"invert m={m} {name}: {dt * 1e3:.1f} ms incl. 2 x 32 MB PCIe copies ({2.67 * m ** 3 / dt / 1e12:.2f} TFLOP/s equivalent)")
+    finally:
+        ctx.set_tuning("refactor_mode", 0)
+
+
+@pytest.mark.parametrize("which", ["primal", "dual"])
+def test_solver_parity_with_lu_refactorisation_every_few_pivots(env, which):
+    # refactorising often with the blocked LU must not change status / objective (netlib BLEND, m = 74)
+    prob, exp = P.netlib("blend")
+    ctx, O = env["ctx"], env["O"]
+    try:
+        ctx.set_tuning("refactor_mode", 2)
+        res = _solver(env, which, refactor_every=7).solve(prob)
+    finally:
+        ctx.set_tuning("refactor_mode", 0)
+    ref = O.solve(prob, O.PRIMAL if which == "primal" else O.DUAL, 1000, O.MODE_EXACT)
+    assert res.is_optimal and _rel(res.solution.obj(), ref.obj) < 1e-9
+    P.check_expectation(exp, res.kind, res.solution.obj(), res.solution.x())
