@@ -38,6 +38,8 @@ WORKLOADS = {
     # BASELINE.json configs[2] shape: dense 4096x8192 (Gte rows => standard form 4096x12288), DUAL simplex, revised engine
     # (explicit basis inverse).  The entering/leaving rules are the reference's (steepest edge is not built yet).
     "dense_revised_dual_4096x12288": dict(m=4096, ns=8192, pivots=200, sample_m=512, sample_pivots=6, dual=True),
+    # the same LP with dual steepest edge (exact weights from the rank-1 update's epilogue) + Harris ratio test
+    "dense_revised_dual_dse_4096x12288": dict(m=4096, ns=8192, pivots=200, sample_m=512, sample_pivots=6, dual=True, dse=True),
     "dense_tableau_tiny": dict(m=256, ns=256, pivots=20, sample_m=128, sample_pivots=4),
     # BASELINE.json configs[3]: "batch of 65536 independent small LPs (64x128), sharded one shard per GPU at 1/2/4/8 B200"
     "batch_small_lps_65536x64x128": dict(batch=True, nlp=65536, m=64, ns=128, sample_lps=150),
@@ -287,13 +289,23 @@ def run_ours(args, wl, name):
     n = m + ns
     dual = bool(wl.get("dual"))
     engine = N.ENGINE_REVISED if dual else N.ENGINE_TABLEAU
-    o = N.default_opts(P, engine=engine, check_every=min(P, 16), profile=True)
+    rules = dict(pricing=N.PRICE_STEEPEST_EDGE, ratio=N.RATIO_HARRIS) if wl.get("dse") else {}
+    o = N.default_opts(P, engine=engine, check_every=min(P, 16), profile=True, **rules)
     ctx.check(N.lib.ellp_b200_generate_dense_ex(ctx.h, m, ns, SEED, 1 if dual else 0, C.byref(o)))
 
+    full_solve = bool(wl.get("dse"))  # steepest edge reaches the optimum within a few hundred pivots: a step = one whole solve
+    if full_solve:
+        o.max_iter = N.U64_MAX
+
     def step():
+        if full_solve:  # rebuild the LP in HBM (0.1 ms) and solve it to optimality
+            ctx.check(N.lib.ellp_b200_generate_dense_ex(ctx.h, m, ns, SEED, 1 if dual else 0, C.byref(o)))
         res = N.Result()
         ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(o), C.byref(res)))
-        assert res.status == N.MAXITER and res.iters == P, (res.status, res.iters)
+        if full_solve:
+            assert res.status == N.OPTIMAL, res.status
+        else:
+            assert res.status == N.MAXITER and res.iters == P, (res.status, res.iters)
         return res
 
     for _ in range(args.warmup):
@@ -306,15 +318,17 @@ def run_ours(args, wl, name):
     t0 = time.perf_counter()
     dev_ms = rank1_ms = 0.0
     n_rank1 = 0
+    pivots_done = 0
     for _ in range(args.steps):
         r = step()
-        dev_ms += r.ms_device; rank1_ms += r.ms_rank1; n_rank1 += r.n_rank1
+        dev_ms += r.ms_device; rank1_ms += r.ms_rank1; n_rank1 += r.n_rank1; pivots_done += r.iters
     ctx.check(N.lib.ellp_b200_sync(ctx.h))
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     launches = ctx.launch_count() - launches0
     clk = clocks.stop()
-    value = args.steps * P / dt
+    value = pivots_done / dt
+    P = pivots_done // args.steps
 
     # roofline of the dominant kernel (K3 rank-1 update of the m x n tableau): algorithmic bytes per launch
     peak, peak_src = measured_peak()
@@ -348,7 +362,7 @@ def run_ours(args, wl, name):
         y0 = np.zeros(m); d0 = c_h.copy()
         B0 = np.arange(ns, n, dtype=np.int32); N0 = np.arange(ns, dtype=np.int32); Ns0 = np.zeros(ns, dtype=np.uint8)
         sf = N.StdForm(m, n, N.ptr(A_np), N.ptr(c_h), N.ptr(b_h), N.ptr(kind_h), N.ptr(lb_h), N.ptr(ub_h))
-        oe = N.default_opts(P, engine=engine, check_every=min(P, 16))
+        oe = N.default_opts(P, engine=engine, check_every=min(P, 16), **rules)
         xs = torch.empty(n, dtype=torch.float64, pin_memory=True).numpy()
 
         def e2e_step():
@@ -359,12 +373,17 @@ def run_ours(args, wl, name):
             res = N.Result()
             fn = N.lib.ellp_b200_dual_solve_with_initial if dual else N.lib.ellp_b200_primal_solve_with_initial
             ctx.check(fn(ctx.h, C.byref(sf), C.byref(pt), C.byref(oe), C.byref(res)))
-            assert res.status == N.MAXITER and res.iters == P
+            assert (res.status == N.OPTIMAL) if full_solve else (res.status == N.MAXITER and res.iters == P)
+            e2e_pivots[0] += res.iters
             return res.obj
 
+        e2e_pivots = [0]
+        if full_solve:
+            oe.max_iter = N.U64_MAX
         for _ in range(min(args.warmup, 3)):
             e2e_step()
         torch.cuda.synchronize()
+        e2e_pivots[0] = 0
         t0 = time.perf_counter()
         for _ in range(args.steps):
             obj = e2e_step()
@@ -372,7 +391,7 @@ def run_ours(args, wl, name):
         dte = time.perf_counter() - t0
         h2d = 8 * m * n + 8 * (3 * n + m) + n + 8 * n + 4 * m + 4 * ns + ns
         d2h = 8 * n + 4 * m + 4 * ns + ns + 120 * ((P + 15) // 16)
-        e2e = {"value": args.steps * P / dte, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        e2e = {"value": e2e_pivots[0] / dte, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": 1e3 * dte / args.steps, "api": "ellp_b200_%s_solve_with_initial (host buffers, pinned)" % ("dual" if dual else "primal"),
                "objective_after_step": obj}
         del A_h
@@ -387,7 +406,7 @@ def run_ours(args, wl, name):
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": name, "m": m, "n": n, "pivots_per_step": P, "engine": "revised (explicit B^-1), dual simplex" if dual else "tableau (B^-1 A resident, in place)",
-                       "tie_rule": "reference folds", "l2": (f"A_N {8.0 * m * ns / 1e6:.0f} MB + B^-1 {8.0 * m * m / 1e6:.0f} MB streamed every pivot (> 126 MB L2, no flush)" if dual
+                       "tie_rule": "reference folds", "dual_rules": "steepest edge + Harris" if wl.get("dse") else "reference (first infeasible / first min ratio)", "l2": (f"A_N {8.0 * m * ns / 1e6:.0f} MB + B^-1 {8.0 * m * m / 1e6:.0f} MB streamed every pivot (> 126 MB L2, no flush)" if dual
                               else f"tableau {8.0 * m * n / 1e9:.1f} GB >> 126 MB L2 (no flush needed)"),
                        "baseline_config": "BASELINE.json configs[4]" if name == DEFAULT_WORKLOAD else "north_star / smaller variant"},
             "device_ms_per_step": dev_ms / args.steps, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,

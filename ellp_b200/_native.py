@@ -19,6 +19,8 @@ OPTIMAL, INFEASIBLE, UNBOUNDED, MAXITER = 0, 1, 2, 3
 PRIMAL, DUAL = 0, 1
 TIES_REFERENCE, TIES_CANONICAL = 0, 1
 ENGINE_AUTO, ENGINE_REVISED, ENGINE_TABLEAU = 0, 1, 2
+PRICE_REFERENCE, PRICE_STEEPEST_EDGE = 0, 1
+RATIO_REFERENCE, RATIO_HARRIS = 0, 1
 U64_MAX = 2**64 - 1
 
 TRACE_DTYPE = np.dtype([("phase", "<i4"), ("iter", "<i4"), ("entering", "<i4"), ("leaving", "<i4"),
@@ -38,7 +40,7 @@ class Point(C.Structure):
 class Opts(C.Structure):
     _fields_ = [("max_iter", C.c_uint64), ("tie_rule", C.c_int32), ("engine", C.c_int32),
                 ("refactor_every", C.c_int32), ("check_every", C.c_int32), ("phase_tag", C.c_int32),
-                ("profile", C.c_int32), ("trace", C.c_void_p), ("trace_cap", C.c_int64)]
+                ("profile", C.c_int32), ("trace", C.c_void_p), ("trace_cap", C.c_int64), ("pricing", C.c_int32), ("ratio", C.c_int32)]
 
 
 class Result(C.Structure):
@@ -180,7 +182,7 @@ class Context:
 
 
 def default_opts(max_iter: Optional[int] = 1000, tie_rule: int = TIES_REFERENCE, refactor_every: int = 0,
-                 check_every: int = 0, profile: bool = False, engine: int = ENGINE_AUTO) -> Opts:
+                 check_every: int = 0, profile: bool = False, engine: int = ENGINE_AUTO, pricing: int = 0, ratio: int = 0) -> Opts:
     o = Opts()
     lib.ellp_b200_default_opts(C.byref(o))
     o.max_iter = U64_MAX if max_iter is None else int(max_iter)
@@ -189,6 +191,8 @@ def default_opts(max_iter: Optional[int] = 1000, tie_rule: int = TIES_REFERENCE,
     o.check_every = check_every
     o.profile = 1 if profile else 0
     o.engine = engine
+    o.pricing = pricing
+    o.ratio = ratio
     return o
 
 

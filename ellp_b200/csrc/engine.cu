@@ -197,6 +197,13 @@ void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap, bool tableau, bool sh
     lp.part = a.take<double>(tableau ? 8 : (size_t)KS * ld);
     lp.lam = a.take<double>(std::max<size_t>(m, 1));
     lp.lu_piv = a.take<int32_t>(std::max<size_t>(m, 1));
+    if (!tableau) {
+        lp.w = a.take<double>(ld);
+        lp.npart = a.take<double>((m / kNormCols + 2) * ld);
+    } else {
+        lp.w = nullptr;
+        lp.npart = nullptr;
+    }
     lp.trace = trace_cap > 0 ? a.take<ellp_trace_rec>((size_t)trace_cap) : nullptr;
     if (sharded) {
         lp.colstat = a.take<uint8_t>(n);
@@ -234,13 +241,18 @@ int write_state(ellp_b200_ctx* ctx) {
 }
 
 void launch_rank1(ellp_b200_ctx* ctx, double* E, int64_t ld, int R, int C, const double* alpha, const double* prow,
-                  const PivotState* st, int r_fixed, double* dj = nullptr) {
+                  const PivotState* st, int r_fixed, double* dj = nullptr, double* npart = nullptr) {
     if (C <= 0 || R <= 0) return;
-    const int cpc = std::max(kColsInFlight, ctx->rank1_cols_per_cta);
+    const int cpc = npart ? kNormCols : std::max(kColsInFlight, ctx->rank1_cols_per_cta);
     dim3 grid((unsigned)((R + 2 * kRank1Threads - 1) / (2 * kRank1Threads)), (unsigned)((C + cpc - 1) / cpc));
     const bool stream = (double)ld * C * 8.0 > (double)ctx->rank1_stream_min_mb * 1048576.0;
-    if (stream) LAUNCH(k_rank1<true>, grid, kRank1Threads, E, ld, R, C, alpha, prow, st, r_fixed, cpc, dj);
-    else LAUNCH(k_rank1<false>, grid, kRank1Threads, E, ld, R, C, alpha, prow, st, r_fixed, cpc, dj);
+    if (npart) {
+        if (stream) LAUNCH((k_rank1<true, true>), grid, kRank1Threads, E, ld, R, C, alpha, prow, st, r_fixed, cpc, dj, npart);
+        else LAUNCH((k_rank1<false, true>), grid, kRank1Threads, E, ld, R, C, alpha, prow, st, r_fixed, cpc, dj, npart);
+    } else {
+        if (stream) LAUNCH((k_rank1<true, false>), grid, kRank1Threads, E, ld, R, C, alpha, prow, st, r_fixed, cpc, dj, npart);
+        else LAUNCH((k_rank1<false, false>), grid, kRank1Threads, E, ld, R, C, alpha, prow, st, r_fixed, cpc, dj, npart);
+    }
 }
 
 int gemv_grid(int ncols) { return std::max(1, std::min((ncols + 7) / 8, 148 * 32)); }
@@ -255,7 +267,19 @@ int refactor(ellp_b200_ctx* ctx, uint64_t* count) {
     if (int rc = read_state(ctx)) return rc;
     PivotState saved = *ctx->h_st;
     const bool use_lu = !ctx->tableau && (ctx->refactor_mode == 2 || (ctx->refactor_mode == 0 && m >= 128));
-    if (use_lu) {
+    bool diagonal = false;
+    if (!ctx->tableau && ctx->refactor_mode == 0) {  // slack / artificial bases: B is diagonal, invert it directly
+        int flags[2] = {0, 0};
+        CUDA_TRY(cudaMemsetAsync(ctx->d_flag, 0, 2 * sizeof(int), ctx->stream));
+        LAUNCH(k_check_diag_basis, m, 128, lp.A, lp.ld, m, lp.Bv, ctx->d_flag);
+        CUDA_TRY(cudaMemcpyAsync(flags, ctx->d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        diagonal = (flags[0] == 0);
+        if (diagonal && flags[1]) return set_err(ctx, ELLP_E_ELLP, dev_err_message(kErrSingular));
+    }
+    if (diagonal) {
+        LAUNCH(k_diag_inverse, m, 256, lp);
+    } else if (use_lu) {
         // K4: blocked partial-pivot LU of [A_B | I] with DMMA trailing updates, then the blocked back substitution (refactor.cuh)
         LAUNCH(k_gj_init, 2 * m, 256, lp);
         double* G = lp.G;
@@ -380,17 +404,31 @@ void launch_dual_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, bool profile,
     DevLP& lp = ctx->lp;
     PivotState* st = ctx->d_st;
     const int m = lp.m, nN = lp.nN;
-    LAUNCH(k_dual_leaving, 1, 1024, lp, st);                                                  // dual :200-236
+    const bool dse = o->pricing == ELLP_PRICE_STEEPEST_EDGE;
+    if (dse) LAUNCH(k_dual_leaving_dse, 1, 1024, lp, st);                                     // steepest edge (no reference counterpart)
+    else LAUNCH(k_dual_leaving, 1, 1024, lp, st);                                             // dual :200-236
     LAUNCH(k_gather_row, (m + 255) / 256, 256, lp.Binv, lp.ld, m, st, lp.rho, 0);             // rho = e_r^T B^-1 (:248-253)
     LAUNCH(k_gemv_t<EPI_PLAIN>, gemv_grid(nN), 256, lp.A, lp.ld, lp.Nv, nN, lp.rho, lp.rN,  // alpha = A_N^T rho (:255)
            (const double*)nullptr, (const uint8_t*)nullptr, (double*)nullptr, st, 0);
-    LAUNCH(k_select_dual, 1, 1024, lp, st);                                                   // :257-289
+    if (o->ratio == ELLP_RATIO_HARRIS) LAUNCH(k_select_dual_harris, 1, 1024, lp, 1e-9, st);
+    else LAUNCH(k_select_dual, 1, 1024, lp, st);                                              // :257-289
     dim3 fg((unsigned)((lp.ld + 255) / 256), (unsigned)ctx->KS);
     LAUNCH(k_ftran_partial, fg, 128, lp.Binv, lp.ld, m, lp.A, st, lp.part, ctx->kc);          // :294
-    LAUNCH(k_dual_update, 1, 1024, lp, ctx->KS, st);                                          // :296-333
+    LAUNCH(k_dual_update_vec, (std::max(m, nN) + 255) / 256, 256, lp, ctx->KS, st);           // :296-316
+    LAUNCH(k_dual_update_tail, 1, 32, lp, ctx->KS, st);                                       // :296, :302, :314-333
     if (profile && *ev_used + 2 <= ctx->ev.size()) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
-    launch_rank1(ctx, lp.Binv, lp.ld, m, m, lp.dcol, lp.prow, st, 0);
+    launch_rank1(ctx, lp.Binv, lp.ld, m, m, lp.dcol, lp.prow, st, 0, nullptr, dse ? lp.npart : nullptr);
     if (profile && (*ev_used & 1)) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
+    if (dse) LAUNCH(k_sum_norms, (m + 255) / 256, 256, lp.npart, lp.ld, m, (m + kNormCols - 1) / kNormCols, lp.w, st, 1);
+}
+
+// exact dual steepest-edge weights from the current basis inverse (start of a run / after a refactorisation)
+void launch_row_norms(ellp_b200_ctx* ctx) {
+    DevLP& lp = ctx->lp;
+    const int m = lp.m;
+    dim3 grid((unsigned)((m + 2 * kRank1Threads - 1) / (2 * kRank1Threads)), (unsigned)((m + kNormCols - 1) / kNormCols));
+    LAUNCH(k_rownorms_partial, grid, kRank1Threads, lp.Binv, lp.ld, m, m, kNormCols, lp.npart);
+    LAUNCH(k_sum_norms, (m + 255) / 256, 256, lp.npart, lp.ld, m, (m + kNormCols - 1) / kNormCols, lp.w, ctx->d_st, 0);
 }
 
 double host_dual_obj(const ellp_std_form* sf, const double* y, const double* d) {  // standard_form.rs:52-68
@@ -464,7 +502,7 @@ int ellp_b200_create(int device, ellp_b200_ctx** out) {
     auto* ctx = new ellp_b200_ctx();
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc(&ctx->d_st, sizeof(PivotState)) != cudaSuccess || cudaMalloc(&ctx->d_flag, sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_st, sizeof(PivotState)) != cudaSuccess || cudaMalloc(&ctx->d_flag, 4 * sizeof(int)) != cudaSuccess ||
         cudaMallocHost(&ctx->h_st, sizeof(PivotState)) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
         delete ctx;
@@ -938,6 +976,8 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
         if (int rc = refactor(ctx, &res->refactors)) return rc;
     }
     LAUNCH(k_init_cB, (int)((lp.ld + 255) / 256), 256, lp);
+    const bool dse = ctx->solver == ELLP_DUAL && !ctx->tableau && o->pricing == ELLP_PRICE_STEEPEST_EDGE;
+    if (dse) launch_row_norms(ctx);
     if (ctx->solver == ELLP_PRIMAL) LAUNCH(k_obj_dot, 1, 1024, lp.c, lp.x, lp.n_glob, ctx->d_st);
     int check_every = o->check_every > 0 ? o->check_every : (lp.m >= 2048 ? 1 : 8);
     int refactor_every = o->refactor_every > 0 ? o->refactor_every : ((lp.m <= 512 && !ctx->tableau) ? 100 : 0);
@@ -961,6 +1001,7 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
         if (h.status != kRunning) break;
         if (refactor_every > 0 && ctx->pivots_since_refactor >= (uint64_t)refactor_every) {
             if ((rc_loop = refactor(ctx, &res->refactors))) break;
+            if (dse) launch_row_norms(ctx);
         }
     }
     CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));

@@ -9,7 +9,7 @@
 //   k_ratio_primal              ratio fold, step, apply     primal :296-434, :205-232
 //   k_dual_leaving              first infeasible basic      dual :200-236
 //   k_select_dual               min-ratio entering          dual :257-289
-//   k_dual_update               d, y, x, obj, swap          dual :296-333
+//   k_dual_update_vec/_tail     d, y, x, obj, swap          dual :296-333
 //   k_gather_row / k_rank1      replace `A_B.clone().lu()`  primal :173, dual :241
 //   k_gj_*                      basis refactorisation (Gauss-Jordan with the LU's pivot rule)
 //
@@ -49,6 +49,8 @@ struct DevLP {
     double* part;  // KS x ld split-K partial sums
     double* lam;   // m
     int32_t* lu_piv;  // m: row pivots of the blocked LU refactorisation
+    double* w;        // ld: dual steepest-edge weights ||e_i^T B^-1||^2
+    double* npart;    // (m / kNormCols + 1) x ld: per-column-group partial row norms written by k_rank1<.., true>
     ellp_trace_rec* trace;
     // tableau engine (ELLP_ENGINE_TABLEAU): T = B^-1 A lives in the buffer of A (in place), dj = reduced costs
     double* T;     // ld x n, nullptr for the revised engine
@@ -666,11 +668,13 @@ __global__ void k_step_gather(DevLP lp, const double* __restrict__ E, int C, Piv
 constexpr int kRank1Threads = 256;
 constexpr int kColsInFlight = 8;
 
-template <bool STREAM>
+constexpr int kNormCols = 128;  // columns per CTA when the row norms ride along (keeps the partial-norm scratch at m^2/128 doubles)
+
+template <bool STREAM, bool NORMS>
 __global__ void __launch_bounds__(kRank1Threads) k_rank1(double* __restrict__ E, int64_t ld, int R, int C,
                                                          const double* __restrict__ alpha, const double* __restrict__ prow,
                                                          const PivotState* st, int r_fixed, int cols_per_cta,
-                                                         double* __restrict__ dj) {
+                                                         double* __restrict__ dj, double* __restrict__ npart) {
     int r = r_fixed;
     if (st) {
         if (!st->do_update) return;
@@ -691,6 +695,7 @@ __global__ void __launch_bounds__(kRank1Threads) k_rank1(double* __restrict__ E,
     na.y = (row + 1 < R) ? -na.y : 0.;  // a padding row (ld > R) is never modified: fma(0, p, e) == e for finite p
     const bool r0 = (row == r), r1 = (row + 1 == r);
     double* base = E + row;
+    double n0 = 0., n1 = 0.;  // NORMS: sum of squares of the UPDATED entries of this thread's two rows over the CTA's columns
     int j = c0;
     for (; j + kColsInFlight <= c1; j += kColsInFlight) {
         double2 e[kColsInFlight];
@@ -704,6 +709,7 @@ __global__ void __launch_bounds__(kRank1Threads) k_rank1(double* __restrict__ E,
         for (int u = 0; u < kColsInFlight; ++u) {
             e[u].x = r0 ? p[u] : fma(na.x, p[u], e[u].x);
             e[u].y = r1 ? p[u] : fma(na.y, p[u], e[u].y);
+            if (NORMS) { n0 = fma(e[u].x, e[u].x, n0); n1 = fma(e[u].y, e[u].y, n1); }
             if (STREAM) st_f64x2_stream(base + (int64_t)(j + u) * ld, e[u]);
             else st_f64x2(base + (int64_t)(j + u) * ld, e[u]);
         }
@@ -713,8 +719,10 @@ __global__ void __launch_bounds__(kRank1Threads) k_rank1(double* __restrict__ E,
         const double p = __ldg(prow + j);
         e.x = r0 ? p : fma(na.x, p, e.x);
         e.y = r1 ? p : fma(na.y, p, e.y);
+        if (NORMS) { n0 = fma(e.x, e.x, n0); n1 = fma(e.y, e.y, n1); }
         st_f64x2(base + (int64_t)j * ld, e);
     }
+    if (NORMS) st_f64x2(npart + (int64_t)blockIdx.y * ld + row, make_double2(n0, (row + 1 < R) ? n1 : 0.));
 }
 
 // scalar variant for matrices whose leading dimension is odd (kernel-level entry point only)
@@ -728,6 +736,32 @@ __global__ void k_rank1_scalar(double* __restrict__ E, int64_t ld, int R, int C,
         double* e = E + (int64_t)j * ld + i;
         *e = (i == r) ? p : fma(na, p, *e);
     }
+}
+
+// row norms of E without updating it (initial dual steepest-edge weights / after a refactorisation)
+__global__ void __launch_bounds__(kRank1Threads) k_rownorms_partial(const double* __restrict__ E, int64_t ld, int R, int C,
+                                                                    int cols_per_cta, double* __restrict__ npart) {
+    const int64_t row = ((int64_t)blockIdx.x * kRank1Threads + threadIdx.x) * 2;
+    if (row >= R) return;
+    const int c0 = blockIdx.y * cols_per_cta, c1 = min(C, c0 + cols_per_cta);
+    double n0 = 0., n1 = 0.;
+    for (int j = c0; j < c1; ++j) {
+        const double2 e = ld_f64x2(E + (int64_t)j * ld + row);
+        n0 = fma(e.x, e.x, n0);
+        n1 = fma(e.y, e.y, n1);
+    }
+    st_f64x2(npart + (int64_t)blockIdx.y * ld + row, make_double2(n0, (row + 1 < R) ? n1 : 0.));
+}
+
+// w_i = sum over column groups in a fixed order => the weights are bitwise reproducible
+__global__ void k_sum_norms(const double* __restrict__ npart, int64_t ld, int m, int groups, double* __restrict__ w, const PivotState* st,
+                            int need_update) {
+    if (need_update && !st->do_update) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    double a = 0.;
+    for (int g = 0; g < groups; ++g) a += npart[(int64_t)g * ld + i];
+    w[i] = a;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -836,59 +870,187 @@ __global__ void __launch_bounds__(1024) k_select_dual(DevLP lp, PivotState* st) 
     }
 }
 
-// dual :294-333
-__global__ void __launch_bounds__(1024) k_dual_update(DevLP lp, int KS, PivotState* st) {
+// dual steepest edge: leaving row = argmax infeasibility_i^2 / w_i (ties: smallest position); same outputs as k_dual_leaving
+__global__ void __launch_bounds__(1024) k_dual_leaving_dse(DevLP lp, PivotState* st) {
+    if (threadIdx.x == 0) st->do_update = 0;
     if (st->status != kRunning) return;
+    __shared__ double s_v[32];
+    __shared__ int s_i[32];
     const int tid = threadIdx.x;
-    const int m = lp.m;
-    const int r_pos = st->r_pos, q_pos = st->q_pos, q_var = st->q_var, leave_var = st->leave_var;
-    const double theta_d = st->theta_d, delta = st->delta;
-    for (int i = tid; i < m; i += blockDim.x) {  // alpha_q = B^-1 a_q
-        double a = 0.;
-        for (int ks = 0; ks < KS; ++ks) a += lp.part[(int64_t)ks * lp.ld + i];
-        lp.dcol[i] = a;
-    }
-    for (int j = tid; j < lp.nN; j += blockDim.x) {  // :298-300
-        const int var = lp.Nv[j];
-        lp.d[var] = lp.d[var] - theta_d * lp.rN[j];
-    }
-    for (int i = tid; i < m; i += blockDim.x) lp.y[i] = lp.y[i] + theta_d * lp.rho[i];  // :304
-    __syncthreads();
-    const double alpha_r = lp.dcol[r_pos];
-    const double theta_p = delta / alpha_r;  // :306
-    for (int i = tid; i < m; i += blockDim.x) {  // :310-312
+    const unsigned full = 0xffffffffu;
+    double bv = -1.;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < lp.m; i += blockDim.x) {
         const int var = lp.Bv[i];
-        lp.x[var] = lp.x[var] - theta_p * lp.dcol[i];
+        const double x_i = lp.x[var];
+        const int kind = lp.kind[var];
+        double p = 0.;
+        if ((kind == ELLP_LOWER || kind == ELLP_TWOSIDED) && x_i < lp.lb[var] - kEps) p = lp.lb[var] - x_i;
+        if ((kind == ELLP_UPPER || kind == ELLP_TWOSIDED) && x_i > lp.ub[var] + kEps) p = x_i - lp.ub[var];
+        if (p > 0.) {
+            const double score = p * p / fmax(lp.w[i], 1e-300);
+            if (score > bv) { bv = score; bi = i; }
+        }
     }
-    for (int j = tid; j < m; j += blockDim.x) lp.prow[j] = lp.rho[j] / alpha_r;  // scaled pivot row for k_rank1
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const double ov = __shfl_xor_sync(full, bv, off);
+        const int oi = __shfl_xor_sync(full, bi, off);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((tid & 31) == 0) { s_v[tid >> 5] = bv; s_i[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid < 32) {
+        bv = s_v[tid];
+        bi = s_i[tid];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const double ov = __shfl_xor_sync(full, bv, off);
+            const int oi = __shfl_xor_sync(full, bi, off);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (tid == 0) {
+            if (bi == 0x7fffffff) {
+                st->status = ELLP_OPTIMAL;
+            } else {
+                const int var = lp.Bv[bi];
+                const double x_i = lp.x[var];
+                const int kind = lp.kind[var];
+                double delta;
+                int side;
+                if ((kind == ELLP_UPPER || kind == ELLP_TWOSIDED) && x_i > lp.ub[var] + kEps) { delta = x_i - lp.ub[var]; side = ELLP_NB_UPPER; }
+                else { delta = x_i - lp.lb[var]; side = ELLP_NB_LOWER; }
+                st->r_pos = bi;
+                st->leave_var = var;
+                st->delta = delta;
+                st->new_side = side;
+            }
+        }
+    }
+}
+
+// Harris' two-pass dual ratio test: theta_max = min over eligible j of (d_j +- tol) / alpha~_j, then the largest |alpha~_j|
+// among { j : d_j / alpha~_j <= theta_max } (ties: first position)
+__global__ void __launch_bounds__(1024) k_select_dual_harris(DevLP lp, double tol, PivotState* st) {
+    if (st->status != kRunning) return;
+    __shared__ double s_t[32];
+    __shared__ int s_p[32];
+    const int tid = threadIdx.x;
+    const unsigned full = 0xffffffffu;
+    const bool neg = st->delta < 0.;
+    double tmin = CUDART_INF;
+    for (int j = tid; j < lp.nN; j += blockDim.x) {
+        double a = lp.rN[j];
+        if (neg) a = -a;
+        const int side = lp.Ns[j];
+        const bool keep = (side == ELLP_NB_LOWER) ? (a > kEps) : (side == ELLP_NB_UPPER ? (a < -kEps) : (fabs(a) > kEps));
+        if (keep) {
+            const double t = lp.d[lp.Nv[j]] / a + tol / fabs(a);
+            if (t < tmin) tmin = t;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) tmin = fmin(tmin, __shfl_xor_sync(full, tmin, off));
+    if ((tid & 31) == 0) s_t[tid >> 5] = tmin;
+    __syncthreads();
+    tmin = s_t[0];
+    for (int w = 1; w < 32; ++w) tmin = fmin(tmin, s_t[w]);
+    __syncthreads();
+    double ba = -1.;
+    int bp = 0x7fffffff;
+    for (int j = tid; j < lp.nN; j += blockDim.x) {
+        double a = lp.rN[j];
+        if (neg) a = -a;
+        const int side = lp.Ns[j];
+        const bool keep = (side == ELLP_NB_LOWER) ? (a > kEps) : (side == ELLP_NB_UPPER ? (a < -kEps) : (fabs(a) > kEps));
+        if (keep && lp.d[lp.Nv[j]] / a <= tmin && fabs(a) > ba) { ba = fabs(a); bp = j; }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const double oa = __shfl_xor_sync(full, ba, off);
+        const int op = __shfl_xor_sync(full, bp, off);
+        if (oa > ba || (oa == ba && op < bp)) { ba = oa; bp = op; }
+    }
+    if ((tid & 31) == 0) { s_t[tid >> 5] = ba; s_p[tid >> 5] = bp; }
     __syncthreads();
     if (tid == 0) {
-        lp.d[leave_var] = -theta_d;  // :296 (leaving variable is not in N, so the order vs :298 is immaterial)
-        lp.d[q_var] = 0.;            // :302
-        lp.x[q_var] = lp.x[q_var] + theta_p;  // :314
-        const int64_t t = st->trace_len;
-        if (lp.trace && t < st->trace_cap) {
-            ellp_trace_rec rec;
-            rec.phase = st->phase_tag;
-            rec.iter = (int32_t)st->pivots;
-            rec.entering = q_var;
-            rec.leaving = leave_var;
-            rec.step = theta_p;
-            rec.obj = st->obj;
-            lp.trace[t] = rec;
+        ba = -1.;
+        bp = 0x7fffffff;
+        for (int w = 0; w < 32; ++w) if (s_t[w] > ba || (s_t[w] == ba && s_p[w] < bp)) { ba = s_t[w]; bp = s_p[w]; }
+        if (bp == 0x7fffffff) st->status = ELLP_INFEASIBLE;  // dual unbounded
+        else {
+            double a = lp.rN[bp];
+            if (neg) a = -a;
+            const double t = lp.d[lp.Nv[bp]] / a;
+            st->q_pos = bp;
+            st->q_var = lp.Nv[bp];
+            st->q_side = lp.Ns[bp];
+            st->theta_d = neg ? -t : t;
         }
-        st->trace_len = t + 1;
-        st->obj = st->obj + theta_d * delta;  // :316
-        lp.Bv[r_pos] = q_var;                 // :322-323
-        lp.Nv[q_pos] = leave_var;
-        lp.Ns[q_pos] = (uint8_t)st->new_side;
-        lp.cB[r_pos] = lp.c[q_var];
-        st->alpha_r = alpha_r;
-        st->step = theta_p;
-        st->do_update = 1;
-        st->pivots += 1;
-        if (st->pivots >= st->max_iter) st->status = ELLP_MAXITER;  // :191-194 at the next loop head
     }
+}
+
+// dual :294-316, element-wise part over the whole grid: alpha_q = B^-1 a_q (sum of the split-K partials, fixed order),
+// d_N -= theta_d alpha, y += theta_d rho, x_B -= theta_p alpha_q, and the scaled pivot row for k_rank1.
+// Every thread re-derives alpha_q[r] itself (KS cached loads), so no second launch is needed to broadcast it.
+__global__ void __launch_bounds__(256) k_dual_update_vec(DevLP lp, int KS, const PivotState* st) {
+    if (st->status != kRunning) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = lp.m;
+    const int r_pos = st->r_pos;
+    const double theta_d = st->theta_d, delta = st->delta;
+    double alpha_r = 0.;
+    for (int ks = 0; ks < KS; ++ks) alpha_r += lp.part[(int64_t)ks * lp.ld + r_pos];
+    const double theta_p = delta / alpha_r;  // :306
+    if (t < m) {
+        double a = 0.;
+        for (int ks = 0; ks < KS; ++ks) a += lp.part[(int64_t)ks * lp.ld + t];
+        lp.dcol[t] = a;
+        const double rho = lp.rho[t];
+        lp.y[t] = lp.y[t] + theta_d * rho;       // :304
+        const int var = lp.Bv[t];
+        lp.x[var] = lp.x[var] - theta_p * a;     // :310-312
+        lp.prow[t] = rho / alpha_r;
+    }
+    if (t < lp.nN) {                             // :298-300
+        const int var = lp.Nv[t];
+        lp.d[var] = lp.d[var] - theta_d * lp.rN[t];
+    }
+}
+
+// dual :296, :302, :314-333: the scalar tail (entering / leaving entries, objective, index swap, trace)
+__global__ void k_dual_update_tail(DevLP lp, int KS, PivotState* st) {
+    if (st->status != kRunning) return;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int r_pos = st->r_pos, q_pos = st->q_pos, q_var = st->q_var, leave_var = st->leave_var;
+    const double theta_d = st->theta_d, delta = st->delta;
+    const double alpha_r = lp.dcol[r_pos];
+    const double theta_p = delta / alpha_r;
+    lp.d[leave_var] = -theta_d;  // :296 (the leaving variable is not in N, so the order vs :298 is immaterial)
+    lp.d[q_var] = 0.;            // :302
+    lp.x[q_var] = lp.x[q_var] + theta_p;  // :314
+    const int64_t t = st->trace_len;
+    if (lp.trace && t < st->trace_cap) {
+        ellp_trace_rec rec;
+        rec.phase = st->phase_tag;
+        rec.iter = (int32_t)st->pivots;
+        rec.entering = q_var;
+        rec.leaving = leave_var;
+        rec.step = theta_p;
+        rec.obj = st->obj;
+        lp.trace[t] = rec;
+    }
+    st->trace_len = t + 1;
+    st->obj = st->obj + theta_d * delta;  // :316
+    lp.Bv[r_pos] = q_var;                 // :322-323
+    lp.Nv[q_pos] = leave_var;
+    lp.Ns[q_pos] = (uint8_t)st->new_side;
+    lp.cB[r_pos] = lp.c[q_var];
+    st->alpha_r = alpha_r;
+    st->step = theta_p;
+    st->do_update = 1;
+    st->pivots += 1;
+    if (st->pivots >= st->max_iter) st->status = ELLP_MAXITER;  // :191-194 at the next loop head
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -972,6 +1134,23 @@ __global__ void k_gj_swap_gather(double* __restrict__ M, int64_t ld, int c_begin
     const double a = col[k], b = col[p];
     if (p != k) { col[k] = b; col[p] = a; }
     prow[j - c_begin] = b / st->alpha_r;
+}
+
+// revised engine: is A_B diagonal (slack / artificial starting bases are)?  Then B^-1 = diag(1 / a_ii) needs no factorisation.
+__global__ void k_check_diag_basis(const double* __restrict__ A, int64_t ld, int m, const int32_t* __restrict__ Bv, int* __restrict__ flags) {
+    const int i = blockIdx.x;
+    const double* col = A + (int64_t)Bv[i] * ld;
+    bool offdiag = false;
+    for (int k = threadIdx.x; k < m; k += blockDim.x)
+        if (k != i && col[k] != 0.) offdiag = true;
+    if (offdiag) flags[0] = 1;
+    if (threadIdx.x == 0 && fabs(col[i]) < kEps) flags[1] = 1;  // |U_ii| < EPS (primal :175-179)
+}
+
+__global__ void k_diag_inverse(DevLP lp) {
+    const int j = blockIdx.x;  // column of Binv
+    const double d = lp.A[(int64_t)lp.Bv[j] * lp.ld + j];
+    for (int64_t i = threadIdx.x; i < lp.ld; i += blockDim.x) lp.Binv[(int64_t)j * lp.ld + i] = (i == j) ? 1.0 / d : 0.;
 }
 
 // tableau engine: is column Bv[i] of T exactly e_i for every i (slack / identity starting basis)?

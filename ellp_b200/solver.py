@@ -83,8 +83,10 @@ class _GpuSimplexSolver:
 
     def __init__(self, max_iter: Optional[int] = 1000, *, ctx: Optional[N.Context] = None,
                  tie_rule: int = N.TIES_REFERENCE, refactor_every: int = 0, check_every: int = 0, trace_cap: int = 0,
-                 engine: int = N.ENGINE_AUTO):
+                 engine: int = N.ENGINE_AUTO, pricing: int = 0, ratio: int = 0):
         self.max_iter = max_iter
+        self.pricing = pricing
+        self.ratio = ratio
         self._ctx = ctx
         self.tie_rule = tie_rule
         self.refactor_every = refactor_every
@@ -105,7 +107,8 @@ class _GpuSimplexSolver:
         return self._ctx or default_context()
 
     def _opts(self):
-        o = N.default_opts(self.max_iter, self.tie_rule, self.refactor_every, self.check_every, engine=self.engine)
+        o = N.default_opts(self.max_iter, self.tie_rule, self.refactor_every, self.check_every, engine=self.engine,
+                           pricing=self.pricing, ratio=self.ratio)
         tr = None
         if self.trace_cap:
             tr = np.zeros(self.trace_cap, dtype=N.TRACE_DTYPE)

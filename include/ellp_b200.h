@@ -49,6 +49,13 @@ enum { ELLP_PRIMAL = 0, ELLP_DUAL = 1 };
 /* tie rules: 0 reproduces the reference's sequential folds (primal :271-286, :379-399) exactly,
  * 1 is the order-free form of SURVEY appendix A.1/A.2 (needed when columns are sharded). */
 enum { ELLP_TIES_REFERENCE = 0, ELLP_TIES_CANONICAL = 1 };
+/* dual leaving row: the reference's first-infeasible rule (dual :200-236) or dual steepest edge with EXACT weights
+ * w_i = ||e_i^T B^-1||^2, recomputed every pivot as a by-product of the rank-1 update's write-back (no extra pass over
+ * B^-1).  Dual entering column: the reference's first-minimum ratio (dual :263-279) or Harris' two-pass test with a
+ * 1e-9 tolerance (largest |alpha| among the near-minimal ratios).  The reference has neither (README.md:114 lists steepest
+ * edge as TODO): parity for these rules is status / objective only. */
+enum { ELLP_PRICE_REFERENCE = 0, ELLP_PRICE_STEEPEST_EDGE = 1 };
+enum { ELLP_RATIO_REFERENCE = 0, ELLP_RATIO_HARRIS = 1 };
 /* engines: explicit basis inverse (revised simplex) or full tableau (column-shardable) */
 enum { ELLP_ENGINE_AUTO = 0, ELLP_ENGINE_REVISED = 1, ELLP_ENGINE_TABLEAU = 2 };
 
@@ -103,6 +110,8 @@ typedef struct {
     int32_t  profile;         /* 1: record CUDA events around every rank-1 update launch */
     ellp_trace_rec* trace;    /* optional caller buffer */
     int64_t  trace_cap;
+    int32_t  pricing;         /* ELLP_PRICE_*: dual leaving-row rule (primal pricing is always Dantzig like the reference) */
+    int32_t  ratio;           /* ELLP_RATIO_*: dual entering-column rule */
 } ellp_opts;
 
 typedef struct {

@@ -479,3 +479,35 @@ def test_solver_parity_with_lu_refactorisation_every_few_pivots(env, which):
     ref = O.solve(prob, O.PRIMAL if which == "primal" else O.DUAL, 1000, O.MODE_EXACT)
     assert res.is_optimal and _rel(res.solution.obj(), ref.obj) < 1e-9
     P.check_expectation(exp, res.kind, res.solution.obj(), res.solution.x())
+
+
+# ---------------------------------------------------------------- optional rules: dual steepest edge + Harris ratio
+@pytest.mark.parametrize("pricing,ratio", [(1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("name", P.NETLIB)
+def test_dual_steepest_edge_and_harris_reach_the_same_optimum(env, name, pricing, ratio):
+    # no reference counterpart (README.md:114 lists steepest edge as TODO): status + objective parity only
+    prob, exp = P.netlib(name)
+    O = env["O"]
+    res = _solver(env, "dual", pricing=pricing, ratio=ratio).solve(prob)
+    ref = O.solve(prob, O.DUAL, 1000, O.MODE_EXACT)
+    assert res.is_optimal and ref.status == O.OPTIMAL
+    assert _rel(res.solution.obj(), ref.obj) < 1e-9
+    P.check_expectation(exp, res.kind, res.solution.obj(), res.solution.x())
+    print(f"{name} pricing={pricing} ratio={ratio}: pivots {res.iters} (reference rules: {ref.iters})")
+
+
+def test_dual_steepest_edge_needs_fewer_pivots_on_a_dense_lp(env):
+    import bench_lp
+    S, N, O = env["S"], env["N"], env["O"]
+    m, ns = 96, 192
+    lp = bench_lp.dense_lp(m, ns, 21, 1)
+    out = {}
+    for pricing in (0, 1):
+        st = [lp[k].copy() for k in ("x", "B", "N", "N_side", "y", "d")]
+        sol = S.GpuDualSimplexSolver.new(None, ctx=env["ctx"], pricing=pricing, ratio=pricing)
+        res, _ = sol.solve_with_initial(m, m + ns, lp["A"], lp["c"], lp["b"], lp["kind"], lp["lb"], lp["ub"], *st)
+        assert res.status == N.OPTIMAL
+        out[pricing] = (res.iters, float(np.dot(lp["c"], st[0])))
+    assert _rel(out[1][1], out[0][1]) < 1e-9
+    assert out[1][0] < out[0][0]
+    print(f"dense {m}x{ns} dual: first-infeasible {out[0][0]} pivots, steepest edge + Harris {out[1][0]} pivots")
