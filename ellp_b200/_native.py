@@ -40,7 +40,8 @@ class Point(C.Structure):
 class Opts(C.Structure):
     _fields_ = [("max_iter", C.c_uint64), ("tie_rule", C.c_int32), ("engine", C.c_int32),
                 ("refactor_every", C.c_int32), ("check_every", C.c_int32), ("phase_tag", C.c_int32),
-                ("profile", C.c_int32), ("trace", C.c_void_p), ("trace_cap", C.c_int64), ("pricing", C.c_int32), ("ratio", C.c_int32)]
+                ("profile", C.c_int32), ("trace", C.c_void_p), ("trace_cap", C.c_int64), ("pricing", C.c_int32), ("ratio", C.c_int32),
+                ("block_k", C.c_int32)]
 
 
 class Result(C.Structure):
@@ -123,6 +124,8 @@ def _load():
         "ellp_b200_download_std_form": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
         "ellp_b200_rank1_update_dev": (C.c_int, [vp, vp, i64, i64, i64, vp, i64, i32, C.POINTER(C.c_float)]),
         "ellp_b200_rank1_update": (C.c_int, [vp, vp, i64, i64, i64, vp, i64]),
+        "ellp_b200_rankk_update_dev": (C.c_int, [vp, vp, i64, i64, i64, vp, vp, i64, i32, i32, C.POINTER(C.c_float)]),
+        "ellp_b200_rankk_update": (C.c_int, [vp, vp, i64, i64, i64, vp, vp, i32]),
         "ellp_b200_gemv_t": (C.c_int, [vp, vp, i64, i64, i64, vp, i64, vp, vp]),
         "ellp_b200_gemv_n": (C.c_int, [vp, vp, i64, i64, i64, vp, vp]),
         "ellp_b200_invert": (C.c_int, [vp, vp, i64, vp]),
@@ -182,7 +185,8 @@ class Context:
 
 
 def default_opts(max_iter: Optional[int] = 1000, tie_rule: int = TIES_REFERENCE, refactor_every: int = 0,
-                 check_every: int = 0, profile: bool = False, engine: int = ENGINE_AUTO, pricing: int = 0, ratio: int = 0) -> Opts:
+                 check_every: int = 0, profile: bool = False, engine: int = ENGINE_AUTO, pricing: int = 0, ratio: int = 0,
+                 block_k: int = 0) -> Opts:
     o = Opts()
     lib.ellp_b200_default_opts(C.byref(o))
     o.max_iter = U64_MAX if max_iter is None else int(max_iter)
@@ -193,6 +197,7 @@ def default_opts(max_iter: Optional[int] = 1000, tie_rule: int = TIES_REFERENCE,
     o.engine = engine
     o.pricing = pricing
     o.ratio = ratio
+    o.block_k = block_k
     return o
 
 

@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 #include "batch.cuh"
 #include "refactor.cuh"
+#include "blocked.cuh"
 
 using namespace ellp;
 
@@ -91,6 +92,9 @@ struct ellp_b200_ctx {
     // tuning (ellp_b200_set_tuning)
     int rank1_cols_per_cta = 8;
     int rank1_stream_min_mb = 96;
+    int blk_kmax = 0;             // slots allocated for the blocked (deferred rank-k) tableau engine; 0 = rank-1 engine only
+    int blk_fill = 0;             // slots used since the last flush
+    int flush_col_steps = 8;      // column steps (of 64 columns) per CTA of k_blk_flush
     int refactor_mode = 0;        // 0 auto (blocked LU + DMMA for m >= 128, Gauss-Jordan below), 1 Gauss-Jordan, 2 blocked LU  // evict-first policy when the updated matrix is larger than this
 };
 
@@ -159,7 +163,7 @@ int ensure_arena(ellp_b200_ctx* ctx, size_t bytes) {
     return ELLP_OK;
 }
 
-void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap, bool tableau, bool sharded = false, int nranks = 1,
+void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap, bool tableau, int blk_kmax, bool sharded = false, int nranks = 1,
            double** sendcol = nullptr, uint8_t** d_sides = nullptr) {
     // n = locally stored columns (A / T, dj, key, prow); ng = length of the replicated per-variable vectors
     const size_t ld = (size_t)lp.ld, m = (size_t)lp.m, n = (size_t)lp.n, ng = (size_t)lp.n_glob;
@@ -181,7 +185,12 @@ void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap, bool tableau, bool sh
         lp.Binv = nullptr;
         lp.T = const_cast<double*>(lp.A);
         lp.dj = a.take<double>(n);
+        lp.ldv = (int64_t)align_up(n, 4);
+        lp.U = blk_kmax > 0 ? a.take<double>(ld * (size_t)blk_kmax) : nullptr;
+        lp.V = blk_kmax > 0 ? a.take<double>((size_t)lp.ldv * (size_t)blk_kmax) : nullptr;
     } else {
+        lp.U = lp.V = nullptr;
+        lp.ldv = 0;
         lp.G = a.take<double>(ld * 2 * m);
         lp.Binv = lp.G ? lp.G + ld * m : nullptr;
         lp.T = nullptr;
@@ -216,6 +225,12 @@ void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap, bool tableau, bool sh
         lp.colstat = nullptr;
         lp.xchg = nullptr;
     }
+}
+
+// slots of the blocked (deferred rank-k) tableau engine requested by the caller (ellp_opts::block_k), 0 = rank-1 engine
+int blk_slots(const ellp_opts* o, bool tableau) {
+    if (!tableau || !o || o->block_k <= 1) return 0;
+    return std::min<int>(o->block_k, kBlkMax);
 }
 
 const char* dev_err_message(int e) {
@@ -344,14 +359,37 @@ int refactor(ellp_b200_ctx* ctx, uint64_t* count) {
 }
 
 // tableau engine, primal: 5 launches per pivot, the rank-1 update of T is >99 % of the bytes
-void launch_tableau_primal_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, bool profile, size_t* ev_used) {
+// blocked engine: T -= U V over the slots filled since the last flush (k_blk_flush, fp64 tensor pipe), timed like K3
+void launch_flush(ellp_b200_ctx* ctx, bool profile, size_t* ev_used) {
+    DevLP& lp = ctx->lp;
+    const int cnt = ctx->blk_fill;
+    ctx->blk_fill = 0;
+    if (cnt <= 0) return;
+    const int K4 = (cnt + 3) & ~3;
+    const size_t smem = blk_flush_smem_bytes(K4);
+    const int steps_total = (lp.n + kFlushCols - 1) / kFlushCols;
+    const int col_steps = std::max(1, std::min(ctx->flush_col_steps, steps_total));
+    dim3 grid((unsigned)((lp.ld + kFlushRows - 1) / kFlushRows), (unsigned)((steps_total + col_steps - 1) / col_steps));
+    const bool stream = (double)lp.ld * lp.n * 8.0 > (double)ctx->rank1_stream_min_mb * 1048576.0;
+    if (profile && ev_used && *ev_used + 2 <= ctx->ev.size()) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
+    if (stream) LAUNCH_SMEM(k_blk_flush<true>, grid, 256, smem, lp.T, lp.ld, lp.m, lp.n, lp.U, lp.V, lp.ldv, cnt, col_steps);
+    else LAUNCH_SMEM(k_blk_flush<false>, grid, 256, smem, lp.T, lp.ld, lp.m, lp.n, lp.U, lp.V, lp.ldv, cnt, col_steps);
+    if (profile && ev_used && (*ev_used & 1)) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
+}
+
+void launch_tableau_primal_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, bool profile, size_t* ev_used, int blk) {
     DevLP& lp = ctx->lp;
     PivotState* st = ctx->d_st;
     const int m = lp.m, nN = lp.nN, n = lp.n;
     LAUNCH(k_price_tab, (nN + 255) / 256, 256, lp.dj, lp.Nv, lp.Ns, nN, lp.rN, lp.key, st);     // primal :189, :253-270
     LAUNCH_SMEM(k_select_primal, 1, kScanThreads, kScanSmemBytes, lp.key, lp.rN, lp.Nv, lp.Ns, nN, o->tie_rule, st);           // :271-292
-    LAUNCH(k_ratio_prep, (m + 255) / 256, 256, lp, 0, st);                                       // :295-367
+    LAUNCH(k_ratio_prep, (m + 255) / 256, 256, lp, 0, blk > 0 ? ctx->blk_fill : 0, st);         // :295-367
     LAUNCH_SMEM(k_ratio_pick, 1, kScanThreads, kScanSmemBytes, lp, o->tie_rule, st);             // :379-434, :205-232
+    if (blk > 0) {  // deferred row reduction: new (U, V) slot now, T -= U V every blk pivots
+        LAUNCH(k_blk_row, (int)((std::max<int64_t>(lp.ld, lp.ldv) + 255) / 256), 256, lp, ctx->blk_fill, st);
+        if (++ctx->blk_fill >= blk) launch_flush(ctx, profile, ev_used);
+        return;
+    }
     LAUNCH(k_step_gather, (std::max(m, n) + 255) / 256, 256, lp, lp.T, n, st);                   // :408-417 + pivot row
     if (profile && *ev_used + 2 <= ctx->ev.size()) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
     launch_rank1(ctx, lp.T, lp.ld, m, n, lp.dcol, lp.prow, st, 0, lp.dj);
@@ -359,7 +397,7 @@ void launch_tableau_primal_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, boo
 }
 
 // column-sharded tableau: 7 kernels + 3 NCCL collectives per pivot, no host involvement
-int launch_sharded_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, bool profile, size_t* ev_used) {
+int launch_sharded_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, bool profile, size_t* ev_used, int blk) {
     DevLP& lp = ctx->lp;
     PivotState* st = ctx->d_st;
     const int m = lp.m, n = lp.n, G = ctx->nranks;
@@ -368,10 +406,15 @@ int launch_sharded_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, bool profil
     NCCL_TRY(nccl::api.AllGather(lp.xchg + 0, lp.xchg + 16, 1, nccl::kFloat64, ctx->nccl_comm, ctx->stream));
     LAUNCH(k_shard_pick, 1, 1024, lp, G, st);
     NCCL_TRY(nccl::api.AllGather(lp.xchg + 8, lp.xchg + 32, 3, nccl::kFloat64, ctx->nccl_comm, ctx->stream));
-    LAUNCH(k_shard_stage_column, (int)((lp.ld + 255) / 256), 256, lp, G, st, ctx->sendcol);
+    LAUNCH(k_shard_stage_column, (int)((lp.ld + 255) / 256), 256, lp, G, blk > 0 ? ctx->blk_fill : 0, st, ctx->sendcol);
     NCCL_TRY(nccl::api.AllReduce(ctx->sendcol, lp.dcol, (size_t)lp.ld, nccl::kFloat64, nccl::kSum, ctx->nccl_comm, ctx->stream));
-    LAUNCH(k_ratio_prep, (m + 255) / 256, 256, lp, -1, st);
+    LAUNCH(k_ratio_prep, (m + 255) / 256, 256, lp, -1, 0, st);
     LAUNCH_SMEM(k_ratio_pick, 1, kScanThreads, kScanSmemBytes, lp, o->tie_rule, st);
+    if (blk > 0) {
+        LAUNCH(k_blk_row, (int)((std::max<int64_t>(lp.ld, lp.ldv) + 255) / 256), 256, lp, ctx->blk_fill, st);
+        if (++ctx->blk_fill >= blk) launch_flush(ctx, profile, ev_used);
+        return ELLP_OK;
+    }
     LAUNCH(k_step_gather, (std::max(m, n) + 255) / 256, 256, lp, lp.T, n, st);
     if (profile && *ev_used + 2 <= ctx->ev.size()) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
     launch_rank1(ctx, lp.T, lp.ld, m, n, lp.dcol, lp.prow, st, 0, lp.dj);
@@ -392,7 +435,7 @@ void launch_primal_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, bool profil
     // FTRAN d = B^-1 a_q  (primal :295)
     dim3 fg((unsigned)((lp.ld + 255) / 256), (unsigned)ctx->KS);
     LAUNCH(k_ftran_partial, fg, 128, lp.Binv, lp.ld, m, lp.A, st, lp.part, ctx->kc);
-    LAUNCH(k_ratio_prep, (m + 255) / 256, 256, lp, ctx->KS, st);
+    LAUNCH(k_ratio_prep, (m + 255) / 256, 256, lp, ctx->KS, 0, st);
     LAUNCH_SMEM(k_ratio_pick, 1, kScanThreads, kScanSmemBytes, lp, o->tie_rule, st);
     LAUNCH(k_step_gather, (m + 255) / 256, 256, lp, lp.Binv, m, st);
     if (profile && *ev_used + 2 <= ctx->ev.size()) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
@@ -545,6 +588,7 @@ int ellp_b200_set_tuning(ellp_b200_ctx* ctx, const char* key, int value) {
     if (!std::strcmp(key, "rank1_cols_per_cta")) ctx->rank1_cols_per_cta = value;
     else if (!std::strcmp(key, "rank1_stream_min_mb")) ctx->rank1_stream_min_mb = value;
     else if (!std::strcmp(key, "refactor_mode")) ctx->refactor_mode = value;
+    else if (!std::strcmp(key, "flush_col_steps")) ctx->flush_col_steps = std::max(1, value);
     else return set_err(ctx, ELLP_E_ARG, std::string("unknown tuning key ") + key);
     return ELLP_OK;
 }
@@ -575,12 +619,13 @@ int ellp_b200_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_poi
     const bool tableau = o && o->engine == ELLP_ENGINE_TABLEAU;
     if (tableau && solver != ELLP_PRIMAL)
         return set_err(ctx, ELLP_E_ARG, "ELLP_ENGINE_TABLEAU implements the primal path only; use ELLP_ENGINE_REVISED for the dual");
+    const int blk = blk_slots(o, tableau);
     Arena probe;
-    carve(probe, lp, KS, tcap, tableau);
+    carve(probe, lp, KS, tcap, tableau, blk);
     if (int rc = ensure_arena(ctx, probe.off + 256)) return rc;
     Arena a;
     a.base = ctx->arena;
-    carve(a, lp, KS, tcap, tableau);
+    carve(a, lp, KS, tcap, tableau, blk);
     cudaStream_t s = ctx->stream;
     // zero the padded scratch once (padding rows must stay zero)
     CUDA_TRY(cudaMemsetAsync(lp.cB, 0, (size_t)((char*)lp.lam - (char*)lp.cB), s));
@@ -617,6 +662,8 @@ int ellp_b200_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_poi
     ctx->solver = solver;
     ctx->resident = true;
     ctx->tableau = tableau;
+    ctx->blk_kmax = blk;
+    ctx->blk_fill = 0;
     ctx->sharded = false;
     ctx->binv_valid = false;
     // host buffers are only borrowed for the duration of the call
@@ -644,12 +691,13 @@ int ellp_b200_generate_dense_ex(ellp_b200_ctx* ctx, int32_t m, int32_t n_struct,
     const int64_t tcap = o->trace ? o->trace_cap : 0;
     const bool tableau = o->engine == ELLP_ENGINE_TABLEAU;
     if (tableau && variant == 1) return set_err(ctx, ELLP_E_ARG, "the dual variant needs ELLP_ENGINE_REVISED");
+    const int blk = blk_slots(o, tableau);
     Arena probe;
-    carve(probe, lp, KS, tcap, tableau);
+    carve(probe, lp, KS, tcap, tableau, blk);
     if (int rc = ensure_arena(ctx, probe.off + 256)) return rc;
     Arena a;
     a.base = ctx->arena;
-    carve(a, lp, KS, tcap, tableau);
+    carve(a, lp, KS, tcap, tableau, blk);
     CUDA_TRY(cudaMemsetAsync(lp.cB, 0, (size_t)((char*)lp.lam - (char*)lp.cB), ctx->stream));
     CUDA_TRY(cudaMemsetAsync(lp.y, 0, sizeof(double) * lp.ld, ctx->stream));
     LAUNCH(k_gen_dense_cols, 148 * 16, 256, const_cast<double*>(lp.A), lp.ld, m, (int64_t)n_struct, (int64_t)0, (int64_t)lp.n, seed,
@@ -662,6 +710,8 @@ int ellp_b200_generate_dense_ex(ellp_b200_ctx* ctx, int32_t m, int32_t n_struct,
     ctx->solver = variant == 0 ? ELLP_PRIMAL : ELLP_DUAL;
     ctx->resident = true;
     ctx->tableau = tableau;
+    ctx->blk_kmax = blk;
+    ctx->blk_fill = 0;
     ctx->sharded = false;
     ctx->binv_valid = false;
     ctx->dual_obj0 = 0.;  // y = 0 and every bound is Lower(0): dual_obj(y, d) = 0
@@ -722,12 +772,15 @@ static int sharded_prepare(ellp_b200_ctx* ctx, int32_t m, int32_t n_glob, const 
     lp.nN = lp.n;
     lp.ld = m;
     const int64_t tcap = o->trace ? o->trace_cap : 0;
+    const int blk = blk_slots(o, true);
     Arena probe;
-    carve(probe, lp, 1, tcap, true, true, ctx->nranks);
+    carve(probe, lp, 1, tcap, true, blk, true, ctx->nranks);
     if (int rc = ensure_arena(ctx, probe.off + 256)) return rc;
     Arena a;
     a.base = ctx->arena;
-    carve(a, lp, 1, tcap, true, true, ctx->nranks, &ctx->sendcol, &ctx->d_sides);
+    carve(a, lp, 1, tcap, true, blk, true, ctx->nranks, &ctx->sendcol, &ctx->d_sides);
+    ctx->blk_kmax = blk;
+    ctx->blk_fill = 0;
     CUDA_TRY(cudaMemsetAsync(lp.cB, 0, (size_t)((char*)lp.lam - (char*)lp.cB), ctx->stream));
     CUDA_TRY(cudaMemsetAsync(lp.y, 0, sizeof(double) * lp.ld, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(lp.xchg, 0, sizeof(double) * (64 + 4 * (size_t)ctx->nranks), ctx->stream));
@@ -979,6 +1032,14 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
     const bool dse = ctx->solver == ELLP_DUAL && !ctx->tableau && o->pricing == ELLP_PRICE_STEEPEST_EDGE;
     if (dse) launch_row_norms(ctx);
     if (ctx->solver == ELLP_PRIMAL) LAUNCH(k_obj_dot, 1, 1024, lp.c, lp.x, lp.n_glob, ctx->d_st);
+    // blocked tableau engine: slots were allocated at upload time; the caller may lower block_k per run
+    const int blk = (ctx->tableau && ctx->blk_kmax > 0 && o->block_k > 1) ? std::min(o->block_k, ctx->blk_kmax) : 0;
+    ctx->blk_fill = 0;
+    if (blk > 0) {
+        const size_t smem = blk_flush_smem_bytes((blk + 3) & ~3);
+        CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     int check_every = o->check_every > 0 ? o->check_every : (lp.m >= 2048 ? 1 : 8);
     int refactor_every = o->refactor_every > 0 ? o->refactor_every : ((lp.m <= 512 && !ctx->tableau) ? 100 : 0);
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -989,8 +1050,8 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
         if (o->max_iter - h.pivots < (uint64_t)batch) batch = (int)std::max<uint64_t>(1, o->max_iter - h.pivots);
         if (refactor_every > 0) batch = (int)std::min<uint64_t>(batch, std::max<uint64_t>(1, refactor_every - ctx->pivots_since_refactor));
         for (int k = 0; k < batch; ++k) {
-            if (ctx->sharded) { if ((rc_loop = launch_sharded_iteration(ctx, o, profile, &ev_used))) break; }
-            else if (ctx->tableau) launch_tableau_primal_iteration(ctx, o, profile, &ev_used);
+            if (ctx->sharded) { if ((rc_loop = launch_sharded_iteration(ctx, o, profile, &ev_used, blk))) break; }
+            else if (ctx->tableau) launch_tableau_primal_iteration(ctx, o, profile, &ev_used, blk);
             else if (ctx->solver == ELLP_PRIMAL) launch_primal_iteration(ctx, o, profile, &ev_used);
             else launch_dual_iteration(ctx, o, profile, &ev_used);
         }
@@ -1004,6 +1065,7 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
             if (dse) launch_row_norms(ctx);
         }
     }
+    if (blk > 0) launch_flush(ctx, profile, &ev_used);  // leave a consistent tableau behind (the solve may be continued)
     CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (rc_loop) return rc_loop;
@@ -1222,6 +1284,55 @@ int ellp_b200_rank1_update(ellp_b200_ctx* ctx, double* E, int64_t R, int64_t C, 
     if (rc == ELLP_OK) CUDA_TRY(cudaMemcpy(E, dE, sizeof(double) * ld * C, cudaMemcpyDeviceToHost));
     cudaFree(dE);
     cudaFree(da);
+    return rc;
+}
+
+// K3b on caller-supplied DEVICE data: E (R x C, ld) -= U (R x k, ld) * V (k x C, row stride ldv); reps timed launches
+int ellp_b200_rankk_update_dev(ellp_b200_ctx* ctx, double* E, int64_t R, int64_t C, int64_t ld, const double* U, const double* V,
+                               int64_t ldv, int32_t k, int32_t reps, float* ms_avg) {
+    if (!ctx || !E || !U || !V || R <= 0 || C <= 0 || ld < R || (ld % 2) != 0 || ldv < C || k < 1 || k > kBlkMax || reps < 1 ||
+        (reinterpret_cast<uintptr_t>(E) & 15) != 0)
+        return set_err(ctx, ELLP_E_ARG, "rankk_update needs ld even, ld >= R, ldv >= C, 1 <= k <= 64 and a 16-byte aligned E");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int K4 = (k + 3) & ~3;
+    const size_t smem = blk_flush_smem_bytes(K4);
+    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush_smem_bytes(kBlkMax)));
+    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush_smem_bytes(kBlkMax)));
+    const int steps_total = (int)((C + kFlushCols - 1) / kFlushCols);
+    const int col_steps = std::max(1, std::min(ctx->flush_col_steps, steps_total));
+    dim3 grid((unsigned)((ld + kFlushRows - 1) / kFlushRows), (unsigned)((steps_total + col_steps - 1) / col_steps));
+    const bool stream = (double)ld * C * 8.0 > (double)ctx->rank1_stream_min_mb * 1048576.0;
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int t = 0; t < reps; ++t) {
+        if (stream) LAUNCH_SMEM(k_blk_flush<true>, grid, 256, smem, E, ld, (int)R, (int)C, U, V, ldv, (int)k, col_steps);
+        else LAUNCH_SMEM(k_blk_flush<false>, grid, 256, smem, E, ld, (int)R, (int)C, U, V, ldv, (int)k, col_steps);
+    }
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaGetLastError());
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (ms_avg) *ms_avg = ms / (float)reps;
+    return ELLP_OK;
+}
+
+// same on host buffers (E: R x C with leading dimension ld, U: R x k with leading dimension R, V: k x C row-major)
+int ellp_b200_rankk_update(ellp_b200_ctx* ctx, double* E, int64_t R, int64_t C, int64_t ld, const double* U, const double* V, int32_t k) {
+    if (!ctx || !E || !U || !V || R <= 0 || C <= 0 || ld < R || k < 1 || k > kBlkMax) return ELLP_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int64_t ldp = (int64_t)align_up((size_t)R, 4);
+    double *dE = nullptr, *dU = nullptr, *dV = nullptr;
+    CUDA_TRY(cudaMalloc(&dE, sizeof(double) * ldp * C));
+    CUDA_TRY(cudaMalloc(&dU, sizeof(double) * ldp * k));
+    CUDA_TRY(cudaMalloc(&dV, sizeof(double) * C * k));
+    CUDA_TRY(cudaMemset(dE, 0, sizeof(double) * ldp * C));
+    CUDA_TRY(cudaMemset(dU, 0, sizeof(double) * ldp * k));
+    CUDA_TRY(cudaMemcpy2D(dE, sizeof(double) * ldp, E, sizeof(double) * ld, sizeof(double) * R, C, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy2D(dU, sizeof(double) * ldp, U, sizeof(double) * R, sizeof(double) * R, k, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dV, V, sizeof(double) * C * k, cudaMemcpyHostToDevice));
+    int rc = ellp_b200_rankk_update_dev(ctx, dE, R, C, ldp, dU, dV, C, k, 1, nullptr);
+    if (rc == ELLP_OK) CUDA_TRY(cudaMemcpy2D(E, sizeof(double) * ld, dE, sizeof(double) * ldp, sizeof(double) * R, C, cudaMemcpyDeviceToHost));
+    cudaFree(dE); cudaFree(dU); cudaFree(dV);
     return rc;
 }
 

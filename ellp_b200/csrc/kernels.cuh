@@ -60,6 +60,10 @@ struct DevLP {
     int32_t n_glob;
     int32_t col_lo;
     uint8_t* colstat;  // n local entries: ELLP_NB_* or kColBasic; nullptr when not sharded
+    // blocked (deferred rank-k) tableau engine, see blocked.cuh: T_current = T - U V over the pending slots
+    double* U;         // ld x kBlkMax, column j = pivot column of pending pivot j minus e_r (nullptr: rank-1 engine)
+    double* V;         // kBlkMax x ldv, row j = scaled pivot row of pending pivot j
+    int64_t ldv;
     double* xchg;      // small exchange buffers: [0] local max key | [8..8+3) candidate | [16..16+G) gathered max | [32..32+3G) gathered candidates
 };
 
@@ -384,16 +388,27 @@ __device__ __forceinline__ double primal_ratio(int kind, double lb, double ub, d
 // K2a: pivot column, direction and the per-row ratios (primal :295-367), one row per thread over the whole grid.
 // KS > 0: revised engine, alpha = sum of split-K partials (fixed order); KS == 0: tableau engine, alpha = T[:, q]
 // (copied out because k_rank1 overwrites that column); KS < 0: alpha already sits in dcol (column-sharded tableau).
-__global__ void __launch_bounds__(256) k_ratio_prep(DevLP lp, int KS, PivotState* st) {
+// cnt > 0 (blocked tableau engine, KS == 0): the stored tableau is stale by cnt pending pivots; their rank-1
+// corrections are applied to the entering column in pivot order, a_i = fma(-U[i,j], V[j,q], a_i) -- the same
+// sequence of roundings the rank-1 engine performs on that element.
+__global__ void __launch_bounds__(256) k_ratio_prep(DevLP lp, int KS, int cnt, PivotState* st) {
     if (st->status != kRunning) return;
+    __shared__ double s_vq[64];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int q_var = st->q_var;
     const bool at_lower = (st->q_side == ELLP_NB_LOWER);
+    if (cnt > 0) {
+        if (threadIdx.x < cnt) s_vq[threadIdx.x] = lp.V[(int64_t)threadIdx.x * lp.ldv + (q_var - lp.col_lo)];
+        __syncthreads();
+    }
     double lam = -1.0;  // -1 = skipped (|d_i| < EPS, :321)
     if (i < lp.m) {
         double a = 0.;
         if (KS > 0) { for (int ks = 0; ks < KS; ++ks) a += lp.part[(int64_t)ks * lp.ld + i]; }
-        else if (KS == 0) a = lp.T[(int64_t)q_var * lp.ld + i];
+        else if (KS == 0) {
+            a = lp.T[(int64_t)(q_var - lp.col_lo) * lp.ld + i];
+            for (int j = 0; j < cnt; ++j) a = fma(-lp.U[(int64_t)j * lp.ld + i], s_vq[j], a);
+        }
         else a = lp.dcol[i];
         lp.dcol[i] = a;
         const double d_i = at_lower ? -a : a;  // :296-300
@@ -1268,7 +1283,8 @@ __global__ void __launch_bounds__(1024) k_shard_pick(DevLP lp, int G, PivotState
 }
 
 // xchg[32..32+3G): gathered candidates.  Every rank derives the same winner; the owner stages its pivot column.
-__global__ void k_shard_stage_column(DevLP lp, int G, PivotState* st, double* __restrict__ sendcol) {
+// cnt > 0 (blocked engine): the owner applies the cnt pending rank-1 corrections to its stale column first.
+__global__ void k_shard_stage_column(DevLP lp, int G, int cnt, PivotState* st, double* __restrict__ sendcol) {
     if (st->status != kRunning) return;
     double qv = -1.0, rq = 0., side = 0.;
     for (int g = 0; g < G; ++g) {
@@ -1278,7 +1294,15 @@ __global__ void k_shard_stage_column(DevLP lp, int G, PivotState* st, double* __
     const int q_var = (int)qv;
     const bool mine = (q_var >= lp.col_lo && q_var < lp.col_lo + lp.n);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < lp.ld) sendcol[i] = mine ? lp.T[(int64_t)(q_var - lp.col_lo) * lp.ld + i] : 0.;
+    if (i < lp.ld) {
+        double a = 0.;
+        if (mine) {
+            const int ql = q_var - lp.col_lo;
+            a = lp.T[(int64_t)ql * lp.ld + i];
+            for (int j = 0; j < cnt; ++j) a = fma(-lp.U[(int64_t)j * lp.ld + i], __ldg(lp.V + (int64_t)j * lp.ldv + ql), a);
+        }
+        sendcol[i] = a;
+    }
     if (i == 0) {
         st->lmin_bits = 0x7ff0000000000000ll;
         st->q_var = q_var;

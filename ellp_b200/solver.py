@@ -83,8 +83,9 @@ class _GpuSimplexSolver:
 
     def __init__(self, max_iter: Optional[int] = 1000, *, ctx: Optional[N.Context] = None,
                  tie_rule: int = N.TIES_REFERENCE, refactor_every: int = 0, check_every: int = 0, trace_cap: int = 0,
-                 engine: int = N.ENGINE_AUTO, pricing: int = 0, ratio: int = 0):
+                 engine: int = N.ENGINE_AUTO, pricing: int = 0, ratio: int = 0, block_k: int = 0):
         self.max_iter = max_iter
+        self.block_k = block_k
         self.pricing = pricing
         self.ratio = ratio
         self._ctx = ctx
@@ -108,7 +109,7 @@ class _GpuSimplexSolver:
 
     def _opts(self):
         o = N.default_opts(self.max_iter, self.tie_rule, self.refactor_every, self.check_every, engine=self.engine,
-                           pricing=self.pricing, ratio=self.ratio)
+                           pricing=self.pricing, ratio=self.ratio, block_k=self.block_k)
         tr = None
         if self.trace_cap:
             tr = np.zeros(self.trace_cap, dtype=N.TRACE_DTYPE)

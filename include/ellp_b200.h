@@ -112,6 +112,10 @@ typedef struct {
     int64_t  trace_cap;
     int32_t  pricing;         /* ELLP_PRICE_*: dual leaving-row rule (primal pricing is always Dantzig like the reference) */
     int32_t  ratio;           /* ELLP_RATIO_*: dual entering-column rule */
+    int32_t  block_k;         /* tableau engine: > 1 defers the row reduction and applies it as ONE rank-k update
+                                 (T -= U V on the fp64 tensor pipe) every block_k pivots; 0/1 = rank-1 update per pivot.
+                                 Read at upload / generate time (allocates 8*(m+n)*block_k bytes) and by ellp_b200_run
+                                 (may be lowered per run).  Capped at 64.  Pivot decisions are unchanged. */
 } ellp_opts;
 
 typedef struct {
@@ -121,8 +125,8 @@ typedef struct {
     int64_t  trace_len;
     uint64_t launches;        /* kernels launched by this call */
     double   ms_device;       /* device time of the iteration loop (CUDA events on the ctx stream) */
-    double   ms_rank1;        /* with profile=1: summed device time of the rank-1 update launches */
-    uint64_t n_rank1;         /* with profile=1: number of rank-1 update launches timed */
+    double   ms_rank1;        /* with profile=1: summed device time of the row-reduction launches (k_rank1, or k_blk_flush when block_k > 1) */
+    uint64_t n_rank1;         /* with profile=1: number of row-reduction launches timed */
     uint64_t refactors;
 } ellp_result;
 
@@ -151,7 +155,7 @@ int ellp_b200_generate_dense(ellp_b200_ctx*, int32_t m, int32_t n_struct, uint64
 int ellp_b200_generate_dense_ex(ellp_b200_ctx*, int32_t m, int32_t n_struct, uint64_t seed, int32_t variant, const ellp_opts* o);
 /* copies the resident standard form to host buffers (any pointer may be NULL) */
 int ellp_b200_download_std_form(ellp_b200_ctx*, double* A, double* c, double* b, uint8_t* kind, double* lb, double* ub);
-/* tuning knobs: "rank1_cols_per_cta", "rank1_stream_min_mb" */
+/* tuning knobs: "rank1_cols_per_cta", "rank1_stream_min_mb", "refactor_mode", "flush_col_steps" */
 int ellp_b200_set_tuning(ellp_b200_ctx*, const char* key, int value);
 
 /* ---- K6: batches of independent small LPs (BASELINE.json configs[3]) -------------------------------------------
@@ -269,6 +273,14 @@ int ellp_b200_rank1_update_dev(ellp_b200_ctx*, double* E, int64_t R, int64_t C, 
                                int64_t r, int32_t reps, float* ms_avg);
 /* same on host buffers (copies in, one update, copies out) */
 int ellp_b200_rank1_update(ellp_b200_ctx*, double* E, int64_t R, int64_t C, int64_t ld, const double* alpha, int64_t r);
+
+/* K3b: rank-k row reduction E -= U V (the deferred form of k consecutive K3 updates, see ellp_opts::block_k), fp64
+ * tensor pipe (DMMA m8n8k4).  DEVICE pointers: E is R x C column-major with even ld >= R, U is R x k column-major with
+ * the SAME leading dimension ld, V is k x C row-major with row stride ldv >= C; 1 <= k <= 64. */
+int ellp_b200_rankk_update_dev(ellp_b200_ctx*, double* E, int64_t R, int64_t C, int64_t ld, const double* U, const double* V,
+                               int64_t ldv, int32_t k, int32_t reps, float* ms_avg);
+/* same on host buffers: U is R x k column-major with leading dimension R, V is k x C row-major (row stride C) */
+int ellp_b200_rankk_update(ellp_b200_ctx*, double* E, int64_t R, int64_t C, int64_t ld, const double* U, const double* V, int32_t k);
 
 /* K1/K5: y[j] = dot(M[:, cols[j]], v) for j < ncols (cols == NULL => identity); host buffers */
 int ellp_b200_gemv_t(ellp_b200_ctx*, const double* M, int64_t R, int64_t C, int64_t ld, const int32_t* cols,

@@ -511,3 +511,81 @@ def test_dual_steepest_edge_needs_fewer_pivots_on_a_dense_lp(env):
     assert _rel(out[1][1], out[0][1]) < 1e-9
     assert out[1][0] < out[0][0]
     print(f"dense {m}x{ns} dual: first-infeasible {out[0][0]} pivots, steepest edge + Harris {out[1][0]} pivots")
+
+
+# ---------------------------------------------------------------- blocked tableau engine (deferred rank-k row reduction, K3b)
+@pytest.mark.parametrize("R,C_,k", [(2, 2, 1), (8, 8, 3), (27, 51, 4), (64, 192, 32), (130, 70, 17), (513, 129, 64), (1024, 1000, 32),
+                                    (2050, 333, 8)])
+def test_rankk_update_matches_numpy_and_sequential_rank1(env, R, C_, k):
+    """E -= U V on the fp64 tensor pipe.  DMMA accumulates the k products of an element in one chain starting from
+    e_ij, like k sequential fma(-u, v, e): the result agrees with the exactly rounded sequential update to a few ulp
+    of the magnitudes involved (the tensor pipe's internal rounding points are not specified bit-for-bit)."""
+    N, ctx = env["N"], env["ctx"]
+    rng = np.random.default_rng(R * 7919 + C_ * 31 + k)
+    E = np.asfortranarray(rng.standard_normal((R, C_)))
+    U = np.asfortranarray(rng.standard_normal((R, k)))
+    V = np.ascontiguousarray(rng.standard_normal((k, C_)))
+    got = E.copy(order="F")
+    ctx.check(N.lib.ellp_b200_rankk_update(ctx.h, N.ptr(got), R, C_, R, N.ptr(U), N.ptr(V), k))
+    want = E - U @ V
+    scale = np.abs(E) + np.abs(U) @ np.abs(V)
+    assert (np.abs(got - want) <= 4 * np.finfo(float).eps * scale * max(1, k)).all()
+
+
+@pytest.mark.parametrize("seed,m,n,tie,bk", [(0, 24, 40, 0, 2), (1, 64, 128, 0, 7), (2, 64, 128, 1, 32), (3, 132, 190, 0, 64), (5, 260, 515, 0, 32)])
+def test_blocked_tableau_engine_matches_oracle_trace(env, seed, m, n, tie, bk):
+    """ellp_opts::block_k > 1: identical pivot sequence, basis and point as the oracle (and hence as the rank-1 engine)."""
+    O, S, N = env["O"], env["S"], env["N"]
+    A, b, c = _dense_lp(seed, m, n)
+    Af, cf, kind, lb, ub, x0, B0, N0, Ns0 = _slack_start_primal(A, b, c)
+    xo, Bo, No, Nso = x0.copy(), B0.copy(), N0.copy(), Ns0.copy()
+    ref = O.solve_with_initial(O.PRIMAL, m, n + m, Af, cf, b, kind, lb, ub, xo, Bo, No, Nso, max_iter=None, mode=tie, trace_cap=20000)
+    xg, Bg, Ng, Nsg = x0.copy(), B0.copy(), N0.copy(), Ns0.copy()
+    sol = S.GpuPrimalSimplexSolver.new(None, ctx=env["ctx"], trace_cap=20000, tie_rule=tie, engine=N.ENGINE_TABLEAU, block_k=bk)
+    res, trace = sol.solve_with_initial(m, n + m, Af, cf, b, kind, lb, ub, xg, Bg, Ng, Nsg)
+    assert res.status == ref.status == O.OPTIMAL
+    assert res.iters == len(ref.trace)
+    assert (trace["entering"] == ref.trace["entering"]).all() and (trace["leaving"] == ref.trace["leaving"]).all()
+    np.testing.assert_array_equal(Bg, Bo)
+    np.testing.assert_allclose(xg, xo, rtol=1e-9, atol=1e-9)
+    assert _rel(res.obj, ref.obj) < 1e-9
+
+
+@pytest.mark.parametrize("make", P.GOLDEN + [lambda n=n: P.netlib(n) for n in P.NETLIB],
+                         ids=[f.__name__ for f in P.GOLDEN] + P.NETLIB)
+def test_blocked_tableau_engine_two_phase_primal(env, make):
+    """The reference's own expectations (degenerate netlib LPs, bound flips, unbounded / infeasible verdicts) with the
+    deferred row reduction: same verdict, objective and pivot counts as the oracle."""
+    prob, exp = make()
+    N, S = env["N"], env["S"]
+    res = S.GpuPrimalSimplexSolver.default(ctx=env["ctx"], engine=N.ENGINE_TABLEAU, block_k=8).solve(prob)
+    obj = res.solution.obj() if res.is_optimal else float("nan")
+    x = res.solution.x() if res.is_optimal else []
+    P.check_expectation(exp, res.kind, obj, x)
+    ref = env["O"].solve(prob, env["O"].PRIMAL, 1000, env["O"].MODE_EXACT)
+    assert res.kind == ref.status_name
+    if res.is_optimal:
+        assert _rel(obj, ref.obj) < 1e-9
+        assert res.iters == ref.iters
+
+
+def test_blocked_engine_continues_across_runs_and_matches_rank1_engine(env):
+    """bench.py's usage: the LP stays resident and ellp_b200_run is called repeatedly with a pivot budget.  The blocked
+    engine (flush at the end of every run) must follow the rank-1 engine pivot for pivot over several runs."""
+    N, ctx = env["N"], env["ctx"]
+    m, ns, seed, K, runs = 512, 1024, 3, 50, 4
+    traces = {}
+    for bk in (0, 16):
+        o = N.default_opts(K, engine=N.ENGINE_TABLEAU, block_k=bk, check_every=16)
+        tr = np.zeros(K, dtype=N.TRACE_DTYPE); o.trace = N.ptr(tr); o.trace_cap = K
+        ctx.check(N.lib.ellp_b200_generate_dense(ctx.h, m, ns, seed, C.byref(o)))
+        rows = []
+        for _ in range(runs):
+            res = N.Result()
+            ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(o), C.byref(res)))
+            assert res.status == N.MAXITER and res.iters == K
+            rows.append((tr["entering"].copy(), tr["leaving"].copy(), tr["step"].copy()))
+        traces[bk] = rows
+    for (e0, l0, s0), (e1, l1, s1) in zip(traces[0], traces[16]):
+        assert (e0 == e1).all() and (l0 == l1).all()
+        np.testing.assert_allclose(s1, s0, rtol=1e-9, atol=1e-12)
