@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) k_blk_row(DevLP lp, int slot, PivotState*
 //   The mma is issued on the TRANSPOSED tile (mma rows = tableau columns, mma columns = tableau rows) so that the two
 //   accumulator values a lane owns are two consecutive rows of one column: T moves HBM <-> registers as 16-byte
 //   accesses, 64 contiguous bytes per column per quad, each sector touched once.
-//   -U (128 x K) is staged once per CTA, V (K x 64) per column step; padded strides (== 4 mod 16 doubles) keep the 8-byte
+//   -U (128 x K) is staged once per CTA, V (K x 64) per column step (double-buffered); padded strides (== 4 mod 16 doubles) keep the 8-byte
 //   fragment loads at the 2-wavefront floor.
 // ------------------------------------------------------------------------------------------------
 constexpr int kFlushRows = 128;
@@ -86,27 +86,64 @@ constexpr int kFlushCols = 64;
 constexpr int kFlushSU = kFlushRows + 4;
 constexpr int kFlushSV = kFlushCols + 4;
 
-inline size_t blk_flush_smem_bytes(int K4) { return sizeof(double) * (size_t)K4 * (kFlushSU + kFlushSV); }
+inline size_t blk_flush_smem_bytes(int K4) { return sizeof(double) * (size_t)K4 * (kFlushSU + (K4 <= 48 ? 2 : 1) * kFlushSV); }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// One CTA walks its column steps; two CTAs share an SM so that one streams T (HBM <-> registers) while the other
+// occupies the tensor pipe.  Within a CTA the V tile of step s+1 is fetched L2 -> shared memory by cp.async while the
+// mma of step s runs (double buffer; single buffer above 48 slots, where two stages no longer fit twice per SM).
 template <bool STREAM>
 __global__ void __launch_bounds__(256, 2) k_blk_flush(double* __restrict__ T, int64_t ld, int R, int C, const double* __restrict__ U,
                                                       const double* __restrict__ V, int64_t ldv, int cnt, int col_steps) {
     extern __shared__ __align__(16) double blk_smem[];
     const int K4 = (cnt + 3) & ~3;
-    double* sU = blk_smem;                  // sU[j][row] = -U[row0 + row, j]
-    double* sV = blk_smem + K4 * kFlushSU;  // sV[j][col] = V[j, col0 + col]
+    const bool dbuf = K4 <= 48;
+    double* sU = blk_smem;                         // sU[j][row] = -U[row0 + row, j]
+    double* sV0 = blk_smem + K4 * kFlushSU;        // sV[j][col] = V[j, col0 + col]
+    double* sV1 = dbuf ? sV0 + K4 * kFlushSV : sV0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t row0 = (int64_t)blockIdx.x * kFlushRows;
+    const int wr = (warp & 3) * 32, wc = (warp >> 2) * 32;
+    const int fq = lane >> 2, fk = lane & 3;
+    const int ksteps = K4 >> 2;
+    const int64_t step0 = (int64_t)blockIdx.y * col_steps;
+    const int64_t steps_total = (C + kFlushCols - 1) / kFlushCols;
+    const int nsteps = (int)max((int64_t)0, min((int64_t)col_steps, steps_total - step0));
+    if (nsteps == 0) return;
+    const bool v_aligned = ((ldv & 1) == 0) && ((reinterpret_cast<uintptr_t>(V) & 15) == 0);
+
+    auto stage_v = [&](int s) {  // V tile of step s -> shared memory, 16-byte cp.async where the tile is full and aligned
+        double* sV = (s & 1) ? sV1 : sV0;
+        const int64_t col0 = (step0 + s) * kFlushCols;
+        if (v_aligned && col0 + kFlushCols <= C) {
+            for (int e = tid; e < K4 * (kFlushCols / 2); e += 256) {
+                const int j = e >> 5, c2 = (e & 31) * 2;
+                double* dst = sV + j * kFlushSV + c2;
+                if (j < cnt) cp_async16(dst, V + (int64_t)j * ldv + col0 + c2);
+                else { dst[0] = 0.; dst[1] = 0.; }
+            }
+        } else {
+            for (int e = tid; e < K4 * kFlushCols; e += 256) {
+                const int j = e >> 6, c = e & (kFlushCols - 1);
+                sV[j * kFlushSV + c] = (j < cnt && col0 + c < C) ? V[(int64_t)j * ldv + col0 + c] : 0.;
+            }
+        }
+        cp_async_commit();
+    };
+
+    stage_v(0);
     for (int e = tid; e < K4 * kFlushRows; e += 256) {
         const int j = e >> 7, i = e & (kFlushRows - 1);
         sU[j * kFlushSU + i] = (j < cnt && row0 + i < ld) ? -U[(int64_t)j * ld + row0 + i] : 0.;
     }
-    const int wr = (warp & 3) * 32, wc = (warp >> 2) * 32;
-    const int fq = lane >> 2, fk = lane & 3;
-    const int ksteps = K4 >> 2;
-    for (int s = 0; s < col_steps; ++s) {
-        const int64_t col0 = ((int64_t)blockIdx.y * col_steps + s) * kFlushCols;
-        if (col0 >= C) break;
+    for (int s = 0; s < nsteps; ++s) {
+        const int64_t col0 = (step0 + s) * kFlushCols;
         // issue the loads of this step's 32 x 32 warp tile first: 16 x 16 B in flight per lane
         double2 acc[4][4];  // [column tile][row tile]: rows row0+wr+8*rt+2*fk,+1 ; column col0+wc+8*ct+fq
 #pragma unroll
@@ -123,12 +160,12 @@ __global__ void __launch_bounds__(256, 2) k_blk_flush(double* __restrict__ T, in
                 }
             }
         }
-        __syncthreads();  // previous step's readers of sV are done
-        for (int e = tid; e < K4 * kFlushCols; e += 256) {
-            const int j = e >> 6, c = e & (kFlushCols - 1);
-            sV[j * kFlushSV + c] = (j < cnt && col0 + c < C) ? V[(int64_t)j * ldv + col0 + c] : 0.;
-        }
-        __syncthreads();
+        if (!dbuf && s > 0) { __syncthreads(); stage_v(s); }  // single buffer: refill after every warp left step s-1
+        cp_async_wait<0>();
+        __syncthreads();  // V tile s (and, for s == 0, -U) visible to every warp; every warp left step s-1
+        if (dbuf && s + 1 < nsteps) stage_v(s + 1);
+        const double* sV = (s & 1) ? sV1 : sV0;
+#pragma unroll 2
         for (int ks = 0; ks < ksteps; ++ks) {
             double a[4], b[4];
             const int j = ks * 4 + fk;

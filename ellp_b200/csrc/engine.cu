@@ -1036,9 +1036,9 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
     const int blk = (ctx->tableau && ctx->blk_kmax > 0 && o->block_k > 1) ? std::min(o->block_k, ctx->blk_kmax) : 0;
     ctx->blk_fill = 0;
     if (blk > 0) {
-        const size_t smem = blk_flush_smem_bytes((blk + 3) & ~3);
-        CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int smem = (int)std::max(blk_flush_smem_bytes(48), blk_flush_smem_bytes(kBlkMax));
+        CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     int check_every = o->check_every > 0 ? o->check_every : (lp.m >= 2048 ? 1 : 8);
     int refactor_every = o->refactor_every > 0 ? o->refactor_every : ((lp.m <= 512 && !ctx->tableau) ? 100 : 0);
@@ -1296,8 +1296,9 @@ int ellp_b200_rankk_update_dev(ellp_b200_ctx* ctx, double* E, int64_t R, int64_t
     CUDA_TRY(cudaSetDevice(ctx->device));
     const int K4 = (k + 3) & ~3;
     const size_t smem = blk_flush_smem_bytes(K4);
-    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush_smem_bytes(kBlkMax)));
-    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush_smem_bytes(kBlkMax)));
+    const int smem_max = (int)std::max(blk_flush_smem_bytes(48), blk_flush_smem_bytes(kBlkMax));
+    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     const int steps_total = (int)((C + kFlushCols - 1) / kFlushCols);
     const int col_steps = std::max(1, std::min(ctx->flush_col_steps, steps_total));
     dim3 grid((unsigned)((ld + kFlushRows - 1) / kFlushRows), (unsigned)((steps_total + col_steps - 1) / col_steps));

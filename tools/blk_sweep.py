@@ -63,8 +63,8 @@ if __name__ == "__main__":
         sizes = list(zip(a[0::2], a[1::2]))
     for m, ns in sizes:
         n = m + ns
-        for k in (4, 8, 16, 24, 32, 48, 64):
-            for cs in ((8,) if k not in (16, 32) else (2, 4, 8, 16, 32)):
+        for k in (8, 16, 32, 40, 48, 64):
+            for cs in ((16,) if k not in (32, 48) else (4, 8, 16, 32, 64)):
                 print(json.dumps(flush_point(ctx, m, n, k, cs)), flush=True)
-        for bk in (0, 8, 16, 24, 32, 48, 64):
+        for bk in (16, 32, 48, 64):
             print(json.dumps(loop_point(ctx, m, ns, bk, 192 if bk else 40)), flush=True)
