@@ -35,7 +35,7 @@ constexpr int kBlkMax = 64;  // largest number of pending pivots (slots) support
 __global__ void __launch_bounds__(256) k_blk_row(DevLP lp, int slot, PivotState* st) {
     __shared__ double su[kBlkMax];
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = lp.n, m = lp.m;
+    const int n = lp.nT, m = lp.m;
     if (st->do_step) {
         const double lambda = st->step;
         const bool at_lower = (st->q_side == ELLP_NB_LOWER);
@@ -58,18 +58,31 @@ __global__ void __launch_bounds__(256) k_blk_row(DevLP lp, int slot, PivotState*
         return;
     }
     const int r = st->r_pos;
+    const int qp = lp.condensed ? st->q_pos : -1;
     if (threadIdx.x < slot) su[threadIdx.x] = lp.U[(int64_t)threadIdx.x * lp.ld + r];
     __syncthreads();
     if (t < n) {
-        double e = lp.T[t * lp.ld + r];
-        for (int j = 0; j < slot; ++j) e = fma(-su[j], lp.V[(int64_t)j * lp.ldv + t], e);
-        const double p = e / st->alpha_r;
-        Vslot[t] = p;
-        lp.dj[t] = fma(-st->rq, p, lp.dj[t]);
+        if (t == qp) {
+            // condensed tableau: this stored column is handed over to the leaving variable, whose current column is e_r
+            // (see k_step_gather_cond): pivot-row entry 1/alpha_r, reduced cost 0 - d_q / alpha_r
+            const double p = 1.0 / st->alpha_r;
+            Vslot[t] = p;
+            lp.dj[t] = fma(-st->rq, p, 0.);
+        } else {
+            double e = lp.T[t * lp.ld + r];
+            for (int j = 0; j < slot; ++j) e = fma(-su[j], lp.V[(int64_t)j * lp.ldv + t], e);
+            const double p = e / st->alpha_r;
+            Vslot[t] = p;
+            lp.dj[t] = fma(-st->rq, p, lp.dj[t]);
+        }
     } else if (t < lp.ldv) {
         Vslot[t] = 0.;
     }
-    if (t < lp.ld) Uslot[t] = (t < m ? lp.dcol[t] : 0.) - (t == r ? 1. : 0.);
+    if (t < lp.ld) {
+        Uslot[t] = (t < m ? lp.dcol[t] : 0.) - (t == r ? 1. : 0.);
+        if (qp >= 0) lp.T[(int64_t)qp * lp.ld + t] = (t == r) ? 1. : 0.;  // stale column := e_r ...
+    }
+    if (qp >= 0 && t < slot) lp.V[t * lp.ldv + qp] = 0.;                 // ... with no pending correction before this slot
 }
 
 // ------------------------------------------------------------------------------------------------

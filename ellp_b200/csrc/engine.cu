@@ -183,14 +183,18 @@ void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap, bool tableau, int blk
     if (tableau) {  // T overwrites A in place; no basis inverse is kept
         lp.G = nullptr;
         lp.Binv = nullptr;
-        lp.T = const_cast<double*>(lp.A);
+        lp.condensed = sharded ? 0 : 1;
+        lp.nT = lp.condensed ? (int32_t)nN : (int32_t)n;
+        lp.T = lp.condensed ? a.take<double>(ld * std::max<size_t>(nN, 1)) : const_cast<double*>(lp.A);
         lp.dj = a.take<double>(n);
-        lp.ldv = (int64_t)align_up(n, 4);
+        lp.ldv = (int64_t)align_up((size_t)std::max<int32_t>(lp.nT, 1), 4);
         lp.U = blk_kmax > 0 ? a.take<double>(ld * (size_t)blk_kmax) : nullptr;
         lp.V = blk_kmax > 0 ? a.take<double>((size_t)lp.ldv * (size_t)blk_kmax) : nullptr;
     } else {
         lp.U = lp.V = nullptr;
         lp.ldv = 0;
+        lp.condensed = 0;
+        lp.nT = 0;
         lp.G = a.take<double>(ld * 2 * m);
         lp.Binv = lp.G ? lp.G + ld * m : nullptr;
         lp.T = nullptr;
@@ -328,23 +332,33 @@ int refactor(ellp_b200_ctx* ctx, uint64_t* count) {
             launch_rank1(ctx, lp.G + (int64_t)k * lp.ld, lp.ld, m, cols, lp.dcol, lp.prow, ctx->d_st, 0);
         }
     } else {
+        // F = full tableau B^-1 A in the buffer of A; the condensed engine then keeps only its nonbasic columns
+        double* F = const_cast<double*>(lp.A);
         int mismatch = 0;
         if (!ctx->sharded) {  // a sharded tableau is only accepted with an identity starting basis (checked at upload)
             CUDA_TRY(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
-            LAUNCH(k_check_identity_basis, m, 256, lp.T, lp.ld, m, lp.Bv, ctx->d_flag);
+            LAUNCH(k_check_identity_basis, m, 256, F, lp.ld, m, lp.Bv, ctx->d_flag);
             CUDA_TRY(cudaMemcpyAsync(&mismatch, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         }
         if (mismatch) {
             for (int k = 0; k < m; ++k) {
-                LAUNCH(k_gj_pivot, 1, 1024, lp.T, lp.ld, m, (const int32_t*)lp.Bv, k, lp.dcol, ctx->d_st);
-                LAUNCH(k_gj_swap_gather, (lp.n + 255) / 256, 256, lp.T, lp.ld, 0, lp.n, k, lp.prow, ctx->d_st);
-                launch_rank1(ctx, lp.T, lp.ld, m, lp.n, lp.dcol, lp.prow, ctx->d_st, 0);
+                LAUNCH(k_gj_pivot, 1, 1024, F, lp.ld, m, (const int32_t*)lp.Bv, k, lp.dcol, ctx->d_st);
+                LAUNCH(k_gj_swap_gather, (lp.n + 255) / 256, 256, F, lp.ld, 0, lp.n, k, lp.prow, ctx->d_st);
+                launch_rank1(ctx, F, lp.ld, m, lp.n, lp.dcol, lp.prow, ctx->d_st, 0);
             }
         }
         LAUNCH(k_init_cB, (int)((lp.ld + 255) / 256), 256, lp);
-        LAUNCH(k_gemv_t<EPI_REDCOST>, gemv_grid(lp.n), 256, lp.T, lp.ld, (const int32_t*)nullptr, lp.n, lp.cB, lp.dj, lp.c + lp.col_lo,
-               (const uint8_t*)nullptr, (double*)nullptr, (PivotState*)nullptr, 0);
+        if (lp.condensed) {
+            dim3 gg((unsigned)std::max<int64_t>(1, std::min<int64_t>(8, (lp.ld + 255) / 256)), (unsigned)lp.nN);
+            LAUNCH(k_gather_cols, gg, 256, F, lp.ld, lp.Nv, lp.nN, lp.T);
+            LAUNCH(k_gemv_t<EPI_PLAIN>, gemv_grid(lp.nN), 256, lp.T, lp.ld, (const int32_t*)nullptr, lp.nN, lp.cB, lp.dj, (const double*)nullptr,
+                   (const uint8_t*)nullptr, (double*)nullptr, (PivotState*)nullptr, 0);
+            LAUNCH(k_redcost_pos, (lp.nN + 255) / 256, 256, lp.c, lp.Nv, lp.nN, lp.dj);
+        } else {
+            LAUNCH(k_gemv_t<EPI_REDCOST>, gemv_grid(lp.n), 256, lp.T, lp.ld, (const int32_t*)nullptr, lp.n, lp.cB, lp.dj, lp.c + lp.col_lo,
+                   (const uint8_t*)nullptr, (double*)nullptr, (PivotState*)nullptr, 0);
+        }
     }
     if (int rc = read_state(ctx)) return rc;
     const int err = ctx->h_st->err;
@@ -367,21 +381,21 @@ void launch_flush(ellp_b200_ctx* ctx, bool profile, size_t* ev_used) {
     if (cnt <= 0) return;
     const int K4 = (cnt + 3) & ~3;
     const size_t smem = blk_flush_smem_bytes(K4);
-    const int steps_total = (lp.n + kFlushCols - 1) / kFlushCols;
+    const int steps_total = (lp.nT + kFlushCols - 1) / kFlushCols;
     const int col_steps = std::max(1, std::min(ctx->flush_col_steps, steps_total));
     dim3 grid((unsigned)((lp.ld + kFlushRows - 1) / kFlushRows), (unsigned)((steps_total + col_steps - 1) / col_steps));
-    const bool stream = (double)lp.ld * lp.n * 8.0 > (double)ctx->rank1_stream_min_mb * 1048576.0;
+    const bool stream = (double)lp.ld * lp.nT * 8.0 > (double)ctx->rank1_stream_min_mb * 1048576.0;
     if (profile && ev_used && *ev_used + 2 <= ctx->ev.size()) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
-    if (stream) LAUNCH_SMEM(k_blk_flush<true>, grid, 256, smem, lp.T, lp.ld, lp.m, lp.n, lp.U, lp.V, lp.ldv, cnt, col_steps);
-    else LAUNCH_SMEM(k_blk_flush<false>, grid, 256, smem, lp.T, lp.ld, lp.m, lp.n, lp.U, lp.V, lp.ldv, cnt, col_steps);
+    if (stream) LAUNCH_SMEM(k_blk_flush<true>, grid, 256, smem, lp.T, lp.ld, lp.m, lp.nT, lp.U, lp.V, lp.ldv, cnt, col_steps);
+    else LAUNCH_SMEM(k_blk_flush<false>, grid, 256, smem, lp.T, lp.ld, lp.m, lp.nT, lp.U, lp.V, lp.ldv, cnt, col_steps);
     if (profile && ev_used && (*ev_used & 1)) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
 }
 
 void launch_tableau_primal_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, bool profile, size_t* ev_used, int blk) {
     DevLP& lp = ctx->lp;
     PivotState* st = ctx->d_st;
-    const int m = lp.m, nN = lp.nN, n = lp.n;
-    LAUNCH(k_price_tab, (nN + 255) / 256, 256, lp.dj, lp.Nv, lp.Ns, nN, lp.rN, lp.key, st);     // primal :189, :253-270
+    const int m = lp.m, nN = lp.nN, nT = lp.nT;
+    LAUNCH(k_price_tab, (nN + 255) / 256, 256, lp.dj, lp.Nv, lp.Ns, nN, lp.rN, lp.key, st, lp.condensed);  // primal :189, :253-270
     LAUNCH_SMEM(k_select_primal, 1, kScanThreads, kScanSmemBytes, lp.key, lp.rN, lp.Nv, lp.Ns, nN, o->tie_rule, st);           // :271-292
     LAUNCH(k_ratio_prep, (m + 255) / 256, 256, lp, 0, blk > 0 ? ctx->blk_fill : 0, st);         // :295-367
     LAUNCH_SMEM(k_ratio_pick, 1, kScanThreads, kScanSmemBytes, lp, o->tie_rule, st);             // :379-434, :205-232
@@ -390,9 +404,9 @@ void launch_tableau_primal_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, boo
         if (++ctx->blk_fill >= blk) launch_flush(ctx, profile, ev_used);
         return;
     }
-    LAUNCH(k_step_gather, (std::max(m, n) + 255) / 256, 256, lp, lp.T, n, st);                   // :408-417 + pivot row
+    LAUNCH(k_step_gather_cond, (int)((std::max<int64_t>(lp.ld, nT) + 255) / 256), 256, lp, st);  // :408-417 + pivot row
     if (profile && *ev_used + 2 <= ctx->ev.size()) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
-    launch_rank1(ctx, lp.T, lp.ld, m, n, lp.dcol, lp.prow, st, 0, lp.dj);
+    launch_rank1(ctx, lp.T, lp.ld, m, nT, lp.dcol, lp.prow, st, 0, lp.dj);
     if (profile && (*ev_used & 1)) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
 }
 

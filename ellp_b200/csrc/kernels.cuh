@@ -61,6 +61,12 @@ struct DevLP {
     int32_t col_lo;
     uint8_t* colstat;  // n local entries: ELLP_NB_* or kColBasic; nullptr when not sharded
     // blocked (deferred rank-k) tableau engine, see blocked.cuh: T_current = T - U V over the pending slots
+    // single-GPU tableau engine: CONDENSED tableau -- T stores only the nN nonbasic columns, column p belongs to the
+    // variable at nonbasic position p (Nv[p]); a pivot overwrites the entering column with the leaving variable's
+    // column (the reference swaps A_B / A_N columns the same way, primal :214-217).  Basic columns are unit vectors
+    // and are never stored or updated: half the bytes and flops of the full m x n tableau when n = 2m.
+    int32_t condensed; // 1: T is ld x nN indexed by position; 0: T is ld x n indexed by (local) variable (sharded engine)
+    int32_t nT;        // columns stored in T (nN when condensed, n otherwise)
     double* U;         // ld x kBlkMax, column j = pivot column of pending pivot j minus e_r (nullptr: rank-1 engine)
     double* V;         // kBlkMax x ldv, row j = scaled pivot row of pending pivot j
     int64_t ldv;
@@ -397,8 +403,9 @@ __global__ void __launch_bounds__(256) k_ratio_prep(DevLP lp, int KS, int cnt, P
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int q_var = st->q_var;
     const bool at_lower = (st->q_side == ELLP_NB_LOWER);
+    const int qc = lp.condensed ? st->q_pos : (q_var - lp.col_lo);  // stored column of the entering variable
     if (cnt > 0) {
-        if (threadIdx.x < cnt) s_vq[threadIdx.x] = lp.V[(int64_t)threadIdx.x * lp.ldv + (q_var - lp.col_lo)];
+        if (threadIdx.x < cnt) s_vq[threadIdx.x] = lp.V[(int64_t)threadIdx.x * lp.ldv + qc];
         __syncthreads();
     }
     double lam = -1.0;  // -1 = skipped (|d_i| < EPS, :321)
@@ -406,7 +413,7 @@ __global__ void __launch_bounds__(256) k_ratio_prep(DevLP lp, int KS, int cnt, P
         double a = 0.;
         if (KS > 0) { for (int ks = 0; ks < KS; ++ks) a += lp.part[(int64_t)ks * lp.ld + i]; }
         else if (KS == 0) {
-            a = lp.T[(int64_t)(q_var - lp.col_lo) * lp.ld + i];
+            a = lp.T[(int64_t)qc * lp.ld + i];
             for (int j = 0; j < cnt; ++j) a = fma(-lp.U[(int64_t)j * lp.ld + i], s_vq[j], a);
         }
         else a = lp.dcol[i];
@@ -669,6 +676,49 @@ __global__ void k_step_gather(DevLP lp, const double* __restrict__ E, int C, Piv
         }
     }
     if (st->do_update && t < C) lp.prow[t] = E[(int64_t)t * lp.ld + st->r_pos] / st->alpha_r;
+}
+
+// K2c for the condensed tableau: as k_step_gather, plus the column bookkeeping of the condensed form.  The entering
+// column (position q_pos) is handed over to the leaving variable, whose current column is e_r: the stored column is
+// overwritten with e_r and its pivot-row entry is 1/alpha_r, so the generic update T[:,q] -= (d - e_r) p_q (k_rank1)
+// leaves -d_i/alpha_r in rows i != r and 1/alpha_r in row r; the reduced cost of the leaving variable, 0 while basic,
+// becomes -d_q/alpha_r the same way.
+__global__ void k_step_gather_cond(DevLP lp, PivotState* st) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (st->do_step) {
+        const double lambda = st->step;
+        const bool at_lower = (st->q_side == ELLP_NB_LOWER);
+        if (t < lp.m) {
+            const double a = lp.dcol[t];
+            const double d_i = at_lower ? -a : a;
+            const int var = (st->do_update && t == st->r_pos) ? st->leave_var : lp.Bv[t];
+            lp.x[var] = lp.x[var] + lambda * d_i;
+        }
+        if (t == 0) {
+            const int q = st->q_var;
+            lp.x[q] = at_lower ? lp.x[q] + lambda : lp.x[q] - lambda;
+        }
+    }
+    if (!st->do_update) return;
+    const int r = st->r_pos, qp = st->q_pos;
+    if (t < lp.nT) {
+        if (t == qp) { lp.prow[t] = 1.0 / st->alpha_r; lp.dj[t] = 0.; }
+        else lp.prow[t] = lp.T[(int64_t)t * lp.ld + r] / st->alpha_r;
+    }
+    if (t < lp.ld) lp.T[(int64_t)qp * lp.ld + t] = (t == r) ? 1. : 0.;
+}
+
+// condensed tableau set-up: T[:, p] = F[:, Nv[p]] (F = full tableau B^-1 A built in the buffer of A)
+__global__ void k_gather_cols(const double* __restrict__ F, int64_t ld, const int32_t* __restrict__ Nv, int nN, double* __restrict__ T) {
+    const int p = blockIdx.y;
+    if (p >= nN) return;
+    const double* src = F + (int64_t)Nv[p] * ld;
+    double* dst = T + (int64_t)p * ld;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ld; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+__global__ void k_redcost_pos(const double* __restrict__ c, const int32_t* __restrict__ Nv, int nN, double* __restrict__ dj) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < nN) dj[p] = c[Nv[p]] - dj[p];  // d_p = c_p - c_B^T (B^-1 a_p); dj holds the dot product on entry
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1183,12 +1233,12 @@ __global__ void k_check_identity_basis(const double* __restrict__ T, int64_t ld,
 
 // tableau engine pricing: reduced costs are a maintained row, so the Dantzig keys are a pure O(n - m) pass
 __global__ void k_price_tab(const double* __restrict__ dj, const int32_t* __restrict__ Nv, const uint8_t* __restrict__ Ns, int nN,
-                            double* __restrict__ rN, double* __restrict__ key, PivotState* st) {
+                            double* __restrict__ rN, double* __restrict__ key, PivotState* st, int condensed) {
     if (blockIdx.x == 0 && threadIdx.x == 0) { st->do_update = 0; st->do_step = 0; }
     if (st->status != kRunning) return;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nN) return;
-    const double r = dj[Nv[j]];
+    const double r = condensed ? dj[j] : dj[Nv[j]];
     const int side = Ns[j];
     double k = -1.0;
     if (!(fabs(r) < kEps)) {  // primal :258-269
