@@ -23,6 +23,7 @@
 // `A_B.clone().lu()` + solves, primal_simplex_solver.rs:173-189,295.
 #pragma once
 #include "kernels.cuh"
+#include <cooperative_groups.h>
 #include "refactor.cuh"
 
 namespace ellp {
@@ -32,57 +33,291 @@ constexpr int kBlkMax = 64;  // largest number of pending pivots (slots) support
 // K2c (blocked): the primal step x_B += lambda d, x_q +-= lambda (primal :408-417), the scaled pivot row of the CURRENT
 // tableau, the reduced-cost row update d_j -= d_q p_j, and the new (U, V) slot.  A bound flip or a finished solve
 // leaves an all-zero slot, so the host can schedule slots without knowing what the device decided.
-__global__ void __launch_bounds__(256) k_blk_row(DevLP lp, int slot, PivotState* st) {
-    __shared__ double su[kBlkMax];
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// Grid-stride over [t0, ...) with stride `stride`; every thread of the block must call it (one __syncthreads).
+__device__ __forceinline__ void blk_row_body(const DevLP& lp, int slot, const PivotState* st, int64_t t0, int64_t stride, double* su) {
     const int n = lp.nT, m = lp.m;
-    if (st->do_step) {
-        const double lambda = st->step;
-        const bool at_lower = (st->q_side == ELLP_NB_LOWER);
-        if (t < m) {
-            const double a = lp.dcol[t];
+    const int do_step = __ldcg(&st->do_step), do_update = __ldcg(&st->do_update);
+    const int r = __ldcg(&st->r_pos);
+    const int64_t tmax = max(lp.ld, lp.ldv);
+    if (do_step) {
+        const double lambda = __ldcg(&st->step);
+        const bool at_lower = (__ldcg(&st->q_side) == ELLP_NB_LOWER);
+        const int leave_var = __ldcg(&st->leave_var);
+        for (int64_t t = t0; t < m; t += stride) {
+            const double a = __ldcg(lp.dcol + t);
             const double d_i = at_lower ? -a : a;
-            const int var = (st->do_update && t == st->r_pos) ? st->leave_var : lp.Bv[t];
-            lp.x[var] = lp.x[var] + lambda * d_i;
+            const int var = (do_update && t == r) ? leave_var : __ldcg(lp.Bv + t);
+            lp.x[var] = __ldcg(lp.x + var) + lambda * d_i;
         }
-        if (t == 0) {
-            const int q = st->q_var;
-            lp.x[q] = at_lower ? lp.x[q] + lambda : lp.x[q] - lambda;
+        if (t0 == 0) {
+            const int q = __ldcg(&st->q_var);
+            lp.x[q] = at_lower ? __ldcg(lp.x + q) + lambda : __ldcg(lp.x + q) - lambda;
         }
     }
     double* Uslot = lp.U + (int64_t)slot * lp.ld;
     double* Vslot = lp.V + (int64_t)slot * lp.ldv;
-    if (!st->do_update) {
-        if (t < lp.ld) Uslot[t] = 0.;
-        if (t < lp.ldv) Vslot[t] = 0.;
+    if (!do_update) {
+        for (int64_t t = t0; t < tmax; t += stride) {
+            if (t < lp.ld) Uslot[t] = 0.;
+            if (t < lp.ldv) Vslot[t] = 0.;
+        }
         return;
     }
-    const int r = st->r_pos;
-    const int qp = lp.condensed ? st->q_pos : -1;
-    if (threadIdx.x < slot) su[threadIdx.x] = lp.U[(int64_t)threadIdx.x * lp.ld + r];
+    const int qp = lp.condensed ? __ldcg(&st->q_pos) : -1;
+    const double alpha_r = __ldcg(&st->alpha_r), rq = __ldcg(&st->rq);
+    if (threadIdx.x < slot) su[threadIdx.x] = __ldcg(lp.U + (int64_t)threadIdx.x * lp.ld + r);
     __syncthreads();
-    if (t < n) {
-        if (t == qp) {
-            // condensed tableau: this stored column is handed over to the leaving variable, whose current column is e_r
-            // (see k_step_gather_cond): pivot-row entry 1/alpha_r, reduced cost 0 - d_q / alpha_r
-            const double p = 1.0 / st->alpha_r;
-            Vslot[t] = p;
-            lp.dj[t] = fma(-st->rq, p, 0.);
-        } else {
-            double e = lp.T[t * lp.ld + r];
-            for (int j = 0; j < slot; ++j) e = fma(-su[j], lp.V[(int64_t)j * lp.ldv + t], e);
-            const double p = e / st->alpha_r;
-            Vslot[t] = p;
-            lp.dj[t] = fma(-st->rq, p, lp.dj[t]);
+    for (int64_t t = t0; t < tmax; t += stride) {
+        if (t < n) {
+            if (t == qp) {
+                // condensed tableau: this stored column is handed over to the leaving variable, whose current column is e_r
+                // (see k_step_gather_cond): pivot-row entry 1/alpha_r, reduced cost 0 - d_q / alpha_r
+                const double p = 1.0 / alpha_r;
+                Vslot[t] = p;
+                lp.dj[t] = fma(-rq, p, 0.);
+            } else {
+                double e = __ldcg(lp.T + t * lp.ld + r);
+                for (int j = 0; j < slot; ++j) e = fma(-su[j], __ldcg(lp.V + (int64_t)j * lp.ldv + t), e);
+                const double p = e / alpha_r;
+                Vslot[t] = p;
+                lp.dj[t] = fma(-rq, p, __ldcg(lp.dj + t));
+            }
+        } else if (t < lp.ldv) {
+            Vslot[t] = 0.;
         }
-    } else if (t < lp.ldv) {
-        Vslot[t] = 0.;
+        if (t < lp.ld) {
+            Uslot[t] = (t < m ? __ldcg(lp.dcol + t) : 0.) - (t == r ? 1. : 0.);
+            if (qp >= 0) lp.T[(int64_t)qp * lp.ld + t] = (t == r) ? 1. : 0.;  // stale column := e_r ...
+        }
+        if (qp >= 0 && t < slot) lp.V[t * lp.ldv + qp] = 0.;                 // ... with no pending correction before this slot
     }
-    if (t < lp.ld) {
-        Uslot[t] = (t < m ? lp.dcol[t] : 0.) - (t == r ? 1. : 0.);
-        if (qp >= 0) lp.T[(int64_t)qp * lp.ld + t] = (t == r) ? 1. : 0.;  // stale column := e_r ...
+}
+
+__global__ void __launch_bounds__(256) k_blk_row(DevLP lp, int slot, PivotState* st) {
+    __shared__ double su[kBlkMax];
+    blk_row_body(lp, slot, st, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x, su);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 (cooperative): up to `npiv` complete primal pivots of the blocked engine in ONE launch.  The five dependent
+// kernels of an iteration (price, select, column + ratios, ratio pick, row + slot) become phases of a persistent
+// grid separated by grid-wide barriers, so an iteration costs four barriers instead of five launches:
+//   A  Dantzig keys over the nonbasic positions + per-block (best, second best) key            | barrier
+//   B  every block merges the partials.  The fold of primal :271-286 is order-independent when the second best key
+//      is at least 2 EPS below the best (same criterion as k_select_primal's fast path): the winner is known to every
+//      thread without another barrier.  Otherwise block 0 evaluates the sequential fold (select_primal_body) | barrier
+//   C  entering column of the CURRENT tableau (stale column + pending corrections), ratios, per-block two smallest | barrier
+//   D  merge, add the entering variable's own range (primal :305-311); isolated minimum => thread 0 commits the pivot
+//      (ratio_commit), else block 0 evaluates the fold of :379-399 (ratio_pick_body)            | barrier
+//   E  x step, pivot row, reduced-cost row, new (U, V) slot (blk_row_body)                      | barrier
+// Decisions are bit-identical to the five-kernel path (same arithmetic, same fast-path criteria, same fold code).
+// Launch: cooperative, kScanThreads threads per block, kScanSmemBytes dynamic shared memory, grid <= co-resident CTAs.
+// ------------------------------------------------------------------------------------------------
+struct Top2 {
+    double a1, a2;
+    int i1;
+};
+template <bool MAX> __device__ __forceinline__ bool top2_better(double a, double b) { return MAX ? (a > b) : (a < b); }
+template <bool MAX> __device__ __forceinline__ void top2_push(Top2& t, double v, int i) {
+    if (top2_better<MAX>(v, t.a1)) { t.a2 = t.a1; t.a1 = v; t.i1 = i; }
+    else if (top2_better<MAX>(v, t.a2)) t.a2 = v;
+}
+template <bool MAX> __device__ __forceinline__ void top2_merge(Top2& t, const Top2& o) {
+    if (top2_better<MAX>(o.a1, t.a1)) {
+        const double second = top2_better<MAX>(t.a1, o.a2) ? t.a1 : o.a2;
+        t.a1 = o.a1; t.i1 = o.i1; t.a2 = second;
+    } else {
+        // o.a1 does not beat t.a1: it competes for second place (also when it EQUALS t.a1 => a2 == a1 => "tie")
+        if (top2_better<MAX>(o.a1, t.a2)) t.a2 = o.a1;
     }
-    if (qp >= 0 && t < slot) lp.V[t * lp.ldv + qp] = 0.;                 // ... with no pending correction before this slot
+}
+struct Top2Smem {
+    double a1[32], a2[32];
+    int i1[32];
+};
+// block-wide merge; the result is valid in every thread
+template <bool MAX> __device__ __forceinline__ Top2 top2_block(Top2 t, Top2Smem* sh) {
+    const unsigned full = 0xffffffffu;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        Top2 o;
+        o.a1 = __shfl_xor_sync(full, t.a1, off);
+        o.a2 = __shfl_xor_sync(full, t.a2, off);
+        o.i1 = __shfl_xor_sync(full, t.i1, off);
+        // both partners of an xor-shuffle must end with the same triple: merge in a fixed (lane-bit) order
+        Top2 lo = ((threadIdx.x & off) == 0) ? t : o, hi = ((threadIdx.x & off) == 0) ? o : t;
+        top2_merge<MAX>(lo, hi);
+        t = lo;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) { sh->a1[warp] = t.a1; sh->a2[warp] = t.a2; sh->i1[warp] = t.i1; }
+    __syncthreads();
+    const double worst = MAX ? -1.0 : CUDART_INF;
+    Top2 r;
+    r.a1 = (lane < nw) ? sh->a1[lane] : worst;
+    r.a2 = (lane < nw) ? sh->a2[lane] : worst;
+    r.i1 = (lane < nw) ? sh->i1[lane] : -1;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        Top2 o;
+        o.a1 = __shfl_xor_sync(full, r.a1, off);
+        o.a2 = __shfl_xor_sync(full, r.a2, off);
+        o.i1 = __shfl_xor_sync(full, r.i1, off);
+        Top2 lo = ((lane & off) == 0) ? r : o, hi = ((lane & off) == 0) ? o : r;
+        top2_merge<MAX>(lo, hi);
+        r = lo;
+    }
+    return r;
+}
+
+// merges the per-block partials part[3*b .. 3*b+2] = (a1, a2, i1) of all `nb` blocks; result valid in every thread
+template <bool MAX> __device__ __forceinline__ Top2 top2_grid(const double* part, int nb, Top2Smem* sh) {
+    const double worst = MAX ? -1.0 : CUDART_INF;
+    Top2 t{worst, worst, -1};
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        Top2 o;
+        o.a1 = __ldcg(part + 3 * b);
+        o.a2 = __ldcg(part + 3 * b + 1);
+        o.i1 = (int)__ldcg(part + 3 * b + 2);
+        top2_merge<MAX>(t, o);
+    }
+    return top2_block<MAX>(t, sh);
+}
+
+__device__ __forceinline__ void blk_zero_slot(const DevLP& lp, int slot, int64_t t0, int64_t stride) {
+    double* Uslot = lp.U + (int64_t)slot * lp.ld;
+    double* Vslot = lp.V + (int64_t)slot * lp.ldv;
+    const int64_t tmax = max(lp.ld, lp.ldv);
+    for (int64_t t = t0; t < tmax; t += stride) {
+        if (t < lp.ld) Uslot[t] = 0.;
+        if (t < lp.ldv) Vslot[t] = 0.;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads, 1) k_blk_pivots(DevLP lp, int tie_rule, int slot0, int npiv, PivotState* st) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char scan_smem[];
+    __shared__ Top2Smem s_top;
+    __shared__ double s_vec[kBlkMax];
+    const int tid = threadIdx.x;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + tid, gsize = (int64_t)gridDim.x * blockDim.x;
+    const int G = gridDim.x;
+    double* partA = lp.coop;            // 3 * G: per-block (best key, second best key, position of the best)
+    double* partC = lp.coop + 3 * 1024;  // 3 * G: per-block (smallest ratio, second smallest, basis position of the smallest)
+    const int nN = lp.nN, m = lp.m;
+    bool run = (__ldcg(&st->status) == kRunning);
+    for (int slot = slot0; slot < slot0 + npiv; ++slot) {
+        if (!run) { blk_zero_slot(lp, slot, gtid, gsize); continue; }
+        // ---- A: pricing (primal :189, :253-270)
+        {
+            Top2 t{-1.0, -1.0, -1};
+            for (int64_t j = gtid; j < nN; j += gsize) {
+                const double r = __ldcg(lp.dj + j);
+                const int side = __ldcg(lp.Ns + j);
+                double k = -1.0;
+                if (!(fabs(r) < kEps)) {
+                    if (r > 0. && side == ELLP_NB_UPPER) k = r;
+                    else if (!(r > 0.) && side == ELLP_NB_LOWER) k = -r;
+                    else if (side == ELLP_NB_FREE) k = fabs(r);
+                }
+                lp.key[j] = k;
+                lp.rN[j] = r;
+                if (k != -1.0) top2_push<true>(t, k, (int)j);
+            }
+            t = top2_block<true>(t, &s_top);
+            if (tid == 0) { partA[3 * blockIdx.x] = t.a1; partA[3 * blockIdx.x + 1] = t.a2; partA[3 * blockIdx.x + 2] = (double)t.i1; }
+        }
+        grid.sync();
+        // ---- B: entering variable (primal :271-292)
+        int q_pos;
+        {
+            const Top2 t = top2_grid<true>(partA, G, &s_top);
+            if (t.a1 == -1.0) {  // no candidate: optimal (:289-292); known to every thread
+                if (gtid == 0) { st->status = ELLP_OPTIMAL; st->do_update = 0; st->do_step = 0; }
+                run = false;
+                blk_zero_slot(lp, slot, gtid, gsize);
+                continue;
+            }
+            const bool fast = !(t.a1 - t.a2 < 2. * kEps);
+            if (fast) {
+                q_pos = t.i1;
+                if (gtid == 0) {
+                    st->q_pos = q_pos;
+                    st->q_var = __ldcg(lp.Nv + q_pos);
+                    st->q_side = __ldcg(lp.Ns + q_pos);
+                    st->rq = __ldcg(lp.dj + q_pos);
+                    st->do_update = 0;
+                    st->do_step = 0;
+                }
+            } else {
+                if (blockIdx.x == 0) {
+                    if (tid == 0) { st->do_update = 0; st->do_step = 0; }
+                    select_primal_body(lp.key, lp.rN, lp.Nv, lp.Ns, nN, tie_rule, st, scan_smem);
+                }
+                grid.sync();
+                if (__ldcg(&st->status) != kRunning) { run = false; blk_zero_slot(lp, slot, gtid, gsize); continue; }
+                q_pos = __ldcg(&st->q_pos);
+            }
+        }
+        const int q_var = __ldcg(lp.Nv + q_pos);
+        const bool at_lower = (__ldcg(lp.Ns + q_pos) == ELLP_NB_LOWER);
+        // ---- C: entering column of the current tableau + ratios (primal :295-367)
+        const int cnt = slot;  // pending slots of this block (the host flushes when the block is full)
+        double lmin_basic;
+        {
+            __syncthreads();
+            if (tid < cnt) s_vec[tid] = __ldcg(lp.V + (int64_t)tid * lp.ldv + q_pos);
+            __syncthreads();
+            Top2 t{CUDART_INF, CUDART_INF, -1};
+            for (int64_t i = gtid; i < lp.ld; i += gsize) {
+                double a = __ldcg(lp.T + (int64_t)q_pos * lp.ld + i);
+                for (int j = 0; j < cnt; ++j) a = fma(-__ldcg(lp.U + (int64_t)j * lp.ld + i), s_vec[j], a);
+                lp.dcol[i] = a;
+                if (i < m) {
+                    const double d_i = at_lower ? -a : a;  // :296-300
+                    double lam = -1.0;                      // -1 = skipped (|d_i| < EPS, :321)
+                    if (!(fabs(d_i) < kEps)) {
+                        const int var = __ldcg(lp.Bv + i);
+                        lam = primal_ratio(lp.kind[var], lp.lb[var], lp.ub[var], __ldcg(lp.x + var), d_i);
+                    }
+                    lp.lam[i] = lam;
+                    if (lam != -1.0 && lam < CUDART_INF) top2_push<false>(t, lam, (int)i);
+                }
+            }
+            t = top2_block<false>(t, &s_top);
+            if (tid == 0) { partC[3 * blockIdx.x] = t.a1; partC[3 * blockIdx.x + 1] = t.a2; partC[3 * blockIdx.x + 2] = (double)t.i1; }
+        }
+        grid.sync();
+        // ---- D: leaving row / bound flip (primal :305-434, :205-232)
+        {
+            Top2 t = top2_grid<false>(partC, G, &s_top);
+            lmin_basic = t.a1;
+            const int kq = lp.kind[q_var];  // :305-311
+            const double lambda0 = (kq == ELLP_TWOSIDED) ? (lp.ub[q_var] - lp.lb[q_var]) : (kq == ELLP_FIXED ? 0. : CUDART_INF);
+            if (lambda0 < CUDART_INF) {
+                Top2 o{lambda0, CUDART_INF, -1};
+                // the entering variable's own range takes part like one more candidate (index -1 = bound flip)
+                if (lambda0 < t.a1) { t.a2 = t.a1; t.a1 = lambda0; t.i1 = -1; }
+                else if (lambda0 < t.a2) t.a2 = lambda0;
+                (void)o;
+            }
+            const bool fast = !(t.a1 < CUDART_INF) || !(t.a2 < t.a1 + 2. * kEps);
+            if (fast) {
+                if (gtid == 0) ratio_commit(lp, st, t.i1, t.a1, at_lower, q_var);
+            } else if (blockIdx.x == 0) {
+                if (tid == 0) st->lmin_bits = __double_as_longlong(lmin_basic);
+                __syncthreads();
+                ratio_pick_body(lp, tie_rule, st, scan_smem);
+            }
+        }
+        grid.sync();
+        // ---- E: step, pivot row, reduced costs, new slot (primal :408-417 + the deferred row reduction)
+        blk_row_body(lp, slot, st, gtid, gsize, s_vec);
+        grid.sync();
+        run = (__ldcg(&st->status) == kRunning);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -95,6 +95,8 @@ struct ellp_b200_ctx {
     int blk_kmax = 0;             // slots allocated for the blocked (deferred rank-k) tableau engine; 0 = rank-1 engine only
     int blk_fill = 0;             // slots used since the last flush
     int flush_col_steps = 8;      // column steps (of 64 columns) per CTA of k_blk_flush
+    int coop_pivots = 1;          // blocked engine: 1 = one cooperative launch per block of pivots (k_blk_pivots), 0 = five kernels per pivot
+    int coop_grid = 0;            // co-resident CTAs of k_blk_pivots (0 = not yet queried)
     int refactor_mode = 0;        // 0 auto (blocked LU + DMMA for m >= 128, Gauss-Jordan below), 1 Gauss-Jordan, 2 blocked LU  // evict-first policy when the updated matrix is larger than this
 };
 
@@ -188,10 +190,12 @@ void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap, bool tableau, int blk
         lp.T = lp.condensed ? a.take<double>(ld * std::max<size_t>(nN, 1)) : const_cast<double*>(lp.A);
         lp.dj = a.take<double>(n);
         lp.ldv = (int64_t)align_up((size_t)std::max<int32_t>(lp.nT, 1), 4);
+        lp.coop = a.take<double>(6 * 1024);
         lp.U = blk_kmax > 0 ? a.take<double>(ld * (size_t)blk_kmax) : nullptr;
         lp.V = blk_kmax > 0 ? a.take<double>((size_t)lp.ldv * (size_t)blk_kmax) : nullptr;
     } else {
         lp.U = lp.V = nullptr;
+        lp.coop = nullptr;
         lp.ldv = 0;
         lp.condensed = 0;
         lp.nT = 0;
@@ -389,6 +393,29 @@ void launch_flush(ellp_b200_ctx* ctx, bool profile, size_t* ev_used) {
     if (stream) LAUNCH_SMEM(k_blk_flush<true>, grid, 256, smem, lp.T, lp.ld, lp.m, lp.nT, lp.U, lp.V, lp.ldv, cnt, col_steps);
     else LAUNCH_SMEM(k_blk_flush<false>, grid, 256, smem, lp.T, lp.ld, lp.m, lp.nT, lp.U, lp.V, lp.ldv, cnt, col_steps);
     if (profile && ev_used && (*ev_used & 1)) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
+}
+
+// blocked engine, single GPU: `npiv` pivots (slots blk_fill .. blk_fill + npiv - 1) in one cooperative launch
+int launch_coop_pivots(ellp_b200_ctx* ctx, const ellp_opts* o, int npiv) {
+    DevLP& lp = ctx->lp;
+    if (ctx->coop_grid == 0) {
+        CUDA_TRY(cudaFuncSetAttribute(k_blk_pivots, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmemBytes));
+        int sms = 0, per_sm = 0, coop = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_blk_pivots, kScanThreads, kScanSmemBytes));
+        ctx->coop_grid = (coop && per_sm > 0) ? std::min(1024, sms * per_sm) : -1;
+    }
+    if (ctx->coop_grid < 0) return set_err(ctx, ELLP_E_CUDA, "cooperative launch unavailable (set tuning coop_pivots = 0)");
+    const int64_t work = std::max<int64_t>(std::max<int64_t>(lp.ld, lp.ldv), lp.nN);
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->coop_grid, (work + kScanThreads - 1) / kScanThreads));
+    int tie = o->tie_rule, slot0 = ctx->blk_fill;
+    PivotState* st = ctx->d_st;
+    void* args[] = {(void*)&lp, (void*)&tie, (void*)&slot0, (void*)&npiv, (void*)&st};
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_blk_pivots, dim3(grid), dim3(kScanThreads), args, (size_t)kScanSmemBytes, ctx->stream));
+    ctx->launches++;
+    ctx->blk_fill += npiv;
+    return ELLP_OK;
 }
 
 void launch_tableau_primal_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, bool profile, size_t* ev_used, int blk) {
@@ -603,6 +630,7 @@ int ellp_b200_set_tuning(ellp_b200_ctx* ctx, const char* key, int value) {
     else if (!std::strcmp(key, "rank1_stream_min_mb")) ctx->rank1_stream_min_mb = value;
     else if (!std::strcmp(key, "refactor_mode")) ctx->refactor_mode = value;
     else if (!std::strcmp(key, "flush_col_steps")) ctx->flush_col_steps = std::max(1, value);
+    else if (!std::strcmp(key, "coop_pivots")) ctx->coop_pivots = value;
     else return set_err(ctx, ELLP_E_ARG, std::string("unknown tuning key ") + key);
     return ELLP_OK;
 }
@@ -1063,6 +1091,18 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
         // never enqueue more iterations than the pivot budget still allows (they would be no-op launches)
         if (o->max_iter - h.pivots < (uint64_t)batch) batch = (int)std::max<uint64_t>(1, o->max_iter - h.pivots);
         if (refactor_every > 0) batch = (int)std::min<uint64_t>(batch, std::max<uint64_t>(1, refactor_every - ctx->pivots_since_refactor));
+        if (blk > 0 && !ctx->sharded && ctx->coop_pivots && lp.condensed) {
+            // cooperative path: whole blocks of pivots per launch, a flush after every full block
+            int left = std::max(batch, blk);
+            if (o->max_iter - h.pivots < (uint64_t)left) left = (int)std::max<uint64_t>(1, o->max_iter - h.pivots);
+            while (left > 0 && !rc_loop) {
+                const int npiv = std::min(left, blk - ctx->blk_fill);
+                rc_loop = launch_coop_pivots(ctx, o, npiv);
+                left -= npiv;
+                if (!rc_loop && ctx->blk_fill >= blk) launch_flush(ctx, profile, &ev_used);
+            }
+            batch = 0;
+        }
         for (int k = 0; k < batch; ++k) {
             if (ctx->sharded) { if ((rc_loop = launch_sharded_iteration(ctx, o, profile, &ev_used, blk))) break; }
             else if (ctx->tableau) launch_tableau_primal_iteration(ctx, o, profile, &ev_used, blk);

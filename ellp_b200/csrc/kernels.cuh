@@ -70,6 +70,7 @@ struct DevLP {
     double* U;         // ld x kBlkMax, column j = pivot column of pending pivot j minus e_r (nullptr: rank-1 engine)
     double* V;         // kBlkMax x ldv, row j = scaled pivot row of pending pivot j
     int64_t ldv;
+    double* coop;      // 6 * 1024 doubles: per-block partials of the cooperative pivot kernel (blocked.cuh)
     double* xchg;      // small exchange buffers: [0] local max key | [8..8+3) candidate | [16..16+G) gathered max | [32..32+3G) gathered candidates
 };
 
@@ -173,11 +174,10 @@ __device__ __forceinline__ void scan_load_tile(const double* __restrict__ val, c
     }
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_select_primal(const double* __restrict__ key, const double* __restrict__ rN,
-                                                                const int32_t* __restrict__ Nv, const uint8_t* __restrict__ Ns,
-                                                                int nN, int tie_rule, PivotState* st) {
-    if (st->status != kRunning) return;
-    extern __shared__ __align__(16) unsigned char scan_smem[];
+// Body shared by k_select_primal (one CTA of kScanThreads threads) and block 0 of the cooperative pivot kernel
+// (blocked.cuh); needs kScanSmemBytes of dynamic shared memory at scan_smem.
+__device__ __forceinline__ void select_primal_body(const double* key, const double* rN, const int32_t* Nv, const uint8_t* Ns,
+                                                   int nN, int tie_rule, PivotState* st, unsigned char* scan_smem) {
     double* sval[2] = {reinterpret_cast<double*>(scan_smem), reinterpret_cast<double*>(scan_smem) + kScanTile};
     int* stag[2] = {reinterpret_cast<int*>(scan_smem + 2 * kScanTile * 8), reinterpret_cast<int*>(scan_smem + 2 * kScanTile * 8) + kScanTile};
     __shared__ double s_red[32];
@@ -304,6 +304,14 @@ __global__ void __launch_bounds__(kScanThreads) k_select_primal(const double* __
             st->rq = rN[bp];
         }
     }
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_select_primal(const double* __restrict__ key, const double* __restrict__ rN,
+                                                                const int32_t* __restrict__ Nv, const uint8_t* __restrict__ Ns,
+                                                                int nN, int tie_rule, PivotState* st) {
+    if (st->status != kRunning) return;
+    extern __shared__ __align__(16) unsigned char scan_smem[];
+    select_primal_body(key, rN, Nv, Ns, nN, tie_rule, st, scan_smem);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -441,8 +449,9 @@ __global__ void __launch_bounds__(256) k_ratio_prep(DevLP lp, int KS, int cnt, P
 // K2b: the ratio fold (primal :305-400), the step decision (:402-434) and the pivot bookkeeping (:205-232), single CTA.
 // tie_rule 0 reproduces the sequential scan with its (lambda, new_basic, new_basic_index) state exactly -- including the
 // stale-index behaviour of :379-399 -- with an exact shortcut when the minimum is isolated.
-__global__ void __launch_bounds__(1024) k_ratio_pick(DevLP lp, int tie_rule, PivotState* st) {
-    if (st->status != kRunning) return;
+__device__ __forceinline__ void ratio_commit(const DevLP& lp, PivotState* st, int nb, double lambda, bool at_lower, int q_var);
+
+__device__ __forceinline__ void ratio_pick_body(const DevLP& lp, int tie_rule, PivotState* st, unsigned char* scan_smem) {
     __shared__ double s_lambda;
     __shared__ int s_nb;
     const int tid = threadIdx.x;
@@ -451,7 +460,6 @@ __global__ void __launch_bounds__(1024) k_ratio_pick(DevLP lp, int tie_rule, Piv
     const bool at_lower = (st->q_side == ELLP_NB_LOWER);
     __syncthreads();
     {
-        extern __shared__ __align__(16) unsigned char scan_smem[];
         double* sval[2] = {reinterpret_cast<double*>(scan_smem), reinterpret_cast<double*>(scan_smem) + kScanTile};
         int* stag[2] = {reinterpret_cast<int*>(scan_smem + 2 * kScanTile * 8), reinterpret_cast<int*>(scan_smem + 2 * kScanTile * 8) + kScanTile};
         __shared__ double s_red[32];
@@ -581,15 +589,21 @@ __global__ void __launch_bounds__(1024) k_ratio_pick(DevLP lp, int tie_rule, Piv
     __syncthreads();
     const double lambda = s_lambda;
     const int nb = s_nb;
+    if (tid == 0) ratio_commit(lp, st, nb, lambda, at_lower, q_var);
+}
+
+// The step decision (:402-434) and the pivot bookkeeping (:205-232) for the outcome (nb, lambda) of the ratio fold:
+// nb = leaving basis position or -1 for a bound flip of the entering variable.  One thread.
+__device__ __forceinline__ void ratio_commit(const DevLP& lp, PivotState* st, int nb, double lambda, bool at_lower, int q_var) {
     if (!(lambda >= 0.)) {  // :402 assert!(lambda >= 0.)
-        if (tid == 0) { st->err = kErrLambdaNegative; st->status = ELLP_UNBOUNDED; st->do_update = 0; st->do_step = 0; }
+        st->err = kErrLambdaNegative; st->status = ELLP_UNBOUNDED; st->do_update = 0; st->do_step = 0;
         return;
     }
     if (isinf(lambda)) {  // :404-406
-        if (tid == 0) { st->status = ELLP_UNBOUNDED; st->do_update = 0; st->do_step = 0; }
+        st->status = ELLP_UNBOUNDED; st->do_update = 0; st->do_step = 0;
         return;
     }
-    if (tid == 0) {
+    {
         st->do_step = (lambda > 0.) ? 1 : 0;  // :408-417 is carried out by k_step_gather (x moves along d by lambda)
         const int q_pos = st->q_pos;
         const int64_t t = st->trace_len;
@@ -641,6 +655,12 @@ __global__ void __launch_bounds__(1024) k_ratio_pick(DevLP lp, int tie_rule, Piv
         st->pivots += 1;
         if (st->status == kRunning && st->pivots >= st->max_iter) st->status = ELLP_MAXITER;  // :163-166 at the next loop head
     }
+}
+
+__global__ void __launch_bounds__(1024) k_ratio_pick(DevLP lp, int tie_rule, PivotState* st) {
+    if (st->status != kRunning) return;
+    extern __shared__ __align__(16) unsigned char scan_smem[];
+    ratio_pick_body(lp, tie_rule, st, scan_smem);
 }
 
 // ------------------------------------------------------------------------------------------------
