@@ -31,16 +31,16 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # BASELINE.json configs[4]: "synthetic dense LP 32768x65536 fp64, tableau column-sharded ... at 1/2/4/8 B200"
-    "dense_tableau_32768x65536": dict(m=32768, ns=32768, pivots=20, sample_m=1024, sample_pivots=3),
+    "dense_tableau_32768x65536": dict(m=32768, ns=32768, pivots=480, block_k=32, sample_m=1024, sample_pivots=3),
     # north_star target size: "for a 16384x32768 dense LP, the row-reduction kernel sustains >= 70% of HBM bandwidth"
-    "dense_tableau_16384x32768": dict(m=16384, ns=16384, pivots=40, sample_m=1024, sample_pivots=3),
-    "dense_tableau_4096x12288": dict(m=4096, ns=8192, pivots=200, sample_m=512, sample_pivots=6),
+    "dense_tableau_16384x32768": dict(m=16384, ns=16384, pivots=480, block_k=32, sample_m=1024, sample_pivots=3),
+    "dense_tableau_4096x12288": dict(m=4096, ns=8192, pivots=960, block_k=32, sample_m=512, sample_pivots=6),
     # BASELINE.json configs[2] shape: dense 4096x8192 (Gte rows => standard form 4096x12288), DUAL simplex, revised engine
     # (explicit basis inverse).  The entering/leaving rules are the reference's (steepest edge is not built yet).
     "dense_revised_dual_4096x12288": dict(m=4096, ns=8192, pivots=200, sample_m=512, sample_pivots=6, dual=True),
     # the same LP with dual steepest edge (exact weights from the rank-1 update's epilogue) + Harris ratio test
     "dense_revised_dual_dse_4096x12288": dict(m=4096, ns=8192, pivots=200, sample_m=512, sample_pivots=6, dual=True, dse=True),
-    "dense_tableau_tiny": dict(m=256, ns=256, pivots=20, sample_m=128, sample_pivots=4),
+    "dense_tableau_tiny": dict(m=256, ns=256, pivots=32, block_k=8, sample_m=128, sample_pivots=4),
     # BASELINE.json configs[3]: "batch of 65536 independent small LPs (64x128), sharded one shard per GPU at 1/2/4/8 B200"
     "batch_small_lps_65536x64x128": dict(batch=True, nlp=65536, m=64, ns=128, sample_lps=150),
     "batch_small_lps_tiny": dict(batch=True, nlp=600, m=64, ns=128, sample_lps=20),
@@ -290,7 +290,10 @@ def run_ours(args, wl, name):
     dual = bool(wl.get("dual"))
     engine = N.ENGINE_REVISED if dual else N.ENGINE_TABLEAU
     rules = dict(pricing=N.PRICE_STEEPEST_EDGE, ratio=N.RATIO_HARRIS) if wl.get("dse") else {}
-    o = N.default_opts(P, engine=engine, check_every=min(P, 16), profile=True, **rules)
+    bk = 0 if dual else (wl.get("block_k", 0) if args.block_k < 0 else args.block_k)
+    if bk > 1:
+        rules["block_k"] = bk
+    o = N.default_opts(P, engine=engine, check_every=min(P, max(16, bk)), profile=True, **rules)
     ctx.check(N.lib.ellp_b200_generate_dense_ex(ctx.h, m, ns, SEED, 1 if dual else 0, C.byref(o)))
 
     full_solve = bool(wl.get("dse"))  # steepest edge reaches the optimum within a few hundred pivots: a step = one whole solve
@@ -330,22 +333,35 @@ def run_ours(args, wl, name):
     value = pivots_done / dt
     P = pivots_done // args.steps
 
-    # roofline of the dominant kernel (K3 rank-1 update of the m x n tableau): algorithmic bytes per launch
+    # roofline of the dominant kernel = the row reduction.  Rank-1 engine: k_rank1 over the m x n tableau (revised engine:
+    # over the m x m basis inverse).  Blocked engine (block_k > 1): k_blk_flush, the deferred rank-k form T -= U V over the
+    # condensed m x (n - m) tableau (only nonbasic columns are stored), once every block_k pivots.
     peak, peak_src = measured_peak()
-    k3_cols = m if dual else n  # revised engine: K3 updates the m x m basis inverse; tableau engine: the m x n tableau
-    alg_bytes = 16.0 * m * k3_cols + 8.0 * (m + k3_cols)
+    if bk > 1:
+        k3_cols = ns
+        alg_bytes = 16.0 * m * k3_cols + 8.0 * bk * (m + k3_cols)
+        kernel = "k_blk_flush (rank-%d row reduction T -= U V of the condensed %d x %d tableau, fp64 DMMA)" % (bk, m, ns)
+        traffic_key = name + ":k_blk_flush"
+    else:
+        k3_cols = m if dual else ns  # revised engine: K3 updates the m x m basis inverse; tableau engine: the condensed tableau
+        alg_bytes = 16.0 * m * k3_cols + 8.0 * (m + k3_cols)
+        kernel = "k_rank1 (rank-1 row reduction of the %s)" % ("basis inverse" if dual else "tableau")
+        traffic_key = name + ":k_rank1"
     k3_ms = rank1_ms / max(n_rank1, 1)
     achieved = alg_bytes / (k3_ms * 1e-3) / 1e9 if n_rank1 else None
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "k3_ncu_traffic.json")) as f:
-            traffic = json.load(f).get(name)
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get(traffic_key)
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_rank1 (rank-1 row reduction of the %s)" % ("basis inverse" if dual else "tableau"), "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "frac_of_8TBs_nominal": (achieved / 8000.0) if achieved else None,
                 "traffic": traffic, "peak_source": peak_src, "ms_per_launch": k3_ms, "launches_timed": n_rank1,
                 "algorithmic_bytes_per_launch": alg_bytes, "share_of_step_device_time": (rank1_ms / dev_ms) if dev_ms else None}
+    if bk > 1 and n_rank1:
+        roofline["dmma_tflops"] = 2.0 * m * k3_cols * bk / (k3_ms * 1e-3) / 1e12
+        roofline["pivots_per_launch"] = bk
 
     # ---- e2e: the C-ABI boundary on HOST buffers (H2D + pivots + D2H inside the timed region)
     e2e = None
@@ -362,7 +378,7 @@ def run_ours(args, wl, name):
         y0 = np.zeros(m); d0 = c_h.copy()
         B0 = np.arange(ns, n, dtype=np.int32); N0 = np.arange(ns, dtype=np.int32); Ns0 = np.zeros(ns, dtype=np.uint8)
         sf = N.StdForm(m, n, N.ptr(A_np), N.ptr(c_h), N.ptr(b_h), N.ptr(kind_h), N.ptr(lb_h), N.ptr(ub_h))
-        oe = N.default_opts(P, engine=engine, check_every=min(P, 16), **rules)
+        oe = N.default_opts(P, engine=engine, check_every=min(P, max(16, bk)), **rules)
         xs = torch.empty(n, dtype=torch.float64, pin_memory=True).numpy()
 
         def e2e_step():
@@ -405,9 +421,10 @@ def run_ours(args, wl, name):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "m": m, "n": n, "pivots_per_step": P, "engine": "revised (explicit B^-1), dual simplex" if dual else "tableau (B^-1 A resident, in place)",
+            "config": {"workload": name, "m": m, "n": n, "pivots_per_step": P, "engine": "revised (explicit B^-1), dual simplex" if dual else ("condensed tableau (nonbasic columns of B^-1 A resident), " + (f"blocked: one cooperative launch per {bk} pivots + one rank-{bk} flush" if bk > 1 else "rank-1 update per pivot")),
+                       "block_k": bk,
                        "tie_rule": "reference folds", "dual_rules": "steepest edge + Harris" if wl.get("dse") else "reference (first infeasible / first min ratio)", "l2": (f"A_N {8.0 * m * ns / 1e6:.0f} MB + B^-1 {8.0 * m * m / 1e6:.0f} MB streamed every pivot (> 126 MB L2, no flush)" if dual
-                              else f"tableau {8.0 * m * n / 1e9:.1f} GB >> 126 MB L2 (no flush needed)"),
+                              else f"condensed tableau {8.0 * m * ns / 1e9:.1f} GB >> 126 MB L2 (no L2 flush needed)"),
                        "baseline_config": "BASELINE.json configs[4]" if name == DEFAULT_WORKLOAD else "north_star / smaller variant"},
             "device_ms_per_step": dev_ms / args.steps, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
             "cpu_baseline": cpu, "e2e": e2e}
@@ -423,6 +440,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--pivots", type=int, default=0, help="pivots per step (0 = workload default)")
+    ap.add_argument("--block-k", type=int, default=-1, help="tableau engine: pivots per deferred rank-k row reduction (-1 = workload default, 0 = rank-1 engine)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

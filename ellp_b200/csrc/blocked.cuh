@@ -63,7 +63,11 @@ __device__ __forceinline__ void blk_row_body(const DevLP& lp, int slot, const Pi
         }
         return;
     }
-    const int qp = lp.condensed ? __ldcg(&st->q_pos) : -1;
+    int qp = -1;  // locally stored column that is handed over to the leaving variable (condensed tableau)
+    if (lp.condensed) {
+        const int q = __ldcg(&st->q_pos) - lp.pos_lo;
+        if (q >= 0 && q < n) qp = q;
+    }
     const double alpha_r = __ldcg(&st->alpha_r), rq = __ldcg(&st->rq);
     if (threadIdx.x < slot) su[threadIdx.x] = __ldcg(lp.U + (int64_t)threadIdx.x * lp.ld + r);
     __syncthreads();

@@ -67,6 +67,8 @@ struct DevLP {
     // and are never stored or updated: half the bytes and flops of the full m x n tableau when n = 2m.
     int32_t condensed; // 1: T is ld x nN indexed by position; 0: T is ld x n indexed by (local) variable (sharded engine)
     int32_t nT;        // columns stored in T (nN when condensed, n otherwise)
+    int32_t pos_lo;    // peer-sharded condensed tableau (peer.cuh): T / dj / V / key / rN hold the nonbasic POSITIONS
+                       // [pos_lo, pos_lo + nT) of the replicated N list; 0 on a single GPU (nT == nN)
     double* U;         // ld x kBlkMax, column j = pivot column of pending pivot j minus e_r (nullptr: rank-1 engine)
     double* V;         // kBlkMax x ldv, row j = scaled pivot row of pending pivot j
     int64_t ldv;
