@@ -17,6 +17,7 @@
 #include "batch.cuh"
 #include "refactor.cuh"
 #include "blocked.cuh"
+#include "peer.cuh"
 
 using namespace ellp;
 
@@ -97,10 +98,20 @@ struct ellp_b200_ctx {
     int flush_col_steps = 8;      // column steps (of 64 columns) per CTA of k_blk_flush
     int coop_pivots = 1;          // blocked engine: 1 = one cooperative launch per block of pivots (k_blk_pivots), 0 = five kernels per pivot
     int coop_grid = 0;            // co-resident CTAs of k_blk_pivots (0 = not yet queried)
+    // peer-memory sharded engine (peer.cuh): condensed tableau split by nonbasic position, exchange fused into the pivot kernel
+    bool peer_mode = false;       // the resident LP uses the peer layout
+    int peer_exchange = 1;        // tuning: sharded + block_k > 1 => peer layout (1) or the NCCL path on the full tableau (0)
+    PeerLinks pl{};               // peer-mapped mailboxes / column buffers (passed to the kernel by value)
+    void* peer_own = nullptr;     // this rank's exchange buffer (cudaMalloc, exported with cudaIpcGetMemHandle)
+    void* peer_map[kMaxPeers] = {nullptr};  // cudaIpcOpenMemHandle mappings of the other ranks' buffers
+    int64_t peer_cap = 0;         // rows per parity slot of the column buffers
+    uint32_t xseq = 0;            // pivots exchanged since the communicator was created (wire sequence number)
+    int coop_grid_peer = 0;
     int refactor_mode = 0;        // 0 auto (blocked LU + DMMA for m >= 128, Gauss-Jordan below), 1 Gauss-Jordan, 2 blocked LU  // evict-first policy when the updated matrix is larger than this
 };
 
 extern "C" { static void batch_free(ellp_b200_ctx* ctx); }
+static void peer_release(ellp_b200_ctx* ctx);
 
 // ---- NCCL, bound at run time (torch ships libnccl.so.2; the library must also load on boxes without it) -----------
 namespace nccl {
@@ -418,6 +429,174 @@ int launch_coop_pivots(ellp_b200_ctx* ctx, const ellp_opts* o, int npiv) {
     return ELLP_OK;
 }
 
+// ---- peer-memory sharded engine (peer.cuh) -------------------------------------------------------------------------
+// Exchange buffer of one rank: [ kMboxWords mailbox words | 2 * cap column words | 2 tickets ], 16 bytes per word.
+// Collective: every rank calls it with the same `rows`.  The cudaIpc handles travel through one ncclAllGather.
+int peer_setup(ellp_b200_ctx* ctx, int64_t rows) {
+    if (ctx->peer_own && ctx->peer_cap >= rows) return ELLP_OK;
+    const int R = ctx->nranks;
+    if (R > kMaxPeers) return set_err(ctx, ELLP_E_ARG, "the peer-memory engine supports at most 8 ranks");
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    peer_release(ctx);
+    const int64_t cap = (int64_t)align_up((size_t)std::max<int64_t>(rows, 1024), 1024);
+    const size_t words = (size_t)kMboxWords + 2 * (size_t)cap;
+    const size_t bytes = words * sizeof(uint4) + 256;
+    CUDA_TRY(cudaMalloc(&ctx->peer_own, bytes));
+    CUDA_TRY(cudaMemsetAsync(ctx->peer_own, 0, bytes, ctx->stream));
+    std::vector<cudaIpcMemHandle_t> handles((size_t)R);
+    if (R > 1) {
+        cudaIpcMemHandle_t mine;
+        CUDA_TRY(cudaIpcGetMemHandle(&mine, ctx->peer_own));
+        unsigned char* d_h = nullptr;
+        CUDA_TRY(cudaMalloc(&d_h, sizeof(cudaIpcMemHandle_t) * (size_t)(R + 1)));
+        CUDA_TRY(cudaMemcpyAsync(d_h, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
+        // the all-gather also orders every rank's memset before any rank's first remote store
+        NCCL_TRY(nccl::api.AllGather(d_h, d_h + sizeof(mine), sizeof(mine), nccl::kUint8, ctx->nccl_comm, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(handles.data(), d_h + sizeof(mine), sizeof(mine) * (size_t)R, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaFree(d_h));
+    }
+    PeerLinks pl{};
+    pl.rank = ctx->rank;
+    pl.nranks = R;
+    pl.col_cap = cap;
+    for (int r = 0; r < R; ++r) {
+        void* base = ctx->peer_own;
+        if (r != ctx->rank) {
+            CUDA_TRY(cudaIpcOpenMemHandle(&ctx->peer_map[r], handles[(size_t)r], cudaIpcMemLazyEnablePeerAccess));
+            base = ctx->peer_map[r];
+        }
+        pl.mbox[r] = reinterpret_cast<uint4*>(base);
+        pl.col[r] = reinterpret_cast<uint4*>(base) + kMboxWords;
+    }
+    pl.ticket = reinterpret_cast<unsigned int*>(reinterpret_cast<uint4*>(ctx->peer_own) + words);
+    ctx->pl = pl;
+    ctx->peer_cap = cap;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return ELLP_OK;
+}
+
+// layout of the peer engine: replicated vectors + the local slice [pos_lo, pos_lo + nT) of the condensed tableau
+void carve_peer(Arena& a, DevLP& lp, int64_t trace_cap, int blk_kmax) {
+    const size_t ld = (size_t)lp.ld, m = (size_t)lp.m, ng = (size_t)lp.n_glob, nN = (size_t)lp.nN, nT = (size_t)lp.nT;
+    lp.c = a.take<double>(ng);
+    lp.b = a.take<double>(m);
+    lp.lb = a.take<double>(ng);
+    lp.ub = a.take<double>(ng);
+    lp.kind = a.take<uint8_t>(ng);
+    lp.x = a.take<double>(ng);
+    lp.Bv = a.take<int32_t>(m);
+    lp.Nv = a.take<int32_t>(nN);
+    lp.Ns = a.take<uint8_t>(nN);
+    lp.y = a.take<double>(ld);
+    lp.d = a.take<double>(ng);
+    lp.G = lp.Binv = nullptr;
+    lp.condensed = 1;
+    lp.T = a.take<double>(ld * nT);
+    lp.A = lp.T;  // the starting basis is the identity: T = A_N; the constraint matrix is not kept separately
+    lp.dj = a.take<double>(nT + 8);
+    lp.ldv = (int64_t)align_up(nT, 4);
+    lp.coop = a.take<double>(6 * 1024);
+    lp.U = a.take<double>(ld * (size_t)blk_kmax);
+    lp.V = a.take<double>((size_t)lp.ldv * (size_t)blk_kmax);
+    lp.cB = a.take<double>(ld);
+    lp.u = a.take<double>(ld);
+    lp.rN = a.take<double>(nT + 8);
+    lp.key = a.take<double>(nT + 8);
+    lp.dcol = a.take<double>(ld);
+    lp.rho = a.take<double>(ld);
+    lp.prow = a.take<double>(nT + 8);
+    lp.part = a.take<double>(8);
+    lp.lam = a.take<double>(m);
+    lp.lu_piv = a.take<int32_t>(m);
+    lp.w = lp.npart = nullptr;
+    lp.trace = trace_cap > 0 ? a.take<ellp_trace_rec>((size_t)trace_cap) : nullptr;
+    lp.colstat = nullptr;
+    lp.xchg = nullptr;
+}
+
+int peer_prepare(ellp_b200_ctx* ctx, int32_t m, int32_t n_glob, const ellp_opts* o, DevLP* out) {
+    if (!ctx->nccl_comm) return set_err(ctx, ELLP_E_ARG, "call ellp_b200_comm_init first");
+    const int nN = n_glob - m;
+    if (nN <= 0 || nN % ctx->nranks != 0) return set_err(ctx, ELLP_E_ARG, "peer sharding needs the number of nonbasic columns (n - m) divisible by the number of ranks");
+    if (m % 4 != 0) return set_err(ctx, ELLP_E_ARG, "column sharding needs m % 4 == 0");
+    const int blk = blk_slots(o, true);
+    if (blk <= 1) return set_err(ctx, ELLP_E_ARG, "the peer-memory engine needs ellp_opts::block_k > 1");
+    DevLP lp{};
+    lp.m = m;
+    lp.n_glob = n_glob;
+    lp.n = n_glob;
+    lp.col_lo = 0;
+    lp.nN = nN;
+    lp.nT = nN / ctx->nranks;
+    lp.pos_lo = ctx->rank * lp.nT;
+    lp.ld = m;
+    const int64_t tcap = o->trace ? o->trace_cap : 0;
+    Arena probe;
+    carve_peer(probe, lp, tcap, blk);
+    if (int rc = ensure_arena(ctx, probe.off + 256)) return rc;
+    Arena a;
+    a.base = ctx->arena;
+    carve_peer(a, lp, tcap, blk);
+    if (int rc = peer_setup(ctx, lp.ld)) return rc;
+    CUDA_TRY(cudaMemsetAsync(lp.cB, 0, (size_t)((char*)lp.lam - (char*)lp.cB), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(lp.y, 0, sizeof(double) * lp.ld, ctx->stream));
+    ctx->blk_kmax = blk;
+    ctx->blk_fill = 0;
+    ctx->KS = 1;
+    ctx->kc = 64;
+    ctx->trace_cap = tcap;
+    ctx->solver = ELLP_PRIMAL;
+    ctx->tableau = true;
+    ctx->sharded = true;
+    ctx->peer_mode = true;
+    ctx->dual_obj0 = 0.;
+    *out = lp;
+    return ELLP_OK;
+}
+
+// reduced-cost row of the local positions of the fresh tableau (identity basis: T = A_N)
+int peer_finish_init(ellp_b200_ctx* ctx) {
+    DevLP& lp = ctx->lp;
+    LAUNCH(k_init_cB, (int)((lp.ld + 255) / 256), 256, lp);
+    LAUNCH(k_gemv_t<EPI_PLAIN>, gemv_grid(lp.nT), 256, lp.T, lp.ld, (const int32_t*)nullptr, lp.nT, lp.cB, lp.dj, (const double*)nullptr,
+           (const uint8_t*)nullptr, (double*)nullptr, (PivotState*)nullptr, 0);
+    LAUNCH(k_redcost_pos_local, (lp.nT + 255) / 256, 256, lp.c, lp.Nv, lp.pos_lo, lp.nT, lp.dj);
+    ctx->resident = true;
+    ctx->binv_valid = true;
+    ctx->pivots_since_refactor = 0;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaGetLastError());
+    return ELLP_OK;
+}
+
+// `npiv` pivots of the peer engine (slots blk_fill .. blk_fill + npiv - 1) in one cooperative launch; every rank
+// issues the same sequence of launches
+int launch_coop_pivots_peer(ellp_b200_ctx* ctx, const ellp_opts* o, int npiv) {
+    DevLP& lp = ctx->lp;
+    if (ctx->coop_grid_peer == 0) {
+        CUDA_TRY(cudaFuncSetAttribute(k_blk_pivots_peer, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmemBytes));
+        int sms = 0, per_sm = 0, coop = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_blk_pivots_peer, kScanThreads, kScanSmemBytes));
+        ctx->coop_grid_peer = (coop && per_sm > 0) ? std::min(1024, sms * per_sm) : -1;
+    }
+    if (ctx->coop_grid_peer < 0) return set_err(ctx, ELLP_E_CUDA, "cooperative launch unavailable");
+    const int64_t work = std::max<int64_t>(std::max<int64_t>(lp.ld, lp.ldv), lp.nT);
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->coop_grid_peer, (work + kScanThreads - 1) / kScanThreads));
+    int tie = o->tie_rule, slot0 = ctx->blk_fill;
+    uint32_t seq0 = ctx->xseq;
+    PivotState* st = ctx->d_st;
+    PeerLinks pl = ctx->pl;
+    void* args[] = {(void*)&lp, (void*)&pl, (void*)&tie, (void*)&slot0, (void*)&npiv, (void*)&seq0, (void*)&st};
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_blk_pivots_peer, dim3(grid), dim3(kScanThreads), args, (size_t)kScanSmemBytes, ctx->stream));
+    ctx->launches++;
+    ctx->blk_fill += npiv;
+    ctx->xseq += (uint32_t)npiv;
+    return ELLP_OK;
+}
+
 void launch_tableau_primal_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, bool profile, size_t* ev_used, int blk) {
     DevLP& lp = ctx->lp;
     PivotState* st = ctx->d_st;
@@ -572,6 +751,14 @@ int ellp::host_solve_trivial(const ellp_std_form* sf, ellp_point* pt, bool minim
     return ELLP_OPTIMAL;
 }
 
+static void peer_release(ellp_b200_ctx* ctx) {
+    for (int r = 0; r < kMaxPeers; ++r)
+        if (ctx->peer_map[r]) { cudaIpcCloseMemHandle(ctx->peer_map[r]); ctx->peer_map[r] = nullptr; }
+    if (ctx->peer_own) { cudaFree(ctx->peer_own); ctx->peer_own = nullptr; }
+    ctx->peer_cap = 0;
+    ctx->pl = PeerLinks{};
+}
+
 extern "C" {
 
 const char* ellp_b200_version(void) { return "ellp_b200 0.1 (sm_100a)"; }
@@ -607,6 +794,7 @@ void ellp_b200_destroy(ellp_b200_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     batch_free(ctx);
+    peer_release(ctx);
     if (ctx->nccl_comm && nccl::api.CommDestroy) nccl::api.CommDestroy(ctx->nccl_comm);
     for (auto e : ctx->ev) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -631,6 +819,7 @@ int ellp_b200_set_tuning(ellp_b200_ctx* ctx, const char* key, int value) {
     else if (!std::strcmp(key, "refactor_mode")) ctx->refactor_mode = value;
     else if (!std::strcmp(key, "flush_col_steps")) ctx->flush_col_steps = std::max(1, value);
     else if (!std::strcmp(key, "coop_pivots")) ctx->coop_pivots = value;
+    else if (!std::strcmp(key, "peer_exchange")) ctx->peer_exchange = value;
     else return set_err(ctx, ELLP_E_ARG, std::string("unknown tuning key ") + key);
     return ELLP_OK;
 }
@@ -707,6 +896,7 @@ int ellp_b200_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_poi
     ctx->blk_kmax = blk;
     ctx->blk_fill = 0;
     ctx->sharded = false;
+    ctx->peer_mode = false;
     ctx->binv_valid = false;
     // host buffers are only borrowed for the duration of the call
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -755,6 +945,7 @@ int ellp_b200_generate_dense_ex(ellp_b200_ctx* ctx, int32_t m, int32_t n_struct,
     ctx->blk_kmax = blk;
     ctx->blk_fill = 0;
     ctx->sharded = false;
+    ctx->peer_mode = false;
     ctx->binv_valid = false;
     ctx->dual_obj0 = 0.;  // y = 0 and every bound is Lower(0): dual_obj(y, d) = 0
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -768,7 +959,7 @@ int ellp_b200_download_std_form(ellp_b200_ctx* ctx, double* A, double* c, double
     CUDA_TRY(cudaSetDevice(ctx->device));
     const DevLP& lp = ctx->lp;
     cudaStream_t s = ctx->stream;
-    if (A) CUDA_TRY(cudaMemcpy2DAsync(A, sizeof(double) * lp.m, lp.A, sizeof(double) * lp.ld, sizeof(double) * lp.m, lp.n, cudaMemcpyDeviceToHost, s));
+    if (A) CUDA_TRY(cudaMemcpy2DAsync(A, sizeof(double) * lp.m, lp.A, sizeof(double) * lp.ld, sizeof(double) * lp.m, ctx->peer_mode ? lp.nT : lp.n, cudaMemcpyDeviceToHost, s));
     if (c) CUDA_TRY(cudaMemcpyAsync(c, lp.c, sizeof(double) * lp.n_glob, cudaMemcpyDeviceToHost, s));
     if (b) CUDA_TRY(cudaMemcpyAsync(b, lp.b, sizeof(double) * lp.m, cudaMemcpyDeviceToHost, s));
     if (kind) CUDA_TRY(cudaMemcpyAsync(kind, lp.kind, (size_t)lp.n_glob, cudaMemcpyDeviceToHost, s));
@@ -855,6 +1046,15 @@ int ellp_b200_sharded_generate_dense(ellp_b200_ctx* ctx, int32_t m, int32_t n_st
     if (!ctx || !o || m <= 0 || n_struct <= 0) return ELLP_E_ARG;
     CUDA_TRY(cudaSetDevice(ctx->device));
     DevLP lp{};
+    if (blk_slots(o, true) > 1 && ctx->peer_exchange) {
+        // peer layout: rank g generates the structural columns (= nonbasic positions) [g nN/G, (g+1) nN/G) straight into T
+        if (int rc = peer_prepare(ctx, m, n_struct + m, o, &lp)) return rc;
+        LAUNCH(k_gen_dense_cols, 148 * 16, 256, lp.T, lp.ld, m, (int64_t)n_struct, (int64_t)lp.pos_lo, (int64_t)(lp.pos_lo + lp.nT), seed, 1.0);
+        LAUNCH(k_gen_dense_vectors, 148 * 2, 256, lp, (int64_t)n_struct, seed, 0);
+        ctx->lp = lp;
+        return peer_finish_init(ctx);
+    }
+    ctx->peer_mode = false;
     if (int rc = sharded_prepare(ctx, m, n_struct + m, o, &lp)) return rc;
     LAUNCH(k_gen_dense_cols, 148 * 16, 256, const_cast<double*>(lp.A), lp.ld, m, (int64_t)n_struct, (int64_t)lp.col_lo,
            (int64_t)(lp.col_lo + lp.n), seed, 1.0);
@@ -869,6 +1069,7 @@ int ellp_b200_sharded_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const 
     const int m = sf->m, ng = sf->n;
     if (pt->nB != m || pt->nN != ng - m) return set_err(ctx, ELLP_E_ARG, "sharded upload: B / N lengths do not match the standard form");
     DevLP lp{};
+    ctx->peer_mode = false;
     if (int rc = sharded_prepare(ctx, m, ng, o, &lp)) return rc;
     cudaStream_t s = ctx->stream;
     // sf->A is THIS RANK's column block [col_lo, col_lo + n) (m x n, lda = m); the vectors are global
@@ -893,6 +1094,30 @@ int ellp_b200_sharded_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const 
     CUDA_TRY(cudaStreamSynchronize(s));
     if (mismatch) return set_err(ctx, ELLP_E_ARG, "sharded tableau: the starting basis must be the identity (slack basis)");
     return sharded_finish_init(ctx);
+}
+
+int ellp_b200_sharded_upload_nonbasic(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_point* pt, const ellp_opts* o) {
+    if (!ctx || !sf || !pt || !o) return ELLP_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int m = sf->m, ng = sf->n;
+    if (pt->nB != m || pt->nN != ng - m) return set_err(ctx, ELLP_E_ARG, "sharded upload: B / N lengths do not match the standard form");
+    DevLP lp{};
+    if (int rc = peer_prepare(ctx, m, ng, o, &lp)) return rc;
+    cudaStream_t s = ctx->stream;
+    // sf->A = the columns of the nonbasic positions [pos_lo, pos_lo + nT) in pt->N order (m x nT, lda = m); vectors are global
+    CUDA_TRY(cudaMemcpyAsync(lp.T, sf->A, sizeof(double) * (size_t)m * lp.nT, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync((void*)lp.c, sf->c, sizeof(double) * ng, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync((void*)lp.b, sf->b, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync((void*)lp.lb, sf->lb, sizeof(double) * ng, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync((void*)lp.ub, sf->ub, sizeof(double) * ng, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync((void*)lp.kind, sf->kind, (size_t)ng, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(lp.x, pt->x, sizeof(double) * ng, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(lp.Bv, pt->B, sizeof(int32_t) * m, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(lp.Nv, pt->N, sizeof(int32_t) * lp.nN, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(lp.Ns, pt->N_side, (size_t)lp.nN, cudaMemcpyHostToDevice, s));
+    ctx->lp = lp;
+    CUDA_TRY(cudaStreamSynchronize(s));  // host buffers are only borrowed for the duration of the call
+    return peer_finish_init(ctx);
 }
 
 // ---- K6: batches of independent small LPs ------------------------------------------------------------------------
@@ -1084,6 +1309,8 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
     }
     int check_every = o->check_every > 0 ? o->check_every : (lp.m >= 2048 ? 1 : 8);
     int refactor_every = o->refactor_every > 0 ? o->refactor_every : ((lp.m <= 512 && !ctx->tableau) ? 100 : 0);
+    if (ctx->peer_mode && ctx->nranks > 1)  // stream-ordered barrier: no rank starts polling before every rank got here
+        NCCL_TRY(nccl::api.AllReduce(lp.part, lp.part + 4, 1, nccl::kFloat64, nccl::kSum, ctx->nccl_comm, ctx->stream));
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
     int rc_loop = ELLP_OK;
     while (h.status == kRunning) {
@@ -1091,7 +1318,19 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
         // never enqueue more iterations than the pivot budget still allows (they would be no-op launches)
         if (o->max_iter - h.pivots < (uint64_t)batch) batch = (int)std::max<uint64_t>(1, o->max_iter - h.pivots);
         if (refactor_every > 0) batch = (int)std::min<uint64_t>(batch, std::max<uint64_t>(1, refactor_every - ctx->pivots_since_refactor));
-        if (blk > 0 && !ctx->sharded && ctx->coop_pivots && lp.condensed) {
+        if (ctx->peer_mode) {
+            // peer engine: whole blocks of pivots per cooperative launch; every rank issues the same launches
+            if (blk <= 1) { rc_loop = set_err(ctx, ELLP_E_ARG, "the peer-memory engine needs ellp_opts::block_k > 1"); break; }
+            int left = std::max(batch, blk);
+            if (o->max_iter - h.pivots < (uint64_t)left) left = (int)std::max<uint64_t>(1, o->max_iter - h.pivots);
+            while (left > 0 && !rc_loop) {
+                const int npiv = std::min(left, blk - ctx->blk_fill);
+                rc_loop = launch_coop_pivots_peer(ctx, o, npiv);
+                left -= npiv;
+                if (!rc_loop && ctx->blk_fill >= blk) launch_flush(ctx, profile, &ev_used);
+            }
+            batch = 0;
+        } else if (blk > 0 && !ctx->sharded && ctx->coop_pivots && lp.condensed) {
             // cooperative path: whole blocks of pivots per launch, a flush after every full block
             int left = std::max(batch, blk);
             if (o->max_iter - h.pivots < (uint64_t)left) left = (int)std::max<uint64_t>(1, o->max_iter - h.pivots);
@@ -1154,6 +1393,14 @@ int ellp_b200_download(ellp_b200_ctx* ctx, ellp_point* pt) {
     CUDA_TRY(cudaSetDevice(ctx->device));
     DevLP& lp = ctx->lp;
     cudaStream_t s = ctx->stream;
+    if (ctx->peer_mode) {  // x, B and the N list (position order) are replicated
+        CUDA_TRY(cudaMemcpyAsync(pt->x, lp.x, sizeof(double) * lp.n_glob, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(pt->B, lp.Bv, sizeof(int32_t) * lp.m, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(pt->N, lp.Nv, sizeof(int32_t) * lp.nN, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(pt->N_side, lp.Ns, (size_t)lp.nN, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        return ELLP_OK;
+    }
     if (ctx->sharded) {  // x and B are replicated; N is rebuilt from the gathered per-column status (ascending variable index)
         CUDA_TRY(cudaMemcpyAsync(pt->x, lp.x, sizeof(double) * lp.n_glob, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaMemcpyAsync(pt->B, lp.Bv, sizeof(int32_t) * lp.m, cudaMemcpyDeviceToHost, s));

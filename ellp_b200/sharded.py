@@ -87,9 +87,11 @@ def bench_main(args, wl, name, METRIC, UNIT, SEED, ClockSampler, measured_peak, 
     init_comm(ctx, rank, world)
     m, ns, P = wl["m"], wl["ns"], (args.pivots or wl["pivots"])
     n = m + ns
-    lo, hi = shard_range(n, world, rank)
+    bk = wl.get("block_k", 0) if getattr(args, "block_k", -1) < 0 else args.block_k
+    peer = bk > 1  # peer-memory engine: condensed tableau split by nonbasic position, exchange fused into the pivot kernel
+    lo, hi = shard_range(ns, world, rank) if peer else shard_range(n, world, rank)
     # order-free tie rule: the arg-select is a reduction over ranks
-    o = N.default_opts(P, engine=N.ENGINE_TABLEAU, tie_rule=N.TIES_CANONICAL, check_every=min(P, 16), profile=True)
+    o = N.default_opts(P, engine=N.ENGINE_TABLEAU, tie_rule=N.TIES_CANONICAL, check_every=min(P, max(16, bk)), profile=True, block_k=bk)
     ctx.check(N.lib.ellp_b200_sharded_generate_dense(ctx.h, m, ns, SEED, C.byref(o)))
 
     def step():
@@ -136,12 +138,13 @@ def bench_main(args, wl, name, METRIC, UNIT, SEED, ClockSampler, measured_peak, 
         x0 = np.zeros(n); x0[ns:] = b_h
         B0 = np.arange(ns, n, dtype=np.int32); N0 = np.arange(ns, dtype=np.int32); Ns0 = np.zeros(ns, dtype=np.uint8)
         sf = N.StdForm(m, n, N.ptr(A_h), N.ptr(c_h), N.ptr(b_h), N.ptr(kind_h), N.ptr(lb_h), N.ptr(ub_h))
-        oe = N.default_opts(P, engine=N.ENGINE_TABLEAU, tie_rule=N.TIES_CANONICAL, check_every=min(P, 16))
+        oe = N.default_opts(P, engine=N.ENGINE_TABLEAU, tie_rule=N.TIES_CANONICAL, check_every=min(P, max(16, bk)), block_k=bk)
+        upload = N.lib.ellp_b200_sharded_upload_nonbasic if peer else N.lib.ellp_b200_sharded_upload
 
         def e2e_step():
             x, B, Nv, Ns = x0.copy(), B0.copy(), N0.copy(), Ns0.copy()
             pt = N.Point(N.ptr(x), N.ptr(B), N.ptr(Nv), N.ptr(Ns), None, None, m, ns)
-            ctx.check(N.lib.ellp_b200_sharded_upload(ctx.h, C.byref(sf), C.byref(pt), C.byref(oe)))
+            ctx.check(upload(ctx.h, C.byref(sf), C.byref(pt), C.byref(oe)))
             res = N.Result()
             ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(oe), C.byref(res)))
             ctx.check(N.lib.ellp_b200_download(ctx.h, C.byref(pt)))
@@ -167,17 +170,26 @@ def bench_main(args, wl, name, METRIC, UNIT, SEED, ClockSampler, measured_peak, 
     if rank == 0:
         peak, peak_src = measured_peak()
         nloc = hi - lo
-        alg_bytes = 16.0 * m * nloc + 8.0 * (m + nloc)
+        if peer:
+            alg_bytes = 16.0 * m * nloc + 8.0 * bk * (m + nloc)
+            kernel = "k_blk_flush (rank-%d row reduction of the local %d x %d slice of the condensed tableau, fp64 DMMA)" % (bk, m, nloc)
+        else:
+            alg_bytes = 16.0 * m * nloc + 8.0 * (m + nloc)
+            kernel = "k_rank1<true> on the local column shard"
         achieved = alg_bytes / (k3_ms * 1e-3) / 1e9 if k3_ms > 0 else None
-        roofline = {"bound": "hbm", "kernel": "k_rank1<true> on the local column shard", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src, "ms_per_launch": k3_ms,
                     "algorithmic_bytes_per_launch": alg_bytes, "note": "per GPU; max over ranks of the mean launch time"}
+        engine = ("condensed tableau split by nonbasic position, blocked (block_k=%d), per-pivot exchange fused into the cooperative "
+                  "pivot kernel over NVLink peer memory (k_blk_pivots_peer)" % bk) if peer else "tableau, column-sharded, rank-1 update per pivot"
+        exchange = ("per pivot: %d x 64 B pricing words + m x 16 B column words stored into every peer (LL protocol, no NCCL call)" % world) if peer \
+            else "2 x ncclAllGather (8 B, 24 B per rank) + 1 x ncclAllReduce (m doubles) per pivot"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": name, "m": m, "n": n, "pivots_per_step": P, "engine": "tableau, column-sharded",
+                "config": {"workload": name, "m": m, "n": n, "pivots_per_step": P, "engine": engine, "block_k": bk,
                            "columns_per_gpu": nloc, "tie_rule": "order-free (canonical)",
-                           "exchange": "2 x ncclAllGather (8 B, 24 B per rank) + 1 x ncclAllReduce (m doubles) per pivot",
+                           "exchange": exchange,
                            "l2": f"local shard {8.0 * m * nloc / 1e9:.2f} GB >> 126 MB L2"},
                 "device_ms_per_step": dev_ms_max / args.steps, "gpu_launches": int(launches) * world, "clocks": clk,
                 "roofline": roofline, "cpu_baseline": None, "e2e": e2e}

@@ -155,7 +155,7 @@ int ellp_b200_generate_dense(ellp_b200_ctx*, int32_t m, int32_t n_struct, uint64
 int ellp_b200_generate_dense_ex(ellp_b200_ctx*, int32_t m, int32_t n_struct, uint64_t seed, int32_t variant, const ellp_opts* o);
 /* copies the resident standard form to host buffers (any pointer may be NULL) */
 int ellp_b200_download_std_form(ellp_b200_ctx*, double* A, double* c, double* b, uint8_t* kind, double* lb, double* ub);
-/* tuning knobs: "rank1_cols_per_cta", "rank1_stream_min_mb", "refactor_mode", "flush_col_steps" */
+/* tuning knobs: "rank1_cols_per_cta", "rank1_stream_min_mb", "refactor_mode", "flush_col_steps", "coop_pivots", "peer_exchange" */
 int ellp_b200_set_tuning(ellp_b200_ctx*, const char* key, int value);
 
 /* ---- K6: batches of independent small LPs (BASELINE.json configs[3]) -------------------------------------------
@@ -203,6 +203,16 @@ int ellp_b200_sharded_generate_dense(ellp_b200_ctx*, int32_t m, int32_t n_struct
  * pt is the global starting point.  Afterwards ellp_b200_run / ellp_b200_download work as in the single-GPU case
  * (download rebuilds N in ascending variable order). */
 int ellp_b200_sharded_upload(ellp_b200_ctx*, const ellp_std_form* sf, const ellp_point* pt, const ellp_opts* o);
+/* Peer-memory engine (o->block_k > 1; ellp_b200/csrc/peer.cuh): the CONDENSED tableau (only the n - m nonbasic columns are
+ * stored) is split by nonbasic POSITION, rank g holding positions [g (n-m)/G, (g+1) (n-m)/G) of pt->N; the arg-reduce and
+ * the pivot-column broadcast are stores into the other ranks' memory (cudaIpc-mapped, NVLink) issued by the same
+ * persistent kernel that pivots -- no NCCL call per pivot.  ellp_b200_sharded_generate_dense selects this engine when
+ * o->block_k > 1 (tuning key "peer_exchange" = 0 keeps the NCCL path).  For host data:
+ * sf describes the GLOBAL standard form except that sf->A holds THIS RANK's nonbasic columns in pt->N order
+ * (m x (n-m)/G, lda = m); the starting basis must be the identity (slack basis; the basis columns are never passed).
+ * Requires (n - m) % G == 0, m % 4 == 0, G <= 8.  ellp_b200_run / ellp_b200_download work as in the single-GPU case and
+ * return N in position order. */
+int ellp_b200_sharded_upload_nonbasic(ellp_b200_ctx*, const ellp_std_form* sf, const ellp_point* pt, const ellp_opts* o);
 
 /* ---- two-phase drivers: {Primal,Dual}SimplexSolver::solve ------------------------------------ */
 /* A Problem as built by Problem::add_var / add_constraint (src/problem.rs:19-106); constraints in

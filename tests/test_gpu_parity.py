@@ -327,6 +327,17 @@ def test_sharded_tableau_two_gpus_matches_single_gpu_and_oracle(env):
     assert "SHARDED_CHECK_OK" in out.stdout
 
 
+def test_sharded_engines_one_rank_match_oracle(env):
+    """Both sharded engines (NCCL path and the peer-memory engine of peer.cuh) with a single rank: the whole protocol --
+    tickets, mailbox words, column words, parity double-buffering -- runs against the rank's own exchange buffer."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=1", "--master-addr", "127.0.0.1",
+                          "--master-port", "29633", os.path.join(root, "tools", "sharded_check.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "SHARDED_CHECK_OK" in out.stdout
+
+
 def test_generated_dual_lp_matches_numpy_twin_and_oracle(env):
     import bench_lp
     N, O, ctx = env["N"], env["O"], env["ctx"]

@@ -1,5 +1,9 @@
-"""Run under torchrun with N ranks (one GPU each): the column-sharded tableau must pivot exactly like the oracle
-(order-free tie rule) and finish with the same point.  Prints SHARDED_CHECK_OK on rank 0."""
+"""Run under torchrun with N ranks (one GPU each; N = 1 works too): the column-sharded tableau engines must pivot exactly
+like the oracle (order-free tie rule) and finish with the same point.  Checks both sharded engines:
+  block_k = 0   the NCCL path (full tableau split by column, 3 collectives per pivot);
+  block_k > 1   the peer-memory engine (condensed tableau split by nonbasic position, exchange fused into the pivot kernel),
+and, on a size the oracle cannot reach (one LU per pivot), the peer engine against the single-GPU blocked engine.
+Prints SHARDED_CHECK_OK on rank 0."""
 import ctypes as C
 import os
 import sys
@@ -22,40 +26,76 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ctx = N.Context(local)
 sharded.init_comm(ctx, rank, world)
 ok = True
-for (m, ns, seed, K) in [(64, 192, 3, 10**6), (256, 768, 4, 300)]:
-    n = m + ns
-    o = N.default_opts(K, engine=N.ENGINE_TABLEAU, tie_rule=N.TIES_CANONICAL, check_every=8)
-    tr = np.zeros(20000, dtype=N.TRACE_DTYPE); o.trace = N.ptr(tr); o.trace_cap = len(tr)
-    # (1) generated in HBM, sharded
-    ctx.check(N.lib.ellp_b200_sharded_generate_dense(ctx.h, m, ns, seed, C.byref(o)))
-    res = N.Result()
-    ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(o), C.byref(res)))
-    lp = bench_lp.dense_lp(m, ns, seed)
-    x, B, Nv, Ns = lp["x"].copy(), lp["B"].copy(), lp["N"].copy(), lp["N_side"].copy()
-    pt = N.Point(N.ptr(x), N.ptr(B), N.ptr(Nv), N.ptr(Ns), None, None, m, ns)
-    ctx.check(N.lib.ellp_b200_download(ctx.h, C.byref(pt)))
-    xo, Bo, No, Nso = lp["x"].copy(), lp["B"].copy(), lp["N"].copy(), lp["N_side"].copy()
-    ref = O.solve_with_initial(O.PRIMAL, m, n, lp["A"], lp["c"], lp["b"], lp["kind"], lp["lb"], lp["ub"], xo, Bo, No, Nso,
-                               max_iter=K, mode=O.MODE_CANONICAL, trace_cap=20000)
-    k = len(ref.trace)
-    good = (res.status == ref.status and res.iters == k and (tr["entering"][:k] == ref.trace["entering"]).all()
-            and (tr["leaving"][:k] == ref.trace["leaving"]).all() and np.array_equal(B, Bo)
-            and np.allclose(x, xo, rtol=1e-9, atol=1e-9) and set(Nv.tolist()) == set(No.tolist()))
-    # (2) the same LP uploaded from host buffers, each rank passing ITS column block
-    lo, hi = sharded.shard_range(n, world, rank)
-    Aloc = np.asfortranarray(lp["A"][:, lo:hi])
-    sf = N.StdForm(m, n, N.ptr(Aloc), N.ptr(lp["c"]), N.ptr(lp["b"]), N.ptr(lp["kind"]), N.ptr(lp["lb"]), N.ptr(lp["ub"]))
-    x2, B2, N2, Ns2 = lp["x"].copy(), lp["B"].copy(), lp["N"].copy(), lp["N_side"].copy()
-    pt2 = N.Point(N.ptr(x2), N.ptr(B2), N.ptr(N2), N.ptr(Ns2), None, None, m, ns)
-    tr2 = np.zeros(20000, dtype=N.TRACE_DTYPE); o.trace = N.ptr(tr2)
-    ctx.check(N.lib.ellp_b200_sharded_upload(ctx.h, C.byref(sf), C.byref(pt2), C.byref(o)))
-    res2 = N.Result()
-    ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(o), C.byref(res2)))
-    ctx.check(N.lib.ellp_b200_download(ctx.h, C.byref(pt2)))
-    good2 = (res2.iters == k and (tr2["entering"][:k] == ref.trace["entering"]).all() and np.array_equal(B2, Bo)
-             and np.allclose(x2, xo, rtol=1e-9, atol=1e-9))
-    print(f"rank {rank}: m={m} n={n} pivots={res.iters} oracle={k} status={res.status}/{ref.status} generated_ok={good} uploaded_ok={good2}", flush=True)
-    ok = ok and good and good2
+for bk in (0, 8, 5):
+    for (m, ns, seed, K) in [(64, 192, 3, 10**6), (256, 768, 4, 300)]:
+        n = m + ns
+        o = N.default_opts(K, engine=N.ENGINE_TABLEAU, tie_rule=N.TIES_CANONICAL, check_every=8, block_k=bk)
+        tr = np.zeros(20000, dtype=N.TRACE_DTYPE); o.trace = N.ptr(tr); o.trace_cap = len(tr)
+        # (1) generated in HBM, sharded
+        ctx.check(N.lib.ellp_b200_sharded_generate_dense(ctx.h, m, ns, seed, C.byref(o)))
+        res = N.Result()
+        ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(o), C.byref(res)))
+        lp = bench_lp.dense_lp(m, ns, seed)
+        x, B, Nv, Ns = lp["x"].copy(), lp["B"].copy(), lp["N"].copy(), lp["N_side"].copy()
+        pt = N.Point(N.ptr(x), N.ptr(B), N.ptr(Nv), N.ptr(Ns), None, None, m, ns)
+        ctx.check(N.lib.ellp_b200_download(ctx.h, C.byref(pt)))
+        xo, Bo, No, Nso = lp["x"].copy(), lp["B"].copy(), lp["N"].copy(), lp["N_side"].copy()
+        ref = O.solve_with_initial(O.PRIMAL, m, n, lp["A"], lp["c"], lp["b"], lp["kind"], lp["lb"], lp["ub"], xo, Bo, No, Nso,
+                                   max_iter=K, mode=O.MODE_CANONICAL, trace_cap=20000)
+        k = len(ref.trace)
+        good = (res.status == ref.status and res.iters == k and (tr["entering"][:k] == ref.trace["entering"]).all()
+                and (tr["leaving"][:k] == ref.trace["leaving"]).all() and np.array_equal(B, Bo)
+                and np.allclose(x, xo, rtol=1e-9, atol=1e-9) and set(Nv.tolist()) == set(No.tolist()))
+        if bk > 1:  # the peer engine keeps the N list in position order like the reference (and the oracle)
+            good = good and np.array_equal(Nv, No) and np.array_equal(Ns, Nso)
+        # (2) the same LP uploaded from host buffers, each rank passing ITS block
+        x2, B2, N2, Ns2 = lp["x"].copy(), lp["B"].copy(), lp["N"].copy(), lp["N_side"].copy()
+        pt2 = N.Point(N.ptr(x2), N.ptr(B2), N.ptr(N2), N.ptr(Ns2), None, None, m, ns)
+        tr2 = np.zeros(20000, dtype=N.TRACE_DTYPE); o.trace = N.ptr(tr2)
+        if bk > 1:  # nonbasic columns of this rank's positions, in N order
+            plo, phi = sharded.shard_range(ns, world, rank)
+            Aloc = np.asfortranarray(lp["A"][:, lp["N"][plo:phi]])
+            sf = N.StdForm(m, n, N.ptr(Aloc), N.ptr(lp["c"]), N.ptr(lp["b"]), N.ptr(lp["kind"]), N.ptr(lp["lb"]), N.ptr(lp["ub"]))
+            ctx.check(N.lib.ellp_b200_sharded_upload_nonbasic(ctx.h, C.byref(sf), C.byref(pt2), C.byref(o)))
+        else:
+            lo, hi = sharded.shard_range(n, world, rank)
+            Aloc = np.asfortranarray(lp["A"][:, lo:hi])
+            sf = N.StdForm(m, n, N.ptr(Aloc), N.ptr(lp["c"]), N.ptr(lp["b"]), N.ptr(lp["kind"]), N.ptr(lp["lb"]), N.ptr(lp["ub"]))
+            ctx.check(N.lib.ellp_b200_sharded_upload(ctx.h, C.byref(sf), C.byref(pt2), C.byref(o)))
+        res2 = N.Result()
+        ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(o), C.byref(res2)))
+        ctx.check(N.lib.ellp_b200_download(ctx.h, C.byref(pt2)))
+        good2 = (res2.iters == k and (tr2["entering"][:k] == ref.trace["entering"]).all() and np.array_equal(B2, Bo)
+                 and np.allclose(x2, xo, rtol=1e-9, atol=1e-9))
+        print(f"rank {rank}: block_k={bk} m={m} n={n} pivots={res.iters} oracle={k} status={res.status}/{ref.status} "
+              f"generated_ok={good} uploaded_ok={good2}", flush=True)
+        ok = ok and good and good2
+
+# (3) a size with many CTAs per rank (grid barriers, last-block tickets, many column words on the wire): the peer engine
+# against the single-GPU blocked engine (itself checked against the oracle at small sizes), same LP, same tie rule.
+m, ns, seed, K, bk = 2048, 4096, 5, 160, 32
+o = N.default_opts(K, engine=N.ENGINE_TABLEAU, tie_rule=N.TIES_CANONICAL, check_every=32, block_k=bk)
+tr_s = np.zeros(K, dtype=N.TRACE_DTYPE); o.trace = N.ptr(tr_s); o.trace_cap = K
+single = N.Context(local)
+single.check(N.lib.ellp_b200_generate_dense(single.h, m, ns, seed, C.byref(o)))
+rs = N.Result()
+single.check(N.lib.ellp_b200_run(single.h, C.byref(o), C.byref(rs)))
+xs = np.zeros(m + ns); Bs = np.zeros(m, dtype=np.int32); Nvs = np.zeros(ns, dtype=np.int32); Nss = np.zeros(ns, dtype=np.uint8)
+single.check(N.lib.ellp_b200_download(single.h, C.byref(N.Point(N.ptr(xs), N.ptr(Bs), N.ptr(Nvs), N.ptr(Nss), None, None, m, ns))))
+single.close()
+tr_p = np.zeros(K, dtype=N.TRACE_DTYPE); o.trace = N.ptr(tr_p)
+ctx.check(N.lib.ellp_b200_sharded_generate_dense(ctx.h, m, ns, seed, C.byref(o)))
+rp = N.Result()
+ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(o), C.byref(rp)))
+xp = np.zeros(m + ns); Bp = np.zeros(m, dtype=np.int32); Nvp = np.zeros(ns, dtype=np.int32); Nsp = np.zeros(ns, dtype=np.uint8)
+ctx.check(N.lib.ellp_b200_download(ctx.h, C.byref(N.Point(N.ptr(xp), N.ptr(Bp), N.ptr(Nvp), N.ptr(Nsp), None, None, m, ns))))
+good3 = (rp.status == rs.status and rp.iters == rs.iters == K and (tr_p["entering"] == tr_s["entering"]).all()
+         and (tr_p["leaving"] == tr_s["leaving"]).all() and np.array_equal(Bp, Bs) and np.array_equal(Nvp, Nvs)
+         and np.array_equal(Nsp, Nss) and xp.tobytes() == xs.tobytes() and rp.obj == rs.obj)
+print(f"rank {rank}: peer vs single-GPU blocked engine m={m} n={m + ns} pivots={rp.iters}/{rs.iters} identical={good3} "
+      f"peer_ms={rp.ms_device:.2f} single_ms={rs.ms_device:.2f}", flush=True)
+ok = ok and good3
+
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0 and int(flag.item()) == 1:
