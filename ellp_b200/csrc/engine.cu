@@ -96,7 +96,7 @@ struct ellp_b200_ctx {
     int blk_kmax = 0;             // slots allocated for the blocked (deferred rank-k) tableau engine; 0 = rank-1 engine only
     int blk_fill = 0;             // slots used since the last flush
     int flush_col_steps = 8;      // column steps (of 64 columns) per CTA of k_blk_flush
-    int coop_pivots = 1;          // blocked engine: 1 = one cooperative launch per block of pivots (k_blk_pivots), 0 = five kernels per pivot
+    int coop_pivots = 2;          // blocked engine: 2 = k_blk_pivots_fused (2 barriers per pivot), 1 = k_blk_pivots (4 barriers), 0 = five kernels per pivot
     int coop_grid = 0;            // co-resident CTAs of k_blk_pivots (0 = not yet queried)
     // peer-memory sharded engine (peer.cuh): condensed tableau split by nonbasic position, exchange fused into the pivot kernel
     bool peer_mode = false;       // the resident LP uses the peer layout
@@ -106,7 +106,13 @@ struct ellp_b200_ctx {
     void* peer_map[kMaxPeers] = {nullptr};  // cudaIpcOpenMemHandle mappings of the other ranks' buffers
     int64_t peer_cap = 0;         // rows per parity slot of the column buffers
     uint32_t xseq = 0;            // pivots exchanged since the communicator was created (wire sequence number)
-    int coop_grid_peer = 0;
+    int coop_grid_fused = 0;
+    long long* tlog = nullptr;    // phase-timing log of k_blk_pivots_fused (tuning key "phase_timing")
+    int tlog_cap = 0;
+    uint32_t tlog_seq0 = 0;
+    int coop_threads = 256;       // tuning: threads per block of k_blk_pivots_fused (64..512)
+    int coop_threads_cached = 0;
+    int coop_ctas_per_sm = 1;     // tuning: resident blocks per SM the fused kernel may use
     int refactor_mode = 0;        // 0 auto (blocked LU + DMMA for m >= 128, Gauss-Jordan below), 1 Gauss-Jordan, 2 blocked LU  // evict-first policy when the updated matrix is larger than this
 };
 
@@ -570,27 +576,41 @@ int peer_finish_init(ellp_b200_ctx* ctx) {
     return ELLP_OK;
 }
 
-// `npiv` pivots of the peer engine (slots blk_fill .. blk_fill + npiv - 1) in one cooperative launch; every rank
-// issues the same sequence of launches
-int launch_coop_pivots_peer(ellp_b200_ctx* ctx, const ellp_opts* o, int npiv) {
+// `npiv` pivots (slots blk_fill .. blk_fill + npiv - 1) in one cooperative launch of the peer-memory pivot kernel; every
+// rank issues the same sequence of launches.  self_only: single-GPU blocked engine (the exchange buffers are this GPU's own).
+int launch_coop_pivots_peer(ellp_b200_ctx* ctx, const ellp_opts* o, int npiv, bool self_only) {
     DevLP& lp = ctx->lp;
-    if (ctx->coop_grid_peer == 0) {
-        CUDA_TRY(cudaFuncSetAttribute(k_blk_pivots_peer, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmemBytes));
+    const void* fn = (const void*)k_blk_pivots_fused;
+    int& grid_cap = ctx->coop_grid_fused;
+    // the fused kernel runs with small blocks: its phases are latency-bound and every block-wide reduction / barrier costs
+    // issue slots per resident warp (measured: 256 threads per block beat 1024)
+    const int threads = std::max(64, std::min(kFusedMaxThreads, ctx->coop_threads & ~31));
+    if (grid_cap == 0 || ctx->coop_threads_cached != threads) {
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmemBytes));
         int sms = 0, per_sm = 0, coop = 0;
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
         CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_blk_pivots_peer, kScanThreads, kScanSmemBytes));
-        ctx->coop_grid_peer = (coop && per_sm > 0) ? std::min(1024, sms * per_sm) : -1;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, kScanSmemBytes));
+        grid_cap = (coop && per_sm > 0) ? std::min(1024, sms * std::min(per_sm, std::max(1, ctx->coop_ctas_per_sm))) : -1;
+        ctx->coop_threads_cached = threads;
     }
-    if (ctx->coop_grid_peer < 0) return set_err(ctx, ELLP_E_CUDA, "cooperative launch unavailable");
+    if (grid_cap < 0) return set_err(ctx, ELLP_E_CUDA, "cooperative launch unavailable");
     const int64_t work = std::max<int64_t>(std::max<int64_t>(lp.ld, lp.ldv), lp.nT);
-    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->coop_grid_peer, (work + kScanThreads - 1) / kScanThreads));
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid_cap, (work + threads - 1) / threads));
     int tie = o->tie_rule, slot0 = ctx->blk_fill;
     uint32_t seq0 = ctx->xseq;
     PivotState* st = ctx->d_st;
     PeerLinks pl = ctx->pl;
+    pl.tlog = ctx->tlog ? ctx->tlog - (int64_t)ctx->tlog_seq0 * kTlogStamps : nullptr;  // the kernel indexes the log by (seq - 1)
+    pl.tlog_cap = ctx->tlog ? (int32_t)(ctx->tlog_seq0 + (uint32_t)ctx->tlog_cap) : 0;
+    if (self_only) {
+        pl.mbox[0] = ctx->pl.mbox[ctx->pl.rank];
+        pl.col[0] = ctx->pl.col[ctx->pl.rank];
+        pl.rank = 0;
+        pl.nranks = 1;
+    }
     void* args[] = {(void*)&lp, (void*)&pl, (void*)&tie, (void*)&slot0, (void*)&npiv, (void*)&seq0, (void*)&st};
-    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_blk_pivots_peer, dim3(grid), dim3(kScanThreads), args, (size_t)kScanSmemBytes, ctx->stream));
+    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, (size_t)kScanSmemBytes, ctx->stream));
     ctx->launches++;
     ctx->blk_fill += npiv;
     ctx->xseq += (uint32_t)npiv;
@@ -802,6 +822,7 @@ void ellp_b200_destroy(ellp_b200_ctx* ctx) {
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->d_st) cudaFree(ctx->d_st);
     if (ctx->d_flag) cudaFree(ctx->d_flag);
+    if (ctx->tlog) cudaFree(ctx->tlog);
     if (ctx->h_st) cudaFreeHost(ctx->h_st);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -820,7 +841,27 @@ int ellp_b200_set_tuning(ellp_b200_ctx* ctx, const char* key, int value) {
     else if (!std::strcmp(key, "flush_col_steps")) ctx->flush_col_steps = std::max(1, value);
     else if (!std::strcmp(key, "coop_pivots")) ctx->coop_pivots = value;
     else if (!std::strcmp(key, "peer_exchange")) ctx->peer_exchange = value;
+    else if (!std::strcmp(key, "coop_threads")) ctx->coop_threads = value;
+    else if (!std::strcmp(key, "coop_ctas_per_sm")) { ctx->coop_ctas_per_sm = value; ctx->coop_threads_cached = 0; }
+    else if (!std::strcmp(key, "phase_timing")) {  // value = pivots to log (0 = off); read back with ellp_b200_phase_log
+        if (ctx->tlog) { cudaFree(ctx->tlog); ctx->tlog = nullptr; }
+        ctx->tlog_cap = 0;
+        if (value > 0) {
+            CUDA_TRY(cudaMalloc(&ctx->tlog, sizeof(long long) * kTlogStamps * (size_t)value));
+            CUDA_TRY(cudaMemset(ctx->tlog, 0, sizeof(long long) * kTlogStamps * (size_t)value));
+            ctx->tlog_cap = value;
+            ctx->tlog_seq0 = ctx->xseq;
+        }
+    }
     else return set_err(ctx, ELLP_E_ARG, std::string("unknown tuning key ") + key);
+    return ELLP_OK;
+}
+
+int ellp_b200_phase_log(ellp_b200_ctx* ctx, int64_t* out, int32_t pivots) {
+    if (!ctx || !out || !ctx->tlog || pivots > ctx->tlog_cap) return ELLP_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemcpy(out, ctx->tlog, sizeof(long long) * kTlogStamps * (size_t)pivots, cudaMemcpyDeviceToHost));
     return ELLP_OK;
 }
 
@@ -1325,7 +1366,7 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
             if (o->max_iter - h.pivots < (uint64_t)left) left = (int)std::max<uint64_t>(1, o->max_iter - h.pivots);
             while (left > 0 && !rc_loop) {
                 const int npiv = std::min(left, blk - ctx->blk_fill);
-                rc_loop = launch_coop_pivots_peer(ctx, o, npiv);
+                rc_loop = launch_coop_pivots_peer(ctx, o, npiv, false);
                 left -= npiv;
                 if (!rc_loop && ctx->blk_fill >= blk) launch_flush(ctx, profile, &ev_used);
             }
@@ -1334,9 +1375,13 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
             // cooperative path: whole blocks of pivots per launch, a flush after every full block
             int left = std::max(batch, blk);
             if (o->max_iter - h.pivots < (uint64_t)left) left = (int)std::max<uint64_t>(1, o->max_iter - h.pivots);
+            if (ctx->coop_pivots == 2 && ctx->peer_cap < lp.ld) {  // exchange buffer of the fused kernel (this GPU's own memory here)
+                if (ctx->nranks == 1) rc_loop = peer_setup(ctx, lp.ld);
+                else rc_loop = set_err(ctx, ELLP_E_ARG, "exchange buffer too small for a single-GPU LP on a multi-rank context");
+            }
             while (left > 0 && !rc_loop) {
                 const int npiv = std::min(left, blk - ctx->blk_fill);
-                rc_loop = launch_coop_pivots(ctx, o, npiv);
+                rc_loop = ctx->coop_pivots == 2 ? launch_coop_pivots_peer(ctx, o, npiv, true) : launch_coop_pivots(ctx, o, npiv);
                 left -= npiv;
                 if (!rc_loop && ctx->blk_fill >= blk) launch_flush(ctx, profile, &ev_used);
             }

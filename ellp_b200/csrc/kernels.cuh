@@ -169,14 +169,15 @@ constexpr int kScanThreads = 1024;
 __device__ __forceinline__ void scan_load_tile(const double* __restrict__ val, const int32_t* __restrict__ tag, int n, int tile,
                                                double* sval, int* stag, int first_thread) {
     const int base = tile * kScanTile;
-    for (int t = threadIdx.x - first_thread; t < kScanTile; t += kScanThreads - first_thread) {
+    for (int t = threadIdx.x - first_thread; t < kScanTile; t += (int)blockDim.x - first_thread) {
         const int i = base + t;
         sval[t] = (i < n) ? __ldcg(val + i) : -1.0;
         stag[t] = (i < n) ? __ldcg(tag + i) : 0;
     }
 }
 
-// Body shared by k_select_primal (one CTA of kScanThreads threads) and block 0 of the cooperative pivot kernel
+// Body shared by k_select_primal (one CTA of kScanThreads threads) and block 0 of the cooperative pivot kernels (any
+// block size that is a multiple of 32 and at least 64)
 // (blocked.cuh); needs kScanSmemBytes of dynamic shared memory at scan_smem.
 __device__ __forceinline__ void select_primal_body(const double* key, const double* rN, const int32_t* Nv, const uint8_t* Ns,
                                                    int nN, int tie_rule, PivotState* st, unsigned char* scan_smem) {
@@ -196,17 +197,17 @@ __device__ __forceinline__ void select_primal_body(const double* key, const doub
         // that element wins the fold whatever the order: it beats every other key strictly, and no other key can displace
         // it or tie with it.  Ties / near-ties fall through to the sequential fold below.
         double kmax = -1.0;
-        for (int j = tid; j < nN; j += kScanThreads) kmax = fmax(kmax, __ldcg(key + j));
+        for (int j = tid; j < nN; j += (int)blockDim.x) kmax = fmax(kmax, __ldcg(key + j));
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) kmax = fmax(kmax, __shfl_xor_sync(full, kmax, off));
         if (lane == 0) s_red[warp] = kmax;
         __syncthreads();
         kmax = s_red[0];
-        for (int w = 1; w < 32; ++w) kmax = fmax(kmax, s_red[w]);
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) kmax = fmax(kmax, s_red[w]);
         __syncthreads();
         int nF = 0, nBand = 0, idxF = 0x7fffffff;
         if (kmax != -1.0) {
-            for (int j = tid; j < nN; j += kScanThreads) {
+            for (int j = tid; j < nN; j += (int)blockDim.x) {
                 const double k = __ldcg(key + j);
                 if (k == -1.0) continue;
                 if (kmax - k < kEps) { ++nF; idxF = min(idxF, j); }
@@ -222,7 +223,7 @@ __device__ __forceinline__ void select_primal_body(const double* key, const doub
         if (lane == 0) { s_redi[warp] = nF; s_redp[warp] = nBand; s_red[warp] = (double)idxF; }
         __syncthreads();
         nF = 0; nBand = 0; idxF = 0x7fffffff;
-        for (int w = 0; w < 32; ++w) { nF += s_redi[w]; nBand += s_redp[w]; idxF = min(idxF, (int)s_red[w]); }
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { nF += s_redi[w]; nBand += s_redp[w]; idxF = min(idxF, (int)s_red[w]); }
         __syncthreads();
         if (kmax == -1.0) { fast = true; bp = -1; }
         else if (nF == 1 && nBand == 0) { fast = true; bp = idxF; bv = Nv[idxF]; }
@@ -265,16 +266,16 @@ __device__ __forceinline__ void select_primal_body(const double* key, const doub
     } else if (tie_rule != ELLP_TIES_REFERENCE) {
         // order-free rule: max key, then the largest variable index within EPS of it
         double kmax = -1.0;
-        for (int j = tid; j < nN; j += kScanThreads) kmax = fmax(kmax, __ldcg(key + j));
+        for (int j = tid; j < nN; j += (int)blockDim.x) kmax = fmax(kmax, __ldcg(key + j));
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) kmax = fmax(kmax, __shfl_xor_sync(full, kmax, off));
         if (lane == 0) s_red[warp] = kmax;
         __syncthreads();
         kmax = s_red[0];
-        for (int w = 1; w < 32; ++w) kmax = fmax(kmax, s_red[w]);
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) kmax = fmax(kmax, s_red[w]);
         int bestv = -1, bestp = -1;
         if (kmax != -1.0) {
-            for (int j = tid; j < nN; j += kScanThreads) {
+            for (int j = tid; j < nN; j += (int)blockDim.x) {
                 const double k = __ldcg(key + j);
                 if (k != -1.0 && (kmax - k < kEps)) {
                     const int v = __ldcg(Nv + j);
@@ -292,7 +293,7 @@ __device__ __forceinline__ void select_primal_body(const double* key, const doub
         if (tid == 0) {
             bv = -1;
             bp = -1;
-            for (int w = 0; w < 32; ++w)
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w)
                 if (s_redp[w] >= 0 && s_redi[w] > bv) { bv = s_redi[w]; bp = s_redp[w]; }
         }
     }
@@ -498,7 +499,7 @@ __device__ __forceinline__ void ratio_pick_body(const DevLP& lp, int tie_rule, P
             if (lane == 0) { s_redi[warp] = nF; s_redp[warp] = nBand; s_red[warp] = (double)idxF; }
             __syncthreads();
             nF = 0; nBand = 0; idxF = 0x7fffffff;
-            for (int w = 0; w < 32; ++w) { nF += s_redi[w]; nBand += s_redp[w]; idxF = min(idxF, (int)s_red[w]); }
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { nF += s_redi[w]; nBand += s_redp[w]; idxF = min(idxF, (int)s_red[w]); }
             __syncthreads();
             const int f0 = (lambda < L + kEps) ? 1 : 0;
             const int band0 = (!f0 && lambda < L + 2. * kEps) ? 1 : 0;
@@ -558,7 +559,7 @@ __device__ __forceinline__ void ratio_pick_body(const DevLP& lp, int tie_rule, P
             if (lane == 0) s_red[warp] = lmin;
             __syncthreads();
             lmin = s_red[0];
-            for (int w = 1; w < 32; ++w) lmin = fmin(lmin, s_red[w]);
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) lmin = fmin(lmin, s_red[w]);
             int bestv = 0x7fffffff, bestp = -1;
             const bool basic_wins = (lmin < lambda + kEps && lmin < CUDART_INF);
             if (basic_wins) {
@@ -580,7 +581,7 @@ __device__ __forceinline__ void ratio_pick_body(const DevLP& lp, int tie_rule, P
             if (tid == 0) {
                 bestv = 0x7fffffff;
                 bestp = -1;
-                for (int w = 0; w < 32; ++w)
+                for (int w = 0; w < (int)(blockDim.x >> 5); ++w)
                     if (s_redp[w] >= 0 && s_redi[w] < bestv) { bestv = s_redi[w]; bestp = s_redp[w]; }
                 if (basic_wins && bestp >= 0) { nb = bestp; lambda = lp.lam[nb]; }
                 s_lambda = lambda;

@@ -51,7 +51,10 @@ struct PeerLinks {
     uint4* mbox[kMaxPeers];  // mbox[r] = rank r's mailbox (peer-mapped unless r == rank)
     uint4* col[kMaxPeers];   // col[r]  = rank r's column buffer, 2 * col_cap words
     unsigned int* ticket;    // local: arrival counters of the last-block pattern (2)
+    long long* tlog;         // optional phase-timing log (tuning key "phase_timing"): kTlogStamps clock64() values per pivot, block 0 thread 0
+    int32_t tlog_cap;        // pivots the log can hold
 };
+constexpr int kTlogStamps = 10;
 
 __device__ __forceinline__ long long peer_now_ns() {
     long long t;
@@ -100,12 +103,252 @@ __device__ __forceinline__ bool peer_arrive_last(unsigned int* ticket, int* s_fl
     return *s_flag != 0;
 }
 
-__global__ void __launch_bounds__(kScanThreads, 1) k_blk_pivots_peer(DevLP lp, PeerLinks pl, int tie_rule, int slot0, int npiv, uint32_t seq0,
-                                                                     PivotState* st) {
+// ------------------------------------------------------------------------------------------------
+// Version 2 of the pivot kernel: TWO barriers per pivot instead of four.
+//   * decisions are replicated: after the merge of phase D every thread knows (leaving row, lambda) and derives
+//     do_step / do_update / the new side / "still running" itself, so nobody waits for one thread to publish them;
+//     the bookkeeping of primal :205-232 (ratio_commit: Bv / Nv / Ns swap, trace, objective, pivot count, status) is
+//     carried out by ONE thread -- the one that owns row r in the x step, after it read Bv[r] -- concurrently with E;
+//   * E is fused with the NEXT pivot's phase A: the thread that writes the new reduced cost d_t prices it at once, so
+//     the per-block (best, second best) of pivot p+1 leave E of pivot p and the only barrier between two pivots is the
+//     pricing mailbox itself.
+// Per pivot: [ticket -> mailbox send] B (mailbox wait) C1 C2 | grid barrier | D E+A'.  Exact tie folds (ratio_pick_body,
+// and select_primal_body for the reference rule on a single rank) keep their extra barriers; they are rare.
+// Serves the single-GPU blocked engine too (nranks == 1: the mailbox and the column buffer are this GPU's own memory).
+// ------------------------------------------------------------------------------------------------
+// ---- block-wide (best, second best, index of the best) on the integer pipe -------------------------------------------
+// Doubles are mapped to order-preserving 64-bit keys; a warp maximum is two redux.sync (high word, then low word among
+// the lanes that hold the winning high word).  Second best = the same reduction with the winner lane contributing its own
+// second.  ~6 warp-collective instructions instead of 5 shuffle steps over a (double, double, int) triple; one
+// __syncthreads per block reduction thanks to two alternating shared-memory buffers.
+__device__ __forceinline__ unsigned long long ord_key(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ord_val(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+template <bool MAX> __device__ __forceinline__ unsigned long long warp_best_u64(unsigned long long v) {
+    const unsigned full = 0xffffffffu;
+    const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+    if (MAX) {
+        const unsigned mh = __reduce_max_sync(full, hi);
+        const unsigned ml = __reduce_max_sync(full, hi == mh ? lo : 0u);
+        return ((unsigned long long)mh << 32) | ml;
+    } else {
+        const unsigned mh = __reduce_min_sync(full, hi);
+        const unsigned ml = __reduce_min_sync(full, hi == mh ? lo : 0xffffffffu);
+        return ((unsigned long long)mh << 32) | ml;
+    }
+}
+template <bool MAX> __device__ __forceinline__ Top2 warp_top2(const Top2& t) {
+    const unsigned full = 0xffffffffu;
+    const unsigned long long k1 = ord_key(t.a1), k2 = ord_key(t.a2);
+    const unsigned long long M = warp_best_u64<MAX>(k1);
+    const int src = __ffs(__ballot_sync(full, k1 == M)) - 1;
+    const unsigned long long S = warp_best_u64<MAX>(((int)(threadIdx.x & 31) == src) ? k2 : k1);
+    Top2 r;
+    r.a1 = ord_val(M);
+    r.a2 = ord_val(S);
+    r.i1 = __shfl_sync(full, t.i1, src);
+    return r;
+}
+struct Top2Fast {
+    double a1[2][32], a2[2][32];
+    int i1[2][32];
+};
+// result valid in every thread; `buf` alternates between calls (block-uniform)
+template <bool MAX> __device__ __forceinline__ Top2 top2_block_fast(const Top2& t, Top2Fast* sh, int& buf) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const Top2 w = warp_top2<MAX>(t);
+    if (lane == 0) { sh->a1[buf][warp] = w.a1; sh->a2[buf][warp] = w.a2; sh->i1[buf][warp] = w.i1; }
+    __syncthreads();
+    const double worst = MAX ? -1.0 : CUDART_INF;
+    Top2 r;
+    r.a1 = (lane < nw) ? sh->a1[buf][lane] : worst;
+    r.a2 = (lane < nw) ? sh->a2[buf][lane] : worst;
+    r.i1 = (lane < nw) ? sh->i1[buf][lane] : -1;
+    buf ^= 1;
+    return warp_top2<MAX>(r);
+}
+template <bool MAX> __device__ __forceinline__ Top2 top2_grid_fast(const double* part, int nb, Top2Fast* sh, int& buf) {
+    const double worst = MAX ? -1.0 : CUDART_INF;
+    Top2 t{worst, worst, -1};
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        Top2 o;
+        o.a1 = __ldcg(part + 3 * b);
+        o.a2 = __ldcg(part + 3 * b + 1);
+        o.i1 = (int)__ldcg(part + 3 * b + 2);
+        top2_merge<MAX>(t, o);
+    }
+    return top2_block_fast<MAX>(t, sh, buf);
+}
+
+// Uniform (replicated in every thread) scalar state of the solve, so that the one thread that does the bookkeeping needs
+// no dependent loads from PivotState: refreshed from st at launch and after every tie-path commit.
+struct PivotRegs {
+    uint64_t pivots, max_iter;
+    int64_t trace_len, trace_cap;
+    double obj;
+    int32_t phase_tag;
+};
+__device__ __forceinline__ void pivot_regs_load(PivotRegs& g, const PivotState* st) {
+    g.pivots = __ldcg(&st->pivots);
+    g.max_iter = __ldcg(&st->max_iter);
+    g.trace_len = __ldcg(&st->trace_len);
+    g.trace_cap = __ldcg(&st->trace_cap);
+    g.obj = __ldcg(&st->obj);
+    g.phase_tag = __ldcg(&st->phase_tag);
+}
+
+// ratio_commit (kernels.cuh) with every scalar input in registers: same stores, two independent loads.  `g` holds the
+// state BEFORE this pivot.  One thread.
+__device__ __forceinline__ void ratio_commit_regs(const DevLP& lp, PivotState* st, const PivotRegs& g, int nb, double lambda, bool at_lower,
+                                                  int q_pos, int q_var, int q_side, double rq, double alpha_r, int side_after) {
+    if (!(lambda >= 0.)) {  // :402 assert!(lambda >= 0.)
+        st->err = kErrLambdaNegative; st->status = ELLP_UNBOUNDED; st->do_update = 0; st->do_step = 0;
+        return;
+    }
+    if (isinf(lambda)) {  // :404-406
+        st->status = ELLP_UNBOUNDED; st->do_update = 0; st->do_step = 0;
+        return;
+    }
+    st->do_step = (lambda > 0.) ? 1 : 0;
+    int leave_var = -1;
+    int status = kRunning;
+    if (nb >= 0) {  // :208-221
+        leave_var = __ldcg(lp.Bv + nb);
+        const double cq = lp.c[q_var];
+        lp.Bv[nb] = q_var;
+        lp.Nv[q_pos] = leave_var;
+        lp.Ns[q_pos] = (uint8_t)side_after;
+        lp.cB[nb] = cq;
+        st->r_pos = nb;
+        st->leave_var = leave_var;
+        st->alpha_r = alpha_r;
+        st->do_update = 1;
+    } else {  // :223-231 bound flip
+        if (q_side == ELLP_NB_FREE) { st->err = kErrFlipFree; st->status = ELLP_UNBOUNDED; status = ELLP_UNBOUNDED; }
+        else lp.Ns[q_pos] = (uint8_t)side_after;
+        st->r_pos = -1;
+        st->do_update = 0;
+    }
+    if (lp.trace && g.trace_len < g.trace_cap) {
+        ellp_trace_rec rec;
+        rec.phase = g.phase_tag;
+        rec.iter = (int32_t)g.pivots;
+        rec.entering = q_var;
+        rec.leaving = leave_var;
+        rec.step = lambda;
+        rec.obj = g.obj;
+        lp.trace[g.trace_len] = rec;
+    }
+    st->trace_len = g.trace_len + 1;
+    st->step = lambda;
+    st->obj = g.obj + rq * (at_lower ? lambda : -lambda);
+    st->pivots = g.pivots + 1;
+    if (status == kRunning && g.pivots + 1 >= g.max_iter) st->status = ELLP_MAXITER;  // :163-166 at the next loop head
+}
+
+struct PivotDec {
+    int do_step, do_update, r, leave_var;  // leave_var >= 0: the bookkeeping already happened (tie path), use it for row r
+    int q_pos, q_var, q_side, side_after;  // side_after: side of nonbasic position q_pos after this pivot (ELLP_NB_*)
+    bool at_lower;
+    double lambda, alpha_r, rq;
+};
+
+__device__ __forceinline__ double dantzig_key(double r, int side) {
+    double k = -1.0;
+    if (!(fabs(r) < kEps)) {
+        if (r > 0. && side == ELLP_NB_UPPER) k = r;
+        else if (!(r > 0.) && side == ELLP_NB_LOWER) k = -r;
+        else if (side == ELLP_NB_FREE) k = fabs(r);
+    }
+    return k;
+}
+
+// x step, (optionally) the bookkeeping, local pivot row / reduced costs / new (U, V) slot, and -- when `price` -- the
+// Dantzig keys of the local positions for the next pivot (returned as this thread's Top2).
+__device__ __forceinline__ Top2 blk_row_price_body(const DevLP& lp, int slot, PivotState* st, const PivotDec& d, const PivotRegs& g, bool commit_here,
+                                                   bool price, int64_t t0, int64_t stride, double* su) {
+    const int n = lp.nT, m = lp.m;
+    const int64_t tmax = max(lp.ld, lp.ldv);
+    const int r = d.r;
+    if (d.do_step) {  // primal :408-417
+        for (int64_t t = t0; t < m; t += stride) {
+            const double a = __ldcg(lp.dcol + t);
+            const double d_i = d.at_lower ? -a : a;
+            const int var = (d.leave_var >= 0 && t == r) ? d.leave_var : __ldcg(lp.Bv + t);
+            lp.x[var] = __ldcg(lp.x + var) + d.lambda * d_i;
+        }
+        if (t0 == 0) lp.x[d.q_var] = d.at_lower ? __ldcg(lp.x + d.q_var) + d.lambda : __ldcg(lp.x + d.q_var) - d.lambda;
+    }
+    if (commit_here)  // this thread owns row r (or is thread 0 for a flip): it read Bv[r] above, now it may overwrite it
+        ratio_commit_regs(lp, st, g, d.do_update ? r : -1, d.lambda, d.at_lower, d.q_pos, d.q_var, d.q_side, d.rq, d.alpha_r, d.side_after);
+    double* Uslot = lp.U + (int64_t)slot * lp.ld;
+    double* Vslot = lp.V + (int64_t)slot * lp.ldv;
+    Top2 best{-1.0, -1.0, -1};
+    const int qp_any = d.q_pos - lp.pos_lo;  // local index of the entering position (may be out of range on this rank)
+    if (!d.do_update) {
+        for (int64_t t = t0; t < tmax; t += stride) {
+            if (t < lp.ld) Uslot[t] = 0.;
+            if (t < lp.ldv) Vslot[t] = 0.;
+            if (price && t < n) {
+                const double rc = __ldcg(lp.dj + t);
+                const int side = (t == qp_any) ? d.side_after : (int)__ldcg(lp.Ns + lp.pos_lo + t);
+                const double k = dantzig_key(rc, side);
+                lp.key[t] = k;
+                lp.rN[t] = rc;
+                if (k != -1.0) top2_push<true>(best, k, (int)t);
+            }
+        }
+        return best;
+    }
+    const int qp = (lp.condensed && qp_any >= 0 && qp_any < n) ? qp_any : -1;
+    if (threadIdx.x < slot) su[threadIdx.x] = __ldcg(lp.U + (int64_t)threadIdx.x * lp.ld + r);
+    __syncthreads();
+    for (int64_t t = t0; t < tmax; t += stride) {
+        if (t < n) {
+            double dnew;
+            if (t == qp) {  // handed over to the leaving variable, whose current column is e_r
+                const double p = 1.0 / d.alpha_r;
+                Vslot[t] = p;
+                dnew = fma(-d.rq, p, 0.);
+            } else {
+                double e = __ldcg(lp.T + t * lp.ld + r);
+                for (int j = 0; j < slot; ++j) e = fma(-su[j], __ldcg(lp.V + (int64_t)j * lp.ldv + t), e);
+                const double p = e / d.alpha_r;
+                Vslot[t] = p;
+                dnew = fma(-d.rq, p, __ldcg(lp.dj + t));
+            }
+            lp.dj[t] = dnew;
+            if (price) {
+                const int side = (t == qp) ? d.side_after : (int)__ldcg(lp.Ns + lp.pos_lo + t);
+                const double k = dantzig_key(dnew, side);
+                lp.key[t] = k;
+                lp.rN[t] = dnew;
+                if (k != -1.0) top2_push<true>(best, k, (int)t);
+            }
+        } else if (t < lp.ldv) {
+            Vslot[t] = 0.;
+        }
+        if (t < lp.ld) {
+            Uslot[t] = (t < m ? __ldcg(lp.dcol + t) : 0.) - (t == r ? 1. : 0.);
+            if (qp >= 0) lp.T[(int64_t)qp * lp.ld + t] = (t == r) ? 1. : 0.;
+        }
+        if (qp >= 0 && t < slot) lp.V[t * lp.ldv + qp] = 0.;
+    }
+    return best;
+}
+
+constexpr int kFusedMaxThreads = 512;
+__global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP lp, PeerLinks pl, int tie_rule, int slot0, int npiv, uint32_t seq0,
+                                                                      PivotState* st) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char scan_smem[];
-    __shared__ Top2Smem s_top;
+    __shared__ Top2Fast s_top;
     __shared__ double s_vec[kBlkMax];
     __shared__ double s_mb[kMaxPeers * kMboxFields];
     __shared__ long long s_ll[32];
@@ -115,45 +358,46 @@ __global__ void __launch_bounds__(kScanThreads, 1) k_blk_pivots_peer(DevLP lp, P
     const int G = gridDim.x, R = pl.nranks, me = pl.rank;
     double* partA = lp.coop;
     double* partC = lp.coop + 3 * 1024;
-    long long* partT = reinterpret_cast<long long*>(lp.coop);  // near-tie round: per-block (variable << 32 | local position), reuses partA
+    long long* partT = reinterpret_cast<long long*>(lp.coop + 3 * 1024);  // near-tie round: the words of partC, idle during phase B
     const int nT = lp.nT, m = lp.m;
     bool run = (__ldcg(&st->status) == kRunning);
+    PivotRegs g;
+    pivot_regs_load(g, st);
+    int rbuf = 0;  // alternating buffer of the block reductions
+    bool priced = false;  // partA of the coming pivot already written by the previous pivot's E
     for (int slot = slot0; slot < slot0 + npiv; ++slot) {
         if (!run) { blk_zero_slot(lp, slot, gtid, gsize); continue; }
         const uint32_t seq = seq0 + (uint32_t)(slot - slot0) + 1u;
         const int par = (int)(seq & 1u);
-        // ---- A: pricing of the local positions (primal :189, :253-270)
-        {
+        long long* tl = (pl.tlog && gtid == 0 && (int)(seq - 1u) < pl.tlog_cap) ? pl.tlog + (int64_t)(seq - 1u) * kTlogStamps : nullptr;
+        if (tl) tl[0] = clock64();
+        // ---- A (first pivot of the launch only): pricing of the local positions (primal :189, :253-270)
+        if (!priced) {
             Top2 t{-1.0, -1.0, -1};
             for (int64_t j = gtid; j < nT; j += gsize) {
                 const double r = __ldcg(lp.dj + j);
-                const int side = __ldcg(lp.Ns + lp.pos_lo + j);
-                double k = -1.0;
-                if (!(fabs(r) < kEps)) {
-                    if (r > 0. && side == ELLP_NB_UPPER) k = r;
-                    else if (!(r > 0.) && side == ELLP_NB_LOWER) k = -r;
-                    else if (side == ELLP_NB_FREE) k = fabs(r);
-                }
+                const double k = dantzig_key(r, __ldcg(lp.Ns + lp.pos_lo + j));
                 lp.key[j] = k;
                 lp.rN[j] = r;
                 if (k != -1.0) top2_push<true>(t, k, (int)j);
             }
-            t = top2_block<true>(t, &s_top);
+            t = top2_block_fast<true>(t, &s_top, rbuf);
             if (tid == 0) { partA[3 * blockIdx.x] = t.a1; partA[3 * blockIdx.x + 1] = t.a2; partA[3 * blockIdx.x + 2] = (double)t.i1; }
-            if (peer_arrive_last(pl.ticket, &s_flag)) {
-                const Top2 loc = top2_grid<true>(partA, G, &s_top);
-                if (tid < R * kMboxFields) {
-                    const int dst = tid / kMboxFields, f = tid % kMboxFields;
-                    double v;
-                    if (f == 0) v = loc.a1;
-                    else if (f == 1) v = loc.a2;
-                    else if (f == 2) v = (loc.i1 >= 0) ? (double)(lp.pos_lo + loc.i1) : -1.0;
-                    else v = (loc.i1 >= 0) ? __ldcg(lp.dj + loc.i1) : 0.;
-                    ll_send(mbox_slot(pl.mbox[dst], par, 0, me, f), v, seq);
-                }
+        }
+        if (peer_arrive_last(pl.ticket, &s_flag)) {
+            const Top2 loc = top2_grid_fast<true>(partA, G, &s_top, rbuf);
+            if (tid < R * kMboxFields) {
+                const int dst = tid / kMboxFields, f = tid % kMboxFields;
+                double v;
+                if (f == 0) v = loc.a1;
+                else if (f == 1) v = loc.a2;
+                else if (f == 2) v = (loc.i1 >= 0) ? (double)(lp.pos_lo + loc.i1) : -1.0;
+                else v = (loc.i1 >= 0) ? __ldcg(lp.dj + loc.i1) : 0.;
+                ll_send(mbox_slot(pl.mbox[dst], par, 0, me, f), v, seq);
             }
         }
-        // ---- B: entering position, identical on every rank (primal :271-292, order-free tie rule)
+        if (tl) tl[1] = clock64();
+        // ---- B: entering position, identical on every rank (primal :271-292)
         int q_pos;
         double rq;
         {
@@ -174,67 +418,82 @@ __global__ void __launch_bounds__(kScanThreads, 1) k_blk_pivots_peer(DevLP lp, P
                 continue;
             }
             q_pos = t.i1;
-            if (t.a1 - t.a2 < 2. * kEps) {
-                // near-tie: largest variable index among the keys within EPS of the global maximum
-                const double kmax = t.a1;
-                long long best = -1;
-                for (int64_t j = gtid; j < nT; j += gsize) {
-                    const double k = lp.key[j];  // written by this thread in phase A
-                    if (k != -1.0 && (kmax - k < kEps)) {
-                        const long long cand = ((long long)__ldcg(lp.Nv + lp.pos_lo + j) << 32) | (long long)j;
-                        best = cand > best ? cand : best;
+            const bool near_tie = (t.a1 - t.a2 < 2. * kEps);
+            if (near_tie && R == 1 && tie_rule == ELLP_TIES_REFERENCE) {
+                // the reference's sequential max_by fold over N (primal :271-286), one block, then a grid barrier
+                __syncthreads();
+                if (blockIdx.x == 0) {
+                    if (tid == 0) { st->do_update = 0; st->do_step = 0; }
+                    select_primal_body(lp.key, lp.rN, lp.Nv, lp.Ns, lp.nN, tie_rule, st, scan_smem);
+                }
+                grid.sync();
+                q_pos = __ldcg(&st->q_pos);
+                rq = __ldcg(&st->rq);
+            } else {
+                if (near_tie) {
+                    // largest variable index among the keys within EPS of the global maximum
+                    const double kmax = t.a1;
+                    long long best = -1;
+                    for (int64_t j = gtid; j < nT; j += gsize) {
+                        const double k = lp.key[j];  // written by this thread (phase A / fused pricing)
+                        if (k != -1.0 && (kmax - k < kEps)) {
+                            const long long cand = ((long long)__ldcg(lp.Nv + lp.pos_lo + j) << 32) | (long long)j;
+                            best = cand > best ? cand : best;
+                        }
                     }
-                }
 #pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
-                    const long long o = __shfl_xor_sync(0xffffffffu, best, off);
-                    best = o > best ? o : best;
-                }
-                __syncthreads();
-                if ((tid & 31) == 0) s_ll[tid >> 5] = best;
-                __syncthreads();
-                if (tid == 0) {
-                    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best = s_ll[w] > best ? s_ll[w] : best;
-                    partT[blockIdx.x] = best;
-                }
-                if (peer_arrive_last(pl.ticket + 1, &s_flag)) {
-                    if (tid == 0) {
-                        long long b = -1;
-                        for (int k = 0; k < G; ++k) { const long long o = __ldcg(partT + k); b = o > b ? o : b; }
-                        s_ll[0] = b;
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const long long o = __shfl_xor_sync(0xffffffffu, best, off);
+                        best = o > best ? o : best;
                     }
                     __syncthreads();
-                    const long long b = s_ll[0];
-                    if (tid < R * 3) {
-                        const int dst = tid / 3, f = tid % 3;
-                        const int jl = (int)(b & 0xffffffffll);
-                        double v;
-                        if (f == 0) v = (b >= 0) ? (double)(b >> 32) : -1.0;
-                        else if (f == 1) v = (b >= 0) ? (double)(lp.pos_lo + jl) : -1.0;
-                        else v = (b >= 0) ? __ldcg(lp.dj + jl) : 0.;
-                        ll_send(mbox_slot(pl.mbox[dst], par, 1, me, f), v, seq);
+                    if ((tid & 31) == 0) s_ll[tid >> 5] = best;
+                    __syncthreads();
+                    if (tid == 0) {
+                        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best = s_ll[w] > best ? s_ll[w] : best;
+                        partT[blockIdx.x] = best;
                     }
+                    if (peer_arrive_last(pl.ticket + 1, &s_flag)) {
+                        if (tid == 0) {
+                            long long b = -1;
+                            for (int k = 0; k < G; ++k) { const long long o = __ldcg(partT + k); b = o > b ? o : b; }
+                            s_ll[0] = b;
+                        }
+                        __syncthreads();
+                        const long long b = s_ll[0];
+                        if (tid < R * 3) {
+                            const int dst = tid / 3, f = tid % 3;
+                            const int jl = (int)(b & 0xffffffffll);
+                            double v;
+                            if (f == 0) v = (b >= 0) ? (double)(b >> 32) : -1.0;
+                            else if (f == 1) v = (b >= 0) ? (double)(lp.pos_lo + jl) : -1.0;
+                            else v = (b >= 0) ? __ldcg(lp.dj + jl) : 0.;
+                            ll_send(mbox_slot(pl.mbox[dst], par, 1, me, f), v, seq);
+                        }
+                    }
+                    __syncthreads();
+                    if (tid < R * 3) s_mb[(tid / 3) * kMboxFields + (tid % 3)] = ll_recv(mbox_slot(pl.mbox[me], par, 1, tid / 3, tid % 3), seq);
+                    __threadfence();
+                    __syncthreads();
+                    double bv = -1.0;
+                    for (int s = 0; s < R; ++s)
+                        if (s_mb[s * kMboxFields] > bv) { bv = s_mb[s * kMboxFields]; q_pos = (int)s_mb[s * kMboxFields + 1]; rq = s_mb[s * kMboxFields + 2]; }
                 }
-                __syncthreads();
-                if (tid < R * 3) s_mb[(tid / 3) * kMboxFields + (tid % 3)] = ll_recv(mbox_slot(pl.mbox[me], par, 1, tid / 3, tid % 3), seq);
-                __threadfence();
-                __syncthreads();
-                double bv = -1.0;
-                for (int s = 0; s < R; ++s)
-                    if (s_mb[s * kMboxFields] > bv) { bv = s_mb[s * kMboxFields]; q_pos = (int)s_mb[s * kMboxFields + 1]; rq = s_mb[s * kMboxFields + 2]; }
-            }
-            if (gtid == 0) {
-                st->q_pos = q_pos;
-                st->q_var = __ldcg(lp.Nv + q_pos);
-                st->q_side = __ldcg(lp.Ns + q_pos);
-                st->rq = rq;
-                st->do_update = 0;
-                st->do_step = 0;
+                if (gtid == 0) {
+                    st->q_pos = q_pos;
+                    st->q_var = __ldcg(lp.Nv + q_pos);
+                    st->q_side = __ldcg(lp.Ns + q_pos);
+                    st->rq = rq;
+                    st->do_update = 0;
+                    st->do_step = 0;
+                }
             }
         }
         const int q_var = __ldcg(lp.Nv + q_pos);
-        const bool at_lower = (__ldcg(lp.Ns + q_pos) == ELLP_NB_LOWER);
-        const int cnt = slot;  // pending slots of this block of pivots
+        const int q_side = __ldcg(lp.Ns + q_pos);
+        const bool at_lower = (q_side == ELLP_NB_LOWER);
+        const int cnt = slot;
+        if (tl) tl[2] = clock64();
         // ---- C1: the owner rebuilds the entering column of the CURRENT tableau and stores it into every rank's buffer
         {
             const int ql = q_pos - lp.pos_lo;
@@ -249,8 +508,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) k_blk_pivots_peer(DevLP lp, P
                 }
             }
         }
+        if (tl) tl[3] = clock64();
         // ---- C2: every rank: column, direction, ratios (primal :295-367)
-        double lmin_basic;
         {
             Top2 t{CUDART_INF, CUDART_INF, -1};
             const uint4* colbuf = pl.col[me] + (int64_t)par * pl.col_cap;
@@ -268,14 +527,20 @@ __global__ void __launch_bounds__(kScanThreads, 1) k_blk_pivots_peer(DevLP lp, P
                     if (lam != -1.0 && lam < CUDART_INF) top2_push<false>(t, lam, (int)i);
                 }
             }
-            t = top2_block<false>(t, &s_top);
+            t = top2_block_fast<false>(t, &s_top, rbuf);
             if (tid == 0) { partC[3 * blockIdx.x] = t.a1; partC[3 * blockIdx.x + 1] = t.a2; partC[3 * blockIdx.x + 2] = (double)t.i1; }
         }
+        if (tl) tl[4] = clock64();
         grid.sync();
-        // ---- D: leaving row / bound flip (primal :305-434, :205-232); replicated, bit-identical on every rank
+        if (tl) tl[5] = clock64();
+        // ---- D: leaving row / bound flip (primal :305-434), replicated in every thread of every rank
+        PivotDec dec;
+        dec.q_pos = q_pos; dec.q_var = q_var; dec.q_side = q_side; dec.at_lower = at_lower; dec.rq = rq;
+        PivotRegs g_next = g;
+        bool commit_here = false;
         {
-            Top2 t = top2_grid<false>(partC, G, &s_top);
-            lmin_basic = t.a1;
+            Top2 t = top2_grid_fast<false>(partC, G, &s_top, rbuf);
+            const double lmin_basic = t.a1;
             const int kq = lp.kind[q_var];  // :305-311
             const double lambda0 = (kq == ELLP_TWOSIDED) ? (lp.ub[q_var] - lp.lb[q_var]) : (kq == ELLP_FIXED ? 0. : CUDART_INF);
             if (lambda0 < CUDART_INF) {
@@ -284,17 +549,65 @@ __global__ void __launch_bounds__(kScanThreads, 1) k_blk_pivots_peer(DevLP lp, P
             }
             const bool fast = !(t.a1 < CUDART_INF) || !(t.a2 < t.a1 + 2. * kEps);
             if (fast) {
-                if (gtid == 0) ratio_commit(lp, st, t.i1, t.a1, at_lower, q_var);
-            } else if (blockIdx.x == 0) {
-                if (tid == 0) st->lmin_bits = __double_as_longlong(lmin_basic);
+                const int nb = t.i1;
+                const double lambda = t.a1;
+                dec.lambda = lambda;
+                dec.leave_var = -1;
+                dec.r = nb;
+                if (!(lambda >= 0.) || isinf(lambda)) {  // :402-406: ratio_commit records Unbounded (+ the assert)
+                    dec.do_step = 0; dec.do_update = 0; dec.alpha_r = 1.; dec.side_after = q_side;
+                    run = false;
+                } else {
+                    dec.do_step = (lambda > 0.) ? 1 : 0;
+                    dec.do_update = (nb >= 0) ? 1 : 0;
+                    if (nb >= 0) {
+                        dec.alpha_r = __ldcg(lp.dcol + nb);
+                        const double d_nb = at_lower ? -dec.alpha_r : dec.alpha_r;
+                        dec.side_after = (d_nb > 0.) ? ELLP_NB_UPPER : ELLP_NB_LOWER;  // :208-221
+                    } else {  // :223-231 bound flip of the entering variable
+                        dec.alpha_r = 1.;
+                        dec.side_after = (q_side == ELLP_NB_LOWER) ? ELLP_NB_UPPER : (q_side == ELLP_NB_UPPER ? ELLP_NB_LOWER : ELLP_NB_FREE);
+                        if (q_side == ELLP_NB_FREE) run = false;  // ratio_commit: kErrFlipFree
+                    }
+                    g_next.pivots = g.pivots + 1;
+                    g_next.trace_len = g.trace_len + 1;
+                    g_next.obj = g.obj + rq * (at_lower ? lambda : -lambda);
+                    if (g_next.pivots >= g.max_iter) run = false;  // ratio_commit: MaxIter at the next loop head
+                }
+                commit_here = (gtid == ((dec.do_update && nb >= 0) ? (int64_t)nb % gsize : 0));
+            } else {
                 __syncthreads();
-                ratio_pick_body(lp, tie_rule, st, scan_smem);
+                if (blockIdx.x == 0) {
+                    if (tid == 0) st->lmin_bits = __double_as_longlong(lmin_basic);
+                    __syncthreads();
+                    ratio_pick_body(lp, tie_rule, st, scan_smem);  // exact fold of :379-399, commits through ratio_commit
+                }
+                grid.sync();
+                dec.do_step = __ldcg(&st->do_step);
+                dec.do_update = __ldcg(&st->do_update);
+                dec.r = __ldcg(&st->r_pos);
+                dec.leave_var = dec.do_update ? __ldcg(&st->leave_var) : -1;
+                dec.lambda = __ldcg(&st->step);
+                dec.alpha_r = __ldcg(&st->alpha_r);
+                dec.side_after = __ldcg(lp.Ns + q_pos);
+                run = (__ldcg(&st->status) == kRunning);
+                pivot_regs_load(g_next, st);
+                g = g_next;  // the tie path committed through PivotState before E
             }
         }
-        grid.sync();
-        // ---- E: step, local pivot row, reduced costs, new slot (primal :408-417 + the deferred row reduction)
-        blk_row_body(lp, slot, st, gtid, gsize, s_vec);
-        run = (__ldcg(&st->status) == kRunning);
+        // ---- E + A': step, bookkeeping, local pivot row, reduced costs, new slot, keys of the next pivot
+        const bool price = run && (slot + 1 < slot0 + npiv);
+        if (tl) tl[6] = clock64();
+        Top2 t = blk_row_price_body(lp, slot, st, dec, g, commit_here, price, gtid, gsize, s_vec);
+        g = g_next;
+        priced = false;
+        if (tl) tl[7] = clock64();
+        if (price) {
+            t = top2_block_fast<true>(t, &s_top, rbuf);
+            if (tid == 0) { partA[3 * blockIdx.x] = t.a1; partA[3 * blockIdx.x + 1] = t.a2; partA[3 * blockIdx.x + 2] = (double)t.i1; }
+            priced = true;
+        }
+        if (tl) tl[8] = clock64();
     }
 }
 

@@ -157,6 +157,9 @@ int ellp_b200_generate_dense_ex(ellp_b200_ctx*, int32_t m, int32_t n_struct, uin
 int ellp_b200_download_std_form(ellp_b200_ctx*, double* A, double* c, double* b, uint8_t* kind, double* lb, double* ub);
 /* tuning knobs: "rank1_cols_per_cta", "rank1_stream_min_mb", "refactor_mode", "flush_col_steps", "coop_pivots", "peer_exchange" */
 int ellp_b200_set_tuning(ellp_b200_ctx*, const char* key, int value);
+/* profiling aid: after set_tuning("phase_timing", P) the fused pivot kernel logs 10 clock64() stamps per pivot (block 0,
+ * thread 0; phase boundaries, see peer.cuh) for the next P pivots; this copies the first `pivots` records (10 int64 each). */
+int ellp_b200_phase_log(ellp_b200_ctx*, int64_t* out, int32_t pivots);
 
 /* ---- K6: batches of independent small LPs (BASELINE.json configs[3]) -------------------------------------------
  * Every LP of the batch has the same standard-form shape m x n and no Free variable; LP k sits at offset k*m*n (A,
