@@ -31,10 +31,10 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # BASELINE.json configs[4]: "synthetic dense LP 32768x65536 fp64, tableau column-sharded ... at 1/2/4/8 B200"
-    "dense_tableau_32768x65536": dict(m=32768, ns=32768, pivots=480, block_k=32, sample_m=1024, sample_pivots=3),
+    "dense_tableau_32768x65536": dict(m=32768, ns=32768, pivots=640, block_k=64, sample_m=1024, sample_pivots=3),
     # north_star target size: "for a 16384x32768 dense LP, the row-reduction kernel sustains >= 70% of HBM bandwidth"
-    "dense_tableau_16384x32768": dict(m=16384, ns=16384, pivots=480, block_k=32, sample_m=1024, sample_pivots=3),
-    "dense_tableau_4096x12288": dict(m=4096, ns=8192, pivots=960, block_k=32, sample_m=512, sample_pivots=6),
+    "dense_tableau_16384x32768": dict(m=16384, ns=16384, pivots=640, block_k=64, sample_m=1024, sample_pivots=3),
+    "dense_tableau_4096x12288": dict(m=4096, ns=8192, pivots=960, block_k=48, sample_m=512, sample_pivots=6),
     # BASELINE.json configs[2] shape: dense 4096x8192 (Gte rows => standard form 4096x12288), DUAL simplex, revised engine
     # (explicit basis inverse).  The entering/leaving rules are the reference's (steepest edge is not built yet).
     "dense_revised_dual_4096x12288": dict(m=4096, ns=8192, pivots=200, sample_m=512, sample_pivots=6, dual=True),
@@ -57,6 +57,32 @@ def measured_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# fp64 tensor pipe (DMMA m8n8k4) peak of one B200: MEASURED_PEAKS.json carries no fp64 figure, so the denominator is derived
+# from ncu: sm__pipe_tensor_subpipe_dmma_cycles_active = 62.1 % at 22.9 TFLOP/s (profiles/r01_ncu_full_blk_flush_k32_summary.txt)
+# => 36.9 TFLOP/s = 148 SMs x 64 fp64 FMA/clk x 1.965 GHz.
+DMMA_PEAK_TFLOPS = 36.9
+DMMA_PEAK_SOURCE = ("derived from ncu (dmma pipe 62.1 % active at 22.9 TFLOP/s, profiles/r01_ncu_full_blk_flush_k32_summary.txt) = "
+                    "148 SMs x 64 fp64 FMA/clk x 1.965 GHz; MEASURED_PEAKS.json has no fp64 entry")
+
+
+def blocked_roofline(roofline: dict, m: int, cols: int, bk: int, ms: float) -> dict:
+    """The rank-k flush moves 16 m cols bytes and does 2 m cols k flops: HBM-bound below k ~ 45, fp64-tensor-bound above.
+    Reports the fraction of BOTH ceilings and names the binding one in `bound` / `frac`."""
+    tfl = 2.0 * m * cols * bk / (ms * 1e-3) / 1e12
+    hbm = {k: roofline[k] for k in ("achieved", "peak", "frac", "peak_source")}
+    t_hbm = roofline["algorithmic_bytes_per_launch"] / (roofline["peak"] * 1e9)
+    t_dmma = 2.0 * m * cols * bk / (DMMA_PEAK_TFLOPS * 1e12)
+    roofline["hbm"] = hbm
+    roofline["tensor_fp64"] = {"achieved": tfl, "peak": DMMA_PEAK_TFLOPS, "frac": tfl / DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "peak_source": DMMA_PEAK_SOURCE}
+    roofline["pivots_per_launch"] = bk
+    roofline["roofline_ms"] = 1e3 * max(t_hbm, t_dmma)
+    roofline["frac_of_binding_roofline"] = 1e3 * max(t_hbm, t_dmma) / ms
+    if t_dmma > t_hbm:
+        roofline.update(bound="tensor", achieved=tfl, peak=DMMA_PEAK_TFLOPS, unit="TFLOP/s", frac=tfl / DMMA_PEAK_TFLOPS, peak_source=DMMA_PEAK_SOURCE)
+        roofline.pop("frac_of_8TBs_nominal", None)
+    return roofline
 
 
 class ClockSampler:
@@ -360,8 +386,7 @@ def run_ours(args, wl, name):
                 "traffic": traffic, "peak_source": peak_src, "ms_per_launch": k3_ms, "launches_timed": n_rank1,
                 "algorithmic_bytes_per_launch": alg_bytes, "share_of_step_device_time": (rank1_ms / dev_ms) if dev_ms else None}
     if bk > 1 and n_rank1:
-        roofline["dmma_tflops"] = 2.0 * m * k3_cols * bk / (k3_ms * 1e-3) / 1e12
-        roofline["pivots_per_launch"] = bk
+        roofline = blocked_roofline(roofline, m, k3_cols, bk, k3_ms)
 
     # ---- e2e: the C-ABI boundary on HOST buffers (H2D + pivots + D2H inside the timed region)
     e2e = None

@@ -447,4 +447,294 @@ __global__ void __launch_bounds__(256, 2) k_blk_flush(double* __restrict__ T, in
     (void)R;
 }
 
+// ------------------------------------------------------------------------------------------------
+// K3b, software-pipelined: same tiling and fragment layout as k_blk_flush, but one CTA per SM with TWO register tiles
+// per warp: the 16 x 16-byte loads of column step s+1 are issued before the DMMA sequence of step s starts, so every
+// warp keeps 8 KB in flight for the whole time it occupies the tensor pipe (64 KB per SM, enough to cover the HBM
+// latency-bandwidth product) instead of alternating "load -> wait -> mma -> store".  V is double-buffered by cp.async
+// for every K <= 64 (one CTA per SM leaves room for 137 KB).  Bit-identical results to k_blk_flush (same operation
+// order per element).
+// ------------------------------------------------------------------------------------------------
+inline size_t blk_flush2_smem_bytes(int K4) { return sizeof(double) * (size_t)K4 * (kFlushSU + 2 * kFlushSV); }
+
+template <bool STREAM>
+__global__ void __launch_bounds__(256, 1) k_blk_flush2(double* __restrict__ T, int64_t ld, int R, int C, const double* __restrict__ U,
+                                                       const double* __restrict__ V, int64_t ldv, int cnt, int col_steps) {
+    extern __shared__ __align__(16) double blk_smem[];
+    const int K4 = (cnt + 3) & ~3;
+    double* sU = blk_smem;                         // sU[j][row] = -U[row0 + row, j]
+    double* sV0 = blk_smem + K4 * kFlushSU;        // sV[j][col] = V[j, col0 + col]
+    double* sV1 = sV0 + K4 * kFlushSV;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * kFlushRows;
+    const int wr = (warp & 3) * 32, wc = (warp >> 2) * 32;
+    const int fq = lane >> 2, fk = lane & 3;
+    const int ksteps = K4 >> 2;
+    const int64_t step0 = (int64_t)blockIdx.y * col_steps;
+    const int64_t steps_total = (C + kFlushCols - 1) / kFlushCols;
+    const int nsteps = (int)max((int64_t)0, min((int64_t)col_steps, steps_total - step0));
+    if (nsteps == 0) return;
+    const bool v_aligned = ((ldv & 1) == 0) && ((reinterpret_cast<uintptr_t>(V) & 15) == 0);
+
+    auto stage_v = [&](int s) {
+        double* sV = (s & 1) ? sV1 : sV0;
+        const int64_t col0 = (step0 + s) * kFlushCols;
+        if (v_aligned && col0 + kFlushCols <= C) {
+            for (int e = tid; e < K4 * (kFlushCols / 2); e += 256) {
+                const int j = e >> 5, c2 = (e & 31) * 2;
+                double* dst = sV + j * kFlushSV + c2;
+                if (j < cnt) cp_async16(dst, V + (int64_t)j * ldv + col0 + c2);
+                else { dst[0] = 0.; dst[1] = 0.; }
+            }
+        } else {
+            for (int e = tid; e < K4 * kFlushCols; e += 256) {
+                const int j = e >> 6, c = e & (kFlushCols - 1);
+                sV[j * kFlushSV + c] = (j < cnt && col0 + c < C) ? V[(int64_t)j * ldv + col0 + c] : 0.;
+            }
+        }
+        cp_async_commit();
+    };
+    auto load_tile = [&](double2 (&acc)[4][4], int s) {
+        const int64_t col0 = (step0 + s) * kFlushCols;
+#pragma unroll
+        for (int ct = 0; ct < 4; ++ct) {
+            const int64_t c = col0 + wc + ct * 8 + fq;
+#pragma unroll
+            for (int rt = 0; rt < 4; ++rt) {
+                const int64_t r = row0 + wr + rt * 8 + 2 * fk;
+                if (c < C && r < ld) {
+                    const double* p = T + c * ld + r;
+                    acc[ct][rt] = STREAM ? ld_f64x2_stream(p) : ld_f64x2(p);
+                } else {
+                    acc[ct][rt] = make_double2(0., 0.);
+                }
+            }
+        }
+    };
+    auto mma_store = [&](double2 (&acc)[4][4], int s) {
+        const double* sV = (s & 1) ? sV1 : sV0;
+#pragma unroll 2
+        for (int ks = 0; ks < ksteps; ++ks) {
+            double a[4], b[4];
+            const int j = ks * 4 + fk;
+#pragma unroll
+            for (int ct = 0; ct < 4; ++ct) a[ct] = sV[j * kFlushSV + wc + ct * 8 + fq];
+#pragma unroll
+            for (int rt = 0; rt < 4; ++rt) b[rt] = sU[j * kFlushSU + wr + rt * 8 + fq];
+#pragma unroll
+            for (int ct = 0; ct < 4; ++ct)
+#pragma unroll
+                for (int rt = 0; rt < 4; ++rt) dmma_m8n8k4(acc[ct][rt].x, acc[ct][rt].y, a[ct], b[rt]);
+        }
+        const int64_t col0 = (step0 + s) * kFlushCols;
+#pragma unroll
+        for (int ct = 0; ct < 4; ++ct) {
+            const int64_t c = col0 + wc + ct * 8 + fq;
+#pragma unroll
+            for (int rt = 0; rt < 4; ++rt) {
+                const int64_t r = row0 + wr + rt * 8 + 2 * fk;
+                if (c < C && r < ld) {
+                    double* p = T + c * ld + r;
+                    if (STREAM) st_f64x2_stream(p, acc[ct][rt]);
+                    else st_f64x2(p, acc[ct][rt]);
+                }
+            }
+        }
+    };
+
+    double2 accA[4][4], accB[4][4];
+    stage_v(0);
+    load_tile(accA, 0);
+    for (int e = tid; e < K4 * kFlushRows; e += 256) {
+        const int j = e >> 7, i = e & (kFlushRows - 1);
+        sU[j * kFlushSU + i] = (j < cnt && row0 + i < ld) ? -U[(int64_t)j * ld + row0 + i] : 0.;
+    }
+    for (int s = 0; s < nsteps; s += 2) {
+        // even step: tile s in accA, prefetch s+1 into accB
+        if (s + 1 < nsteps) load_tile(accB, s + 1);
+        cp_async_wait<0>();
+        __syncthreads();  // V tile s (and -U) visible; every warp left step s-1, so the other V buffer may be refilled
+        if (s + 1 < nsteps) stage_v(s + 1);
+        mma_store(accA, s);
+        if (s + 1 >= nsteps) break;
+        // odd step: tile s+1 in accB, prefetch s+2 into accA
+        if (s + 2 < nsteps) load_tile(accA, s + 2);
+        cp_async_wait<0>();
+        __syncthreads();
+        if (s + 2 < nsteps) stage_v(s + 2);
+        mma_store(accB, s + 1);
+    }
+    (void)R;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3b, version 3: k_blk_flush2 without the block-wide barrier per column step.  The V tiles travel global -> shared
+// memory as bulk asynchronous copies (cp.async.bulk, the TMA copy engine: one 512-byte row of the tile per copy) into
+// a ring of kFlushStages buffers guarded by mbarriers: full[s] (armed with the expected byte count by the producer
+// lane, completed by the copy engine) and empty[s] (one arrival per warp when it has read the tile).  Warps only
+// meet through those mbarriers, so the two warps of an SM sub-partition drift out of phase and one of them occupies
+// the fp64 tensor pipe while the other issues its tile loads / stores -- with a __syncthreads per step every warp hit
+// the load/store phase at the same time and the tensor pipe idled (k_blk_flush2: 69 % DMMA active at k = 64).
+// Requires V rows padded to a multiple of 64 columns (the engine allocates ldv that way) and 16-byte alignment.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFlushStages = 3;
+constexpr int kFlush3Threads = 288;  // 8 consumer warps (4 x 2 warp tiles of 32 x 32) + 1 producer warp
+inline size_t blk_flush3_smem_bytes(int K4) { return sizeof(double) * (size_t)K4 * (kFlushSU + kFlushStages * kFlushSV) + 16 * kFlushStages; }
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned spins = 0;
+    long long t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 1023u) == 0u) {  // a copy that never lands must not hang the GPU
+            long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ll) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <bool STREAM>
+__global__ void __launch_bounds__(kFlush3Threads, 1) k_blk_flush3(double* __restrict__ T, int64_t ld, int R, int C, const double* __restrict__ U,
+                                                       const double* __restrict__ V, int64_t ldv, int cnt, int col_steps) {
+    extern __shared__ __align__(16) double blk_smem[];
+    const int K4 = (cnt + 3) & ~3;
+    double* sU = blk_smem;                         // sU[j][row] = -U[row0 + row, j]
+    double* sVr = blk_smem + K4 * kFlushSU;        // ring: sV[stage][j][col] = V[j, col0 + col]
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(sVr + kFlushStages * K4 * kFlushSV);
+    unsigned long long* empty = full + kFlushStages;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * kFlushRows;
+    const int wr = (warp & 3) * 32, wc = (warp >> 2) * 32;
+    const int fq = lane >> 2, fk = lane & 3;
+    const int ksteps = K4 >> 2;
+    const int64_t step0 = (int64_t)blockIdx.y * col_steps;
+    const int64_t steps_total = (C + kFlushCols - 1) / kFlushCols;
+    const int nsteps = (int)max((int64_t)0, min((int64_t)col_steps, steps_total - step0));
+    if (nsteps == 0) return;
+    const unsigned tile_bytes = (unsigned)cnt * kFlushCols * (unsigned)sizeof(double);
+
+    // producer warp (warp 8): V tile of step t -> ring slot t % kFlushStages, one 512-byte row per lane and copy
+    auto issue_v = [&](int t) {
+        const int slot = t % kFlushStages;
+        const int use = t / kFlushStages;
+        if (lane == 0) {
+            if (use > 0) mbar_wait(&empty[slot], (unsigned)((use - 1) & 1));  // every consumer warp released the previous tile of this slot
+            mbar_arrive_expect_tx(&full[slot], tile_bytes);
+        }
+        __syncwarp();
+        double* dst = sVr + (size_t)slot * K4 * kFlushSV;
+        const double* src = V + (step0 + t) * kFlushCols;
+        for (int j = lane; j < cnt; j += 32) bulk_g2s(dst + j * kFlushSV, src + (int64_t)j * ldv, kFlushCols * (unsigned)sizeof(double), &full[slot]);
+    };
+    auto load_tile = [&](double2 (&acc)[4][4], int s) {
+        const int64_t col0 = (step0 + s) * kFlushCols;
+#pragma unroll
+        for (int ct = 0; ct < 4; ++ct) {
+            const int64_t c = col0 + wc + ct * 8 + fq;
+#pragma unroll
+            for (int rt = 0; rt < 4; ++rt) {
+                const int64_t r = row0 + wr + rt * 8 + 2 * fk;
+                if (c < C && r < ld) {
+                    const double* p = T + c * ld + r;
+                    acc[ct][rt] = STREAM ? ld_f64x2_stream(p) : ld_f64x2(p);
+                } else {
+                    acc[ct][rt] = make_double2(0., 0.);
+                }
+            }
+        }
+    };
+    auto mma_store = [&](double2 (&acc)[4][4], int s) {
+        const int slot = s % kFlushStages;
+        mbar_wait(&full[slot], (unsigned)((s / kFlushStages) & 1));
+        const double* sV = sVr + (size_t)slot * K4 * kFlushSV;
+#pragma unroll 2
+        for (int ks = 0; ks < ksteps; ++ks) {
+            double a[4], b[4];
+            const int j = ks * 4 + fk;
+#pragma unroll
+            for (int ct = 0; ct < 4; ++ct) a[ct] = sV[j * kFlushSV + wc + ct * 8 + fq];
+#pragma unroll
+            for (int rt = 0; rt < 4; ++rt) b[rt] = sU[j * kFlushSU + wr + rt * 8 + fq];
+#pragma unroll
+            for (int ct = 0; ct < 4; ++ct)
+#pragma unroll
+                for (int rt = 0; rt < 4; ++rt) dmma_m8n8k4(acc[ct][rt].x, acc[ct][rt].y, a[ct], b[rt]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);  // this warp no longer reads the slot
+        const int64_t col0 = (step0 + s) * kFlushCols;
+#pragma unroll
+        for (int ct = 0; ct < 4; ++ct) {
+            const int64_t c = col0 + wc + ct * 8 + fq;
+#pragma unroll
+            for (int rt = 0; rt < 4; ++rt) {
+                const int64_t r = row0 + wr + rt * 8 + 2 * fk;
+                if (c < C && r < ld) {
+                    double* p = T + c * ld + r;
+                    if (STREAM) st_f64x2_stream(p, acc[ct][rt]);
+                    else st_f64x2(p, acc[ct][rt]);
+                }
+            }
+        }
+    };
+
+    if (tid == 0) {
+        for (int i = 0; i < kFlushStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    double2 accA[4][4], accB[4][4];
+    if (warp < 8) load_tile(accA, 0);
+    for (int e = tid; e < K4 * kFlushRows; e += kFlush3Threads) {
+        const int j = e >> 7, i = e & (kFlushRows - 1);
+        sU[j * kFlushSU + i] = (j < cnt && row0 + i < ld) ? -U[(int64_t)j * ld + row0 + i] : 0.;
+    }
+    // rows cnt .. K4-1 of every ring slot are never copied: zero them once
+    for (int e = tid; e < kFlushStages * (K4 - cnt) * kFlushSV; e += kFlush3Threads) {
+        const int slot = e / ((K4 - cnt) * kFlushSV), rem = e - slot * (K4 - cnt) * kFlushSV;
+        sVr[(size_t)slot * K4 * kFlushSV + (size_t)cnt * kFlushSV + rem] = 0.;
+    }
+    __syncthreads();  // barriers initialised, -U and the zero rows visible (the only block-wide barrier)
+    if (warp == 8) {  // producer
+        for (int t = 0; t < nsteps; ++t) issue_v(t);
+        return;
+    }
+    for (int s = 0; s < nsteps; s += 2) {
+        if (s + 1 < nsteps) load_tile(accB, s + 1);
+        mma_store(accA, s);
+        if (s + 1 >= nsteps) break;
+        if (s + 2 < nsteps) load_tile(accA, s + 2);
+        mma_store(accB, s + 1);
+    }
+    (void)R;
+}
+
 }  // namespace ellp

@@ -96,6 +96,9 @@ struct ellp_b200_ctx {
     int blk_kmax = 0;             // slots allocated for the blocked (deferred rank-k) tableau engine; 0 = rank-1 engine only
     int blk_fill = 0;             // slots used since the last flush
     int flush_col_steps = 8;      // column steps (of 64 columns) per CTA of k_blk_flush
+    int flush_kernel = 3;         // tuning: 1 = k_blk_flush (2 CTAs/SM), 2 = k_blk_flush2 (register prefetch, 1 CTA/SM), 3 = k_blk_flush3 (+ bulk-copy ring)
+    bool flush_attrs_set = false;
+    int flush2_col_steps = 32;    // column steps per CTA of k_blk_flush2
     int coop_pivots = 2;          // blocked engine: 2 = k_blk_pivots_fused (2 barriers per pivot), 1 = k_blk_pivots (4 barriers), 0 = five kernels per pivot
     int coop_grid = 0;            // co-resident CTAs of k_blk_pivots (0 = not yet queried)
     // peer-memory sharded engine (peer.cuh): condensed tableau split by nonbasic position, exchange fused into the pivot kernel
@@ -206,7 +209,7 @@ void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap, bool tableau, int blk
         lp.nT = lp.condensed ? (int32_t)nN : (int32_t)n;
         lp.T = lp.condensed ? a.take<double>(ld * std::max<size_t>(nN, 1)) : const_cast<double*>(lp.A);
         lp.dj = a.take<double>(n);
-        lp.ldv = (int64_t)align_up((size_t)std::max<int32_t>(lp.nT, 1), 4);
+        lp.ldv = (int64_t)align_up((size_t)std::max<int32_t>(lp.nT, 1), 64);  // whole 64-column tiles: k_blk_flush3 bulk-copies V rows unguarded
         lp.coop = a.take<double>(6 * 1024);
         lp.U = blk_kmax > 0 ? a.take<double>(ld * (size_t)blk_kmax) : nullptr;
         lp.V = blk_kmax > 0 ? a.take<double>((size_t)lp.ldv * (size_t)blk_kmax) : nullptr;
@@ -393,6 +396,48 @@ int refactor(ellp_b200_ctx* ctx, uint64_t* count) {
     return ELLP_OK;
 }
 
+// One launch of the rank-k row reduction E -= U V (K3b).  Kernel choice (tuning key "flush_kernel"): 3 = bulk-copy /
+// mbarrier ring, one CTA per SM (needs V rows padded to whole 64-column tiles, 16-byte aligned); 2 = cp.async double
+// buffer with a block barrier per step, one CTA per SM; 1 = two CTAs per SM without register prefetch.
+void launch_rankk(ellp_b200_ctx* ctx, double* E, int64_t ld, int R, int C, const double* U, const double* V, int64_t ldv, int cnt) {
+    const int K4 = (cnt + 3) & ~3;
+    const int steps_total = (C + kFlushCols - 1) / kFlushCols;
+    int kern = ctx->flush_kernel;
+    const bool bulk_ok = (ldv % 2 == 0) && ((reinterpret_cast<uintptr_t>(V) & 15) == 0) && ((int64_t)steps_total * kFlushCols <= ldv);
+    if (kern == 3 && !bulk_ok) kern = 2;
+    const size_t smem = kern == 3 ? blk_flush3_smem_bytes(K4) : (kern == 2 ? blk_flush2_smem_bytes(K4) : blk_flush_smem_bytes(K4));
+    int col_steps = std::max(1, std::min(kern == 1 ? ctx->flush_col_steps : ctx->flush2_col_steps, steps_total));
+    if (kern != 1) {  // one CTA per SM: keep at least ~8 waves of CTAs so the last partial wave stays small (narrow shards)
+        const int64_t row_blocks = (ld + kFlushRows - 1) / kFlushRows;
+        while (col_steps > 4 && row_blocks * ((steps_total + col_steps - 1) / col_steps) < 8 * 148) col_steps >>= 1;
+    }
+    dim3 grid((unsigned)((ld + kFlushRows - 1) / kFlushRows), (unsigned)((steps_total + col_steps - 1) / col_steps));
+    const bool stream = (double)ld * C * 8.0 > (double)ctx->rank1_stream_min_mb * 1048576.0;
+    if (kern == 3) {
+        if (stream) LAUNCH_SMEM(k_blk_flush3<true>, grid, kFlush3Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
+        else LAUNCH_SMEM(k_blk_flush3<false>, grid, kFlush3Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
+    } else if (kern == 2) {
+        if (stream) LAUNCH_SMEM(k_blk_flush2<true>, grid, 256, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
+        else LAUNCH_SMEM(k_blk_flush2<false>, grid, 256, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
+    } else {
+        if (stream) LAUNCH_SMEM(k_blk_flush<true>, grid, 256, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
+        else LAUNCH_SMEM(k_blk_flush<false>, grid, 256, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
+    }
+}
+
+int flush_attrs(ellp_b200_ctx* ctx) {
+    if (ctx->flush_attrs_set) return ELLP_OK;
+    const int smem1 = (int)std::max(blk_flush_smem_bytes(48), blk_flush_smem_bytes(kBlkMax));
+    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush2_smem_bytes(kBlkMax)));
+    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush2_smem_bytes(kBlkMax)));
+    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush3_smem_bytes(kBlkMax)));
+    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush3_smem_bytes(kBlkMax)));
+    ctx->flush_attrs_set = true;
+    return ELLP_OK;
+}
+
 // tableau engine, primal: 5 launches per pivot, the rank-1 update of T is >99 % of the bytes
 // blocked engine: T -= U V over the slots filled since the last flush (k_blk_flush, fp64 tensor pipe), timed like K3
 void launch_flush(ellp_b200_ctx* ctx, bool profile, size_t* ev_used) {
@@ -400,15 +445,8 @@ void launch_flush(ellp_b200_ctx* ctx, bool profile, size_t* ev_used) {
     const int cnt = ctx->blk_fill;
     ctx->blk_fill = 0;
     if (cnt <= 0) return;
-    const int K4 = (cnt + 3) & ~3;
-    const size_t smem = blk_flush_smem_bytes(K4);
-    const int steps_total = (lp.nT + kFlushCols - 1) / kFlushCols;
-    const int col_steps = std::max(1, std::min(ctx->flush_col_steps, steps_total));
-    dim3 grid((unsigned)((lp.ld + kFlushRows - 1) / kFlushRows), (unsigned)((steps_total + col_steps - 1) / col_steps));
-    const bool stream = (double)lp.ld * lp.nT * 8.0 > (double)ctx->rank1_stream_min_mb * 1048576.0;
     if (profile && ev_used && *ev_used + 2 <= ctx->ev.size()) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
-    if (stream) LAUNCH_SMEM(k_blk_flush<true>, grid, 256, smem, lp.T, lp.ld, lp.m, lp.nT, lp.U, lp.V, lp.ldv, cnt, col_steps);
-    else LAUNCH_SMEM(k_blk_flush<false>, grid, 256, smem, lp.T, lp.ld, lp.m, lp.nT, lp.U, lp.V, lp.ldv, cnt, col_steps);
+    launch_rankk(ctx, lp.T, lp.ld, lp.m, lp.nT, lp.U, lp.V, lp.ldv, cnt);
     if (profile && ev_used && (*ev_used & 1)) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
 }
 
@@ -501,7 +539,7 @@ void carve_peer(Arena& a, DevLP& lp, int64_t trace_cap, int blk_kmax) {
     lp.T = a.take<double>(ld * nT);
     lp.A = lp.T;  // the starting basis is the identity: T = A_N; the constraint matrix is not kept separately
     lp.dj = a.take<double>(nT + 8);
-    lp.ldv = (int64_t)align_up(nT, 4);
+    lp.ldv = (int64_t)align_up(nT, 64);
     lp.coop = a.take<double>(6 * 1024);
     lp.U = a.take<double>(ld * (size_t)blk_kmax);
     lp.V = a.take<double>((size_t)lp.ldv * (size_t)blk_kmax);
@@ -838,7 +876,8 @@ int ellp_b200_set_tuning(ellp_b200_ctx* ctx, const char* key, int value) {
     if (!std::strcmp(key, "rank1_cols_per_cta")) ctx->rank1_cols_per_cta = value;
     else if (!std::strcmp(key, "rank1_stream_min_mb")) ctx->rank1_stream_min_mb = value;
     else if (!std::strcmp(key, "refactor_mode")) ctx->refactor_mode = value;
-    else if (!std::strcmp(key, "flush_col_steps")) ctx->flush_col_steps = std::max(1, value);
+    else if (!std::strcmp(key, "flush_col_steps")) { ctx->flush_col_steps = std::max(1, value); ctx->flush2_col_steps = std::max(1, value); }
+    else if (!std::strcmp(key, "flush_kernel")) ctx->flush_kernel = value;
     else if (!std::strcmp(key, "coop_pivots")) ctx->coop_pivots = value;
     else if (!std::strcmp(key, "peer_exchange")) ctx->peer_exchange = value;
     else if (!std::strcmp(key, "coop_threads")) ctx->coop_threads = value;
@@ -1343,11 +1382,7 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
     // blocked tableau engine: slots were allocated at upload time; the caller may lower block_k per run
     const int blk = (ctx->tableau && ctx->blk_kmax > 0 && o->block_k > 1) ? std::min(o->block_k, ctx->blk_kmax) : 0;
     ctx->blk_fill = 0;
-    if (blk > 0) {
-        const int smem = (int)std::max(blk_flush_smem_bytes(48), blk_flush_smem_bytes(kBlkMax));
-        CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    }
+    if (blk > 0) { if (int rc = flush_attrs(ctx)) return rc; }
     int check_every = o->check_every > 0 ? o->check_every : (lp.m >= 2048 ? 1 : 8);
     int refactor_every = o->refactor_every > 0 ? o->refactor_every : ((lp.m <= 512 && !ctx->tableau) ? 100 : 0);
     if (ctx->peer_mode && ctx->nranks > 1)  // stream-ordered barrier: no rank starts polling before every rank got here
@@ -1640,20 +1675,9 @@ int ellp_b200_rankk_update_dev(ellp_b200_ctx* ctx, double* E, int64_t R, int64_t
         (reinterpret_cast<uintptr_t>(E) & 15) != 0)
         return set_err(ctx, ELLP_E_ARG, "rankk_update needs ld even, ld >= R, ldv >= C, 1 <= k <= 64 and a 16-byte aligned E");
     CUDA_TRY(cudaSetDevice(ctx->device));
-    const int K4 = (k + 3) & ~3;
-    const size_t smem = blk_flush_smem_bytes(K4);
-    const int smem_max = (int)std::max(blk_flush_smem_bytes(48), blk_flush_smem_bytes(kBlkMax));
-    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    const int steps_total = (int)((C + kFlushCols - 1) / kFlushCols);
-    const int col_steps = std::max(1, std::min(ctx->flush_col_steps, steps_total));
-    dim3 grid((unsigned)((ld + kFlushRows - 1) / kFlushRows), (unsigned)((steps_total + col_steps - 1) / col_steps));
-    const bool stream = (double)ld * C * 8.0 > (double)ctx->rank1_stream_min_mb * 1048576.0;
+    if (int rc = flush_attrs(ctx)) return rc;
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-    for (int t = 0; t < reps; ++t) {
-        if (stream) LAUNCH_SMEM(k_blk_flush<true>, grid, 256, smem, E, ld, (int)R, (int)C, U, V, ldv, (int)k, col_steps);
-        else LAUNCH_SMEM(k_blk_flush<false>, grid, 256, smem, E, ld, (int)R, (int)C, U, V, ldv, (int)k, col_steps);
-    }
+    for (int t = 0; t < reps; ++t) launch_rankk(ctx, E, ld, (int)R, (int)C, U, V, ldv, (int)k);
     CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(cudaGetLastError());
@@ -1671,13 +1695,15 @@ int ellp_b200_rankk_update(ellp_b200_ctx* ctx, double* E, int64_t R, int64_t C, 
     double *dE = nullptr, *dU = nullptr, *dV = nullptr;
     CUDA_TRY(cudaMalloc(&dE, sizeof(double) * ldp * C));
     CUDA_TRY(cudaMalloc(&dU, sizeof(double) * ldp * k));
-    CUDA_TRY(cudaMalloc(&dV, sizeof(double) * C * k));
+    const int64_t ldvp = (int64_t)align_up((size_t)C, 64);  // rows of V padded to whole 64-column tiles (k_blk_flush3)
+    CUDA_TRY(cudaMalloc(&dV, sizeof(double) * ldvp * k));
     CUDA_TRY(cudaMemset(dE, 0, sizeof(double) * ldp * C));
     CUDA_TRY(cudaMemset(dU, 0, sizeof(double) * ldp * k));
+    CUDA_TRY(cudaMemset(dV, 0, sizeof(double) * ldvp * k));
     CUDA_TRY(cudaMemcpy2D(dE, sizeof(double) * ldp, E, sizeof(double) * ld, sizeof(double) * R, C, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy2D(dU, sizeof(double) * ldp, U, sizeof(double) * R, sizeof(double) * R, k, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(dV, V, sizeof(double) * C * k, cudaMemcpyHostToDevice));
-    int rc = ellp_b200_rankk_update_dev(ctx, dE, R, C, ldp, dU, dV, C, k, 1, nullptr);
+    CUDA_TRY(cudaMemcpy2D(dV, sizeof(double) * ldvp, V, sizeof(double) * C, sizeof(double) * C, k, cudaMemcpyHostToDevice));
+    int rc = ellp_b200_rankk_update_dev(ctx, dE, R, C, ldp, dU, dV, ldvp, k, 1, nullptr);
     if (rc == ELLP_OK) CUDA_TRY(cudaMemcpy2D(E, sizeof(double) * ld, dE, sizeof(double) * ldp, sizeof(double) * R, C, cudaMemcpyDeviceToHost));
     cudaFree(dE); cudaFree(dU); cudaFree(dV);
     return rc;

@@ -43,6 +43,41 @@ def pick_entering(local_max_keys, candidates, eps: float = 1e-10):
     return best if best[0] >= 0 else None
 
 
+# ---- peer-memory engine (ellp_b200/csrc/peer.cuh): host restatement of the per-pivot protocol, used by the CPU tests ----
+def top2_merge_max(t, o):
+    """(best, second, index) merge of k_blk_pivots_fused phase B (top2_merge<true>): `o` wins only when strictly larger;
+    an equal best from another source becomes the SECOND, which is what flags the near-tie."""
+    a1, a2, i1 = t
+    b1, b2, j1 = o
+    if b1 > a1:
+        return (b1, a1 if a1 > b2 else b2, j1)
+    return (a1, b1 if b1 > a2 else a2, i1)
+
+
+def merge_pricing(msgs, eps: float = 1e-10):
+    """msgs[g] = (best key, second best key, global position of the best, reduced cost of the best) from rank g, or
+    (-1, -1, -1, 0) when rank g has no candidate.  Returns (status, position, reduced cost):
+    'optimal' (no candidate anywhere), 'pick' (isolated maximum) or 'near_tie' (second round needed)."""
+    t = (-1.0, -1.0, -1)
+    rq = 0.0
+    for (a1, a2, pos, r) in msgs:
+        if a1 > t[0]:
+            rq = r
+        t = top2_merge_max(t, (a1, a2, int(pos)))
+    if t[0] == -1.0:
+        return "optimal", -1, 0.0
+    if t[0] - t[1] < 2.0 * eps:
+        return "near_tie", t[2], rq
+    return "pick", t[2], rq
+
+
+def merge_near_tie(cands):
+    """Second round: cands[g] = (variable index, global position, reduced cost) of rank g's largest variable index whose
+    key lies within EPS of the global maximum, or (-1, -1, 0).  The largest variable index wins."""
+    best = max(cands, key=lambda c: c[0])
+    return int(best[1]), best[2]
+
+
 def nccl_library_path() -> str:
     try:
         import nvidia.nccl as pkg  # torch's bundled NCCL
@@ -180,6 +215,10 @@ def bench_main(args, wl, name, METRIC, UNIT, SEED, ClockSampler, measured_peak, 
         roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src, "ms_per_launch": k3_ms,
                     "algorithmic_bytes_per_launch": alg_bytes, "note": "per GPU; max over ranks of the mean launch time"}
+        roofline["algorithmic_bytes_per_launch"] = alg_bytes
+        if peer and achieved:
+            import bench as _bench
+            roofline = _bench.blocked_roofline(roofline, m, nloc, bk, k3_ms)
         engine = ("condensed tableau split by nonbasic position, blocked (block_k=%d), per-pivot exchange fused into the cooperative "
                   "pivot kernel over NVLink peer memory (k_blk_pivots_peer)" % bk) if peer else "tableau, column-sharded, rank-1 update per pivot"
         exchange = ("per pivot: %d x 64 B pricing words + m x 16 B column words stored into every peer (LL protocol, no NCCL call)" % world) if peer \

@@ -99,6 +99,129 @@ def test_sharded_protocol_matches_oracle_world2(m, ns, seed, K):
         np.testing.assert_allclose(x, xo, rtol=1e-9, atol=1e-9)
 
 
+def _peer_worker(rank, world, port, m, ns, seed, K, bk, ret):
+    """Peer-memory engine protocol (ellp_b200/csrc/peer.cuh) on numpy shards over gloo: condensed tableau split by
+    nonbasic POSITION, deferred rank-k updates (U replicated, V local), pricing mailbox = all_gather of 4 doubles per
+    rank, near-tie second round, pivot column 'stored into every rank' = broadcast from the owner."""
+    sys.path.insert(0, ROOT)
+    import bench_lp
+    from ellp_b200 import sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lp = bench_lp.dense_lp(m, ns, seed)
+    n = m + ns
+    plo, phi = sharded.shard_range(ns, world, rank)
+    nT = phi - plo
+    Nv, Ns = lp["N"].copy(), lp["N_side"].copy()     # replicated N list (position order)
+    T = lp["A"][:, Nv[plo:phi]].copy()                # local positions of the condensed tableau (identity basis => T = A_N)
+    dj = lp["c"][Nv[plo:phi]].copy()
+    x, Bv, c = lp["x"].copy(), lp["B"].copy(), lp["c"]
+    U = np.zeros((m, bk)); V = np.zeros((bk, nT)); fill = 0
+    trace = []
+    for it in range(K):
+        side = Ns[plo:phi]
+        key = np.where((np.abs(dj) >= EPS) & (dj < 0) & (side == 0), -dj, -1.0)
+        order = np.argsort(-key, kind="stable")
+        a1 = key[order[0]]
+        a2 = key[order[1]] if nT > 1 else -1.0
+        msg = torch.tensor([a1, a2, float(plo + order[0]) if a1 != -1.0 else -1.0, dj[order[0]] if a1 != -1.0 else 0.0], dtype=torch.float64)
+        box = [torch.zeros(4, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(box, msg)
+        status, q_pos, rq = sharded.merge_pricing([tuple(b.tolist()) for b in box])
+        if status == "optimal":
+            break
+        if status == "near_tie":
+            kmax = max(float(b[0]) for b in box)
+            cand = np.nonzero((key != -1.0) & (kmax - key < EPS))[0]
+            mine = (-1.0, -1.0, 0.0)
+            if len(cand):
+                j = cand[np.argmax(Nv[plo + cand])]
+                mine = (float(Nv[plo + j]), float(plo + j), float(dj[j]))
+            box2 = [torch.zeros(3, dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(box2, torch.tensor(mine, dtype=torch.float64))
+            q_pos, rq = sharded.merge_near_tie([tuple(b.tolist()) for b in box2])
+        q_var = int(Nv[q_pos])
+        owner = q_pos // nT
+        col = torch.zeros(m, dtype=torch.float64)
+        if owner == rank:                              # stale column + pending corrections, in pivot order
+            a = T[:, q_pos - plo].copy()
+            for j in range(fill):
+                a = a - U[:, j] * V[j, q_pos - plo]
+            col = torch.from_numpy(a)
+        dist.broadcast(col, src=owner)
+        alpha = col.numpy()
+        d = -alpha                                     # entering from its lower bound
+        lam = np.full(m, np.inf)
+        act = (np.abs(d) >= EPS) & (d < 0)
+        lam[act] = np.where(x[Bv[act]] > 0, (0 - x[Bv[act]]) / d[act], 0.0)
+        lmin = lam.min()
+        if not np.isfinite(lmin):
+            break
+        tie = np.nonzero(lam - lmin < EPS)[0]
+        r = tie[np.argmin(Bv[tie])]
+        lam_r = lam[r]
+        x[Bv] += lam_r * d
+        x[q_var] += lam_r
+        leave = int(Bv[r])
+        trace.append((q_var, leave))
+        # current pivot row of the local positions (stale row + pending corrections), scaled
+        e = T[r, :].copy()
+        for j in range(fill):
+            e = e - U[r, j] * V[j, :]
+        p = e / alpha[r]
+        if owner == rank:                              # the entering position is handed to the leaving variable (column e_r)
+            ql = q_pos - plo
+            p[ql] = 1.0 / alpha[r]
+            dj[ql] = 0.0
+            T[:, ql] = 0.0; T[r, ql] = 1.0
+            V[:fill, ql] = 0.0
+        dj -= rq * p
+        u = alpha.copy(); u[r] -= 1.0
+        U[:, fill] = u; V[fill, :] = p; fill += 1
+        Bv[r] = q_var; Nv[q_pos] = leave; Ns[q_pos] = 0 if d[r] <= 0 else 1
+        if fill == bk:                                 # flush: T -= U V (k_blk_flush*)
+            T -= U @ V
+            U[:] = 0.0; V[:] = 0.0; fill = 0
+    ret[rank] = (trace, x, Bv, Nv)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("m,ns,seed,K,bk", [(16, 48, 1, 40, 4), (32, 96, 2, 60, 8)])
+def test_peer_protocol_matches_oracle_world2(m, ns, seed, K, bk):
+    sys.path.insert(0, ROOT)
+    import bench_lp
+    from oracle import binding as O
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29900 + (os.getpid() % 90)
+    mp.spawn(_peer_worker, args=(world, port, m, ns, seed, K, bk, ret), nprocs=world, join=True)
+    lp = bench_lp.dense_lp(m, ns, seed)
+    xo, Bo, No = lp["x"].copy(), lp["B"].copy(), lp["N"].copy()
+    ref = O.solve_with_initial(O.PRIMAL, m, m + ns, lp["A"], lp["c"], lp["b"], lp["kind"], lp["lb"], lp["ub"], xo, Bo,
+                               No, lp["N_side"].copy(), max_iter=K, mode=O.MODE_CANONICAL, trace_cap=K)
+    want = list(zip(ref.trace["entering"].tolist(), ref.trace["leaving"].tolist()))
+    for rank in range(world):
+        trace, x, Bv, Nv = ret[rank]
+        assert trace == want
+        np.testing.assert_array_equal(Bv, Bo)
+        np.testing.assert_array_equal(Nv, No)          # the N list keeps the reference's position order
+        np.testing.assert_allclose(x, xo, rtol=1e-9, atol=1e-9)
+
+
+def test_pricing_merge_rules():
+    from ellp_b200 import sharded
+    none = (-1.0, -1.0, -1.0, 0.0)
+    assert sharded.merge_pricing([none, none])[0] == "optimal"
+    assert sharded.merge_pricing([(3.0, 1.0, 5.0, -3.0), (2.0, 0.5, 70.0, -2.0)]) == ("pick", 5, -3.0)
+    assert sharded.merge_pricing([(2.0, 0.5, 5.0, -2.0), (3.0, 1.0, 70.0, -3.0)]) == ("pick", 70, -3.0)
+    # equal maxima on two ranks, or a second best within 2 EPS on the same rank: second round
+    assert sharded.merge_pricing([(3.0, 1.0, 5.0, -3.0), (3.0, 0.5, 70.0, -3.0)])[0] == "near_tie"
+    assert sharded.merge_pricing([(3.0, 3.0 - 1e-11, 5.0, -3.0), none])[0] == "near_tie"
+    assert sharded.merge_near_tie([(12.0, 5.0, -3.0), (40.0, 70.0, -3.0), (-1.0, -1.0, 0.0)]) == (70, -3.0)
+
+
 def test_shard_range_partition():
     from ellp_b200 import sharded
     for world in (1, 2, 4, 8):

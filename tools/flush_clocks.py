@@ -1,0 +1,18 @@
+"""Clocks / power while k_blk_flush2 runs back to back (is the fp64 tensor pipe power-limited?)."""
+import ctypes as C, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import bench as BM
+from ellp_b200 import _native as N
+import blk_sweep as B
+ctx = N.Context(0)
+for fk, k, cs in ((2, 64, 32), (2, 48, 32), (1, 32, 8), (1, 24, 8)):
+    ctx.set_tuning("flush_kernel", fk)
+    B.flush_point(ctx, 32768, 32768, k, cs, reps=3)
+    s = BM.ClockSampler(0); s.Q = s.Q; s.start(); time.sleep(0.3)
+    d = B.flush_point(ctx, 32768, 32768, k, cs, reps=300, warm=2)
+    clk = s.stop()
+    pw = [float(r[3]) for r in s.rows if len(r) > 3]
+    d.update(flush_kernel=fk, clocks=clk, power_w_max=max(pw) if pw else None, power_w_med=sorted(pw)[len(pw)//2] if pw else None,
+             sm_mhz_min=min(float(r[1]) for r in s.rows) if s.rows else None)
+    print(json.dumps(d), flush=True)
