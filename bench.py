@@ -86,14 +86,42 @@ def blocked_roofline(roofline: dict, m: int, cols: int, bk: int, ms: float) -> d
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  Samples NVML in-process every
+    10 ms (the timed region of a step can be shorter than one `nvidia-smi -lms` period); falls back to an nvidia-smi
+    subprocess when pynvml is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nv, self.stop_flag, self.thread = index, [], None, None, False, None
+
+    def _nvml_loop(self):
+        nv, h = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((sm, mx, pw, int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates all GPUs of the box regardless of CUDA_VISIBLE_DEVICES; LOCAL_RANK == physical index under torchrun
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].strip().isdigit() else self.index
+            self.nv = (nv, nv.nvmlDeviceGetHandleByIndex(phys))
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -106,6 +134,17 @@ class ClockSampler:
             self.rows.append([t.strip() for t in line.split(",")])
 
     def stop(self) -> dict:
+        if self.nv:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            nv = self.nv[0]
+            bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            reasons = sorted({name for (_, _, _, rs) in self.rows for name, bit in bits.items() if rs & bit})
+            sm = [r[0] for r in self.rows]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": float(min(sm)) if sm else None,
+                    "sm_max_mhz": float(max(r[1] for r in self.rows)) if sm else None, "power_w_max": max((r[2] for r in self.rows), default=None),
+                    "reasons": reasons, "samples": len(sm), "source": "nvml, 10 ms period"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -120,7 +159,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs

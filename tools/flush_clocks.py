@@ -12,7 +12,5 @@ for fk, k, cs in ((2, 64, 32), (2, 48, 32), (1, 32, 8), (1, 24, 8)):
     s = BM.ClockSampler(0); s.Q = s.Q; s.start(); time.sleep(0.3)
     d = B.flush_point(ctx, 32768, 32768, k, cs, reps=300, warm=2)
     clk = s.stop()
-    pw = [float(r[3]) for r in s.rows if len(r) > 3]
-    d.update(flush_kernel=fk, clocks=clk, power_w_max=max(pw) if pw else None, power_w_med=sorted(pw)[len(pw)//2] if pw else None,
-             sm_mhz_min=min(float(r[1]) for r in s.rows) if s.rows else None)
+    d.update(flush_kernel=fk, clocks=clk)
     print(json.dumps(d), flush=True)
