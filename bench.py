@@ -469,7 +469,10 @@ def run_ours(args, wl, name):
             obj = e2e_step()
         torch.cuda.synchronize()
         dte = time.perf_counter() - t0
-        h2d = 8 * m * n + 8 * (3 * n + m) + n + 8 * n + 4 * m + 4 * ns + ns
+        # tableau engine, >= 32 MB, slack basis: only the nonbasic columns of A cross PCIe (the basis columns are verified to be
+        # unit vectors on the host while the DMA runs, ellp_b200_upload); otherwise the whole matrix is uploaded
+        cols_up = ns if (not dual and 8.0 * m * n >= 32 * 1048576) else n
+        h2d = 8 * m * cols_up + 8 * (3 * n + m) + n + 8 * n + 4 * m + 4 * ns + ns
         d2h = 8 * n + 4 * m + 4 * ns + ns + 120 * ((P + 15) // 16)
         e2e = {"value": e2e_pivots[0] / dte, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": 1e3 * dte / args.steps, "api": "ellp_b200_%s_solve_with_initial (host buffers, pinned)" % ("dual" if dual else "primal"),

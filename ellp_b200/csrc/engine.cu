@@ -9,7 +9,9 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <limits>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "engine.hpp"
@@ -102,6 +104,7 @@ struct ellp_b200_ctx {
     int coop_pivots = 2;          // blocked engine: 2 = k_blk_pivots_fused (2 barriers per pivot), 1 = k_blk_pivots (4 barriers), 0 = five kernels per pivot
     int coop_grid = 0;            // co-resident CTAs of k_blk_pivots (0 = not yet queried)
     // peer-memory sharded engine (peer.cuh): condensed tableau split by nonbasic position, exchange fused into the pivot kernel
+    bool a_resident = true;       // false after the condensed fast upload: only T = A_N is on the device
     bool peer_mode = false;       // the resident LP uses the peer layout
     int peer_exchange = 1;        // tuning: sharded + block_k > 1 => peer layout (1) or the NCCL path on the full tableau (0)
     PeerLinks pl{};               // peer-mapped mailboxes / column buffers (passed to the kernel by value)
@@ -183,6 +186,33 @@ int ensure_arena(ellp_b200_ctx* ctx, size_t bytes) {
     CUDA_TRY(cudaMalloc(&ctx->arena, bytes));
     ctx->arena_bytes = bytes;
     return ELLP_OK;
+}
+
+// true iff column B[i] of the column-major m x n matrix A is the unit vector e_i for every basis position i.
+// Memory-bound scan of m^2 doubles, split over host threads (it overlaps the DMA of the nonbasic columns).
+bool host_basis_is_identity(const double* A, int m, const int32_t* B) {
+    const size_t total = (size_t)m * m;
+    unsigned nthreads = 1;
+    if (total >= ((size_t)1 << 22)) nthreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::atomic<bool> ok{true};
+    auto work = [&](int i0, int i1) {
+        for (int i = i0; i < i1 && ok.load(std::memory_order_relaxed); ++i) {
+            const double* col = A + (size_t)B[i] * m;
+            bool good = (col[i] == 1.0);
+            double acc = 0.;
+            for (int k = 0; k < m; ++k) acc += (col[k] != 0.0) ? 1.0 : 0.0;  // branch-free count of nonzeros (NaN counts too)
+            if (!good || acc != 1.0) ok.store(false, std::memory_order_relaxed);
+        }
+    };
+    if (nthreads == 1) { work(0, m); return ok.load(); }
+    std::vector<std::thread> th;
+    const int chunk = (m + (int)nthreads - 1) / (int)nthreads;
+    for (unsigned t = 0; t < nthreads; ++t) {
+        const int i0 = (int)t * chunk, i1 = std::min(m, i0 + chunk);
+        if (i0 < i1) th.emplace_back(work, i0, i1);
+    }
+    for (auto& t : th) t.join();
+    return ok.load();
 }
 
 void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap, bool tableau, int blk_kmax, bool sharded = false, int nranks = 1,
@@ -941,7 +971,27 @@ int ellp_b200_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_poi
     // zero the padded scratch once (padding rows must stay zero)
     CUDA_TRY(cudaMemsetAsync(lp.cB, 0, (size_t)((char*)lp.lam - (char*)lp.cB), s));
     CUDA_TRY(cudaMemsetAsync(lp.y, 0, sizeof(double) * lp.ld, s));
-    if (lp.ld == m) {
+    // Condensed tableau, large LP: only the nonbasic columns are ever needed on the device when the starting basis is the
+    // identity (slack / artificial basis -- what the reference's phase builders produce, primal_problem.rs:234-246).  Their
+    // DMA goes straight into T while host threads verify that the basis columns are unit vectors; if they are, the basis
+    // half of A never crosses PCIe.  Otherwise (or for small LPs) the whole matrix is uploaded and T is built on the device.
+    bool fast_condensed = false;
+    if (tableau && lp.condensed && lp.nN > 0 && (double)m * n * 8.0 >= 32.0 * 1048576.0) {
+        if (lp.ld != m) CUDA_TRY(cudaMemsetAsync(lp.T, 0, sizeof(double) * (size_t)lp.ld * lp.nN, s));
+        for (int p0 = 0; p0 < lp.nN;) {  // runs of consecutive variable indices in N travel as one copy
+            int p1 = p0 + 1;
+            while (p1 < lp.nN && pt->N[p1] == pt->N[p1 - 1] + 1) ++p1;
+            const double* src = sf->A + (size_t)pt->N[p0] * m;
+            double* dst = lp.T + (size_t)p0 * lp.ld;
+            if (lp.ld == m) CUDA_TRY(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)m * (p1 - p0), cudaMemcpyHostToDevice, s));
+            else CUDA_TRY(cudaMemcpy2DAsync(dst, sizeof(double) * lp.ld, src, sizeof(double) * m, sizeof(double) * m, p1 - p0, cudaMemcpyHostToDevice, s));
+            p0 = p1;
+        }
+        fast_condensed = host_basis_is_identity(sf->A, m, pt->B);
+    }
+    if (fast_condensed) {
+        // A stays unpopulated on the device (ellp_b200_download_std_form reports that)
+    } else if (lp.ld == m) {
         CUDA_TRY(cudaMemcpyAsync((void*)lp.A, sf->A, sizeof(double) * (size_t)m * n, cudaMemcpyHostToDevice, s));
     } else {
         CUDA_TRY(cudaMemsetAsync((void*)lp.A, 0, sizeof(double) * (size_t)lp.ld * n, s));
@@ -978,8 +1028,18 @@ int ellp_b200_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_poi
     ctx->sharded = false;
     ctx->peer_mode = false;
     ctx->binv_valid = false;
+    ctx->a_resident = !fast_condensed;
+    if (fast_condensed) {  // T = A_N already sits in place: reduced-cost row d_p = c_p - c_B^T a_p, as at the end of refactor()
+        LAUNCH(k_init_cB, (int)((lp.ld + 255) / 256), 256, lp);
+        LAUNCH(k_gemv_t<EPI_PLAIN>, gemv_grid(lp.nN), 256, lp.T, lp.ld, (const int32_t*)nullptr, lp.nN, lp.cB, lp.dj, (const double*)nullptr,
+               (const uint8_t*)nullptr, (double*)nullptr, (PivotState*)nullptr, 0);
+        LAUNCH(k_redcost_pos, (lp.nN + 255) / 256, 256, lp.c, lp.Nv, lp.nN, lp.dj);
+        ctx->binv_valid = true;
+        ctx->pivots_since_refactor = 0;
+    }
     // host buffers are only borrowed for the duration of the call
     CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaGetLastError());
     return ELLP_OK;
 }
 
@@ -1027,6 +1087,7 @@ int ellp_b200_generate_dense_ex(ellp_b200_ctx* ctx, int32_t m, int32_t n_struct,
     ctx->sharded = false;
     ctx->peer_mode = false;
     ctx->binv_valid = false;
+    ctx->a_resident = true;
     ctx->dual_obj0 = 0.;  // y = 0 and every bound is Lower(0): dual_obj(y, d) = 0
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(cudaGetLastError());
@@ -1039,6 +1100,7 @@ int ellp_b200_download_std_form(ellp_b200_ctx* ctx, double* A, double* c, double
     CUDA_TRY(cudaSetDevice(ctx->device));
     const DevLP& lp = ctx->lp;
     cudaStream_t s = ctx->stream;
+    if (A && !ctx->a_resident) return set_err(ctx, ELLP_E_ARG, "A is not resident (condensed upload kept only the nonbasic columns)");
     if (A) CUDA_TRY(cudaMemcpy2DAsync(A, sizeof(double) * lp.m, lp.A, sizeof(double) * lp.ld, sizeof(double) * lp.m, ctx->peer_mode ? lp.nT : lp.n, cudaMemcpyDeviceToHost, s));
     if (c) CUDA_TRY(cudaMemcpyAsync(c, lp.c, sizeof(double) * lp.n_glob, cudaMemcpyDeviceToHost, s));
     if (b) CUDA_TRY(cudaMemcpyAsync(b, lp.b, sizeof(double) * lp.m, cudaMemcpyDeviceToHost, s));

@@ -600,3 +600,47 @@ def test_blocked_engine_continues_across_runs_and_matches_rank1_engine(env):
     for (e0, l0, s0), (e1, l1, s1) in zip(traces[0], traces[16]):
         assert (e0 == e1).all() and (l0 == l1).all()
         np.testing.assert_allclose(s1, s0, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("bk", [0, 16])
+def test_condensed_fast_upload_matches_resident_run_and_falls_back_on_a_non_identity_basis(env, bk):
+    """Large LP through the C ABI on HOST buffers: with a slack basis only the nonbasic columns cross PCIe (the basis columns
+    are verified to be unit vectors by host threads during the DMA) -- same pivots, point and basis as the run on the LP
+    generated in HBM; with a basis that is NOT the identity the call falls back to the full upload + device refactorisation
+    and still follows the oracle."""
+    import bench_lp
+    N, S, O, ctx = env["N"], env["S"], env["O"], env["ctx"]
+    m, ns, seed, K = 1024, 3072, 7, 48  # m * n * 8 = 33.5 MB >= the 32 MB threshold of the fast path
+    n = m + ns
+    o = N.default_opts(K, engine=N.ENGINE_TABLEAU, block_k=bk, check_every=16)
+    tr1 = np.zeros(K, dtype=N.TRACE_DTYPE); o.trace = N.ptr(tr1); o.trace_cap = K
+    ctx.check(N.lib.ellp_b200_generate_dense(ctx.h, m, ns, seed, C.byref(o)))
+    r1 = N.Result()
+    ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(o), C.byref(r1)))
+    x1 = np.zeros(n); B1 = np.zeros(m, dtype=np.int32); N1 = np.zeros(ns, dtype=np.int32); Ns1 = np.zeros(ns, dtype=np.uint8)
+    ctx.check(N.lib.ellp_b200_download(ctx.h, C.byref(N.Point(N.ptr(x1), N.ptr(B1), N.ptr(N1), N.ptr(Ns1), None, None, m, ns))))
+    lp = bench_lp.dense_lp(m, ns, seed)
+    sol = S.GpuPrimalSimplexSolver.new(K, ctx=ctx, trace_cap=K, engine=N.ENGINE_TABLEAU, block_k=bk)
+    x2, B2, N2, Ns2 = lp["x"].copy(), lp["B"].copy(), lp["N"].copy(), lp["N_side"].copy()
+    res, tr2 = sol.solve_with_initial(m, n, lp["A"], lp["c"], lp["b"], lp["kind"], lp["lb"], lp["ub"], x2, B2, N2, Ns2)
+    assert res.status == r1.status == N.MAXITER and res.iters == r1.iters == K
+    assert (tr2["entering"] == tr1["entering"]).all() and (tr2["leaving"] == tr1["leaving"]).all()
+    assert x2.tobytes() == x1.tobytes() and np.array_equal(B2, B1) and np.array_equal(N2, N1) and np.array_equal(Ns2, Ns1)
+    # the fast path must not have uploaded A
+    rc = N.lib.ellp_b200_download_std_form(ctx.h, N.ptr(np.zeros((m, n), order="F")), None, None, None, None, None)
+    assert rc == N.E_ARG
+    # non-identity basis: scale one slack column and its variable (x_s -> x_s / 2 keeps A x = b)
+    A3 = lp["A"].copy(order="F"); x3 = lp["x"].copy()
+    j = int(lp["B"][5]); A3[:, j] *= 2.0; x3[j] *= 0.5
+    K3 = 4
+    xo, Bo, No, Nso = x3.copy(), lp["B"].copy(), lp["N"].copy(), lp["N_side"].copy()
+    ref = O.solve_with_initial(O.PRIMAL, m, n, A3, lp["c"], lp["b"], lp["kind"], lp["lb"], lp["ub"], xo, Bo, No, Nso, max_iter=K3, trace_cap=K3)
+    sol3 = S.GpuPrimalSimplexSolver.new(K3, ctx=ctx, trace_cap=K3, engine=N.ENGINE_TABLEAU, block_k=bk)
+    xg, Bg, Ng, Nsg = x3.copy(), lp["B"].copy(), lp["N"].copy(), lp["N_side"].copy()
+    res3, tr3 = sol3.solve_with_initial(m, n, A3, lp["c"], lp["b"], lp["kind"], lp["lb"], lp["ub"], xg, Bg, Ng, Nsg)
+    k = len(ref.trace)
+    assert res3.status == ref.status and res3.iters == k == K3
+    assert (tr3["entering"] == ref.trace["entering"]).all() and (tr3["leaving"] == ref.trace["leaving"]).all()
+    np.testing.assert_array_equal(Bg, Bo)
+    np.testing.assert_allclose(xg, xo, rtol=1e-9, atol=1e-9)
+
