@@ -19,9 +19,10 @@
 // cannot finish pivot p+1 without every rank's pricing message for p+1, which is sent after that rank finished pivot p.
 // A consumer that waits longer than kPeerTimeoutNs traps (a dead peer must not hang the GPU).
 //
-// Per pivot and rank (slot = index of the pending (U, V) pair, cf. blocked.cuh):
-//   A   Dantzig keys of the local positions, per-block (best, second best); the LAST block to arrive (atomic ticket)
-//       merges them and stores (best key, second key, global position, reduced cost) into every rank's mailbox
+// Per pivot and rank (slot = index of the pending (U, V) pair, cf. blocked.cuh), k_blk_pivots_fused:
+//   A   (first pivot of a launch only; afterwards E already did it) Dantzig keys of the local positions, per-block
+//       (best, second best); the LAST block to arrive (atomic ticket) merges them and stores (best key, second key,
+//       global position, reduced cost) into every rank's mailbox
 //   B   every block polls the G mailbox entries and merges them in rank order => the same entering position on every
 //       rank without a grid barrier (the mailbox wait IS the barrier).  Near-tie (best - second < 2 EPS, any two
 //       ranks): second round with the order-free rule of SURVEY appendix A.1 (largest variable index within EPS of the
@@ -29,9 +30,11 @@
 //   C1  the owner of the entering position rebuilds that column of the current tableau (stale column + pending
 //       corrections, same arithmetic as k_ratio_prep) and stores it into every rank's column buffer
 //   C2  every rank polls the column (row i by the thread that needs row i), ratios, per-block two smallest | grid barrier
-//   D   merge, entering variable's own range, commit (ratio_commit) or the exact tie fold (ratio_pick_body) | grid barrier
-//   E   x step, local part of the pivot row and of the reduced-cost row, new (U, V) slot (blk_row_body).  No barrier:
-//       the next pivot's phase A/B separates it from the next reader.
+//   D   every thread merges the partials and derives the decision itself (leaving row, lambda, new side, still running);
+//       exact tie fold (ratio_pick_body) only when the minimum is not isolated
+//   E   x step, bookkeeping by the one thread that owns row r, local part of the pivot row and of the reduced-cost row,
+//       new (U, V) slot, and the Dantzig keys of the NEXT pivot (phase A of pivot p+1).  No barrier: the next pivot's
+//       ticket / mailbox separates it from the next reader.
 // Reference lines: pricing primal_simplex_solver.rs:189,253-292; column + ratios :295-367; fold/step/apply :379-434,
 // :205-232.  Decisions equal those of the NCCL path and of the oracle's canonical mode pivot for pivot (tests).
 #pragma once
