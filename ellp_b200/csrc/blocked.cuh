@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(256, 2) k_blk_flush(double* __restrict__ T, in
     stage_v(0);
     for (int e = tid; e < K4 * kFlushRows; e += 256) {
         const int j = e >> 7, i = e & (kFlushRows - 1);
-        sU[j * kFlushSU + i] = (j < cnt && row0 + i < ld) ? -U[(int64_t)j * ld + row0 + i] : 0.;
+        sU[j * kFlushSU + i] = (j < cnt && row0 + i < R) ? -U[(int64_t)j * ld + row0 + i] : 0.;
     }
     for (int s = 0; s < nsteps; ++s) {
         const int64_t col0 = (step0 + s) * kFlushCols;
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(256, 2) k_blk_flush(double* __restrict__ T, in
 #pragma unroll
             for (int rt = 0; rt < 4; ++rt) {
                 const int64_t r = row0 + wr + rt * 8 + 2 * fk;
-                if (c < C && r < ld) {
+                if (c < C && r < R) {
                     const double* p = T + c * ld + r;
                     acc[ct][rt] = STREAM ? ld_f64x2_stream(p) : ld_f64x2(p);
                 } else {
@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(256, 2) k_blk_flush(double* __restrict__ T, in
 #pragma unroll
             for (int rt = 0; rt < 4; ++rt) {
                 const int64_t r = row0 + wr + rt * 8 + 2 * fk;
-                if (c < C && r < ld) {
+                if (c < C && r < R) {
                     double* p = T + c * ld + r;
                     if (STREAM) st_f64x2_stream(p, acc[ct][rt]);
                     else st_f64x2(p, acc[ct][rt]);
@@ -444,7 +444,6 @@ __global__ void __launch_bounds__(256, 2) k_blk_flush(double* __restrict__ T, in
             }
         }
     }
-    (void)R;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -502,7 +501,7 @@ __global__ void __launch_bounds__(256, 1) k_blk_flush2(double* __restrict__ T, i
 #pragma unroll
             for (int rt = 0; rt < 4; ++rt) {
                 const int64_t r = row0 + wr + rt * 8 + 2 * fk;
-                if (c < C && r < ld) {
+                if (c < C && r < R) {
                     const double* p = T + c * ld + r;
                     acc[ct][rt] = STREAM ? ld_f64x2_stream(p) : ld_f64x2(p);
                 } else {
@@ -533,7 +532,7 @@ __global__ void __launch_bounds__(256, 1) k_blk_flush2(double* __restrict__ T, i
 #pragma unroll
             for (int rt = 0; rt < 4; ++rt) {
                 const int64_t r = row0 + wr + rt * 8 + 2 * fk;
-                if (c < C && r < ld) {
+                if (c < C && r < R) {
                     double* p = T + c * ld + r;
                     if (STREAM) st_f64x2_stream(p, acc[ct][rt]);
                     else st_f64x2(p, acc[ct][rt]);
@@ -547,7 +546,7 @@ __global__ void __launch_bounds__(256, 1) k_blk_flush2(double* __restrict__ T, i
     load_tile(accA, 0);
     for (int e = tid; e < K4 * kFlushRows; e += 256) {
         const int j = e >> 7, i = e & (kFlushRows - 1);
-        sU[j * kFlushSU + i] = (j < cnt && row0 + i < ld) ? -U[(int64_t)j * ld + row0 + i] : 0.;
+        sU[j * kFlushSU + i] = (j < cnt && row0 + i < R) ? -U[(int64_t)j * ld + row0 + i] : 0.;
     }
     for (int s = 0; s < nsteps; s += 2) {
         // even step: tile s in accA, prefetch s+1 into accB
@@ -564,7 +563,6 @@ __global__ void __launch_bounds__(256, 1) k_blk_flush2(double* __restrict__ T, i
         if (s + 2 < nsteps) stage_v(s + 2);
         mma_store(accB, s + 1);
     }
-    (void)R;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -663,7 +661,7 @@ __global__ void __launch_bounds__(kFlush3Threads, 1) k_blk_flush3(double* __rest
 #pragma unroll
             for (int rt = 0; rt < 4; ++rt) {
                 const int64_t r = row0 + wr + rt * 8 + 2 * fk;
-                if (c < C && r < ld) {
+                if (c < C && r < R) {
                     const double* p = T + c * ld + r;
                     acc[ct][rt] = STREAM ? ld_f64x2_stream(p) : ld_f64x2(p);
                 } else {
@@ -698,7 +696,7 @@ __global__ void __launch_bounds__(kFlush3Threads, 1) k_blk_flush3(double* __rest
 #pragma unroll
             for (int rt = 0; rt < 4; ++rt) {
                 const int64_t r = row0 + wr + rt * 8 + 2 * fk;
-                if (c < C && r < ld) {
+                if (c < C && r < R) {
                     double* p = T + c * ld + r;
                     if (STREAM) st_f64x2_stream(p, acc[ct][rt]);
                     else st_f64x2(p, acc[ct][rt]);
@@ -715,7 +713,7 @@ __global__ void __launch_bounds__(kFlush3Threads, 1) k_blk_flush3(double* __rest
     if (warp < 8) load_tile(accA, 0);
     for (int e = tid; e < K4 * kFlushRows; e += kFlush3Threads) {
         const int j = e >> 7, i = e & (kFlushRows - 1);
-        sU[j * kFlushSU + i] = (j < cnt && row0 + i < ld) ? -U[(int64_t)j * ld + row0 + i] : 0.;
+        sU[j * kFlushSU + i] = (j < cnt && row0 + i < R) ? -U[(int64_t)j * ld + row0 + i] : 0.;
     }
     // rows cnt .. K4-1 of every ring slot are never copied: zero them once
     for (int e = tid; e < kFlushStages * (K4 - cnt) * kFlushSV; e += kFlush3Threads) {
@@ -734,7 +732,6 @@ __global__ void __launch_bounds__(kFlush3Threads, 1) k_blk_flush3(double* __rest
         if (s + 2 < nsteps) load_tile(accA, s + 2);
         mma_store(accB, s + 1);
     }
-    (void)R;
 }
 
 }  // namespace ellp

@@ -119,6 +119,8 @@ struct ellp_b200_ctx {
     int coop_threads = 256;       // tuning: threads per block of k_blk_pivots_fused (64..512)
     int coop_threads_cached = 0;
     int coop_ctas_per_sm = 1;     // tuning: resident blocks per SM the fused kernel may use
+    int lu_panel_grid = 0;        // co-resident CTAs of k_lu_panel_coop (0 = not yet queried, -1 = unavailable)
+    int refactor_panel = 0;       // tuning: 1 = single-CTA panel kernel
     int refactor_mode = 0;        // 0 auto (blocked LU + DMMA for m >= 128, Gauss-Jordan below), 1 Gauss-Jordan, 2 blocked LU  // evict-first policy when the updated matrix is larger than this
 };
 
@@ -244,9 +246,12 @@ void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap, bool tableau, int blk
         lp.U = blk_kmax > 0 ? a.take<double>(ld * (size_t)blk_kmax) : nullptr;
         lp.V = blk_kmax > 0 ? a.take<double>((size_t)lp.ldv * (size_t)blk_kmax) : nullptr;
     } else {
-        lp.U = lp.V = nullptr;
-        lp.coop = nullptr;
-        lp.ldv = 0;
+        // revised engine: V = row-major block row of the blocked LU (operand of the rank-kPanel trailing update),
+        // coop = publication slots of the cooperative panel factorisation (refactor.cuh)
+        lp.U = nullptr;
+        lp.ldv = (int64_t)align_up(2 * m, 64);
+        lp.V = a.take<double>((size_t)kPanel * (size_t)lp.ldv);
+        lp.coop = a.take<double>(lu_panel_pub_doubles(160));
         lp.condensed = 0;
         lp.nT = 0;
         lp.G = a.take<double>(ld * 2 * m);
@@ -330,6 +335,78 @@ void launch_rank1(ellp_b200_ctx* ctx, double* E, int64_t ld, int R, int C, const
 
 int gemv_grid(int ncols) { return std::max(1, std::min((ncols + 7) / 8, 148 * 32)); }
 
+// One launch of the rank-k row reduction E -= U V (K3b).  Kernel choice (tuning key "flush_kernel"): 3 = bulk-copy /
+// mbarrier ring, one CTA per SM (needs V rows padded to whole 64-column tiles, 16-byte aligned); 2 = cp.async double
+// buffer with a block barrier per step, one CTA per SM; 1 = two CTAs per SM without register prefetch.
+void launch_rankk(ellp_b200_ctx* ctx, double* E, int64_t ld, int R, int C, const double* U, const double* V, int64_t ldv, int cnt) {
+    const int K4 = (cnt + 3) & ~3;
+    const int steps_total = (C + kFlushCols - 1) / kFlushCols;
+    int kern = ctx->flush_kernel;
+    const bool bulk_ok = (ldv % 2 == 0) && ((reinterpret_cast<uintptr_t>(V) & 15) == 0) && ((int64_t)steps_total * kFlushCols <= ldv);
+    if (kern == 3 && !bulk_ok) kern = 2;
+    const size_t smem = kern == 3 ? blk_flush3_smem_bytes(K4) : (kern == 2 ? blk_flush2_smem_bytes(K4) : blk_flush_smem_bytes(K4));
+    int col_steps = std::max(1, std::min(kern == 1 ? ctx->flush_col_steps : ctx->flush2_col_steps, steps_total));
+    if (kern != 1) {  // one CTA per SM: keep at least ~8 waves of CTAs so the last partial wave stays small (narrow shards)
+        const int64_t row_blocks = (R + kFlushRows - 1) / kFlushRows;
+        while (col_steps > 4 && row_blocks * ((steps_total + col_steps - 1) / col_steps) < 8 * 148) col_steps >>= 1;
+    }
+    dim3 grid((unsigned)((R + kFlushRows - 1) / kFlushRows), (unsigned)((steps_total + col_steps - 1) / col_steps));
+    const bool stream = (double)R * C * 8.0 > (double)ctx->rank1_stream_min_mb * 1048576.0;
+    if (kern == 3) {
+        if (stream) LAUNCH_SMEM(k_blk_flush3<true>, grid, kFlush3Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
+        else LAUNCH_SMEM(k_blk_flush3<false>, grid, kFlush3Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
+    } else if (kern == 2) {
+        if (stream) LAUNCH_SMEM(k_blk_flush2<true>, grid, 256, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
+        else LAUNCH_SMEM(k_blk_flush2<false>, grid, 256, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
+    } else {
+        if (stream) LAUNCH_SMEM(k_blk_flush<true>, grid, 256, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
+        else LAUNCH_SMEM(k_blk_flush<false>, grid, 256, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
+    }
+}
+
+int flush_attrs(ellp_b200_ctx* ctx) {
+    if (ctx->flush_attrs_set) return ELLP_OK;
+    const int smem1 = (int)std::max(blk_flush_smem_bytes(48), blk_flush_smem_bytes(kBlkMax));
+    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush2_smem_bytes(kBlkMax)));
+    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush2_smem_bytes(kBlkMax)));
+    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush3_smem_bytes(kBlkMax)));
+    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush3_smem_bytes(kBlkMax)));
+    ctx->flush_attrs_set = true;
+    return ELLP_OK;
+}
+
+// panel factorisation of the blocked LU: cooperative multi-CTA kernel while a CTA's slice of the panel fits shared
+// memory, the single-CTA kernel otherwise
+int launch_lu_panel(ellp_b200_ctx* ctx, double* G, int64_t ld, int m, int k0, int nb) {
+    DevLP& lp = ctx->lp;
+    if (ctx->lu_panel_grid == 0) {
+        int sms = 0, coop = 0, per_sm = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+        CUDA_TRY(cudaFuncSetAttribute(k_lu_panel_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, kLuPanelSmemMax));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lu_panel_coop, 256, kLuPanelSmemMax));
+        ctx->lu_panel_grid = (coop && per_sm > 0) ? std::min(sms, 159) : -1;
+    }
+    const int rows = m - k0;
+    int nctas = ctx->lu_panel_grid > 0 ? std::max(1, std::min(ctx->lu_panel_grid, rows / 64)) : 0;
+    int rpc = nctas > 0 ? (rows + nctas - 1) / nctas : 0;
+    const size_t smem = (size_t)rpc * (kPanel + 1) * sizeof(double);
+    if (nctas == 0 || smem > (size_t)kLuPanelSmemMax || ctx->refactor_panel == 1) {
+        LAUNCH(k_lu_panel, 1, 1024, G, ld, m, k0, nb, lp.lu_piv, ctx->d_st);
+        return ELLP_OK;
+    }
+    nctas = (rows + rpc - 1) / rpc;  // drop CTAs that would hold no row
+    LuPanelPub* pub = reinterpret_cast<LuPanelPub*>(lp.coop);
+    int32_t* piv = lp.lu_piv;
+    PivotState* st = ctx->d_st;
+    void* args[] = {(void*)&G, (void*)&ld, (void*)&m, (void*)&k0, (void*)&nb, (void*)&rpc, (void*)&piv, (void*)&pub, (void*)&st};
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_lu_panel_coop, dim3(nctas), dim3(256), args, smem, ctx->stream));
+    ctx->launches++;
+    return ELLP_OK;
+}
+
 // Gauss-Jordan refactorisation (see kernels.cuh).  Revised engine: B^-1 from the current basis on G = [A_B | I].
 // Tableau engine: T = B^-1 A built in place (skipped when the basis columns already are the identity), then the
 // reduced-cost row d = c - c_B^T T.
@@ -358,24 +435,20 @@ int refactor(ellp_b200_ctx* ctx, uint64_t* count) {
         double* G = lp.G;
         const int64_t ld = lp.ld;
         const int ncols = 2 * m;
+        if (int rc = flush_attrs(ctx)) return rc;
         for (int k0 = 0; k0 < m; k0 += kPanel) {
             const int nb = std::min(kPanel, m - k0), c0 = k0 + nb;
-            LAUNCH(k_lu_panel, 1, 1024, G, ld, m, k0, nb, lp.lu_piv, ctx->d_st);
+            if (int rc = launch_lu_panel(ctx, G, ld, m, k0, nb)) return rc;
             LAUNCH(k_lu_swap_rows, (ncols - nb + 255) / 256, 256, G, ld, ncols, k0, nb, lp.lu_piv, ctx->d_st);
-            LAUNCH(k_lu_trsm_lower, (ncols - c0 + 127) / 128, 128, G, ld, ncols, k0, nb, c0, ctx->d_st);
-            const int M = m - c0, N = ncols - c0;
-            if (M > 0) {
-                dim3 grid((unsigned)((M + kGemmTile - 1) / kGemmTile), (unsigned)((N + kGemmTile - 1) / kGemmTile));
-                LAUNCH(k_dgemm_sub_dmma, grid, 256, G + (int64_t)c0 * ld + c0, G + (int64_t)k0 * ld + c0, G + (int64_t)c0 * ld + k0, ld, M, N, nb, ctx->d_st);
-            }
+            if (ncols > c0) LAUNCH(k_lu_trsm_lower, (ncols - c0 + 127) / 128, 128, G, ld, ncols, k0, nb, c0, ctx->d_st, lp.V, lp.ldv);
+            // G22 -= L21 U12 over rows [c0, ld) (padding rows are zero) and ALL remaining columns: fp64 tensor pipe (k_blk_flush3)
+            if (m > c0) launch_rankk(ctx, G + (int64_t)c0 * ld + c0, ld, (int)(ld - c0), ncols - c0, G + (int64_t)k0 * ld + c0, lp.V, lp.ldv, nb);
         }
         for (int k0 = ((m - 1) / kPanel) * kPanel; k0 >= 0; k0 -= kPanel) {
             const int nb = std::min(kPanel, m - k0);
-            LAUNCH(k_lu_trsm_upper, (m + 127) / 128, 128, G, ld, ncols, k0, nb, m, ctx->d_st);
-            if (k0 > 0) {
-                dim3 grid((unsigned)((k0 + kGemmTile - 1) / kGemmTile), (unsigned)((m + kGemmTile - 1) / kGemmTile));
-                LAUNCH(k_dgemm_sub_dmma, grid, 256, G + (int64_t)m * ld, G + (int64_t)k0 * ld, G + (int64_t)m * ld + k0, ld, k0, m, nb, ctx->d_st);
-            }
+            LAUNCH(k_lu_trsm_upper, (m + 127) / 128, 128, G, ld, ncols, k0, nb, m, ctx->d_st, lp.V, lp.ldv);
+            // X[0:k0, :] -= U[0:k0, k0:k0+nb] X[k0:k0+nb, :]
+            if (k0 > 0) launch_rankk(ctx, G + (int64_t)m * ld, ld, k0, m, G + (int64_t)k0 * ld, lp.V, lp.ldv, nb);
         }
     } else if (!ctx->tableau) {
         LAUNCH(k_gj_init, 2 * m, 256, lp);
@@ -426,48 +499,6 @@ int refactor(ellp_b200_ctx* ctx, uint64_t* count) {
     return ELLP_OK;
 }
 
-// One launch of the rank-k row reduction E -= U V (K3b).  Kernel choice (tuning key "flush_kernel"): 3 = bulk-copy /
-// mbarrier ring, one CTA per SM (needs V rows padded to whole 64-column tiles, 16-byte aligned); 2 = cp.async double
-// buffer with a block barrier per step, one CTA per SM; 1 = two CTAs per SM without register prefetch.
-void launch_rankk(ellp_b200_ctx* ctx, double* E, int64_t ld, int R, int C, const double* U, const double* V, int64_t ldv, int cnt) {
-    const int K4 = (cnt + 3) & ~3;
-    const int steps_total = (C + kFlushCols - 1) / kFlushCols;
-    int kern = ctx->flush_kernel;
-    const bool bulk_ok = (ldv % 2 == 0) && ((reinterpret_cast<uintptr_t>(V) & 15) == 0) && ((int64_t)steps_total * kFlushCols <= ldv);
-    if (kern == 3 && !bulk_ok) kern = 2;
-    const size_t smem = kern == 3 ? blk_flush3_smem_bytes(K4) : (kern == 2 ? blk_flush2_smem_bytes(K4) : blk_flush_smem_bytes(K4));
-    int col_steps = std::max(1, std::min(kern == 1 ? ctx->flush_col_steps : ctx->flush2_col_steps, steps_total));
-    if (kern != 1) {  // one CTA per SM: keep at least ~8 waves of CTAs so the last partial wave stays small (narrow shards)
-        const int64_t row_blocks = (ld + kFlushRows - 1) / kFlushRows;
-        while (col_steps > 4 && row_blocks * ((steps_total + col_steps - 1) / col_steps) < 8 * 148) col_steps >>= 1;
-    }
-    dim3 grid((unsigned)((ld + kFlushRows - 1) / kFlushRows), (unsigned)((steps_total + col_steps - 1) / col_steps));
-    const bool stream = (double)ld * C * 8.0 > (double)ctx->rank1_stream_min_mb * 1048576.0;
-    if (kern == 3) {
-        if (stream) LAUNCH_SMEM(k_blk_flush3<true>, grid, kFlush3Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
-        else LAUNCH_SMEM(k_blk_flush3<false>, grid, kFlush3Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
-    } else if (kern == 2) {
-        if (stream) LAUNCH_SMEM(k_blk_flush2<true>, grid, 256, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
-        else LAUNCH_SMEM(k_blk_flush2<false>, grid, 256, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
-    } else {
-        if (stream) LAUNCH_SMEM(k_blk_flush<true>, grid, 256, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
-        else LAUNCH_SMEM(k_blk_flush<false>, grid, 256, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
-    }
-}
-
-int flush_attrs(ellp_b200_ctx* ctx) {
-    if (ctx->flush_attrs_set) return ELLP_OK;
-    const int smem1 = (int)std::max(blk_flush_smem_bytes(48), blk_flush_smem_bytes(kBlkMax));
-    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
-    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
-    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush2_smem_bytes(kBlkMax)));
-    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush2_smem_bytes(kBlkMax)));
-    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush3_smem_bytes(kBlkMax)));
-    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush3_smem_bytes(kBlkMax)));
-    ctx->flush_attrs_set = true;
-    return ELLP_OK;
-}
-
 // tableau engine, primal: 5 launches per pivot, the rank-1 update of T is >99 % of the bytes
 // blocked engine: T -= U V over the slots filled since the last flush (k_blk_flush, fp64 tensor pipe), timed like K3
 void launch_flush(ellp_b200_ctx* ctx, bool profile, size_t* ev_used) {
@@ -476,7 +507,7 @@ void launch_flush(ellp_b200_ctx* ctx, bool profile, size_t* ev_used) {
     ctx->blk_fill = 0;
     if (cnt <= 0) return;
     if (profile && ev_used && *ev_used + 2 <= ctx->ev.size()) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
-    launch_rankk(ctx, lp.T, lp.ld, lp.m, lp.nT, lp.U, lp.V, lp.ldv, cnt);
+    launch_rankk(ctx, lp.T, lp.ld, (int)lp.ld, lp.nT, lp.U, lp.V, lp.ldv, cnt);
     if (profile && ev_used && (*ev_used & 1)) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
 }
 
@@ -906,6 +937,7 @@ int ellp_b200_set_tuning(ellp_b200_ctx* ctx, const char* key, int value) {
     if (!std::strcmp(key, "rank1_cols_per_cta")) ctx->rank1_cols_per_cta = value;
     else if (!std::strcmp(key, "rank1_stream_min_mb")) ctx->rank1_stream_min_mb = value;
     else if (!std::strcmp(key, "refactor_mode")) ctx->refactor_mode = value;
+    else if (!std::strcmp(key, "refactor_panel")) ctx->refactor_panel = value;
     else if (!std::strcmp(key, "flush_col_steps")) { ctx->flush_col_steps = std::max(1, value); ctx->flush2_col_steps = std::max(1, value); }
     else if (!std::strcmp(key, "flush_kernel")) ctx->flush_kernel = value;
     else if (!std::strcmp(key, "coop_pivots")) ctx->coop_pivots = value;
@@ -1739,7 +1771,7 @@ int ellp_b200_rankk_update_dev(ellp_b200_ctx* ctx, double* E, int64_t R, int64_t
     CUDA_TRY(cudaSetDevice(ctx->device));
     if (int rc = flush_attrs(ctx)) return rc;
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-    for (int t = 0; t < reps; ++t) launch_rankk(ctx, E, ld, (int)R, (int)C, U, V, ldv, (int)k);
+    for (int t = 0; t < reps; ++t) launch_rankk(ctx, E, ld, (int)ld, (int)C, U, V, ldv, (int)k);  // rows up to ld: padding rows of U are zero
     CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(cudaGetLastError());
