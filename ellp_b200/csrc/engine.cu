@@ -1303,6 +1303,10 @@ static void batch_free(ellp_b200_ctx* ctx) {
 }
 
 static int batch_alloc(ellp_b200_ctx* ctx, int nlp, int m, int n0, int trace_cap) {
+    {   // same shape as the resident batch (the latency path solves one small LP after another): keep the buffers
+        auto& R = ctx->batch;
+        if (R.A && R.nlp == nlp && R.m == m && R.n0 == n0 && R.trace_cap == trace_cap) return ELLP_OK;
+    }
     batch_free(ctx);
     auto& B = ctx->batch;
     B.nlp = nlp; B.m = m; B.n0 = n0; B.nc = n0 + m; B.ld = (m % 2 == 0) ? m + 1 : m; B.trace_cap = trace_cap;

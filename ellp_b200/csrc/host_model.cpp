@@ -536,7 +536,58 @@ int device_phase(ellp_b200_ctx* ctx, int solver, HostStdForm& sf, HostPoint& pt,
 }
 
 // primal_simplex_solver.rs:32-93
+// Latency path of PrimalSimplexSolver::solve for netlib-sized problems: the whole two-phase solve (PrimalPhase1::from,
+// phase 1, verdict, PrimalPhase2::from, phase 2 -- primal_simplex_solver.rs:32-93) is ONE launch of the shared-memory kernel
+// K6 (batch.cuh) with a batch of one LP, instead of ~7 launches per pivot.  Taken when ellp_opts::engine is AUTO, the
+// standard form has no Free variable and fits shared memory; any outcome that needs the reference's panic text or the
+// MaxIter objective falls through to the general path, which reproduces it.  Pivot for pivot the same solve
+// (tests/test_gpu_parity.py::test_batch_kernel_single_lp_follows_oracle_pivot_for_pivot).
+bool try_small_primal(ellp_b200_ctx* ctx, const Model& mdl, const ellp_opts* o, ellp_solution* sol, int64_t* toff, bool* infeasible_std) {
+    *infeasible_std = false;
+    if (o->engine != ELLP_ENGINE_AUTO) return false;
+    HostStdForm sf;
+    if (!standardize(mdl, sf)) { *infeasible_std = true; return true; }
+    const int m = sf.m, n = sf.n;
+    if (m < 1 || n < m || (int)sf.lim.size() != n) return false;
+    if ((double)(m + 2) * (double)n * 8.0 + 64.0 * (n + m) > 200.0 * 1024.0) return false;
+    std::vector<uint8_t> kind(n);
+    std::vector<double> lo(n), hi(n);
+    for (int j = 0; j < n; ++j) {
+        if (sf.lim[j].kind == ELLP_FREE) return false;
+        kind[j] = sf.lim[j].kind; lo[j] = sf.lim[j].lo; hi[j] = sf.lim[j].hi;
+    }
+    ellp_batch bt{1, m, n, sf.A.v.data(), sf.c.data(), sf.b.data(), kind.data(), lo.data(), hi.data()};
+    std::vector<double> x((size_t)n + m, 0.);
+    int32_t status = -1, iters[2] = {0, 0}, err = 0, tlen = 0;
+    double obj = 0.;
+    ellp_batch_result res{};
+    res.status = &status; res.obj = &obj; res.x = x.data(); res.iters = iters; res.err = &err; res.trace_len = &tlen;
+    const int64_t tcap = o->trace ? std::max<int64_t>(0, o->trace_cap - *toff) : 0;
+    if (tcap > 0) { res.trace = o->trace + *toff; res.trace_cap = (int32_t)std::min<int64_t>(tcap, 1 << 20); }
+    if (ellp_b200_primal_solve_batch(ctx, &bt, o, &res) != ELLP_OK) return false;
+    if (err != 0 || status < 0 || status == ELLP_MAXITER) return false;
+    sol->status = status;
+    sol->iters[0] = (uint64_t)iters[0];
+    sol->iters[1] = (uint64_t)iters[1];
+    sol->launches += res.launches;
+    sol->ms_device += res.ms_device;
+    if (tcap > 0) { *toff += std::min<int64_t>(tlen, res.trace_cap); sol->trace_len += tlen; }
+    else sol->trace_len += iters[0] + iters[1];
+    if (status == ELLP_OPTIMAL) {
+        sol->obj = obj;
+        if (sol->x) std::copy(x.begin(), x.begin() + mdl.vars.size(), sol->x);
+    }
+    return true;
+}
+
 void run_primal(ellp_b200_ctx* ctx, const Model& mdl, const ellp_opts* o, ellp_solution* sol, int64_t* toff) {
+    {
+        bool infeasible_std = false;
+        if (try_small_primal(ctx, mdl, o, sol, toff, &infeasible_std)) {
+            if (infeasible_std) sol->status = ELLP_INFEASIBLE;
+            return;
+        }
+    }
     PrimalStage ps;
     if (!build_primal_phase1(mdl, ps)) { sol->status = ELLP_INFEASIBLE; return; }
     int st = device_phase(ctx, ELLP_PRIMAL, ps.sf, ps.pt, o, 0, sol, toff);

@@ -33,10 +33,13 @@ def _rel(a, b):
 
 # ---------------------------------------------------------------- the reference's own integration tests
 @pytest.mark.parametrize("which", ["primal", "dual"])
+@pytest.mark.parametrize("engine", ["auto", "revised"])
 @pytest.mark.parametrize("make", P.GOLDEN, ids=[f.__name__ for f in P.GOLDEN])
-def test_golden_integration_on_gpu(env, which, make):
+def test_golden_integration_on_gpu(env, which, make, engine):
+    # engine "auto": small primal solves take the one-launch shared-memory path (K6); "revised": the general device loop
     prob, exp = make()
-    res = _solver(env, which).solve(prob)
+    N = env["N"]
+    res = _solver(env, which, engine=N.ENGINE_AUTO if engine == "auto" else N.ENGINE_REVISED).solve(prob)
     obj = res.solution.obj() if res.is_optimal else float("nan")
     x = res.solution.x() if res.is_optimal else []
     P.check_expectation(exp, res.kind, obj, x)
@@ -51,12 +54,15 @@ def test_golden_integration_on_gpu(env, which, make):
     assert res.used_primal_fallback == ref.used_primal_fallback
 
 
+@pytest.mark.parametrize("engine", ["auto", "revised"])
 @pytest.mark.parametrize("which", ["primal", "dual"])
 @pytest.mark.parametrize("name", P.NETLIB)
-def test_netlib_on_gpu(env, which, name):
+def test_netlib_on_gpu(env, which, name, engine):
     prob, exp = P.netlib(name)
-    O = env["O"]
-    res = _solver(env, which, trace_cap=4096).solve(prob)
+    O, N = env["O"], env["N"]
+    res = _solver(env, which, trace_cap=4096, engine=N.ENGINE_AUTO if engine == "auto" else N.ENGINE_REVISED).solve(prob)
+    if which == "primal":
+        assert (res.launches <= 4) == (engine == "auto"), res.launches  # one launch for the whole solve on the latency path
     assert res.is_optimal, res
     P.check_expectation(exp, res.kind, res.solution.obj(), res.solution.x())
     ref = O.solve(prob, O.PRIMAL if which == "primal" else O.DUAL, 1000, O.MODE_EXACT, trace_cap=4096)
@@ -66,13 +72,14 @@ def test_netlib_on_gpu(env, which, name):
     print(f"{name} {which}: gpu iters {res.iters} oracle iters {ref.iters} launches {res.launches}")
 
 
+@pytest.mark.parametrize("engine", ["auto", "revised"])
 @pytest.mark.parametrize("which", ["primal", "dual"])
-def test_afiro_pivot_sequence_matches_oracle(env, which):
+def test_afiro_pivot_sequence_matches_oracle(env, which, engine):
     # the reference's sequential tie folds are reproduced on the device, so even this heavily degenerate LP pivots
     # identically to the oracle
     prob, _ = P.netlib("afiro")
-    O = env["O"]
-    res = _solver(env, which, trace_cap=4096).solve(prob)
+    O, N = env["O"], env["N"]
+    res = _solver(env, which, trace_cap=4096, engine=N.ENGINE_AUTO if engine == "auto" else N.ENGINE_REVISED).solve(prob)
     ref = O.solve(prob, O.PRIMAL if which == "primal" else O.DUAL, 1000, O.MODE_EXACT, trace_cap=4096)
     assert res.iters == ref.iters
     assert (res.trace["entering"] == ref.trace["entering"]).all()
