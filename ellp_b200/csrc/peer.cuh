@@ -271,15 +271,53 @@ __device__ __forceinline__ double dantzig_key(double r, int side) {
     return k;
 }
 
+// acc - sum_j g[j * stride] * coef[j], j ascending (one fma per pending pivot, i.e. the roundings of j rank-1 updates), with the
+// loads issued 16 at a time: the chain of dependent fmas is short, the exposed latency was one L2 round trip per 4 terms.
+__device__ __forceinline__ double corr_chain(double acc, const double* g, int64_t stride, const double* coef, int cnt) {
+    int j = 0;
+    for (; j + 16 <= cnt; j += 16) {
+        double v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = __ldcg(g + (int64_t)(j + q) * stride);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) acc = fma(-v[q], coef[j + q], acc);
+    }
+    for (; j + 4 <= cnt; j += 4) {
+        double v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = __ldcg(g + (int64_t)(j + q) * stride);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc = fma(-v[q], coef[j + q], acc);
+    }
+    for (; j < cnt; ++j) acc = fma(-__ldcg(g + (int64_t)j * stride), coef[j], acc);
+    return acc;
+}
+
+// What phase C2 already loaded for the first row a thread owns (row == its global thread index): phase E reuses it
+// instead of walking Bv -> x again.
+struct RowCache {
+    int64_t row;  // -1: nothing cached
+    double a;     // entering-column entry (valid for row < ld)
+    double xv;    // x[var] before the step (valid for row < m)
+    int var;      // Bv[row] before the bookkeeping
+};
+
 // x step, (optionally) the bookkeeping, local pivot row / reduced costs / new (U, V) slot, and -- when `price` -- the
 // Dantzig keys of the local positions for the next pivot (returned as this thread's Top2).
 __device__ __forceinline__ Top2 blk_row_price_body(const DevLP& lp, int slot, PivotState* st, const PivotDec& d, const PivotRegs& g, bool commit_here,
-                                                   bool price, int64_t t0, int64_t stride, double* su) {
+                                                   bool price, int64_t t0, int64_t stride, double* su, const RowCache& rc) {
     const int n = lp.nT, m = lp.m;
     const int64_t tmax = max(lp.ld, lp.ldv);
     const int r = d.r;
+    // the corrections of the pivot row need U[r, 0..slot): issue those loads before anything else of this phase
+    if (d.do_update && threadIdx.x < slot) su[threadIdx.x] = __ldcg(lp.U + (int64_t)threadIdx.x * lp.ld + r);
     if (d.do_step) {  // primal :408-417
         for (int64_t t = t0; t < m; t += stride) {
+            if (t == rc.row) {  // Bv[t] (before the bookkeeping), x and the column entry are already in registers
+                const double d_i = d.at_lower ? -rc.a : rc.a;
+                lp.x[rc.var] = rc.xv + d.lambda * d_i;
+                continue;
+            }
             const double a = __ldcg(lp.dcol + t);
             const double d_i = d.at_lower ? -a : a;
             const int var = (d.leave_var >= 0 && t == r) ? d.leave_var : __ldcg(lp.Bv + t);
@@ -309,25 +347,25 @@ __device__ __forceinline__ Top2 blk_row_price_body(const DevLP& lp, int slot, Pi
         return best;
     }
     const int qp = (lp.condensed && qp_any >= 0 && qp_any < n) ? qp_any : -1;
-    if (threadIdx.x < slot) su[threadIdx.x] = __ldcg(lp.U + (int64_t)threadIdx.x * lp.ld + r);
     __syncthreads();
     for (int64_t t = t0; t < tmax; t += stride) {
         if (t < n) {
             double dnew;
+            const double dold = __ldcg(lp.dj + t);
+            const int side_t = price ? (int)__ldcg(lp.Ns + lp.pos_lo + t) : 0;
             if (t == qp) {  // handed over to the leaving variable, whose current column is e_r
                 const double p = 1.0 / d.alpha_r;
                 Vslot[t] = p;
                 dnew = fma(-d.rq, p, 0.);
             } else {
-                double e = __ldcg(lp.T + t * lp.ld + r);
-                for (int j = 0; j < slot; ++j) e = fma(-su[j], __ldcg(lp.V + (int64_t)j * lp.ldv + t), e);
+                const double e = corr_chain(__ldcg(lp.T + t * lp.ld + r), lp.V + t, lp.ldv, su, slot);
                 const double p = e / d.alpha_r;
                 Vslot[t] = p;
-                dnew = fma(-d.rq, p, __ldcg(lp.dj + t));
+                dnew = fma(-d.rq, p, dold);
             }
             lp.dj[t] = dnew;
             if (price) {
-                const int side = (t == qp) ? d.side_after : (int)__ldcg(lp.Ns + lp.pos_lo + t);
+                const int side = (t == qp) ? d.side_after : side_t;
                 const double k = dantzig_key(dnew, side);
                 lp.key[t] = k;
                 lp.rN[t] = dnew;
@@ -337,7 +375,8 @@ __device__ __forceinline__ Top2 blk_row_price_body(const DevLP& lp, int slot, Pi
             Vslot[t] = 0.;
         }
         if (t < lp.ld) {
-            Uslot[t] = (t < m ? __ldcg(lp.dcol + t) : 0.) - (t == r ? 1. : 0.);
+            const double a = (t == rc.row) ? rc.a : (t < m ? __ldcg(lp.dcol + t) : 0.);
+            Uslot[t] = (t < m ? a : 0.) - (t == r ? 1. : 0.);
             if (qp >= 0) lp.T[(int64_t)qp * lp.ld + t] = (t == r) ? 1. : 0.;
         }
         if (qp >= 0 && t < slot) lp.V[t * lp.ldv + qp] = 0.;
@@ -505,27 +544,37 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
                 if (tid < cnt) s_vec[tid] = __ldcg(lp.V + (int64_t)tid * lp.ldv + ql);
                 __syncthreads();
                 for (int64_t i = gtid; i < lp.ld; i += gsize) {
-                    double a = __ldcg(lp.T + (int64_t)ql * lp.ld + i);
-                    for (int j = 0; j < cnt; ++j) a = fma(-__ldcg(lp.U + (int64_t)j * lp.ld + i), s_vec[j], a);
+                    const double a = corr_chain(__ldcg(lp.T + (int64_t)ql * lp.ld + i), lp.U + i, lp.ld, s_vec, cnt);
                     for (int d = 0; d < R; ++d) ll_send(pl.col[d] + (int64_t)par * pl.col_cap + i, a, seq);
                 }
             }
         }
         if (tl) tl[3] = clock64();
         // ---- C2: every rank: column, direction, ratios (primal :295-367)
+        RowCache rc;
+        rc.row = -1;
+        const int kq = lp.kind[q_var];  // :305-311, loaded before the barrier that phase D waits behind
+        const double lambda0 = (kq == ELLP_TWOSIDED) ? (lp.ub[q_var] - lp.lb[q_var]) : (kq == ELLP_FIXED ? 0. : CUDART_INF);
         {
             Top2 t{CUDART_INF, CUDART_INF, -1};
             const uint4* colbuf = pl.col[me] + (int64_t)par * pl.col_cap;
             for (int64_t i = gtid; i < lp.ld; i += gsize) {
+                // Bv -> x / bounds do not depend on the column: walk them while the column word is in flight
+                int var = 0;
+                double xv = 0., lbv = 0., ubv = 0.;
+                int kv = ELLP_FIXED;
+                if (i < m) {
+                    var = __ldcg(lp.Bv + i);
+                    xv = __ldcg(lp.x + var);
+                    kv = lp.kind[var]; lbv = lp.lb[var]; ubv = lp.ub[var];
+                }
                 const double a = ll_recv(colbuf + i, seq);
                 lp.dcol[i] = a;
+                if (i == gtid) { rc.row = i; rc.a = a; rc.var = var; rc.xv = xv; }
                 if (i < m) {
                     const double d_i = at_lower ? -a : a;  // :296-300
                     double lam = -1.0;                      // -1 = skipped (|d_i| < EPS, :321)
-                    if (!(fabs(d_i) < kEps)) {
-                        const int var = __ldcg(lp.Bv + i);
-                        lam = primal_ratio(lp.kind[var], lp.lb[var], lp.ub[var], __ldcg(lp.x + var), d_i);
-                    }
+                    if (!(fabs(d_i) < kEps)) lam = primal_ratio(kv, lbv, ubv, xv, d_i);
                     lp.lam[i] = lam;
                     if (lam != -1.0 && lam < CUDART_INF) top2_push<false>(t, lam, (int)i);
                 }
@@ -544,8 +593,6 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
         {
             Top2 t = top2_grid_fast<false>(partC, G, &s_top, rbuf);
             const double lmin_basic = t.a1;
-            const int kq = lp.kind[q_var];  // :305-311
-            const double lambda0 = (kq == ELLP_TWOSIDED) ? (lp.ub[q_var] - lp.lb[q_var]) : (kq == ELLP_FIXED ? 0. : CUDART_INF);
             if (lambda0 < CUDART_INF) {
                 if (lambda0 < t.a1) { t.a2 = t.a1; t.a1 = lambda0; t.i1 = -1; }
                 else if (lambda0 < t.a2) t.a2 = lambda0;
@@ -601,7 +648,8 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
         // ---- E + A': step, bookkeeping, local pivot row, reduced costs, new slot, keys of the next pivot
         const bool price = run && (slot + 1 < slot0 + npiv);
         if (tl) tl[6] = clock64();
-        Top2 t = blk_row_price_body(lp, slot, st, dec, g, commit_here, price, gtid, gsize, s_vec);
+        if (rc.row >= m) { rc.var = 0; rc.xv = 0.; }
+        Top2 t = blk_row_price_body(lp, slot, st, dec, g, commit_here, price, gtid, gsize, s_vec, rc);
         g = g_next;
         priced = false;
         if (tl) tl[7] = clock64();

