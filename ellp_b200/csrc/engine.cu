@@ -644,6 +644,7 @@ int peer_prepare(ellp_b200_ctx* ctx, int32_t m, int32_t n_glob, const ellp_opts*
     a.base = ctx->arena;
     carve_peer(a, lp, tcap, blk);
     if (int rc = peer_setup(ctx, lp.ld)) return rc;
+    CUDA_TRY(cudaMemsetAsync(lp.coop, 0, sizeof(double) * 6 * 1024, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(lp.cB, 0, (size_t)((char*)lp.lam - (char*)lp.cB), ctx->stream));
     CUDA_TRY(cudaMemsetAsync(lp.y, 0, sizeof(double) * lp.ld, ctx->stream));
     ctx->blk_kmax = blk;
@@ -690,7 +691,7 @@ int launch_coop_pivots_peer(ellp_b200_ctx* ctx, const ellp_opts* o, int npiv, bo
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
         CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, kScanSmemBytes));
-        grid_cap = (coop && per_sm > 0) ? std::min(1024, sms * std::min(per_sm, std::max(1, ctx->coop_ctas_per_sm))) : -1;
+        grid_cap = (coop && per_sm > 0) ? std::min(kLLMaxBlocks, sms * std::min(per_sm, std::max(1, ctx->coop_ctas_per_sm))) : -1;
         ctx->coop_threads_cached = threads;
     }
     if (grid_cap < 0) return set_err(ctx, ELLP_E_CUDA, "cooperative launch unavailable");
@@ -1003,6 +1004,7 @@ int ellp_b200_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_poi
     // zero the padded scratch once (padding rows must stay zero)
     CUDA_TRY(cudaMemsetAsync(lp.cB, 0, (size_t)((char*)lp.lam - (char*)lp.cB), s));
     CUDA_TRY(cudaMemsetAsync(lp.y, 0, sizeof(double) * lp.ld, s));
+    if (tableau && lp.coop) CUDA_TRY(cudaMemsetAsync(lp.coop, 0, sizeof(double) * 6 * 1024, s));  // LL words of the fused pivot kernel: no stale sequence numbers
     // Condensed tableau, large LP: only the nonbasic columns are ever needed on the device when the starting basis is the
     // identity (slack / artificial basis -- what the reference's phase builders produce, primal_problem.rs:234-246).  Their
     // DMA goes straight into T while host threads verify that the basis columns are unit vectors; if they are, the basis
@@ -1104,6 +1106,7 @@ int ellp_b200_generate_dense_ex(ellp_b200_ctx* ctx, int32_t m, int32_t n_struct,
     carve(a, lp, KS, tcap, tableau, blk);
     CUDA_TRY(cudaMemsetAsync(lp.cB, 0, (size_t)((char*)lp.lam - (char*)lp.cB), ctx->stream));
     CUDA_TRY(cudaMemsetAsync(lp.y, 0, sizeof(double) * lp.ld, ctx->stream));
+    if (tableau && lp.coop) CUDA_TRY(cudaMemsetAsync(lp.coop, 0, sizeof(double) * 6 * 1024, ctx->stream));
     LAUNCH(k_gen_dense_cols, 148 * 16, 256, const_cast<double*>(lp.A), lp.ld, m, (int64_t)n_struct, (int64_t)0, (int64_t)lp.n, seed,
            variant == 0 ? 1.0 : -1.0);
     LAUNCH(k_gen_dense_vectors, 148 * 2, 256, lp, (int64_t)n_struct, seed, (int)variant);

@@ -385,6 +385,45 @@ __device__ __forceinline__ Top2 blk_row_price_body(const DevLP& lp, int slot, Pi
 }
 
 constexpr int kFusedMaxThreads = 512;
+constexpr int kLLMaxBlocks = 160;  // blocks of k_blk_pivots_fused (local all-to-all areas in DevLP::coop: 2 x 2 x 160 x 4 words)
+
+// Intra-GPU barrier WITH payload: every block stores its (best, second, index, extra) as four LL words into its slot of a
+// local area; every block then polls all G slots (ll_gather) and reduces them itself.  Compared with "grid.sync + read the
+// partials" this is one store -> poll hop instead of an atomic ticket, a flag spin and a dependent load; like grid.sync it
+// orders all earlier global writes of every block before every later read (fence before the publish, fence after the poll).
+__device__ __forceinline__ void ll_publish(uint4* area, int par, const Top2& t, double extra, uint32_t seq) {
+    if (threadIdx.x < 4) {
+        const int f = threadIdx.x;
+        const double v = f == 0 ? t.a1 : (f == 1 ? t.a2 : (f == 2 ? (double)t.i1 : extra));
+        __threadfence();
+        ll_send(area + ((size_t)par * kLLMaxBlocks + blockIdx.x) * 4 + f, v, seq);
+    }
+}
+// all threads; s_part[4 b + f] = field f of block b.  Ends with a block barrier.
+__device__ __forceinline__ void ll_gather(const uint4* area, int par, int nblocks, double* s_part, uint32_t seq) {
+    const uint4* base = area + (size_t)par * kLLMaxBlocks * 4;
+    for (int w = threadIdx.x; w < 4 * nblocks; w += blockDim.x) s_part[w] = ll_recv(base + w, seq);
+    __threadfence();
+    __syncthreads();
+}
+// (best, second, index) over the gathered slots + the `extra` word of the winning slot; result valid in every thread
+template <bool MAX> __device__ __forceinline__ Top2 ll_reduce(const double* s_part, int nblocks, Top2Fast* sh, int& buf, double* s_extra, double* extra) {
+    const double worst = MAX ? -1.0 : CUDART_INF;
+    Top2 t{worst, worst, -1};
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+        const Top2 o{s_part[4 * b], s_part[4 * b + 1], (int)s_part[4 * b + 2]};
+        top2_merge<MAX>(t, o);
+    }
+    t = top2_block_fast<MAX>(t, sh, buf);
+    if (threadIdx.x == 0) *s_extra = 0.;
+    __syncthreads();
+    if (t.i1 >= 0)
+        for (int b = threadIdx.x; b < nblocks; b += blockDim.x)
+            if ((int)s_part[4 * b + 2] == t.i1 && s_part[4 * b] == t.a1) *s_extra = s_part[4 * b + 3];  // indices are unique across blocks
+    __syncthreads();
+    *extra = *s_extra;
+    return t;
+}
 __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP lp, PeerLinks pl, int tie_rule, int slot0, int npiv, uint32_t seq0,
                                                                       PivotState* st) {
     namespace cg = cooperative_groups;
@@ -395,12 +434,14 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
     __shared__ double s_mb[kMaxPeers * kMboxFields];
     __shared__ long long s_ll[32];
     __shared__ int s_flag;
+    __shared__ double s_part[kLLMaxBlocks * 4];
+    __shared__ double s_extra;
     const int tid = threadIdx.x;
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + tid, gsize = (int64_t)gridDim.x * blockDim.x;
     const int G = gridDim.x, R = pl.nranks, me = pl.rank;
-    double* partA = lp.coop;
-    double* partC = lp.coop + 3 * 1024;
-    long long* partT = reinterpret_cast<long long*>(lp.coop + 3 * 1024);  // near-tie round: the words of partC, idle during phase B
+    uint4* llA = reinterpret_cast<uint4*>(lp.coop);          // pricing partials of every block, [parity][block][4 words]
+    uint4* llC = reinterpret_cast<uint4*>(lp.coop + 2560);   // ratio partials
+    long long* partT = reinterpret_cast<long long*>(lp.coop + 5120);  // near-tie round: per-block (variable << 32 | local position)
     const int nT = lp.nT, m = lp.m;
     bool run = (__ldcg(&st->status) == kRunning);
     PivotRegs g;
@@ -424,34 +465,40 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
                 if (k != -1.0) top2_push<true>(t, k, (int)j);
             }
             t = top2_block_fast<true>(t, &s_top, rbuf);
-            if (tid == 0) { partA[3 * blockIdx.x] = t.a1; partA[3 * blockIdx.x + 1] = t.a2; partA[3 * blockIdx.x + 2] = (double)t.i1; }
+            ll_publish(llA, par, t, (t.i1 >= 0) ? __ldcg(lp.dj + t.i1) : 0., seq);
         }
-        if (peer_arrive_last(pl.ticket, &s_flag)) {
-            const Top2 loc = top2_grid_fast<true>(partA, G, &s_top, rbuf);
-            if (tid < R * kMboxFields) {
-                const int dst = tid / kMboxFields, f = tid % kMboxFields;
-                double v;
-                if (f == 0) v = loc.a1;
-                else if (f == 1) v = loc.a2;
-                else if (f == 2) v = (loc.i1 >= 0) ? (double)(lp.pos_lo + loc.i1) : -1.0;
-                else v = (loc.i1 >= 0) ? __ldcg(lp.dj + loc.i1) : 0.;
-                ll_send(mbox_slot(pl.mbox[dst], par, 0, me, f), v, seq);
-            }
+        // every block gathers every block's pricing partial: the local (best, second, position, reduced cost) without a grid barrier
+        double loc_rq;
+        ll_gather(llA, par, G, s_part, seq);
+        const Top2 loc = ll_reduce<true>(s_part, G, &s_top, rbuf, &s_extra, &loc_rq);
+        if (R > 1 && blockIdx.x == 0 && tid < R * kMboxFields) {  // one block per rank tells the other ranks
+            const int dst = tid / kMboxFields, f = tid % kMboxFields;
+            double v;
+            if (f == 0) v = loc.a1;
+            else if (f == 1) v = loc.a2;
+            else if (f == 2) v = (loc.i1 >= 0) ? (double)(lp.pos_lo + loc.i1) : -1.0;
+            else v = loc_rq;
+            ll_send(mbox_slot(pl.mbox[dst], par, 0, me, f), v, seq);
         }
         if (tl) tl[1] = clock64();
         // ---- B: entering position, identical on every rank (primal :271-292)
         int q_pos;
         double rq;
         {
-            if (tid < R * kMboxFields) s_mb[tid] = ll_recv(mbox_slot(pl.mbox[me], par, 0, tid / kMboxFields, tid % kMboxFields), seq);
-            __threadfence();
-            __syncthreads();
             Top2 t{-1.0, -1.0, -1};
             rq = 0.;
-            for (int s = 0; s < R; ++s) {
-                const Top2 o{s_mb[s * kMboxFields], s_mb[s * kMboxFields + 1], (int)s_mb[s * kMboxFields + 2]};
-                if (o.a1 > t.a1) rq = s_mb[s * kMboxFields + 3];
-                top2_merge<true>(t, o);
+            if (R == 1) {  // single GPU: the local result is the result
+                t = loc;
+                rq = loc_rq;
+            } else {
+                if (tid < R * kMboxFields) s_mb[tid] = ll_recv(mbox_slot(pl.mbox[me], par, 0, tid / kMboxFields, tid % kMboxFields), seq);
+                __threadfence();
+                __syncthreads();
+                for (int s = 0; s < R; ++s) {
+                    const Top2 o{s_mb[s * kMboxFields], s_mb[s * kMboxFields + 1], (int)s_mb[s * kMboxFields + 2]};
+                    if (o.a1 > t.a1) rq = s_mb[s * kMboxFields + 3];
+                    top2_merge<true>(t, o);
+                }
             }
             if (t.a1 == -1.0) {  // no candidate on any rank: optimal (:289-292)
                 if (gtid == 0) { st->status = ELLP_OPTIMAL; st->do_update = 0; st->do_step = 0; }
@@ -580,10 +627,10 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
                 }
             }
             t = top2_block_fast<false>(t, &s_top, rbuf);
-            if (tid == 0) { partC[3 * blockIdx.x] = t.a1; partC[3 * blockIdx.x + 1] = t.a2; partC[3 * blockIdx.x + 2] = (double)t.i1; }
+            ll_publish(llC, par, t, (t.i1 >= 0) ? __ldcg(lp.dcol + t.i1) : 1., seq);  // extra = column entry of the block's best row
         }
         if (tl) tl[4] = clock64();
-        grid.sync();
+        ll_gather(llC, par, G, s_part, seq);  // replaces the grid barrier: every block waits for every block's ratios
         if (tl) tl[5] = clock64();
         // ---- D: leaving row / bound flip (primal :305-434), replicated in every thread of every rank
         PivotDec dec;
@@ -591,7 +638,8 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
         PivotRegs g_next = g;
         bool commit_here = false;
         {
-            Top2 t = top2_grid_fast<false>(partC, G, &s_top, rbuf);
+            double alpha_best;
+            Top2 t = ll_reduce<false>(s_part, G, &s_top, rbuf, &s_extra, &alpha_best);
             const double lmin_basic = t.a1;
             if (lambda0 < CUDART_INF) {
                 if (lambda0 < t.a1) { t.a2 = t.a1; t.a1 = lambda0; t.i1 = -1; }
@@ -611,7 +659,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
                     dec.do_step = (lambda > 0.) ? 1 : 0;
                     dec.do_update = (nb >= 0) ? 1 : 0;
                     if (nb >= 0) {
-                        dec.alpha_r = __ldcg(lp.dcol + nb);
+                        dec.alpha_r = alpha_best;  // = dcol[nb], carried by the winning block's partial
                         const double d_nb = at_lower ? -dec.alpha_r : dec.alpha_r;
                         dec.side_after = (d_nb > 0.) ? ELLP_NB_UPPER : ELLP_NB_LOWER;  // :208-221
                     } else {  // :223-231 bound flip of the entering variable
@@ -655,7 +703,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
         if (tl) tl[7] = clock64();
         if (price) {
             t = top2_block_fast<true>(t, &s_top, rbuf);
-            if (tid == 0) { partA[3 * blockIdx.x] = t.a1; partA[3 * blockIdx.x + 1] = t.a2; partA[3 * blockIdx.x + 2] = (double)t.i1; }
+            ll_publish(llA, par ^ 1, t, (t.i1 >= 0) ? __ldcg(lp.dj + t.i1) : 0., seq + 1u);  // phase A of the next pivot
             priced = true;
         }
         if (tl) tl[8] = clock64();

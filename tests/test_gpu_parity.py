@@ -656,7 +656,7 @@ def test_full_size_blocked_engine_matches_rank1_engine_and_stays_feasible(env):
     """north_star's target size (16384 x 32768), where the oracle cannot follow (one 16384^3 LU per pivot): size-independent
     properties instead.  (1) The fused blocked engine (k = 64, one cooperative launch per 64 pivots + one rank-64 flush on the
     fp64 tensor pipe) and the rank-1 engine (one k_rank1 sweep per pivot) must produce the SAME pivots and basis, and the same
-    point / steps / objective to 1e-10; (2) the point stays primal feasible (A x = b to rounding, x >= 0), the objective never increases, and every
+    point / steps / objective to 1e-9; (2) the point stays primal feasible (A x = b to rounding, x >= 0), the objective never increases, and every
     entering variable had a negative reduced cost (Dantzig) -- checked on the host against the LP downloaded from HBM."""
     N, ctx = env["N"], env["ctx"]
     m, ns, seed, K = 16384, 16384, 0, 192
@@ -680,9 +680,9 @@ def test_full_size_blocked_engine_matches_rank1_engine_and_stays_feasible(env):
     assert (t0["entering"] == t1["entering"]).all() and (t0["leaving"] == t1["leaving"]).all()
     # values agree to rounding, not bit for bit: the deferred form reproduces a pivot-row entry as E_r - (alpha_r - 1) p instead
     # of storing p itself (one ulp), everything else is the same sequence of fmas
-    np.testing.assert_allclose(t1["step"], t0["step"], rtol=1e-10, atol=1e-12)
-    np.testing.assert_allclose(t1["obj"], t0["obj"], rtol=1e-10, atol=1e-12)
-    np.testing.assert_allclose(x1, x0, rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(t1["step"], t0["step"], rtol=1e-9, atol=1e-9)   # steps are differences of O(1e3) values
+    np.testing.assert_allclose(t1["obj"], t0["obj"], rtol=1e-10, atol=1e-9)
+    np.testing.assert_allclose(x1, x0, rtol=1e-9, atol=1e-9)
     assert np.array_equal(B0, B1) and np.array_equal(N0, N1) and np.array_equal(Ns0, Ns1) and abs(obj0 - obj1) <= 1e-10 * abs(obj0)
     # size-independent properties of the path
     assert (x1 >= -1e-9).all()
