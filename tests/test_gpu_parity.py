@@ -689,7 +689,9 @@ def test_full_size_blocked_engine_matches_rank1_engine_and_stays_feasible(env):
     resid = A @ x1 - b
     assert np.abs(resid).max() <= 1e-9 * np.abs(b).max()
     assert sorted(B1.tolist() + N1.tolist()) == list(range(n))             # B and N partition the variables
-    assert np.count_nonzero(x1[N1]) == 0                                   # nonbasic variables sit at their (zero) bound
+    assert np.abs(x1[N1]).max() <= 1e-9                                    # nonbasic variables sit at their (zero) bound, to rounding:
+    #                                                                        like the reference (x[B] += lambda d, primal :408-417) a leaving
+    #                                                                        variable is not snapped to its bound
     assert (np.diff(t1["obj"]) <= 1e-9 * np.abs(t1["obj"]).max()).all()    # the objective never increases
     assert abs(float(c @ x1) - obj1) <= 1e-9 * max(1.0, abs(obj1))
     assert (t1["step"] >= 0).all()
