@@ -587,6 +587,25 @@ def test_blocked_tableau_engine_two_phase_primal(env, make):
         assert res.iters == ref.iters
 
 
+@pytest.mark.parametrize("name", P.NETLIB + ["beale_cycle", "small_prob_2", "small_prob_5"])
+@pytest.mark.parametrize("bk", [0, 8, 64])
+def test_tableau_engines_with_the_order_free_tie_rule_follow_the_oracle_on_degenerate_lps(env, name, bk):
+    """ELLP_TIES_CANONICAL (the rule the multi-GPU engines need) on heavily degenerate LPs: near-ties in pricing and in the ratio
+    test take the second-round / exact-fold paths of the pivot kernels.  Same pivots as the oracle's canonical mode, phase by
+    phase (Beale's LP cycles under this rule -- both sides must then stop at max_iter with the same trace)."""
+    prob, exp = P.netlib(name) if name in P.NETLIB else P.GOLDEN_BY_NAME[name]()
+    N, S, O = env["N"], env["S"], env["O"]
+    res = S.GpuPrimalSimplexSolver.new(300, ctx=env["ctx"], engine=N.ENGINE_TABLEAU, block_k=bk, tie_rule=N.TIES_CANONICAL, trace_cap=4096).solve(prob)
+    ref = O.solve(prob, O.PRIMAL, 300, O.MODE_CANONICAL, trace_cap=4096)
+    assert res.kind == ref.status_name
+    assert res.iters[:2] == ref.iters[:2]
+    k = len(ref.trace)
+    assert len(res.trace) == k
+    assert (res.trace["entering"] == ref.trace["entering"]).all() and (res.trace["leaving"] == ref.trace["leaving"]).all()
+    if res.is_optimal:
+        assert _rel(res.solution.obj(), ref.obj) < 1e-9
+
+
 def test_blocked_engine_continues_across_runs_and_matches_rank1_engine(env):
     """bench.py's usage: the LP stays resident and ellp_b200_run is called repeatedly with a pivot budget.  The blocked
     engine (flush at the end of every run) must follow the rank-1 engine pivot for pivot over several runs."""

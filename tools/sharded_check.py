@@ -71,6 +71,41 @@ for bk in (0, 8, 5):
               f"generated_ok={good} uploaded_ok={good2}", flush=True)
         ok = ok and good and good2
 
+# (2b) near-ties ACROSS ranks: every structural column appears twice, once in each half of N, so the two copies have the
+# same Dantzig key on different ranks (world >= 2) -- the second mailbox round (order-free rule: largest variable index)
+# decides, and must decide like the oracle's canonical mode.  Also exercises ties in the ratio test (duplicate rows).
+for bk in (8, 64):
+    m, half, seed, K = 64, 96, 11, 400
+    base = bench_lp.dense_lp(m, half, seed)
+    ns = 2 * half
+    n = m + ns
+    A = np.zeros((m, n), order="F")
+    A[:, :half] = base["A"][:, :half]; A[:, half:ns] = base["A"][:, :half]; A[:, ns:] = np.eye(m)
+    A[m // 2:, :ns] = A[:m - m // 2, :ns]                       # duplicate rows => ties in the ratio test too
+    c = np.concatenate([base["c"][:half], base["c"][:half], np.zeros(m)])
+    b = base["b"].copy(); b[m // 2:] = b[:m - m // 2]
+    kind = np.ones(n, dtype=np.uint8); lb = np.zeros(n); ub = np.zeros(n)
+    x0 = np.concatenate([np.zeros(ns), b]); B0 = np.arange(ns, n, dtype=np.int32); N0 = np.arange(ns, dtype=np.int32); Ns0 = np.zeros(ns, dtype=np.uint8)
+    xo, Bo, No, Nso = x0.copy(), B0.copy(), N0.copy(), Ns0.copy()
+    ref = O.solve_with_initial(O.PRIMAL, m, n, A, c, b, kind, lb, ub, xo, Bo, No, Nso, max_iter=K, mode=O.MODE_CANONICAL, trace_cap=K)
+    o = N.default_opts(K, engine=N.ENGINE_TABLEAU, tie_rule=N.TIES_CANONICAL, check_every=8, block_k=bk)
+    tr = np.zeros(K, dtype=N.TRACE_DTYPE); o.trace = N.ptr(tr); o.trace_cap = K
+    plo, phi = sharded.shard_range(ns, world, rank)
+    Aloc = np.asfortranarray(A[:, N0[plo:phi]])
+    sf = N.StdForm(m, n, N.ptr(Aloc), N.ptr(c), N.ptr(b), N.ptr(kind), N.ptr(lb), N.ptr(ub))
+    xg, Bg, Ng, Nsg = x0.copy(), B0.copy(), N0.copy(), Ns0.copy()
+    pt = N.Point(N.ptr(xg), N.ptr(Bg), N.ptr(Ng), N.ptr(Nsg), None, None, m, ns)
+    ctx.check(N.lib.ellp_b200_sharded_upload_nonbasic(ctx.h, C.byref(sf), C.byref(pt), C.byref(o)))
+    res = N.Result()
+    ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(o), C.byref(res)))
+    ctx.check(N.lib.ellp_b200_download(ctx.h, C.byref(pt)))
+    k = len(ref.trace)
+    good = (res.status == ref.status and res.iters == k and (tr["entering"][:k] == ref.trace["entering"]).all()
+            and (tr["leaving"][:k] == ref.trace["leaving"]).all() and np.array_equal(Bg, Bo) and np.array_equal(Ng, No)
+            and np.allclose(xg, xo, rtol=1e-9, atol=1e-9))
+    print(f"rank {rank}: duplicated columns/rows (cross-rank near-ties) block_k={bk} pivots={res.iters} oracle={k} status={res.status}/{ref.status} ok={good}", flush=True)
+    ok = ok and good
+
 # (3) a size with many CTAs per rank (grid barriers, last-block tickets, many column words on the wire): the peer engine
 # against the single-GPU blocked engine (itself checked against the oracle at small sizes), same LP, same tie rule.
 m, ns, seed, K, bk = 2048, 4096, 5, 160, 32
