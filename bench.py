@@ -31,9 +31,9 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # BASELINE.json configs[4]: "synthetic dense LP 32768x65536 fp64, tableau column-sharded ... at 1/2/4/8 B200"
-    "dense_tableau_32768x65536": dict(m=32768, ns=32768, pivots=640, block_k=64, sample_m=1024, sample_pivots=3),
+    "dense_tableau_32768x65536": dict(m=32768, ns=32768, pivots=672, block_k=56, sample_m=1024, sample_pivots=3),
     # north_star target size: "for a 16384x32768 dense LP, the row-reduction kernel sustains >= 70% of HBM bandwidth"
-    "dense_tableau_16384x32768": dict(m=16384, ns=16384, pivots=640, block_k=64, sample_m=1024, sample_pivots=3),
+    "dense_tableau_16384x32768": dict(m=16384, ns=16384, pivots=672, block_k=48, sample_m=1024, sample_pivots=3),
     "dense_tableau_4096x12288": dict(m=4096, ns=8192, pivots=960, block_k=48, sample_m=512, sample_pivots=6),
     # BASELINE.json configs[2] shape: dense 4096x8192 (Gte rows => standard form 4096x12288), DUAL simplex, revised engine
     # (explicit basis inverse).  The entering/leaving rules are the reference's (steepest edge is not built yet).

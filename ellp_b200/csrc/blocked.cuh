@@ -734,4 +734,114 @@ __global__ void __launch_bounds__(kFlush3Threads, 1) k_blk_flush3(double* __rest
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K3b, version 4 (tensor-bound regime, k >= ~40): same ring / fragment layout as k_blk_flush3, but SIXTEEN consumer warps per
+// SM (CTA tile 128 rows x 128 columns per step, warps 4 x 4, warp tile 32 x 32) with ONE register tile per warp.  ncu on
+// version 3 showed 40 % of the warp samples in the fixed-latency wait behind each DMMA: a warp cannot issue DMMAs back to
+// back, so two warps per scheduler leave the fp64 tensor pipe ~25 % idle; four warps per scheduler saturate it, and the
+// tile loads of one warp hide behind the DMMA phases of the other three (no register prefetch needed: 112 registers).
+// ------------------------------------------------------------------------------------------------
+constexpr int kFlush4Cols = 128;
+constexpr int kFlush4SV = kFlush4Cols + 4;
+constexpr int kFlush4Threads = 544;  // 16 consumer warps + 1 producer warp
+inline int blk_flush4_stages(int K4) { return K4 <= 40 ? 3 : 2; }
+inline size_t blk_flush4_smem_bytes(int K4) { return sizeof(double) * (size_t)K4 * (kFlushSU + blk_flush4_stages(K4) * kFlush4SV) + 16 * 3; }
+
+template <bool STREAM>
+__global__ void __launch_bounds__(kFlush4Threads, 1) k_blk_flush4(double* __restrict__ T, int64_t ld, int R, int C, const double* __restrict__ U,
+                                                                  const double* __restrict__ V, int64_t ldv, int cnt, int col_steps, int stages) {
+    extern __shared__ __align__(16) double blk_smem[];
+    const int K4 = (cnt + 3) & ~3;
+    double* sU = blk_smem;                         // sU[j][row] = -U[row0 + row, j]
+    double* sVr = blk_smem + K4 * kFlushSU;        // ring: sV[stage][j][col] = V[j, col0 + col]
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(sVr + (size_t)stages * K4 * kFlush4SV);
+    unsigned long long* empty = full + 3;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * kFlushRows;
+    const int wr = (warp & 3) * 32, wc = ((warp >> 2) & 3) * 32;
+    const int fq = lane >> 2, fk = lane & 3;
+    const int ksteps = K4 >> 2;
+    const int64_t step0 = (int64_t)blockIdx.y * col_steps;
+    const int64_t steps_total = (C + kFlush4Cols - 1) / kFlush4Cols;
+    const int nsteps = (int)max((int64_t)0, min((int64_t)col_steps, steps_total - step0));
+    if (nsteps == 0) return;
+    const unsigned tile_bytes = (unsigned)cnt * kFlush4Cols * (unsigned)sizeof(double);
+    if (tid == 0) {
+        for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 16); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int e = tid; e < K4 * kFlushRows; e += kFlush4Threads) {
+        const int j = e >> 7, i = e & (kFlushRows - 1);
+        sU[j * kFlushSU + i] = (j < cnt && row0 + i < R) ? -U[(int64_t)j * ld + row0 + i] : 0.;
+    }
+    for (int e = tid; e < stages * (K4 - cnt) * kFlush4SV; e += kFlush4Threads) {  // rows cnt .. K4-1 are never copied: zero them once
+        const int slot = e / ((K4 - cnt) * kFlush4SV), rem = e - slot * (K4 - cnt) * kFlush4SV;
+        sVr[(size_t)slot * K4 * kFlush4SV + (size_t)cnt * kFlush4SV + rem] = 0.;
+    }
+    __syncthreads();  // the only block-wide barrier
+    if (warp == 16) {  // producer: V tile of step t -> ring slot t % stages, one 1 KB row per lane and copy
+        for (int t = 0; t < nsteps; ++t) {
+            const int slot = t % stages, use = t / stages;
+            if (lane == 0) {
+                if (use > 0) mbar_wait(&empty[slot], (unsigned)((use - 1) & 1));
+                mbar_arrive_expect_tx(&full[slot], tile_bytes);
+            }
+            __syncwarp();
+            double* dst = sVr + (size_t)slot * K4 * kFlush4SV;
+            const double* src = V + (step0 + t) * kFlush4Cols;
+            for (int j = lane; j < cnt; j += 32) bulk_g2s(dst + j * kFlush4SV, src + (int64_t)j * ldv, kFlush4Cols * (unsigned)sizeof(double), &full[slot]);
+        }
+        return;
+    }
+    for (int s = 0; s < nsteps; ++s) {
+        const int64_t col0 = (step0 + s) * kFlush4Cols;
+        double2 acc[4][4];
+#pragma unroll
+        for (int ct = 0; ct < 4; ++ct) {
+            const int64_t c = col0 + wc + ct * 8 + fq;
+#pragma unroll
+            for (int rt = 0; rt < 4; ++rt) {
+                const int64_t r = row0 + wr + rt * 8 + 2 * fk;
+                if (c < C && r < R) {
+                    const double* p = T + c * ld + r;
+                    acc[ct][rt] = STREAM ? ld_f64x2_stream(p) : ld_f64x2(p);
+                } else {
+                    acc[ct][rt] = make_double2(0., 0.);
+                }
+            }
+        }
+        const int slot = s % stages;
+        mbar_wait(&full[slot], (unsigned)((s / stages) & 1));
+        const double* sV = sVr + (size_t)slot * K4 * kFlush4SV;
+#pragma unroll 2
+        for (int ks = 0; ks < ksteps; ++ks) {
+            double a[4], b[4];
+            const int j = ks * 4 + fk;
+#pragma unroll
+            for (int ct = 0; ct < 4; ++ct) a[ct] = sV[j * kFlush4SV + wc + ct * 8 + fq];
+#pragma unroll
+            for (int rt = 0; rt < 4; ++rt) b[rt] = sU[j * kFlushSU + wr + rt * 8 + fq];
+#pragma unroll
+            for (int ct = 0; ct < 4; ++ct)
+#pragma unroll
+                for (int rt = 0; rt < 4; ++rt) dmma_m8n8k4(acc[ct][rt].x, acc[ct][rt].y, a[ct], b[rt]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
+#pragma unroll
+        for (int ct = 0; ct < 4; ++ct) {
+            const int64_t c = col0 + wc + ct * 8 + fq;
+#pragma unroll
+            for (int rt = 0; rt < 4; ++rt) {
+                const int64_t r = row0 + wr + rt * 8 + 2 * fk;
+                if (c < C && r < R) {
+                    double* p = T + c * ld + r;
+                    if (STREAM) st_f64x2_stream(p, acc[ct][rt]);
+                    else st_f64x2(p, acc[ct][rt]);
+                }
+            }
+        }
+    }
+}
+
 }  // namespace ellp

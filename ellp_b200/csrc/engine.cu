@@ -98,7 +98,9 @@ struct ellp_b200_ctx {
     int blk_kmax = 0;             // slots allocated for the blocked (deferred rank-k) tableau engine; 0 = rank-1 engine only
     int blk_fill = 0;             // slots used since the last flush
     int flush_col_steps = 8;      // column steps (of 64 columns) per CTA of k_blk_flush
-    int flush_kernel = 3;         // tuning: 1 = k_blk_flush (2 CTAs/SM), 2 = k_blk_flush2 (register prefetch, 1 CTA/SM), 3 = k_blk_flush3 (+ bulk-copy ring)
+    int flush_kernel = 0;         // tuning: 0 = auto (4 for k >= flush4_min_k, else 3), 1 = k_blk_flush (2 CTAs/SM), 2 = k_blk_flush2 (register
+                                  // prefetch, 1 CTA/SM), 3 = k_blk_flush3 (+ bulk-copy ring), 4 = k_blk_flush4 (16 consumer warps, tensor-bound regime)
+    int flush4_min_k = 40;
     bool flush_attrs_set = false;
     int flush2_col_steps = 32;    // column steps per CTA of k_blk_flush2
     int coop_pivots = 2;          // blocked engine: 2 = k_blk_pivots_fused (2 barriers per pivot), 1 = k_blk_pivots (4 barriers), 0 = five kernels per pivot
@@ -241,7 +243,7 @@ void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap, bool tableau, int blk
         lp.nT = lp.condensed ? (int32_t)nN : (int32_t)n;
         lp.T = lp.condensed ? a.take<double>(ld * std::max<size_t>(nN, 1)) : const_cast<double*>(lp.A);
         lp.dj = a.take<double>(n);
-        lp.ldv = (int64_t)align_up((size_t)std::max<int32_t>(lp.nT, 1), 64);  // whole 64-column tiles: k_blk_flush3 bulk-copies V rows unguarded
+        lp.ldv = (int64_t)align_up((size_t)std::max<int32_t>(lp.nT, 1), 128);  // whole 64-column tiles: k_blk_flush3 bulk-copies V rows unguarded
         lp.coop = a.take<double>(6 * 1024);
         lp.U = blk_kmax > 0 ? a.take<double>(ld * (size_t)blk_kmax) : nullptr;
         lp.V = blk_kmax > 0 ? a.take<double>((size_t)lp.ldv * (size_t)blk_kmax) : nullptr;
@@ -249,7 +251,7 @@ void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap, bool tableau, int blk
         // revised engine: V = row-major block row of the blocked LU (operand of the rank-kPanel trailing update),
         // coop = publication slots of the cooperative panel factorisation (refactor.cuh)
         lp.U = nullptr;
-        lp.ldv = (int64_t)align_up(2 * m, 64);
+        lp.ldv = (int64_t)align_up(2 * m, 128);
         lp.V = a.take<double>((size_t)kPanel * (size_t)lp.ldv);
         lp.coop = a.take<double>(lu_panel_pub_doubles(160));
         lp.condensed = 0;
@@ -340,11 +342,16 @@ int gemv_grid(int ncols) { return std::max(1, std::min((ncols + 7) / 8, 148 * 32
 // buffer with a block barrier per step, one CTA per SM; 1 = two CTAs per SM without register prefetch.
 void launch_rankk(ellp_b200_ctx* ctx, double* E, int64_t ld, int R, int C, const double* U, const double* V, int64_t ldv, int cnt) {
     const int K4 = (cnt + 3) & ~3;
-    const int steps_total = (C + kFlushCols - 1) / kFlushCols;
     int kern = ctx->flush_kernel;
-    const bool bulk_ok = (ldv % 2 == 0) && ((reinterpret_cast<uintptr_t>(V) & 15) == 0) && ((int64_t)steps_total * kFlushCols <= ldv);
-    if (kern == 3 && !bulk_ok) kern = 2;
-    const size_t smem = kern == 3 ? blk_flush3_smem_bytes(K4) : (kern == 2 ? blk_flush2_smem_bytes(K4) : blk_flush_smem_bytes(K4));
+    // auto (measured at 32768^2, profiles/r01_flush_kernel_sweeps.jsonl): the 16-warp kernel wins for 40 <= k <= 56 (3 or 2 ring
+    // stages fit next to -U), the register-prefetching kernel below (HBM-bound) and at k > 56 (only two wide stages would fit)
+    if (kern == 0) kern = (cnt >= ctx->flush4_min_k && cnt <= 56) ? 4 : 3;
+    const bool base_ok = (ldv % 2 == 0) && ((reinterpret_cast<uintptr_t>(V) & 15) == 0);
+    if (kern == 4 && !(base_ok && (int64_t)((C + kFlush4Cols - 1) / kFlush4Cols) * kFlush4Cols <= ldv)) kern = 3;
+    if (kern == 3 && !(base_ok && (int64_t)((C + kFlushCols - 1) / kFlushCols) * kFlushCols <= ldv)) kern = 2;
+    const int cols_per_step = kern == 4 ? kFlush4Cols : kFlushCols;
+    const int steps_total = (C + cols_per_step - 1) / cols_per_step;
+    const size_t smem = kern == 4 ? blk_flush4_smem_bytes(K4) : (kern == 3 ? blk_flush3_smem_bytes(K4) : (kern == 2 ? blk_flush2_smem_bytes(K4) : blk_flush_smem_bytes(K4)));
     int col_steps = std::max(1, std::min(kern == 1 ? ctx->flush_col_steps : ctx->flush2_col_steps, steps_total));
     if (kern != 1) {  // one CTA per SM: keep at least ~8 waves of CTAs so the last partial wave stays small (narrow shards)
         const int64_t row_blocks = (R + kFlushRows - 1) / kFlushRows;
@@ -352,7 +359,11 @@ void launch_rankk(ellp_b200_ctx* ctx, double* E, int64_t ld, int R, int C, const
     }
     dim3 grid((unsigned)((R + kFlushRows - 1) / kFlushRows), (unsigned)((steps_total + col_steps - 1) / col_steps));
     const bool stream = (double)R * C * 8.0 > (double)ctx->rank1_stream_min_mb * 1048576.0;
-    if (kern == 3) {
+    if (kern == 4) {
+        const int stages = blk_flush4_stages(K4);
+        if (stream) LAUNCH_SMEM(k_blk_flush4<true>, grid, kFlush4Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps, stages);
+        else LAUNCH_SMEM(k_blk_flush4<false>, grid, kFlush4Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps, stages);
+    } else if (kern == 3) {
         if (stream) LAUNCH_SMEM(k_blk_flush3<true>, grid, kFlush3Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
         else LAUNCH_SMEM(k_blk_flush3<false>, grid, kFlush3Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
     } else if (kern == 2) {
@@ -373,6 +384,9 @@ int flush_attrs(ellp_b200_ctx* ctx) {
     CUDA_TRY(cudaFuncSetAttribute(k_blk_flush2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush2_smem_bytes(kBlkMax)));
     CUDA_TRY(cudaFuncSetAttribute(k_blk_flush3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush3_smem_bytes(kBlkMax)));
     CUDA_TRY(cudaFuncSetAttribute(k_blk_flush3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush3_smem_bytes(kBlkMax)));
+    const int smem4 = (int)std::max(blk_flush4_smem_bytes(kBlkMax), blk_flush4_smem_bytes(40));
+    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
+    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
     ctx->flush_attrs_set = true;
     return ELLP_OK;
 }
@@ -600,7 +614,7 @@ void carve_peer(Arena& a, DevLP& lp, int64_t trace_cap, int blk_kmax) {
     lp.T = a.take<double>(ld * nT);
     lp.A = lp.T;  // the starting basis is the identity: T = A_N; the constraint matrix is not kept separately
     lp.dj = a.take<double>(nT + 8);
-    lp.ldv = (int64_t)align_up(nT, 64);
+    lp.ldv = (int64_t)align_up(nT, 128);
     lp.coop = a.take<double>(6 * 1024);
     lp.U = a.take<double>(ld * (size_t)blk_kmax);
     lp.V = a.take<double>((size_t)lp.ldv * (size_t)blk_kmax);
@@ -941,6 +955,7 @@ int ellp_b200_set_tuning(ellp_b200_ctx* ctx, const char* key, int value) {
     else if (!std::strcmp(key, "refactor_panel")) ctx->refactor_panel = value;
     else if (!std::strcmp(key, "flush_col_steps")) { ctx->flush_col_steps = std::max(1, value); ctx->flush2_col_steps = std::max(1, value); }
     else if (!std::strcmp(key, "flush_kernel")) ctx->flush_kernel = value;
+    else if (!std::strcmp(key, "flush4_min_k")) ctx->flush4_min_k = value;
     else if (!std::strcmp(key, "coop_pivots")) ctx->coop_pivots = value;
     else if (!std::strcmp(key, "peer_exchange")) ctx->peer_exchange = value;
     else if (!std::strcmp(key, "coop_threads")) ctx->coop_threads = value;
@@ -1796,7 +1811,7 @@ int ellp_b200_rankk_update(ellp_b200_ctx* ctx, double* E, int64_t R, int64_t C, 
     double *dE = nullptr, *dU = nullptr, *dV = nullptr;
     CUDA_TRY(cudaMalloc(&dE, sizeof(double) * ldp * C));
     CUDA_TRY(cudaMalloc(&dU, sizeof(double) * ldp * k));
-    const int64_t ldvp = (int64_t)align_up((size_t)C, 64);  // rows of V padded to whole 64-column tiles (k_blk_flush3)
+    const int64_t ldvp = (int64_t)align_up((size_t)C, 128);  // rows of V padded to whole 64-column tiles (k_blk_flush3)
     CUDA_TRY(cudaMalloc(&dV, sizeof(double) * ldvp * k));
     CUDA_TRY(cudaMemset(dE, 0, sizeof(double) * ldp * C));
     CUDA_TRY(cudaMemset(dU, 0, sizeof(double) * ldp * k));
