@@ -103,7 +103,9 @@ __global__ void __launch_bounds__(256) k_blk_row(DevLP lp, int slot, PivotState*
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2 (cooperative): up to `npiv` complete primal pivots of the blocked engine in ONE launch.  The five dependent
+// Helpers of the cooperative pivot kernel (k_blk_pivots_fused, peer.cuh): up to `npiv` complete primal pivots of the blocked engine in ONE launch.
+// (The first cooperative version -- five phases, four grid barriers per pivot -- is described here; the fused kernel keeps the
+// phases but needs two barriers, see peer.cuh.)  The five dependent
 // kernels of an iteration (price, select, column + ratios, ratio pick, row + slot) become phases of a persistent
 // grid separated by grid-wide barriers, so an iteration costs four barriers instead of five launches:
 //   A  Dantzig keys over the nonbasic positions + per-block (best, second best) key            | barrier
@@ -196,131 +198,6 @@ __device__ __forceinline__ void blk_zero_slot(const DevLP& lp, int slot, int64_t
     for (int64_t t = t0; t < tmax; t += stride) {
         if (t < lp.ld) Uslot[t] = 0.;
         if (t < lp.ldv) Vslot[t] = 0.;
-    }
-}
-
-__global__ void __launch_bounds__(kScanThreads, 1) k_blk_pivots(DevLP lp, int tie_rule, int slot0, int npiv, PivotState* st) {
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
-    extern __shared__ __align__(16) unsigned char scan_smem[];
-    __shared__ Top2Smem s_top;
-    __shared__ double s_vec[kBlkMax];
-    const int tid = threadIdx.x;
-    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + tid, gsize = (int64_t)gridDim.x * blockDim.x;
-    const int G = gridDim.x;
-    double* partA = lp.coop;            // 3 * G: per-block (best key, second best key, position of the best)
-    double* partC = lp.coop + 3 * 1024;  // 3 * G: per-block (smallest ratio, second smallest, basis position of the smallest)
-    const int nN = lp.nN, m = lp.m;
-    bool run = (__ldcg(&st->status) == kRunning);
-    for (int slot = slot0; slot < slot0 + npiv; ++slot) {
-        if (!run) { blk_zero_slot(lp, slot, gtid, gsize); continue; }
-        // ---- A: pricing (primal :189, :253-270)
-        {
-            Top2 t{-1.0, -1.0, -1};
-            for (int64_t j = gtid; j < nN; j += gsize) {
-                const double r = __ldcg(lp.dj + j);
-                const int side = __ldcg(lp.Ns + j);
-                double k = -1.0;
-                if (!(fabs(r) < kEps)) {
-                    if (r > 0. && side == ELLP_NB_UPPER) k = r;
-                    else if (!(r > 0.) && side == ELLP_NB_LOWER) k = -r;
-                    else if (side == ELLP_NB_FREE) k = fabs(r);
-                }
-                lp.key[j] = k;
-                lp.rN[j] = r;
-                if (k != -1.0) top2_push<true>(t, k, (int)j);
-            }
-            t = top2_block<true>(t, &s_top);
-            if (tid == 0) { partA[3 * blockIdx.x] = t.a1; partA[3 * blockIdx.x + 1] = t.a2; partA[3 * blockIdx.x + 2] = (double)t.i1; }
-        }
-        grid.sync();
-        // ---- B: entering variable (primal :271-292)
-        int q_pos;
-        {
-            const Top2 t = top2_grid<true>(partA, G, &s_top);
-            if (t.a1 == -1.0) {  // no candidate: optimal (:289-292); known to every thread
-                if (gtid == 0) { st->status = ELLP_OPTIMAL; st->do_update = 0; st->do_step = 0; }
-                run = false;
-                blk_zero_slot(lp, slot, gtid, gsize);
-                continue;
-            }
-            const bool fast = !(t.a1 - t.a2 < 2. * kEps);
-            if (fast) {
-                q_pos = t.i1;
-                if (gtid == 0) {
-                    st->q_pos = q_pos;
-                    st->q_var = __ldcg(lp.Nv + q_pos);
-                    st->q_side = __ldcg(lp.Ns + q_pos);
-                    st->rq = __ldcg(lp.dj + q_pos);
-                    st->do_update = 0;
-                    st->do_step = 0;
-                }
-            } else {
-                if (blockIdx.x == 0) {
-                    if (tid == 0) { st->do_update = 0; st->do_step = 0; }
-                    select_primal_body(lp.key, lp.rN, lp.Nv, lp.Ns, nN, tie_rule, st, scan_smem);
-                }
-                grid.sync();
-                if (__ldcg(&st->status) != kRunning) { run = false; blk_zero_slot(lp, slot, gtid, gsize); continue; }
-                q_pos = __ldcg(&st->q_pos);
-            }
-        }
-        const int q_var = __ldcg(lp.Nv + q_pos);
-        const bool at_lower = (__ldcg(lp.Ns + q_pos) == ELLP_NB_LOWER);
-        // ---- C: entering column of the current tableau + ratios (primal :295-367)
-        const int cnt = slot;  // pending slots of this block (the host flushes when the block is full)
-        double lmin_basic;
-        {
-            __syncthreads();
-            if (tid < cnt) s_vec[tid] = __ldcg(lp.V + (int64_t)tid * lp.ldv + q_pos);
-            __syncthreads();
-            Top2 t{CUDART_INF, CUDART_INF, -1};
-            for (int64_t i = gtid; i < lp.ld; i += gsize) {
-                double a = __ldcg(lp.T + (int64_t)q_pos * lp.ld + i);
-                for (int j = 0; j < cnt; ++j) a = fma(-__ldcg(lp.U + (int64_t)j * lp.ld + i), s_vec[j], a);
-                lp.dcol[i] = a;
-                if (i < m) {
-                    const double d_i = at_lower ? -a : a;  // :296-300
-                    double lam = -1.0;                      // -1 = skipped (|d_i| < EPS, :321)
-                    if (!(fabs(d_i) < kEps)) {
-                        const int var = __ldcg(lp.Bv + i);
-                        lam = primal_ratio(lp.kind[var], lp.lb[var], lp.ub[var], __ldcg(lp.x + var), d_i);
-                    }
-                    lp.lam[i] = lam;
-                    if (lam != -1.0 && lam < CUDART_INF) top2_push<false>(t, lam, (int)i);
-                }
-            }
-            t = top2_block<false>(t, &s_top);
-            if (tid == 0) { partC[3 * blockIdx.x] = t.a1; partC[3 * blockIdx.x + 1] = t.a2; partC[3 * blockIdx.x + 2] = (double)t.i1; }
-        }
-        grid.sync();
-        // ---- D: leaving row / bound flip (primal :305-434, :205-232)
-        {
-            Top2 t = top2_grid<false>(partC, G, &s_top);
-            lmin_basic = t.a1;
-            const int kq = lp.kind[q_var];  // :305-311
-            const double lambda0 = (kq == ELLP_TWOSIDED) ? (lp.ub[q_var] - lp.lb[q_var]) : (kq == ELLP_FIXED ? 0. : CUDART_INF);
-            if (lambda0 < CUDART_INF) {
-                Top2 o{lambda0, CUDART_INF, -1};
-                // the entering variable's own range takes part like one more candidate (index -1 = bound flip)
-                if (lambda0 < t.a1) { t.a2 = t.a1; t.a1 = lambda0; t.i1 = -1; }
-                else if (lambda0 < t.a2) t.a2 = lambda0;
-                (void)o;
-            }
-            const bool fast = !(t.a1 < CUDART_INF) || !(t.a2 < t.a1 + 2. * kEps);
-            if (fast) {
-                if (gtid == 0) ratio_commit(lp, st, t.i1, t.a1, at_lower, q_var);
-            } else if (blockIdx.x == 0) {
-                if (tid == 0) st->lmin_bits = __double_as_longlong(lmin_basic);
-                __syncthreads();
-                ratio_pick_body(lp, tie_rule, st, scan_smem);
-            }
-        }
-        grid.sync();
-        // ---- E: step, pivot row, reduced costs, new slot (primal :408-417 + the deferred row reduction)
-        blk_row_body(lp, slot, st, gtid, gsize, s_vec);
-        grid.sync();
-        run = (__ldcg(&st->status) == kRunning);
     }
 }
 
@@ -447,132 +324,16 @@ __global__ void __launch_bounds__(256, 2) k_blk_flush(double* __restrict__ T, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3b, software-pipelined: same tiling and fragment layout as k_blk_flush, but one CTA per SM with TWO register tiles
-// per warp: the 16 x 16-byte loads of column step s+1 are issued before the DMMA sequence of step s starts, so every
-// warp keeps 8 KB in flight for the whole time it occupies the tensor pipe (64 KB per SM, enough to cover the HBM
-// latency-bandwidth product) instead of alternating "load -> wait -> mma -> store".  V is double-buffered by cp.async
-// for every K <= 64 (one CTA per SM leaves room for 137 KB).  Bit-identical results to k_blk_flush (same operation
-// order per element).
-// ------------------------------------------------------------------------------------------------
-inline size_t blk_flush2_smem_bytes(int K4) { return sizeof(double) * (size_t)K4 * (kFlushSU + 2 * kFlushSV); }
-
-template <bool STREAM>
-__global__ void __launch_bounds__(256, 1) k_blk_flush2(double* __restrict__ T, int64_t ld, int R, int C, const double* __restrict__ U,
-                                                       const double* __restrict__ V, int64_t ldv, int cnt, int col_steps) {
-    extern __shared__ __align__(16) double blk_smem[];
-    const int K4 = (cnt + 3) & ~3;
-    double* sU = blk_smem;                         // sU[j][row] = -U[row0 + row, j]
-    double* sV0 = blk_smem + K4 * kFlushSU;        // sV[j][col] = V[j, col0 + col]
-    double* sV1 = sV0 + K4 * kFlushSV;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t row0 = (int64_t)blockIdx.x * kFlushRows;
-    const int wr = (warp & 3) * 32, wc = (warp >> 2) * 32;
-    const int fq = lane >> 2, fk = lane & 3;
-    const int ksteps = K4 >> 2;
-    const int64_t step0 = (int64_t)blockIdx.y * col_steps;
-    const int64_t steps_total = (C + kFlushCols - 1) / kFlushCols;
-    const int nsteps = (int)max((int64_t)0, min((int64_t)col_steps, steps_total - step0));
-    if (nsteps == 0) return;
-    const bool v_aligned = ((ldv & 1) == 0) && ((reinterpret_cast<uintptr_t>(V) & 15) == 0);
-
-    auto stage_v = [&](int s) {
-        double* sV = (s & 1) ? sV1 : sV0;
-        const int64_t col0 = (step0 + s) * kFlushCols;
-        if (v_aligned && col0 + kFlushCols <= C) {
-            for (int e = tid; e < K4 * (kFlushCols / 2); e += 256) {
-                const int j = e >> 5, c2 = (e & 31) * 2;
-                double* dst = sV + j * kFlushSV + c2;
-                if (j < cnt) cp_async16(dst, V + (int64_t)j * ldv + col0 + c2);
-                else { dst[0] = 0.; dst[1] = 0.; }
-            }
-        } else {
-            for (int e = tid; e < K4 * kFlushCols; e += 256) {
-                const int j = e >> 6, c = e & (kFlushCols - 1);
-                sV[j * kFlushSV + c] = (j < cnt && col0 + c < C) ? V[(int64_t)j * ldv + col0 + c] : 0.;
-            }
-        }
-        cp_async_commit();
-    };
-    auto load_tile = [&](double2 (&acc)[4][4], int s) {
-        const int64_t col0 = (step0 + s) * kFlushCols;
-#pragma unroll
-        for (int ct = 0; ct < 4; ++ct) {
-            const int64_t c = col0 + wc + ct * 8 + fq;
-#pragma unroll
-            for (int rt = 0; rt < 4; ++rt) {
-                const int64_t r = row0 + wr + rt * 8 + 2 * fk;
-                if (c < C && r < R) {
-                    const double* p = T + c * ld + r;
-                    acc[ct][rt] = STREAM ? ld_f64x2_stream(p) : ld_f64x2(p);
-                } else {
-                    acc[ct][rt] = make_double2(0., 0.);
-                }
-            }
-        }
-    };
-    auto mma_store = [&](double2 (&acc)[4][4], int s) {
-        const double* sV = (s & 1) ? sV1 : sV0;
-#pragma unroll 2
-        for (int ks = 0; ks < ksteps; ++ks) {
-            double a[4], b[4];
-            const int j = ks * 4 + fk;
-#pragma unroll
-            for (int ct = 0; ct < 4; ++ct) a[ct] = sV[j * kFlushSV + wc + ct * 8 + fq];
-#pragma unroll
-            for (int rt = 0; rt < 4; ++rt) b[rt] = sU[j * kFlushSU + wr + rt * 8 + fq];
-#pragma unroll
-            for (int ct = 0; ct < 4; ++ct)
-#pragma unroll
-                for (int rt = 0; rt < 4; ++rt) dmma_m8n8k4(acc[ct][rt].x, acc[ct][rt].y, a[ct], b[rt]);
-        }
-        const int64_t col0 = (step0 + s) * kFlushCols;
-#pragma unroll
-        for (int ct = 0; ct < 4; ++ct) {
-            const int64_t c = col0 + wc + ct * 8 + fq;
-#pragma unroll
-            for (int rt = 0; rt < 4; ++rt) {
-                const int64_t r = row0 + wr + rt * 8 + 2 * fk;
-                if (c < C && r < R) {
-                    double* p = T + c * ld + r;
-                    if (STREAM) st_f64x2_stream(p, acc[ct][rt]);
-                    else st_f64x2(p, acc[ct][rt]);
-                }
-            }
-        }
-    };
-
-    double2 accA[4][4], accB[4][4];
-    stage_v(0);
-    load_tile(accA, 0);
-    for (int e = tid; e < K4 * kFlushRows; e += 256) {
-        const int j = e >> 7, i = e & (kFlushRows - 1);
-        sU[j * kFlushSU + i] = (j < cnt && row0 + i < R) ? -U[(int64_t)j * ld + row0 + i] : 0.;
-    }
-    for (int s = 0; s < nsteps; s += 2) {
-        // even step: tile s in accA, prefetch s+1 into accB
-        if (s + 1 < nsteps) load_tile(accB, s + 1);
-        cp_async_wait<0>();
-        __syncthreads();  // V tile s (and -U) visible; every warp left step s-1, so the other V buffer may be refilled
-        if (s + 1 < nsteps) stage_v(s + 1);
-        mma_store(accA, s);
-        if (s + 1 >= nsteps) break;
-        // odd step: tile s+1 in accB, prefetch s+2 into accA
-        if (s + 2 < nsteps) load_tile(accA, s + 2);
-        cp_async_wait<0>();
-        __syncthreads();
-        if (s + 2 < nsteps) stage_v(s + 2);
-        mma_store(accB, s + 1);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K3b, version 3: k_blk_flush2 without the block-wide barrier per column step.  The V tiles travel global -> shared
+// K3b, version 3: k_blk_flush with one CTA per SM, TWO register tiles per warp (the 16 x 16-byte loads of column step s+1 are
+// issued before the DMMA sequence of step s starts: 8 KB in flight per warp for the whole time it occupies the tensor pipe)
+// and no block-wide barrier per column step.  The V tiles travel global -> shared
 // memory as bulk asynchronous copies (cp.async.bulk, the TMA copy engine: one 512-byte row of the tile per copy) into
 // a ring of kFlushStages buffers guarded by mbarriers: full[s] (armed with the expected byte count by the producer
 // lane, completed by the copy engine) and empty[s] (one arrival per warp when it has read the tile).  Warps only
 // meet through those mbarriers, so the two warps of an SM sub-partition drift out of phase and one of them occupies
 // the fp64 tensor pipe while the other issues its tile loads / stores -- with a __syncthreads per step every warp hit
-// the load/store phase at the same time and the tensor pipe idled (k_blk_flush2: 69 % DMMA active at k = 64).
+// the load/store phase at the same time and the tensor pipe idled (an intermediate version with a barrier per step: 69 % DMMA
+// active at k = 64, profiles/r01_flush_kernel_sweeps.jsonl, flush_kernel = 2 rows).
 // Requires V rows padded to a multiple of 64 columns (the engine allocates ldv that way) and 16-byte alignment.
 // ------------------------------------------------------------------------------------------------
 constexpr int kFlushStages = 3;

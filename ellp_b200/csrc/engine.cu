@@ -98,13 +98,12 @@ struct ellp_b200_ctx {
     int blk_kmax = 0;             // slots allocated for the blocked (deferred rank-k) tableau engine; 0 = rank-1 engine only
     int blk_fill = 0;             // slots used since the last flush
     int flush_col_steps = 8;      // column steps (of 64 columns) per CTA of k_blk_flush
-    int flush_kernel = 0;         // tuning: 0 = auto (4 for k >= flush4_min_k, else 3), 1 = k_blk_flush (2 CTAs/SM), 2 = k_blk_flush2 (register
-                                  // prefetch, 1 CTA/SM), 3 = k_blk_flush3 (+ bulk-copy ring), 4 = k_blk_flush4 (16 consumer warps, tensor-bound regime)
+    int flush_kernel = 0;         // tuning: 0 = auto (4 for k >= flush4_min_k, else 3), 1 = k_blk_flush (2 CTAs/SM, also the fallback for an unpadded V),
+                                  // 3 = k_blk_flush3 (register prefetch + bulk-copy ring), 4 = k_blk_flush4 (16 consumer warps, tensor-bound regime)
     int flush4_min_k = 40;
     bool flush_attrs_set = false;
-    int flush2_col_steps = 32;    // column steps per CTA of k_blk_flush2
-    int coop_pivots = 2;          // blocked engine: 2 = k_blk_pivots_fused (2 barriers per pivot), 1 = k_blk_pivots (4 barriers), 0 = five kernels per pivot
-    int coop_grid = 0;            // co-resident CTAs of k_blk_pivots (0 = not yet queried)
+    int flush2_col_steps = 32;    // column steps per CTA of k_blk_flush3 / k_blk_flush4
+    int coop_pivots = 1;          // blocked engine: 1 = k_blk_pivots_fused (one cooperative launch per block of pivots), 0 = five kernels per pivot
     // peer-memory sharded engine (peer.cuh): condensed tableau split by nonbasic position, exchange fused into the pivot kernel
     bool a_resident = true;       // false after the condensed fast upload: only T = A_N is on the device
     bool peer_mode = false;       // the resident LP uses the peer layout
@@ -338,8 +337,8 @@ void launch_rank1(ellp_b200_ctx* ctx, double* E, int64_t ld, int R, int C, const
 int gemv_grid(int ncols) { return std::max(1, std::min((ncols + 7) / 8, 148 * 32)); }
 
 // One launch of the rank-k row reduction E -= U V (K3b).  Kernel choice (tuning key "flush_kernel"): 3 = bulk-copy /
-// mbarrier ring, one CTA per SM (needs V rows padded to whole 64-column tiles, 16-byte aligned); 2 = cp.async double
-// buffer with a block barrier per step, one CTA per SM; 1 = two CTAs per SM without register prefetch.
+// mbarrier ring, one CTA per SM (needs V rows padded to whole tiles, 16-byte aligned); 4 = the same ring with 16 consumer warps;
+// 1 = two CTAs per SM without register prefetch (any V).
 void launch_rankk(ellp_b200_ctx* ctx, double* E, int64_t ld, int R, int C, const double* U, const double* V, int64_t ldv, int cnt) {
     const int K4 = (cnt + 3) & ~3;
     int kern = ctx->flush_kernel;
@@ -348,10 +347,11 @@ void launch_rankk(ellp_b200_ctx* ctx, double* E, int64_t ld, int R, int C, const
     if (kern == 0) kern = (cnt >= ctx->flush4_min_k && cnt <= 56) ? 4 : 3;
     const bool base_ok = (ldv % 2 == 0) && ((reinterpret_cast<uintptr_t>(V) & 15) == 0);
     if (kern == 4 && !(base_ok && (int64_t)((C + kFlush4Cols - 1) / kFlush4Cols) * kFlush4Cols <= ldv)) kern = 3;
-    if (kern == 3 && !(base_ok && (int64_t)((C + kFlushCols - 1) / kFlushCols) * kFlushCols <= ldv)) kern = 2;
+    if (kern == 3 && !(base_ok && (int64_t)((C + kFlushCols - 1) / kFlushCols) * kFlushCols <= ldv)) kern = 1;
+    if (kern == 2) kern = 1;
     const int cols_per_step = kern == 4 ? kFlush4Cols : kFlushCols;
     const int steps_total = (C + cols_per_step - 1) / cols_per_step;
-    const size_t smem = kern == 4 ? blk_flush4_smem_bytes(K4) : (kern == 3 ? blk_flush3_smem_bytes(K4) : (kern == 2 ? blk_flush2_smem_bytes(K4) : blk_flush_smem_bytes(K4)));
+    const size_t smem = kern == 4 ? blk_flush4_smem_bytes(K4) : (kern == 3 ? blk_flush3_smem_bytes(K4) : blk_flush_smem_bytes(K4));
     int col_steps = std::max(1, std::min(kern == 1 ? ctx->flush_col_steps : ctx->flush2_col_steps, steps_total));
     if (kern != 1) {  // one CTA per SM: keep at least ~8 waves of CTAs so the last partial wave stays small (narrow shards)
         const int64_t row_blocks = (R + kFlushRows - 1) / kFlushRows;
@@ -366,9 +366,6 @@ void launch_rankk(ellp_b200_ctx* ctx, double* E, int64_t ld, int R, int C, const
     } else if (kern == 3) {
         if (stream) LAUNCH_SMEM(k_blk_flush3<true>, grid, kFlush3Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
         else LAUNCH_SMEM(k_blk_flush3<false>, grid, kFlush3Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
-    } else if (kern == 2) {
-        if (stream) LAUNCH_SMEM(k_blk_flush2<true>, grid, 256, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
-        else LAUNCH_SMEM(k_blk_flush2<false>, grid, 256, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
     } else {
         if (stream) LAUNCH_SMEM(k_blk_flush<true>, grid, 256, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
         else LAUNCH_SMEM(k_blk_flush<false>, grid, 256, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
@@ -380,8 +377,6 @@ int flush_attrs(ellp_b200_ctx* ctx) {
     const int smem1 = (int)std::max(blk_flush_smem_bytes(48), blk_flush_smem_bytes(kBlkMax));
     CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
-    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush2_smem_bytes(kBlkMax)));
-    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush2_smem_bytes(kBlkMax)));
     CUDA_TRY(cudaFuncSetAttribute(k_blk_flush3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush3_smem_bytes(kBlkMax)));
     CUDA_TRY(cudaFuncSetAttribute(k_blk_flush3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush3_smem_bytes(kBlkMax)));
     const int smem4 = (int)std::max(blk_flush4_smem_bytes(kBlkMax), blk_flush4_smem_bytes(40));
@@ -523,29 +518,6 @@ void launch_flush(ellp_b200_ctx* ctx, bool profile, size_t* ev_used) {
     if (profile && ev_used && *ev_used + 2 <= ctx->ev.size()) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
     launch_rankk(ctx, lp.T, lp.ld, (int)lp.ld, lp.nT, lp.U, lp.V, lp.ldv, cnt);
     if (profile && ev_used && (*ev_used & 1)) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
-}
-
-// blocked engine, single GPU: `npiv` pivots (slots blk_fill .. blk_fill + npiv - 1) in one cooperative launch
-int launch_coop_pivots(ellp_b200_ctx* ctx, const ellp_opts* o, int npiv) {
-    DevLP& lp = ctx->lp;
-    if (ctx->coop_grid == 0) {
-        CUDA_TRY(cudaFuncSetAttribute(k_blk_pivots, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmemBytes));
-        int sms = 0, per_sm = 0, coop = 0;
-        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
-        CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_blk_pivots, kScanThreads, kScanSmemBytes));
-        ctx->coop_grid = (coop && per_sm > 0) ? std::min(1024, sms * per_sm) : -1;
-    }
-    if (ctx->coop_grid < 0) return set_err(ctx, ELLP_E_CUDA, "cooperative launch unavailable (set tuning coop_pivots = 0)");
-    const int64_t work = std::max<int64_t>(std::max<int64_t>(lp.ld, lp.ldv), lp.nN);
-    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->coop_grid, (work + kScanThreads - 1) / kScanThreads));
-    int tie = o->tie_rule, slot0 = ctx->blk_fill;
-    PivotState* st = ctx->d_st;
-    void* args[] = {(void*)&lp, (void*)&tie, (void*)&slot0, (void*)&npiv, (void*)&st};
-    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_blk_pivots, dim3(grid), dim3(kScanThreads), args, (size_t)kScanSmemBytes, ctx->stream));
-    ctx->launches++;
-    ctx->blk_fill += npiv;
-    return ELLP_OK;
 }
 
 // ---- peer-memory sharded engine (peer.cuh) -------------------------------------------------------------------------
@@ -1526,13 +1498,13 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
             // cooperative path: whole blocks of pivots per launch, a flush after every full block
             int left = std::max(batch, blk);
             if (o->max_iter - h.pivots < (uint64_t)left) left = (int)std::max<uint64_t>(1, o->max_iter - h.pivots);
-            if (ctx->coop_pivots == 2 && ctx->peer_cap < lp.ld) {  // exchange buffer of the fused kernel (this GPU's own memory here)
+            if (ctx->peer_cap < lp.ld) {  // exchange buffer of the fused kernel (this GPU's own memory here)
                 if (ctx->nranks == 1) rc_loop = peer_setup(ctx, lp.ld);
                 else rc_loop = set_err(ctx, ELLP_E_ARG, "exchange buffer too small for a single-GPU LP on a multi-rank context");
             }
             while (left > 0 && !rc_loop) {
                 const int npiv = std::min(left, blk - ctx->blk_fill);
-                rc_loop = ctx->coop_pivots == 2 ? launch_coop_pivots_peer(ctx, o, npiv, true) : launch_coop_pivots(ctx, o, npiv);
+                rc_loop = launch_coop_pivots_peer(ctx, o, npiv, true);
                 left -= npiv;
                 if (!rc_loop && ctx->blk_fill >= blk) launch_flush(ctx, profile, &ev_used);
             }

@@ -1,4 +1,4 @@
-"""Clocks / power while k_blk_flush2 runs back to back (is the fp64 tensor pipe power-limited?)."""
+"""Clocks / power while the rank-k flush kernels run back to back (is the fp64 tensor pipe power-limited?)."""
 import ctypes as C, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -6,7 +6,7 @@ import bench as BM
 from ellp_b200 import _native as N
 import blk_sweep as B
 ctx = N.Context(0)
-for fk, k, cs in ((2, 64, 32), (2, 48, 32), (1, 32, 8), (1, 24, 8)):
+for fk, k, cs in ((3, 64, 32), (4, 56, 32), (4, 48, 32), (1, 24, 8)):
     ctx.set_tuning("flush_kernel", fk)
     B.flush_point(ctx, 32768, 32768, k, cs, reps=3)
     s = BM.ClockSampler(0); s.Q = s.Q; s.start(); time.sleep(0.3)
