@@ -103,21 +103,12 @@ __global__ void __launch_bounds__(256) k_blk_row(DevLP lp, int slot, PivotState*
 }
 
 // ------------------------------------------------------------------------------------------------
-// Helpers of the cooperative pivot kernel (k_blk_pivots_fused, peer.cuh): up to `npiv` complete primal pivots of the blocked engine in ONE launch.
-// (The first cooperative version -- five phases, four grid barriers per pivot -- is described here; the fused kernel keeps the
-// phases but needs two barriers, see peer.cuh.)  The five dependent
-// kernels of an iteration (price, select, column + ratios, ratio pick, row + slot) become phases of a persistent
-// grid separated by grid-wide barriers, so an iteration costs four barriers instead of five launches:
-//   A  Dantzig keys over the nonbasic positions + per-block (best, second best) key            | barrier
-//   B  every block merges the partials.  The fold of primal :271-286 is order-independent when the second best key
-//      is at least 2 EPS below the best (same criterion as k_select_primal's fast path): the winner is known to every
-//      thread without another barrier.  Otherwise block 0 evaluates the sequential fold (select_primal_body) | barrier
-//   C  entering column of the CURRENT tableau (stale column + pending corrections), ratios, per-block two smallest | barrier
-//   D  merge, add the entering variable's own range (primal :305-311); isolated minimum => thread 0 commits the pivot
-//      (ratio_commit), else block 0 evaluates the fold of :379-399 (ratio_pick_body)            | barrier
-//   E  x step, pivot row, reduced-cost row, new (U, V) slot (blk_row_body)                      | barrier
-// Decisions are bit-identical to the five-kernel path (same arithmetic, same fast-path criteria, same fold code).
-// Launch: cooperative, kScanThreads threads per block, kScanSmemBytes dynamic shared memory, grid <= co-resident CTAs.
+// Helpers of the cooperative pivot kernel (k_blk_pivots_fused, peer.cuh), which runs up to `npiv` complete primal pivots of
+// the blocked engine in ONE launch: the five dependent kernels of an iteration (price, select, column + ratios, ratio pick,
+// row + slot) become phases of a persistent grid.  Every reduction carries (best, second best, index of the best): the tie
+// folds of primal :271-286 / :379-399 are order-independent when the second best is at least 2 EPS away from the best (same
+// criterion as the fast paths of k_select_primal / k_ratio_pick), so the winner is known without evaluating the fold;
+// otherwise one block evaluates it (select_primal_body / ratio_pick_body).  Decisions are identical to the five-kernel path.
 // ------------------------------------------------------------------------------------------------
 struct Top2 {
     double a1, a2;
@@ -137,60 +128,6 @@ template <bool MAX> __device__ __forceinline__ void top2_merge(Top2& t, const To
         if (top2_better<MAX>(o.a1, t.a2)) t.a2 = o.a1;
     }
 }
-struct Top2Smem {
-    double a1[32], a2[32];
-    int i1[32];
-};
-// block-wide merge; the result is valid in every thread
-template <bool MAX> __device__ __forceinline__ Top2 top2_block(Top2 t, Top2Smem* sh) {
-    const unsigned full = 0xffffffffu;
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        Top2 o;
-        o.a1 = __shfl_xor_sync(full, t.a1, off);
-        o.a2 = __shfl_xor_sync(full, t.a2, off);
-        o.i1 = __shfl_xor_sync(full, t.i1, off);
-        // both partners of an xor-shuffle must end with the same triple: merge in a fixed (lane-bit) order
-        Top2 lo = ((threadIdx.x & off) == 0) ? t : o, hi = ((threadIdx.x & off) == 0) ? o : t;
-        top2_merge<MAX>(lo, hi);
-        t = lo;
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    __syncthreads();
-    if (lane == 0) { sh->a1[warp] = t.a1; sh->a2[warp] = t.a2; sh->i1[warp] = t.i1; }
-    __syncthreads();
-    const double worst = MAX ? -1.0 : CUDART_INF;
-    Top2 r;
-    r.a1 = (lane < nw) ? sh->a1[lane] : worst;
-    r.a2 = (lane < nw) ? sh->a2[lane] : worst;
-    r.i1 = (lane < nw) ? sh->i1[lane] : -1;
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        Top2 o;
-        o.a1 = __shfl_xor_sync(full, r.a1, off);
-        o.a2 = __shfl_xor_sync(full, r.a2, off);
-        o.i1 = __shfl_xor_sync(full, r.i1, off);
-        Top2 lo = ((lane & off) == 0) ? r : o, hi = ((lane & off) == 0) ? o : r;
-        top2_merge<MAX>(lo, hi);
-        r = lo;
-    }
-    return r;
-}
-
-// merges the per-block partials part[3*b .. 3*b+2] = (a1, a2, i1) of all `nb` blocks; result valid in every thread
-template <bool MAX> __device__ __forceinline__ Top2 top2_grid(const double* part, int nb, Top2Smem* sh) {
-    const double worst = MAX ? -1.0 : CUDART_INF;
-    Top2 t{worst, worst, -1};
-    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
-        Top2 o;
-        o.a1 = __ldcg(part + 3 * b);
-        o.a2 = __ldcg(part + 3 * b + 1);
-        o.i1 = (int)__ldcg(part + 3 * b + 2);
-        top2_merge<MAX>(t, o);
-    }
-    return top2_block<MAX>(t, sh);
-}
-
 __device__ __forceinline__ void blk_zero_slot(const DevLP& lp, int slot, int64_t t0, int64_t stride) {
     double* Uslot = lp.U + (int64_t)slot * lp.ld;
     double* Vslot = lp.V + (int64_t)slot * lp.ldv;

@@ -175,19 +175,6 @@ template <bool MAX> __device__ __forceinline__ Top2 top2_block_fast(const Top2& 
     buf ^= 1;
     return warp_top2<MAX>(r);
 }
-template <bool MAX> __device__ __forceinline__ Top2 top2_grid_fast(const double* part, int nb, Top2Fast* sh, int& buf) {
-    const double worst = MAX ? -1.0 : CUDART_INF;
-    Top2 t{worst, worst, -1};
-    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
-        Top2 o;
-        o.a1 = __ldcg(part + 3 * b);
-        o.a2 = __ldcg(part + 3 * b + 1);
-        o.i1 = (int)__ldcg(part + 3 * b + 2);
-        top2_merge<MAX>(t, o);
-    }
-    return top2_block_fast<MAX>(t, sh, buf);
-}
-
 // Uniform (replicated in every thread) scalar state of the solve, so that the one thread that does the bookkeeping needs
 // no dependent loads from PivotState: refreshed from st at launch and after every tie-path commit.
 struct PivotRegs {
