@@ -7,10 +7,10 @@ for w in dense_tableau_32768x65536 dense_tableau_16384x32768 dense_tableau_4096x
   timeout 900 python bench.py --workload $w > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err; echo "$w rc=$?"; tail -2 gpurun_out/bench_$w.err; cut -c1-1500 gpurun_out/bench_$w.json
 done
 timeout 600 python bench.py --impl reference > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "reference rc=$?"; cut -c1-600 gpurun_out/bench_reference.json
-CMD="python bench.py --steps 1 --warmup 1 --pivots 128 --no-e2e --no-cpu"
+CMD="python bench.py --steps 1 --warmup 1 --pivots 112 --no-e2e --no-cpu"
 $CMD > gpurun_out/plain_blk.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_blk64_32k.csv $CMD > gpurun_out/ncu_list_blk.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_blk56_32k.csv $CMD > gpurun_out/ncu_list_blk.log 2>&1
 echo "ncu list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:k_blk_flush3 -s 2 -c 1 -o gpurun_out/prof_blk_flush3_k64 $CMD > gpurun_out/ncu_flush.log 2>&1; echo "ncu flush rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:k_blk_pivots_fused -s 2 -c 1 -o gpurun_out/prof_blk_pivots_fused_k64 $CMD > gpurun_out/ncu_pivots.log 2>&1; echo "ncu pivots rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:k_blk_flush4 -s 2 -c 1 -o gpurun_out/prof_blk_flush4_k56 $CMD > gpurun_out/ncu_flush.log 2>&1; echo "ncu flush rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:k_blk_pivots_fused -s 2 -c 1 -o gpurun_out/prof_blk_pivots_fused_k56 $CMD > gpurun_out/ncu_pivots.log 2>&1; echo "ncu pivots rc=$?"
 ls -la gpurun_out/*.ncu-rep
