@@ -77,6 +77,15 @@ struct ellp_b200_ctx {
     double* sendcol = nullptr;  // ld doubles staged for the pivot-column all-reduce (inside the arena)
     uint8_t* d_sides = nullptr; // n_glob bytes: colstat of every column (gathered) / scatter source
     int* d_flag = nullptr;
+    SelScratch* d_sel = nullptr;   // scratch of the multi-block selection kernels (kernels.cuh)
+    // CUDA graph of `graph_iters` iterations of the revised engine (the 8-9 dependent launches of an iteration are
+    // launch-latency bound: replaying them from a graph removes most of the gaps).  Rebuilt when the resident LP or the
+    // rules change; not used with profile = 1 (events around the row reduction).
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_iters = 0;
+    uint64_t graph_key = 0, graph_launches = 0;
+    uint64_t lp_generation = 0;   // bumped by every upload / generate
+    int use_graphs = 1;           // tuning key "cuda_graphs"
     uint64_t pivots_since_refactor = 0;
     PivotState* d_st = nullptr;
     PivotState* h_st = nullptr;  // pinned
@@ -655,6 +664,7 @@ int peer_finish_init(ellp_b200_ctx* ctx) {
            (const uint8_t*)nullptr, (double*)nullptr, (PivotState*)nullptr, 0);
     LAUNCH(k_redcost_pos_local, (lp.nT + 255) / 256, 256, lp.c, lp.Nv, lp.pos_lo, lp.nT, lp.dj);
     ctx->resident = true;
+    ctx->lp_generation++;
     ctx->binv_valid = true;
     ctx->pivots_since_refactor = 0;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -774,13 +784,14 @@ void launch_dual_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, bool profile,
     PivotState* st = ctx->d_st;
     const int m = lp.m, nN = lp.nN;
     const bool dse = o->pricing == ELLP_PRICE_STEEPEST_EDGE;
-    if (dse) LAUNCH(k_dual_leaving_dse, 1, 1024, lp, st);                                     // steepest edge (no reference counterpart)
-    else LAUNCH(k_dual_leaving, 1, 1024, lp, st);                                             // dual :200-236
+    const int sel_m = std::max(1, std::min(kSelMaxBlocks, (m + 255) / 256)), sel_n = std::max(1, std::min(kSelMaxBlocks, (nN + 255) / 256));
+    if (dse) LAUNCH(k_dual_leaving_dse, sel_m, 256, lp, st, ctx->d_sel);                      // steepest edge (no reference counterpart)
+    else LAUNCH(k_dual_leaving, sel_m, 256, lp, st, ctx->d_sel);                              // dual :200-236
     LAUNCH(k_gather_row, (m + 255) / 256, 256, lp.Binv, lp.ld, m, st, lp.rho, 0);             // rho = e_r^T B^-1 (:248-253)
     LAUNCH(k_gemv_t<EPI_PLAIN>, gemv_grid(nN), 256, lp.A, lp.ld, lp.Nv, nN, lp.rho, lp.rN,  // alpha = A_N^T rho (:255)
            (const double*)nullptr, (const uint8_t*)nullptr, (double*)nullptr, st, 0);
     if (o->ratio == ELLP_RATIO_HARRIS) LAUNCH(k_select_dual_harris, 1, 1024, lp, 1e-9, st);
-    else LAUNCH(k_select_dual, 1, 1024, lp, st);                                              // :257-289
+    else LAUNCH(k_select_dual, sel_n, 256, lp, st, ctx->d_sel);                               // :257-289
     dim3 fg((unsigned)((lp.ld + 255) / 256), (unsigned)ctx->KS);
     LAUNCH(k_ftran_partial, fg, 128, lp.Binv, lp.ld, m, lp.A, st, lp.part, ctx->kc);          // :294
     LAUNCH(k_dual_update_vec, (std::max(m, nN) + 255) / 256, 256, lp, ctx->KS, st);           // :296-316
@@ -880,6 +891,7 @@ int ellp_b200_create(int device, ellp_b200_ctx** out) {
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMalloc(&ctx->d_st, sizeof(PivotState)) != cudaSuccess || cudaMalloc(&ctx->d_flag, 4 * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_sel, sizeof(SelScratch)) != cudaSuccess || cudaMemset(ctx->d_sel, 0, sizeof(SelScratch)) != cudaSuccess ||
         cudaMallocHost(&ctx->h_st, sizeof(PivotState)) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
         delete ctx;
@@ -908,6 +920,8 @@ void ellp_b200_destroy(ellp_b200_ctx* ctx) {
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->d_st) cudaFree(ctx->d_st);
     if (ctx->d_flag) cudaFree(ctx->d_flag);
+    if (ctx->d_sel) cudaFree(ctx->d_sel);
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     if (ctx->tlog) cudaFree(ctx->tlog);
     if (ctx->h_st) cudaFreeHost(ctx->h_st);
     cudaStreamDestroy(ctx->stream);
@@ -929,6 +943,7 @@ int ellp_b200_set_tuning(ellp_b200_ctx* ctx, const char* key, int value) {
     else if (!std::strcmp(key, "flush_kernel")) ctx->flush_kernel = value;
     else if (!std::strcmp(key, "flush4_min_k")) ctx->flush4_min_k = value;
     else if (!std::strcmp(key, "coop_pivots")) ctx->coop_pivots = value;
+    else if (!std::strcmp(key, "cuda_graphs")) ctx->use_graphs = value;
     else if (!std::strcmp(key, "peer_exchange")) ctx->peer_exchange = value;
     else if (!std::strcmp(key, "coop_threads")) ctx->coop_threads = value;
     else if (!std::strcmp(key, "coop_ctas_per_sm")) { ctx->coop_ctas_per_sm = value; ctx->coop_threads_cached = 0; }
@@ -1043,6 +1058,7 @@ int ellp_b200_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_poi
     ctx->trace_cap = tcap;
     ctx->solver = solver;
     ctx->resident = true;
+    ctx->lp_generation++;
     ctx->tableau = tableau;
     ctx->blk_kmax = blk;
     ctx->blk_fill = 0;
@@ -1103,6 +1119,7 @@ int ellp_b200_generate_dense_ex(ellp_b200_ctx* ctx, int32_t m, int32_t n_struct,
     ctx->trace_cap = tcap;
     ctx->solver = variant == 0 ? ELLP_PRIMAL : ELLP_DUAL;
     ctx->resident = true;
+    ctx->lp_generation++;
     ctx->tableau = tableau;
     ctx->blk_kmax = blk;
     ctx->blk_fill = 0;
@@ -1199,6 +1216,7 @@ static int sharded_finish_init(ellp_b200_ctx* ctx) {
     LAUNCH(k_gemv_t<EPI_REDCOST>, gemv_grid(lp.n), 256, lp.T, lp.ld, (const int32_t*)nullptr, lp.n, lp.cB, lp.dj, lp.c + lp.col_lo,
            (const uint8_t*)nullptr, (double*)nullptr, (PivotState*)nullptr, 0);
     ctx->resident = true;
+    ctx->lp_generation++;
     ctx->binv_valid = true;
     ctx->pivots_since_refactor = 0;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1471,7 +1489,7 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
     const int blk = (ctx->tableau && ctx->blk_kmax > 0 && o->block_k > 1) ? std::min(o->block_k, ctx->blk_kmax) : 0;
     ctx->blk_fill = 0;
     if (blk > 0) { if (int rc = flush_attrs(ctx)) return rc; }
-    int check_every = o->check_every > 0 ? o->check_every : (lp.m >= 2048 ? 1 : 8);
+    int check_every = o->check_every > 0 ? o->check_every : 8;  // iterations enqueued per host read-back (finished solves make them no-ops)
     int refactor_every = o->refactor_every > 0 ? o->refactor_every : ((lp.m <= 512 && !ctx->tableau) ? 100 : 0);
     if (ctx->peer_mode && ctx->nranks > 1)  // stream-ordered barrier: no rank starts polling before every rank got here
         NCCL_TRY(nccl::api.AllReduce(lp.part, lp.part + 4, 1, nccl::kFloat64, nccl::kSum, ctx->nccl_comm, ctx->stream));
@@ -1508,6 +1526,31 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
                 left -= npiv;
                 if (!rc_loop && ctx->blk_fill >= blk) launch_flush(ctx, profile, &ev_used);
             }
+            batch = 0;
+        }
+        if (batch > 1 && batch == check_every && !ctx->tableau && !ctx->sharded && !profile && ctx->use_graphs) {
+            // revised engine: replay `batch` iterations from a CUDA graph (kernels gate on PivotState::status, so iterations
+            // after the end of the solve are no-ops exactly as with direct launches)
+            const uint64_t key = ctx->lp_generation * 1000003ull + (uint64_t)(ctx->solver * 64 + o->pricing * 16 + o->ratio * 4 + o->tie_rule) * 131ull + (uint64_t)batch;
+            if (!ctx->graph_exec || ctx->graph_key != key) {
+                if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+                cudaGraph_t graph = nullptr;
+                const uint64_t l0 = ctx->launches;
+                CUDA_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+                for (int k = 0; k < batch; ++k) {
+                    if (ctx->solver == ELLP_PRIMAL) launch_primal_iteration(ctx, o, false, &ev_used);
+                    else launch_dual_iteration(ctx, o, false, &ev_used);
+                }
+                CUDA_TRY(cudaStreamEndCapture(ctx->stream, &graph));
+                ctx->graph_launches = ctx->launches - l0;
+                ctx->launches = l0;
+                CUDA_TRY(cudaGraphInstantiate(&ctx->graph_exec, graph, 0));
+                CUDA_TRY(cudaGraphDestroy(graph));
+                ctx->graph_key = key;
+                ctx->graph_iters = batch;
+            }
+            CUDA_TRY(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+            ctx->launches += ctx->graph_launches;
             batch = 0;
         }
         for (int k = 0; k < batch; ++k) {

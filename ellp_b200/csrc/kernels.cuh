@@ -84,6 +84,22 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Sum of the KS split-K partials of row `row` in FIXED order (ks ascending: bitwise deterministic), the loads issued 16 at a
+// time (the additions are a dependent chain anyway; the exposed latency was one L2 round trip per 4 partials).
+__device__ __forceinline__ double sum_partials(const double* __restrict__ part, int64_t ld, int KS, int64_t row) {
+    double a = 0.;
+    int ks = 0;
+    for (; ks + 16 <= KS; ks += 16) {
+        double v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = part[(int64_t)(ks + q) * ld + row];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) a += v[q];
+    }
+    for (; ks < KS; ++ks) a += part[(int64_t)ks * ld + row];
+    return a;
+}
+
 __device__ __forceinline__ double2 ld_f64x2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ double2 ld_f64x2_stream(const double* p) { return __ldcs(reinterpret_cast<const double2*>(p)); }
 __device__ __forceinline__ void st_f64x2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
@@ -422,7 +438,7 @@ __global__ void __launch_bounds__(256) k_ratio_prep(DevLP lp, int KS, int cnt, P
     double lam = -1.0;  // -1 = skipped (|d_i| < EPS, :321)
     if (i < lp.m) {
         double a = 0.;
-        if (KS > 0) { for (int ks = 0; ks < KS; ++ks) a += lp.part[(int64_t)ks * lp.ld + i]; }
+        if (KS > 0) a = sum_partials(lp.part, lp.ld, KS, i);
         else if (KS == 0) {
             a = lp.T[(int64_t)qc * lp.ld + i];
             for (int j = 0; j < cnt; ++j) a = fma(-lp.U[(int64_t)j * lp.ld + i], s_vq[j], a);
@@ -852,17 +868,39 @@ __global__ void k_sum_norms(const double* __restrict__ npart, int64_t ld, int m,
     w[i] = a;
 }
 
+// Scratch of the multi-block selection kernels: per-block partial results + the ticket of the last-block pattern (the block
+// whose arrival completes the grid finishes the selection, so no second launch and no single-CTA scan is needed).
+constexpr int kSelMaxBlocks = 128;
+struct SelScratch {
+    unsigned int ticket;
+    int flag;                      // NaN seen (dual ratio)
+    double val[kSelMaxBlocks];
+    int idx[kSelMaxBlocks];
+};
+__device__ __forceinline__ bool sel_arrive_last(SelScratch* sc, int* s_last) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(&sc->ticket, 1u);
+        *s_last = (t == gridDim.x - 1);
+        if (*s_last) { sc->ticket = 0u; __threadfence(); }
+    }
+    __syncthreads();
+    return *s_last != 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Dual simplex kernels
 // ------------------------------------------------------------------------------------------------
 // dual :200-236 -- first basis position (in B order) whose variable violates its bound by more than EPS
-__global__ void __launch_bounds__(1024) k_dual_leaving(DevLP lp, PivotState* st) {
-    if (threadIdx.x == 0) st->do_update = 0;
+__global__ void __launch_bounds__(256) k_dual_leaving(DevLP lp, PivotState* st, SelScratch* sc) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->do_update = 0;
     if (st->status != kRunning) return;
-    __shared__ int s_min[32];
+    __shared__ int s_min[8];
+    __shared__ int s_last;
     const int tid = threadIdx.x;
     int best = 0x7fffffff;
-    for (int i = tid; i < lp.m; i += blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + tid; i < lp.m; i += gridDim.x * blockDim.x) {
         const int var = lp.Bv[i];
         const double x_i = lp.x[var];
         const int kind = lp.kind[var];
@@ -876,56 +914,58 @@ __global__ void __launch_bounds__(1024) k_dual_leaving(DevLP lp, PivotState* st)
     for (int off = 16; off >= 1; off >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
     if ((tid & 31) == 0) s_min[tid >> 5] = best;
     __syncthreads();
-    if (tid < 32) {
-        best = (tid < (blockDim.x >> 5)) ? s_min[tid] : 0x7fffffff;
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
-        if (tid == 0) {
-            if (best == 0x7fffffff) {
-                st->status = ELLP_OPTIMAL;  // :243-246
-            } else {
-                const int var = lp.Bv[best];
-                const double x_i = lp.x[var];
-                const int kind = lp.kind[var];
-                double delta;
-                int side;
-                if (kind == ELLP_LOWER) { delta = x_i - lp.lb[var]; side = ELLP_NB_LOWER; }
-                else if (kind == ELLP_UPPER) { delta = x_i - lp.ub[var]; side = ELLP_NB_UPPER; }
-                else if (x_i > lp.ub[var] + kEps) { delta = x_i - lp.ub[var]; side = ELLP_NB_UPPER; }
-                else { delta = x_i - lp.lb[var]; side = ELLP_NB_LOWER; }
-                st->r_pos = best;
-                st->leave_var = var;
-                st->delta = delta;
-                st->new_side = side;
-            }
+    if (tid == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best = min(best, s_min[w]);
+        sc->idx[blockIdx.x] = best;
+    }
+    if (!sel_arrive_last(sc, &s_last)) return;
+    if (tid == 0) {  // the first violated position over all blocks: exact min, order-free
+        best = 0x7fffffff;
+        for (int b = 0; b < (int)gridDim.x; ++b) best = min(best, __ldcg(&sc->idx[b]));
+        if (best == 0x7fffffff) {
+            st->status = ELLP_OPTIMAL;  // :243-246
+        } else {
+            const int var = lp.Bv[best];
+            const double x_i = lp.x[var];
+            const int kind = lp.kind[var];
+            double delta;
+            int side;
+            if (kind == ELLP_LOWER) { delta = x_i - lp.lb[var]; side = ELLP_NB_LOWER; }
+            else if (kind == ELLP_UPPER) { delta = x_i - lp.ub[var]; side = ELLP_NB_UPPER; }
+            else if (x_i > lp.ub[var] + kEps) { delta = x_i - lp.ub[var]; side = ELLP_NB_UPPER; }
+            else { delta = x_i - lp.lb[var]; side = ELLP_NB_LOWER; }
+            st->r_pos = best;
+            st->leave_var = var;
+            st->delta = delta;
+            st->new_side = side;
         }
     }
 }
 
 // dual :257-289 -- entering = first minimum of d_j / alpha~_j over eligible nonbasics (exact compare,
 // first in N-position order on equality) == lexicographic min of (ratio, position): order-free.
-__global__ void __launch_bounds__(1024) k_select_dual(DevLP lp, PivotState* st) {
+__global__ void __launch_bounds__(256) k_select_dual(DevLP lp, PivotState* st, SelScratch* sc) {
     if (st->status != kRunning) return;
-    __shared__ double s_t[32];
-    __shared__ int s_p[32];
-    __shared__ int s_nan;
+    __shared__ double s_t[8];
+    __shared__ int s_p[8];
+    __shared__ int s_last;
     const int tid = threadIdx.x;
-    if (tid == 0) s_nan = 0;
-    __syncthreads();
     const bool neg = st->delta < 0.;
     double bt = 0.;
     int bp = 0x7fffffff;
-    for (int j = tid; j < lp.nN; j += blockDim.x) {
+    bool nan_seen = false;
+    for (int j = blockIdx.x * blockDim.x + tid; j < lp.nN; j += gridDim.x * blockDim.x) {
         double a = lp.rN[j];
         if (neg) a = -a;
         const int side = lp.Ns[j];
         const bool keep = (side == ELLP_NB_LOWER) ? (a > kEps) : (side == ELLP_NB_UPPER ? (a < -kEps) : true);
         if (keep) {
             const double t = lp.d[lp.Nv[j]] / a;
-            if (t != t) s_nan = 1;
+            if (t != t) nan_seen = true;
             if (bp == 0x7fffffff || t < bt) { bt = t; bp = j; }  // j increases per thread: keeps the first minimum
         }
     }
+    if (nan_seen) atomicOr(&sc->flag, 1);
     const unsigned full = 0xffffffffu;
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
@@ -935,40 +975,48 @@ __global__ void __launch_bounds__(1024) k_select_dual(DevLP lp, PivotState* st) 
     }
     if ((tid & 31) == 0) { s_t[tid >> 5] = bt; s_p[tid >> 5] = bp; }
     __syncthreads();
-    if (tid < 32) {
-        const int nw = blockDim.x >> 5;
-        bt = (tid < nw) ? s_t[tid] : 0.;
-        bp = (tid < nw) ? s_p[tid] : 0x7fffffff;
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            const double ot = __shfl_xor_sync(full, bt, off);
-            const int op = __shfl_xor_sync(full, bp, off);
+    if (tid == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+            const double ot = s_t[w];
+            const int op = s_p[w];
             if (op != 0x7fffffff && (bp == 0x7fffffff || ot < bt || (ot == bt && op < bp))) { bt = ot; bp = op; }
         }
-        if (tid == 0) {
-            if (s_nan) { st->err = kErrNaNDualRatio; st->status = ELLP_INFEASIBLE; }
-            else if (bp == 0x7fffffff) st->status = ELLP_INFEASIBLE;  // :281-284 dual unbounded
-            else {
-                st->q_pos = bp;
-                st->q_var = lp.Nv[bp];
-                st->q_side = lp.Ns[bp];
-                st->theta_d = neg ? -bt : bt;  // :286-289
-            }
+        sc->val[blockIdx.x] = bt;
+        sc->idx[blockIdx.x] = bp;
+    }
+    if (!sel_arrive_last(sc, &s_last)) return;
+    if (tid == 0) {  // lexicographic min of (ratio, position) over the blocks: the first minimum in N order
+        bt = 0.;
+        bp = 0x7fffffff;
+        for (int b = 0; b < (int)gridDim.x; ++b) {
+            const double ot = __ldcg(&sc->val[b]);
+            const int op = __ldcg(&sc->idx[b]);
+            if (op != 0x7fffffff && (bp == 0x7fffffff || ot < bt || (ot == bt && op < bp))) { bt = ot; bp = op; }
+        }
+        const int nan_flag = atomicExch(&sc->flag, 0);
+        if (nan_flag) { st->err = kErrNaNDualRatio; st->status = ELLP_INFEASIBLE; }
+        else if (bp == 0x7fffffff) st->status = ELLP_INFEASIBLE;  // :281-284 dual unbounded
+        else {
+            st->q_pos = bp;
+            st->q_var = lp.Nv[bp];
+            st->q_side = lp.Ns[bp];
+            st->theta_d = neg ? -bt : bt;  // :286-289
         }
     }
 }
 
 // dual steepest edge: leaving row = argmax infeasibility_i^2 / w_i (ties: smallest position); same outputs as k_dual_leaving
-__global__ void __launch_bounds__(1024) k_dual_leaving_dse(DevLP lp, PivotState* st) {
-    if (threadIdx.x == 0) st->do_update = 0;
+__global__ void __launch_bounds__(256) k_dual_leaving_dse(DevLP lp, PivotState* st, SelScratch* sc) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->do_update = 0;
     if (st->status != kRunning) return;
-    __shared__ double s_v[32];
-    __shared__ int s_i[32];
+    __shared__ double s_v[8];
+    __shared__ int s_i[8];
+    __shared__ int s_last;
     const int tid = threadIdx.x;
     const unsigned full = 0xffffffffu;
     double bv = -1.;
     int bi = 0x7fffffff;
-    for (int i = tid; i < lp.m; i += blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + tid; i < lp.m; i += gridDim.x * blockDim.x) {
         const int var = lp.Bv[i];
         const double x_i = lp.x[var];
         const int kind = lp.kind[var];
@@ -988,31 +1036,35 @@ __global__ void __launch_bounds__(1024) k_dual_leaving_dse(DevLP lp, PivotState*
     }
     if ((tid & 31) == 0) { s_v[tid >> 5] = bv; s_i[tid >> 5] = bi; }
     __syncthreads();
-    if (tid < 32) {
-        bv = s_v[tid];
-        bi = s_i[tid];
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            const double ov = __shfl_xor_sync(full, bv, off);
-            const int oi = __shfl_xor_sync(full, bi, off);
+    if (tid == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            if (s_v[w] > bv || (s_v[w] == bv && s_i[w] < bi)) { bv = s_v[w]; bi = s_i[w]; }
+        sc->val[blockIdx.x] = bv;
+        sc->idx[blockIdx.x] = bi;
+    }
+    if (!sel_arrive_last(sc, &s_last)) return;
+    if (tid == 0) {
+        bv = -1.;
+        bi = 0x7fffffff;
+        for (int b = 0; b < (int)gridDim.x; ++b) {
+            const double ov = __ldcg(&sc->val[b]);
+            const int oi = __ldcg(&sc->idx[b]);
             if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
         }
-        if (tid == 0) {
-            if (bi == 0x7fffffff) {
-                st->status = ELLP_OPTIMAL;
-            } else {
-                const int var = lp.Bv[bi];
-                const double x_i = lp.x[var];
-                const int kind = lp.kind[var];
-                double delta;
-                int side;
-                if ((kind == ELLP_UPPER || kind == ELLP_TWOSIDED) && x_i > lp.ub[var] + kEps) { delta = x_i - lp.ub[var]; side = ELLP_NB_UPPER; }
-                else { delta = x_i - lp.lb[var]; side = ELLP_NB_LOWER; }
-                st->r_pos = bi;
-                st->leave_var = var;
-                st->delta = delta;
-                st->new_side = side;
-            }
+        if (bi == 0x7fffffff) {
+            st->status = ELLP_OPTIMAL;
+        } else {
+            const int var = lp.Bv[bi];
+            const double x_i = lp.x[var];
+            const int kind = lp.kind[var];
+            double delta;
+            int side;
+            if ((kind == ELLP_UPPER || kind == ELLP_TWOSIDED) && x_i > lp.ub[var] + kEps) { delta = x_i - lp.ub[var]; side = ELLP_NB_UPPER; }
+            else { delta = x_i - lp.lb[var]; side = ELLP_NB_LOWER; }
+            st->r_pos = bi;
+            st->leave_var = var;
+            st->delta = delta;
+            st->new_side = side;
         }
     }
 }
@@ -1087,12 +1139,10 @@ __global__ void __launch_bounds__(256) k_dual_update_vec(DevLP lp, int KS, const
     const int m = lp.m;
     const int r_pos = st->r_pos;
     const double theta_d = st->theta_d, delta = st->delta;
-    double alpha_r = 0.;
-    for (int ks = 0; ks < KS; ++ks) alpha_r += lp.part[(int64_t)ks * lp.ld + r_pos];
+    const double alpha_r = sum_partials(lp.part, lp.ld, KS, r_pos);
     const double theta_p = delta / alpha_r;  // :306
     if (t < m) {
-        double a = 0.;
-        for (int ks = 0; ks < KS; ++ks) a += lp.part[(int64_t)ks * lp.ld + t];
+        const double a = sum_partials(lp.part, lp.ld, KS, t);
         lp.dcol[t] = a;
         const double rho = lp.rho[t];
         lp.y[t] = lp.y[t] + theta_d * rho;       // :304
