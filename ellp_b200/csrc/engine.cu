@@ -20,6 +20,7 @@
 #include "refactor.cuh"
 #include "blocked.cuh"
 #include "peer.cuh"
+#include "small.cuh"
 
 using namespace ellp;
 
@@ -86,6 +87,8 @@ struct ellp_b200_ctx {
     uint64_t graph_key = 0, graph_launches = 0;
     uint64_t lp_generation = 0;   // bumped by every upload / generate
     int use_graphs = 1;           // tuning key "cuda_graphs"
+    int small_path = 1;           // tuning key "small_path": single-CTA kernels for netlib-sized LPs on the revised engine (small.cuh)
+    bool small_attr_set = false;
     uint64_t pivots_since_refactor = 0;
     PivotState* d_st = nullptr;
     PivotState* h_st = nullptr;  // pinned
@@ -468,6 +471,13 @@ int refactor(ellp_b200_ctx* ctx, uint64_t* count) {
             // X[0:k0, :] -= U[0:k0, k0:k0+nb] X[k0:k0+nb, :]
             if (k0 > 0) launch_rankk(ctx, G + (int64_t)m * ld, ld, k0, m, G + (int64_t)k0 * ld, lp.V, lp.ldv, nb);
         }
+    } else if (!ctx->tableau && ctx->small_path && m <= kSmallMaxM && gj_small_smem_bytes(lp.ld, m) <= (size_t)kGjSmallSmemMax) {
+        // netlib-sized basis: the whole Gauss-Jordan inverse in one single-CTA launch (small.cuh)
+        if (!ctx->small_attr_set) {
+            CUDA_TRY(cudaFuncSetAttribute(k_gj_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kGjSmallSmemMax));
+            ctx->small_attr_set = true;
+        }
+        LAUNCH_SMEM(k_gj_small, 1, kSmallThreads, gj_small_smem_bytes(lp.ld, m), lp, ctx->d_st);
     } else if (!ctx->tableau) {
         LAUNCH(k_gj_init, 2 * m, 256, lp);
         for (int k = 0; k < m; ++k) {
@@ -944,6 +954,7 @@ int ellp_b200_set_tuning(ellp_b200_ctx* ctx, const char* key, int value) {
     else if (!std::strcmp(key, "flush4_min_k")) ctx->flush4_min_k = value;
     else if (!std::strcmp(key, "coop_pivots")) ctx->coop_pivots = value;
     else if (!std::strcmp(key, "cuda_graphs")) ctx->use_graphs = value;
+    else if (!std::strcmp(key, "small_path")) ctx->small_path = value;
     else if (!std::strcmp(key, "peer_exchange")) ctx->peer_exchange = value;
     else if (!std::strcmp(key, "coop_threads")) ctx->coop_threads = value;
     else if (!std::strcmp(key, "coop_ctas_per_sm")) { ctx->coop_ctas_per_sm = value; ctx->coop_threads_cached = 0; }
@@ -1528,7 +1539,14 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
             }
             batch = 0;
         }
-        if (batch > 1 && batch == check_every && !ctx->tableau && !ctx->sharded && !profile && ctx->use_graphs) {
+        if (!ctx->tableau && !ctx->sharded && ctx->solver == ELLP_DUAL && ctx->small_path && !profile && lp.m <= kSmallMaxM &&
+            o->pricing == ELLP_PRICE_REFERENCE && o->ratio == ELLP_RATIO_REFERENCE) {
+            // netlib-sized dual: every iteration up to the next refactorisation / the pivot budget in ONE single-CTA launch
+            uint64_t iters = std::min<uint64_t>(o->max_iter - h.pivots, 1u << 20);
+            if (refactor_every > 0) iters = std::min<uint64_t>(iters, std::max<uint64_t>(1, refactor_every - ctx->pivots_since_refactor));
+            LAUNCH(k_dual_small, 1, kSmallThreads, lp, ctx->kc, ctx->KS, (int)std::max<uint64_t>(1, iters), ctx->d_st);
+            batch = 0;
+        } else if (batch > 1 && batch == check_every && !ctx->tableau && !ctx->sharded && !profile && ctx->use_graphs) {
             // revised engine: replay `batch` iterations from a CUDA graph (kernels gate on PivotState::status, so iterations
             // after the end of the solve are no-ops exactly as with direct launches)
             const uint64_t key = ctx->lp_generation * 1000003ull + (uint64_t)(ctx->solver * 64 + o->pricing * 16 + o->ratio * 4 + o->tie_rule) * 131ull + (uint64_t)batch;
