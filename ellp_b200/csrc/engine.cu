@@ -992,6 +992,10 @@ int ellp_b200_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_poi
     CUDA_TRY(cudaSetDevice(ctx->device));
     const int m = sf->m, n = sf->n;
     if (m <= 0 || n < m) return set_err(ctx, ELLP_E_ARG, "upload needs 0 < m <= n");
+    for (int i = 0; i < pt->nB; ++i)  // the reference would panic on the first out-of-range column access (primal :144-148)
+        if (pt->B[i] < 0 || pt->B[i] >= n) return set_err(ctx, ELLP_E_PANIC, "index out of bounds: basic variable index outside the standard form");
+    for (int j = 0; j < pt->nN; ++j)
+        if (pt->N[j] < 0 || pt->N[j] >= n) return set_err(ctx, ELLP_E_PANIC, "index out of bounds: nonbasic variable index outside the standard form");
     DevLP lp{};
     lp.m = m;
     lp.n = n;
