@@ -21,20 +21,22 @@
 //
 // Per pivot and rank (slot = index of the pending (U, V) pair, cf. blocked.cuh), k_blk_pivots_fused:
 //   A   (first pivot of a launch only; afterwards E already did it) Dantzig keys of the local positions, per-block
-//       (best, second best); the LAST block to arrive (atomic ticket) merges them and stores (best key, second key,
-//       global position, reduced cost) into every rank's mailbox
-//   B   every block polls the G mailbox entries and merges them in rank order => the same entering position on every
-//       rank without a grid barrier (the mailbox wait IS the barrier).  Near-tie (best - second < 2 EPS, any two
-//       ranks): second round with the order-free rule of SURVEY appendix A.1 (largest variable index within EPS of the
-//       global maximum), again one mailbox entry per rank.
+//       (best, second best, position, reduced cost), published as four LL words per block in a local area (ll_publish)
+//   B   every block polls all blocks' words and reduces them (ll_gather / ll_reduce): an all-to-all that doubles as the
+//       grid barrier and leaves the rank-local result in every thread.  One block then stores it into every rank's
+//       mailbox; every block polls the G mailbox entries and merges them in rank order => the same entering position on
+//       every rank.  Near-tie (best - second < 2 EPS, any two ranks): second round with the order-free rule of SURVEY
+//       appendix A.1 (largest variable index within EPS of the global maximum), one mailbox entry per rank (here the
+//       rank-local reduction uses the last-block ticket: the path is rare).
 //   C1  the owner of the entering position rebuilds that column of the current tableau (stale column + pending
 //       corrections, same arithmetic as k_ratio_prep) and stores it into every rank's column buffer
-//   C2  every rank polls the column (row i by the thread that needs row i), ratios, per-block two smallest | grid barrier
+//   C2  every rank polls the column (row i by the thread that needs row i), ratios, per-block two smallest + the column
+//       entry of the best row, published like in A; gathering them is the second (and last) barrier of the pivot
 //   D   every thread merges the partials and derives the decision itself (leaving row, lambda, new side, still running);
 //       exact tie fold (ratio_pick_body) only when the minimum is not isolated
 //   E   x step, bookkeeping by the one thread that owns row r, local part of the pivot row and of the reduced-cost row,
 //       new (U, V) slot, and the Dantzig keys of the NEXT pivot (phase A of pivot p+1).  No barrier: the next pivot's
-//       ticket / mailbox separates it from the next reader.
+//       all-to-all separates it from the next reader.
 // Reference lines: pricing primal_simplex_solver.rs:189,253-292; column + ratios :295-367; fold/step/apply :379-434,
 // :205-232.  Decisions equal those of the NCCL path and of the oracle's canonical mode pivot for pivot (tests).
 #pragma once
