@@ -28,6 +28,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly ONE JSON line: keep NCCL's "NCCL version ..." banner (printed to stdout at NCCL_DEBUG=VERSION) out of it
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 WORKLOADS = {
     # BASELINE.json configs[4]: "synthetic dense LP 32768x65536 fp64, tableau column-sharded ... at 1/2/4/8 B200"
