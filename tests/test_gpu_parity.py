@@ -715,3 +715,26 @@ def test_full_size_blocked_engine_matches_rank1_engine_and_stays_feasible(env):
     assert abs(float(c @ x1) - obj1) <= 1e-9 * max(1.0, abs(obj1))
     assert (t1["step"] >= 0).all()
 
+
+@pytest.mark.parametrize("seed", range(60))
+def test_random_lps_with_mixed_bounds_match_oracle(env, seed):
+    """Seeded random LPs with Lower / Upper / Free / Fixed variables and <=, >=, = rows (the generator of
+    tests/test_oracle_highs.py, where the oracle is cross-checked against HiGHS): both GPU solvers must return the oracle's
+    verdict, objective and point -- including the reference's quirky verdicts (square systems, Fixed variables in the dual)."""
+    import test_oracle_highs as TH
+    O, N = env["O"], env["N"]
+    prob = TH._random_lp(seed)[0]
+    for which, tag in ((O.PRIMAL, "primal"), (O.DUAL, "dual")):
+        try:
+            ref = O.solve(prob, which, 1000, O.MODE_EXACT)
+        except O.OracleError:
+            with pytest.raises(Exception):
+                _solver(env, tag).solve(prob)
+            continue
+        res = _solver(env, tag).solve(prob)
+        assert res.kind == ref.status_name, (seed, tag, res.kind, ref.status_name)
+        assert res.used_primal_fallback == ref.used_primal_fallback
+        if res.is_optimal:
+            assert _rel(res.solution.obj(), ref.obj) < 1e-9, (seed, tag)
+            np.testing.assert_allclose(res.solution.x(), ref.x, rtol=1e-8, atol=1e-8)
+
