@@ -738,3 +738,28 @@ def test_random_lps_with_mixed_bounds_match_oracle(env, seed):
             assert _rel(res.solution.obj(), ref.obj) < 1e-9, (seed, tag)
             np.testing.assert_allclose(res.solution.x(), ref.x, rtol=1e-8, atol=1e-8)
 
+
+def test_fused_pivot_kernel_with_more_rows_than_threads(env):
+    """m = 40960 rows > 148 CTAs x 256 threads: every phase of k_blk_pivots_fused walks its grid-stride loops more than once
+    (the register row cache only covers the first row of a thread).  Same pivots / basis as the rank-1 engine, values to 1e-9."""
+    N, ctx = env["N"], env["ctx"]
+    m, ns, seed, K = 40960, 4096, 3, 48
+    n = m + ns
+    runs = {}
+    for bk in (0, 16):
+        o = N.default_opts(K, engine=N.ENGINE_TABLEAU, block_k=bk, check_every=16)
+        tr = np.zeros(K, dtype=N.TRACE_DTYPE); o.trace = N.ptr(tr); o.trace_cap = K
+        ctx.check(N.lib.ellp_b200_generate_dense(ctx.h, m, ns, seed, C.byref(o)))
+        res = N.Result()
+        ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(o), C.byref(res)))
+        x = np.zeros(n); B = np.zeros(m, dtype=np.int32); Nv = np.zeros(ns, dtype=np.int32); Ns = np.zeros(ns, dtype=np.uint8)
+        ctx.check(N.lib.ellp_b200_download(ctx.h, C.byref(N.Point(N.ptr(x), N.ptr(B), N.ptr(Nv), N.ptr(Ns), None, None, m, ns))))
+        assert res.status == N.MAXITER and res.iters == K
+        runs[bk] = (tr.copy(), x, B, Nv, Ns, res.obj)
+    t0, x0, B0, N0, Ns0, obj0 = runs[0]
+    t1, x1, B1, N1, Ns1, obj1 = runs[16]
+    assert (t0["entering"] == t1["entering"]).all() and (t0["leaving"] == t1["leaving"]).all()
+    np.testing.assert_allclose(t1["step"], t0["step"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(x1, x0, rtol=1e-9, atol=1e-9)
+    assert np.array_equal(B0, B1) and np.array_equal(N0, N1) and np.array_equal(Ns0, Ns1) and abs(obj0 - obj1) <= 1e-9 * abs(obj0)
+
