@@ -1,14 +1,20 @@
 #!/usr/bin/env python
 """bench.py -- simplex pivots/s of the B200 pivot loop on the dense LP of BASELINE.json configs[4].
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--pivots P]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--pivots P] [--block-k k]
 
 A "step" = one pass of the hot path over one batch of synthetic input = P simplex pivots of the same dense LP
 (`min -c.x, Ax <= b, x >= 0`, A ~ U(0,1); standard form m x (n_struct + m), slack starting basis; built in HBM by a
 counter-based generator).  `value` times steps with the tableau resident in HBM (each step continues pivoting where
 the previous one stopped); `e2e` times the reference-facing C-ABI call ellp_b200_primal_solve_with_initial on HOST
-buffers (H2D of the whole standard form + P pivots + D2H of the point, every step).  N > 1: the tableau is
-column-sharded, one rank per GPU (torchrun), see ellp_b200/sharded.py.
+buffers (H2D of the standard form -- only its nonbasic columns when the starting basis is verified to be the identity --
++ P pivots + D2H of the point, every step).  N > 1: the condensed tableau is split by nonbasic position, one rank per GPU
+(torchrun), with the per-pivot exchange fused into the pivot kernel over NVLink peer memory (ellp_b200/sharded.py,
+ellp_b200/csrc/peer.cuh).
+
+Other workloads (--workload): the north_star target size 16384x32768, 4096x12288, the dual simplex on the revised engine
+(configs[2] shape, reference rules and steepest edge + Harris), the batch of 65536 small LPs (configs[3]) and the netlib
+LPs through the public API (configs[0] / configs[1]).
 
 `--impl reference` times the reference's own CPU algorithm (the oracle port of ellp's PrimalSimplexSolver::
 solve_with_initial: a fresh dense LU per pivot, single thread like the reference) on a bounded sample.
