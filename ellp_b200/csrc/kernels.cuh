@@ -1373,7 +1373,6 @@ __global__ void __launch_bounds__(1024) k_shard_local_max(DevLP lp, const PivotS
 
 // xchg[16..16+G): gathered local maxima.  Candidate = largest local variable index with key > K* - EPS.
 __global__ void __launch_bounds__(1024) k_shard_pick(DevLP lp, int G, PivotState* st) {
-    __shared__ double s[32];
     __shared__ int s_i[32];
     if (st->status != kRunning) return;
     double kmax = -1.0;
@@ -1402,7 +1401,6 @@ __global__ void __launch_bounds__(1024) k_shard_pick(DevLP lp, int G, PivotState
             lp.xchg[10] = (best >= 0) ? (double)lp.colstat[best] : 0.;
         }
     }
-    (void)s;
 }
 
 // xchg[32..32+3G): gathered candidates.  Every rank derives the same winner; the owner stages its pivot column.
