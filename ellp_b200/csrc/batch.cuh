@@ -120,11 +120,17 @@ __device__ __forceinline__ double warp_max_nonneg(double v) {
     const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
     return __hiloint2double((int)mh, (int)ml);
 }
-__device__ __forceinline__ double warp_min_nonneg(double v) {
-    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+// warp-wide min of ANY doubles (no NaN): order-preserving 64-bit keys (sign bit flipped for x >= 0, all bits for x < 0).  The
+// ratios of primal :327-367 are >= 0 except for the reference's TwoSided quirk ((lb - x_i) / d_i with d_i < 0 and x_i < lb),
+// whose negative value must win the minimum so that assert!(lambda >= 0.) (:402) is reported as kErrLambdaNegative.
+__device__ __forceinline__ double warp_min_any(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long k = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
     const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
     const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
-    return __hiloint2double((int)mh, (int)ml);
+    const unsigned long long km = ((unsigned long long)mh << 32) | ml;
+    return __longlong_as_double((long long)((km >> 63) ? (km & 0x7fffffffffffffffull) : ~km));
 }
 
 // One solve_with_initial on the condensed shared-memory tableau (primal :160-235).  Returns the SolutionStatus; all
@@ -259,7 +265,7 @@ __device__ int batch_run_phase(const BatchSmem& s, int m, int n0, int ld, uint64
             }
             s.lam[i] = lam;
         }
-        lloc = warp_min_nonneg(lloc);
+        lloc = warp_min_any(lloc);
         if (lane == 0) sh_w[warp] = lloc;
         __syncthreads();
         double lmin = sh_w[0];

@@ -992,6 +992,10 @@ int ellp_b200_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_poi
     CUDA_TRY(cudaSetDevice(ctx->device));
     const int m = sf->m, n = sf->n;
     if (m <= 0 || n < m) return set_err(ctx, ELLP_E_ARG, "upload needs 0 < m <= n");
+    // the copies below read m / n - m entries: the lengths must match (solve_with_initial reports the reference's Err first)
+    if (pt->nB != m || pt->nN != n - m) return set_err(ctx, ELLP_E_ARG, "upload: B / N lengths do not match the standard form");
+    if (!pt->x || !pt->B || (n > m && (!pt->N || !pt->N_side))) return set_err(ctx, ELLP_E_ARG, "upload: x / B / N / N_side must not be NULL");
+    if (solver == ELLP_DUAL && (!pt->y || !pt->d)) return set_err(ctx, ELLP_E_ARG, "dual solve needs y and d");
     for (int i = 0; i < pt->nB; ++i)  // the reference would panic on the first out-of-range column access (primal :144-148)
         if (pt->B[i] < 0 || pt->B[i] >= n) return set_err(ctx, ELLP_E_PANIC, "index out of bounds: basic variable index outside the standard form");
     for (int j = 0; j < pt->nN; ++j)
@@ -1332,24 +1336,29 @@ static int batch_alloc(ellp_b200_ctx* ctx, int nlp, int m, int n0, int trace_cap
     }
     batch_free(ctx);
     auto& B = ctx->batch;
-    B.nlp = nlp; B.m = m; B.n0 = n0; B.nc = n0 + m; B.ld = (m % 2 == 0) ? m + 1 : m; B.trace_cap = trace_cap;
+    const int nc = n0 + m;
     const size_t L = (size_t)nlp, nN = (size_t)n0;  // nc - m = n0 nonbasic positions
-    CUDA_TRY(cudaMalloc(&B.A, sizeof(double) * L * m * n0));
-    CUDA_TRY(cudaMalloc(&B.c, sizeof(double) * L * n0));
-    CUDA_TRY(cudaMalloc(&B.b, sizeof(double) * L * m));
-    CUDA_TRY(cudaMalloc(&B.lb, sizeof(double) * L * n0));
-    CUDA_TRY(cudaMalloc(&B.ub, sizeof(double) * L * n0));
-    CUDA_TRY(cudaMalloc(&B.kind, L * n0));
-    CUDA_TRY(cudaMalloc(&B.x, sizeof(double) * L * B.nc));
-    CUDA_TRY(cudaMalloc(&B.obj, sizeof(double) * L));
-    CUDA_TRY(cudaMalloc(&B.B, sizeof(int32_t) * L * m));
-    CUDA_TRY(cudaMalloc(&B.N, sizeof(int32_t) * L * nN));
-    CUDA_TRY(cudaMalloc(&B.Ns, L * nN));
-    CUDA_TRY(cudaMalloc(&B.status, sizeof(int32_t) * L));
-    CUDA_TRY(cudaMalloc(&B.iters, sizeof(int32_t) * 2 * L));
-    CUDA_TRY(cudaMalloc(&B.err, sizeof(int32_t) * L));
-    CUDA_TRY(cudaMalloc(&B.trace_len, sizeof(int32_t) * L));
-    if (trace_cap > 0) CUDA_TRY(cudaMalloc(&B.trace, sizeof(ellp_trace_rec) * L * trace_cap));
+    // a failed allocation must not leave a half-built batch behind (the next call with the same shape would take the
+    // "keep the buffers" return above and the kernel would write through null pointers): roll back, report, keep nlp = 0
+    auto take = [&](void* pp, size_t bytes) {
+        const cudaError_t e = cudaMalloc(reinterpret_cast<void**>(pp), bytes);
+        if (e != cudaSuccess) {
+            ctx->err = std::string("cudaMalloc (batch): ") + cudaGetErrorString(e);
+            cudaGetLastError();
+            batch_free(ctx);
+            return false;
+        }
+        return true;
+    };
+    if (!take(&B.A, sizeof(double) * L * m * n0) || !take(&B.c, sizeof(double) * L * n0) || !take(&B.b, sizeof(double) * L * m) ||
+        !take(&B.lb, sizeof(double) * L * n0) || !take(&B.ub, sizeof(double) * L * n0) || !take(&B.kind, L * n0) ||
+        !take(&B.x, sizeof(double) * L * nc) || !take(&B.obj, sizeof(double) * L) || !take(&B.B, sizeof(int32_t) * L * m) ||
+        !take(&B.N, sizeof(int32_t) * L * nN) || !take(&B.Ns, L * nN) || !take(&B.status, sizeof(int32_t) * L) ||
+        !take(&B.iters, sizeof(int32_t) * 2 * L) || !take(&B.err, sizeof(int32_t) * L) || !take(&B.trace_len, sizeof(int32_t) * L) ||
+        (trace_cap > 0 && !take(&B.trace, sizeof(ellp_trace_rec) * L * trace_cap)))
+        return ELLP_E_CUDA;
+    // the shape is recorded only once every buffer exists
+    B.nlp = nlp; B.m = m; B.n0 = n0; B.nc = nc; B.ld = (m % 2 == 0) ? m + 1 : m; B.trace_cap = trace_cap;
     return ELLP_OK;
 }
 
@@ -1506,6 +1515,9 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
     if (blk > 0) { if (int rc = flush_attrs(ctx)) return rc; }
     int check_every = o->check_every > 0 ? o->check_every : 8;  // iterations enqueued per host read-back (finished solves make them no-ops)
     int refactor_every = o->refactor_every > 0 ? o->refactor_every : ((lp.m <= 512 && !ctx->tableau) ? 100 : 0);
+    // a tableau can only be rebuilt from a resident constraint matrix: the condensed fast upload keeps no A, the peer layout
+    // aliases A with its slice of T, the NCCL-sharded layout transforms A in place
+    if (ctx->tableau && (!ctx->a_resident || ctx->peer_mode || ctx->sharded)) refactor_every = 0;
     if (ctx->peer_mode && ctx->nranks > 1)  // stream-ordered barrier: no rank starts polling before every rank got here
         NCCL_TRY(nccl::api.AllReduce(lp.part, lp.part + 4, 1, nccl::kFloat64, nccl::kSum, ctx->nccl_comm, ctx->stream));
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -1587,6 +1599,7 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
         ctx->pivots_since_refactor += h.pivots - before;
         if (h.status != kRunning) break;
         if (refactor_every > 0 && ctx->pivots_since_refactor >= (uint64_t)refactor_every) {
+            if (blk > 0) launch_flush(ctx, profile, &ev_used);  // pending (U, V) slots belong to the tableau that is about to be replaced
             if ((rc_loop = refactor(ctx, &res->refactors))) break;
             if (dse) launch_row_norms(ctx);
         }
@@ -1674,7 +1687,10 @@ static int solve_with_initial(ellp_b200_ctx* ctx, const ellp_std_form* sf, ellp_
         return ELLP_OK;
     }
     if (solver == ELLP_DUAL) {  // dual :139-151
+        if (!pt->y || !pt->d) return set_err(ctx, ELLP_E_ARG, "dual solve needs y and d");
         for (int j = 0; j < pt->nN; ++j) {
+            if (pt->N[j] < 0 || pt->N[j] >= n)  // d[N_i.index] would panic on the out-of-range index first
+                return set_err(ctx, ELLP_E_PANIC, "index out of bounds: nonbasic variable index outside the standard form");
             const double d_i = pt->d[pt->N[j]];
             const int side = pt->N_side[j];
             const bool infeasible = side == ELLP_NB_LOWER ? d_i < -kEps : (side == ELLP_NB_UPPER ? d_i > kEps : std::fabs(d_i) > kEps);

@@ -491,12 +491,37 @@ def test_solver_parity_with_lu_refactorisation_every_few_pivots(env, which):
     ctx, O = env["ctx"], env["O"]
     try:
         ctx.set_tuning("refactor_mode", 2)
-        res = _solver(env, which, refactor_every=7).solve(prob)
+        # ENGINE_REVISED: the one-launch shared-memory path (K6, engine AUTO) ignores refactor_every
+        res = _solver(env, which, refactor_every=7, engine=env["N"].ENGINE_REVISED).solve(prob)
     finally:
         ctx.set_tuning("refactor_mode", 0)
     ref = O.solve(prob, O.PRIMAL if which == "primal" else O.DUAL, 1000, O.MODE_EXACT)
     assert res.is_optimal and _rel(res.solution.obj(), ref.obj) < 1e-9
     P.check_expectation(exp, res.kind, res.solution.obj(), res.solution.x())
+
+
+@pytest.mark.parametrize("engine,block_k,mode", [("revised", 0, 2), ("revised", 0, 1), ("tableau", 0, 0), ("tableau", 8, 0)])
+def test_refactorisation_really_runs_and_keeps_the_pivot_sequence(env, engine, block_k, mode):
+    # refactor_every = 5 is not a multiple of block_k = 8: pending (U, V) slots must be flushed before the tableau is rebuilt
+    O, S, N, ctx = env["O"], env["S"], env["N"], env["ctx"]
+    m, n = 48, 80
+    A, b, c = _dense_lp(77, m, n)
+    Af, cf, kind, lb, ub, x0, B0, N0, Ns0 = _slack_start_primal(A, b, c)
+    xo, Bo, No, Nso = x0.copy(), B0.copy(), N0.copy(), Ns0.copy()
+    ref = O.solve_with_initial(O.PRIMAL, m, n + m, Af, cf, b, kind, lb, ub, xo, Bo, No, Nso, max_iter=None, trace_cap=20000)
+    xg, Bg, Ng, Nsg = x0.copy(), B0.copy(), N0.copy(), Ns0.copy()
+    try:
+        ctx.set_tuning("refactor_mode", mode)
+        sol = S.GpuPrimalSimplexSolver.new(None, ctx=ctx, trace_cap=20000, refactor_every=5, block_k=block_k,
+                                           engine=N.ENGINE_REVISED if engine == "revised" else N.ENGINE_TABLEAU)
+        res, trace = sol.solve_with_initial(m, n + m, Af, cf, b, kind, lb, ub, xg, Bg, Ng, Nsg)
+    finally:
+        ctx.set_tuning("refactor_mode", 0)
+    assert res.refactors >= len(ref.trace) // 8 > 0, res.refactors
+    assert res.status == ref.status == O.OPTIMAL and res.iters == len(ref.trace)
+    assert (trace["entering"] == ref.trace["entering"]).all() and (trace["leaving"] == ref.trace["leaving"]).all()
+    np.testing.assert_array_equal(Bg, Bo)
+    np.testing.assert_allclose(xg, xo, rtol=1e-9, atol=1e-9)
 
 
 # ---------------------------------------------------------------- optional rules: dual steepest edge + Harris ratio
