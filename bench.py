@@ -45,8 +45,12 @@ WORKLOADS = {
     "dense_tableau_16384x32768": dict(m=16384, ns=16384, pivots=672, block_k=48, sample_m=1024, sample_pivots=3),
     "dense_tableau_4096x12288": dict(m=4096, ns=8192, pivots=960, block_k=48, sample_m=512, sample_pivots=6),
     # BASELINE.json configs[2] shape: dense 4096x8192 (Gte rows => standard form 4096x12288), DUAL simplex, revised engine
-    # (explicit basis inverse).  The entering/leaving rules are the reference's (steepest edge is not built yet).
+    # (explicit basis inverse), the reference's entering / leaving rules.
     "dense_revised_dual_4096x12288": dict(m=4096, ns=8192, pivots=200, sample_m=512, sample_pivots=6, dual=True),
+    # the same LP and rules on the blocked condensed tableau (dual_blocked.cuh): one cooperative launch per block of pivots
+    "dense_tableau_dual_4096x12288": dict(m=4096, ns=8192, pivots=960, block_k=48, sample_m=512, sample_pivots=6, dual=True, tableau=True),
+    "dense_tableau_dual_16384x32768": dict(m=16384, ns=16384, pivots=672, block_k=48, sample_m=1024, sample_pivots=3, dual=True, tableau=True),
+    "dense_tableau_dual_32768x65536": dict(m=32768, ns=32768, pivots=672, block_k=56, sample_m=1024, sample_pivots=3, dual=True, tableau=True),
     # the same LP with dual steepest edge (exact weights from the rank-1 update's epilogue) + Harris ratio test
     "dense_revised_dual_dse_4096x12288": dict(m=4096, ns=8192, pivots=200, sample_m=512, sample_pivots=6, dual=True, dse=True),
     # BASELINE.json configs[0] / configs[1]: netlib LPs of the reference's tests/benchmark_problems (fixtures in tests/golden/),
@@ -448,14 +452,15 @@ def run_ours(args, wl, name):
     m, ns, P = wl["m"], wl["ns"], (args.pivots or wl["pivots"])
     n = m + ns
     dual = bool(wl.get("dual"))
-    engine = N.ENGINE_REVISED if dual else N.ENGINE_TABLEAU
+    tab = (not dual) or bool(wl.get("tableau"))
+    engine = N.ENGINE_TABLEAU if tab else N.ENGINE_REVISED
     rules = dict(pricing=N.PRICE_STEEPEST_EDGE, ratio=N.RATIO_HARRIS) if wl.get("dse") else {}
-    bk = 0 if dual else (wl.get("block_k", 0) if args.block_k < 0 else args.block_k)
+    bk = 0 if not tab else (wl.get("block_k", 0) if args.block_k < 0 else args.block_k)
     if bk > 1:
         rules["block_k"] = bk
     # revised (dual) engine: the timed steps run WITHOUT per-launch events so that its iterations replay from a CUDA graph; one
     # extra profiled step after the timed region supplies the row-reduction timing of the roofline object
-    o = N.default_opts(P, engine=engine, check_every=min(P, max(16, bk)), profile=not dual, **rules)
+    o = N.default_opts(P, engine=engine, check_every=min(P, max(16, bk)), profile=tab, **rules)
     ctx.check(N.lib.ellp_b200_generate_dense_ex(ctx.h, m, ns, SEED, 1 if dual else 0, C.byref(o)))
 
     full_solve = bool(wl.get("dse"))  # steepest edge reaches the optimum within a few hundred pivots: a step = one whole solve
@@ -495,7 +500,7 @@ def run_ours(args, wl, name):
     value = pivots_done / dt
     P = pivots_done // args.steps
     dev_ms_timed = dev_ms
-    if dual:  # profiled pass (direct launches, CUDA events around every k_rank1) for the roofline numbers only
+    if not tab:  # profiled pass (direct launches, CUDA events around every k_rank1) for the roofline numbers only
         o.profile = 1
         r = step()
         dev_ms, rank1_ms, n_rank1 = r.ms_device, r.ms_rank1, r.n_rank1
@@ -511,9 +516,9 @@ def run_ours(args, wl, name):
         kernel = "k_blk_flush (rank-%d row reduction T -= U V of the condensed %d x %d tableau, fp64 DMMA)" % (bk, m, ns)
         traffic_key = name + ":k_blk_flush"
     else:
-        k3_cols = m if dual else ns  # revised engine: K3 updates the m x m basis inverse; tableau engine: the condensed tableau
+        k3_cols = ns if tab else m  # revised engine: K3 updates the m x m basis inverse; tableau engine: the condensed tableau
         alg_bytes = 16.0 * m * k3_cols + 8.0 * (m + k3_cols)
-        kernel = "k_rank1 (rank-1 row reduction of the %s)" % ("basis inverse" if dual else "tableau")
+        kernel = "k_rank1 (rank-1 row reduction of the %s)" % ("tableau" if tab else "basis inverse")
         traffic_key = name + ":k_rank1"
     k3_ms = rank1_ms / max(n_rank1, 1)
     achieved = alg_bytes / (k3_ms * 1e-3) / 1e9 if n_rank1 else None
@@ -574,7 +579,7 @@ def run_ours(args, wl, name):
         dte = time.perf_counter() - t0
         # tableau engine, >= 32 MB, slack basis: only the nonbasic columns of A cross PCIe (the basis columns are verified to be
         # unit vectors on the host while the DMA runs, ellp_b200_upload); otherwise the whole matrix is uploaded
-        cols_up = ns if (not dual and 8.0 * m * n >= 32 * 1048576) else n
+        cols_up = ns if (tab and 8.0 * m * n >= 32 * 1048576) else n
         h2d = 8 * m * cols_up + 8 * (3 * n + m) + n + 8 * n + 4 * m + 4 * ns + ns
         d2h = 8 * n + 4 * m + 4 * ns + ns + 120 * ((P + 15) // 16)
         e2e = {"value": e2e_pivots[0] / dte, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -591,9 +596,9 @@ def run_ours(args, wl, name):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "m": m, "n": n, "pivots_per_step": P, "engine": "revised (explicit B^-1), dual simplex" if dual else ("condensed tableau (nonbasic columns of B^-1 A resident), " + (f"blocked: one cooperative launch per {bk} pivots + one rank-{bk} flush" if bk > 1 else "rank-1 update per pivot")),
+            "config": {"workload": name, "m": m, "n": n, "pivots_per_step": P, "engine": "revised (explicit B^-1), dual simplex" if not tab else (("dual simplex, " if dual else "") + "condensed tableau (nonbasic columns of B^-1 A resident), " + (f"blocked: one cooperative launch per {bk} pivots + one rank-{bk} flush" if bk > 1 else "rank-1 update per pivot")),
                        "block_k": bk,
-                       "tie_rule": "reference folds", "dual_rules": "steepest edge + Harris" if wl.get("dse") else "reference (first infeasible / first min ratio)", "l2": (f"A_N {8.0 * m * ns / 1e6:.0f} MB + B^-1 {8.0 * m * m / 1e6:.0f} MB streamed every pivot (> 126 MB L2, no flush)" if dual
+                       "tie_rule": "reference folds", "dual_rules": "steepest edge + Harris" if wl.get("dse") else "reference (first infeasible / first min ratio)", "l2": (f"A_N {8.0 * m * ns / 1e6:.0f} MB + B^-1 {8.0 * m * m / 1e6:.0f} MB streamed every pivot (> 126 MB L2, no flush)" if not tab
                               else f"condensed tableau {8.0 * m * ns / 1e9:.1f} GB >> 126 MB L2 (no L2 flush needed)"),
                        "baseline_config": "BASELINE.json configs[4]" if name == DEFAULT_WORKLOAD else "north_star / smaller variant"},
             "device_ms_per_step": dev_ms_timed / args.steps, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,

@@ -22,6 +22,8 @@ ENGINE_AUTO, ENGINE_REVISED, ENGINE_TABLEAU = 0, 1, 2
 PRICE_REFERENCE, PRICE_STEEPEST_EDGE = 0, 1
 RATIO_REFERENCE, RATIO_HARRIS = 0, 1
 U64_MAX = 2**64 - 1
+FREE, LOWER, UPPER, TWOSIDED, FIXED = 0, 1, 2, 3, 4   # ellp_bound_kind (problem.rs:190-197)
+NB_LOWER, NB_UPPER, NB_FREE = 0, 1, 2               # ellp_nb_side (standard_form.rs NonbasicBound)
 
 TRACE_DTYPE = np.dtype([("phase", "<i4"), ("iter", "<i4"), ("entering", "<i4"), ("leaving", "<i4"),
                         ("step", "<f8"), ("obj", "<f8")])

@@ -20,6 +20,7 @@
 #include "refactor.cuh"
 #include "blocked.cuh"
 #include "peer.cuh"
+#include "dual_blocked.cuh"
 #include "small.cuh"
 
 using namespace ellp;
@@ -126,6 +127,15 @@ struct ellp_b200_ctx {
     int64_t peer_cap = 0;         // rows per parity slot of the column buffers
     uint32_t xseq = 0;            // pivots exchanged since the communicator was created (wire sequence number)
     int coop_grid_fused = 0;
+    int coop_grid_dual = 0, coop_threads_cached_dual = 0;  // k_blk_dual_pivots_fused
+    // tableau engines with a general (non-identity) starting basis: B^-1 of the basis the tableau was built from lives in
+    // lp.G / lp.Binv (has_binv), with the scratch the blocked LU needs next to the tableau's own U / V
+    bool has_binv = false;
+    double* rf_V = nullptr;       // kPanel x rf_ldv block row of the LU
+    int64_t rf_ldv = 0;
+    double* rf_coop = nullptr;    // publication slots of the cooperative panel kernel
+    bool dj_live = false;         // dual on the tableau: dj (not lp.d) holds the current reduced costs of the nonbasic positions
+    bool tab_from_binv = false;   // T was built as B^-1 A_N (y at download = B^-T (c_B0 - d_B0)); false: diagonal starting basis (bscale)
     long long* tlog = nullptr;    // phase-timing log of k_blk_pivots_fused (tuning key "phase_timing")
     int tlog_cap = 0;
     uint32_t tlog_seq0 = 0;
@@ -203,35 +213,48 @@ int ensure_arena(ellp_b200_ctx* ctx, size_t bytes) {
     return ELLP_OK;
 }
 
-// true iff column B[i] of the column-major m x n matrix A is the unit vector e_i for every basis position i.
-// Memory-bound scan of m^2 doubles, split over host threads (it overlaps the DMA of the nonbasic columns).
-bool host_basis_is_identity(const double* A, int m, const int32_t* B) {
+// true iff column B[i] of the column-major m x n matrix A is a multiple d_i e_i (d_i != 0) of the unit vector e_i for every basis
+// position i (slack bases: +1 for Lte / Eq artificial columns, -1 for Gte rows); diag receives d.  Memory-bound scan of m^2
+// doubles, split over host threads (it overlaps the DMA of the nonbasic columns).
+bool host_basis_is_diagonal(const double* A, int m, const int32_t* B, double* diag, bool* all_ones) {
     const size_t total = (size_t)m * m;
     unsigned nthreads = 1;
     if (total >= ((size_t)1 << 22)) nthreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    std::atomic<bool> ok{true};
+    std::atomic<bool> ok{true}, ones{true};
     auto work = [&](int i0, int i1) {
         for (int i = i0; i < i1 && ok.load(std::memory_order_relaxed); ++i) {
             const double* col = A + (size_t)B[i] * m;
-            bool good = (col[i] == 1.0);
+            const double d = col[i];
+            const bool good = (d != 0.0) && (d == d) && !std::isinf(d);
             double acc = 0.;
             for (int k = 0; k < m; ++k) acc += (col[k] != 0.0) ? 1.0 : 0.0;  // branch-free count of nonzeros (NaN counts too)
             if (!good || acc != 1.0) ok.store(false, std::memory_order_relaxed);
+            if (d != 1.0) ones.store(false, std::memory_order_relaxed);
+            diag[i] = d;
         }
     };
-    if (nthreads == 1) { work(0, m); return ok.load(); }
-    std::vector<std::thread> th;
-    const int chunk = (m + (int)nthreads - 1) / (int)nthreads;
-    for (unsigned t = 0; t < nthreads; ++t) {
-        const int i0 = (int)t * chunk, i1 = std::min(m, i0 + chunk);
-        if (i0 < i1) th.emplace_back(work, i0, i1);
+    if (nthreads == 1) { work(0, m); }
+    else {
+        std::vector<std::thread> th;
+        const int chunk = (m + (int)nthreads - 1) / (int)nthreads;
+        for (unsigned t = 0; t < nthreads; ++t) {
+            const int i0 = (int)t * chunk, i1 = std::min(m, i0 + chunk);
+            if (i0 < i1) th.emplace_back(work, i0, i1);
+        }
+        for (auto& t : th) t.join();
     }
-    for (auto& t : th) t.join();
+    *all_ones = ones.load();
     return ok.load();
 }
 
+struct RefactorScratch {
+    double* V = nullptr;
+    int64_t ldv = 0;
+    double* coop = nullptr;
+};
+
 void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap, bool tableau, int blk_kmax, bool sharded = false, int nranks = 1,
-           double** sendcol = nullptr, uint8_t** d_sides = nullptr) {
+           double** sendcol = nullptr, uint8_t** d_sides = nullptr, bool with_binv = false, RefactorScratch* rf = nullptr) {
     // n = locally stored columns (A / T, dj, key, prow); ng = length of the replicated per-variable vectors
     const size_t ld = (size_t)lp.ld, m = (size_t)lp.m, n = (size_t)lp.n, ng = (size_t)lp.n_glob;
     const size_t nN = sharded ? n : (size_t)lp.nN;
@@ -247,9 +270,21 @@ void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap, bool tableau, int blk
     lp.Ns = a.take<uint8_t>(std::max<size_t>(nN, 1));
     lp.y = a.take<double>(ld);
     lp.d = a.take<double>(ng);
-    if (tableau) {  // T overwrites A in place; no basis inverse is kept
+    if (tableau) {  // condensed: T is separate from A; NCCL-sharded: T overwrites A in place
         lp.G = nullptr;
         lp.Binv = nullptr;
+        if (with_binv && !sharded) {  // general starting basis: B^-1 (revised-engine refactorisation), then T = B^-1 A_N
+            lp.G = a.take<double>(ld * 2 * m);
+            lp.Binv = lp.G ? lp.G + ld * m : nullptr;
+            RefactorScratch r;
+            r.ldv = (int64_t)align_up(std::max(2 * m, nN), 128);
+            r.V = a.take<double>((size_t)kPanel * (size_t)r.ldv);
+            r.coop = a.take<double>(lu_panel_pub_doubles(160));
+            if (rf) *rf = r;
+        }
+        lp.Bv0 = a.take<int32_t>(std::max<size_t>(m, 1));
+        lp.bscale = a.take<double>(ld);
+        lp.dpos = a.take<double>(std::max<size_t>(nN, 1));
         lp.condensed = sharded ? 0 : 1;
         lp.nT = lp.condensed ? (int32_t)nN : (int32_t)n;
         lp.T = lp.condensed ? a.take<double>(ld * std::max<size_t>(nN, 1)) : const_cast<double*>(lp.A);
@@ -278,7 +313,7 @@ void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap, bool tableau, int blk
     lp.key = a.take<double>(std::max<size_t>(nN, 1));
     lp.dcol = a.take<double>(ld);
     lp.rho = a.take<double>(ld);
-    lp.prow = a.take<double>((tableau ? n : 2 * m) + 8);
+    lp.prow = a.take<double>(std::max(tableau ? n : 2 * m, (tableau && with_binv) ? 2 * m : (size_t)0) + 8);
     lp.part = a.take<double>(tableau ? 8 : (size_t)KS * ld);
     lp.lam = a.take<double>(std::max<size_t>(m, 1));
     lp.lu_piv = a.take<int32_t>(std::max<size_t>(m, 1));
@@ -286,7 +321,7 @@ void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap, bool tableau, int blk
         lp.w = a.take<double>(ld);
         lp.npart = a.take<double>((m / kNormCols + 2) * ld);
     } else {
-        lp.w = nullptr;
+        lp.w = a.take<double>(ld);
         lp.npart = nullptr;
     }
     lp.trace = trace_cap > 0 ? a.take<ellp_trace_rec>((size_t)trace_cap) : nullptr;
@@ -304,8 +339,9 @@ void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap, bool tableau, int blk
 }
 
 // slots of the blocked (deferred rank-k) tableau engine requested by the caller (ellp_opts::block_k), 0 = rank-1 engine
-int blk_slots(const ellp_opts* o, bool tableau) {
-    if (!tableau || !o || o->block_k <= 1) return 0;
+int blk_slots(const ellp_opts* o, bool tableau, int solver = ELLP_PRIMAL) {
+    if (!tableau || !o) return 0;
+    if (o->block_k <= 1) return solver == ELLP_DUAL ? 32 : 0;  // the dual runs only on the blocked engine (dual_blocked.cuh)
     return std::min<int>(o->block_k, kBlkMax);
 }
 
@@ -400,8 +436,7 @@ int flush_attrs(ellp_b200_ctx* ctx) {
 
 // panel factorisation of the blocked LU: cooperative multi-CTA kernel while a CTA's slice of the panel fits shared
 // memory, the single-CTA kernel otherwise
-int launch_lu_panel(ellp_b200_ctx* ctx, double* G, int64_t ld, int m, int k0, int nb) {
-    DevLP& lp = ctx->lp;
+int launch_lu_panel(ellp_b200_ctx* ctx, const DevLP& lp, double* G, int64_t ld, int m, int k0, int nb) {
     if (ctx->lu_panel_grid == 0) {
         int sms = 0, coop = 0, per_sm = 0;
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -428,18 +463,14 @@ int launch_lu_panel(ellp_b200_ctx* ctx, double* G, int64_t ld, int m, int k0, in
     return ELLP_OK;
 }
 
-// Gauss-Jordan refactorisation (see kernels.cuh).  Revised engine: B^-1 from the current basis on G = [A_B | I].
-// Tableau engine: T = B^-1 A built in place (skipped when the basis columns already are the identity), then the
-// reduced-cost row d = c - c_B^T T.
-int refactor(ellp_b200_ctx* ctx, uint64_t* count) {
-    DevLP& lp = ctx->lp;
+// B^-1 of the basis lp.Bv, from the resident constraint matrix lp.A, into lp.Binv = right half of G = [A_B | I] (see kernels.cuh /
+// refactor.cuh).  The revised engine passes its own DevLP; the tableau engines pass a copy whose V / ldv / coop point to the LU
+// scratch (ctx->rf_*).  Does not touch PivotState except err / gj_piv (the caller saves and restores it).
+int refactor_binv(ellp_b200_ctx* ctx, const DevLP& lp) {
     const int m = lp.m;
-    // preserve the iteration's index-level state around the factorisation
-    if (int rc = read_state(ctx)) return rc;
-    PivotState saved = *ctx->h_st;
-    const bool use_lu = !ctx->tableau && (ctx->refactor_mode == 2 || (ctx->refactor_mode == 0 && m >= 128));
+    const bool use_lu = (ctx->refactor_mode == 2 || (ctx->refactor_mode == 0 && m >= 128));
     bool diagonal = false;
-    if (!ctx->tableau && ctx->refactor_mode == 0) {  // slack / artificial bases: B is diagonal, invert it directly
+    if (ctx->refactor_mode == 0) {  // slack / artificial bases: B is diagonal, invert it directly
         int flags[2] = {0, 0};
         CUDA_TRY(cudaMemsetAsync(ctx->d_flag, 0, 2 * sizeof(int), ctx->stream));
         LAUNCH(k_check_diag_basis, m, 128, lp.A, lp.ld, m, lp.Bv, ctx->d_flag);
@@ -459,7 +490,7 @@ int refactor(ellp_b200_ctx* ctx, uint64_t* count) {
         if (int rc = flush_attrs(ctx)) return rc;
         for (int k0 = 0; k0 < m; k0 += kPanel) {
             const int nb = std::min(kPanel, m - k0), c0 = k0 + nb;
-            if (int rc = launch_lu_panel(ctx, G, ld, m, k0, nb)) return rc;
+            if (int rc = launch_lu_panel(ctx, lp, G, ld, m, k0, nb)) return rc;
             LAUNCH(k_lu_swap_rows, (ncols - nb + 255) / 256, 256, G, ld, ncols, k0, nb, lp.lu_piv, ctx->d_st);
             if (ncols > c0) LAUNCH(k_lu_trsm_lower, (ncols - c0 + 127) / 128, 128, G, ld, ncols, k0, nb, c0, ctx->d_st, lp.V, lp.ldv);
             // G22 -= L21 U12 over rows [c0, ld) (padding rows are zero) and ALL remaining columns: fp64 tensor pipe (k_blk_flush3)
@@ -471,14 +502,14 @@ int refactor(ellp_b200_ctx* ctx, uint64_t* count) {
             // X[0:k0, :] -= U[0:k0, k0:k0+nb] X[k0:k0+nb, :]
             if (k0 > 0) launch_rankk(ctx, G + (int64_t)m * ld, ld, k0, m, G + (int64_t)k0 * ld, lp.V, lp.ldv, nb);
         }
-    } else if (!ctx->tableau && ctx->small_path && m <= kSmallMaxM && gj_small_smem_bytes(lp.ld, m) <= (size_t)kGjSmallSmemMax) {
+    } else if (ctx->small_path && m <= kSmallMaxM && gj_small_smem_bytes(lp.ld, m) <= (size_t)kGjSmallSmemMax) {
         // netlib-sized basis: the whole Gauss-Jordan inverse in one single-CTA launch (small.cuh)
         if (!ctx->small_attr_set) {
             CUDA_TRY(cudaFuncSetAttribute(k_gj_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kGjSmallSmemMax));
             ctx->small_attr_set = true;
         }
         LAUNCH_SMEM(k_gj_small, 1, kSmallThreads, gj_small_smem_bytes(lp.ld, m), lp, ctx->d_st);
-    } else if (!ctx->tableau) {
+    } else {
         LAUNCH(k_gj_init, 2 * m, 256, lp);
         for (int k = 0; k < m; ++k) {
             LAUNCH(k_gj_pivot, 1, 1024, lp.G, lp.ld, m, (const int32_t*)nullptr, k, lp.dcol, ctx->d_st);
@@ -486,9 +517,55 @@ int refactor(ellp_b200_ctx* ctx, uint64_t* count) {
             LAUNCH(k_gj_swap_gather, (cols + 255) / 256, 256, lp.G, lp.ld, k, 2 * m, k, lp.prow, ctx->d_st);
             launch_rank1(ctx, lp.G + (int64_t)k * lp.ld, lp.ld, m, cols, lp.dcol, lp.prow, ctx->d_st, 0);
         }
+    }
+    return ELLP_OK;
+}
+
+// Condensed tableau from a general basis: B^-1 by refactor_binv, then T = B^-1 A_N as m / kb rank-kb updates on the fp64 tensor
+// pipe (the row-reduction kernel K3b with U = a column block of B^-1 and V = minus the matching row block of A_N).
+// Replaces m sequential full-tableau Gauss-Jordan sweeps; leaves A intact and B^-1 behind for the dual's y.
+int tableau_from_binv(ellp_b200_ctx* ctx) {
+    DevLP& lp = ctx->lp;
+    DevLP rl = lp;
+    rl.V = ctx->rf_V;
+    rl.ldv = ctx->rf_ldv;
+    rl.coop = ctx->rf_coop;
+    if (int rc = refactor_binv(ctx, rl)) return rc;
+    if (int rc = flush_attrs(ctx)) return rc;
+    const int m = lp.m, nT = lp.nT;
+    // row blocks of A_N go through the tableau's own V (blk_kmax rows) when the blocked engine is active, else through the LU's block row
+    double* Vb = lp.V ? lp.V : ctx->rf_V;
+    const int64_t ldvb = lp.V ? lp.ldv : ctx->rf_ldv;
+    const int kb = lp.V ? std::min(ctx->blk_kmax, kBlkMax) : kPanel;
+    if (!lp.V && ldvb < nT) return set_err(ctx, ELLP_E_ARG, "tableau start from a general basis needs n - m <= 2 m without block_k (use block_k > 1)");
+    CUDA_TRY(cudaMemsetAsync(lp.T, 0, sizeof(double) * (size_t)lp.ld * (size_t)nT, ctx->stream));
+    for (int k0 = 0; k0 < m; k0 += kb) {
+        const int nb = std::min(kb, m - k0);
+        dim3 gg((unsigned)((nT + 255) / 256), (unsigned)nb);
+        LAUNCH(k_gather_rows_neg, gg, 256, lp.A, lp.ld, lp.Nv + lp.pos_lo, nT, k0, Vb, ldvb);
+        launch_rankk(ctx, lp.T, lp.ld, (int)lp.ld, nT, lp.Binv + (int64_t)k0 * lp.ld, Vb, ldvb, nb);
+    }
+    if (lp.V) CUDA_TRY(cudaMemsetAsync(lp.V, 0, sizeof(double) * (size_t)lp.ldv * (size_t)ctx->blk_kmax, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(lp.Bv0, lp.Bv, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->tab_from_binv = true;
+    return ELLP_OK;
+}
+
+// Refactorisation.  Revised engine: B^-1 from the current basis on G = [A_B | I].  Tableau engine: T = B^-1 A_N rebuilt from the
+// resident A (gathered when the basis columns are the identity, through B^-1 otherwise), then -- primal -- the reduced-cost row
+// d = c - c_B^T T; the dual keeps its own d (dual :296-302 never recomputes it).
+int refactor(ellp_b200_ctx* ctx, uint64_t* count) {
+    DevLP& lp = ctx->lp;
+    const int m = lp.m;
+    // preserve the iteration's index-level state around the factorisation
+    if (int rc = read_state(ctx)) return rc;
+    PivotState saved = *ctx->h_st;
+    if (!ctx->tableau) {
+        if (int rc = refactor_binv(ctx, lp)) return rc;
     } else {
-        // F = full tableau B^-1 A in the buffer of A; the condensed engine then keeps only its nonbasic columns
+        // F = A (sharded in-place engine: the tableau itself); the condensed engine keeps only the nonbasic columns in T
         double* F = const_cast<double*>(lp.A);
+        if (ctx->dj_live) LAUNCH(k_dual_tab_scatter_d, (lp.nN + 255) / 256, 256, lp, (const double*)lp.dj);  // mid-solve: d follows dj
         int mismatch = 0;
         if (!ctx->sharded) {  // a sharded tableau is only accepted with an identity starting basis (checked at upload)
             CUDA_TRY(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
@@ -496,20 +573,35 @@ int refactor(ellp_b200_ctx* ctx, uint64_t* count) {
             CUDA_TRY(cudaMemcpyAsync(&mismatch, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         }
-        if (mismatch) {
+        bool built = false;
+        if (mismatch && lp.condensed && ctx->has_binv) {
+            if (int rc = tableau_from_binv(ctx)) return rc;
+            built = true;
+        } else if (mismatch) {  // no room for B^-1 was reserved: m in-place Gauss-Jordan sweeps over the full tableau (destroys A)
             for (int k = 0; k < m; ++k) {
                 LAUNCH(k_gj_pivot, 1, 1024, F, lp.ld, m, (const int32_t*)lp.Bv, k, lp.dcol, ctx->d_st);
                 LAUNCH(k_gj_swap_gather, (lp.n + 255) / 256, 256, F, lp.ld, 0, lp.n, k, lp.prow, ctx->d_st);
                 launch_rank1(ctx, F, lp.ld, m, lp.n, lp.dcol, lp.prow, ctx->d_st, 0);
             }
+            ctx->a_resident = false;
         }
         LAUNCH(k_init_cB, (int)((lp.ld + 255) / 256), 256, lp);
         if (lp.condensed) {
-            dim3 gg((unsigned)std::max<int64_t>(1, std::min<int64_t>(8, (lp.ld + 255) / 256)), (unsigned)lp.nN);
-            LAUNCH(k_gather_cols, gg, 256, F, lp.ld, lp.Nv, lp.nN, lp.T);
-            LAUNCH(k_gemv_t<EPI_PLAIN>, gemv_grid(lp.nN), 256, lp.T, lp.ld, (const int32_t*)nullptr, lp.nN, lp.cB, lp.dj, (const double*)nullptr,
-                   (const uint8_t*)nullptr, (double*)nullptr, (PivotState*)nullptr, 0);
-            LAUNCH(k_redcost_pos, (lp.nN + 255) / 256, 256, lp.c, lp.Nv, lp.nN, lp.dj);
+            if (!built) {
+                dim3 gg((unsigned)std::max<int64_t>(1, std::min<int64_t>(8, (lp.ld + 255) / 256)), (unsigned)lp.nN);
+                LAUNCH(k_gather_cols, gg, 256, F, lp.ld, lp.Nv, lp.nN, lp.T);
+                CUDA_TRY(cudaMemcpyAsync(lp.Bv0, lp.Bv, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToDevice, ctx->stream));
+                LAUNCH(k_fill_const, (int)((lp.ld + 255) / 256), 256, lp.bscale, (int64_t)lp.ld, 1.0);
+                ctx->tab_from_binv = false;
+            }
+            if (ctx->solver == ELLP_DUAL) {
+                LAUNCH(k_dual_tab_init, (lp.nT + 255) / 256, 256, lp);
+                ctx->dj_live = true;
+            } else {
+                LAUNCH(k_gemv_t<EPI_PLAIN>, gemv_grid(lp.nN), 256, lp.T, lp.ld, (const int32_t*)nullptr, lp.nN, lp.cB, lp.dj, (const double*)nullptr,
+                       (const uint8_t*)nullptr, (double*)nullptr, (PivotState*)nullptr, 0);
+                LAUNCH(k_redcost_pos, (lp.nN + 255) / 256, 256, lp.c, lp.Nv, lp.nN, lp.dj);
+            }
         } else {
             LAUNCH(k_gemv_t<EPI_REDCOST>, gemv_grid(lp.n), 256, lp.T, lp.ld, (const int32_t*)nullptr, lp.n, lp.cB, lp.dj, lp.c + lp.col_lo,
                    (const uint8_t*)nullptr, (double*)nullptr, (PivotState*)nullptr, 0);
@@ -686,19 +778,22 @@ int peer_finish_init(ellp_b200_ctx* ctx) {
 // rank issues the same sequence of launches.  self_only: single-GPU blocked engine (the exchange buffers are this GPU's own).
 int launch_coop_pivots_peer(ellp_b200_ctx* ctx, const ellp_opts* o, int npiv, bool self_only) {
     DevLP& lp = ctx->lp;
-    const void* fn = (const void*)k_blk_pivots_fused;
-    int& grid_cap = ctx->coop_grid_fused;
+    const bool dual = (ctx->solver == ELLP_DUAL);  // dual_blocked.cuh: same layout, same exchange buffers, no tie folds (no dynamic smem)
+    const void* fn = dual ? (const void*)k_blk_dual_pivots_fused : (const void*)k_blk_pivots_fused;
+    const size_t smem = dual ? 0 : (size_t)kScanSmemBytes;
+    int& grid_cap = dual ? ctx->coop_grid_dual : ctx->coop_grid_fused;
+    int& threads_cached = dual ? ctx->coop_threads_cached_dual : ctx->coop_threads_cached;
     // the fused kernel runs with small blocks: its phases are latency-bound and every block-wide reduction / barrier costs
     // issue slots per resident warp (measured: 256 threads per block beat 1024)
     const int threads = std::max(64, std::min(kFusedMaxThreads, ctx->coop_threads & ~31));
-    if (grid_cap == 0 || ctx->coop_threads_cached != threads) {
-        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmemBytes));
+    if (grid_cap == 0 || threads_cached != threads) {
+        if (smem) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int sms = 0, per_sm = 0, coop = 0;
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
         CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, kScanSmemBytes));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
         grid_cap = (coop && per_sm > 0) ? std::min(kLLMaxBlocks, sms * std::min(per_sm, std::max(1, ctx->coop_ctas_per_sm))) : -1;
-        ctx->coop_threads_cached = threads;
+        threads_cached = threads;
     }
     if (grid_cap < 0) return set_err(ctx, ELLP_E_CUDA, "cooperative launch unavailable");
     const int64_t work = std::max<int64_t>(std::max<int64_t>(lp.ld, lp.ldv), lp.nT);
@@ -715,8 +810,13 @@ int launch_coop_pivots_peer(ellp_b200_ctx* ctx, const ellp_opts* o, int npiv, bo
         pl.rank = 0;
         pl.nranks = 1;
     }
-    void* args[] = {(void*)&lp, (void*)&pl, (void*)&tie, (void*)&slot0, (void*)&npiv, (void*)&seq0, (void*)&st};
-    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, (size_t)kScanSmemBytes, ctx->stream));
+    if (dual) {
+        void* args[] = {(void*)&lp, (void*)&pl, (void*)&slot0, (void*)&npiv, (void*)&seq0, (void*)&st};
+        CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, ctx->stream));
+    } else {
+        void* args[] = {(void*)&lp, (void*)&pl, (void*)&tie, (void*)&slot0, (void*)&npiv, (void*)&seq0, (void*)&st};
+        CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, ctx->stream));
+    }
     ctx->launches++;
     ctx->blk_fill += npiv;
     ctx->xseq += (uint32_t)npiv;
@@ -819,6 +919,27 @@ void launch_row_norms(ellp_b200_ctx* ctx) {
     dim3 grid((unsigned)((m + 2 * kRank1Threads - 1) / (2 * kRank1Threads)), (unsigned)((m + kNormCols - 1) / kNormCols));
     LAUNCH(k_rownorms_partial, grid, kRank1Threads, lp.Binv, lp.ld, m, m, kNormCols, lp.npart);
     LAUNCH(k_sum_norms, (m + 255) / 256, 256, lp.npart, lp.ld, m, (m + kNormCols - 1) / kNormCols, lp.w, ctx->d_st, 0);
+}
+
+// dual on the tableau: lp.d and lp.y of the current point.  d: the maintained row dj scattered to the variables (basic variables
+// keep 0 / their starting value, dual :302); y from d through the basis B0 the tableau was built from: a_j^T y = c_j - d_j for
+// j in B0, i.e. y = B0^-T (c_B0 - d_B0) -- a diagonal scaling when B0 was diagonal (slack basis), one transposed GEMV with the
+// kept B0^-1 otherwise.  The reference accumulates y += theta_dual rho instead (dual :304); both satisfy d = c - A^T y.
+int dual_tab_export(ellp_b200_ctx* ctx) {
+    DevLP& lp = ctx->lp;
+    const double* dpos = lp.dj;
+    if (ctx->peer_mode && ctx->nranks > 1) {
+        NCCL_TRY(nccl::api.AllGather(lp.dj, lp.dpos, (size_t)lp.nT, nccl::kFloat64, ctx->nccl_comm, ctx->stream));
+        dpos = lp.dpos;
+    }
+    LAUNCH(k_dual_tab_scatter_d, (lp.nN + 255) / 256, 256, lp, dpos);
+    LAUNCH(k_dual_tab_yrhs, (int)((lp.ld + 255) / 256), 256, lp, (const int32_t*)lp.Bv0, lp.u);
+    if (ctx->tab_from_binv)
+        LAUNCH(k_gemv_t<EPI_PLAIN>, gemv_grid(lp.m), 256, lp.Binv, lp.ld, (const int32_t*)nullptr, lp.m, lp.u, lp.y, (const double*)nullptr,
+               (const uint8_t*)nullptr, (double*)nullptr, (PivotState*)nullptr, 0);
+    else
+        LAUNCH(k_dual_tab_y_diag, (lp.m + 255) / 256, 256, lp, (const double*)lp.u, (const double*)lp.bscale);
+    return ELLP_OK;
 }
 
 double host_dual_obj(const ellp_std_form* sf, const double* y, const double* d) {  // standard_form.rs:52-68
@@ -957,7 +1078,7 @@ int ellp_b200_set_tuning(ellp_b200_ctx* ctx, const char* key, int value) {
     else if (!std::strcmp(key, "small_path")) ctx->small_path = value;
     else if (!std::strcmp(key, "peer_exchange")) ctx->peer_exchange = value;
     else if (!std::strcmp(key, "coop_threads")) ctx->coop_threads = value;
-    else if (!std::strcmp(key, "coop_ctas_per_sm")) { ctx->coop_ctas_per_sm = value; ctx->coop_threads_cached = 0; }
+    else if (!std::strcmp(key, "coop_ctas_per_sm")) { ctx->coop_ctas_per_sm = value; ctx->coop_threads_cached = 0; ctx->coop_threads_cached_dual = 0; }
     else if (!std::strcmp(key, "phase_timing")) {  // value = pivots to log (0 = off); read back with ellp_b200_phase_log
         if (ctx->tlog) { cudaFree(ctx->tlog); ctx->tlog = nullptr; }
         ctx->tlog_cap = 0;
@@ -1012,15 +1133,21 @@ int ellp_b200_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_poi
     const int KS = (m + kc - 1) / kc;
     const int64_t tcap = (o && o->trace) ? o->trace_cap : 0;
     const bool tableau = o && o->engine == ELLP_ENGINE_TABLEAU;
-    if (tableau && solver != ELLP_PRIMAL)
-        return set_err(ctx, ELLP_E_ARG, "ELLP_ENGINE_TABLEAU implements the primal path only; use ELLP_ENGINE_REVISED for the dual");
-    const int blk = blk_slots(o, tableau);
+    const int blk = blk_slots(o, tableau, solver);
+    // tableau engines: room for B^-1 of a general starting basis (T = B^-1 A_N, y of the dual) unless the LP is so large that
+    // the caller is expected to start from the slack basis (the fast condensed path below)
+    const bool with_binv = tableau && ((double)m * 2.0 * m * 8.0 <= 24.0 * 1073741824.0);
     Arena probe;
-    carve(probe, lp, KS, tcap, tableau, blk);
+    carve(probe, lp, KS, tcap, tableau, blk, false, 1, nullptr, nullptr, with_binv);
     if (int rc = ensure_arena(ctx, probe.off + 256)) return rc;
     Arena a;
     a.base = ctx->arena;
-    carve(a, lp, KS, tcap, tableau, blk);
+    RefactorScratch rf;
+    carve(a, lp, KS, tcap, tableau, blk, false, 1, nullptr, nullptr, with_binv, &rf);
+    ctx->has_binv = with_binv;
+    ctx->rf_V = rf.V; ctx->rf_ldv = rf.ldv; ctx->rf_coop = rf.coop;
+    ctx->tab_from_binv = false;
+    ctx->dj_live = false;
     cudaStream_t s = ctx->stream;
     // zero the padded scratch once (padding rows must stay zero)
     CUDA_TRY(cudaMemsetAsync(lp.cB, 0, (size_t)((char*)lp.lam - (char*)lp.cB), s));
@@ -1030,7 +1157,8 @@ int ellp_b200_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_poi
     // identity (slack / artificial basis -- what the reference's phase builders produce, primal_problem.rs:234-246).  Their
     // DMA goes straight into T while host threads verify that the basis columns are unit vectors; if they are, the basis
     // half of A never crosses PCIe.  Otherwise (or for small LPs) the whole matrix is uploaded and T is built on the device.
-    bool fast_condensed = false;
+    bool fast_condensed = false, diag_ones = true;
+    std::vector<double> diag0((size_t)std::max(m, 1), 1.0);
     if (tableau && lp.condensed && lp.nN > 0 && (double)m * n * 8.0 >= 32.0 * 1048576.0) {
         if (lp.ld != m) CUDA_TRY(cudaMemsetAsync(lp.T, 0, sizeof(double) * (size_t)lp.ld * lp.nN, s));
         for (int p0 = 0; p0 < lp.nN;) {  // runs of consecutive variable indices in N travel as one copy
@@ -1042,7 +1170,7 @@ int ellp_b200_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_poi
             else CUDA_TRY(cudaMemcpy2DAsync(dst, sizeof(double) * lp.ld, src, sizeof(double) * m, sizeof(double) * m, p1 - p0, cudaMemcpyHostToDevice, s));
             p0 = p1;
         }
-        fast_condensed = host_basis_is_identity(sf->A, m, pt->B);
+        fast_condensed = host_basis_is_diagonal(sf->A, m, pt->B, diag0.data(), &diag_ones);
     }
     if (fast_condensed) {
         // A stays unpopulated on the device (ellp_b200_download_std_form reports that)
@@ -1087,9 +1215,21 @@ int ellp_b200_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_poi
     ctx->a_resident = !fast_condensed;
     if (fast_condensed) {  // T = A_N already sits in place: reduced-cost row d_p = c_p - c_B^T a_p, as at the end of refactor()
         LAUNCH(k_init_cB, (int)((lp.ld + 255) / 256), 256, lp);
-        LAUNCH(k_gemv_t<EPI_PLAIN>, gemv_grid(lp.nN), 256, lp.T, lp.ld, (const int32_t*)nullptr, lp.nN, lp.cB, lp.dj, (const double*)nullptr,
-               (const uint8_t*)nullptr, (double*)nullptr, (PivotState*)nullptr, 0);
-        LAUNCH(k_redcost_pos, (lp.nN + 255) / 256, 256, lp.c, lp.Nv, lp.nN, lp.dj);
+        CUDA_TRY(cudaMemcpyAsync(lp.Bv0, lp.Bv, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToDevice, s));
+        LAUNCH(k_fill_const, (int)((lp.ld + 255) / 256), 256, lp.bscale, (int64_t)lp.ld, 1.0);
+        if (!diag_ones) {  // diagonal basis D (Gte rows: -1 slacks): T = D^-1 A_N, row by row
+            CUDA_TRY(cudaMemcpyAsync(lp.bscale, diag0.data(), sizeof(double) * (size_t)m, cudaMemcpyHostToDevice, s));
+            dim3 gs((unsigned)((lp.ld / 2 + 255) / 256), (unsigned)std::min(lp.nN, 4096));
+            LAUNCH(k_scale_rows_inv, gs, 256, lp.T, lp.ld, m, lp.nN, (const double*)lp.bscale);
+        }
+        if (solver == ELLP_DUAL) {
+            LAUNCH(k_dual_tab_init, (lp.nT + 255) / 256, 256, lp);
+            ctx->dj_live = true;
+        } else {
+            LAUNCH(k_gemv_t<EPI_PLAIN>, gemv_grid(lp.nN), 256, lp.T, lp.ld, (const int32_t*)nullptr, lp.nN, lp.cB, lp.dj, (const double*)nullptr,
+                   (const uint8_t*)nullptr, (double*)nullptr, (PivotState*)nullptr, 0);
+            LAUNCH(k_redcost_pos, (lp.nN + 255) / 256, 256, lp.c, lp.Nv, lp.nN, lp.dj);
+        }
         ctx->binv_valid = true;
         ctx->pivots_since_refactor = 0;
     }
@@ -1118,19 +1258,21 @@ int ellp_b200_generate_dense_ex(ellp_b200_ctx* ctx, int32_t m, int32_t n_struct,
     const int KS = (m + kc - 1) / kc;
     const int64_t tcap = o->trace ? o->trace_cap : 0;
     const bool tableau = o->engine == ELLP_ENGINE_TABLEAU;
-    if (tableau && variant == 1) return set_err(ctx, ELLP_E_ARG, "the dual variant needs ELLP_ENGINE_REVISED");
-    const int blk = blk_slots(o, tableau);
+    const int blk = blk_slots(o, tableau, variant == 0 ? ELLP_PRIMAL : ELLP_DUAL);
     Arena probe;
     carve(probe, lp, KS, tcap, tableau, blk);
     if (int rc = ensure_arena(ctx, probe.off + 256)) return rc;
     Arena a;
     a.base = ctx->arena;
     carve(a, lp, KS, tcap, tableau, blk);
+    ctx->has_binv = false;
+    ctx->tab_from_binv = false;
+    ctx->dj_live = false;
     CUDA_TRY(cudaMemsetAsync(lp.cB, 0, (size_t)((char*)lp.lam - (char*)lp.cB), ctx->stream));
     CUDA_TRY(cudaMemsetAsync(lp.y, 0, sizeof(double) * lp.ld, ctx->stream));
     if (tableau && lp.coop) CUDA_TRY(cudaMemsetAsync(lp.coop, 0, sizeof(double) * 6 * 1024, ctx->stream));
     LAUNCH(k_gen_dense_cols, 148 * 16, 256, const_cast<double*>(lp.A), lp.ld, m, (int64_t)n_struct, (int64_t)0, (int64_t)lp.n, seed,
-           variant == 0 ? 1.0 : -1.0);
+           variant == 0 ? 1.0 : -1.0, 1.0);
     LAUNCH(k_gen_dense_vectors, 148 * 2, 256, lp, (int64_t)n_struct, seed, (int)variant);
     ctx->lp = lp;
     ctx->KS = KS;
@@ -1147,6 +1289,17 @@ int ellp_b200_generate_dense_ex(ellp_b200_ctx* ctx, int32_t m, int32_t n_struct,
     ctx->binv_valid = false;
     ctx->a_resident = true;
     ctx->dual_obj0 = 0.;  // y = 0 and every bound is Lower(0): dual_obj(y, d) = 0
+    if (tableau && variant == 1) {
+        // slack basis B = -I (A x - s = b): T = B^-1 A_N = -A_N, generated straight into T; dj = d = c
+        LAUNCH(k_gen_dense_cols, 148 * 16, 256, lp.T, lp.ld, m, (int64_t)n_struct, (int64_t)0, (int64_t)n_struct, seed, 1.0, -1.0);
+        CUDA_TRY(cudaMemcpyAsync(lp.Bv0, lp.Bv, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToDevice, ctx->stream));
+        LAUNCH(k_fill_const, (int)((lp.ld + 255) / 256), 256, lp.bscale, (int64_t)lp.ld, -1.0);
+        LAUNCH(k_init_cB, (int)((lp.ld + 255) / 256), 256, lp);
+        LAUNCH(k_dual_tab_init, (lp.nT + 255) / 256, 256, lp);
+        ctx->dj_live = true;
+        ctx->binv_valid = true;
+        ctx->pivots_since_refactor = 0;
+    }
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(cudaGetLastError());
     return ELLP_OK;
@@ -1250,7 +1403,7 @@ int ellp_b200_sharded_generate_dense(ellp_b200_ctx* ctx, int32_t m, int32_t n_st
     if (blk_slots(o, true) > 1 && ctx->peer_exchange) {
         // peer layout: rank g generates the structural columns (= nonbasic positions) [g nN/G, (g+1) nN/G) straight into T
         if (int rc = peer_prepare(ctx, m, n_struct + m, o, &lp)) return rc;
-        LAUNCH(k_gen_dense_cols, 148 * 16, 256, lp.T, lp.ld, m, (int64_t)n_struct, (int64_t)lp.pos_lo, (int64_t)(lp.pos_lo + lp.nT), seed, 1.0);
+        LAUNCH(k_gen_dense_cols, 148 * 16, 256, lp.T, lp.ld, m, (int64_t)n_struct, (int64_t)lp.pos_lo, (int64_t)(lp.pos_lo + lp.nT), seed, 1.0, 1.0);
         LAUNCH(k_gen_dense_vectors, 148 * 2, 256, lp, (int64_t)n_struct, seed, 0);
         ctx->lp = lp;
         return peer_finish_init(ctx);
@@ -1258,7 +1411,7 @@ int ellp_b200_sharded_generate_dense(ellp_b200_ctx* ctx, int32_t m, int32_t n_st
     ctx->peer_mode = false;
     if (int rc = sharded_prepare(ctx, m, n_struct + m, o, &lp)) return rc;
     LAUNCH(k_gen_dense_cols, 148 * 16, 256, const_cast<double*>(lp.A), lp.ld, m, (int64_t)n_struct, (int64_t)lp.col_lo,
-           (int64_t)(lp.col_lo + lp.n), seed, 1.0);
+           (int64_t)(lp.col_lo + lp.n), seed, 1.0, 1.0);
     LAUNCH(k_gen_dense_vectors, 148 * 2, 256, lp, (int64_t)n_struct, seed, 0);
     ctx->lp = lp;
     return sharded_finish_init(ctx);
@@ -1510,7 +1663,15 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
     if (dse) launch_row_norms(ctx);
     if (ctx->solver == ELLP_PRIMAL) LAUNCH(k_obj_dot, 1, 1024, lp.c, lp.x, lp.n_glob, ctx->d_st);
     // blocked tableau engine: slots were allocated at upload time; the caller may lower block_k per run
-    const int blk = (ctx->tableau && ctx->blk_kmax > 0 && o->block_k > 1) ? std::min(o->block_k, ctx->blk_kmax) : 0;
+    int blk = (ctx->tableau && ctx->blk_kmax > 0 && o->block_k > 1) ? std::min(o->block_k, ctx->blk_kmax) : 0;
+    const bool dual_tab = ctx->tableau && ctx->solver == ELLP_DUAL;
+    if (dual_tab) {  // the dual runs only on the blocked condensed tableau (single GPU or peer layout)
+        if (blk == 0) blk = ctx->blk_kmax;
+        if (blk <= 1 || !lp.condensed || (ctx->sharded && !ctx->peer_mode))
+            return set_err(ctx, ELLP_E_ARG, "the dual tableau engine needs the condensed blocked layout (block_k > 1; sharded: the peer engine)");
+        if (o->pricing != ELLP_PRICE_REFERENCE || o->ratio != ELLP_RATIO_REFERENCE)
+            return set_err(ctx, ELLP_E_ARG, "steepest-edge pricing / the Harris ratio test of the dual need ELLP_ENGINE_REVISED");
+    }
     ctx->blk_fill = 0;
     if (blk > 0) { if (int rc = flush_attrs(ctx)) return rc; }
     int check_every = o->check_every > 0 ? o->check_every : 8;  // iterations enqueued per host read-back (finished solves make them no-ops)
@@ -1539,7 +1700,7 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
                 if (!rc_loop && ctx->blk_fill >= blk) launch_flush(ctx, profile, &ev_used);
             }
             batch = 0;
-        } else if (blk > 0 && !ctx->sharded && ctx->coop_pivots && lp.condensed) {
+        } else if (blk > 0 && !ctx->sharded && (ctx->coop_pivots || dual_tab) && lp.condensed) {
             // cooperative path: whole blocks of pivots per launch, a flush after every full block
             int left = std::max(batch, blk);
             if (o->max_iter - h.pivots < (uint64_t)left) left = (int)std::max<uint64_t>(1, o->max_iter - h.pivots);
@@ -1639,11 +1800,18 @@ int ellp_b200_download(ellp_b200_ctx* ctx, ellp_point* pt) {
     CUDA_TRY(cudaSetDevice(ctx->device));
     DevLP& lp = ctx->lp;
     cudaStream_t s = ctx->stream;
+    if (ctx->tableau && ctx->solver == ELLP_DUAL && ctx->dj_live && pt->y && pt->d) {
+        if (int rc = dual_tab_export(ctx)) return rc;
+    }
     if (ctx->peer_mode) {  // x, B and the N list (position order) are replicated
         CUDA_TRY(cudaMemcpyAsync(pt->x, lp.x, sizeof(double) * lp.n_glob, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaMemcpyAsync(pt->B, lp.Bv, sizeof(int32_t) * lp.m, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaMemcpyAsync(pt->N, lp.Nv, sizeof(int32_t) * lp.nN, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaMemcpyAsync(pt->N_side, lp.Ns, (size_t)lp.nN, cudaMemcpyDeviceToHost, s));
+        if (ctx->solver == ELLP_DUAL && pt->y && pt->d) {
+            CUDA_TRY(cudaMemcpyAsync(pt->y, lp.y, sizeof(double) * lp.m, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaMemcpyAsync(pt->d, lp.d, sizeof(double) * lp.n_glob, cudaMemcpyDeviceToHost, s));
+        }
         CUDA_TRY(cudaStreamSynchronize(s));
         return ELLP_OK;
     }

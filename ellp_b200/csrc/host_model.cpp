@@ -520,7 +520,6 @@ int device_phase(ellp_b200_ctx* ctx, int solver, HostStdForm& sf, HostPoint& pt,
     ellp_point p{pt.x.data(), pt.B.data(), pt.N.data(), pt.Ns.data(), pt.y.data(), pt.d.data(), nB, nN};
     ellp_opts o = *base;
     o.phase_tag = phase_tag;
-    if (solver == ELLP_DUAL) o.engine = ELLP_ENGINE_REVISED;  // the tableau engine implements the primal path only
     if (base->trace) { o.trace = base->trace + *trace_off; o.trace_cap = std::max<int64_t>(0, base->trace_cap - *trace_off); if (o.trace_cap == 0) o.trace = nullptr; }
     ellp_result r;
     const int rc = (solver == ELLP_PRIMAL) ? ellp_b200_primal_solve_with_initial(ctx, &f, &p, &o, &r)

@@ -74,6 +74,10 @@ struct DevLP {
     int64_t ldv;
     double* coop;      // 6 * 1024 doubles: per-block partials of the cooperative pivot kernel (blocked.cuh)
     double* xchg;      // small exchange buffers: [0] local max key | [8..8+3) candidate | [16..16+G) gathered max | [32..32+3G) gathered candidates
+    // dual simplex on the tableau (dual_blocked.cuh): the basis the tableau was built from, needed to rebuild y from d
+    int32_t* Bv0;      // m: variable that was basic in row i when T was built
+    double* bscale;    // ld: diagonal of that basis when it was diagonal (generated LPs / identity start); scratch for the y right-hand side
+    double* dpos;      // nN: reduced costs of all nonbasic positions (download: all-gather of dj on the peer engine)
 };
 
 constexpr uint8_t kColBasic = 3;
@@ -1496,7 +1500,7 @@ __global__ void k_fill_uniform(double* __restrict__ out, uint64_t count, uint64_
 // col_lo/col_hi select the locally stored column range (column sharding); element values depend only on the
 // GLOBAL (row, column) index so every sharding sees the same LP.
 __global__ void k_gen_dense_cols(double* __restrict__ A, int64_t ld, int m, int64_t ns, int64_t col_lo, int64_t col_hi, uint64_t seed,
-                                 double slack_sign) {
+                                 double slack_sign, double struct_sign) {
     const int64_t ncol = col_hi - col_lo;
     const int64_t total = ncol * ld;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -1506,7 +1510,7 @@ __global__ void k_gen_dense_cols(double* __restrict__ A, int64_t ld, int m, int6
         if (i < m) {
             if (j < ns) {
                 const uint64_t h = splitmix64(seed * 0x2545f4914f6cdd1dull + (uint64_t)(j * m + i));
-                v = (double)(h >> 11) * (1.0 / 9007199254740992.0);
+                v = struct_sign * ((double)(h >> 11) * (1.0 / 9007199254740992.0));
             } else {
                 v = (j - ns == i) ? slack_sign : 0.;
             }

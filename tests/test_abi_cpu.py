@@ -178,3 +178,40 @@ def test_problem_builder_matches_reference_unit_tests():
         p.add_constraint([(VariableId(99), 1.0)], ConstraintOp.Eq, 0.0)
     p.add_constraint([(x, 2.0)], ConstraintOp.Lte, 1.0)
     assert p.is_feasible([0.5]) and not p.is_feasible([0.75]) and not p.is_feasible([0.1, 0.2])
+
+
+# ---------------------------------------------------------------- the header is valid C and the ctypes mirrors match it
+def _build_c_abi_smoke():
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "c_abi", "c_abi_smoke")
+    src = os.path.join(root, "tests", "c_abi", "c_abi_smoke.c")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(root, "include"), src, "-o", exe,
+                           "-L" + os.path.join(root, "ellp_b200"), "-lellp_b200", "-Wl,-rpath," + os.path.join(root, "ellp_b200"), "-lm"])
+    return exe
+
+
+def test_header_is_c99_and_struct_layouts_equal_the_ctypes_mirrors():
+    import json
+    import subprocess
+    from ellp_b200 import _native as N
+    exe = _build_c_abi_smoke()
+    lay = json.loads(subprocess.run([exe], capture_output=True, text=True, check=True).stdout)
+    pairs = {"ellp_std_form": N.StdForm, "ellp_point": N.Point, "ellp_opts": N.Opts, "ellp_result": N.Result, "ellp_batch": N.Batch,
+             "ellp_batch_result": N.BatchResult, "ellp_problem_desc": N.ProblemDesc, "ellp_solution": N.Solution}
+    checked = 0
+    for cname, cls in pairs.items():
+        assert lay["sizeof " + cname] == C.sizeof(cls), cname
+        names = [f[0] for f in cls._fields_]
+        cfields = [k.split(".", 1)[1] for k in lay if k.startswith(cname + ".")]
+        assert cfields == names, (cname, cfields, names)   # same fields in the same order
+        for f in names:
+            off, size = lay[f"{cname}.{f}"]
+            d = getattr(cls, f)
+            assert (d.offset, d.size) == (off, size), (cname, f)
+            checked += 1
+    assert lay["sizeof ellp_trace_rec"] == N.TRACE_DTYPE.itemsize
+    for f in N.TRACE_DTYPE.names:
+        off, size = lay[f"ellp_trace_rec.{f}"]
+        assert N.TRACE_DTYPE.fields[f][1] == off and N.TRACE_DTYPE.fields[f][0].itemsize == size
+    assert checked > 60

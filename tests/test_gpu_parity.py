@@ -788,3 +788,140 @@ def test_fused_pivot_kernel_with_more_rows_than_threads(env):
     np.testing.assert_allclose(x1, x0, rtol=1e-9, atol=1e-9)
     assert np.array_equal(B0, B1) and np.array_equal(N0, N1) and np.array_equal(Ns0, Ns1) and abs(obj0 - obj1) <= 1e-9 * abs(obj0)
 
+
+
+# ---------------------------------------------------------------- dual simplex on the blocked condensed tableau (dual_blocked.cuh)
+def _gte_dual_start(A, b, c):
+    """min c.x, A x - s = b, x,s >= 0 with the slack basis B = -I (dual feasible: y = 0, d = c >= 0)."""
+    m, n = A.shape
+    Af = np.asfortranarray(np.hstack([A, -np.eye(m)]))
+    cf = np.concatenate([c, np.zeros(m)])
+    kind = np.ones(n + m, dtype=np.uint8); lb = np.zeros(n + m); ub = np.zeros(n + m)
+    x0 = np.concatenate([np.zeros(n), -b]); B0 = np.arange(n, n + m, dtype=np.int32)
+    N0 = np.arange(n, dtype=np.int32); Ns0 = np.zeros(n, dtype=np.uint8)
+    return Af, cf, kind, lb, ub, [x0, B0, N0, Ns0, np.zeros(m), cf.copy()]
+
+
+@pytest.mark.parametrize("seed,m,n,bk", [(10, 24, 40, 2), (11, 64, 128, 7), (12, 130, 190, 32), (13, 64, 128, 64), (14, 260, 515, 32), (15, 132, 190, 0)])
+def test_dual_tableau_engine_matches_oracle_trace(env, seed, m, n, bk):
+    """dual_simplex_solver.rs:188-334 on the blocked tableau (general starting basis -I => T = B^-1 A_N through K4): same pivots,
+    x, y, d, B, N as the oracle."""
+    O, S, N = env["O"], env["S"], env["N"]
+    A, b, c = _dense_lp(seed, m, n)
+    Af, cf, kind, lb, ub, start = _gte_dual_start(A, b, c)
+    st = [a.copy() for a in start]
+    ref = O.solve_with_initial(O.DUAL, m, n + m, Af, cf, b, kind, lb, ub, *st, max_iter=None, trace_cap=20000)
+    sg = [a.copy() for a in start]
+    sol = S.GpuDualSimplexSolver.new(None, ctx=env["ctx"], trace_cap=20000, engine=N.ENGINE_TABLEAU, block_k=bk, check_every=5)
+    res, trace = sol.solve_with_initial(m, n + m, Af, cf, b, kind, lb, ub, *sg)
+    assert res.status == ref.status == O.OPTIMAL
+    assert res.iters == len(ref.trace) > 5
+    assert (trace["entering"] == ref.trace["entering"]).all() and (trace["leaving"] == ref.trace["leaving"]).all()
+    np.testing.assert_allclose(trace["step"], ref.trace["step"], rtol=1e-8, atol=1e-8)
+    np.testing.assert_allclose(trace["obj"], ref.trace["obj"], rtol=1e-8, atol=1e-8)
+    for g, o in zip(sg[:1] + sg[4:], st[:1] + st[4:]):
+        np.testing.assert_allclose(g, o, rtol=1e-9, atol=1e-9)
+    for g, o in zip(sg[1:4], st[1:4]):
+        np.testing.assert_array_equal(g, o)
+    assert _rel(res.obj, ref.obj) < 1e-9
+    # d = c - A^T y holds for the exported dual point
+    np.testing.assert_allclose(sg[5], cf - Af.T @ sg[4], rtol=0, atol=1e-8)
+
+
+@pytest.mark.parametrize("bk", [8, 32])
+@pytest.mark.parametrize("make", P.GOLDEN + [lambda n=n: P.netlib(n) for n in P.NETLIB],
+                         ids=[f.__name__ for f in P.GOLDEN] + P.NETLIB)
+def test_dual_tableau_engine_two_phase(env, make, bk):
+    """DualSimplexSolver::solve (dual_simplex_solver.rs:32-108) with both phases on the tableau engine: the starting bases come
+    from an LU of A^T (dual_problem.rs:140-160), i.e. they are NOT the identity."""
+    prob, exp = make()
+    O, N = env["O"], env["N"]
+    res = _solver(env, "dual", engine=N.ENGINE_TABLEAU, block_k=bk, trace_cap=8192).solve(prob)
+    obj = res.solution.obj() if res.is_optimal else float("nan")
+    x = res.solution.x() if res.is_optimal else []
+    P.check_expectation(exp, res.kind, obj, x)
+    ref = O.solve(prob, O.DUAL, 1000, O.MODE_EXACT, trace_cap=8192)
+    assert res.kind == ref.status_name
+    assert res.used_primal_fallback == ref.used_primal_fallback
+    if res.is_optimal:
+        assert _rel(obj, ref.obj) < 1e-9
+
+
+def test_afiro_dual_pivot_sequence_on_the_tableau_engine(env):
+    prob, _ = P.netlib("afiro")
+    O, N = env["O"], env["N"]
+    res = _solver(env, "dual", trace_cap=4096, engine=N.ENGINE_TABLEAU, block_k=16).solve(prob)
+    ref = O.solve(prob, O.DUAL, 1000, O.MODE_EXACT, trace_cap=4096)
+    assert res.iters == ref.iters
+    assert (res.trace["entering"] == ref.trace["entering"]).all()
+    assert (res.trace["leaving"] == ref.trace["leaving"]).all()
+    np.testing.assert_allclose(res.trace["step"], ref.trace["step"], rtol=1e-9, atol=1e-9)
+
+
+def test_generated_dual_lp_on_the_tableau_engine_matches_oracle_and_revised_engine(env):
+    import bench_lp
+    N, O, ctx = env["N"], env["O"], env["ctx"]
+    m, ns, seed, K = 64, 128, 9, 60
+    n = ns + m
+    lp = bench_lp.dense_lp(m, ns, seed, 1)
+    ref = O.solve_with_initial(O.DUAL, m, n, lp["A"], lp["c"], lp["b"], lp["kind"], lp["lb"], lp["ub"], lp["x"].copy(),
+                               lp["B"].copy(), lp["N"].copy(), lp["N_side"].copy(), lp["y"].copy(), lp["d"].copy(),
+                               max_iter=K, trace_cap=K)
+    k = len(ref.trace)
+    for bk in (8, 32):
+        o = N.default_opts(K, engine=N.ENGINE_TABLEAU, block_k=bk, check_every=16)
+        tr = np.zeros(K, dtype=N.TRACE_DTYPE); o.trace = N.ptr(tr); o.trace_cap = K
+        ctx.check(N.lib.ellp_b200_generate_dense_ex(ctx.h, m, ns, seed, 1, C.byref(o)))
+        res = N.Result()
+        ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(o), C.byref(res)))
+        assert res.status == ref.status and res.iters == k > 5
+        assert (tr["entering"][:k] == ref.trace["entering"]).all() and (tr["leaving"][:k] == ref.trace["leaving"]).all()
+        x = np.zeros(n); B = np.zeros(m, dtype=np.int32); Nv = np.zeros(ns, dtype=np.int32); Ns = np.zeros(ns, dtype=np.uint8)
+        y = np.zeros(m); d = np.zeros(n)
+        pt = N.Point(N.ptr(x), N.ptr(B), N.ptr(Nv), N.ptr(Ns), N.ptr(y), N.ptr(d), m, ns)
+        ctx.check(N.lib.ellp_b200_download(ctx.h, C.byref(pt)))
+        np.testing.assert_allclose(d, lp["c"] - lp["A"].T @ y, rtol=0, atol=1e-8)
+        np.testing.assert_allclose(lp["A"] @ x, lp["b"], rtol=1e-9, atol=1e-8)
+
+
+def test_dual_tableau_error_paths(env):
+    """Free nonbasic with a zero pivot-row entry and a zero reduced cost: 0 / 0 = NaN => partial_cmp().unwrap() panics
+    (dual :279); no eligible entering column => Infeasible (dual :281-284)."""
+    O, S, N = env["O"], env["S"], env["N"]
+    from ellp_b200.solver import EllPPanic
+    # x0 + s = -1, x0 >= 0, s >= 0 basic: row has only nonnegative entries for a Lower-side nonbasic => dual unbounded
+    A = np.asfortranarray(np.array([[1.0, 1.0]])); c = np.array([1.0, 0.0]); b = np.array([-1.0])
+    kind = np.array([N.LOWER, N.LOWER], dtype=np.uint8); lb = np.zeros(2); ub = np.zeros(2)
+    st = [np.array([0.0, -1.0]), np.array([1], dtype=np.int32), np.array([0], dtype=np.int32), np.array([0], dtype=np.uint8), np.zeros(1), c.copy()]
+    for engine in (N.ENGINE_TABLEAU, N.ENGINE_REVISED):
+        sg = [a.copy() for a in st]
+        res, _ = S.GpuDualSimplexSolver.new(None, ctx=env["ctx"], engine=engine, block_k=4).solve_with_initial(1, 2, A, c, b, kind, lb, ub, *sg)
+        so = [a.copy() for a in st]
+        ref = O.solve_with_initial(O.DUAL, 1, 2, A, c, b, kind, lb, ub, *so, max_iter=None)
+        assert res.status == ref.status == O.INFEASIBLE
+    # Free nonbasic column that is identically zero with d = 0: ratio 0 / 0
+    A = np.asfortranarray(np.array([[0.0, 1.0]])); c = np.array([0.0, 0.0])
+    kind = np.array([N.FREE, N.LOWER], dtype=np.uint8)
+    st = [np.array([0.0, -1.0]), np.array([1], dtype=np.int32), np.array([0], dtype=np.int32), np.array([N.NB_FREE], dtype=np.uint8), np.zeros(1), c.copy()]
+    for engine in (N.ENGINE_TABLEAU, N.ENGINE_REVISED):
+        sg = [a.copy() for a in st]
+        with pytest.raises(EllPPanic, match="unwrap"):
+            S.GpuDualSimplexSolver.new(None, ctx=env["ctx"], engine=engine, block_k=4).solve_with_initial(1, 2, A, c, b, kind, lb, ub, *sg)
+    # dual-infeasible starting point (dual :139-151)
+    A = np.asfortranarray(np.array([[1.0, 1.0]])); c = np.array([-1.0, 0.0])
+    kind = np.array([N.LOWER, N.LOWER], dtype=np.uint8)
+    st = [np.array([0.0, 1.0]), np.array([1], dtype=np.int32), np.array([0], dtype=np.int32), np.array([0], dtype=np.uint8), np.zeros(1), c.copy()]
+    with pytest.raises(EllPPanic, match="dual infeasible"):
+        S.GpuDualSimplexSolver.new(None, ctx=env["ctx"], engine=N.ENGINE_TABLEAU, block_k=4).solve_with_initial(1, 2, A, c, b, kind, lb, ub, *st)
+
+
+def test_plain_c_program_drives_the_boundary(env):
+    """tests/c_abi/c_abi_smoke.c (gcc -std=c99): primal + dual solve_with_initial and the reference's Err text from C."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "c_abi", "c_abi_smoke")
+    if not os.path.exists(exe):
+        import test_abi_cpu
+        exe = test_abi_cpu._build_c_abi_smoke()
+    out = subprocess.run([exe, "solve"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "C_ABI_SMOKE_OK" in out.stdout, out.stdout + out.stderr
