@@ -49,6 +49,8 @@ WORKLOADS = {
     "dense_revised_dual_4096x12288": dict(m=4096, ns=8192, pivots=200, sample_m=512, sample_pivots=6, dual=True),
     # the same LP and rules on the blocked condensed tableau (dual_blocked.cuh): one cooperative launch per block of pivots
     "dense_tableau_dual_4096x12288": dict(m=4096, ns=8192, pivots=960, block_k=48, sample_m=512, sample_pivots=6, dual=True, tableau=True),
+    # ... and with dual Devex pricing (reference weights updated from the entering column, no extra pass): a step = one whole solve
+    "dense_tableau_dual_devex_4096x12288": dict(m=4096, ns=8192, pivots=200, block_k=48, sample_m=512, sample_pivots=6, dual=True, tableau=True, devex=True),
     "dense_tableau_dual_16384x32768": dict(m=16384, ns=16384, pivots=672, block_k=48, sample_m=1024, sample_pivots=3, dual=True, tableau=True),
     "dense_tableau_dual_32768x65536": dict(m=32768, ns=32768, pivots=672, block_k=56, sample_m=1024, sample_pivots=3, dual=True, tableau=True),
     # the same LP with dual steepest edge (exact weights from the rank-1 update's epilogue) + Harris ratio test
@@ -80,9 +82,22 @@ def measured_peak():
 # fp64 tensor pipe (DMMA m8n8k4) peak of one B200: MEASURED_PEAKS.json carries no fp64 figure, so the denominator is derived
 # from ncu: sm__pipe_tensor_subpipe_dmma_cycles_active = 62.1 % at 22.9 TFLOP/s (profiles/r01_ncu_full_blk_flush_k32_summary.txt)
 # => 36.9 TFLOP/s = 148 SMs x 64 fp64 FMA/clk x 1.965 GHz.
-DMMA_PEAK_TFLOPS = 36.9
-DMMA_PEAK_SOURCE = ("derived from ncu (dmma pipe 62.1 % active at 22.9 TFLOP/s, profiles/r01_ncu_full_blk_flush_k32_summary.txt) = "
-                    "148 SMs x 64 fp64 FMA/clk x 1.965 GHz; MEASURED_PEAKS.json has no fp64 entry")
+DMMA_NOMINAL_TFLOPS = 36.9
+
+
+def _fp64_peak():
+    """Denominator of the fp64 tensor roofline: cuBLAS DGEMM 8192^3 MEASURED on this pool's B200 (tools/fp64_peaks.py ->
+    profiles/r02_fp64_peaks.json, burst = best of 10 for a kernel timed alone); the 148 x 64 x 1.965 GHz figure stays as nominal."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_fp64_peaks.json")) as f:
+            d = json.load(f)["dgemm_8192"]
+        return float(d["tflops_burst"]), ("measured cuBLAS DGEMM 8192^3 on this pool's B200 (profiles/r02_fp64_peaks.json: burst %.2f, sustained %.2f TFLOP/s); "
+                                          "nominal 148 SMs x 64 fp64 FMA/clk x 1.965 GHz = %.1f" % (d["tflops_burst"], d["tflops_sustained"], DMMA_NOMINAL_TFLOPS))
+    except Exception:
+        return DMMA_NOMINAL_TFLOPS, "nominal 148 SMs x 64 fp64 FMA/clk x 1.965 GHz (profiles/r02_fp64_peaks.json missing)"
+
+
+DMMA_PEAK_TFLOPS, DMMA_PEAK_SOURCE = _fp64_peak()
 
 
 def blocked_roofline(roofline: dict, m: int, cols: int, bk: int, ms: float) -> dict:
@@ -93,7 +108,8 @@ def blocked_roofline(roofline: dict, m: int, cols: int, bk: int, ms: float) -> d
     t_hbm = roofline["algorithmic_bytes_per_launch"] / (roofline["peak"] * 1e9)
     t_dmma = 2.0 * m * cols * bk / (DMMA_PEAK_TFLOPS * 1e12)
     roofline["hbm"] = hbm
-    roofline["tensor_fp64"] = {"achieved": tfl, "peak": DMMA_PEAK_TFLOPS, "frac": tfl / DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "peak_source": DMMA_PEAK_SOURCE}
+    roofline["tensor_fp64"] = {"achieved": tfl, "peak": DMMA_PEAK_TFLOPS, "frac": tfl / DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "peak_source": DMMA_PEAK_SOURCE,
+                               "nominal": DMMA_NOMINAL_TFLOPS, "frac_of_nominal": tfl / DMMA_NOMINAL_TFLOPS}
     roofline["pivots_per_launch"] = bk
     roofline["roofline_ms"] = 1e3 * max(t_hbm, t_dmma)
     roofline["frac_of_binding_roofline"] = 1e3 * max(t_hbm, t_dmma) / ms
@@ -101,6 +117,29 @@ def blocked_roofline(roofline: dict, m: int, cols: int, bk: int, ms: float) -> d
         roofline.update(bound="tensor", achieved=tfl, peak=DMMA_PEAK_TFLOPS, unit="TFLOP/s", frac=tfl / DMMA_PEAK_TFLOPS, peak_source=DMMA_PEAK_SOURCE)
         roofline.pop("frac_of_8TBs_nominal", None)
     return roofline
+
+
+def k3_target_leg(ctx, N, peak, peak_src, R=16384, Cc=32768, reps=20):
+    """north_star's kernel target on a driver-visible record: K3 (k_rank1, the rank-1 row reduction that replaces the reference's
+    per-pivot LU) on a 16384 x 32768 fp64 matrix that never leaves HBM; algorithmic bytes 16 R C + 8 (R + C) per launch, timed
+    with CUDA events on the library's stream (ellp_b200_rank1_update_dev)."""
+    E = C.c_void_p(); al = C.c_void_p()
+    ctx.check(N.lib.ellp_b200_dev_alloc(ctx.h, 8 * R * Cc, C.byref(E)))
+    ctx.check(N.lib.ellp_b200_dev_alloc(ctx.h, 8 * R, C.byref(al)))
+    try:
+        ctx.check(N.lib.ellp_b200_dev_fill_uniform(ctx.h, E, R * Cc, 11, 0, 0.0, 1.0))
+        ctx.check(N.lib.ellp_b200_dev_fill_uniform(ctx.h, al, R, 12, 0, 0.5, 1.5))
+        ms = C.c_float(0)
+        ctx.check(N.lib.ellp_b200_rank1_update_dev(ctx.h, E, R, Cc, R, al, R // 3, 3, C.byref(ms)))      # warm-up
+        ctx.check(N.lib.ellp_b200_rank1_update_dev(ctx.h, E, R, Cc, R, al, R // 3, reps, C.byref(ms)))
+    finally:
+        ctx.check(N.lib.ellp_b200_dev_free(ctx.h, E))
+        ctx.check(N.lib.ellp_b200_dev_free(ctx.h, al))
+    alg = 16.0 * R * Cc + 8.0 * (R + Cc)
+    gbs = alg / (ms.value * 1e-3) / 1e9
+    return {"kernel": "k_rank1<STREAM> (K3) on a %d x %d fp64 matrix (8.59 GB >> L2)" % (R, Cc), "ms": float(ms.value), "launches_timed": reps,
+            "algorithmic_bytes_per_launch": alg, "GB/s": gbs, "peak": peak, "frac": gbs / peak, "frac_of_8TBs_nominal": gbs / 8000.0,
+            "peak_source": peak_src, "target": ">= 0.70 of HBM bandwidth (BASELINE.json north_star)", "met": gbs / peak >= 0.70}
 
 
 class ClockSampler:
@@ -199,6 +238,32 @@ def cpu_reference_sample(wl: dict, pivots: int):
                             f"{wl['m']}^3 dense LU: ~{(wl['m'] / ms) ** 3 * dt / pivots:.0f} s extrapolated)"
 
 
+def cpu_scaling_fields(wl: dict, value: float, budget_s: float = 25.0) -> dict:
+    """Structured form of the CPU sample: its size, the m^3 extrapolation to the full workload, and measured seconds per pivot
+    at 2x (and, budget permitting, 4x) the sample size that back the cubic law (one dense LU per pivot, primal :173 / dual :241)."""
+    ms = wl["sample_m"]
+    out = {"sample_config": {"m": ms, "n": ms + int(ms * wl["ns"] / wl["m"])}, "same_config_as_gpu_arm": ms == wl["m"],
+           "seconds_per_pivot": {str(ms): 1.0 / value}}
+    t_used = 0.0
+    for mult in (2, 4):
+        mm = ms * mult
+        est = (mult ** 3) / value
+        if mm > wl["m"] or t_used + est > budget_s:
+            break
+        v, dtc, _ = cpu_reference_sample(dict(wl, sample_m=mm), 1)
+        out["seconds_per_pivot"][str(mm)] = 1.0 / v
+        t_used += dtc
+    sizes = sorted(int(k) for k in out["seconds_per_pivot"])
+    if len(sizes) >= 2:
+        a, b = sizes[0], sizes[-1]
+        out["measured_exponent"] = float(np.log(out["seconds_per_pivot"][str(b)] / out["seconds_per_pivot"][str(a)]) / np.log(b / a))
+    big = sizes[-1]
+    out["extrapolated_full_size_seconds_per_pivot"] = out["seconds_per_pivot"][str(big)] * (wl["m"] / big) ** 3
+    out["extrapolated_full_size_pivots_per_s"] = 1.0 / out["extrapolated_full_size_seconds_per_pivot"]
+    out["extrapolation"] = f"m^3 law from the largest timed size ({big}) to m = {wl['m']}"
+    return out
+
+
 def run_reference(args, wl, name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -211,11 +276,15 @@ def run_reference(args, wl, name):
         _, _, sample = cpu_reference_sample(wl, P)
     dt = time.perf_counter() - t0
     value = args.steps * P / dt
+    cpu = {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample, "host_cores_available": os.cpu_count(),
+           "threads_note": "ellp's loop is single-threaded (nalgebra LU, no rayon): 1 core is all the reference uses"}
+    cpu.update(cpu_scaling_fields(wl, value))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "m": wl["m"], "n": wl["m"] + wl["ns"]},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "config": {"workload": name, "m": wl["m"], "n": wl["m"] + wl["ns"], "timed_sample": cpu["sample_config"],
+                       "note": "one reference pivot at the full size is a %d^3 dense LU (~%.0f s extrapolated): the timed steps run the same generator at the sample size" % (wl["m"], cpu["extrapolated_full_size_seconds_per_pivot"])},
+            "cpu_baseline": cpu,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -454,7 +523,7 @@ def run_ours(args, wl, name):
     dual = bool(wl.get("dual"))
     tab = (not dual) or bool(wl.get("tableau"))
     engine = N.ENGINE_TABLEAU if tab else N.ENGINE_REVISED
-    rules = dict(pricing=N.PRICE_STEEPEST_EDGE, ratio=N.RATIO_HARRIS) if wl.get("dse") else {}
+    rules = dict(pricing=N.PRICE_STEEPEST_EDGE, ratio=N.RATIO_HARRIS) if wl.get("dse") else (dict(pricing=N.PRICE_DEVEX) if wl.get("devex") else {})
     bk = 0 if not tab else (wl.get("block_k", 0) if args.block_k < 0 else args.block_k)
     if bk > 1:
         rules["block_k"] = bk
@@ -463,7 +532,7 @@ def run_ours(args, wl, name):
     o = N.default_opts(P, engine=engine, check_every=min(P, max(16, bk)), profile=tab, **rules)
     ctx.check(N.lib.ellp_b200_generate_dense_ex(ctx.h, m, ns, SEED, 1 if dual else 0, C.byref(o)))
 
-    full_solve = bool(wl.get("dse"))  # steepest edge reaches the optimum within a few hundred pivots: a step = one whole solve
+    full_solve = bool(wl.get("dse") or wl.get("devex"))  # steepest edge / Devex reach the optimum within a few hundred pivots: a step = one whole solve
     if full_solve:
         o.max_iter = N.U64_MAX
 
@@ -534,6 +603,11 @@ def run_ours(args, wl, name):
                 "algorithmic_bytes_per_launch": alg_bytes, "share_of_step_device_time": (rank1_ms / dev_ms) if dev_ms else None}
     if bk > 1 and n_rank1:
         roofline = blocked_roofline(roofline, m, k3_cols, bk, k3_ms)
+    if name == DEFAULT_WORKLOAD or getattr(args, "k3_target", False):
+        try:
+            roofline["k3_target"] = k3_target_leg(ctx, N, peak, peak_src)
+        except Exception as e:  # never lose the bench line over the extra leg
+            roofline["k3_target"] = {"error": str(e)}
 
     # ---- e2e: the C-ABI boundary on HOST buffers (H2D + pivots + D2H inside the timed region)
     e2e = None
@@ -592,13 +666,14 @@ def run_ours(args, wl, name):
         v, dtc, sample = cpu_reference_sample(wl, max(6, wl["sample_pivots"] * 20))
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample, "seconds": dtc,
                "host_cores_available": os.cpu_count()}
+        cpu.update(cpu_scaling_fields(wl, v, budget_s=14.0))
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": name, "m": m, "n": n, "pivots_per_step": P, "engine": "revised (explicit B^-1), dual simplex" if not tab else (("dual simplex, " if dual else "") + "condensed tableau (nonbasic columns of B^-1 A resident), " + (f"blocked: one cooperative launch per {bk} pivots + one rank-{bk} flush" if bk > 1 else "rank-1 update per pivot")),
                        "block_k": bk,
-                       "tie_rule": "reference folds", "dual_rules": "steepest edge + Harris" if wl.get("dse") else "reference (first infeasible / first min ratio)", "l2": (f"A_N {8.0 * m * ns / 1e6:.0f} MB + B^-1 {8.0 * m * m / 1e6:.0f} MB streamed every pivot (> 126 MB L2, no flush)" if not tab
+                       "tie_rule": "reference folds", "dual_rules": "steepest edge + Harris" if wl.get("dse") else ("Devex leaving row, reference ratio test" if wl.get("devex") else "reference (first infeasible / first min ratio)"), "l2": (f"A_N {8.0 * m * ns / 1e6:.0f} MB + B^-1 {8.0 * m * m / 1e6:.0f} MB streamed every pivot (> 126 MB L2, no flush)" if not tab
                               else f"condensed tableau {8.0 * m * ns / 1e9:.1f} GB >> 126 MB L2 (no L2 flush needed)"),
                        "baseline_config": "BASELINE.json configs[4]" if name == DEFAULT_WORKLOAD else "north_star / smaller variant"},
             "device_ms_per_step": dev_ms_timed / args.steps, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
@@ -614,6 +689,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--k3-target", action="store_true", help="also time K3 (k_rank1) at the north_star target size 16384x32768 (always on for the default workload)")
     ap.add_argument("--pivots", type=int, default=0, help="pivots per step (0 = workload default)")
     ap.add_argument("--block-k", type=int, default=-1, help="tableau engine: pivots per deferred rank-k row reduction (-1 = workload default, 0 = rank-1 engine)")
     ap.add_argument("--no-e2e", action="store_true")

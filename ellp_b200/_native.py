@@ -19,7 +19,7 @@ OPTIMAL, INFEASIBLE, UNBOUNDED, MAXITER = 0, 1, 2, 3
 PRIMAL, DUAL = 0, 1
 TIES_REFERENCE, TIES_CANONICAL = 0, 1
 ENGINE_AUTO, ENGINE_REVISED, ENGINE_TABLEAU = 0, 1, 2
-PRICE_REFERENCE, PRICE_STEEPEST_EDGE = 0, 1
+PRICE_REFERENCE, PRICE_STEEPEST_EDGE, PRICE_DEVEX = 0, 1, 2
 RATIO_REFERENCE, RATIO_HARRIS = 0, 1
 U64_MAX = 2**64 - 1
 FREE, LOWER, UPPER, TWOSIDED, FIXED = 0, 1, 2, 3, 4   # ellp_bound_kind (problem.rs:190-197)
@@ -120,6 +120,8 @@ def _load():
         "ellp_b200_comm_unique_id": (C.c_int, [C.c_char_p, vp]),
         "ellp_b200_comm_init": (C.c_int, [vp, C.c_char_p, vp, C.c_int, C.c_int]),
         "ellp_b200_sharded_generate_dense": (C.c_int, [vp, i32, i32, u64, C.POINTER(Opts)]),
+        "ellp_b200_sharded_generate_dense_ex": (C.c_int, [vp, i32, i32, u64, i32, C.POINTER(Opts)]),
+        "ellp_b200_sharded_upload_nonbasic_ex": (C.c_int, [vp, C.POINTER(StdForm), C.POINTER(Point), C.c_int, vp, C.POINTER(Opts)]),
         "ellp_b200_sharded_upload": (C.c_int, [vp, C.POINTER(StdForm), C.POINTER(Point), C.POINTER(Opts)]),
         "ellp_b200_phase_log": (C.c_int, [vp, C.POINTER(C.c_int64), C.c_int32]),
         "ellp_b200_sharded_upload_nonbasic": (C.c_int, [vp, C.POINTER(StdForm), C.POINTER(Point), C.POINTER(Opts)]),

@@ -35,6 +35,8 @@
 
 namespace ellp {
 
+constexpr double kDualSnapUlps = 16.;
+
 struct LexAcc {
     double v, al;  // ratio, pivot-row entry of the candidate
     int p;         // global nonbasic position, -1 = no candidate
@@ -91,13 +93,11 @@ __device__ __forceinline__ bool dual_violation(int kind, double lb, double ub, d
     return false;  // Free and Fixed basic variables never leave (:204, :232)
 }
 
-// steepest-edge variant of the leaving rule (no reference counterpart): score = infeasibility^2 / w_i, ties: smallest position
-struct LeaveCand {
-    double key;    // reference rule: (double)position (minimised); steepest edge: -score (minimised)
-    double delta;
-    int i;         // -1 = none
-};
-
+// DEVEX = true: leaving row = argmax infeasibility^2 / w_i with dual Devex reference weights (ELLP_PRICE_DEVEX; no reference
+// counterpart: ellp picks the first infeasible row): w starts at 1 (reference framework = the starting basis), and after a pivot
+// on (r, q): w_i = max(w_i, (alpha_q[i] / alpha_q[r])^2 w_r) for i != r, w_r = max(w_r / alpha_q[r]^2, 1) -- all from the
+// entering column every row thread holds anyway, so the rule costs no extra pass and no extra exchange.
+template <bool DEVEX>
 __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_dual_pivots_fused(DevLP lp, PeerLinks pl, int slot0, int npiv, uint32_t seq0, PivotState* st) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
@@ -127,22 +127,27 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_dual_pivots_fused(D
         const int par = (int)(seq & 1u);
         // ---- L (first pivot of the launch only; afterwards phase C did it): first infeasible basis position (dual :200-236)
         if (!have_L) {
-            Top2 t{CUDART_INF, CUDART_INF, -1};
+            Top2 t{DEVEX ? -1.0 : CUDART_INF, DEVEX ? -1.0 : CUDART_INF, -1};
             double my_delta = 0.;
             for (int64_t i = gtid; i < m; i += gsize) {
                 const int var = __ldcg(lp.Bv + i);
                 double dl;
-                if (dual_violation(lp.kind[var], lp.lb[var], lp.ub[var], __ldcg(lp.x + var), &dl)) { t.a1 = (double)i; t.i1 = (int)i; my_delta = dl; break; }
+                if (dual_violation(lp.kind[var], lp.lb[var], lp.ub[var], __ldcg(lp.x + var), &dl)) {
+                    if (DEVEX) {
+                        const double score = dl * dl / __ldcg(lp.w + i);
+                        if (score > t.a1) { t.a1 = score; t.i1 = (int)i; my_delta = dl; }
+                    } else { t.a1 = (double)i; t.i1 = (int)i; my_delta = dl; break; }
+                }
             }
             const int mine = t.i1;
-            t = top2_block_fast<false>(t, &s_top, rbuf);
+            t = top2_block_fast<DEVEX>(t, &s_top, rbuf);
             if (mine >= 0 && mine == t.i1) s_delta = my_delta;
             __syncthreads();
             ll_publish(llA, par, t, (t.i1 >= 0) ? s_delta : 0., seq);
         }
         double delta;
         ll_gather(llA, par, G, s_part, seq);
-        const Top2 L = ll_reduce<false>(s_part, G, &s_top, rbuf, &s_extra, &delta);
+        const Top2 L = ll_reduce<DEVEX>(s_part, G, &s_top, rbuf, &s_extra, &delta);
         if (L.i1 < 0) {  // no infeasible basic variable: optimal (:243-246)
             if (gtid == 0) { st->status = ELLP_OPTIMAL; st->do_update = 0; st->do_step = 0; }
             run = false;
@@ -150,6 +155,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_dual_pivots_fused(D
             continue;
         }
         const int r = L.i1;
+        const double w_r = DEVEX ? __ldcg(lp.w + r) : 1.;
         const bool neg = delta < 0.;
         const int new_side = neg ? ELLP_NB_LOWER : ELLP_NB_UPPER;
         // ---- R: pivot row over the local positions, ratios, lexicographic minimum (dual :255-279)
@@ -234,7 +240,14 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_dual_pivots_fused(D
                 } else {
                     const double a_raw = (t == gtid) ? a_first : lp.rN[t];
                     Vslot[t] = a_raw / alpha_rq;
-                    lp.dj[t] = __ldcg(lp.dj + t) - theta_d * a_raw;  // :298-300
+                    const double dold = __ldcg(lp.dj + t), prod = theta_d * a_raw;
+                    double dnew = dold - prod;  // :298-300
+                    // A difference that cancels to a few ulps of its operands is an exact tie of the ratio test (d_t / alpha_t ==
+                    // theta_dual) seen through rounding: store the exact zero.  The pivot row of the tableau carries other rounding
+                    // errors than the reference's A_N^T rho, so without this the next degenerate ratio test would rank its ties by
+                    // +-1e-17 / alpha_t -- i.e. prefer the SMALLEST pivot element -- instead of by position (dual :270-279).
+                    if (fabs(dnew) <= kDualSnapUlps * 2.220446049250313e-16 * fmax(fabs(dold), fabs(prod))) dnew = 0.;
+                    lp.dj[t] = dnew;
                 }
             } else {
                 Vslot[t] = 0.;
@@ -249,16 +262,17 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_dual_pivots_fused(D
         g_next.obj = g.obj + theta_d * delta;  // :316
         if (g_next.pivots >= g.max_iter) run = false;  // :191-194 at the next loop head
         const bool want_L = run && (slot + 1 < slot0 + npiv);
-        Top2 tl{CUDART_INF, CUDART_INF, -1};
+        Top2 tl{DEVEX ? -1.0 : CUDART_INF, DEVEX ? -1.0 : CUDART_INF, -1};
         double my_delta = 0.;
         const uint4* colbuf = pl.col[me] + (int64_t)par * pl.col_cap;
         for (int64_t i = gtid; i < lp.ld; i += gsize) {
             int var = 0, kv = ELLP_FIXED;
-            double xv = 0., lbv = 0., ubv = 0.;
+            double xv = 0., lbv = 0., ubv = 0., w_i = 1.;
             if (i < m) {  // independent of the column: in flight while the column entry is rebuilt / polled
                 var = __ldcg(lp.Bv + i);
                 xv = __ldcg(lp.x + var);
                 kv = lp.kind[var]; lbv = lp.lb[var]; ubv = lp.ub[var];
+                if (DEVEX) w_i = __ldcg(lp.w + i);
             }
             double a;
             if (owner) {
@@ -301,8 +315,18 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_dual_pivots_fused(D
                     if (g_next.pivots >= g.max_iter) st->status = ELLP_MAXITER;
                     kv = lp.kind[q_var]; lbv = lp.lb[q_var]; ubv = lp.ub[q_var];
                 }
+                if (DEVEX) {
+                    const double ratio = a / alpha_rq;
+                    w_i = (i == r) ? fmax(w_r / (alpha_rq * alpha_rq), 1.) : fmax(w_i, ratio * ratio * w_r);
+                    lp.w[i] = w_i;
+                }
                 double dl;
-                if (want_L && tl.i1 < 0 && dual_violation(kv, lbv, ubv, xv, &dl)) { tl.a1 = (double)i; tl.i1 = (int)i; my_delta = dl; }
+                if (want_L && dual_violation(kv, lbv, ubv, xv, &dl)) {
+                    if (DEVEX) {
+                        const double score = dl * dl / w_i;
+                        if (score > tl.a1) { tl.a1 = score; tl.i1 = (int)i; my_delta = dl; }
+                    } else if (tl.i1 < 0) { tl.a1 = (double)i; tl.i1 = (int)i; my_delta = dl; }
+                }
             }
             Uslot[i] = (i < m ? a : 0.) - (i == r ? 1. : 0.);
         }
@@ -310,7 +334,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_dual_pivots_fused(D
         have_L = false;
         if (want_L) {  // phase L of the next pivot
             const int mine = tl.i1;
-            tl = top2_block_fast<false>(tl, &s_top, rbuf);
+            tl = top2_block_fast<DEVEX>(tl, &s_top, rbuf);
             if (mine >= 0 && mine == tl.i1) s_delta = my_delta;
             __syncthreads();
             ll_publish(llA, par ^ 1, tl, (tl.i1 >= 0) ? s_delta : 0., seq + 1u);

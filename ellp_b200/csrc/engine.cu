@@ -127,13 +127,14 @@ struct ellp_b200_ctx {
     int64_t peer_cap = 0;         // rows per parity slot of the column buffers
     uint32_t xseq = 0;            // pivots exchanged since the communicator was created (wire sequence number)
     int coop_grid_fused = 0;
-    int coop_grid_dual = 0, coop_threads_cached_dual = 0;  // k_blk_dual_pivots_fused
+    int coop_grid_dual[2] = {0, 0}, coop_threads_cached_dual[2] = {0, 0};  // k_blk_dual_pivots_fused<false / true>
     // tableau engines with a general (non-identity) starting basis: B^-1 of the basis the tableau was built from lives in
     // lp.G / lp.Binv (has_binv), with the scratch the blocked LU needs next to the tableau's own U / V
     bool has_binv = false;
     double* rf_V = nullptr;       // kPanel x rf_ldv block row of the LU
     int64_t rf_ldv = 0;
     double* rf_coop = nullptr;    // publication slots of the cooperative panel kernel
+    bool devex_live = false;      // lp.w holds Devex reference weights of the resident solve (reset by upload / generate / refactor)
     bool dj_live = false;         // dual on the tableau: dj (not lp.d) holds the current reduced costs of the nonbasic positions
     bool tab_from_binv = false;   // T was built as B^-1 A_N (y at download = B^-T (c_B0 - d_B0)); false: diagonal starting basis (bscale)
     long long* tlog = nullptr;    // phase-timing log of k_blk_pivots_fused (tuning key "phase_timing")
@@ -615,6 +616,7 @@ int refactor(ellp_b200_ctx* ctx, uint64_t* count) {
     if (err == kErrSingular) return set_err(ctx, ELLP_E_ELLP, dev_err_message(err));
     ctx->binv_valid = true;
     ctx->pivots_since_refactor = 0;
+    if (ctx->tableau && ctx->devex_live) LAUNCH(k_fill_const, (int)((lp.ld + 255) / 256), 256, lp.w, (int64_t)lp.ld, 1.0);  // new reference framework
     if (count) ++*count;
     return ELLP_OK;
 }
@@ -711,18 +713,22 @@ void carve_peer(Arena& a, DevLP& lp, int64_t trace_cap, int blk_kmax) {
     lp.part = a.take<double>(8);
     lp.lam = a.take<double>(m);
     lp.lu_piv = a.take<int32_t>(m);
-    lp.w = lp.npart = nullptr;
+    lp.w = a.take<double>(ld);
+    lp.npart = nullptr;
+    lp.Bv0 = a.take<int32_t>(m);
+    lp.bscale = a.take<double>(ld);
+    lp.dpos = a.take<double>(nN);
     lp.trace = trace_cap > 0 ? a.take<ellp_trace_rec>((size_t)trace_cap) : nullptr;
     lp.colstat = nullptr;
     lp.xchg = nullptr;
 }
 
-int peer_prepare(ellp_b200_ctx* ctx, int32_t m, int32_t n_glob, const ellp_opts* o, DevLP* out) {
+int peer_prepare(ellp_b200_ctx* ctx, int32_t m, int32_t n_glob, const ellp_opts* o, DevLP* out, int solver = ELLP_PRIMAL) {
     if (!ctx->nccl_comm) return set_err(ctx, ELLP_E_ARG, "call ellp_b200_comm_init first");
     const int nN = n_glob - m;
     if (nN <= 0 || nN % ctx->nranks != 0) return set_err(ctx, ELLP_E_ARG, "peer sharding needs the number of nonbasic columns (n - m) divisible by the number of ranks");
     if (m % 4 != 0) return set_err(ctx, ELLP_E_ARG, "column sharding needs m % 4 == 0");
-    const int blk = blk_slots(o, true);
+    const int blk = blk_slots(o, true, solver);
     if (blk <= 1) return set_err(ctx, ELLP_E_ARG, "the peer-memory engine needs ellp_opts::block_k > 1");
     DevLP lp{};
     lp.m = m;
@@ -749,22 +755,39 @@ int peer_prepare(ellp_b200_ctx* ctx, int32_t m, int32_t n_glob, const ellp_opts*
     ctx->KS = 1;
     ctx->kc = 64;
     ctx->trace_cap = tcap;
-    ctx->solver = ELLP_PRIMAL;
+    ctx->solver = solver;
     ctx->tableau = true;
     ctx->sharded = true;
     ctx->peer_mode = true;
+    ctx->has_binv = false;
+    ctx->tab_from_binv = false;
+    ctx->dj_live = false;
+    ctx->devex_live = false;
+    ctx->a_resident = true;  // lp.A aliases the local slice of T (= A_N while the tableau is fresh): download_std_form reads it
     ctx->dual_obj0 = 0.;
     *out = lp;
     return ELLP_OK;
 }
 
 // reduced-cost row of the local positions of the fresh tableau (identity basis: T = A_N)
-int peer_finish_init(ellp_b200_ctx* ctx) {
+// (primal) / dj = d of the local positions (dual).  diag_scaled: lp.bscale holds the diagonal of the starting basis and T still
+// holds A_N: divide its rows (T = D^-1 A_N).
+int peer_finish_init(ellp_b200_ctx* ctx, bool diag_scaled = false) {
     DevLP& lp = ctx->lp;
     LAUNCH(k_init_cB, (int)((lp.ld + 255) / 256), 256, lp);
-    LAUNCH(k_gemv_t<EPI_PLAIN>, gemv_grid(lp.nT), 256, lp.T, lp.ld, (const int32_t*)nullptr, lp.nT, lp.cB, lp.dj, (const double*)nullptr,
-           (const uint8_t*)nullptr, (double*)nullptr, (PivotState*)nullptr, 0);
-    LAUNCH(k_redcost_pos_local, (lp.nT + 255) / 256, 256, lp.c, lp.Nv, lp.pos_lo, lp.nT, lp.dj);
+    CUDA_TRY(cudaMemcpyAsync(lp.Bv0, lp.Bv, sizeof(int32_t) * (size_t)lp.m, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (diag_scaled) {
+        dim3 gs((unsigned)((lp.ld / 2 + 255) / 256), (unsigned)std::min(lp.nT, 4096));
+        LAUNCH(k_scale_rows_inv, gs, 256, lp.T, lp.ld, lp.m, lp.nT, (const double*)lp.bscale);
+    }
+    if (ctx->solver == ELLP_DUAL) {
+        LAUNCH(k_dual_tab_init, (lp.nT + 255) / 256, 256, lp);
+        ctx->dj_live = true;
+    } else {
+        LAUNCH(k_gemv_t<EPI_PLAIN>, gemv_grid(lp.nT), 256, lp.T, lp.ld, (const int32_t*)nullptr, lp.nT, lp.cB, lp.dj, (const double*)nullptr,
+               (const uint8_t*)nullptr, (double*)nullptr, (PivotState*)nullptr, 0);
+        LAUNCH(k_redcost_pos_local, (lp.nT + 255) / 256, 256, lp.c, lp.Nv, lp.pos_lo, lp.nT, lp.dj);
+    }
     ctx->resident = true;
     ctx->lp_generation++;
     ctx->binv_valid = true;
@@ -779,10 +802,11 @@ int peer_finish_init(ellp_b200_ctx* ctx) {
 int launch_coop_pivots_peer(ellp_b200_ctx* ctx, const ellp_opts* o, int npiv, bool self_only) {
     DevLP& lp = ctx->lp;
     const bool dual = (ctx->solver == ELLP_DUAL);  // dual_blocked.cuh: same layout, same exchange buffers, no tie folds (no dynamic smem)
-    const void* fn = dual ? (const void*)k_blk_dual_pivots_fused : (const void*)k_blk_pivots_fused;
+    const bool devex = dual && o->pricing == ELLP_PRICE_DEVEX;
+    const void* fn = dual ? (devex ? (const void*)k_blk_dual_pivots_fused<true> : (const void*)k_blk_dual_pivots_fused<false>) : (const void*)k_blk_pivots_fused;
     const size_t smem = dual ? 0 : (size_t)kScanSmemBytes;
-    int& grid_cap = dual ? ctx->coop_grid_dual : ctx->coop_grid_fused;
-    int& threads_cached = dual ? ctx->coop_threads_cached_dual : ctx->coop_threads_cached;
+    int& grid_cap = dual ? ctx->coop_grid_dual[devex ? 1 : 0] : ctx->coop_grid_fused;
+    int& threads_cached = dual ? ctx->coop_threads_cached_dual[devex ? 1 : 0] : ctx->coop_threads_cached;
     // the fused kernel runs with small blocks: its phases are latency-bound and every block-wide reduction / barrier costs
     // issue slots per resident warp (measured: 256 threads per block beat 1024)
     const int threads = std::max(64, std::min(kFusedMaxThreads, ctx->coop_threads & ~31));
@@ -1078,7 +1102,7 @@ int ellp_b200_set_tuning(ellp_b200_ctx* ctx, const char* key, int value) {
     else if (!std::strcmp(key, "small_path")) ctx->small_path = value;
     else if (!std::strcmp(key, "peer_exchange")) ctx->peer_exchange = value;
     else if (!std::strcmp(key, "coop_threads")) ctx->coop_threads = value;
-    else if (!std::strcmp(key, "coop_ctas_per_sm")) { ctx->coop_ctas_per_sm = value; ctx->coop_threads_cached = 0; ctx->coop_threads_cached_dual = 0; }
+    else if (!std::strcmp(key, "coop_ctas_per_sm")) { ctx->coop_ctas_per_sm = value; ctx->coop_threads_cached = 0; ctx->coop_threads_cached_dual[0] = ctx->coop_threads_cached_dual[1] = 0; }
     else if (!std::strcmp(key, "phase_timing")) {  // value = pivots to log (0 = off); read back with ellp_b200_phase_log
         if (ctx->tlog) { cudaFree(ctx->tlog); ctx->tlog = nullptr; }
         ctx->tlog_cap = 0;
@@ -1148,6 +1172,7 @@ int ellp_b200_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_poi
     ctx->rf_V = rf.V; ctx->rf_ldv = rf.ldv; ctx->rf_coop = rf.coop;
     ctx->tab_from_binv = false;
     ctx->dj_live = false;
+    ctx->devex_live = false;
     cudaStream_t s = ctx->stream;
     // zero the padded scratch once (padding rows must stay zero)
     CUDA_TRY(cudaMemsetAsync(lp.cB, 0, (size_t)((char*)lp.lam - (char*)lp.cB), s));
@@ -1268,6 +1293,7 @@ int ellp_b200_generate_dense_ex(ellp_b200_ctx* ctx, int32_t m, int32_t n_struct,
     ctx->has_binv = false;
     ctx->tab_from_binv = false;
     ctx->dj_live = false;
+    ctx->devex_live = false;
     CUDA_TRY(cudaMemsetAsync(lp.cB, 0, (size_t)((char*)lp.lam - (char*)lp.cB), ctx->stream));
     CUDA_TRY(cudaMemsetAsync(lp.y, 0, sizeof(double) * lp.ld, ctx->stream));
     if (tableau && lp.coop) CUDA_TRY(cudaMemsetAsync(lp.coop, 0, sizeof(double) * 6 * 1024, ctx->stream));
@@ -1397,14 +1423,24 @@ static int sharded_finish_init(ellp_b200_ctx* ctx) {
 }
 
 int ellp_b200_sharded_generate_dense(ellp_b200_ctx* ctx, int32_t m, int32_t n_struct, uint64_t seed, const ellp_opts* o) {
-    if (!ctx || !o || m <= 0 || n_struct <= 0) return ELLP_E_ARG;
+    return ellp_b200_sharded_generate_dense_ex(ctx, m, n_struct, seed, 0, o);
+}
+
+int ellp_b200_sharded_generate_dense_ex(ellp_b200_ctx* ctx, int32_t m, int32_t n_struct, uint64_t seed, int32_t variant, const ellp_opts* o) {
+    if (!ctx || !o || m <= 0 || n_struct <= 0 || variant < 0 || variant > 1) return ELLP_E_ARG;
     CUDA_TRY(cudaSetDevice(ctx->device));
     DevLP lp{};
-    if (blk_slots(o, true) > 1 && ctx->peer_exchange) {
+    const int solver = variant == 0 ? ELLP_PRIMAL : ELLP_DUAL;
+    if (variant == 1 && !(blk_slots(o, true, solver) > 1 && ctx->peer_exchange))
+        return set_err(ctx, ELLP_E_ARG, "the sharded dual needs the peer-memory engine (block_k > 1)");
+    if (blk_slots(o, true, solver) > 1 && ctx->peer_exchange) {
         // peer layout: rank g generates the structural columns (= nonbasic positions) [g nN/G, (g+1) nN/G) straight into T
-        if (int rc = peer_prepare(ctx, m, n_struct + m, o, &lp)) return rc;
-        LAUNCH(k_gen_dense_cols, 148 * 16, 256, lp.T, lp.ld, m, (int64_t)n_struct, (int64_t)lp.pos_lo, (int64_t)(lp.pos_lo + lp.nT), seed, 1.0, 1.0);
-        LAUNCH(k_gen_dense_vectors, 148 * 2, 256, lp, (int64_t)n_struct, seed, 0);
+        // (dual variant: slack basis -I, so T = B^-1 A_N = -A_N)
+        if (int rc = peer_prepare(ctx, m, n_struct + m, o, &lp, solver)) return rc;
+        LAUNCH(k_gen_dense_cols, 148 * 16, 256, lp.T, lp.ld, m, (int64_t)n_struct, (int64_t)lp.pos_lo, (int64_t)(lp.pos_lo + lp.nT), seed, 1.0,
+               variant == 0 ? 1.0 : -1.0);
+        LAUNCH(k_gen_dense_vectors, 148 * 2, 256, lp, (int64_t)n_struct, seed, (int)variant);
+        LAUNCH(k_fill_const, (int)((lp.ld + 255) / 256), 256, lp.bscale, (int64_t)lp.ld, variant == 0 ? 1.0 : -1.0);
         ctx->lp = lp;
         return peer_finish_init(ctx);
     }
@@ -1451,13 +1487,29 @@ int ellp_b200_sharded_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const 
 }
 
 int ellp_b200_sharded_upload_nonbasic(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_point* pt, const ellp_opts* o) {
-    if (!ctx || !sf || !pt || !o) return ELLP_E_ARG;
+    return ellp_b200_sharded_upload_nonbasic_ex(ctx, sf, pt, ELLP_PRIMAL, nullptr, o);
+}
+
+int ellp_b200_sharded_upload_nonbasic_ex(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_point* pt, int solver, const double* basis_diag,
+                                         const ellp_opts* o) {
+    if (!ctx || !sf || !pt || !o || (solver != ELLP_PRIMAL && solver != ELLP_DUAL)) return ELLP_E_ARG;
     CUDA_TRY(cudaSetDevice(ctx->device));
     const int m = sf->m, ng = sf->n;
     if (pt->nB != m || pt->nN != ng - m) return set_err(ctx, ELLP_E_ARG, "sharded upload: B / N lengths do not match the standard form");
+    if (solver == ELLP_DUAL && (!pt->y || !pt->d)) return set_err(ctx, ELLP_E_ARG, "dual solve needs y and d");
+    if (basis_diag)
+        for (int i = 0; i < m; ++i)
+            if (basis_diag[i] == 0. || basis_diag[i] != basis_diag[i]) return set_err(ctx, ELLP_E_ELLP, dev_err_message(kErrSingular));
     DevLP lp{};
-    if (int rc = peer_prepare(ctx, m, ng, o, &lp)) return rc;
+    if (int rc = peer_prepare(ctx, m, ng, o, &lp, solver)) return rc;
     cudaStream_t s = ctx->stream;
+    if (basis_diag) CUDA_TRY(cudaMemcpyAsync(lp.bscale, basis_diag, sizeof(double) * (size_t)m, cudaMemcpyHostToDevice, s));
+    else LAUNCH(k_fill_const, (int)((lp.ld + 255) / 256), 256, lp.bscale, (int64_t)lp.ld, 1.0);
+    if (solver == ELLP_DUAL) {
+        CUDA_TRY(cudaMemcpyAsync(lp.y, pt->y, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(lp.d, pt->d, sizeof(double) * ng, cudaMemcpyHostToDevice, s));
+        ctx->dual_obj0 = host_dual_obj(sf, pt->y, pt->d);
+    }
     // sf->A = the columns of the nonbasic positions [pos_lo, pos_lo + nT) in pt->N order (m x nT, lda = m); vectors are global
     CUDA_TRY(cudaMemcpyAsync(lp.T, sf->A, sizeof(double) * (size_t)m * lp.nT, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync((void*)lp.c, sf->c, sizeof(double) * ng, cudaMemcpyHostToDevice, s));
@@ -1471,7 +1523,7 @@ int ellp_b200_sharded_upload_nonbasic(ellp_b200_ctx* ctx, const ellp_std_form* s
     CUDA_TRY(cudaMemcpyAsync(lp.Ns, pt->N_side, (size_t)lp.nN, cudaMemcpyHostToDevice, s));
     ctx->lp = lp;
     CUDA_TRY(cudaStreamSynchronize(s));  // host buffers are only borrowed for the duration of the call
-    return peer_finish_init(ctx);
+    return peer_finish_init(ctx, basis_diag != nullptr);
 }
 
 // ---- K6: batches of independent small LPs ------------------------------------------------------------------------
@@ -1669,13 +1721,22 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
         if (blk == 0) blk = ctx->blk_kmax;
         if (blk <= 1 || !lp.condensed || (ctx->sharded && !ctx->peer_mode))
             return set_err(ctx, ELLP_E_ARG, "the dual tableau engine needs the condensed blocked layout (block_k > 1; sharded: the peer engine)");
-        if (o->pricing != ELLP_PRICE_REFERENCE || o->ratio != ELLP_RATIO_REFERENCE)
-            return set_err(ctx, ELLP_E_ARG, "steepest-edge pricing / the Harris ratio test of the dual need ELLP_ENGINE_REVISED");
+        if ((o->pricing != ELLP_PRICE_REFERENCE && o->pricing != ELLP_PRICE_DEVEX) || o->ratio != ELLP_RATIO_REFERENCE)
+            return set_err(ctx, ELLP_E_ARG, "the dual tableau engine prices with the reference rule or ELLP_PRICE_DEVEX; exact steepest edge / the Harris ratio test need ELLP_ENGINE_REVISED");
+        if (o->pricing == ELLP_PRICE_DEVEX && !ctx->devex_live) {  // reference framework = the current basis
+            LAUNCH(k_fill_const, (int)((lp.ld + 255) / 256), 256, lp.w, (int64_t)lp.ld, 1.0);
+            ctx->devex_live = true;
+        }
+    } else if (o->pricing == ELLP_PRICE_DEVEX) {
+        return set_err(ctx, ELLP_E_ARG, "ELLP_PRICE_DEVEX is implemented by the dual tableau engine");
     }
     ctx->blk_fill = 0;
     if (blk > 0) { if (int rc = flush_attrs(ctx)) return rc; }
     int check_every = o->check_every > 0 ? o->check_every : 8;  // iterations enqueued per host read-back (finished solves make them no-ops)
-    int refactor_every = o->refactor_every > 0 ? o->refactor_every : ((lp.m <= 512 && !ctx->tableau) ? 100 : 0);
+    // default: netlib-sized LPs rebuild B^-1 (revised engine) / the tableau from A through B^-1 (tableau engines that kept room
+    // for it) every 100 pivots, which bounds the drift of the updated matrix; large LPs refactor only on request
+    const bool can_rebuild = !ctx->tableau || (ctx->has_binv && ctx->a_resident && lp.condensed && !ctx->peer_mode && !ctx->sharded);
+    int refactor_every = o->refactor_every > 0 ? o->refactor_every : ((lp.m <= 512 && can_rebuild) ? 100 : 0);
     // a tableau can only be rebuilt from a resident constraint matrix: the condensed fast upload keeps no A, the peer layout
     // aliases A with its slice of T, the NCCL-sharded layout transforms A in place
     if (ctx->tableau && (!ctx->a_resident || ctx->peer_mode || ctx->sharded)) refactor_every = 0;
@@ -1763,6 +1824,7 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
             if (blk > 0) launch_flush(ctx, profile, &ev_used);  // pending (U, V) slots belong to the tableau that is about to be replaced
             if ((rc_loop = refactor(ctx, &res->refactors))) break;
             if (dse) launch_row_norms(ctx);
+            if (ctx->tableau && !ctx->a_resident) refactor_every = 0;  // the in-place rebuild consumed A: it cannot be repeated
         }
     }
     if (blk > 0) launch_flush(ctx, profile, &ev_used);  // leave a consistent tableau behind (the solve may be continued)

@@ -458,11 +458,14 @@ void dual_to_phase2(DualStage& ds, DualStage2& out) {
     std::vector<char> basic(sf.n, 0);
     for (int b : ds.pt.B) { const int j = (int)boxed.vars[b].id; basic[j] = 1; pt.B.push_back(j); }  // :264-273
     if (!pt.B.empty()) {
+        // quirk Q17: phase 1 drops rows without kept variables, so B can have fewer entries than the standard form has rows; the
+        // reference then panics inside nalgebra (non-square triangular solve / tr_mul dimension mismatch at :283).  Checked BEFORE
+        // the solve: a non-square A_B must never reach the triangular solves.
+        require((int)pt.B.size() == sf.m, "Matrix multiplication dimensions mismatch (dual_problem.rs:283)");
         RowPivotLU blu(pick_columns(sf.A, pt.B));
         std::vector<double> y(pt.B.size());
         for (size_t i = 0; i < pt.B.size(); ++i) y[i] = sf.c[pt.B[i]];
         require(blu.solve_transposed(y), "called `Option::unwrap()` on a `None` value (tr_solve)");
-        require((int)y.size() == sf.m, "Matrix multiplication dimensions mismatch (dual_problem.rs:283)");
         std::vector<double> d(sf.n);
         for (int j = 0; j < sf.n; ++j) d[j] = sf.c[j] - inner(sf.A.colp(j), y.data(), sf.m);
         std::vector<double> xN;

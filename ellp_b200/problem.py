@@ -17,6 +17,22 @@ import numpy as np
 EPS = 1e-10  # src/util.rs:1
 
 
+def rust_f64(v: float) -> str:
+    """`format!("{}", v)` of Rust for an f64: shortest round-trip digits, never an exponent, integers without ".0"."""
+    v = float(v)
+    if v != v:
+        return "NaN"
+    if v in (float("inf"), float("-inf")):
+        return "inf" if v > 0 else "-inf"
+    r = repr(v)
+    if "e" in r or "E" in r:
+        from decimal import Decimal
+        r = format(Decimal(r), "f")
+    if r.endswith(".0"):
+        r = r[:-2]
+    return r
+
+
 class EllPError(Exception):
     """src/error.rs:3-11"""
 
@@ -63,17 +79,29 @@ class Bound:
     def Fixed(val: float) -> "Bound":
         return Bound(BoundKind.Fixed, float(val), float(val))
 
-    def __str__(self) -> str:  # src/problem.rs:213-223
-        inf = "∞"
+    def __str__(self) -> str:  # impl Display for Bound, src/problem.rs:213-223
+        inf = "\u221e"
         if self.kind == BoundKind.Free:
             return f"(-{inf}, {inf})"
         if self.kind == BoundKind.Lower:
-            return f"[{self.lb}, {inf})"
+            return f"[{rust_f64(self.lb)}, {inf})"
         if self.kind == BoundKind.Upper:
-            return f"(-{inf}, {self.ub}]"
+            return f"(-{inf}, {rust_f64(self.ub)}]"
         if self.kind == BoundKind.TwoSided:
-            return f"[{self.lb}, {self.ub}]"
-        return f"[{self.lb}, {self.lb}]"
+            return f"[{rust_f64(self.lb)}, {rust_f64(self.ub)}]"
+        return f"[{rust_f64(self.lb)}, {rust_f64(self.lb)}]"
+
+    def display(self, var: "Variable") -> str:  # Bound::display, src/problem.rs:199-210
+        lte, gte = "\u2264", "\u2265"
+        if self.kind == BoundKind.Free:
+            return f"{var} free"
+        if self.kind == BoundKind.Lower:
+            return f"{var} {gte} {rust_f64(self.lb)}"
+        if self.kind == BoundKind.Upper:
+            return f"{var} {lte} {rust_f64(self.ub)}"
+        if self.kind == BoundKind.TwoSided:
+            return f"{rust_f64(self.lb)} {lte} {var} {lte} {rust_f64(self.ub)}"
+        return f"{var} = {rust_f64(self.lb)}"
 
 
 @dataclass(frozen=True)
@@ -93,6 +121,9 @@ class Variable:  # src/problem.rs:156-188
     obj_coeff: float
     bound: Bound
     name: Optional[str] = None
+
+    def __str__(self) -> str:  # impl Display for Variable, src/problem.rs:353-360
+        return self.name if self.name is not None else f"id[{int(self.id)}]"
 
 
 @dataclass
@@ -204,15 +235,24 @@ class Problem:
             rhs=np.array([c.rhs for c in self.constraints], dtype=np.float64),
         )
 
-    def __str__(self) -> str:  # src/problem.rs:305-351 (shape only)
-        lines = ["minimize"]
-        lines.append(" ".join(f"{'+' if v.obj_coeff >= 0 else '-'} {abs(v.obj_coeff)} {v.name or f'x{int(v.id)}'}" for v in self.variables))
-        lines.append("subject to")
-        names = {v.id: (v.name or f"x{int(v.id)}") for v in self.variables}
-        sym = {ConstraintOp.Lte: "≤", ConstraintOp.Eq: "=", ConstraintOp.Gte: "≥"}
-        for c in self.constraints:
-            lhs = " ".join(f"{'+' if cf >= 0 else '-'} {abs(cf)} {names[v]}" for v, cf in c.coeffs if cf != 0.0)
-            lines.append(f"{lhs} {sym[c.op]} {c.rhs}")
+    def __str__(self) -> str:  # impl Display for Problem, src/problem.rs:305-351 (trailing blanks included)
+        out = [f"{len(self.variables)} variables and {len(self.constraints)} constraints\n\n", "minimize\n"]
+        by_id = {}
         for v in self.variables:
-            lines.append(f"{names[v.id]}: {v.bound}")
-        return "\n".join(lines)
+            assert v.id not in by_id  # "should have have repeated ids" (sic, :323)
+            by_id[v.id] = v
+            if v.obj_coeff == 0.0:
+                continue
+            out.append(f"{'+' if v.obj_coeff > 0.0 else '-'} {rust_f64(abs(v.obj_coeff))} {v} ")
+        out.append("\n\nsubject to\n")
+        sym = {ConstraintOp.Lte: "\u2264", ConstraintOp.Eq: "=", ConstraintOp.Gte: "\u2265"}
+        for c in self.constraints:  # Constraint::display, :252-274
+            for vid, cf in c.coeffs:
+                if cf == 0.0:
+                    continue
+                out.append(f"{'+' if cf >= 0.0 else '-'} {rust_f64(abs(cf))} {by_id[vid]} ")
+            out.append(f"{sym[c.op]} {rust_f64(c.rhs)}\n")
+        out.append("\nwith the bounds\n")
+        for v in self.variables:
+            out.append(v.bound.display(v) + "\n")
+        return "".join(out)

@@ -122,15 +122,16 @@ def bench_main(args, wl, name, METRIC, UNIT, SEED, ClockSampler, measured_peak, 
     init_comm(ctx, rank, world)
     m, ns, P = wl["m"], wl["ns"], (args.pivots or wl["pivots"])
     n = m + ns
+    # the SAME block_k and pivots per step at every N (so that N = 1, 2, 4, 8 run the same pivots and end on the same objective);
+    # a per-N tuned block length is reported separately under "tuned"
     bk = wl.get("block_k", 0) if getattr(args, "block_k", -1) < 0 else args.block_k
-    if getattr(args, "block_k", -1) < 0 and bk > 1 and world >= 4:
-        P = (P + 63) // 64 * 64
-        bk = 64  # narrow shards: the pivot kernel's latency dominates, the longest block of pivots amortises the flush best (measured at 8 GPUs: k = 32 / 40 / 56 / 64 -> 26.5k / 27.3k / 28.8k / 29.8k pivots/s)
+    dual = bool(wl.get("dual")) and bool(wl.get("tableau"))
+    variant = 1 if dual else 0
     peer = bk > 1  # peer-memory engine: condensed tableau split by nonbasic position, exchange fused into the pivot kernel
     lo, hi = shard_range(ns, world, rank) if peer else shard_range(n, world, rank)
-    # order-free tie rule: the arg-select is a reduction over ranks
+    # order-free tie rule: the arg-select is a reduction over ranks; the dual's rules are order-free as they are
     o = N.default_opts(P, engine=N.ENGINE_TABLEAU, tie_rule=N.TIES_CANONICAL, check_every=min(P, max(16, bk)), profile=True, block_k=bk)
-    ctx.check(N.lib.ellp_b200_sharded_generate_dense(ctx.h, m, ns, SEED, C.byref(o)))
+    ctx.check(N.lib.ellp_b200_sharded_generate_dense_ex(ctx.h, m, ns, SEED, variant, C.byref(o)))
 
     def step():
         res = N.Result()
@@ -164,6 +165,60 @@ def bench_main(args, wl, name, METRIC, UNIT, SEED, ClockSampler, measured_peak, 
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dt, dev_ms_max, k3_ms = [float(v) for v in tt.cpu()]
     value = args.steps * P / dt
+    obj_resident = float(r.obj)
+
+    # tuned extra (narrow shards: the pivot kernel's latency dominates and the longest block amortises the flush best)
+    tuned = None
+    if peer and world >= 4 and getattr(args, "block_k", -1) < 0 and bk != 64:
+        Pt = (P + 63) // 64 * 64
+        ot = N.default_opts(Pt, engine=N.ENGINE_TABLEAU, tie_rule=N.TIES_CANONICAL, check_every=64, block_k=64)
+        ctx.check(N.lib.ellp_b200_sharded_generate_dense_ex(ctx.h, m, ns, SEED, variant, C.byref(ot)))
+        rt = N.Result()
+        for _ in range(3):
+            ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(ot), C.byref(rt)))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(ot), C.byref(rt)))
+        ctx.check(N.lib.ellp_b200_sync(ctx.h))
+        torch.cuda.synchronize()
+        tq = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tq, op=dist.ReduceOp.MAX)
+        tuned = {"block_k": 64, "pivots_per_step": Pt, "value": args.steps * Pt / float(tq.cpu()[0]), "unit": UNIT}
+
+    # parity check (every run with N > 1): 64 pivots of a 2048 x 6144 LP on the peer engine (all ranks) and on this rank's own
+    # single-GPU blocked engine must give the same trace, x, B, N, objective -- bit for bit; a mismatch fails the bench (rc != 0)
+    parity = None
+    if peer:
+        pm, pns, pK, pbk = 2048, 4096, 64, 32
+        po = N.default_opts(pK, engine=N.ENGINE_TABLEAU, tie_rule=N.TIES_CANONICAL, check_every=32, block_k=pbk)
+
+        def run_and_fetch(c_, gen):
+            tr = np.zeros(pK, dtype=N.TRACE_DTYPE); po.trace = N.ptr(tr); po.trace_cap = pK
+            c_.check(gen(c_.h, pm, pns, SEED + 5, variant, C.byref(po)))
+            rr = N.Result()
+            c_.check(N.lib.ellp_b200_run(c_.h, C.byref(po), C.byref(rr)))
+            x = np.zeros(pm + pns); B = np.zeros(pm, dtype=np.int32); Nv = np.zeros(pns, dtype=np.int32); Ns = np.zeros(pns, dtype=np.uint8)
+            y = np.zeros(pm); d = np.zeros(pm + pns)
+            c_.check(N.lib.ellp_b200_download(c_.h, C.byref(N.Point(N.ptr(x), N.ptr(B), N.ptr(Nv), N.ptr(Ns), N.ptr(y) if dual else None,
+                                                                  N.ptr(d) if dual else None, pm, pns))))
+            return rr, tr, (x, B, Nv, Ns, y, d)
+
+        single = N.Context(local_rank)
+        rs, trs, ds = run_and_fetch(single, N.lib.ellp_b200_generate_dense_ex)
+        single.close()
+        rp, trp, dp = run_and_fetch(ctx, N.lib.ellp_b200_sharded_generate_dense_ex)
+        same = (rp.status == rs.status and rp.iters == rs.iters == pK and rp.obj == rs.obj and trp.tobytes() == trs.tobytes()
+                and all(a.tobytes() == b.tobytes() for a, b in zip(dp, ds)))
+        flag = torch.tensor([1 if same else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        parity = "ok" if int(flag.item()) == 1 else "MISMATCH"
+        if parity != "ok":
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "parity_check": parity, "n_gpus": world, "error": "peer engine and single-GPU engine disagree"}), flush=True)
+            ctx.close()
+            dist.destroy_process_group()
+            raise SystemExit(3)
 
     # e2e: every rank uploads ITS column block from pinned host memory, pivots, downloads the point
     e2e = None
@@ -171,9 +226,16 @@ def bench_main(args, wl, name, METRIC, UNIT, SEED, ClockSampler, measured_peak, 
         nloc = hi - lo
         A_h = torch.empty(m * nloc, dtype=torch.float64, pin_memory=True).numpy()
         c_h = np.zeros(n); b_h = np.zeros(m); lb_h = np.zeros(n); ub_h = np.zeros(n); kind_h = np.zeros(n, dtype=np.uint8)
-        ctx.check(N.lib.ellp_b200_sharded_generate_dense(ctx.h, m, ns, SEED, C.byref(o)))
-        ctx.check(N.lib.ellp_b200_download_std_form(ctx.h, N.ptr(A_h), N.ptr(c_h), N.ptr(b_h), N.ptr(kind_h), N.ptr(lb_h), N.ptr(ub_h)))
-        x0 = np.zeros(n); x0[ns:] = b_h
+        ctx.check(N.lib.ellp_b200_sharded_generate_dense_ex(ctx.h, m, ns, SEED, variant, C.byref(o)))
+        if dual:  # the resident slice is the tableau -A_N: the host copy of A_N comes from the numpy twin of the generator
+            import bench_lp
+            idx = (np.arange(lo, hi, dtype=np.uint64)[:, None] * np.uint64(m) + np.arange(m, dtype=np.uint64)[None, :]).reshape(-1)
+            A_h[:] = bench_lp._uniform01(SEED, idx)
+            ctx.check(N.lib.ellp_b200_download_std_form(ctx.h, None, N.ptr(c_h), N.ptr(b_h), N.ptr(kind_h), N.ptr(lb_h), N.ptr(ub_h)))
+        else:
+            ctx.check(N.lib.ellp_b200_download_std_form(ctx.h, N.ptr(A_h), N.ptr(c_h), N.ptr(b_h), N.ptr(kind_h), N.ptr(lb_h), N.ptr(ub_h)))
+        x0 = np.zeros(n); x0[ns:] = -b_h if dual else b_h
+        y0 = np.zeros(m); d0 = c_h.copy(); diag = -np.ones(m)
         B0 = np.arange(ns, n, dtype=np.int32); N0 = np.arange(ns, dtype=np.int32); Ns0 = np.zeros(ns, dtype=np.uint8)
         sf = N.StdForm(m, n, N.ptr(A_h), N.ptr(c_h), N.ptr(b_h), N.ptr(kind_h), N.ptr(lb_h), N.ptr(ub_h))
         oe = N.default_opts(P, engine=N.ENGINE_TABLEAU, tie_rule=N.TIES_CANONICAL, check_every=min(P, max(16, bk)), block_k=bk)
@@ -181,13 +243,17 @@ def bench_main(args, wl, name, METRIC, UNIT, SEED, ClockSampler, measured_peak, 
 
         def e2e_step():
             x, B, Nv, Ns = x0.copy(), B0.copy(), N0.copy(), Ns0.copy()
-            pt = N.Point(N.ptr(x), N.ptr(B), N.ptr(Nv), N.ptr(Ns), None, None, m, ns)
-            ctx.check(upload(ctx.h, C.byref(sf), C.byref(pt), C.byref(oe)))
+            y, d = y0.copy(), d0.copy()
+            pt = N.Point(N.ptr(x), N.ptr(B), N.ptr(Nv), N.ptr(Ns), N.ptr(y) if dual else None, N.ptr(d) if dual else None, m, ns)
+            if dual:
+                ctx.check(N.lib.ellp_b200_sharded_upload_nonbasic_ex(ctx.h, C.byref(sf), C.byref(pt), N.DUAL, N.ptr(diag), C.byref(oe)))
+            else:
+                ctx.check(upload(ctx.h, C.byref(sf), C.byref(pt), C.byref(oe)))
             res = N.Result()
             ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(oe), C.byref(res)))
             ctx.check(N.lib.ellp_b200_download(ctx.h, C.byref(pt)))
             assert res.status == N.MAXITER and res.iters == P
-            return float(np.dot(c_h, x))
+            return float(res.obj) if dual else float(np.dot(c_h, x))
 
         for _ in range(min(args.warmup, 3)):
             e2e_step()
@@ -222,7 +288,7 @@ def bench_main(args, wl, name, METRIC, UNIT, SEED, ClockSampler, measured_peak, 
         if peer and achieved:
             import bench as _bench
             roofline = _bench.blocked_roofline(roofline, m, nloc, bk, k3_ms)
-        engine = ("condensed tableau split by nonbasic position, blocked (block_k=%d), per-pivot exchange fused into the cooperative "
+        engine = ("dual simplex, " if dual else "") + ("condensed tableau split by nonbasic position, blocked (block_k=%d), per-pivot exchange fused into the cooperative "
                   "pivot kernel over NVLink peer memory (k_blk_pivots_peer)" % bk) if peer else "tableau, column-sharded, rank-1 update per pivot"
         exchange = ("per pivot: %d x 64 B pricing words + m x 16 B column words stored into every peer (LL protocol, no NCCL call)" % world) if peer \
             else "2 x ncclAllGather (8 B, 24 B per rank) + 1 x ncclAllReduce (m doubles) per pivot"
@@ -234,7 +300,9 @@ def bench_main(args, wl, name, METRIC, UNIT, SEED, ClockSampler, measured_peak, 
                            "exchange": exchange,
                            "l2": f"local shard {8.0 * m * nloc / 1e9:.2f} GB >> 126 MB L2"},
                 "device_ms_per_step": dev_ms_max / args.steps, "gpu_launches": int(launches) * world, "clocks": clk,
-                "roofline": roofline, "cpu_baseline": None, "e2e": e2e}
+                "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "parity_check": parity,
+                "parity_check_what": "64 pivots of a 2048 x 6144 LP: peer engine on all ranks vs every rank's single-GPU blocked engine, bit-identical trace / x / B / N / objective" if parity else None,
+                "objective_after_timed_steps": obj_resident, "tuned": tuned}
         print(json.dumps(line), flush=True)
     dist.barrier()
     ctx.close()

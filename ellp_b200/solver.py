@@ -14,7 +14,7 @@ from typing import List, Optional
 import numpy as np
 
 from . import _native as N
-from .problem import EllPError, Problem
+from .problem import EllPError, Problem, rust_f64
 
 
 class EllPPanic(RuntimeError):
@@ -31,6 +31,11 @@ class Solution:  # src/solver.rs:35-54
 
     def x(self) -> np.ndarray:
         return self._x
+
+    def x_display(self) -> str:
+        """``format!("{}", sol.x())``: the nalgebra Display of the solution vector (see the example in src/lib.rs:45-59)."""
+        from .standard_form import nalgebra_display
+        return nalgebra_display(self._x)
 
 
 @dataclass
@@ -50,12 +55,12 @@ class SolverResult:  # src/solver.rs:6-25
 
     def __str__(self) -> str:  # src/solver.rs:14-25
         if self.kind == "Optimal":
-            return f"found optimal point with objective {self.solution.obj()}"
+            return f"found optimal point with objective {rust_f64(self.solution.obj())}"
         if self.kind == "Infeasible":
             return "problem is infeasible"
         if self.kind == "Unbounded":
             return "problem is unbounded"
-        return f"reached max iterations, current objective = {self.obj}"
+        return f"reached max iterations, current objective = {rust_f64(self.obj)}"
 
 
 _STATUS = {N.OPTIMAL: "Optimal", N.INFEASIBLE: "Infeasible", N.UNBOUNDED: "Unbounded", N.MAXITER: "MaxIter"}

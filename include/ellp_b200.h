@@ -54,7 +54,7 @@ enum { ELLP_TIES_REFERENCE = 0, ELLP_TIES_CANONICAL = 1 };
  * B^-1).  Dual entering column: the reference's first-minimum ratio (dual :263-279) or Harris' two-pass test with a
  * 1e-9 tolerance (largest |alpha| among the near-minimal ratios).  The reference has neither (README.md:114 lists steepest
  * edge as TODO): parity for these rules is status / objective only. */
-enum { ELLP_PRICE_REFERENCE = 0, ELLP_PRICE_STEEPEST_EDGE = 1 };
+enum { ELLP_PRICE_REFERENCE = 0, ELLP_PRICE_STEEPEST_EDGE = 1, ELLP_PRICE_DEVEX = 2 /* tableau engines: Devex reference weights, see ellp_opts::pricing */ };
 enum { ELLP_RATIO_REFERENCE = 0, ELLP_RATIO_HARRIS = 1 };
 /* engines: explicit basis inverse (revised simplex) or full tableau (column-shardable) */
 enum { ELLP_ENGINE_AUTO = 0, ELLP_ENGINE_REVISED = 1, ELLP_ENGINE_TABLEAU = 2 };
@@ -110,8 +110,8 @@ typedef struct {
     int32_t  profile;         /* 1: record CUDA events around every rank-1 update launch */
     ellp_trace_rec* trace;    /* optional caller buffer */
     int64_t  trace_cap;
-    int32_t  pricing;         /* ELLP_PRICE_*: dual leaving-row rule (primal pricing is always Dantzig like the reference) */
-    int32_t  ratio;           /* ELLP_RATIO_*: dual entering-column rule */
+    int32_t  pricing;         /* ELLP_PRICE_*: dual leaving-row rule, revised engine (primal pricing is always Dantzig like the reference) */
+    int32_t  ratio;           /* ELLP_RATIO_*: dual entering-column rule, revised engine */
     int32_t  block_k;         /* tableau engine: > 1 defers the row reduction and applies it as ONE rank-k update
                                  (T -= U V on the fp64 tensor pipe) every block_k pivots; 0/1 = rank-1 update per pivot.
                                  Read at upload / generate time (allocates 8*(m+n)*block_k bytes) and by ellp_b200_run
@@ -151,7 +151,8 @@ int ellp_b200_download(ellp_b200_ctx*, ellp_point*);
  * (splitmix64 of seed and the global element index).  o->engine selects the resident representation. */
 int ellp_b200_generate_dense(ellp_b200_ctx*, int32_t m, int32_t n_struct, uint64_t seed, const ellp_opts* o);
 /* variant 0: as above (primal feasible slack basis); variant 1: min c.x s.t. A x - s = b: the
- * slack basis is dual feasible (x_B = -b, y = 0, d = c) and the resident solver is the dual one (revised engine). */
+ * slack basis is dual feasible (x_B = -b, y = 0, d = c) and the resident solver is the dual one (revised engine, or -- with
+ * ELLP_ENGINE_TABLEAU -- the blocked condensed tableau of dual_blocked.cuh, generated directly as T = B^-1 A_N = -A_N). */
 int ellp_b200_generate_dense_ex(ellp_b200_ctx*, int32_t m, int32_t n_struct, uint64_t seed, int32_t variant, const ellp_opts* o);
 /* copies the resident standard form to host buffers (any pointer may be NULL) */
 int ellp_b200_download_std_form(ellp_b200_ctx*, double* A, double* c, double* b, uint8_t* kind, double* lb, double* ub);
@@ -194,7 +195,9 @@ int ellp_b200_batch_download_lp(ellp_b200_ctx*, int32_t k, double* A, double* c,
 int ellp_b200_batch_download_all(ellp_b200_ctx*, double* A, double* c, double* b);   /* whole resident batch */
 
 /* ---- column-sharded tableau: one process per GPU (BASELINE.json configs[4]) ----------------------------------
- * Rank g stores global columns [g*n/G, (g+1)*n/G) of the tableau and of the reduced-cost row; x, the basis list and
+ * Two engines.  The default for block_k > 1 is the PEER-MEMORY engine described further down (exchange fused into the pivot
+ * kernel, no NCCL call per pivot).  The first implementation, kept for block_k <= 1 / tuning key "peer_exchange" = 0:
+ * rank g stores global columns [g*n/G, (g+1)*n/G) of the tableau and of the reduced-cost row; x, the basis list and
  * the bounds are replicated.  Per pivot: local pricing, two tiny NCCL all-gathers (arg-select with the order-free
  * tie rule), an NCCL all-reduce that broadcasts the pivot column from its owner, a replicated ratio test, and the
  * local rank-1 update.  Requires n % G == 0, m % 4 == 0 and an identity (slack) starting basis.
@@ -216,6 +219,13 @@ int ellp_b200_sharded_upload(ellp_b200_ctx*, const ellp_std_form* sf, const ellp
  * Requires (n - m) % G == 0, m % 4 == 0, G <= 8.  ellp_b200_run / ellp_b200_download work as in the single-GPU case and
  * return N in position order. */
 int ellp_b200_sharded_upload_nonbasic(ellp_b200_ctx*, const ellp_std_form* sf, const ellp_point* pt, const ellp_opts* o);
+/* The same for either solver (ELLP_PRIMAL | ELLP_DUAL: the dual loop of dual_simplex_solver.rs:188-334 on the sharded tableau,
+ * dual_blocked.cuh; pt->y / pt->d required) and for a DIAGONAL starting basis: basis_diag[i] = A[i, B[i]] (NULL = identity; a
+ * Gte row's slack gives -1), the rows of the tableau are divided by it on the device. */
+int ellp_b200_sharded_upload_nonbasic_ex(ellp_b200_ctx*, const ellp_std_form* sf, const ellp_point* pt, int solver, const double* basis_diag,
+                                         const ellp_opts* o);
+/* variant as in ellp_b200_generate_dense_ex (1 = dual-feasible slack basis; peer engine only) */
+int ellp_b200_sharded_generate_dense_ex(ellp_b200_ctx*, int32_t m, int32_t n_struct, uint64_t seed, int32_t variant, const ellp_opts* o);
 
 /* ---- two-phase drivers: {Primal,Dual}SimplexSolver::solve ------------------------------------ */
 /* A Problem as built by Problem::add_var / add_constraint (src/problem.rs:19-106); constraints in

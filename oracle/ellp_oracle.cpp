@@ -1073,10 +1073,11 @@ DualPhase2 dual_phase1_to_phase2(DualPhase1& p1) {  // :258-404
     if (!B.empty()) {  // :275-350
         Vec y(B.size());
         for (size_t i = 0; i < B.size(); ++i) y[i] = sf.c[B[i]];
+        // NB: quirk Q17 -- when B.len() != rows the reference panics inside nalgebra (non-square triangular solve, or the
+        // A.tr_mul(&y) dimension mismatch at :283); checked before the solve so that a non-square A_B never reaches it
+        ORC_ASSERT((int)B.size() == sf.A.r, "Matrix multiplication dimensions mismatch (dual_problem.rs:283)");
         LU A_B_lu(select_columns(sf.A, B));
         if (!A_B_lu.solve_transpose(y)) throw Panic("called `Option::unwrap()` on a `None` value (tr_solve)");
-        // NB: A.tr_mul(&y) panics on a dimension mismatch when B.len() != rows (quirk Q17)
-        ORC_ASSERT((int)y.size() == sf.A.r, "Matrix multiplication dimensions mismatch (dual_problem.rs:283)");
         Vec d(sf.c);
         for (int j = 0; j < sf.A.c; ++j) d[j] = sf.c[j] - dot(sf.A.col(j), y.data(), sf.A.r);
         Vec x_N;

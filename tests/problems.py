@@ -240,3 +240,39 @@ def check_expectation(exp, status_name: str, obj: float, x) -> None:
         assert abs(obj - exp[1]) < ABS_EPS or abs(obj / exp[1] - 1.0) < REL_EPS, f"obj: {obj}, expected: {exp[1]}"
     else:
         raise AssertionError(kind)
+
+
+def random_lp_all_bounds(seed):
+    """Seeded random LP with every Bound kind incl. TwoSided (quirks Q3 / Q17 live there) and <=, =, >= rows.  Used for
+    GPU-vs-oracle fuzzing only: the reference's own verdicts on TwoSided variables are not comparable with an exact solver
+    (tests/test_oracle_highs.py explains why), but whatever the reference does, the GPU path must do the same."""
+    import numpy as np
+    from ellp_b200.problem import Bound, ConstraintOp, Problem
+    rng = np.random.default_rng(1000 + seed)
+    nv, nc = int(rng.integers(2, 10)), int(rng.integers(1, 7))
+    p = Problem.new()
+    ids = []
+    for j in range(nv):
+        kind = rng.choice(["lower", "upper", "free", "fixed", "twosided", "twosided", "twosided"])
+        c = float(np.round(rng.normal(), 2))
+        if kind == "lower":
+            b = Bound.Lower(float(rng.integers(-2, 3)))
+        elif kind == "upper":
+            b = Bound.Upper(float(rng.integers(0, 6)))
+        elif kind == "free":
+            b = Bound.Free()
+        elif kind == "fixed":
+            b = Bound.Fixed(float(rng.integers(-1, 3)))
+        else:
+            lo = float(rng.integers(-3, 2))
+            b = Bound.TwoSided(lo, lo + float(rng.integers(1, 6)))
+        ids.append(p.add_var(c, b, f"x{j}"))
+    for i in range(nc):
+        row = np.round(rng.normal(size=nv), 2)
+        row[rng.random(nv) < 0.3] = 0.0
+        if not row.any():
+            row[int(rng.integers(nv))] = 1.0
+        rhs = float(np.round(rng.normal() * 3, 2))
+        op = rng.choice([ConstraintOp.Lte, ConstraintOp.Gte, ConstraintOp.Eq], p=[0.45, 0.35, 0.2])
+        p.add_constraint([(ids[j], float(row[j])) for j in range(nv) if row[j] != 0.0], op, rhs)
+    return p

@@ -215,3 +215,79 @@ def test_header_is_c99_and_struct_layouts_equal_the_ctypes_mirrors():
         off, size = lay[f"ellp_trace_rec.{f}"]
         assert N.TRACE_DTYPE.fields[f][1] == off and N.TRACE_DTYPE.fields[f][0].itemsize == size
     assert checked > 60
+
+
+# ---------------------------------------------------------------- Display impls (src/problem.rs:199-223,305-360; standard_form.rs:223-237; solver.rs:14-25)
+LIB_RS_EXAMPLE = """minimize
++ 2 x1 + 10 x2 + 1 x4
+
+subject to
++ 2.5 x1 + 3.5 x2 \u2265 5
++ 2.5 x2 + 4.5 x1 \u2264 1
+- 1 x3 - 3 x4 - 4 x5 = 2
+
+with the bounds
+-1 \u2264 x1 \u2264 1
+x2 \u2264 6
+x3 \u2265 0
+x4 = 0
+x5 free
+"""
+LIB_RS_POINT = """
+  \u250c                     \u2510
+  \u2502 -0.9473684210526313 \u2502
+  \u2502  2.1052631578947367 \u2502
+  \u2502                   0 \u2502
+  \u2502                   0 \u2502
+  \u2502                -0.5 \u2502
+  \u2514                     \u2518
+
+"""
+
+
+def _lib_rs_problem():
+    p = Problem.new()
+    x1 = p.add_var(2., Bound.TwoSided(-1., 1.), "x1"); x2 = p.add_var(10., Bound.Upper(6.), "x2")
+    x3 = p.add_var(0., Bound.Lower(0.), "x3"); x4 = p.add_var(1., Bound.Fixed(0.), "x4"); x5 = p.add_var(0., Bound.Free(), "x5")
+    p.add_constraint([(x1, 2.5), (x2, 3.5)], ConstraintOp.Gte, 5.)
+    p.add_constraint([(x2, 2.5), (x1, 4.5)], ConstraintOp.Lte, 1.)
+    p.add_constraint([(x3, -1.), (x4, -3.), (x5, -4.)], ConstraintOp.Eq, 2.)
+    return p
+
+
+def test_display_of_problem_and_vectors_reproduces_the_output_documented_in_lib_rs():
+    """Golden text: the console output the reference documents for its own example (src/lib.rs:62-98).  The Display impl
+    (problem.rs:305-351) also prints a '{} variables and {} constraints' header and a blank after every objective term,
+    which the doc block drops; both are checked separately."""
+    from ellp_b200.standard_form import nalgebra_display
+    from ellp_b200.problem import rust_f64
+    text = str(_lib_rs_problem())
+    assert text.startswith("5 variables and 3 constraints\n\nminimize\n+ 2 x1 + 10 x2 + 1 x4 \n\nsubject to\n")
+    body = text.split("\n", 2)[2]
+    assert [ln.rstrip() for ln in body.splitlines()] == LIB_RS_EXAMPLE.splitlines()
+    assert nalgebra_display([-0.9473684210526313, 2.1052631578947367, 0., 0., -0.5]) == LIB_RS_POINT
+    assert nalgebra_display(np.zeros((0, 3))) == "[ ]"
+    assert nalgebra_display(np.array([[1.5, -2.], [10., 0.25]])) == "\n  \u250c           \u2510\n  \u2502  1.5   -2 \u2502\n  \u2502   10 0.25 \u2502\n  \u2514           \u2518\n\n"
+    # f64 Display of Rust: integers without '.0', never an exponent
+    assert [rust_f64(v) for v in (2.0, -0.5, 1e21, 1e-7, float("inf"), 19.157894736842103)] == \
+        ["2", "-0.5", "1000000000000000000000", "0.0000001", "inf", "19.157894736842103"]
+    # unnamed variables print as id[k] (problem.rs:353-360); Bound Display (:213-223)
+    q = Problem.new(); v = q.add_var(1., Bound.Lower(0.))
+    assert "id[0] \u2265 0" in str(q)
+    assert [str(b) for b in (Bound.Free(), Bound.Lower(1.), Bound.Upper(2.5), Bound.TwoSided(-1., 1.), Bound.Fixed(3.))] == \
+        ["(-\u221e, \u221e)", "[1, \u221e)", "(-\u221e, 2.5]", "[-1, 1]", "[3, 3]"]
+
+
+def test_display_of_standard_form_and_solver_result():
+    from ellp_b200.standard_form import StandardForm
+    from ellp_b200.solver import Solution, SolverResult
+    sf = StandardForm.from_problem(_lib_rs_problem())
+    ref = O.stage(_lib_rs_problem(), 0)
+    np.testing.assert_array_equal(sf.A, ref.A)
+    assert (sf.rows(), sf.cols()) == (ref.m, ref.n)
+    text = str(sf)
+    assert text.startswith("c:\n  \u250c") and "\n\nA:\n  \u250c" in text and "bounds:\n\nx0: [-1, 1]\nx1: (-\u221e, 6]\nx2: [0, \u221e)\nx3: [0, 0]\nx4: (-\u221e, \u221e)\n" in text
+    assert text.count("\n  \u2502") == len(sf.c) + sf.rows() + len(sf.b)
+    assert str(SolverResult("Optimal", Solution(19.157894736842103, np.zeros(1)))) == "found optimal point with objective 19.157894736842103"
+    assert str(SolverResult("Infeasible")) == "problem is infeasible" and str(SolverResult("Unbounded")) == "problem is unbounded"
+    assert str(SolverResult("MaxIter", obj=float("inf"))) == "reached max iterations, current objective = inf"

@@ -925,3 +925,136 @@ def test_plain_c_program_drives_the_boundary(env):
         exe = test_abi_cpu._build_c_abi_smoke()
     out = subprocess.run([exe, "solve"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "C_ABI_SMOKE_OK" in out.stdout, out.stdout + out.stderr
+
+
+# ---------------------------------------------------------------- TwoSided fuzz, device panic paths, K6 sample size
+@pytest.mark.parametrize("seed", range(60))
+def test_random_lps_with_twosided_bounds_match_oracle(env, seed):
+    """GPU vs ORACLE (not vs HiGHS) on LPs with TwoSided / Fixed / Free / Lower / Upper variables: quirks Q3 (`x_i < lb` on the
+    upper branch, primal :359-363) and Q17 live on TwoSided variables, and whatever the reference does there -- a wrong optimum,
+    `assert!(lambda >= 0.)`, a dimension-mismatch panic -- the GPU path must do the same."""
+    O, N = env["O"], env["N"]
+    prob = P.random_lp_all_bounds(seed)
+    for which, tag in ((O.PRIMAL, "primal"), (O.DUAL, "dual")):
+        for engine in (N.ENGINE_AUTO, N.ENGINE_REVISED):
+            try:
+                ref = O.solve(prob, which, 1000, O.MODE_EXACT)
+            except O.OracleError as e:
+                with pytest.raises(Exception) as ei:
+                    _solver(env, tag, engine=engine).solve(prob)
+                # same panic / Err site: compare the leading words of the message
+                assert str(e).split(": ", 1)[1][:24] in str(ei.value), (seed, tag, str(e), str(ei.value))
+                continue
+            res = _solver(env, tag, engine=engine).solve(prob)
+            assert res.kind == ref.status_name, (seed, tag, engine, res.kind, ref.status_name)
+            assert res.used_primal_fallback == ref.used_primal_fallback
+            assert res.iters == ref.iters, (seed, tag, engine, res.iters, ref.iters)
+            if res.is_optimal:
+                assert _rel(res.solution.obj(), ref.obj) < 1e-9, (seed, tag)
+                np.testing.assert_allclose(res.solution.x(), ref.x, rtol=1e-8, atol=1e-8)
+
+
+def test_device_panic_paths_match_the_reference(env):
+    """panic!/assert! sites of the pivot loop reached ON THE DEVICE (PivotState::err), every engine that implements the path:
+    `pivot should have been unbounded` (primal :229), `assertion failed: lambda >= 0.` (primal :402).  `NaN detected` (primal
+    :282) is dead code in the reference -- (r1 - r2).abs() >= EPS is false for a NaN, so the index rule decides -- and a NaN cost
+    simply cycles to MaxIter, on the GPU as in the oracle."""
+    O, S, N = env["O"], env["S"], env["N"]
+    from ellp_b200.solver import EllPPanic
+    engines = [(N.ENGINE_AUTO, 0), (N.ENGINE_REVISED, 0), (N.ENGINE_TABLEAU, 0), (N.ENGINE_TABLEAU, 4)]
+    # (1) a nonbasic TwoSided variable parked on the Free side whose own range is the binding ratio: bound flip of a Free side
+    A = np.asfortranarray(np.array([[1.0, 1.0]])); c = np.array([-1.0, 0.0]); b = np.array([2.0])
+    kind = np.array([N.TWOSIDED, N.FREE], dtype=np.uint8); lb = np.array([0., 0.]); ub = np.array([1., 0.])
+    st = [np.array([0.0, 2.0]), np.array([1], dtype=np.int32), np.array([0], dtype=np.int32), np.array([N.NB_FREE], dtype=np.uint8)]
+    with pytest.raises(O.OracleError, match="pivot should have been unbounded"):
+        O.solve_with_initial(O.PRIMAL, 1, 2, A, c, b, kind, lb, ub, *[a.copy() for a in st], max_iter=50)
+    for engine, bk in engines:
+        with pytest.raises(EllPPanic, match="pivot should have been unbounded"):
+            S.GpuPrimalSimplexSolver.new(50, ctx=env["ctx"], engine=engine, block_k=bk).solve_with_initial(1, 2, A, c, b, kind, lb, ub, *[a.copy() for a in st])
+    # (2) quirk Q3: basic TwoSided variable below its lower bound moving further down => negative ratio => assert!(lambda >= 0.)
+    A = np.asfortranarray(np.array([[1.0, 1.0]])); c = np.array([-1.0, 0.0]); b = np.array([-1.0])
+    kind = np.array([N.LOWER, N.TWOSIDED], dtype=np.uint8); lb = np.array([0., 0.]); ub = np.array([0., 5.])
+    st = [np.array([0.0, -1.0]), np.array([1], dtype=np.int32), np.array([0], dtype=np.int32), np.array([N.NB_LOWER], dtype=np.uint8)]
+    with pytest.raises(O.OracleError, match="lambda >= 0"):
+        O.solve_with_initial(O.PRIMAL, 1, 2, A, c, b, kind, lb, ub, *[a.copy() for a in st], max_iter=50)
+    for engine, bk in engines:
+        with pytest.raises(EllPPanic, match="lambda >= 0"):
+            S.GpuPrimalSimplexSolver.new(50, ctx=env["ctx"], engine=engine, block_k=bk).solve_with_initial(1, 2, A, c, b, kind, lb, ub, *[a.copy() for a in st])
+    # (3) NaN cost: no panic in the reference, the loop cycles until max_iter
+    A = np.asfortranarray(np.array([[1.0, 1.0, 1.0]])); c = np.array([float("nan"), -1.0, 0.0]); b = np.array([2.0])
+    kind = np.array([N.LOWER] * 3, dtype=np.uint8); lb = np.zeros(3); ub = np.zeros(3)
+    st = [np.array([0.0, 0.0, 2.0]), np.array([2], dtype=np.int32), np.array([0, 1], dtype=np.int32), np.array([0, 0], dtype=np.uint8)]
+    ref = O.solve_with_initial(O.PRIMAL, 1, 3, A, c, b, kind, lb, ub, *[a.copy() for a in st], max_iter=20)
+    assert ref.status == O.MAXITER
+    for engine, bk in engines[:2]:
+        res, _ = S.GpuPrimalSimplexSolver.new(20, ctx=env["ctx"], engine=engine, block_k=bk).solve_with_initial(1, 3, A, c, b, kind, lb, ub, *[a.copy() for a in st])
+        assert res.status == N.MAXITER and res.iters == 20
+
+
+def test_batch_kernel_256_generated_lps_follow_the_oracle_pivot_for_pivot(env):
+    """256 LPs of the configs[3] shape (64 x 128) against the oracle -- status, objective, point, pivot counts per
+    phase AND the complete pivot trace (entering / leaving variable of every pivot of both phases)."""
+    from ellp_b200.problem import Bound, ConstraintOp, Problem
+    N, O, ctx = env["N"], env["O"], env["ctx"]
+    nlp, m, ns, seed, cap = 256, 64, 128, 5, 1024
+    ctx.check(N.lib.ellp_b200_batch_generate(ctx.h, nlp, m, ns, seed, 0, cap))
+    o = N.default_opts(None)
+    res = N.BatchResult()
+    ctx.check(N.lib.ellp_b200_batch_run(ctx.h, C.byref(o), C.byref(res)))
+    n0 = ns + m
+    status = np.zeros(nlp, dtype=np.int32); obj = np.zeros(nlp); x = np.zeros((nlp, n0 + m)); iters = np.zeros((nlp, 2), dtype=np.int32)
+    err = np.zeros(nlp, dtype=np.int32); tr = np.zeros((nlp, cap), dtype=N.TRACE_DTYPE); tl = np.zeros(nlp, dtype=np.int32)
+    out = N.BatchResult(N.ptr(status), N.ptr(obj), N.ptr(x), N.ptr(iters), N.ptr(err), N.ptr(tr), cap, N.ptr(tl), 0.0, 0, 0)
+    ctx.check(N.lib.ellp_b200_batch_download(ctx.h, C.byref(out)))
+    assert (err == 0).all() and (status == N.OPTIMAL).all()
+    A_all = np.zeros((nlp, n0, m)); c_all = np.zeros((nlp, n0)); b_all = np.zeros((nlp, m))
+    ctx.check(N.lib.ellp_b200_batch_download_all(ctx.h, N.ptr(A_all), N.ptr(c_all), N.ptr(b_all)))
+    pivots = 0
+    for k in range(nlp):
+        A = A_all[k].T  # per-LP column-major m x n0
+        p = Problem.new()
+        ids = [p.add_var(c_all[k][j], Bound.Lower(0.0)) for j in range(ns)]
+        for i in range(m):
+            p.add_constraint([(ids[j], A[i, j]) for j in range(ns)], ConstraintOp.Lte, b_all[k][i])
+        ref = O.solve(p, O.PRIMAL, None, O.MODE_EXACT, trace_cap=cap)
+        assert ref.status == O.OPTIMAL
+        assert _rel(obj[k], ref.obj) < 1e-9
+        np.testing.assert_allclose(x[k][:ns], ref.x, rtol=1e-9, atol=1e-9)
+        assert list(iters[k]) == ref.iters[:2], (k, iters[k], ref.iters)
+        L = int(tl[k])
+        assert L == len(ref.trace) == int(iters[k].sum())
+        assert (tr[k]["entering"][:L] == ref.trace["entering"]).all() and (tr[k]["leaving"][:L] == ref.trace["leaving"]).all(), k
+        pivots += L
+    assert pivots == out.pivots
+
+
+@pytest.mark.parametrize("name", P.NETLIB)
+def test_dual_devex_on_the_tableau_engine_reaches_the_same_optimum(env, name):
+    prob, exp = P.netlib(name)
+    O, N = env["O"], env["N"]
+    res = _solver(env, "dual", engine=N.ENGINE_TABLEAU, block_k=16, pricing=N.PRICE_DEVEX).solve(prob)
+    ref = O.solve(prob, O.DUAL, 1000, O.MODE_EXACT)
+    assert res.kind == ref.status_name == "Optimal"
+    assert _rel(res.solution.obj(), ref.obj) < 1e-9
+    P.check_expectation(exp, res.kind, res.solution.obj(), res.solution.x())
+
+
+def test_dual_devex_needs_fewer_pivots_on_a_dense_lp_and_agrees_with_the_reference_rule(env):
+    O, S, N = env["O"], env["S"], env["N"]
+    m, n = 192, 320
+    A, b, c = _dense_lp(21, m, n)
+    Af, cf, kind, lb, ub, start = _gte_dual_start(A, b, c)
+    out = {}
+    for tag, pricing in (("reference", N.PRICE_REFERENCE), ("devex", N.PRICE_DEVEX)):
+        sg = [a.copy() for a in start]
+        sol = S.GpuDualSimplexSolver.new(None, ctx=env["ctx"], engine=N.ENGINE_TABLEAU, block_k=16, pricing=pricing)
+        res, _ = sol.solve_with_initial(m, n + m, Af, cf, b, kind, lb, ub, *sg)
+        assert res.status == N.OPTIMAL
+        np.testing.assert_allclose(Af @ sg[0], b, rtol=1e-9, atol=1e-8)
+        np.testing.assert_allclose(sg[5], cf - Af.T @ sg[4], rtol=0, atol=1e-8)
+        out[tag] = (res.iters, res.obj)
+    st = [a.copy() for a in start]
+    ref = O.solve_with_initial(O.DUAL, m, n + m, Af, cf, b, kind, lb, ub, *st, max_iter=None)
+    assert _rel(out["reference"][1], ref.obj) < 1e-9 and _rel(out["devex"][1], ref.obj) < 1e-9
+    assert out["devex"][0] < out["reference"][0], out
+    print("dual pivots to optimal", out)

@@ -131,6 +131,72 @@ print(f"rank {rank}: peer vs single-GPU blocked engine m={m} n={m + ns} pivots={
       f"peer_ms={rp.ms_device:.2f} single_ms={rs.ms_device:.2f}", flush=True)
 ok = ok and good3
 
+# (4) DUAL simplex on the peer engine (dual_blocked.cuh): generated in HBM and uploaded from host buffers (slack basis -I passed as
+# basis_diag), against the oracle's DualSimplexSolver loop: same pivots, x, y, d, B, N
+for bk in (8, 5):
+    for (m, ns, seed, K) in [(64, 192, 3, 10**6), (256, 768, 4, 300)]:
+        n = m + ns
+        lp = bench_lp.dense_lp(m, ns, seed, 1)
+        st = [lp[k].copy() for k in ("x", "B", "N", "N_side", "y", "d")]
+        ref = O.solve_with_initial(O.DUAL, m, n, lp["A"], lp["c"], lp["b"], lp["kind"], lp["lb"], lp["ub"], *st, max_iter=K, trace_cap=20000)
+        k = len(ref.trace)
+        o = N.default_opts(K, engine=N.ENGINE_TABLEAU, check_every=8, block_k=bk)
+        oks = []
+        for mode in ("generated", "uploaded"):
+            tr = np.zeros(20000, dtype=N.TRACE_DTYPE); o.trace = N.ptr(tr); o.trace_cap = len(tr)
+            g = [lp[q].copy() for q in ("x", "B", "N", "N_side", "y", "d")]
+            pt = N.Point(N.ptr(g[0]), N.ptr(g[1]), N.ptr(g[2]), N.ptr(g[3]), N.ptr(g[4]), N.ptr(g[5]), m, ns)
+            if mode == "generated":
+                ctx.check(N.lib.ellp_b200_sharded_generate_dense_ex(ctx.h, m, ns, seed, 1, C.byref(o)))
+            else:
+                plo, phi = sharded.shard_range(ns, world, rank)
+                Aloc = np.asfortranarray(lp["A"][:, lp["N"][plo:phi]])
+                sf = N.StdForm(m, n, N.ptr(Aloc), N.ptr(lp["c"]), N.ptr(lp["b"]), N.ptr(lp["kind"]), N.ptr(lp["lb"]), N.ptr(lp["ub"]))
+                diag = -np.ones(m)
+                ctx.check(N.lib.ellp_b200_sharded_upload_nonbasic_ex(ctx.h, C.byref(sf), C.byref(pt), N.DUAL, N.ptr(diag), C.byref(o)))
+            res = N.Result()
+            ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(o), C.byref(res)))
+            ctx.check(N.lib.ellp_b200_download(ctx.h, C.byref(pt)))
+            good = (res.status == ref.status and res.iters == k and (tr["entering"][:k] == ref.trace["entering"]).all()
+                    and (tr["leaving"][:k] == ref.trace["leaving"]).all() and np.array_equal(g[1], st[1]) and np.array_equal(g[2], st[2])
+                    and np.array_equal(g[3], st[3]) and np.allclose(g[0], st[0], rtol=1e-9, atol=1e-9)
+                    and np.allclose(g[4], st[4], rtol=1e-9, atol=1e-9) and np.allclose(g[5], st[5], rtol=1e-9, atol=1e-9)
+                    and abs(res.obj - ref.obj) <= 1e-9 * max(1.0, abs(ref.obj)))
+            oks.append(good)
+        print(f"rank {rank}: DUAL peer engine block_k={bk} m={m} n={n} pivots={res.iters} oracle={k} status={res.status}/{ref.status} "
+              f"generated_ok={oks[0]} uploaded_ok={oks[1]}", flush=True)
+        ok = ok and all(oks)
+
+# (5) the dual at a size with many CTAs per rank: peer engine vs the single-GPU dual tableau engine, bit for bit
+m, ns, seed, K, bk = 2048, 4096, 5, 160, 32
+o = N.default_opts(K, engine=N.ENGINE_TABLEAU, check_every=32, block_k=bk)
+tr_s = np.zeros(K, dtype=N.TRACE_DTYPE); o.trace = N.ptr(tr_s); o.trace_cap = K
+single = N.Context(local)
+single.check(N.lib.ellp_b200_generate_dense_ex(single.h, m, ns, seed, 1, C.byref(o)))
+rs = N.Result()
+single.check(N.lib.ellp_b200_run(single.h, C.byref(o), C.byref(rs)))
+
+
+def _dl(c_):
+    x = np.zeros(m + ns); B = np.zeros(m, dtype=np.int32); Nv = np.zeros(ns, dtype=np.int32); Ns = np.zeros(ns, dtype=np.uint8)
+    y = np.zeros(m); d = np.zeros(m + ns)
+    c_.check(N.lib.ellp_b200_download(c_.h, C.byref(N.Point(N.ptr(x), N.ptr(B), N.ptr(Nv), N.ptr(Ns), N.ptr(y), N.ptr(d), m, ns))))
+    return x, B, Nv, Ns, y, d
+
+
+ds = _dl(single)
+single.close()
+tr_p = np.zeros(K, dtype=N.TRACE_DTYPE); o.trace = N.ptr(tr_p)
+ctx.check(N.lib.ellp_b200_sharded_generate_dense_ex(ctx.h, m, ns, seed, 1, C.byref(o)))
+rp = N.Result()
+ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(o), C.byref(rp)))
+dp = _dl(ctx)
+good5 = (rp.status == rs.status and rp.iters == rs.iters == K and (tr_p["entering"] == tr_s["entering"]).all()
+         and (tr_p["leaving"] == tr_s["leaving"]).all() and rp.obj == rs.obj and all(a.tobytes() == b.tobytes() for a, b in zip(dp, ds)))
+print(f"rank {rank}: DUAL peer vs single-GPU dual tableau engine m={m} n={m + ns} pivots={rp.iters}/{rs.iters} identical={good5} "
+      f"peer_ms={rp.ms_device:.2f} single_ms={rs.ms_device:.2f}", flush=True)
+ok = ok and good5
+
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0 and int(flag.item()) == 1:
