@@ -38,6 +38,25 @@ sys.path.insert(0, ROOT)
 if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
     os.environ["NCCL_DEBUG"] = "WARN"
 
+# Anything a native library prints to fd 1 (NCCL's "NCCL version ..." banner, a stray printf) must not reach the driver: main()
+# points fd 1 at stderr for the whole run and emit() writes the ONE JSON line to the saved descriptor.
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    fd = int(os.environ.get("ELLP_BENCH_STDOUT_FD", "1"))
+    sys.stdout.flush()
+    os.write(fd, data)
+
+
+def _protect_stdout() -> None:
+    if "ELLP_BENCH_STDOUT_FD" in os.environ:
+        return
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.set_inheritable(saved, False)
+    os.dup2(2, 1)
+    os.environ["ELLP_BENCH_STDOUT_FD"] = str(saved)
+
+
 WORKLOADS = {
     # BASELINE.json configs[4]: "synthetic dense LP 32768x65536 fp64, tableau column-sharded ... at 1/2/4/8 B200"
     "dense_tableau_32768x65536": dict(m=32768, ns=32768, pivots=672, block_k=56, sample_m=1024, sample_pivots=3),
@@ -286,7 +305,7 @@ def run_reference(args, wl, name):
                        "note": "one reference pivot at the full size is a %d^3 dense LU (~%.0f s extrapolated): the timed steps run the same generator at the sample size" % (wl["m"], cpu["extrapolated_full_size_seconds_per_pivot"])},
             "cpu_baseline": cpu,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ batch of small LPs
@@ -323,11 +342,11 @@ def run_batch(args, wl, name):
             piv += v * dts
         dt = time.perf_counter() - t0
         value = piv / dt
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        emit(({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": name, "nlp": wl["nlp"], "m": wl["m"], "n_struct": wl["ns"]},
                           "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
-                          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+                          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
     torch.cuda.set_device(local_rank)
     dist = None
@@ -417,7 +436,7 @@ def run_batch(args, wl, name):
                 "device_ms_per_step": dev_ms / args.steps, "gpu_launches": args.steps * world, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": None if not e2e else {"value": pe_total / dte, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"] * world, "d2h_bytes_per_step": e2e["d2h"] * world,
                                              "ms_per_step": 1e3 * dte / args.steps, "api": "ellp_b200_primal_solve_batch (host buffers, pinned)"}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist:
         dist.barrier(); dist.destroy_process_group()
     ctx.close()
@@ -453,11 +472,11 @@ def run_netlib(args, wl, name):
                 r = O.solve(prob, O.PRIMAL, 1000, O.MODE_EXACT); piv += sum(r.iters)
         dt = time.perf_counter() - t0
         v = piv / dt
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        emit(({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                           "data": "netlib fixture (tests/golden)", "config": {"workload": name, "solves_per_step": reps},
                           "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"{args.steps * reps} complete PrimalSimplexSolver::solve calls"},
-                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
     import torch
     from ellp_b200 import _native as N
@@ -500,7 +519,7 @@ def run_netlib(args, wl, name):
             "e2e": {"value": pr["pivots_per_s_wall"], "unit": UNIT, "h2d_bytes_per_step": int(reps * alg_bytes), "d2h_bytes_per_step": int(reps * 8 * (n + m + 4)), "ms_per_solve": pr["wall_ms_median"],
                     "api": "GpuPrimalSimplexSolver.default().solve(Problem)"},
             "solvers": out}
-    print(json.dumps(line), flush=True)
+    emit(line)
     ctx.close()
 
 
@@ -678,7 +697,7 @@ def run_ours(args, wl, name):
                        "baseline_config": "BASELINE.json configs[4]" if name == DEFAULT_WORKLOAD else "north_star / smaller variant"},
             "device_ms_per_step": dev_ms_timed / args.steps, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
             "cpu_baseline": cpu, "e2e": e2e}
-    print(json.dumps(line), flush=True)
+    emit(line)
     ctx.close()
 
 
@@ -695,6 +714,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    _protect_stdout()
     wl = WORKLOADS[args.workload]
     if wl.get("netlib"):
         return run_netlib(args, wl, args.workload)

@@ -256,7 +256,7 @@ __device__ int batch_run_phase(const BatchSmem& s, int m, int n0, int ld, uint64
             const double a = s.T[(size_t)q_pos * ld + i];
             s.dcol[i] = a;
             const double d_i = at_lower ? -a : a;
-            double lam = -1.0;
+            double lam = kLamSkipped;
             if (!(fabs(d_i) < kEps)) {
                 const int var = s.Bv[i];
                 lam = primal_ratio(s.kind[var], s.lo[var], s.hi[var], s.x[var], d_i);
@@ -284,7 +284,7 @@ __device__ int batch_run_phase(const BatchSmem& s, int m, int n0, int ld, uint64
                 int nF = 0, nBand = 0, idxF = 0x7fffffff;
                 for (int i = tid; i < m; i += kBatchThreads) {
                     const double l = s.lam[i];
-                    if (l == -1.0) continue;
+                    if (l == kLamSkipped) continue;
                     if (l < L + kEps) { ++nF; idxF = min(idxF, i); }
                     else if (l < L + 2. * kEps) ++nBand;
                 }
@@ -309,9 +309,9 @@ __device__ int batch_run_phase(const BatchSmem& s, int m, int n0, int ld, uint64
                     int nbi = 0;
                     for (int c0 = 0; c0 < m; c0 += 32) {
                         const int i = c0 + lane;
-                        const double l = (i < m) ? s.lam[i] : -1.0;
+                        const double l = (i < m) ? s.lam[i] : kLamSkipped;
                         const int v = (i < m) ? s.Bv[i] : 0;
-                        const bool cand = (l != -1.0) && (l < CUDART_INF);
+                        const bool cand = (l != kLamSkipped) && (l < CUDART_INF);
                         unsigned rem = __ballot_sync(full, cand);
                         while (rem) {
                             int eff = 0;
@@ -340,7 +340,7 @@ __device__ int batch_run_phase(const BatchSmem& s, int m, int n0, int ld, uint64
             int bestv = 0x7fffffff, bestp = -1;
             for (int i = 0; i < m; ++i) {
                 const double l = s.lam[i];
-                if (l != -1.0 && (l - lmin < kEps) && s.Bv[i] < bestv) { bestv = s.Bv[i]; bestp = i; }
+                if (l != kLamSkipped && (l - lmin < kEps) && s.Bv[i] < bestv) { bestv = s.Bv[i]; bestp = i; }
             }
             nb = bestp;
             lambda = s.lam[nb];

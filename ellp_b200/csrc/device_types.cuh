@@ -8,7 +8,10 @@ namespace ellp {
 constexpr double kEps = 0.0000000001;  // reference: src/util.rs:1
 
 // status values stored in PivotState::status while a solve is resident on the device
-constexpr int32_t kRunning = -1;  // 0..3 are the ELLP_* statuses
+constexpr int32_t kRunning = -1;
+// marks a basis row that takes no part in the ratio test (|d_i| < EPS, primal :321); no ratio can have this value (a negative
+// ratio, quirk Q3, is a legitimate candidate that ends in assert!(lambda >= 0.))
+constexpr double kLamSkipped = -1.7976931348623157e308;  // 0..3 are the ELLP_* statuses
 // device-detected panic!/assert! sites of the reference (PivotState::err)
 enum DevErr : int32_t {
     kErrNone = 0,

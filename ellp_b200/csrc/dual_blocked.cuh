@@ -386,6 +386,30 @@ __global__ void k_scale_rows_inv(double* __restrict__ T, int64_t ld, int m, int 
         st_f64x2(T + (int64_t)j * ld + i, v);
     }
 }
+// ---- x_B = B^-1 b - T x_N at a tableau rebuild (the reference never recomputes x; a rebuild is where the drift of the
+// incrementally updated point is removed as well).  Deterministic: column chunks, partial sums added in chunk order.
+constexpr int kXChunks = 32;
+// part[c * ld + i] = sum over the columns j of chunk c of M[i, j] * v(j);  v(j) = vec[idx ? idx[j] : j]
+__global__ void __launch_bounds__(256) k_gemv_n_chunks(const double* __restrict__ M, int64_t ld, int R, int C, const double* __restrict__ vec,
+                                                       const int32_t* __restrict__ idx, double* __restrict__ part) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y, per = (C + kXChunks - 1) / kXChunks;
+    const int j0 = c * per, j1 = min(C, j0 + per);
+    if (i >= R) return;
+    double acc = 0.;
+    for (int j = j0; j < j1; ++j) acc = fma(M[(int64_t)j * ld + i], vec[idx ? idx[j] : j], acc);
+    part[(int64_t)c * ld + i] = acc;
+}
+// x[Bv[i]] = sum_c pb[c][i] * (inv_diag ? 1 / bscale[i] ... ) - sum_c pt[c][i]
+__global__ void k_xB_finish(DevLP lp, const double* __restrict__ pb, const double* __restrict__ pt, int diag_only) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= lp.m) return;
+    double xb = 0., xt = 0.;
+    if (diag_only) xb = lp.b[i] / lp.bscale[i];
+    else for (int c = 0; c < kXChunks; ++c) xb += pb[(int64_t)c * lp.ld + i];
+    for (int c = 0; c < kXChunks; ++c) xt += pt[(int64_t)c * lp.ld + i];
+    lp.x[lp.Bv[i]] = xb - xt;
+}
 __global__ void k_fill_const(double* __restrict__ p, int64_t n, double v) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;

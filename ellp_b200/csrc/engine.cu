@@ -126,14 +126,14 @@ struct ellp_b200_ctx {
     void* peer_map[kMaxPeers] = {nullptr};  // cudaIpcOpenMemHandle mappings of the other ranks' buffers
     int64_t peer_cap = 0;         // rows per parity slot of the column buffers
     uint32_t xseq = 0;            // pivots exchanged since the communicator was created (wire sequence number)
-    int coop_grid_fused = 0;
-    int coop_grid_dual[2] = {0, 0}, coop_threads_cached_dual[2] = {0, 0};  // k_blk_dual_pivots_fused<false / true>
+    int coop_grid[4] = {0, 0, 0, 0}, coop_threads_cached[4] = {0, 0, 0, 0};  // k_blk_pivots_fused<false / true>, k_blk_dual_pivots_fused<false / true>
     // tableau engines with a general (non-identity) starting basis: B^-1 of the basis the tableau was built from lives in
     // lp.G / lp.Binv (has_binv), with the scratch the blocked LU needs next to the tableau's own U / V
     bool has_binv = false;
     double* rf_V = nullptr;       // kPanel x rf_ldv block row of the LU
     int64_t rf_ldv = 0;
     double* rf_coop = nullptr;    // publication slots of the cooperative panel kernel
+    bool recompute_x = false;     // set by ellp_b200_run around mid-solve rebuilds of the tableau (not at the start of a run: the caller's x is authoritative)
     bool devex_live = false;      // lp.w holds Devex reference weights of the resident solve (reset by upload / generate / refactor)
     bool dj_live = false;         // dual on the tableau: dj (not lp.d) holds the current reduced costs of the nonbasic positions
     bool tab_from_binv = false;   // T was built as B^-1 A_N (y at download = B^-T (c_B0 - d_B0)); false: diagonal starting basis (bscale)
@@ -141,7 +141,6 @@ struct ellp_b200_ctx {
     int tlog_cap = 0;
     uint32_t tlog_seq0 = 0;
     int coop_threads = 256;       // tuning: threads per block of k_blk_pivots_fused (64..512)
-    int coop_threads_cached = 0;
     int coop_ctas_per_sm = 1;     // tuning: resident blocks per SM the fused kernel may use
     int lu_panel_grid = 0;        // co-resident CTAs of k_lu_panel_coop (0 = not yet queried, -1 = unavailable)
     int refactor_panel = 0;       // tuning: 1 = single-CTA panel kernel
@@ -286,6 +285,8 @@ void carve(Arena& a, DevLP& lp, int KS, int64_t trace_cap, bool tableau, int blk
         lp.Bv0 = a.take<int32_t>(std::max<size_t>(m, 1));
         lp.bscale = a.take<double>(ld);
         lp.dpos = a.take<double>(std::max<size_t>(nN, 1));
+        lp.wN = a.take<double>(std::max<size_t>(nN, 1));
+        lp.xpart = a.take<double>(2 * 32 * ld);
         lp.condensed = sharded ? 0 : 1;
         lp.nT = lp.condensed ? (int32_t)nN : (int32_t)n;
         lp.T = lp.condensed ? a.take<double>(ld * std::max<size_t>(nN, 1)) : const_cast<double*>(lp.A);
@@ -595,6 +596,14 @@ int refactor(ellp_b200_ctx* ctx, uint64_t* count) {
                 LAUNCH(k_fill_const, (int)((lp.ld + 255) / 256), 256, lp.bscale, (int64_t)lp.ld, 1.0);
                 ctx->tab_from_binv = false;
             }
+            if (ctx->recompute_x && lp.xpart && !ctx->peer_mode) {
+                // mid-solve rebuild: x_B = B^-1 b - T x_N removes the drift of the incrementally updated point
+                static_assert(kXChunks == 32, "lp.xpart is carved for 32 chunks");
+                dim3 gx((unsigned)((m + 255) / 256), (unsigned)kXChunks);
+                if (built) LAUNCH(k_gemv_n_chunks, gx, 256, (const double*)lp.Binv, lp.ld, m, m, lp.b, (const int32_t*)nullptr, lp.xpart);
+                LAUNCH(k_gemv_n_chunks, gx, 256, (const double*)lp.T, lp.ld, m, lp.nT, (const double*)lp.x, (const int32_t*)lp.Nv, lp.xpart + (int64_t)kXChunks * lp.ld);
+                LAUNCH(k_xB_finish, (m + 255) / 256, 256, lp, (const double*)lp.xpart, (const double*)(lp.xpart + (int64_t)kXChunks * lp.ld), built ? 0 : 1);
+            }
             if (ctx->solver == ELLP_DUAL) {
                 LAUNCH(k_dual_tab_init, (lp.nT + 255) / 256, 256, lp);
                 ctx->dj_live = true;
@@ -616,7 +625,10 @@ int refactor(ellp_b200_ctx* ctx, uint64_t* count) {
     if (err == kErrSingular) return set_err(ctx, ELLP_E_ELLP, dev_err_message(err));
     ctx->binv_valid = true;
     ctx->pivots_since_refactor = 0;
-    if (ctx->tableau && ctx->devex_live) LAUNCH(k_fill_const, (int)((lp.ld + 255) / 256), 256, lp.w, (int64_t)lp.ld, 1.0);  // new reference framework
+    if (ctx->tableau && ctx->devex_live) {  // new reference framework
+        LAUNCH(k_fill_const, (int)((lp.ld + 255) / 256), 256, lp.w, (int64_t)lp.ld, 1.0);
+        if (lp.wN) LAUNCH(k_fill_const, (lp.nT + 255) / 256, 256, lp.wN, (int64_t)lp.nT, 1.0);
+    }
     if (count) ++*count;
     return ELLP_OK;
 }
@@ -718,6 +730,7 @@ void carve_peer(Arena& a, DevLP& lp, int64_t trace_cap, int blk_kmax) {
     lp.Bv0 = a.take<int32_t>(m);
     lp.bscale = a.take<double>(ld);
     lp.dpos = a.take<double>(nN);
+    lp.wN = a.take<double>(nT + 8);
     lp.trace = trace_cap > 0 ? a.take<ellp_trace_rec>((size_t)trace_cap) : nullptr;
     lp.colstat = nullptr;
     lp.xchg = nullptr;
@@ -802,11 +815,12 @@ int peer_finish_init(ellp_b200_ctx* ctx, bool diag_scaled = false) {
 int launch_coop_pivots_peer(ellp_b200_ctx* ctx, const ellp_opts* o, int npiv, bool self_only) {
     DevLP& lp = ctx->lp;
     const bool dual = (ctx->solver == ELLP_DUAL);  // dual_blocked.cuh: same layout, same exchange buffers, no tie folds (no dynamic smem)
-    const bool devex = dual && o->pricing == ELLP_PRICE_DEVEX;
-    const void* fn = dual ? (devex ? (const void*)k_blk_dual_pivots_fused<true> : (const void*)k_blk_dual_pivots_fused<false>) : (const void*)k_blk_pivots_fused;
+    const bool devex = o->pricing == ELLP_PRICE_DEVEX;
+    const void* fn = dual ? (devex ? (const void*)k_blk_dual_pivots_fused<true> : (const void*)k_blk_dual_pivots_fused<false>)
+                          : (devex ? (const void*)k_blk_pivots_fused<true> : (const void*)k_blk_pivots_fused<false>);
     const size_t smem = dual ? 0 : (size_t)kScanSmemBytes;
-    int& grid_cap = dual ? ctx->coop_grid_dual[devex ? 1 : 0] : ctx->coop_grid_fused;
-    int& threads_cached = dual ? ctx->coop_threads_cached_dual[devex ? 1 : 0] : ctx->coop_threads_cached;
+    int& grid_cap = ctx->coop_grid[(dual ? 2 : 0) + (devex ? 1 : 0)];
+    int& threads_cached = ctx->coop_threads_cached[(dual ? 2 : 0) + (devex ? 1 : 0)];
     // the fused kernel runs with small blocks: its phases are latency-bound and every block-wide reduction / barrier costs
     // issue slots per resident warp (measured: 256 threads per block beat 1024)
     const int threads = std::max(64, std::min(kFusedMaxThreads, ctx->coop_threads & ~31));
@@ -1102,7 +1116,7 @@ int ellp_b200_set_tuning(ellp_b200_ctx* ctx, const char* key, int value) {
     else if (!std::strcmp(key, "small_path")) ctx->small_path = value;
     else if (!std::strcmp(key, "peer_exchange")) ctx->peer_exchange = value;
     else if (!std::strcmp(key, "coop_threads")) ctx->coop_threads = value;
-    else if (!std::strcmp(key, "coop_ctas_per_sm")) { ctx->coop_ctas_per_sm = value; ctx->coop_threads_cached = 0; ctx->coop_threads_cached_dual[0] = ctx->coop_threads_cached_dual[1] = 0; }
+    else if (!std::strcmp(key, "coop_ctas_per_sm")) { ctx->coop_ctas_per_sm = value; for (int& v : ctx->coop_threads_cached) v = 0; }
     else if (!std::strcmp(key, "phase_timing")) {  // value = pivots to log (0 = off); read back with ellp_b200_phase_log
         if (ctx->tlog) { cudaFree(ctx->tlog); ctx->tlog = nullptr; }
         ctx->tlog_cap = 0;
@@ -1728,7 +1742,12 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
             ctx->devex_live = true;
         }
     } else if (o->pricing == ELLP_PRICE_DEVEX) {
-        return set_err(ctx, ELLP_E_ARG, "ELLP_PRICE_DEVEX is implemented by the dual tableau engine");
+        const bool fused_primal = ctx->tableau && blk > 1 && lp.condensed && (ctx->peer_mode || (!ctx->sharded && ctx->coop_pivots));
+        if (!fused_primal) return set_err(ctx, ELLP_E_ARG, "ELLP_PRICE_DEVEX is implemented by the blocked tableau engines (ELLP_ENGINE_TABLEAU, block_k > 1)");
+        if (!ctx->devex_live) {  // reference framework = the current nonbasic set
+            LAUNCH(k_fill_const, (lp.nT + 255) / 256, 256, lp.wN, (int64_t)lp.nT, 1.0);
+            ctx->devex_live = true;
+        }
     }
     ctx->blk_fill = 0;
     if (blk > 0) { if (int rc = flush_attrs(ctx)) return rc; }
@@ -1736,7 +1755,9 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
     // default: netlib-sized LPs rebuild B^-1 (revised engine) / the tableau from A through B^-1 (tableau engines that kept room
     // for it) every 100 pivots, which bounds the drift of the updated matrix; large LPs refactor only on request
     const bool can_rebuild = !ctx->tableau || (ctx->has_binv && ctx->a_resident && lp.condensed && !ctx->peer_mode && !ctx->sharded);
-    int refactor_every = o->refactor_every > 0 ? o->refactor_every : ((lp.m <= 512 && can_rebuild) ? 100 : 0);
+    // (the dual and Devex-priced solves on the tableau every 25: on degenerate LPs -- netlib ADLITTLE's dual phase 1 -- a hundred accumulated updates
+    // are enough for a pivot on rounding noise; the reference itself refactors at EVERY pivot)
+    int refactor_every = o->refactor_every > 0 ? o->refactor_every : ((lp.m <= 512 && can_rebuild) ? ((dual_tab || (ctx->tableau && o->pricing == ELLP_PRICE_DEVEX)) ? 25 : 100) : 0);
     // a tableau can only be rebuilt from a resident constraint matrix: the condensed fast upload keeps no A, the peer layout
     // aliases A with its slice of T, the NCCL-sharded layout transforms A in place
     if (ctx->tableau && (!ctx->a_resident || ctx->peer_mode || ctx->sharded)) refactor_every = 0;
@@ -1822,7 +1843,10 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
         if (h.status != kRunning) break;
         if (refactor_every > 0 && ctx->pivots_since_refactor >= (uint64_t)refactor_every) {
             if (blk > 0) launch_flush(ctx, profile, &ev_used);  // pending (U, V) slots belong to the tableau that is about to be replaced
-            if ((rc_loop = refactor(ctx, &res->refactors))) break;
+            ctx->recompute_x = ctx->tableau;
+            rc_loop = refactor(ctx, &res->refactors);
+            ctx->recompute_x = false;
+            if (rc_loop) break;
             if (dse) launch_row_norms(ctx);
             if (ctx->tableau && !ctx->a_resident) refactor_every = 0;  // the in-place rebuild consumed A: it cannot be repeated
         }

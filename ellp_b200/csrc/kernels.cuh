@@ -77,6 +77,8 @@ struct DevLP {
     // dual simplex on the tableau (dual_blocked.cuh): the basis the tableau was built from, needed to rebuild y from d
     int32_t* Bv0;      // m: variable that was basic in row i when T was built
     double* bscale;    // ld: diagonal of that basis when it was diagonal (generated LPs / identity start); scratch for the y right-hand side
+    double* xpart;     // 2 * kXChunks * ld: partial sums of the x_B recomputation at a tableau rebuild
+    double* wN;        // nT: primal Devex reference weights of the stored nonbasic positions (ELLP_PRICE_DEVEX)
     double* dpos;      // nN: reduced costs of all nonbasic positions (download: all-gather of dj on the peer engine)
 };
 
@@ -187,11 +189,11 @@ constexpr int kScanThreads = 1024;
 
 // Warps 1..31 stream (value, tag) tiles from global into shared memory while warp 0 folds the previous tile.
 __device__ __forceinline__ void scan_load_tile(const double* __restrict__ val, const int32_t* __restrict__ tag, int n, int tile,
-                                               double* sval, int* stag, int first_thread) {
+                                               double* sval, int* stag, int first_thread, double pad = -1.0) {
     const int base = tile * kScanTile;
     for (int t = threadIdx.x - first_thread; t < kScanTile; t += (int)blockDim.x - first_thread) {
         const int i = base + t;
-        sval[t] = (i < n) ? __ldcg(val + i) : -1.0;
+        sval[t] = (i < n) ? __ldcg(val + i) : pad;
         stag[t] = (i < n) ? __ldcg(tag + i) : 0;
     }
 }
@@ -439,7 +441,7 @@ __global__ void __launch_bounds__(256) k_ratio_prep(DevLP lp, int KS, int cnt, P
         if (threadIdx.x < cnt) s_vq[threadIdx.x] = lp.V[(int64_t)threadIdx.x * lp.ldv + qc];
         __syncthreads();
     }
-    double lam = -1.0;  // -1 = skipped (|d_i| < EPS, :321)
+    double lam = kLamSkipped;  // skipped (|d_i| < EPS, :321)
     if (i < lp.m) {
         double a = 0.;
         if (KS > 0) a = sum_partials(lp.part, lp.ld, KS, i);
@@ -456,8 +458,10 @@ __global__ void __launch_bounds__(256) k_ratio_prep(DevLP lp, int KS, int cnt, P
         }
         lp.lam[i] = lam;
     }
-    // block minimum of the finite ratios -> one atomicMin per block (ratios are >= 0, so their bit patterns order like integers)
-    double v = (lam >= 0. && lam < CUDART_INF) ? lam : CUDART_INF;
+    // block minimum of the finite ratios -> one atomicMin per block (non-negative doubles order like their bit patterns).  A
+    // negative ratio (quirk Q3) enters as 0: the pick kernel then sees it below L + EPS and either takes it (=> assert!(lambda >=
+    // 0.), primal :402) or falls back to the exact sequential fold -- it must never look like "no finite ratio".
+    double v = (lam != kLamSkipped && lam < CUDART_INF) ? fmax(lam, 0.) : CUDART_INF;
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, off));
     __shared__ double s[8];
@@ -505,7 +509,7 @@ __device__ __forceinline__ void ratio_pick_body(const DevLP& lp, int tie_rule, P
             if (L < CUDART_INF) {
                 for (int i = tid; i < m; i += blockDim.x) {
                     const double l = lp.lam[i];
-                    if (l == -1.0) continue;
+                    if (l == kLamSkipped) continue;
                     if (l < L + kEps) { ++nF; idxF = min(idxF, i); }
                     else if (l < L + 2. * kEps) ++nBand;
                 }
@@ -534,7 +538,7 @@ __device__ __forceinline__ void ratio_pick_body(const DevLP& lp, int tie_rule, P
             bool have_nbi = false;
             int nbi = 0;
             const int ntiles = (m + kScanTile - 1) / kScanTile;
-            scan_load_tile(lp.lam, lp.Bv, m, 0, sval[0], stag[0], 0);
+            scan_load_tile(lp.lam, lp.Bv, m, 0, sval[0], stag[0], 0, kLamSkipped);
             __syncthreads();
             for (int t = 0; t < ntiles; ++t) {
                 if (warp == 0) {
@@ -544,7 +548,7 @@ __device__ __forceinline__ void ratio_pick_body(const DevLP& lp, int tie_rule, P
                         const double l = sl[c + lane];
                         const int v = sv[c + lane];
                         // lambda_i = +inf never changes the state (:379, :387), so it is not a candidate here
-                        const bool cand = (l != -1.0) && (l < CUDART_INF);
+                        const bool cand = (l != kLamSkipped) && (l < CUDART_INF);
                         unsigned rem = __ballot_sync(full, cand);
                         while (rem) {
                             int eff = 0;  // 1 strict (:379), 2 tie accepted (:387-399)
@@ -563,7 +567,7 @@ __device__ __forceinline__ void ratio_pick_body(const DevLP& lp, int tie_rule, P
                         }
                     }
                 } else if (t + 1 < ntiles) {
-                    scan_load_tile(lp.lam, lp.Bv, m, t + 1, sval[(t + 1) & 1], stag[(t + 1) & 1], 32);
+                    scan_load_tile(lp.lam, lp.Bv, m, t + 1, sval[(t + 1) & 1], stag[(t + 1) & 1], 32, kLamSkipped);
                 }
                 __syncthreads();
             }
@@ -572,7 +576,7 @@ __device__ __forceinline__ void ratio_pick_body(const DevLP& lp, int tie_rule, P
             double lmin = CUDART_INF;
             for (int i = tid; i < m; i += blockDim.x) {
                 const double l = lp.lam[i];
-                if (l != -1.0 && l < lmin) lmin = l;
+                if (l != kLamSkipped && l < lmin) lmin = l;
             }
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) lmin = fmin(lmin, __shfl_xor_sync(full, lmin, off));
@@ -585,7 +589,7 @@ __device__ __forceinline__ void ratio_pick_body(const DevLP& lp, int tie_rule, P
             if (basic_wins) {
                 for (int i = tid; i < m; i += blockDim.x) {
                     const double l = lp.lam[i];
-                    if (l != -1.0 && (l - lmin < kEps)) {
+                    if (l != kLamSkipped && (l - lmin < kEps)) {
                         const int v = lp.Bv[i];
                         if (v < bestv) { bestv = v; bestp = i; }
                     }

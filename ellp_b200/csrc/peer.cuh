@@ -48,7 +48,8 @@ namespace ellp {
 constexpr int kMaxPeers = 8;
 constexpr long long kPeerTimeoutNs = 8000000000ll;  // 8 s
 constexpr int kMboxFields = 4;
-constexpr int kMboxWords = 2 /*parity*/ * 2 /*round*/ * kMaxPeers * kMboxFields;  // uint4 words per rank
+constexpr int kMboxRounds = 3;  // 0: pricing, 1: near-tie round, 2: the owner's ratio-test decision
+constexpr int kMboxWords = 2 /*parity*/ * kMboxRounds * kMaxPeers * kMboxFields;  // uint4 words per rank
 
 struct PeerLinks {
     int32_t rank, nranks;
@@ -90,7 +91,7 @@ __device__ __forceinline__ double ll_recv(const uint4* src, uint32_t seq) {
 }
 
 __device__ __forceinline__ uint4* mbox_slot(uint4* base, int par, int round, int src, int field) {
-    return base + (((par * 2 + round) * kMaxPeers + src) * kMboxFields + field);
+    return base + (((par * kMboxRounds + round) * kMaxPeers + src) * kMboxFields + field);
 }
 
 // Last-block pattern: returns true in every thread of exactly one block per call site and pivot -- the block whose
@@ -248,6 +249,7 @@ struct PivotDec {
     int q_pos, q_var, q_side, side_after;  // side_after: side of nonbasic position q_pos after this pivot (ELLP_NB_*)
     bool at_lower;
     double lambda, alpha_r, rq;
+    double wq;  // Devex reference weight of the entering position (ELLP_PRICE_DEVEX)
 };
 
 __device__ __forceinline__ double dantzig_key(double r, int side) {
@@ -258,6 +260,15 @@ __device__ __forceinline__ double dantzig_key(double r, int side) {
         else if (side == ELLP_NB_FREE) k = fabs(r);
     }
     return k;
+}
+
+// ELLP_PRICE_DEVEX (no reference counterpart: ellp prices with Dantzig's rule): key = r^2 / w over the same candidates, with
+// primal Devex reference weights w per nonbasic position: after a pivot on (r, q) with scaled pivot row p_t = alpha_rt / alpha_rq,
+// w_t = max(w_t, p_t^2 w_q) and the position handed to the leaving variable gets max(w_q / alpha_rq^2, 1).  p_t is what the row
+// phase computes anyway, so the rule adds one load and one store per position and no exchange.
+__device__ __forceinline__ double devex_key(double r, int side, double w) {
+    const double k = dantzig_key(r, side);
+    return (k == -1.0) ? -1.0 : r * r / w;
 }
 
 // acc - sum_j g[j * stride] * coef[j], j ascending (one fma per pending pivot, i.e. the roundings of j rank-1 updates), with the
@@ -293,9 +304,13 @@ struct RowCache {
 
 // x step, (optionally) the bookkeeping, local pivot row / reduced costs / new (U, V) slot, and -- when `price` -- the
 // Dantzig keys of the local positions for the next pivot (returned as this thread's Top2).
+template <bool DEVEX>
 __device__ __forceinline__ Top2 blk_row_price_body(const DevLP& lp, int slot, PivotState* st, const PivotDec& d, const PivotRegs& g, bool commit_here,
-                                                   bool price, int64_t t0, int64_t stride, double* su, const RowCache& rc) {
+                                                   bool price, int64_t t0, int64_t stride, double* su, const RowCache& rc, const uint4* colsrc,
+                                                   uint32_t seq) {
     const int n = lp.nT, m = lp.m;
+    // entering-column entry of row t: phase C2 left it in dcol on a deciding rank; the other ranks poll the owner's LL word
+    auto col_at = [&](int64_t t) { return colsrc ? ll_recv(colsrc + t, seq) : __ldcg(lp.dcol + t); };
     const int64_t tmax = max(lp.ld, lp.ldv);
     const int r = d.r;
     // the corrections of the pivot row need U[r, 0..slot): issue those loads before anything else of this phase
@@ -307,7 +322,7 @@ __device__ __forceinline__ Top2 blk_row_price_body(const DevLP& lp, int slot, Pi
                 lp.x[rc.var] = rc.xv + d.lambda * d_i;
                 continue;
             }
-            const double a = __ldcg(lp.dcol + t);
+            const double a = col_at(t);
             const double d_i = d.at_lower ? -a : a;
             const int var = (d.leave_var >= 0 && t == r) ? d.leave_var : __ldcg(lp.Bv + t);
             lp.x[var] = __ldcg(lp.x + var) + d.lambda * d_i;
@@ -327,7 +342,7 @@ __device__ __forceinline__ Top2 blk_row_price_body(const DevLP& lp, int slot, Pi
             if (price && t < n) {
                 const double rc = __ldcg(lp.dj + t);
                 const int side = (t == qp_any) ? d.side_after : (int)__ldcg(lp.Ns + lp.pos_lo + t);
-                const double k = dantzig_key(rc, side);
+                const double k = DEVEX ? devex_key(rc, side, __ldcg(lp.wN + t)) : dantzig_key(rc, side);
                 lp.key[t] = k;
                 lp.rN[t] = rc;
                 if (k != -1.0) top2_push<true>(best, k, (int)t);
@@ -339,23 +354,27 @@ __device__ __forceinline__ Top2 blk_row_price_body(const DevLP& lp, int slot, Pi
     __syncthreads();
     for (int64_t t = t0; t < tmax; t += stride) {
         if (t < n) {
-            double dnew;
+            double dnew, wnew = 1.;
             const double dold = __ldcg(lp.dj + t);
+            const double wold = DEVEX ? __ldcg(lp.wN + t) : 1.;
             const int side_t = price ? (int)__ldcg(lp.Ns + lp.pos_lo + t) : 0;
             if (t == qp) {  // handed over to the leaving variable, whose current column is e_r
                 const double p = 1.0 / d.alpha_r;
                 Vslot[t] = p;
                 dnew = fma(-d.rq, p, 0.);
+                if (DEVEX) wnew = fmax(d.wq / (d.alpha_r * d.alpha_r), 1.);
             } else {
                 const double e = corr_chain(__ldcg(lp.T + t * lp.ld + r), lp.V + t, lp.ldv, su, slot);
                 const double p = e / d.alpha_r;
                 Vslot[t] = p;
                 dnew = fma(-d.rq, p, dold);
+                if (DEVEX) wnew = fmax(wold, p * p * d.wq);
             }
             lp.dj[t] = dnew;
+            if (DEVEX) lp.wN[t] = wnew;
             if (price) {
                 const int side = (t == qp) ? d.side_after : side_t;
-                const double k = dantzig_key(dnew, side);
+                const double k = DEVEX ? devex_key(dnew, side, wnew) : dantzig_key(dnew, side);
                 lp.key[t] = k;
                 lp.rN[t] = dnew;
                 if (k != -1.0) top2_push<true>(best, k, (int)t);
@@ -364,7 +383,7 @@ __device__ __forceinline__ Top2 blk_row_price_body(const DevLP& lp, int slot, Pi
             Vslot[t] = 0.;
         }
         if (t < lp.ld) {
-            const double a = (t == rc.row) ? rc.a : (t < m ? __ldcg(lp.dcol + t) : 0.);
+            const double a = (t == rc.row) ? rc.a : (t < m ? col_at(t) : 0.);
             Uslot[t] = (t < m ? a : 0.) - (t == r ? 1. : 0.);
             if (qp >= 0) lp.T[(int64_t)qp * lp.ld + t] = (t == r) ? 1. : 0.;
         }
@@ -413,6 +432,7 @@ template <bool MAX> __device__ __forceinline__ Top2 ll_reduce(const double* s_pa
     *extra = *s_extra;
     return t;
 }
+template <bool DEVEX>
 __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP lp, PeerLinks pl, int tie_rule, int slot0, int npiv, uint32_t seq0,
                                                                       PivotState* st) {
     namespace cg = cooperative_groups;
@@ -448,7 +468,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
             Top2 t{-1.0, -1.0, -1};
             for (int64_t j = gtid; j < nT; j += gsize) {
                 const double r = __ldcg(lp.dj + j);
-                const double k = dantzig_key(r, __ldcg(lp.Ns + lp.pos_lo + j));
+                const double k = DEVEX ? devex_key(r, __ldcg(lp.Ns + lp.pos_lo + j), __ldcg(lp.wN + j)) : dantzig_key(r, __ldcg(lp.Ns + lp.pos_lo + j));
                 lp.key[j] = k;
                 lp.rN[j] = r;
                 if (k != -1.0) top2_push<true>(t, k, (int)j);
@@ -472,7 +492,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
         if (tl) tl[1] = clock64();
         // ---- B: entering position, identical on every rank (primal :271-292)
         int q_pos;
-        double rq;
+        double rq, wq = 1.;
         {
             Top2 t{-1.0, -1.0, -1};
             rq = 0.;
@@ -507,7 +527,9 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
                 grid.sync();
                 q_pos = __ldcg(&st->q_pos);
                 rq = __ldcg(&st->rq);
+                if (DEVEX) wq = __ldcg(lp.wN + q_pos);  // R == 1: every position is local
             } else {
+                if (DEVEX) wq = rq * rq / t.a1;  // key = r^2 / w of the winning position; the same value on every rank
                 if (near_tie) {
                     // largest variable index among the keys within EPS of the global maximum
                     const double kmax = t.a1;
@@ -539,23 +561,24 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
                         }
                         __syncthreads();
                         const long long b = s_ll[0];
-                        if (tid < R * 3) {
-                            const int dst = tid / 3, f = tid % 3;
+                        if (tid < R * kMboxFields) {
+                            const int dst = tid / kMboxFields, f = tid % kMboxFields;
                             const int jl = (int)(b & 0xffffffffll);
                             double v;
                             if (f == 0) v = (b >= 0) ? (double)(b >> 32) : -1.0;
                             else if (f == 1) v = (b >= 0) ? (double)(lp.pos_lo + jl) : -1.0;
-                            else v = (b >= 0) ? __ldcg(lp.dj + jl) : 0.;
+                            else if (f == 2) v = (b >= 0) ? __ldcg(lp.dj + jl) : 0.;
+                            else v = (DEVEX && b >= 0) ? __ldcg(lp.wN + jl) : 1.;
                             ll_send(mbox_slot(pl.mbox[dst], par, 1, me, f), v, seq);
                         }
                     }
                     __syncthreads();
-                    if (tid < R * 3) s_mb[(tid / 3) * kMboxFields + (tid % 3)] = ll_recv(mbox_slot(pl.mbox[me], par, 1, tid / 3, tid % 3), seq);
+                    if (tid < R * kMboxFields) s_mb[tid] = ll_recv(mbox_slot(pl.mbox[me], par, 1, tid / kMboxFields, tid % kMboxFields), seq);
                     __threadfence();
                     __syncthreads();
                     double bv = -1.0;
                     for (int s = 0; s < R; ++s)
-                        if (s_mb[s * kMboxFields] > bv) { bv = s_mb[s * kMboxFields]; q_pos = (int)s_mb[s * kMboxFields + 1]; rq = s_mb[s * kMboxFields + 2]; }
+                        if (s_mb[s * kMboxFields] > bv) { bv = s_mb[s * kMboxFields]; q_pos = (int)s_mb[s * kMboxFields + 1]; rq = s_mb[s * kMboxFields + 2]; wq = s_mb[s * kMboxFields + 3]; }
                 }
                 if (gtid == 0) {
                     st->q_pos = q_pos;
@@ -586,47 +609,78 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
             }
         }
         if (tl) tl[3] = clock64();
-        // ---- C2: every rank: column, direction, ratios (primal :295-367)
+        // ---- C2 + D on the rank that OWNS the entering position only (R > 1; a single rank owns everything): column, direction,
+        // ratios (primal :295-367), leaving row / bound flip (:305-434).  The other ranks do not wait for the column: they wait for
+        // the owner's decision (three words in their mailbox, one NVLink hop after the owner's local ratio test) and pick the
+        // column words up in phase E, by which time they have been in flight for the whole of the owner's phases C2 / D.  All
+        // ranks then derive do_step / do_update / sides / "still running" from the same (lambda, row, pivot element).
         RowCache rc;
         rc.row = -1;
+        const bool decide_here = (R == 1) || (q_pos >= lp.pos_lo && q_pos < lp.pos_lo + nT);
         const int kq = lp.kind[q_var];  // :305-311, loaded before the barrier that phase D waits behind
         const double lambda0 = (kq == ELLP_TWOSIDED) ? (lp.ub[q_var] - lp.lb[q_var]) : (kq == ELLP_FIXED ? 0. : CUDART_INF);
-        {
-            Top2 t{CUDART_INF, CUDART_INF, -1};
-            const uint4* colbuf = pl.col[me] + (int64_t)par * pl.col_cap;
-            for (int64_t i = gtid; i < lp.ld; i += gsize) {
-                // Bv -> x / bounds do not depend on the column: walk them while the column word is in flight
-                int var = 0;
-                double xv = 0., lbv = 0., ubv = 0.;
-                int kv = ELLP_FIXED;
-                if (i < m) {
-                    var = __ldcg(lp.Bv + i);
-                    xv = __ldcg(lp.x + var);
-                    kv = lp.kind[var]; lbv = lp.lb[var]; ubv = lp.ub[var];
-                }
-                const double a = ll_recv(colbuf + i, seq);
-                lp.dcol[i] = a;
-                if (i == gtid) { rc.row = i; rc.a = a; rc.var = var; rc.xv = xv; }
-                if (i < m) {
-                    const double d_i = at_lower ? -a : a;  // :296-300
-                    double lam = -1.0;                      // -1 = skipped (|d_i| < EPS, :321)
-                    if (!(fabs(d_i) < kEps)) lam = primal_ratio(kv, lbv, ubv, xv, d_i);
-                    lp.lam[i] = lam;
-                    if (lam != -1.0 && lam < CUDART_INF) top2_push<false>(t, lam, (int)i);
-                }
-            }
-            t = top2_block_fast<false>(t, &s_top, rbuf);
-            ll_publish(llC, par, t, (t.i1 >= 0) ? __ldcg(lp.dcol + t.i1) : 1., seq);  // extra = column entry of the block's best row
-        }
-        if (tl) tl[4] = clock64();
-        ll_gather(llC, par, G, s_part, seq);  // replaces the grid barrier: every block waits for every block's ratios
-        if (tl) tl[5] = clock64();
-        // ---- D: leaving row / bound flip (primal :305-434), replicated in every thread of every rank
         PivotDec dec;
-        dec.q_pos = q_pos; dec.q_var = q_var; dec.q_side = q_side; dec.at_lower = at_lower; dec.rq = rq;
+        dec.q_pos = q_pos; dec.q_var = q_var; dec.q_side = q_side; dec.at_lower = at_lower; dec.rq = rq; dec.wq = wq;
         PivotRegs g_next = g;
         bool commit_here = false;
-        {
+        // the decision from (lambda, candidate row or -1, column entry of that row): primal :402-434 + :205-232, replicated
+        auto decide = [&](double lambda, int nb, double alpha_nb) {
+            dec.lambda = lambda;
+            dec.leave_var = -1;
+            dec.r = nb;
+            if (!(lambda >= 0.) || isinf(lambda)) {  // :402-406: ratio_commit records Unbounded (+ the assert)
+                dec.do_step = 0; dec.do_update = 0; dec.alpha_r = 1.; dec.side_after = q_side;
+                run = false;
+            } else {
+                dec.do_step = (lambda > 0.) ? 1 : 0;
+                dec.do_update = (nb >= 0) ? 1 : 0;
+                if (nb >= 0) {
+                    dec.alpha_r = alpha_nb;  // = dcol[nb]
+                    const double d_nb = at_lower ? -dec.alpha_r : dec.alpha_r;
+                    dec.side_after = (d_nb > 0.) ? ELLP_NB_UPPER : ELLP_NB_LOWER;  // :208-221
+                } else {  // :223-231 bound flip of the entering variable
+                    dec.alpha_r = 1.;
+                    dec.side_after = (q_side == ELLP_NB_LOWER) ? ELLP_NB_UPPER : (q_side == ELLP_NB_UPPER ? ELLP_NB_LOWER : ELLP_NB_FREE);
+                    if (q_side == ELLP_NB_FREE) run = false;  // ratio_commit: kErrFlipFree
+                }
+                g_next.pivots = g.pivots + 1;
+                g_next.trace_len = g.trace_len + 1;
+                g_next.obj = g.obj + rq * (at_lower ? lambda : -lambda);
+                if (g_next.pivots >= g.max_iter) run = false;  // ratio_commit: MaxIter at the next loop head
+            }
+            commit_here = (gtid == ((dec.do_update && nb >= 0) ? (int64_t)nb % gsize : 0));
+        };
+        if (decide_here) {
+            {
+                Top2 t{CUDART_INF, CUDART_INF, -1};
+                const uint4* colbuf = pl.col[me] + (int64_t)par * pl.col_cap;
+                for (int64_t i = gtid; i < lp.ld; i += gsize) {
+                    // Bv -> x / bounds do not depend on the column: walk them while the column word is in flight
+                    int var = 0;
+                    double xv = 0., lbv = 0., ubv = 0.;
+                    int kv = ELLP_FIXED;
+                    if (i < m) {
+                        var = __ldcg(lp.Bv + i);
+                        xv = __ldcg(lp.x + var);
+                        kv = lp.kind[var]; lbv = lp.lb[var]; ubv = lp.ub[var];
+                    }
+                    const double a = ll_recv(colbuf + i, seq);
+                    lp.dcol[i] = a;
+                    if (i == gtid) { rc.row = i; rc.a = a; rc.var = var; rc.xv = xv; }
+                    if (i < m) {
+                        const double d_i = at_lower ? -a : a;  // :296-300
+                        double lam = kLamSkipped;               // skipped (|d_i| < EPS, :321)
+                        if (!(fabs(d_i) < kEps)) lam = primal_ratio(kv, lbv, ubv, xv, d_i);
+                        lp.lam[i] = lam;
+                        if (lam != kLamSkipped && lam < CUDART_INF) top2_push<false>(t, lam, (int)i);
+                    }
+                }
+                t = top2_block_fast<false>(t, &s_top, rbuf);
+                ll_publish(llC, par, t, (t.i1 >= 0) ? __ldcg(lp.dcol + t.i1) : 1., seq);  // extra = column entry of the block's best row
+            }
+            if (tl) tl[4] = clock64();
+            ll_gather(llC, par, G, s_part, seq);  // replaces the grid barrier: every block waits for every block's ratios
+            if (tl) tl[5] = clock64();
             double alpha_best;
             Top2 t = ll_reduce<false>(s_part, G, &s_top, rbuf, &s_extra, &alpha_best);
             const double lmin_basic = t.a1;
@@ -635,33 +689,11 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
                 else if (lambda0 < t.a2) t.a2 = lambda0;
             }
             const bool fast = !(t.a1 < CUDART_INF) || !(t.a2 < t.a1 + 2. * kEps);
+            double msg_lambda, msg_alpha;
+            int msg_nb;
             if (fast) {
-                const int nb = t.i1;
-                const double lambda = t.a1;
-                dec.lambda = lambda;
-                dec.leave_var = -1;
-                dec.r = nb;
-                if (!(lambda >= 0.) || isinf(lambda)) {  // :402-406: ratio_commit records Unbounded (+ the assert)
-                    dec.do_step = 0; dec.do_update = 0; dec.alpha_r = 1.; dec.side_after = q_side;
-                    run = false;
-                } else {
-                    dec.do_step = (lambda > 0.) ? 1 : 0;
-                    dec.do_update = (nb >= 0) ? 1 : 0;
-                    if (nb >= 0) {
-                        dec.alpha_r = alpha_best;  // = dcol[nb], carried by the winning block's partial
-                        const double d_nb = at_lower ? -dec.alpha_r : dec.alpha_r;
-                        dec.side_after = (d_nb > 0.) ? ELLP_NB_UPPER : ELLP_NB_LOWER;  // :208-221
-                    } else {  // :223-231 bound flip of the entering variable
-                        dec.alpha_r = 1.;
-                        dec.side_after = (q_side == ELLP_NB_LOWER) ? ELLP_NB_UPPER : (q_side == ELLP_NB_UPPER ? ELLP_NB_LOWER : ELLP_NB_FREE);
-                        if (q_side == ELLP_NB_FREE) run = false;  // ratio_commit: kErrFlipFree
-                    }
-                    g_next.pivots = g.pivots + 1;
-                    g_next.trace_len = g.trace_len + 1;
-                    g_next.obj = g.obj + rq * (at_lower ? lambda : -lambda);
-                    if (g_next.pivots >= g.max_iter) run = false;  // ratio_commit: MaxIter at the next loop head
-                }
-                commit_here = (gtid == ((dec.do_update && nb >= 0) ? (int64_t)nb % gsize : 0));
+                decide(t.a1, t.i1, alpha_best);
+                msg_lambda = t.a1; msg_nb = t.i1; msg_alpha = alpha_best;
             } else {
                 __syncthreads();
                 if (blockIdx.x == 0) {
@@ -680,13 +712,29 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
                 run = (__ldcg(&st->status) == kRunning);
                 pivot_regs_load(g_next, st);
                 g = g_next;  // the tie path committed through PivotState before E
+                msg_lambda = (__ldcg(&st->err) == kErrLambdaNegative) ? -1.0 : dec.lambda;  // the other ranks raise the same assert
+                msg_nb = dec.do_update ? dec.r : -1;
+                msg_alpha = dec.alpha_r;
             }
+            if (R > 1 && blockIdx.x == 0 && tid < R * 3) {  // the decision to every other rank
+                const int dst = tid / 3, f = tid % 3;
+                if (dst != me) ll_send(mbox_slot(pl.mbox[dst], par, 2, 0, f), f == 0 ? msg_lambda : (f == 1 ? (double)msg_nb : msg_alpha), seq);
+            }
+        } else {
+            if (tl) { tl[4] = clock64(); tl[5] = tl[4]; }
+            __syncthreads();
+            if (tid < 3) s_mb[tid] = ll_recv(mbox_slot(pl.mbox[me], par, 2, 0, tid), seq);
+            __threadfence();
+            __syncthreads();
+            decide(s_mb[0], (int)s_mb[1], s_mb[2]);
+            __syncthreads();  // s_mb is reused by the next pivot's pricing merge
         }
         // ---- E + A': step, bookkeeping, local pivot row, reduced costs, new slot, keys of the next pivot
         const bool price = run && (slot + 1 < slot0 + npiv);
         if (tl) tl[6] = clock64();
         if (rc.row >= m) { rc.var = 0; rc.xv = 0.; }
-        Top2 t = blk_row_price_body(lp, slot, st, dec, g, commit_here, price, gtid, gsize, s_vec, rc);
+        const uint4* colsrc = decide_here ? nullptr : pl.col[me] + (int64_t)par * pl.col_cap;  // not a deciding rank: the column is still in its LL words
+        Top2 t = blk_row_price_body<DEVEX>(lp, slot, st, dec, g, commit_here, price, gtid, gsize, s_vec, rc, colsrc, seq);
         g = g_next;
         priced = false;
         if (tl) tl[7] = clock64();

@@ -78,6 +78,26 @@ def merge_near_tie(cands):
     return int(best[1]), best[2]
 
 
+def merge_dual_entering(msgs):
+    """Entering position of the sharded DUAL (dual_blocked.cuh, phase R): msgs[g] = (ratio, nan flag, global position or -1,
+    pivot-row entry) of rank g's lexicographic minimum of (d_j / alpha~_j, position) over its eligible positions.  Returns
+    ('nan' | 'infeasible' | 'pick', position, ratio, pivot-row entry): Iterator::min_by's first minimum over the whole N list
+    (dual_simplex_solver.rs:270-279) -- order-free, so merging the ranks in any order gives the same answer."""
+    best = None
+    nan = False
+    for (v, f, p, al) in msgs:
+        if f != 0.0:
+            nan = True
+        p = int(p)
+        if p >= 0 and (best is None or v < best[0] or (v == best[0] and p < best[1])):
+            best = (v, p, al)
+    if nan:
+        return "nan", -1, 0.0, 0.0
+    if best is None:
+        return "infeasible", -1, 0.0, 0.0
+    return "pick", best[1], best[0], best[2]
+
+
 def nccl_library_path() -> str:
     try:
         import nvidia.nccl as pkg  # torch's bundled NCCL
@@ -106,6 +126,13 @@ def init_comm(ctx: N.Context, rank: int, world: int):
     raw = bytes(t.cpu().tolist())
     idbuf = (C.c_ubyte * 128).from_buffer_copy(raw)
     ctx.check(N.lib.ellp_b200_comm_init(ctx.h, path, C.cast(idbuf, C.c_void_p), rank, world))
+
+
+def _emit(line: dict) -> None:
+    """bench.py's emit(): the ONE JSON line goes to the descriptor bench.py saved before pointing fd 1 at stderr."""
+    import sys
+    sys.stdout.flush()
+    os.write(int(os.environ.get("ELLP_BENCH_STDOUT_FD", "1")), (json.dumps(line) + "\n").encode())
 
 
 def bench_main(args, wl, name, METRIC, UNIT, SEED, ClockSampler, measured_peak, cpu_reference_sample):
@@ -215,7 +242,7 @@ def bench_main(args, wl, name, METRIC, UNIT, SEED, ClockSampler, measured_peak, 
         parity = "ok" if int(flag.item()) == 1 else "MISMATCH"
         if parity != "ok":
             if rank == 0:
-                print(json.dumps({"metric": METRIC, "parity_check": parity, "n_gpus": world, "error": "peer engine and single-GPU engine disagree"}), flush=True)
+                _emit({"metric": METRIC, "parity_check": parity, "n_gpus": world, "error": "peer engine and single-GPU engine disagree"})
             ctx.close()
             dist.destroy_process_group()
             raise SystemExit(3)
@@ -303,7 +330,7 @@ def bench_main(args, wl, name, METRIC, UNIT, SEED, ClockSampler, measured_peak, 
                 "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "parity_check": parity,
                 "parity_check_what": "64 pivots of a 2048 x 6144 LP: peer engine on all ranks vs every rank's single-GPU blocked engine, bit-identical trace / x / B / N / objective" if parity else None,
                 "objective_after_timed_steps": obj_resident, "tuned": tuned}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     dist.barrier()
     ctx.close()
     dist.destroy_process_group()

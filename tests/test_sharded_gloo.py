@@ -210,6 +210,127 @@ def test_peer_protocol_matches_oracle_world2(m, ns, seed, K, bk):
         np.testing.assert_allclose(x, xo, rtol=1e-9, atol=1e-9)
 
 
+def _peer_dual_worker(rank, world, port, m, ns, seed, K, bk, ret):
+    """DUAL simplex on the peer layout (ellp_b200/csrc/dual_blocked.cuh) on numpy shards over gloo: leaving row from the
+    replicated x (no exchange), pivot row + ratios per shard, mailbox merge = all_gather of 4 doubles per rank
+    (sharded.merge_dual_entering), entering column broadcast from its owner AFTER the local part of the update, deferred rank-k
+    updates, cancellation snap of the reduced costs."""
+    sys.path.insert(0, ROOT)
+    import bench_lp
+    from ellp_b200 import sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lp = bench_lp.dense_lp(m, ns, seed, 1)
+    plo, phi = sharded.shard_range(ns, world, rank)
+    nT = phi - plo
+    Nv, Ns = lp["N"].copy(), lp["N_side"].copy()
+    T = -lp["A"][:, Nv[plo:phi]].copy()               # slack basis -I: T = B^-1 A_N = -A_N
+    dj = lp["d"][Nv[plo:phi]].copy()
+    x, Bv = lp["x"].copy(), lp["B"].copy()
+    U = np.zeros((m, bk)); V = np.zeros((bk, nT)); fill = 0
+    trace = []
+    status = "maxiter"
+    for it in range(K):
+        viol = np.nonzero(x[Bv] < 0 - EPS)[0]          # every variable is Lower(0): first infeasible position (dual :200-236)
+        if len(viol) == 0:
+            status = "optimal"
+            break
+        r = int(viol[0])
+        delta = x[Bv[r]] - 0.0
+        neg = delta < 0
+        a_raw = T[r, :].copy()                         # pivot row of the local positions: stale row + pending corrections
+        for j in range(fill):
+            a_raw = a_raw - U[r, j] * V[j, :]
+        a = -a_raw if neg else a_raw
+        side = Ns[plo:phi]
+        keep = np.where(side == 0, a > EPS, a < -EPS)
+        mine = (0.0, 0.0, -1.0, 0.0)
+        if keep.any():
+            ratio = np.full(nT, np.inf)
+            ratio[keep] = dj[keep] / a[keep]
+            ratio[ratio == 0.0] = 0.0
+            jl = int(np.lexsort((np.arange(nT), ratio))[0])
+            mine = (float(ratio[jl]), float(np.isnan(ratio[keep]).any()), float(plo + jl), float(a_raw[jl]))
+        box = [torch.zeros(4, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(box, torch.tensor(mine, dtype=torch.float64))
+        what, q_pos, ratio_q, alpha_rq = sharded.merge_dual_entering([tuple(b.tolist()) for b in box])
+        if what != "pick":
+            status = what
+            break
+        theta_d = -ratio_q if neg else ratio_q
+        theta_p = delta / alpha_rq
+        owner = q_pos // nT
+        ql = q_pos - plo
+        # E: local part of the update, before the column is needed
+        p = a_raw / alpha_rq
+        prod = theta_d * a_raw
+        dnew = dj - prod
+        dnew[np.abs(dnew) <= 16 * 2.220446049250313e-16 * np.maximum(np.abs(dj), np.abs(prod))] = 0.0
+        col = torch.zeros(m, dtype=torch.float64)
+        if owner == rank:
+            acol = T[:, ql].copy()
+            for j in range(fill):
+                acol = acol - U[:, j] * V[j, ql]
+            col = torch.from_numpy(acol)
+            p[ql] = 1.0 / alpha_rq
+            dnew[ql] = -theta_d
+            T[:, ql] = 0.0; T[r, ql] = 1.0
+            V[:fill, ql] = 0.0
+        dj = dnew
+        dist.broadcast(col, src=owner)
+        alpha_q = col.numpy()
+        assert alpha_q[r] == alpha_rq                  # the row-derived and the column-derived pivot element are the same bits
+        x[Bv] = x[Bv] - theta_p * alpha_q
+        q_var, leave = int(Nv[q_pos]), int(Bv[r])
+        x[q_var] = x[q_var] + theta_p
+        trace.append((q_var, leave))
+        u = alpha_q.copy(); u[r] -= 1.0
+        U[:, fill] = u; V[fill, :] = p; fill += 1
+        Bv[r] = q_var; Nv[q_pos] = leave; Ns[q_pos] = 0 if neg else 1
+        if fill == bk:
+            T -= U @ V
+            U[:] = 0.0; V[:] = 0.0; fill = 0
+    ret[rank] = (trace, x, Bv, Nv, status)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("m,ns,seed,K,bk", [(16, 48, 1, 400, 4), (32, 96, 2, 60, 8)])
+def test_peer_dual_protocol_matches_oracle_world2(m, ns, seed, K, bk):
+    sys.path.insert(0, ROOT)
+    import bench_lp
+    from oracle import binding as O
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29700 + (os.getpid() % 90)
+    mp.spawn(_peer_dual_worker, args=(world, port, m, ns, seed, K, bk, ret), nprocs=world, join=True)
+    lp = bench_lp.dense_lp(m, ns, seed, 1)
+    st = [lp[k].copy() for k in ("x", "B", "N", "N_side", "y", "d")]
+    ref = O.solve_with_initial(O.DUAL, m, m + ns, lp["A"], lp["c"], lp["b"], lp["kind"], lp["lb"], lp["ub"], *st, max_iter=K, trace_cap=K)
+    want = list(zip(ref.trace["entering"].tolist(), ref.trace["leaving"].tolist()))
+    assert len(want) > 5
+    for rank in range(world):
+        trace, x, Bv, Nv, status = ret[rank]
+        assert trace == want
+        assert (status == "optimal") == (ref.status == O.OPTIMAL)
+        np.testing.assert_array_equal(Bv, st[1])
+        np.testing.assert_array_equal(Nv, st[2])
+        np.testing.assert_allclose(x, st[0], rtol=1e-9, atol=1e-9)
+
+
+def test_dual_entering_merge_rules():
+    from ellp_b200 import sharded
+    none = (0.0, 0.0, -1.0, 0.0)
+    assert sharded.merge_dual_entering([none, none])[0] == "infeasible"
+    assert sharded.merge_dual_entering([(0.5, 0.0, 7.0, 2.0), (0.25, 0.0, 40.0, -1.0)]) == ("pick", 40, 0.25, -1.0)
+    # equal ratios: the smaller POSITION wins whatever the rank order (Iterator::min_by keeps the first minimum)
+    assert sharded.merge_dual_entering([(0.5, 0.0, 41.0, 2.0), (0.5, 0.0, 7.0, 3.0)]) == ("pick", 7, 0.5, 3.0)
+    assert sharded.merge_dual_entering([(0.5, 0.0, 7.0, 3.0), (0.5, 0.0, 41.0, 2.0)]) == ("pick", 7, 0.5, 3.0)
+    assert sharded.merge_dual_entering([(0.5, 1.0, 7.0, 3.0), none])[0] == "nan"
+    assert sharded.merge_dual_entering([(float("inf"), 0.0, 3.0, 0.0), none]) == ("pick", 3, float("inf"), 0.0)
+
+
 def test_pricing_merge_rules():
     from ellp_b200 import sharded
     none = (-1.0, -1.0, -1.0, 0.0)

@@ -33,3 +33,16 @@ for engine, bk, rf in [(N.ENGINE_REVISED, 0, 0), (N.ENGINE_TABLEAU, 8, 0), (N.EN
     except Exception as e:
         print(f"  engine={engine} bk={bk} refactor_every={rf}: EXC {type(e).__name__}: {e}")
 ctx.close()
+
+# primal Devex through the public API (two phases) for several rebuild periods
+from ellp_b200.solver import GpuPrimalSimplexSolver
+ctx = N.Context(0)
+refp = O.solve(prob, O.PRIMAL, 1000, O.MODE_EXACT)
+print(f"{name} primal: oracle {refp.status_name} obj={refp.obj!r} iters={refp.iters}")
+for pricing, rf, bk in [(N.PRICE_REFERENCE, 0, 16), (N.PRICE_DEVEX, 0, 16), (N.PRICE_DEVEX, 25, 16), (N.PRICE_DEVEX, 50, 16), (N.PRICE_DEVEX, 10, 8)]:
+    try:
+        r = GpuPrimalSimplexSolver.default(ctx=ctx, engine=N.ENGINE_TABLEAU, block_k=bk, pricing=pricing, tie_rule=N.TIES_CANONICAL, refactor_every=rf).solve(prob)
+        print(f"  pricing={pricing} refactor_every={rf} bk={bk}: {r.kind} obj={r.solution.obj() if r.is_optimal else None!r} iters={r.iters}")
+    except Exception as e:
+        print(f"  pricing={pricing} refactor_every={rf} bk={bk}: EXC {type(e).__name__}: {e}")
+ctx.close()
