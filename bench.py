@@ -161,6 +161,75 @@ def k3_target_leg(ctx, N, peak, peak_src, R=16384, Cc=32768, reps=20):
             "peak_source": peak_src, "target": ">= 0.70 of HBM bandwidth (BASELINE.json north_star)", "met": gbs / peak >= 0.70}
 
 
+def other_config_legs(ctx, N) -> dict:
+    """Short legs of the OTHER BASELINE.json configs on the default (driver-run) bench line, so that one record carries all of them:
+    configs[2] (dense 4096x8192 dual: reference rules, pivots/s; Devex, whole solve), configs[3] (batch of 65536 small LPs, one GPU)
+    and configs[0] (netlib AFIRO through the public API).  Each leg is a few timed repetitions after a warm-up; failures are reported
+    in place and never lose the main line."""
+    out = {}
+    try:  # configs[2]: dual simplex on the blocked tableau
+        m, ns, P, bk = 4096, 8192, 960, 48
+        o = N.default_opts(P, engine=N.ENGINE_TABLEAU, check_every=bk, block_k=bk)
+        ctx.check(N.lib.ellp_b200_generate_dense_ex(ctx.h, m, ns, SEED, 1, C.byref(o)))
+        res = N.Result()
+        for _ in range(2):
+            ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(o), C.byref(res)))
+        t0 = time.perf_counter(); piv = 0
+        for _ in range(5):
+            ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(o), C.byref(res))); piv += res.iters
+        ctx.check(N.lib.ellp_b200_sync(ctx.h))
+        dt = time.perf_counter() - t0
+        leg = {"workload": "dense_tableau_dual_4096x12288", "pivots_per_s": piv / dt, "pivots_timed": int(piv), "rules": "reference (first infeasible row, first minimum ratio)"}
+        od = N.default_opts(None, engine=N.ENGINE_TABLEAU, check_every=96, block_k=bk, pricing=N.PRICE_DEVEX)
+        od.max_iter = N.U64_MAX
+        ts = []
+        for _ in range(4):
+            ctx.check(N.lib.ellp_b200_generate_dense_ex(ctx.h, m, ns, SEED, 1, C.byref(od)))
+            t0 = time.perf_counter()
+            ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(od), C.byref(res)))
+            ts.append(time.perf_counter() - t0)
+        leg["devex_complete_solve"] = {"status": int(res.status), "pivots": int(res.iters), "ms_per_solve": 1e3 * min(ts[1:]), "objective": float(res.obj)}
+        out["configs[2]"] = leg
+    except Exception as e:
+        out["configs[2]"] = {"error": str(e)}
+    try:  # configs[3]: batch of independent small LPs, this GPU
+        nlp, m, ns = 65536, 64, 128
+        ctx.check(N.lib.ellp_b200_batch_generate(ctx.h, nlp, m, ns, SEED, 0, 0))
+        o = N.default_opts(None)
+        br = N.BatchResult()
+        ctx.check(N.lib.ellp_b200_batch_run(ctx.h, C.byref(o), C.byref(br)))
+        it = np.zeros((nlp, 2), dtype=np.int32); stt = np.zeros(nlp, dtype=np.int32)
+        got = N.BatchResult(N.ptr(stt), None, None, N.ptr(it), None, None, 0, None, 0.0, 0, 0)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            ctx.check(N.lib.ellp_b200_batch_run(ctx.h, C.byref(o), C.byref(br)))
+        ctx.check(N.lib.ellp_b200_sync(ctx.h))
+        dt = (time.perf_counter() - t0) / 2
+        ctx.check(N.lib.ellp_b200_batch_download(ctx.h, C.byref(got)))
+        out["configs[3]"] = {"workload": "batch_small_lps_65536x64x128 (1 GPU)", "pivots_per_s": float(got.pivots) / dt, "lps_per_s": nlp / dt,
+                             "all_optimal": bool((stt == N.OPTIMAL).all()), "pivots_per_batch": int(got.pivots)}
+    except Exception as e:
+        out["configs[3]"] = {"error": str(e)}
+    try:  # configs[0]: netlib AFIRO, whole two-phase solves through the public API
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import problems as P
+        from ellp_b200.solver import GpuDualSimplexSolver, GpuPrimalSimplexSolver
+        prob, exp = P.netlib("afiro")
+        leg = {"workload": "netlib_afiro"}
+        for tag, cls in (("primal", GpuPrimalSimplexSolver), ("dual", GpuDualSimplexSolver)):
+            sol = cls.default(ctx=ctx)
+            r = sol.solve(prob)
+            ts = []
+            for _ in range(20):
+                t0 = time.perf_counter(); r = sol.solve(prob); ts.append(time.perf_counter() - t0)
+            leg[tag] = {"status": r.kind, "objective": r.solution.obj() if r.is_optimal else None, "ms_per_solve": 1e3 * float(np.median(ts)),
+                        "pivots": int(sum(r.iters)), "launches": int(r.launches)}
+        out["configs[0]"] = leg
+    except Exception as e:
+        out["configs[0]"] = {"error": str(e)}
+    return out
+
+
 class ClockSampler:
     """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  Samples NVML in-process every
     10 ms (the timed region of a step can be shorter than one `nvidia-smi -lms` period); falls back to an nvidia-smi
@@ -586,6 +655,7 @@ def run_ours(args, wl, name):
     launches = ctx.launch_count() - launches0
     clk = clocks.stop()
     value = pivots_done / dt
+    obj_resident = float(r.obj)  # same pivots at every N (same block_k, same pivots per step) => the same number in the N > 1 lines
     P = pivots_done // args.steps
     dev_ms_timed = dev_ms
     if not tab:  # profiled pass (direct launches, CUDA events around every k_rank1) for the roofline numbers only
@@ -696,7 +766,9 @@ def run_ours(args, wl, name):
                               else f"condensed tableau {8.0 * m * ns / 1e9:.1f} GB >> 126 MB L2 (no L2 flush needed)"),
                        "baseline_config": "BASELINE.json configs[4]" if name == DEFAULT_WORKLOAD else "north_star / smaller variant"},
             "device_ms_per_step": dev_ms_timed / args.steps, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
-            "cpu_baseline": cpu, "e2e": e2e}
+            "cpu_baseline": cpu, "e2e": e2e, "objective_after_timed_steps": obj_resident}
+    if name == DEFAULT_WORKLOAD and not args.no_other_configs:
+        line["other_configs"] = other_config_legs(ctx, N)
     emit(line)
     ctx.close()
 
@@ -709,6 +781,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--k3-target", action="store_true", help="also time K3 (k_rank1) at the north_star target size 16384x32768 (always on for the default workload)")
+    ap.add_argument("--no-other-configs", action="store_true", help="default workload: skip the short legs of configs[0], [2], [3] appended to the line")
+    ap.add_argument("--owner-ratio", type=int, default=-1, help="sharded primal: 1 = only the owner of the entering column runs the ratio test, 0 = every rank, -1 = library default")
     ap.add_argument("--pivots", type=int, default=0, help="pivots per step (0 = workload default)")
     ap.add_argument("--block-k", type=int, default=-1, help="tableau engine: pivots per deferred rank-k row reduction (-1 = workload default, 0 = rank-1 engine)")
     ap.add_argument("--no-e2e", action="store_true")

@@ -107,7 +107,6 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_dual_pivots_fused(D
     __shared__ double s_su[kBlkMax];
     __shared__ double s_mb[kMaxPeers * kMboxFields];
     __shared__ double s_part[kLLMaxBlocks * 4];
-    __shared__ double s_extra;
     __shared__ double s_delta;
     const int tid = threadIdx.x;
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + tid, gsize = (int64_t)gridDim.x * blockDim.x;
@@ -147,7 +146,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_dual_pivots_fused(D
         }
         double delta;
         ll_gather(llA, par, G, s_part, seq);
-        const Top2 L = ll_reduce<DEVEX>(s_part, G, &s_top, rbuf, &s_extra, &delta);
+        const Top2 L = ll_reduce_w<DEVEX>(s_part, G, &delta);
         if (L.i1 < 0) {  // no infeasible basic variable: optimal (:243-246)
             if (gtid == 0) { st->status = ELLP_OPTIMAL; st->do_update = 0; st->do_step = 0; }
             run = false;
@@ -187,12 +186,15 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_dual_pivots_fused(D
         }
         ll_gather(llC, par, G, s_part, seq);
         LexAcc loc{0., 0., -1, 0};
-        for (int b = tid; b < G; b += blockDim.x) {
-            const int p = (int)s_part[4 * b + 2];
-            if (s_part[4 * b + 1] != 0.) loc.nan = 1;
-            if (p >= 0) lex_push(loc, s_part[4 * b], p, s_part[4 * b + 3]);
+        {   // every warp reduces all G partials itself (cf. ll_reduce_w): no block barrier
+            const int lane = tid & 31, per = (G + 31) >> 5;
+            for (int b = lane * per; b < min(G, (lane + 1) * per); ++b) {
+                const int p = (int)s_part[4 * b + 2];
+                if (s_part[4 * b + 1] != 0.) loc.nan = 1;
+                if (p >= 0) lex_push(loc, s_part[4 * b], p, s_part[4 * b + 3]);
+            }
+            loc = warp_lexmin(loc);
         }
-        loc = block_lexmin(loc, &s_lex, lbuf);
         if (R > 1) {  // every rank's (ratio, nan flag, position, pivot-row entry) to every rank
             if (blockIdx.x == 0 && tid < R * kMboxFields) {
                 const int dst = tid / kMboxFields, f = tid % kMboxFields;

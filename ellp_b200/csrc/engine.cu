@@ -133,6 +133,10 @@ struct ellp_b200_ctx {
     double* rf_V = nullptr;       // kPanel x rf_ldv block row of the LU
     int64_t rf_ldv = 0;
     double* rf_coop = nullptr;    // publication slots of the cooperative panel kernel
+    cudaStream_t copy_stream = nullptr;   // H2D / D2H of the pipelined batch path (ellp_b200_primal_solve_batch)
+    std::vector<cudaEvent_t> chunk_ev;
+    int owner_ratio = 0;          // tuning key "owner_ratio": 0 every rank runs the primal ratio test (default), 1 only the owner of the entering column + decision broadcast
+    int batch_pipeline = 1;       // tuning key "batch_pipeline": 0 = upload, run, download one after the other
     bool recompute_x = false;     // set by ellp_b200_run around mid-solve rebuilds of the tableau (not at the start of a run: the caller's x is authoritative)
     bool devex_live = false;      // lp.w holds Devex reference weights of the resident solve (reset by upload / generate / refactor)
     bool dj_live = false;         // dual on the tableau: dj (not lp.d) holds the current reduced costs of the nonbasic positions
@@ -842,6 +846,7 @@ int launch_coop_pivots_peer(ellp_b200_ctx* ctx, const ellp_opts* o, int npiv, bo
     PeerLinks pl = ctx->pl;
     pl.tlog = ctx->tlog ? ctx->tlog - (int64_t)ctx->tlog_seq0 * kTlogStamps : nullptr;  // the kernel indexes the log by (seq - 1)
     pl.tlog_cap = ctx->tlog ? (int32_t)(ctx->tlog_seq0 + (uint32_t)ctx->tlog_cap) : 0;
+    pl.owner_only = ctx->owner_ratio > 0 ? 1 : 0;  // every rank launches with the same value; measured at 8 GPUs: the redundant test is 2 % faster
     if (self_only) {
         pl.mbox[0] = ctx->pl.mbox[ctx->pl.rank];
         pl.col[0] = ctx->pl.col[ctx->pl.rank];
@@ -1092,6 +1097,8 @@ void ellp_b200_destroy(ellp_b200_ctx* ctx) {
     if (ctx->d_sel) cudaFree(ctx->d_sel);
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     if (ctx->tlog) cudaFree(ctx->tlog);
+    for (auto e : ctx->chunk_ev) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->h_st) cudaFreeHost(ctx->h_st);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1115,6 +1122,8 @@ int ellp_b200_set_tuning(ellp_b200_ctx* ctx, const char* key, int value) {
     else if (!std::strcmp(key, "cuda_graphs")) ctx->use_graphs = value;
     else if (!std::strcmp(key, "small_path")) ctx->small_path = value;
     else if (!std::strcmp(key, "peer_exchange")) ctx->peer_exchange = value;
+    else if (!std::strcmp(key, "batch_pipeline")) ctx->batch_pipeline = value;
+    else if (!std::strcmp(key, "owner_ratio")) ctx->owner_ratio = value;
     else if (!std::strcmp(key, "coop_threads")) ctx->coop_threads = value;
     else if (!std::strcmp(key, "coop_ctas_per_sm")) { ctx->coop_ctas_per_sm = value; for (int& v : ctx->coop_threads_cached) v = 0; }
     else if (!std::strcmp(key, "phase_timing")) {  // value = pivots to log (0 = off); read back with ellp_b200_phase_log
@@ -1690,11 +1699,88 @@ int ellp_b200_batch_download_all(ellp_b200_ctx* ctx, double* A, double* c, doubl
     return ELLP_OK;
 }
 
+// Host buffers in, results out.  Large batches are pipelined: the batch is cut into chunks; the H2D copy of chunk c + 1 (copy
+// stream) overlaps the pivoting of chunk c (compute stream), and the D2H of chunk c's results follows its kernel on the copy
+// stream -- the PCIe transfer (6.4 GB for 65536 LPs of 64 x 192) hides behind the kernel instead of preceding it.
 int ellp_b200_primal_solve_batch(ellp_b200_ctx* ctx, const ellp_batch* bt, const ellp_opts* o, ellp_batch_result* res) {
     if (!ctx || !bt || !o || !res) return ELLP_E_ARG;
-    if (int rc = ellp_b200_batch_upload(ctx, bt, res->trace ? res->trace_cap : 0)) return rc;
-    if (int rc = ellp_b200_batch_run(ctx, o, res)) return rc;
-    return ellp_b200_batch_download(ctx, res);
+    if (bt->nlp <= 0 || bt->m <= 0 || bt->n < bt->m) return ELLP_E_ARG;
+    const int tcap = res->trace ? res->trace_cap : 0;
+    const size_t lp_bytes = sizeof(double) * (size_t)bt->m * bt->n;
+    const int nchunks = (int)std::min<size_t>(16, std::max<size_t>(1, ((size_t)bt->nlp * lp_bytes) >> 28));  // ~256 MB of A per chunk
+    if (nchunks <= 1 || ctx->batch_pipeline == 0) {
+        if (int rc = ellp_b200_batch_upload(ctx, bt, tcap)) return rc;
+        if (int rc = ellp_b200_batch_run(ctx, o, res)) return rc;
+        return ellp_b200_batch_download(ctx, res);
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (int rc = batch_alloc(ctx, bt->nlp, bt->m, bt->n, tcap)) return rc;
+    auto& B = ctx->batch;
+    const size_t smem = batch_smem_bytes(B.m, B.n0, B.ld);
+    if (smem > 227 * 1024) return set_err(ctx, ELLP_E_ARG, "LP too large for the shared-memory kernel (needs about (m+1)*n*8 bytes <= ~215 KB)");
+    CUDA_TRY(cudaFuncSetAttribute(k_batch_primal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!ctx->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (ctx->chunk_ev.size() < 2 * (size_t)nchunks) {
+        const size_t old = ctx->chunk_ev.size();
+        ctx->chunk_ev.resize(2 * (size_t)nchunks);
+        for (size_t i = old; i < ctx->chunk_ev.size(); ++i) CUDA_TRY(cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming));
+    }
+    int sms = 148, per_sm = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_batch_primal, kBatchThreads, smem);
+    const size_t m = (size_t)bt->m, n = (size_t)bt->n, nc = (size_t)B.nc;
+    const int per = (bt->nlp + nchunks - 1) / nchunks;
+    cudaStream_t cs = ctx->copy_stream, ks = ctx->stream;
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ks));
+    CUDA_TRY(cudaStreamWaitEvent(cs, ctx->ev0, 0));  // the copies start after whatever was queued on the compute stream
+    for (int c = 0; c < nchunks; ++c) {
+        const size_t l0 = (size_t)c * per, cnt = std::min<size_t>(per, (size_t)bt->nlp - l0);
+        if (cnt == 0) break;
+        CUDA_TRY(cudaMemcpyAsync(B.A + l0 * m * n, bt->A + l0 * m * n, sizeof(double) * cnt * m * n, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaMemcpyAsync(B.c + l0 * n, bt->c + l0 * n, sizeof(double) * cnt * n, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaMemcpyAsync(B.b + l0 * m, bt->b + l0 * m, sizeof(double) * cnt * m, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaMemcpyAsync(B.lb + l0 * n, bt->lb + l0 * n, sizeof(double) * cnt * n, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaMemcpyAsync(B.ub + l0 * n, bt->ub + l0 * n, sizeof(double) * cnt * n, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaMemcpyAsync(B.kind + l0 * n, bt->kind + l0 * n, cnt * n, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaEventRecord(ctx->chunk_ev[2 * c], cs));
+        CUDA_TRY(cudaStreamWaitEvent(ks, ctx->chunk_ev[2 * c], 0));
+        BatchArgs a{};
+        a.nlp = (int)cnt; a.m = B.m; a.n0 = B.n0; a.nc = B.nc; a.ld = B.ld;
+        a.mode = 0;
+        a.tie_rule = o->tie_rule;
+        a.trace_cap = B.trace_cap;
+        a.max_iter = o->max_iter;
+        a.A = B.A + l0 * m * n; a.c = B.c + l0 * n; a.b = B.b + l0 * m; a.kind = B.kind + l0 * n; a.lb = B.lb + l0 * n; a.ub = B.ub + l0 * n;
+        a.x = B.x + l0 * nc; a.B = B.B + l0 * m; a.N = B.N + l0 * n; a.Ns = B.Ns + l0 * n;
+        a.status = B.status + l0; a.obj = B.obj + l0; a.iters = B.iters + 2 * l0; a.err = B.err + l0;
+        a.trace = B.trace ? B.trace + l0 * B.trace_cap : nullptr; a.trace_len = B.trace_len + l0;
+        const int grid = (int)std::min<size_t>(cnt, (size_t)sms * std::max(1, per_sm));
+        k_batch_primal<<<grid, kBatchThreads, smem, ks>>>(a);
+        ctx->launches++;
+        CUDA_TRY(cudaEventRecord(ctx->chunk_ev[2 * c + 1], ks));
+        CUDA_TRY(cudaStreamWaitEvent(cs, ctx->chunk_ev[2 * c + 1], 0));
+        if (res->status) CUDA_TRY(cudaMemcpyAsync(res->status + l0, B.status + l0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, cs));
+        if (res->obj) CUDA_TRY(cudaMemcpyAsync(res->obj + l0, B.obj + l0, sizeof(double) * cnt, cudaMemcpyDeviceToHost, cs));
+        if (res->iters) CUDA_TRY(cudaMemcpyAsync(res->iters + 2 * l0, B.iters + 2 * l0, sizeof(int32_t) * 2 * cnt, cudaMemcpyDeviceToHost, cs));
+        if (res->err) CUDA_TRY(cudaMemcpyAsync(res->err + l0, B.err + l0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, cs));
+        if (res->x) CUDA_TRY(cudaMemcpyAsync(res->x + l0 * nc, B.x + l0 * nc, sizeof(double) * cnt * nc, cudaMemcpyDeviceToHost, cs));
+        if (res->trace_len) CUDA_TRY(cudaMemcpyAsync(res->trace_len + l0, B.trace_len + l0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, cs));
+        if (res->trace && B.trace) CUDA_TRY(cudaMemcpyAsync(res->trace + l0 * B.trace_cap, B.trace + l0 * B.trace_cap, sizeof(ellp_trace_rec) * cnt * B.trace_cap, cudaMemcpyDeviceToHost, cs));
+    }
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ks));
+    CUDA_TRY(cudaStreamSynchronize(ks));
+    CUDA_TRY(cudaStreamSynchronize(cs));
+    CUDA_TRY(cudaGetLastError());
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    res->ms_device = ms;
+    res->launches = (uint64_t)nchunks;
+    if (res->iters) {
+        uint64_t pv = 0;
+        for (size_t k = 0; k < 2 * (size_t)bt->nlp; ++k) pv += (uint64_t)res->iters[k];
+        res->pivots = pv;
+    }
+    return ELLP_OK;
 }
 
 int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {

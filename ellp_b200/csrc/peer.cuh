@@ -59,6 +59,8 @@ struct PeerLinks {
     unsigned int* ticket;    // local: arrival counters of the last-block pattern (2)
     long long* tlog;         // optional phase-timing log (tuning key "phase_timing"): kTlogStamps clock64() values per pivot, block 0 thread 0
     int32_t tlog_cap;        // pivots the log can hold
+    int32_t owner_only;      // primal kernel, R > 1: 1 = only the owner of the entering position runs the ratio test and broadcasts
+                             // the decision; 0 = every rank polls the column and decides redundantly (round-1 protocol)
 };
 constexpr int kTlogStamps = 10;
 
@@ -432,6 +434,33 @@ template <bool MAX> __device__ __forceinline__ Top2 ll_reduce(const double* s_pa
     *extra = *s_extra;
     return t;
 }
+// The same reduction done by EVERY WARP on its own (lane l takes a contiguous chunk of the slots, then one warp-wide top-2): no
+// block barrier at all -- s_part is complete after the __syncthreads that ends ll_gather, and a few redundant shared-memory
+// reads per lane are cheaper than the three barriers of ll_reduce on this latency chain.  Ties keep the lowest slot.
+template <bool MAX> __device__ __forceinline__ Top2 ll_reduce_w(const double* s_part, int nblocks, double* extra) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const double worst = MAX ? -1.0 : CUDART_INF;
+    const int per = (nblocks + 31) >> 5;
+    Top2 t{worst, worst, -1};
+    int slot = -1;
+    for (int b = lane * per; b < min(nblocks, (lane + 1) * per); ++b) {
+        const Top2 o{s_part[4 * b], s_part[4 * b + 1], (int)s_part[4 * b + 2]};
+        if (top2_better<MAX>(o.a1, t.a1)) slot = b;
+        top2_merge<MAX>(t, o);
+    }
+    const unsigned long long k1 = ord_key(t.a1), k2 = ord_key(t.a2);
+    const unsigned long long M = warp_best_u64<MAX>(k1);
+    const int src = __ffs(__ballot_sync(full, k1 == M)) - 1;
+    const unsigned long long S = warp_best_u64<MAX>((lane == src) ? k2 : k1);
+    Top2 r;
+    r.a1 = ord_val(M);
+    r.a2 = ord_val(S);
+    r.i1 = __shfl_sync(full, t.i1, src);
+    const int wslot = __shfl_sync(full, slot, src);
+    *extra = (r.i1 >= 0 && wslot >= 0) ? s_part[4 * wslot + 3] : 0.;
+    return r;
+}
 template <bool DEVEX>
 __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP lp, PeerLinks pl, int tie_rule, int slot0, int npiv, uint32_t seq0,
                                                                       PivotState* st) {
@@ -444,7 +473,6 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
     __shared__ long long s_ll[32];
     __shared__ int s_flag;
     __shared__ double s_part[kLLMaxBlocks * 4];
-    __shared__ double s_extra;
     const int tid = threadIdx.x;
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + tid, gsize = (int64_t)gridDim.x * blockDim.x;
     const int G = gridDim.x, R = pl.nranks, me = pl.rank;
@@ -479,7 +507,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
         // every block gathers every block's pricing partial: the local (best, second, position, reduced cost) without a grid barrier
         double loc_rq;
         ll_gather(llA, par, G, s_part, seq);
-        const Top2 loc = ll_reduce<true>(s_part, G, &s_top, rbuf, &s_extra, &loc_rq);
+        const Top2 loc = ll_reduce_w<true>(s_part, G, &loc_rq);
         if (R > 1 && blockIdx.x == 0 && tid < R * kMboxFields) {  // one block per rank tells the other ranks
             const int dst = tid / kMboxFields, f = tid % kMboxFields;
             double v;
@@ -616,7 +644,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
         // ranks then derive do_step / do_update / sides / "still running" from the same (lambda, row, pivot element).
         RowCache rc;
         rc.row = -1;
-        const bool decide_here = (R == 1) || (q_pos >= lp.pos_lo && q_pos < lp.pos_lo + nT);
+        const bool decide_here = (R == 1) || !pl.owner_only || (q_pos >= lp.pos_lo && q_pos < lp.pos_lo + nT);
         const int kq = lp.kind[q_var];  // :305-311, loaded before the barrier that phase D waits behind
         const double lambda0 = (kq == ELLP_TWOSIDED) ? (lp.ub[q_var] - lp.lb[q_var]) : (kq == ELLP_FIXED ? 0. : CUDART_INF);
         PivotDec dec;
@@ -682,7 +710,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
             ll_gather(llC, par, G, s_part, seq);  // replaces the grid barrier: every block waits for every block's ratios
             if (tl) tl[5] = clock64();
             double alpha_best;
-            Top2 t = ll_reduce<false>(s_part, G, &s_top, rbuf, &s_extra, &alpha_best);
+            Top2 t = ll_reduce_w<false>(s_part, G, &alpha_best);
             const double lmin_basic = t.a1;
             if (lambda0 < CUDART_INF) {
                 if (lambda0 < t.a1) { t.a2 = t.a1; t.a1 = lambda0; t.i1 = -1; }
@@ -716,7 +744,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
                 msg_nb = dec.do_update ? dec.r : -1;
                 msg_alpha = dec.alpha_r;
             }
-            if (R > 1 && blockIdx.x == 0 && tid < R * 3) {  // the decision to every other rank
+            if (R > 1 && pl.owner_only && blockIdx.x == 0 && tid < R * 3) {  // the decision to every other rank
                 const int dst = tid / 3, f = tid % 3;
                 if (dst != me) ll_send(mbox_slot(pl.mbox[dst], par, 2, 0, f), f == 0 ? msg_lambda : (f == 1 ? (double)msg_nb : msg_alpha), seq);
             }

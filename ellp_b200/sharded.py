@@ -147,6 +147,8 @@ def bench_main(args, wl, name, METRIC, UNIT, SEED, ClockSampler, measured_peak, 
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = N.Context(local_rank)
     init_comm(ctx, rank, world)
+    if getattr(args, "owner_ratio", -1) >= 0:
+        ctx.set_tuning("owner_ratio", args.owner_ratio)
     m, ns, P = wl["m"], wl["ns"], (args.pivots or wl["pivots"])
     n = m + ns
     # the SAME block_k and pivots per step at every N (so that N = 1, 2, 4, 8 run the same pivots and end on the same objective);
@@ -323,7 +325,7 @@ def bench_main(args, wl, name, METRIC, UNIT, SEED, ClockSampler, measured_peak, 
                 "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": name, "m": m, "n": n, "pivots_per_step": P, "engine": engine, "block_k": bk,
-                           "columns_per_gpu": nloc, "tie_rule": "order-free (canonical)",
+                           "columns_per_gpu": nloc, "tie_rule": "order-free (canonical)", "owner_ratio": getattr(args, "owner_ratio", -1),
                            "exchange": exchange,
                            "l2": f"local shard {8.0 * m * nloc / 1e9:.2f} GB >> 126 MB L2"},
                 "device_ms_per_step": dev_ms_max / args.steps, "gpu_launches": int(launches) * world, "clocks": clk,

@@ -1113,3 +1113,25 @@ def test_complete_solve_of_the_dense_lp_matches_highs(env, m, ns, refactor_every
     assert np.abs(lp["A"] @ x - lp["b"]).max() <= 1e-9 * np.abs(lp["b"]).max()
     assert (x >= -1e-9).all()
     print(f"{key} {pricing}: {res.iters} pivots, {res.ms_device:.1f} ms on the device, {res.refactors} rebuilds, obj {obj!r} (HiGHS {fx[key]['obj']!r}, {fx[key]['nit']} its, {fx[key]['seconds']:.0f} s)")
+
+
+def test_pipelined_host_batch_solve_equals_the_sequential_path(env):
+    """ellp_b200_primal_solve_batch on host buffers: the chunked two-stream pipeline (H2D of chunk c + 1 under the kernel of chunk
+    c) must return exactly what upload -> run -> download returns (tuning key batch_pipeline = 0)."""
+    N, S, ctx = env["N"], env["S"], env["ctx"]
+    nlp, m, ns, seed = 6000, 64, 128, 2
+    n0 = ns + m
+    ctx.check(N.lib.ellp_b200_batch_generate(ctx.h, nlp, m, ns, seed, 0, 0))
+    A = np.zeros((nlp, n0, m)); c = np.zeros((nlp, n0)); b = np.zeros((nlp, m))
+    ctx.check(N.lib.ellp_b200_batch_download_all(ctx.h, N.ptr(A), N.ptr(c), N.ptr(b)))
+    kind = np.ones((nlp, n0), dtype=np.uint8); lb = np.zeros((nlp, n0)); ub = np.zeros((nlp, n0))
+    out = {}
+    for mode in (1, 0):
+        ctx.set_tuning("batch_pipeline", mode)
+        out[mode] = S.primal_solve_batch(A, c, b, kind, lb, ub, max_iter=None, ctx=ctx)
+    ctx.set_tuning("batch_pipeline", 1)
+    p, q = out[1], out[0]
+    assert (p.status == N.OPTIMAL).all() and (p.err == 0).all()
+    assert np.array_equal(p.status, q.status) and np.array_equal(p.iters, q.iters)
+    assert p.obj.tobytes() == q.obj.tobytes() and p.x.tobytes() == q.x.tobytes()
+    assert p.pivots == q.pivots == int(p.iters.sum())

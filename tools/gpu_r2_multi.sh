@@ -22,3 +22,8 @@ fi
 if [[ " $WHAT " == *" batch "* ]]; then
   run bench.py --gpus $N --workload batch_small_lps_65536x64x128 --steps 5 --warmup 3 > gpurun_out/r02_bench_batch_g$N.json 2> gpurun_out/r02_bench_batch_g$N.err; echo "bench batch rc=$?"; cut -c1-400 gpurun_out/r02_bench_batch_g$N.json
 fi
+if [[ " $WHAT " == *" owner "* ]]; then
+  for orr in 0 1; do
+    run bench.py --gpus $N --steps 10 --warmup 3 --owner-ratio $orr --no-e2e > gpurun_out/r02_bench_default_owner${orr}_g$N.json 2> gpurun_out/r02_bench_default_owner${orr}_g$N.err; echo "bench default owner_ratio=$orr rc=$?"; cut -c1-160 gpurun_out/r02_bench_default_owner${orr}_g$N.json
+  done
+fi
