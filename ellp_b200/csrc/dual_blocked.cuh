@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_dual_pivots_fused(D
     __shared__ double s_su[kBlkMax];
     __shared__ double s_mb[kMaxPeers * kMboxFields];
     __shared__ double s_part[kLLMaxBlocks * 4];
+    __shared__ double s_extra;
     __shared__ double s_delta;
     const int tid = threadIdx.x;
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + tid, gsize = (int64_t)gridDim.x * blockDim.x;
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_dual_pivots_fused(D
         }
         double delta;
         ll_gather(llA, par, G, s_part, seq);
-        const Top2 L = ll_reduce_w<DEVEX>(s_part, G, &delta);
+        const Top2 L = (G <= 32) ? ll_reduce_w<DEVEX>(s_part, G, &delta) : ll_reduce<DEVEX>(s_part, G, &s_top, rbuf, &s_extra, &delta);
         if (L.i1 < 0) {  // no infeasible basic variable: optimal (:243-246)
             if (gtid == 0) { st->status = ELLP_OPTIMAL; st->do_update = 0; st->do_step = 0; }
             run = false;
@@ -186,14 +187,21 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_dual_pivots_fused(D
         }
         ll_gather(llC, par, G, s_part, seq);
         LexAcc loc{0., 0., -1, 0};
-        {   // every warp reduces all G partials itself (cf. ll_reduce_w): no block barrier
-            const int lane = tid & 31, per = (G + 31) >> 5;
-            for (int b = lane * per; b < min(G, (lane + 1) * per); ++b) {
+        if (G <= 32) {  // every warp reduces all G partials itself (cf. ll_reduce_w): no block barrier
+            const int b = tid & 31;
+            if (b < G) {
                 const int p = (int)s_part[4 * b + 2];
                 if (s_part[4 * b + 1] != 0.) loc.nan = 1;
                 if (p >= 0) lex_push(loc, s_part[4 * b], p, s_part[4 * b + 3]);
             }
             loc = warp_lexmin(loc);
+        } else {
+            for (int b = tid; b < G; b += blockDim.x) {
+                const int p = (int)s_part[4 * b + 2];
+                if (s_part[4 * b + 1] != 0.) loc.nan = 1;
+                if (p >= 0) lex_push(loc, s_part[4 * b], p, s_part[4 * b + 3]);
+            }
+            loc = block_lexmin(loc, &s_lex, lbuf);
         }
         if (R > 1) {  // every rank's (ratio, nan flag, position, pivot-row entry) to every rank
             if (blockIdx.x == 0 && tid < R * kMboxFields) {
@@ -411,6 +419,21 @@ __global__ void k_xB_finish(DevLP lp, const double* __restrict__ pb, const doubl
     else for (int c = 0; c < kXChunks; ++c) xb += pb[(int64_t)c * lp.ld + i];
     for (int c = 0; c < kXChunks; ++c) xt += pt[(int64_t)c * lp.ld + i];
     lp.x[lp.Bv[i]] = xb - xt;
+}
+// residual check of a long solve: out[0] = max_i |sum_c part[c][i] - b_i| (ordered-bit atomicMax of a non-negative double)
+__global__ void __launch_bounds__(256) k_residual_max(const double* __restrict__ part, int64_t ld, int m, const double* __restrict__ b,
+                                                      unsigned long long* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double r = 0.;
+    if (i < m) {
+        double ax = 0.;
+        for (int c = 0; c < kXChunks; ++c) ax += part[(int64_t)c * ld + i];
+        r = fabs(ax - b[i]);
+        if (r != r) r = CUDART_INF;  // a NaN residual must trigger the rebuild
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, off));
+    if ((threadIdx.x & 31) == 0 && r > 0.) atomicMax(out, (unsigned long long)__double_as_longlong(r));
 }
 __global__ void k_fill_const(double* __restrict__ p, int64_t n, double v) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -135,6 +135,11 @@ struct ellp_b200_ctx {
     double* rf_coop = nullptr;    // publication slots of the cooperative panel kernel
     cudaStream_t copy_stream = nullptr;   // H2D / D2H of the pipelined batch path (ellp_b200_primal_solve_batch)
     std::vector<cudaEvent_t> chunk_ev;
+    int residual_every = -1;      // tuning key "residual_every": pivots between checks of |A x - b| on rebuildable tableau LPs (-1 = default: 1024 for m > 512, 0 = off)
+    double residual_tol = 1e-9;   // relative to 1 + |b|_inf (tuning key "residual_tol_1e12": tolerance in units of 1e-12)
+    double last_residual = 0.;
+    double b_inf = -1.;           // |b|_inf of the resident LP (computed on first use)
+    int fast_upload = 1;          // tuning key "fast_upload": 0 = always upload the whole A (keeps the LP rebuildable: refactor_every works)
     int owner_ratio = 0;          // tuning key "owner_ratio": 0 every rank runs the primal ratio test (default), 1 only the owner of the entering column + decision broadcast
     int batch_pipeline = 1;       // tuning key "batch_pipeline": 0 = upload, run, download one after the other
     bool recompute_x = false;     // set by ellp_b200_run around mid-solve rebuilds of the tableau (not at the start of a run: the caller's x is authoritative)
@@ -557,6 +562,24 @@ int tableau_from_binv(ellp_b200_ctx* ctx) {
     return ELLP_OK;
 }
 
+// |A x - b|_inf of the resident point (tableau engines that kept A): one chunked GEMV over A, deterministic partial sums.
+int primal_residual(ellp_b200_ctx* ctx, double* out) {
+    DevLP& lp = ctx->lp;
+    const int m = lp.m;
+    unsigned long long* slot = reinterpret_cast<unsigned long long*>(ctx->d_flag + 2);  // d_flag holds 4 ints; [0], [1] belong to refactor()
+    CUDA_TRY(cudaMemsetAsync(slot, 0, sizeof(unsigned long long), ctx->stream));
+    dim3 gx((unsigned)((m + 255) / 256), (unsigned)kXChunks);
+    LAUNCH(k_gemv_n_chunks, gx, 256, lp.A, lp.ld, m, lp.n, (const double*)lp.x, (const int32_t*)nullptr, lp.xpart);
+    LAUNCH(k_residual_max, (m + 255) / 256, 256, (const double*)lp.xpart, lp.ld, m, lp.b, slot);
+    unsigned long long bits = 0;
+    CUDA_TRY(cudaMemcpyAsync(&bits, slot, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    double r;
+    std::memcpy(&r, &bits, sizeof(r));
+    *out = r;
+    return ELLP_OK;
+}
+
 // Refactorisation.  Revised engine: B^-1 from the current basis on G = [A_B | I].  Tableau engine: T = B^-1 A_N rebuilt from the
 // resident A (gathered when the basis columns are the identity, through B^-1 otherwise), then -- primal -- the reduced-cost row
 // d = c - c_B^T T; the dual keeps its own d (dual :296-302 never recomputes it).
@@ -780,6 +803,7 @@ int peer_prepare(ellp_b200_ctx* ctx, int32_t m, int32_t n_glob, const ellp_opts*
     ctx->tab_from_binv = false;
     ctx->dj_live = false;
     ctx->devex_live = false;
+    ctx->b_inf = -1.;
     ctx->a_resident = true;  // lp.A aliases the local slice of T (= A_N while the tableau is fresh): download_std_form reads it
     ctx->dual_obj0 = 0.;
     *out = lp;
@@ -1124,6 +1148,9 @@ int ellp_b200_set_tuning(ellp_b200_ctx* ctx, const char* key, int value) {
     else if (!std::strcmp(key, "peer_exchange")) ctx->peer_exchange = value;
     else if (!std::strcmp(key, "batch_pipeline")) ctx->batch_pipeline = value;
     else if (!std::strcmp(key, "owner_ratio")) ctx->owner_ratio = value;
+    else if (!std::strcmp(key, "fast_upload")) ctx->fast_upload = value;
+    else if (!std::strcmp(key, "residual_every")) ctx->residual_every = value;
+    else if (!std::strcmp(key, "residual_tol_1e12")) ctx->residual_tol = 1e-12 * (double)value;
     else if (!std::strcmp(key, "coop_threads")) ctx->coop_threads = value;
     else if (!std::strcmp(key, "coop_ctas_per_sm")) { ctx->coop_ctas_per_sm = value; for (int& v : ctx->coop_threads_cached) v = 0; }
     else if (!std::strcmp(key, "phase_timing")) {  // value = pivots to log (0 = off); read back with ellp_b200_phase_log
@@ -1196,6 +1223,7 @@ int ellp_b200_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_poi
     ctx->tab_from_binv = false;
     ctx->dj_live = false;
     ctx->devex_live = false;
+    ctx->b_inf = -1.;
     cudaStream_t s = ctx->stream;
     // zero the padded scratch once (padding rows must stay zero)
     CUDA_TRY(cudaMemsetAsync(lp.cB, 0, (size_t)((char*)lp.lam - (char*)lp.cB), s));
@@ -1207,7 +1235,7 @@ int ellp_b200_upload(ellp_b200_ctx* ctx, const ellp_std_form* sf, const ellp_poi
     // half of A never crosses PCIe.  Otherwise (or for small LPs) the whole matrix is uploaded and T is built on the device.
     bool fast_condensed = false, diag_ones = true;
     std::vector<double> diag0((size_t)std::max(m, 1), 1.0);
-    if (tableau && lp.condensed && lp.nN > 0 && (double)m * n * 8.0 >= 32.0 * 1048576.0) {
+    if (tableau && lp.condensed && lp.nN > 0 && ctx->fast_upload && (double)m * n * 8.0 >= 32.0 * 1048576.0) {
         if (lp.ld != m) CUDA_TRY(cudaMemsetAsync(lp.T, 0, sizeof(double) * (size_t)lp.ld * lp.nN, s));
         for (int p0 = 0; p0 < lp.nN;) {  // runs of consecutive variable indices in N travel as one copy
             int p1 = p0 + 1;
@@ -1317,6 +1345,7 @@ int ellp_b200_generate_dense_ex(ellp_b200_ctx* ctx, int32_t m, int32_t n_struct,
     ctx->tab_from_binv = false;
     ctx->dj_live = false;
     ctx->devex_live = false;
+    ctx->b_inf = -1.;
     CUDA_TRY(cudaMemsetAsync(lp.cB, 0, (size_t)((char*)lp.lam - (char*)lp.cB), ctx->stream));
     CUDA_TRY(cudaMemsetAsync(lp.y, 0, sizeof(double) * lp.ld, ctx->stream));
     if (tableau && lp.coop) CUDA_TRY(cudaMemsetAsync(lp.coop, 0, sizeof(double) * 6 * 1024, ctx->stream));
@@ -1847,6 +1876,20 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
     // a tableau can only be rebuilt from a resident constraint matrix: the condensed fast upload keeps no A, the peer layout
     // aliases A with its slice of T, the NCCL-sharded layout transforms A in place
     if (ctx->tableau && (!ctx->a_resident || ctx->peer_mode || ctx->sharded)) refactor_every = 0;
+    // residual-triggered rebuild (tableau engines that can rebuild and do not already rebuild periodically)
+    int residual_every = 0;
+    uint64_t pivots_at_check = ctx->pivots_since_refactor;
+    if (ctx->tableau && can_rebuild && lp.xpart && refactor_every == 0) {
+        residual_every = ctx->residual_every >= 0 ? ctx->residual_every : (lp.m > 512 ? 1024 : 0);
+        if (residual_every > 0 && ctx->b_inf < 0.) {
+            std::vector<double> hb((size_t)lp.m);
+            CUDA_TRY(cudaMemcpyAsync(hb.data(), lp.b, sizeof(double) * (size_t)lp.m, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            double mx = 0.;
+            for (double v : hb) mx = std::max(mx, std::fabs(v));
+            ctx->b_inf = mx;
+        }
+    }
     if (ctx->peer_mode && ctx->nranks > 1)  // stream-ordered barrier: no rank starts polling before every rank got here
         NCCL_TRY(nccl::api.AllReduce(lp.part, lp.part + 4, 1, nccl::kFloat64, nccl::kSum, ctx->nccl_comm, ctx->stream));
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -1927,6 +1970,22 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
         if ((rc_loop = read_state(ctx))) break;
         ctx->pivots_since_refactor += h.pivots - before;
         if (h.status != kRunning) break;
+        if (residual_every > 0 && ctx->pivots_since_refactor - pivots_at_check >= (uint64_t)residual_every) {
+            // long solve on a rebuildable tableau: |A x - b|_inf above tolerance => the accumulated updates have drifted, rebuild
+            if (blk > 0) launch_flush(ctx, profile, &ev_used);
+            double rsd = 0.;
+            if ((rc_loop = primal_residual(ctx, &rsd))) break;
+            ctx->last_residual = rsd;
+            pivots_at_check = ctx->pivots_since_refactor;
+            if (!(rsd <= ctx->residual_tol * (1.0 + ctx->b_inf))) {
+                ctx->recompute_x = true;
+                rc_loop = refactor(ctx, &res->refactors);
+                ctx->recompute_x = false;
+                if (rc_loop) break;
+                pivots_at_check = 0;
+                if (ctx->tableau && !ctx->a_resident) residual_every = 0;
+            }
+        }
         if (refactor_every > 0 && ctx->pivots_since_refactor >= (uint64_t)refactor_every) {
             if (blk > 0) launch_flush(ctx, profile, &ev_used);  // pending (U, V) slots belong to the tableau that is about to be replaced
             ctx->recompute_x = ctx->tableau;

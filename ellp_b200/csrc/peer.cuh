@@ -264,13 +264,15 @@ __device__ __forceinline__ double dantzig_key(double r, int side) {
     return k;
 }
 
-// ELLP_PRICE_DEVEX (no reference counterpart: ellp prices with Dantzig's rule): key = r^2 / w over the same candidates, with
+// ELLP_PRICE_DEVEX (no reference counterpart: ellp prices with Dantzig's rule): key = |r| / sqrt(w) over the same candidates (the
+// ordering of r^2 / w at the magnitude of a reduced cost; the EPS-tolerant tie rules of the reference are NOT applied to these keys --
+// keys far below EPS would all "tie" and the index rule would replace the pricing; exact ties keep the first candidate), with
 // primal Devex reference weights w per nonbasic position: after a pivot on (r, q) with scaled pivot row p_t = alpha_rt / alpha_rq,
 // w_t = max(w_t, p_t^2 w_q) and the position handed to the leaving variable gets max(w_q / alpha_rq^2, 1).  p_t is what the row
 // phase computes anyway, so the rule adds one load and one store per position and no exchange.
 __device__ __forceinline__ double devex_key(double r, int side, double w) {
     const double k = dantzig_key(r, side);
-    return (k == -1.0) ? -1.0 : r * r / w;
+    return (k == -1.0) ? -1.0 : fabs(r) / sqrt(w);
 }
 
 // acc - sum_j g[j * stride] * coef[j], j ascending (one fma per pending pivot, i.e. the roundings of j rank-1 updates), with the
@@ -473,6 +475,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
     __shared__ long long s_ll[32];
     __shared__ int s_flag;
     __shared__ double s_part[kLLMaxBlocks * 4];
+    __shared__ double s_extra;
     const int tid = threadIdx.x;
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + tid, gsize = (int64_t)gridDim.x * blockDim.x;
     const int G = gridDim.x, R = pl.nranks, me = pl.rank;
@@ -507,7 +510,9 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
         // every block gathers every block's pricing partial: the local (best, second, position, reduced cost) without a grid barrier
         double loc_rq;
         ll_gather(llA, par, G, s_part, seq);
-        const Top2 loc = ll_reduce_w<true>(s_part, G, &loc_rq);
+        // few blocks (<= one slot per lane): every warp reduces on its own, no block barrier; many blocks: block-wide reduction
+        // (measured at 148 blocks: the per-warp variant costs ~1 us more per reduction, at <= 32 blocks it saves ~0.2 us)
+        const Top2 loc = (G <= 32) ? ll_reduce_w<true>(s_part, G, &loc_rq) : ll_reduce<true>(s_part, G, &s_top, rbuf, &s_extra, &loc_rq);
         if (R > 1 && blockIdx.x == 0 && tid < R * kMboxFields) {  // one block per rank tells the other ranks
             const int dst = tid / kMboxFields, f = tid % kMboxFields;
             double v;
@@ -544,7 +549,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
                 continue;
             }
             q_pos = t.i1;
-            const bool near_tie = (t.a1 - t.a2 < 2. * kEps);
+            const bool near_tie = !DEVEX && (t.a1 - t.a2 < 2. * kEps);
             if (near_tie && R == 1 && tie_rule == ELLP_TIES_REFERENCE) {
                 // the reference's sequential max_by fold over N (primal :271-286), one block, then a grid barrier
                 __syncthreads();
@@ -557,7 +562,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
                 rq = __ldcg(&st->rq);
                 if (DEVEX) wq = __ldcg(lp.wN + q_pos);  // R == 1: every position is local
             } else {
-                if (DEVEX) wq = rq * rq / t.a1;  // key = r^2 / w of the winning position; the same value on every rank
+                if (DEVEX) { const double sq = rq / t.a1; wq = sq * sq; }  // key = |r| / sqrt(w) of the winning position; the same value on every rank
                 if (near_tie) {
                     // largest variable index among the keys within EPS of the global maximum
                     const double kmax = t.a1;
@@ -710,7 +715,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
             ll_gather(llC, par, G, s_part, seq);  // replaces the grid barrier: every block waits for every block's ratios
             if (tl) tl[5] = clock64();
             double alpha_best;
-            Top2 t = ll_reduce_w<false>(s_part, G, &alpha_best);
+            Top2 t = (G <= 32) ? ll_reduce_w<false>(s_part, G, &alpha_best) : ll_reduce<false>(s_part, G, &s_top, rbuf, &s_extra, &alpha_best);
             const double lmin_basic = t.a1;
             if (lambda0 < CUDART_INF) {
                 if (lambda0 < t.a1) { t.a2 = t.a1; t.a1 = lambda0; t.i1 = -1; }

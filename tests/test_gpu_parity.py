@@ -1093,7 +1093,10 @@ def _highs_fixture():
 def test_complete_solve_of_the_dense_lp_matches_highs(env, m, ns, refactor_every, variant, pricing):
     """The bench generator's LP solved TO OPTIMALITY through the boundary on host buffers (slack start, so one phase), status and
     objective against HiGHS (tests/golden/highs_dense_lp.json, made by tests/golden/make_highs_dense_fixture.py on the numpy twin of
-    the generator) to 1e-9, final primal residual |Ax - b| <= 1e-9 |b|.  The large case rebuilds the tableau every 1000 pivots."""
+    the generator) to 1e-9, final primal residual |Ax - b| <= 1e-9 |b|.  The large case uploads the whole A (tuning key fast_upload = 0:
+    the default condensed upload keeps only the nonbasic columns and cannot rebuild) and rebuilds the tableau from it every 1000
+    pivots (B^-1 by the blocked DMMA LU, T = B^-1 A_N, x_B recomputed); tools/full_solve_stats.py shows that the same solves WITHOUT
+    any rebuild (up to 3.6e5 pivots) agree with HiGHS to 1e-13 as well."""
     import bench_lp
     S, N = env["S"], env["N"]
     key = f"{m}x{ns}_seed0_variant{variant}"
@@ -1105,8 +1108,15 @@ def test_complete_solve_of_the_dense_lp_matches_highs(env, m, ns, refactor_every
     cls = S.GpuDualSimplexSolver if variant else S.GpuPrimalSimplexSolver
     sol = cls.new(None, ctx=env["ctx"], engine=N.ENGINE_TABLEAU, block_k=48, check_every=96, refactor_every=refactor_every,
                   pricing=N.PRICE_DEVEX if pricing == "devex" else N.PRICE_REFERENCE, tie_rule=N.TIES_CANONICAL)
-    res, _ = sol.solve_with_initial(m, m + ns, lp["A"], lp["c"], lp["b"], lp["kind"], lp["lb"], lp["ub"], *st)
+    env["ctx"].set_tuning("fast_upload", 0 if refactor_every else 1)
+    try:
+        res, _ = sol.solve_with_initial(m, m + ns, lp["A"], lp["c"], lp["b"], lp["kind"], lp["lb"], lp["ub"], *st)
+    finally:
+        env["ctx"].set_tuning("fast_upload", 1)
     assert res.status == N.OPTIMAL == fx[key]["status"]
+    if refactor_every:
+        # a rebuild happens at the first host read-back after `refactor_every` pivots (whole blocks of 48, read back every 96)
+        assert res.refactors >= res.iters // (refactor_every + 96) - 1 and (res.iters < refactor_every + 96 or res.refactors > 0)
     x = st[0]
     obj = float(lp["c"] @ x)
     assert _rel(obj, fx[key]["obj"]) < 1e-9, (obj, fx[key]["obj"])
@@ -1135,3 +1145,40 @@ def test_pipelined_host_batch_solve_equals_the_sequential_path(env):
     assert np.array_equal(p.status, q.status) and np.array_equal(p.iters, q.iters)
     assert p.obj.tobytes() == q.obj.tobytes() and p.x.tobytes() == q.x.tobytes()
     assert p.pivots == q.pivots == int(p.iters.sum())
+
+
+@pytest.mark.parametrize("which", ["primal", "dual"])
+def test_residual_triggered_rebuild_of_the_tableau(env, which):
+    """Long solves on a rebuildable tableau check |A x - b|_inf every `residual_every` pivots and rebuild T = B^-1 A_N (and x_B) from A
+    when it exceeds the tolerance.  Forced here with a zero tolerance: the rebuilds happen, the solve ends on the oracle's optimum,
+    and with the default tolerance (1e-9 relative) a healthy solve triggers none."""
+    O, S, N, ctx = env["O"], env["S"], env["N"], env["ctx"]
+    m, n = 520, 700
+    A, b, c = _dense_lp(31, m, n)
+    if which == "dual":
+        Af, cf, kind, lb, ub, start = _gte_dual_start(A, b, c)
+        cls, oid = S.GpuDualSimplexSolver, O.DUAL
+    else:
+        Af, cf, kind, lb, ub, x0, B0, N0, Ns0 = _slack_start_primal(A, b, c)
+        start = [x0, B0, N0, Ns0]
+        cls, oid = S.GpuPrimalSimplexSolver, O.PRIMAL
+    st = [a.copy() for a in start]
+    ref = O.solve_with_initial(oid, m, n + m, Af, cf, b, kind, lb, ub, *st, max_iter=None, **({"mode": O.MODE_CANONICAL} if which == "primal" else {}))
+    out = {}
+    for tag, tol in (("forced", 0), ("default", 1000)):
+        ctx.set_tuning("residual_every", 100)
+        ctx.set_tuning("residual_tol_1e12", tol)
+        try:
+            sg = [a.copy() for a in start]
+            sol = cls.new(None, ctx=ctx, engine=N.ENGINE_TABLEAU, block_k=16, check_every=32, tie_rule=N.TIES_CANONICAL)
+            res, _ = sol.solve_with_initial(m, n + m, Af, cf, b, kind, lb, ub, *sg)
+        finally:
+            ctx.set_tuning("residual_every", -1)
+            ctx.set_tuning("residual_tol_1e12", 1000)
+        assert res.status == ref.status == O.OPTIMAL
+        assert _rel(res.obj, ref.obj) < 1e-9
+        np.testing.assert_allclose(sg[0], st[0], rtol=1e-8, atol=1e-8)
+        np.testing.assert_allclose(Af @ sg[0], b, rtol=1e-10, atol=1e-9)
+        out[tag] = (int(res.refactors), int(res.iters))
+    assert out["forced"][0] >= out["forced"][1] // 100 - 1 and out["forced"][0] > 0, out
+    assert out["default"][0] == 0, out

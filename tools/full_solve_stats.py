@@ -12,13 +12,14 @@ from ellp_b200 import solver as S
 m, ns = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (4096, 8192)
 fx = json.load(open(os.path.join(ROOT, "tests", "golden", "highs_dense_lp.json")))
 ctx = N.Context(0)
-for variant, pricing, rf in [(0, "dantzig", 1000), (0, "devex", 1000), (1, "reference", 1000), (1, "devex", 1000), (1, "devex", 0)]:
+for variant, pricing, rf in [(0, "dantzig", 0), (0, "devex", 0), (1, "reference", 0), (1, "devex", 0), (0, "dantzig", 2000), (1, "devex", 500)]:
     lp = bench_lp.dense_lp(m, ns, 0, variant)
     key = f"{m}x{ns}_seed0_variant{variant}"
     cls = S.GpuDualSimplexSolver if variant else S.GpuPrimalSimplexSolver
     sol = cls.new(None, ctx=ctx, engine=N.ENGINE_TABLEAU, block_k=48, check_every=96, refactor_every=rf,
                   pricing=N.PRICE_DEVEX if pricing == "devex" else N.PRICE_REFERENCE, tie_rule=N.TIES_CANONICAL)
     best = None
+    ctx.set_tuning("fast_upload", 0 if rf else 1)  # a rebuild needs the whole A on the device
     for rep in range(2):
         st = [lp[k].copy() for k in ("x", "B", "N", "N_side")] + ([lp["y"].copy(), lp["d"].copy()] if variant else [])
         t0 = time.perf_counter()
