@@ -116,6 +116,9 @@ struct ellp_b200_ctx {
     int flush4_min_k = 40;
     bool flush_attrs_set = false;
     int flush2_col_steps = 32;    // column steps per CTA of k_blk_flush3 / k_blk_flush4
+    int flush_waves = 6;          // tuning key "flush_waves": keep at least this many waves of CTAs (narrow shards); 0 = take flush2_col_steps as given.
+                                  // Sweep on the shard shapes 32768 x {4096, 8192, 16384} (profiles/r02_flush_shard_sweep.jsonl): ~1000 CTAs (7 waves) is the
+                                  // optimum for both kernels; the round-1 value 8 cut narrow shards into 14 waves of short CTAs (0.694 vs 0.618 ms at 32768 x 4096, k = 56)
     int coop_pivots = 1;          // blocked engine: 1 = k_blk_pivots_fused (one cooperative launch per block of pivots), 0 = five kernels per pivot
     // peer-memory sharded engine (peer.cuh): condensed tableau split by nonbasic position, exchange fused into the pivot kernel
     bool a_resident = true;       // false after the condensed fast upload: only T = A_N is on the device
@@ -133,7 +136,8 @@ struct ellp_b200_ctx {
     double* rf_V = nullptr;       // kPanel x rf_ldv block row of the LU
     int64_t rf_ldv = 0;
     double* rf_coop = nullptr;    // publication slots of the cooperative panel kernel
-    cudaStream_t copy_stream = nullptr;   // H2D / D2H of the pipelined batch path (ellp_b200_primal_solve_batch)
+    cudaStream_t copy_stream = nullptr;   // H2D of the pipelined batch path (ellp_b200_primal_solve_batch)
+    cudaStream_t d2h_stream = nullptr;    // D2H of the same
     std::vector<cudaEvent_t> chunk_ev;
     int residual_every = -1;      // tuning key "residual_every": pivots between checks of |A x - b| on rebuildable tableau LPs (-1 = default: 1024 for m > 512, 0 = off)
     double residual_tol = 1e-9;   // relative to 1 + |b|_inf (tuning key "residual_tol_1e12": tolerance in units of 1e-12)
@@ -412,9 +416,9 @@ void launch_rankk(ellp_b200_ctx* ctx, double* E, int64_t ld, int R, int C, const
     const int steps_total = (C + cols_per_step - 1) / cols_per_step;
     const size_t smem = kern == 4 ? blk_flush4_smem_bytes(K4) : (kern == 3 ? blk_flush3_smem_bytes(K4) : blk_flush_smem_bytes(K4));
     int col_steps = std::max(1, std::min(kern == 1 ? ctx->flush_col_steps : ctx->flush2_col_steps, steps_total));
-    if (kern != 1) {  // one CTA per SM: keep at least ~8 waves of CTAs so the last partial wave stays small (narrow shards)
+    if (kern != 1) {  // one CTA per SM: keep at least ~6 waves of CTAs so the last partial wave stays small (narrow shards)
         const int64_t row_blocks = (R + kFlushRows - 1) / kFlushRows;
-        while (col_steps > 4 && row_blocks * ((steps_total + col_steps - 1) / col_steps) < 8 * 148) col_steps >>= 1;
+        while (col_steps > 4 && row_blocks * ((steps_total + col_steps - 1) / col_steps) < (int64_t)ctx->flush_waves * 148) col_steps >>= 1;
     }
     dim3 grid((unsigned)((R + kFlushRows - 1) / kFlushRows), (unsigned)((steps_total + col_steps - 1) / col_steps));
     const bool stream = (double)R * C * 8.0 > (double)ctx->rank1_stream_min_mb * 1048576.0;
@@ -1123,6 +1127,7 @@ void ellp_b200_destroy(ellp_b200_ctx* ctx) {
     if (ctx->tlog) cudaFree(ctx->tlog);
     for (auto e : ctx->chunk_ev) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     if (ctx->h_st) cudaFreeHost(ctx->h_st);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1141,6 +1146,7 @@ int ellp_b200_set_tuning(ellp_b200_ctx* ctx, const char* key, int value) {
     else if (!std::strcmp(key, "refactor_panel")) ctx->refactor_panel = value;
     else if (!std::strcmp(key, "flush_col_steps")) { ctx->flush_col_steps = std::max(1, value); ctx->flush2_col_steps = std::max(1, value); }
     else if (!std::strcmp(key, "flush_kernel")) ctx->flush_kernel = value;
+    else if (!std::strcmp(key, "flush_waves")) ctx->flush_waves = value;
     else if (!std::strcmp(key, "flush4_min_k")) ctx->flush4_min_k = value;
     else if (!std::strcmp(key, "coop_pivots")) ctx->coop_pivots = value;
     else if (!std::strcmp(key, "cuda_graphs")) ctx->use_graphs = value;
@@ -1759,12 +1765,14 @@ int ellp_b200_primal_solve_batch(ellp_b200_ctx* ctx, const ellp_batch* bt, const
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_batch_primal, kBatchThreads, smem);
     const size_t m = (size_t)bt->m, n = (size_t)bt->n, nc = (size_t)B.nc;
     const int per = (bt->nlp + nchunks - 1) / nchunks;
-    cudaStream_t cs = ctx->copy_stream, ks = ctx->stream;
+    if (!ctx->d2h_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = ctx->copy_stream, ks = ctx->stream, ds = ctx->d2h_stream;
     CUDA_TRY(cudaEventRecord(ctx->ev0, ks));
     CUDA_TRY(cudaStreamWaitEvent(cs, ctx->ev0, 0));  // the copies start after whatever was queued on the compute stream
-    for (int c = 0; c < nchunks; ++c) {
+    // three streams: H2D of chunk c + 1 (cs) and D2H of chunk c - 1 (ds) run under the kernel of chunk c (ks); the chunks use
+    // disjoint regions of the device buffers, so the only dependencies are H2D(c) -> kernel(c) -> D2H(c)
+    auto h2d = [&](int c) -> int {
         const size_t l0 = (size_t)c * per, cnt = std::min<size_t>(per, (size_t)bt->nlp - l0);
-        if (cnt == 0) break;
         CUDA_TRY(cudaMemcpyAsync(B.A + l0 * m * n, bt->A + l0 * m * n, sizeof(double) * cnt * m * n, cudaMemcpyHostToDevice, cs));
         CUDA_TRY(cudaMemcpyAsync(B.c + l0 * n, bt->c + l0 * n, sizeof(double) * cnt * n, cudaMemcpyHostToDevice, cs));
         CUDA_TRY(cudaMemcpyAsync(B.b + l0 * m, bt->b + l0 * m, sizeof(double) * cnt * m, cudaMemcpyHostToDevice, cs));
@@ -1772,6 +1780,12 @@ int ellp_b200_primal_solve_batch(ellp_b200_ctx* ctx, const ellp_batch* bt, const
         CUDA_TRY(cudaMemcpyAsync(B.ub + l0 * n, bt->ub + l0 * n, sizeof(double) * cnt * n, cudaMemcpyHostToDevice, cs));
         CUDA_TRY(cudaMemcpyAsync(B.kind + l0 * n, bt->kind + l0 * n, cnt * n, cudaMemcpyHostToDevice, cs));
         CUDA_TRY(cudaEventRecord(ctx->chunk_ev[2 * c], cs));
+        return ELLP_OK;
+    };
+    const int used = (bt->nlp + per - 1) / per;
+    if (int rc = h2d(0)) return rc;
+    for (int c = 0; c < used; ++c) {
+        const size_t l0 = (size_t)c * per, cnt = std::min<size_t>(per, (size_t)bt->nlp - l0);
         CUDA_TRY(cudaStreamWaitEvent(ks, ctx->chunk_ev[2 * c], 0));
         BatchArgs a{};
         a.nlp = (int)cnt; a.m = B.m; a.n0 = B.n0; a.nc = B.nc; a.ld = B.ld;
@@ -1787,23 +1801,25 @@ int ellp_b200_primal_solve_batch(ellp_b200_ctx* ctx, const ellp_batch* bt, const
         k_batch_primal<<<grid, kBatchThreads, smem, ks>>>(a);
         ctx->launches++;
         CUDA_TRY(cudaEventRecord(ctx->chunk_ev[2 * c + 1], ks));
-        CUDA_TRY(cudaStreamWaitEvent(cs, ctx->chunk_ev[2 * c + 1], 0));
-        if (res->status) CUDA_TRY(cudaMemcpyAsync(res->status + l0, B.status + l0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, cs));
-        if (res->obj) CUDA_TRY(cudaMemcpyAsync(res->obj + l0, B.obj + l0, sizeof(double) * cnt, cudaMemcpyDeviceToHost, cs));
-        if (res->iters) CUDA_TRY(cudaMemcpyAsync(res->iters + 2 * l0, B.iters + 2 * l0, sizeof(int32_t) * 2 * cnt, cudaMemcpyDeviceToHost, cs));
-        if (res->err) CUDA_TRY(cudaMemcpyAsync(res->err + l0, B.err + l0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, cs));
-        if (res->x) CUDA_TRY(cudaMemcpyAsync(res->x + l0 * nc, B.x + l0 * nc, sizeof(double) * cnt * nc, cudaMemcpyDeviceToHost, cs));
-        if (res->trace_len) CUDA_TRY(cudaMemcpyAsync(res->trace_len + l0, B.trace_len + l0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, cs));
-        if (res->trace && B.trace) CUDA_TRY(cudaMemcpyAsync(res->trace + l0 * B.trace_cap, B.trace + l0 * B.trace_cap, sizeof(ellp_trace_rec) * cnt * B.trace_cap, cudaMemcpyDeviceToHost, cs));
+        if (c + 1 < used) { if (int rc = h2d(c + 1)) return rc; }
+        CUDA_TRY(cudaStreamWaitEvent(ds, ctx->chunk_ev[2 * c + 1], 0));
+        if (res->status) CUDA_TRY(cudaMemcpyAsync(res->status + l0, B.status + l0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, ds));
+        if (res->obj) CUDA_TRY(cudaMemcpyAsync(res->obj + l0, B.obj + l0, sizeof(double) * cnt, cudaMemcpyDeviceToHost, ds));
+        if (res->iters) CUDA_TRY(cudaMemcpyAsync(res->iters + 2 * l0, B.iters + 2 * l0, sizeof(int32_t) * 2 * cnt, cudaMemcpyDeviceToHost, ds));
+        if (res->err) CUDA_TRY(cudaMemcpyAsync(res->err + l0, B.err + l0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, ds));
+        if (res->x) CUDA_TRY(cudaMemcpyAsync(res->x + l0 * nc, B.x + l0 * nc, sizeof(double) * cnt * nc, cudaMemcpyDeviceToHost, ds));
+        if (res->trace_len) CUDA_TRY(cudaMemcpyAsync(res->trace_len + l0, B.trace_len + l0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, ds));
+        if (res->trace && B.trace) CUDA_TRY(cudaMemcpyAsync(res->trace + l0 * B.trace_cap, B.trace + l0 * B.trace_cap, sizeof(ellp_trace_rec) * cnt * B.trace_cap, cudaMemcpyDeviceToHost, ds));
     }
     CUDA_TRY(cudaEventRecord(ctx->ev1, ks));
     CUDA_TRY(cudaStreamSynchronize(ks));
     CUDA_TRY(cudaStreamSynchronize(cs));
+    CUDA_TRY(cudaStreamSynchronize(ds));
     CUDA_TRY(cudaGetLastError());
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     res->ms_device = ms;
-    res->launches = (uint64_t)nchunks;
+    res->launches = (uint64_t)used;
     if (res->iters) {
         uint64_t pv = 0;
         for (size_t k = 0; k < 2 * (size_t)bt->nlp; ++k) pv += (uint64_t)res->iters[k];

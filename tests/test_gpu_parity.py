@@ -1180,5 +1180,7 @@ def test_residual_triggered_rebuild_of_the_tableau(env, which):
         np.testing.assert_allclose(sg[0], st[0], rtol=1e-8, atol=1e-8)
         np.testing.assert_allclose(Af @ sg[0], b, rtol=1e-10, atol=1e-9)
         out[tag] = (int(res.refactors), int(res.iters))
-    assert out["forced"][0] >= out["forced"][1] // 100 - 1 and out["forced"][0] > 0, out
-    assert out["default"][0] == 0, out
+    # refactors counts the initial build of the tableau (1) + the triggered rebuilds; a check happens at the first host read-back
+    # (every 32 pivots) after 100 pivots since the last check, i.e. at most every 128 pivots
+    assert out["forced"][0] >= 1 + out["forced"][1] // 160 and out["forced"][0] > 1, out
+    assert out["default"][0] == 1, out
