@@ -2129,6 +2129,28 @@ static int solve_with_initial(ellp_b200_ctx* ctx, const ellp_std_form* sf, ellp_
         res->obj = solver == ELLP_PRIMAL ? obj : host_dual_obj(sf, pt->y, pt->d);
         return ELLP_OK;
     }
+    if (solver == ELLP_DUAL && o->max_iter > 0 && pt->nB == m) {
+        // Loop head of the dual (dual :188-246) on the caller's own point: no basic variable violates a bound => Optimal before any
+        // LU / device work (the reference computes the LU first, but its only use would be the pivot that does not happen).  An
+        // O(m) scan of host data; every dual phase 1 that starts feasible (netlib AFIRO) ends here without touching the GPU.
+        bool any = false;
+        for (int i = 0; i < m && !any; ++i) {
+            const int v = pt->B[i];
+            if (v < 0 || v >= n) { any = true; break; }  // let the upload report the out-of-range index
+            const double x_i = pt->x[v];
+            switch (sf->kind[v]) {
+                case ELLP_LOWER: any = x_i < sf->lb[v] - kEps; break;
+                case ELLP_UPPER: any = x_i > sf->ub[v] + kEps; break;
+                case ELLP_TWOSIDED: any = (x_i > sf->ub[v] + kEps) || (x_i < sf->lb[v] - kEps); break;
+                default: break;
+            }
+        }
+        if (!any) {
+            res->status = ELLP_OPTIMAL;
+            res->obj = host_dual_obj(sf, pt->y, pt->d);
+            return ELLP_OK;
+        }
+    }
     if (int rc = ellp_b200_upload(ctx, sf, pt, solver, o)) return rc;
     int rc = ellp_b200_run(ctx, o, res);
     if (rc) return rc;

@@ -104,13 +104,17 @@ typedef struct {
     uint64_t max_iter;        /* solver.max_iter: Default = 1000, new(None) = UINT64_MAX */
     int32_t  tie_rule;        /* ELLP_TIES_* */
     int32_t  engine;          /* ELLP_ENGINE_* */
-    int32_t  refactor_every;  /* rebuild the basis inverse every k pivots (0 = library default) */
+    int32_t  refactor_every;  /* rebuild the basis inverse (revised engine) / the tableau T = B^-1 A_N from the resident A (tableau engines) every k
+                                 pivots; 0 = library default: 100 for m <= 512 (25 for the dual and Devex-priced solves on the tableau), above that
+                                 only when |A x - b|_inf drifts (see ellp_b200_set_tuning "residual_every") */
     int32_t  check_every;     /* host reads the 16-byte status every k iterations (0 = default) */
     int32_t  phase_tag;       /* value stored in trace records */
     int32_t  profile;         /* 1: record CUDA events around every rank-1 update launch */
     ellp_trace_rec* trace;    /* optional caller buffer */
     int64_t  trace_cap;
-    int32_t  pricing;         /* ELLP_PRICE_*: dual leaving-row rule, revised engine (primal pricing is always Dantzig like the reference) */
+    int32_t  pricing;         /* ELLP_PRICE_*: REFERENCE = the reference's rules (primal: Dantzig with its tie fold, dual: first infeasible row);
+                                 STEEPEST_EDGE = exact dual steepest edge (revised engine); DEVEX = Devex reference weights, primal entering
+                                 column and dual leaving row, blocked tableau engines (block_k > 1) */
     int32_t  ratio;           /* ELLP_RATIO_*: dual entering-column rule, revised engine */
     int32_t  block_k;         /* tableau engine: > 1 defers the row reduction and applies it as ONE rank-k update
                                  (T -= U V on the fp64 tensor pipe) every block_k pivots; 0/1 = rank-1 update per pivot.
@@ -156,7 +160,11 @@ int ellp_b200_generate_dense(ellp_b200_ctx*, int32_t m, int32_t n_struct, uint64
 int ellp_b200_generate_dense_ex(ellp_b200_ctx*, int32_t m, int32_t n_struct, uint64_t seed, int32_t variant, const ellp_opts* o);
 /* copies the resident standard form to host buffers (any pointer may be NULL) */
 int ellp_b200_download_std_form(ellp_b200_ctx*, double* A, double* c, double* b, uint8_t* kind, double* lb, double* ub);
-/* tuning knobs: "rank1_cols_per_cta", "rank1_stream_min_mb", "refactor_mode", "flush_col_steps", "coop_pivots", "peer_exchange" */
+/* tuning knobs: "rank1_cols_per_cta", "rank1_stream_min_mb", "refactor_mode", "flush_col_steps", "flush_waves", "flush_kernel", "coop_pivots",
+ * "coop_threads", "peer_exchange", "owner_ratio" (sharded primal: 1 = only the owner of the entering column runs the ratio test), "fast_upload"
+ * (0 = always upload the whole A so that the tableau stays rebuildable), "residual_every" / "residual_tol_1e12" (residual-triggered rebuild of a
+ * rebuildable tableau: pivots between checks of |A x - b|_inf, tolerance in units of 1e-12 relative to 1 + |b|_inf), "batch_pipeline" (0 = upload,
+ * run, download of ellp_b200_primal_solve_batch one after the other), "cuda_graphs", "small_path", "phase_timing" */
 int ellp_b200_set_tuning(ellp_b200_ctx*, const char* key, int value);
 /* profiling aid: after set_tuning("phase_timing", P) the fused pivot kernel logs 10 clock64() stamps per pivot (block 0,
  * thread 0; phase boundaries, see peer.cuh) for the next P pivots; this copies the first `pivots` records (10 int64 each). */

@@ -1184,3 +1184,15 @@ def test_residual_triggered_rebuild_of_the_tableau(env, which):
     # (every 32 pivots) after 100 pivots since the last check, i.e. at most every 128 pivots
     assert out["forced"][0] >= 1 + out["forced"][1] // 160 and out["forced"][0] > 1, out
     assert out["default"][0] == 1, out
+
+
+def test_small_cases_of_every_kernel_family(env):
+    """tools/sanitize_cases.py (written for compute-sanitizer, which this pool keeps closed) as a plain regression: one small,
+    self-checking invocation of every kernel family -- K6 batch, fused primal / dual pivot kernels + flushes, the three rank-k
+    kernels at ragged shapes, blocked LU, single-CTA dual / Gauss-Jordan, rank-1."""
+    import importlib, os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    sc = importlib.import_module("sanitize_cases")
+    for name, fn in sc.CASES.items():
+        print(name, fn(env["ctx"]))
