@@ -189,6 +189,27 @@ def other_config_legs(ctx, N) -> dict:
             ctx.check(N.lib.ellp_b200_run(ctx.h, C.byref(od), C.byref(res)))
             ts.append(time.perf_counter() - t0)
         leg["devex_complete_solve"] = {"status": int(res.status), "pivots": int(res.iters), "ms_per_solve": 1e3 * min(ts[1:]), "objective": float(res.obj)}
+        # the same complete solve END TO END through the boundary: host buffers in (pinned A), point out
+        import torch
+        n = m + ns
+        A_h = torch.empty(m * n, dtype=torch.float64, pin_memory=True).numpy()
+        c_h = np.zeros(n); b_h = np.zeros(m); lb_h = np.zeros(n); ub_h = np.zeros(n); kind_h = np.zeros(n, dtype=np.uint8)
+        ctx.check(N.lib.ellp_b200_generate_dense_ex(ctx.h, m, ns, SEED, 1, C.byref(N.default_opts(1, engine=N.ENGINE_REVISED))))
+        ctx.check(N.lib.ellp_b200_download_std_form(ctx.h, N.ptr(A_h), N.ptr(c_h), N.ptr(b_h), N.ptr(kind_h), N.ptr(lb_h), N.ptr(ub_h)))
+        sf = N.StdForm(m, n, N.ptr(A_h), N.ptr(c_h), N.ptr(b_h), N.ptr(kind_h), N.ptr(lb_h), N.ptr(ub_h))
+        te = []
+        for _ in range(3):
+            x = np.zeros(n); x[ns:] = -b_h
+            B = np.arange(ns, n, dtype=np.int32); Nv = np.arange(ns, dtype=np.int32); Ns = np.zeros(ns, dtype=np.uint8)
+            y = np.zeros(m); d = c_h.copy()
+            pt = N.Point(N.ptr(x), N.ptr(B), N.ptr(Nv), N.ptr(Ns), N.ptr(y), N.ptr(d), m, ns)
+            t0 = time.perf_counter()
+            ctx.check(N.lib.ellp_b200_dual_solve_with_initial(ctx.h, C.byref(sf), C.byref(pt), C.byref(od), C.byref(res)))
+            te.append(time.perf_counter() - t0)
+        leg["devex_complete_solve"]["e2e_ms_per_solve_host_buffers"] = 1e3 * min(te[1:])
+        leg["devex_complete_solve"]["e2e_objective"] = float(res.obj)
+        leg["devex_complete_solve"]["e2e_primal_residual_rel"] = float(np.abs(A_h.reshape((n, m)).T @ x - b_h).max() / np.abs(b_h).max())
+        del A_h
         out["configs[2]"] = leg
     except Exception as e:
         out["configs[2]"] = {"error": str(e)}

@@ -628,16 +628,21 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
         const bool at_lower = (q_side == ELLP_NB_LOWER);
         const int cnt = slot;
         if (tl) tl[2] = clock64();
-        // ---- C1: the owner rebuilds the entering column of the CURRENT tableau and stores it into every rank's buffer
+        // ---- C1: the owner rebuilds the entering column of the CURRENT tableau and stores it into every OTHER rank's buffer; its own
+        // copy goes straight to dcol (phase C2 walks the rows with the same thread mapping, so no store -> poll round trip through L2)
+        const bool own_col = (q_pos >= lp.pos_lo && q_pos < lp.pos_lo + nT);
+        double a_own = 0.;  // entry of the first row this thread owns (row == gtid)
         {
             const int ql = q_pos - lp.pos_lo;
-            if (ql >= 0 && ql < nT) {
+            if (own_col) {
                 __syncthreads();
                 if (tid < cnt) s_vec[tid] = __ldcg(lp.V + (int64_t)tid * lp.ldv + ql);
                 __syncthreads();
                 for (int64_t i = gtid; i < lp.ld; i += gsize) {
                     const double a = corr_chain(__ldcg(lp.T + (int64_t)ql * lp.ld + i), lp.U + i, lp.ld, s_vec, cnt);
-                    for (int d = 0; d < R; ++d) ll_send(pl.col[d] + (int64_t)par * pl.col_cap + i, a, seq);
+                    for (int d = 0; d < R; ++d)
+                        if (d != me) ll_send(pl.col[d] + (int64_t)par * pl.col_cap + i, a, seq);
+                    if (i == gtid) a_own = a; else lp.dcol[i] = a;
                 }
             }
         }
@@ -697,7 +702,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 1) k_blk_pivots_fused(DevLP 
                         xv = __ldcg(lp.x + var);
                         kv = lp.kind[var]; lbv = lp.lb[var]; ubv = lp.ub[var];
                     }
-                    const double a = ll_recv(colbuf + i, seq);
+                    const double a = own_col ? (i == gtid ? a_own : __ldcg(lp.dcol + i)) : ll_recv(colbuf + i, seq);
                     lp.dcol[i] = a;
                     if (i == gtid) { rc.row = i; rc.a = a; rc.var = var; rc.xv = xv; }
                     if (i < m) {

@@ -291,3 +291,56 @@ def test_display_of_standard_form_and_solver_result():
     assert str(SolverResult("Optimal", Solution(19.157894736842103, np.zeros(1)))) == "found optimal point with objective 19.157894736842103"
     assert str(SolverResult("Infeasible")) == "problem is infeasible" and str(SolverResult("Unbounded")) == "problem is unbounded"
     assert str(SolverResult("MaxIter", obj=float("inf"))) == "reached max iterations, current objective = inf"
+
+
+# ---------------------------------------------------------------- rust_shim/src/solvers/gpu/ffi.rs mirrors the header field by field
+def test_rust_ffi_structs_mirror_the_header():
+    """No Rust toolchain here: the #[repr(C)] structs of rust_shim/.../ffi.rs are checked STATICALLY against include/ellp_b200.h --
+    same structs, same number of fields, same order, compatible types -- and every extern "C" fn it declares is exported by the .so."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "ellp_b200.h")).read()
+    ffi = open(os.path.join(root, "rust_shim", "src", "solvers", "gpu", "ffi.rs")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    ffi_nc = re.sub(r"//[^\n]*", "", ffi)
+
+    def c_fields(name):
+        body = re.search(r"typedef struct \{([^{}]*)\}\s*" + name + r"\s*;", hdr, flags=re.S).group(1)
+        out = []
+        for decl in body.split(";"):
+            decl = " ".join(decl.split())
+            if not decl:
+                continue
+            m_ = re.match(r"(const\s+)?(\w+)\s*(\*?)\s*(.*)$", decl)
+            const, ty, star0, rest = m_.groups()
+            for nm in rest.split(","):
+                nm = nm.strip()
+                star = star0 or ("*" if nm.startswith("*") else "")
+                out.append((ty, bool(star), bool(const)))
+        return out
+
+    def rs_fields(name):
+        body = re.search(r"pub struct " + name + r"\s*\{(.*?)\}", ffi_nc, flags=re.S).group(1)
+        out = []
+        for decl in body.split(","):
+            decl = " ".join(decl.split())
+            if not decl:
+                continue
+            ty = decl.split(":", 1)[1].strip()
+            ptr = ty.startswith("*")
+            const = ty.startswith("*const")
+            base = ty.replace("*const", "").replace("*mut", "").strip()
+            out.append((base, ptr, const))
+        return out
+
+    cmap = {"int32_t": "i32", "uint32_t": "u32", "int64_t": "i64", "uint64_t": "u64", "double": "f64", "uint8_t": "u8", "ellp_trace_rec": "ellp_trace_rec"}
+    for name in ("ellp_std_form", "ellp_point", "ellp_trace_rec", "ellp_opts", "ellp_result"):
+        cf, rf = c_fields(name), rs_fields(name)
+        assert len(cf) == len(rf), (name, cf, rf)
+        for (cty, cptr, cconst), (rty, rptr, rconst) in zip(cf, rf):
+            assert cmap[cty] == rty and cptr == rptr and (not cptr or cconst == rconst), (name, cty, rty)
+    lib = C.CDLL(N.LIB_PATH)
+    fns = re.findall(r"pub fn (ellp_b200_\w+)\(", ffi_nc)
+    assert len(fns) >= 6
+    for fn in fns:
+        assert hasattr(lib, fn), fn
+        assert re.search(r"\b" + fn + r"\s*\(", hdr), fn
