@@ -1196,3 +1196,24 @@ def test_small_cases_of_every_kernel_family(env):
     sc = importlib.import_module("sanitize_cases")
     for name, fn in sc.CASES.items():
         print(name, fn(env["ctx"]))
+
+
+def test_dual_solve_that_starts_optimal_needs_no_device_work(env):
+    """Loop head of the dual (dual :188-246): a starting point without any bound violation is Optimal before the first LU; the
+    boundary answers from the host data (0 launches), with the reference's objective (dual_obj(y, d))."""
+    O, S, N = env["O"], env["S"], env["N"]
+    A = np.asfortranarray(np.array([[1.0, 2.0, 1.0, 0.0], [3.0, 1.0, 0.0, 1.0]])); c = np.array([1.0, 1.0, 0.0, 0.0]); b = np.array([4.0, 5.0])
+    kind = np.array([N.LOWER] * 4, dtype=np.uint8); lb = np.zeros(4); ub = np.zeros(4)
+    start = [np.array([0.0, 0.0, 4.0, 5.0]), np.array([2, 3], dtype=np.int32), np.array([0, 1], dtype=np.int32), np.array([0, 0], dtype=np.uint8), np.zeros(2), c.copy()]
+    ref = O.solve_with_initial(O.DUAL, 2, 4, A, c, b, kind, lb, ub, *[a.copy() for a in start], max_iter=10)
+    for engine in (N.ENGINE_REVISED, N.ENGINE_TABLEAU):
+        sg = [a.copy() for a in start]
+        res, _ = S.GpuDualSimplexSolver.new(10, ctx=env["ctx"], engine=engine, block_k=4).solve_with_initial(2, 4, A, c, b, kind, lb, ub, *sg)
+        assert res.status == ref.status == O.OPTIMAL and res.iters == 0 and res.launches == 0
+        assert res.obj == ref.obj
+        for g, s0 in zip(sg, start):
+            np.testing.assert_array_equal(g, s0)
+    # max_iter = 0 still reports MaxIter first (dual :191-194)
+    sg = [a.copy() for a in start]
+    res, _ = S.GpuDualSimplexSolver.new(0, ctx=env["ctx"], engine=N.ENGINE_REVISED).solve_with_initial(2, 4, A, c, b, kind, lb, ub, *sg)
+    assert res.status == N.MAXITER
