@@ -901,7 +901,8 @@ void launch_tableau_primal_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, boo
     LAUNCH(k_price_tab, (nN + 255) / 256, 256, lp.dj, lp.Nv, lp.Ns, nN, lp.rN, lp.key, st, lp.condensed);  // primal :189, :253-270
     LAUNCH_SMEM(k_select_primal, 1, kScanThreads, kScanSmemBytes, lp.key, lp.rN, lp.Nv, lp.Ns, nN, o->tie_rule, st);           // :271-292
     LAUNCH(k_ratio_prep, (m + 255) / 256, 256, lp, 0, blk > 0 ? ctx->blk_fill : 0, st);         // :295-367
-    LAUNCH_SMEM(k_ratio_pick, 1, kScanThreads, kScanSmemBytes, lp, o->tie_rule, st);             // :379-434, :205-232
+    if (o->ratio == ELLP_RATIO_HARRIS) LAUNCH(k_ratio_pick_harris, 1, 1024, lp, 1e-9, st);      // Harris two-pass test (opt-in)
+    else LAUNCH_SMEM(k_ratio_pick, 1, kScanThreads, kScanSmemBytes, lp, o->tie_rule, st);        // :379-434, :205-232
     if (blk > 0) {  // deferred row reduction: new (U, V) slot now, T -= U V every blk pivots
         LAUNCH(k_blk_row, (int)((std::max<int64_t>(lp.ld, lp.ldv) + 255) / 256), 256, lp, ctx->blk_fill, st);
         if (++ctx->blk_fill >= blk) launch_flush(ctx, profile, ev_used);
@@ -953,7 +954,8 @@ void launch_primal_iteration(ellp_b200_ctx* ctx, const ellp_opts* o, bool profil
     dim3 fg((unsigned)((lp.ld + 255) / 256), (unsigned)ctx->KS);
     LAUNCH(k_ftran_partial, fg, 128, lp.Binv, lp.ld, m, lp.A, st, lp.part, ctx->kc);
     LAUNCH(k_ratio_prep, (m + 255) / 256, 256, lp, ctx->KS, 0, st);
-    LAUNCH_SMEM(k_ratio_pick, 1, kScanThreads, kScanSmemBytes, lp, o->tie_rule, st);
+    if (o->ratio == ELLP_RATIO_HARRIS) LAUNCH(k_ratio_pick_harris, 1, 1024, lp, 1e-9, st);
+    else LAUNCH_SMEM(k_ratio_pick, 1, kScanThreads, kScanSmemBytes, lp, o->tie_rule, st);
     LAUNCH(k_step_gather, (m + 255) / 256, 256, lp, lp.Binv, m, st);
     if (profile && *ev_used + 2 <= ctx->ev.size()) cudaEventRecord(ctx->ev[(*ev_used)++], ctx->stream);
     launch_rank1(ctx, lp.Binv, lp.ld, m, m, lp.dcol, lp.prow, st, 0);
@@ -1862,6 +1864,11 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
     // blocked tableau engine: slots were allocated at upload time; the caller may lower block_k per run
     int blk = (ctx->tableau && ctx->blk_kmax > 0 && o->block_k > 1) ? std::min(o->block_k, ctx->blk_kmax) : 0;
     const bool dual_tab = ctx->tableau && ctx->solver == ELLP_DUAL;
+    // primal Harris ratio test (opt-in): implemented by the pick kernel of the kernel-per-phase paths (revised engine, rank-1 and
+    // blocked tableau engines); the fused cooperative kernel keeps the reference's fold
+    const bool primal_harris = ctx->solver == ELLP_PRIMAL && o->ratio == ELLP_RATIO_HARRIS;
+    if (primal_harris && o->pricing == ELLP_PRICE_DEVEX) return set_err(ctx, ELLP_E_ARG, "primal: ELLP_PRICE_DEVEX (fused kernel) and ELLP_RATIO_HARRIS (kernel-per-phase paths) cannot be combined yet");
+    if (primal_harris && (ctx->peer_mode || ctx->sharded)) return set_err(ctx, ELLP_E_ARG, "ELLP_RATIO_HARRIS for the primal is not available on the sharded engines");
     if (dual_tab) {  // the dual runs only on the blocked condensed tableau (single GPU or peer layout)
         if (blk == 0) blk = ctx->blk_kmax;
         if (blk <= 1 || !lp.condensed || (ctx->sharded && !ctx->peer_mode))
@@ -1927,7 +1934,7 @@ int ellp_b200_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_result* res) {
                 if (!rc_loop && ctx->blk_fill >= blk) launch_flush(ctx, profile, &ev_used);
             }
             batch = 0;
-        } else if (blk > 0 && !ctx->sharded && (ctx->coop_pivots || dual_tab) && lp.condensed) {
+        } else if (blk > 0 && !ctx->sharded && ((ctx->coop_pivots && !primal_harris) || dual_tab) && lp.condensed) {
             // cooperative path: whole blocks of pivots per launch, a flush after every full block
             int left = std::max(batch, blk);
             if (o->max_iter - h.pivots < (uint64_t)left) left = (int)std::max<uint64_t>(1, o->max_iter - h.pivots);

@@ -547,6 +547,7 @@ int device_phase(ellp_b200_ctx* ctx, int solver, HostStdForm& sf, HostPoint& pt,
 bool try_small_primal(ellp_b200_ctx* ctx, const Model& mdl, const ellp_opts* o, ellp_solution* sol, int64_t* toff, bool* infeasible_std) {
     *infeasible_std = false;
     if (o->engine != ELLP_ENGINE_AUTO) return false;
+    if (o->pricing != ELLP_PRICE_REFERENCE || o->ratio != ELLP_RATIO_REFERENCE) return false;  // K6 implements the reference's rules only
     HostStdForm sf;
     if (!standardize(mdl, sf)) { *infeasible_std = true; return true; }
     const int m = sf.m, n = sf.n;

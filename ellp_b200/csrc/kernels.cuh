@@ -684,6 +684,82 @@ __device__ __forceinline__ void ratio_commit(const DevLP& lp, PivotState* st, in
     }
 }
 
+// ELLP_RATIO_HARRIS on the primal side (no reference counterpart: ellp's ratio test is the textbook fold of :305-400): Harris'
+// two-pass test with bound flipping.  Pass 1: theta_max = min over the blocking rows of (distance to the bound + tol) / |d_i|, and the
+// entering variable's own range.  Pass 2: among the rows whose exact ratio is <= theta_max take the LARGEST |d_i| (ties: smallest
+// position) -- a pivot element that is not needlessly small; the step is max(ratio, 0).  If the entering variable's own range is not
+// larger than that step it flips bounds instead (no basis change).  Ends in the same ratio_commit as the reference rule.
+__global__ void __launch_bounds__(1024) k_ratio_pick_harris(DevLP lp, double tol, PivotState* st) {
+    if (st->status != kRunning) return;
+    __shared__ double s_v[32];
+    __shared__ int s_i[32];
+    __shared__ double s_theta;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned full = 0xffffffffu;
+    const int m = lp.m;
+    const int q_var = st->q_var;
+    const bool at_lower = (st->q_side == ELLP_NB_LOWER);
+    const int kq = lp.kind[q_var];
+    const double lambda0 = (kq == ELLP_TWOSIDED) ? (lp.ub[q_var] - lp.lb[q_var]) : (kq == ELLP_FIXED ? 0. : CUDART_INF);
+    // exact and relaxed ratio of row i (CUDART_INF when the row does not block)
+    auto ratios = [&](int i, double* exact, double* relaxed, double* mag) {
+        const double a = lp.dcol[i];
+        const double d_i = at_lower ? -a : a;
+        *exact = CUDART_INF; *relaxed = CUDART_INF; *mag = fabs(d_i);
+        if (fabs(d_i) < kEps) return;
+        const int var = lp.Bv[i];
+        const int kind = lp.kind[var];
+        const double x_i = lp.x[var];
+        double slack = CUDART_INF;
+        if (d_i < 0.) { if (kind == ELLP_LOWER || kind == ELLP_TWOSIDED || kind == ELLP_FIXED) slack = x_i - lp.lb[var]; }
+        else { if (kind == ELLP_UPPER || kind == ELLP_TWOSIDED) slack = lp.ub[var] - x_i; else if (kind == ELLP_FIXED) slack = lp.lb[var] - x_i; }
+        if (slack == CUDART_INF) return;
+        *exact = fmax(slack, 0.) / fabs(d_i);
+        *relaxed = (fmax(slack, 0.) + tol) / fabs(d_i);
+    };
+    double tmin = lambda0;
+    for (int i = tid; i < m; i += blockDim.x) {
+        double e, r, g;
+        ratios(i, &e, &r, &g);
+        tmin = fmin(tmin, r);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) tmin = fmin(tmin, __shfl_xor_sync(full, tmin, off));
+    if (lane == 0) s_v[warp] = tmin;
+    __syncthreads();
+    if (tid == 0) { double t = s_v[0]; for (int w = 1; w < (int)(blockDim.x >> 5); ++w) t = fmin(t, s_v[w]); s_theta = t; }
+    __syncthreads();
+    const double theta = s_theta;
+    double bg = -1.;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < m; i += blockDim.x) {
+        double e, r, g;
+        ratios(i, &e, &r, &g);
+        if (e <= theta && (g > bg)) { bg = g; bi = i; }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const double og = __shfl_xor_sync(full, bg, off);
+        const int oi = __shfl_xor_sync(full, bi, off);
+        if (og > bg || (og == bg && oi < bi)) { bg = og; bi = oi; }
+    }
+    __syncthreads();
+    if (lane == 0) { s_v[warp] = bg; s_i[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+        bg = -1.; bi = 0x7fffffff;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) if (s_v[w] > bg || (s_v[w] == bg && s_i[w] < bi)) { bg = s_v[w]; bi = s_i[w]; }
+        int nb = -1;
+        double lambda = lambda0;  // +inf when nothing blocks: ratio_commit reports Unbounded
+        if (bi != 0x7fffffff) {
+            double e, r, g;
+            ratios(bi, &e, &r, &g);
+            if (!(lambda0 <= e)) { nb = bi; lambda = e; }
+        }
+        ratio_commit(lp, st, nb, lambda, at_lower, q_var);
+    }
+}
+
 __global__ void __launch_bounds__(1024) k_ratio_pick(DevLP lp, int tie_rule, PivotState* st) {
     if (st->status != kRunning) return;
     extern __shared__ __align__(16) unsigned char scan_smem[];

@@ -115,7 +115,9 @@ typedef struct {
     int32_t  pricing;         /* ELLP_PRICE_*: REFERENCE = the reference's rules (primal: Dantzig with its tie fold, dual: first infeasible row);
                                  STEEPEST_EDGE = exact dual steepest edge (revised engine); DEVEX = Devex reference weights, primal entering
                                  column and dual leaving row, blocked tableau engines (block_k > 1) */
-    int32_t  ratio;           /* ELLP_RATIO_*: dual entering-column rule, revised engine */
+    int32_t  ratio;           /* ELLP_RATIO_*: HARRIS = Harris' two-pass ratio test with a 1e-9 tolerance: dual entering column (revised engine)
+                                 and -- with bound flipping -- primal leaving row (revised engine, rank-1 / blocked tableau engines on one GPU;
+                                 the blocked engine then runs kernel per phase instead of the fused cooperative kernel) */
     int32_t  block_k;         /* tableau engine: > 1 defers the row reduction and applies it as ONE rank-k update
                                  (T -= U V on the fp64 tensor pipe) every block_k pivots; 0/1 = rank-1 update per pivot.
                                  Read at upload / generate time (allocates 8*(m+n)*block_k bytes) and by ellp_b200_run

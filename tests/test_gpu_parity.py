@@ -1217,3 +1217,34 @@ def test_dual_solve_that_starts_optimal_needs_no_device_work(env):
     sg = [a.copy() for a in start]
     res, _ = S.GpuDualSimplexSolver.new(0, ctx=env["ctx"], engine=N.ENGINE_REVISED).solve_with_initial(2, 4, A, c, b, kind, lb, ub, *sg)
     assert res.status == N.MAXITER
+
+
+@pytest.mark.parametrize("engine,bk", [("revised", 0), ("tableau", 0), ("tableau", 16)])
+@pytest.mark.parametrize("name", P.NETLIB + ["small_prob_1", "small_prob_2", "small_prob_5", "beale_cycle", "small_prob_unbounded_1"])
+def test_primal_harris_ratio_test_reaches_the_same_verdict(env, name, engine, bk):
+    """ELLP_RATIO_HARRIS on the primal side (opt-in, no reference counterpart): same status as the oracle, same objective to 1e-9."""
+    prob, exp = P.netlib(name) if name in P.NETLIB else getattr(P, name)()
+    O, N = env["O"], env["N"]
+    res = _solver(env, "primal", engine=N.ENGINE_REVISED if engine == "revised" else N.ENGINE_TABLEAU, block_k=bk, ratio=N.RATIO_HARRIS,
+                  tie_rule=N.TIES_CANONICAL).solve(prob)
+    ref = O.solve(prob, O.PRIMAL, 1000, O.MODE_EXACT)
+    assert res.kind == ref.status_name
+    if res.is_optimal:
+        assert _rel(res.solution.obj(), ref.obj) < 1e-9
+        assert prob.is_feasible(list(res.solution.x() + 0.0)) or np.allclose(res.solution.x(), ref.x, atol=1e-7)
+
+
+def test_primal_harris_on_a_dense_lp_matches_highs(env):
+    import bench_lp
+    S, N = env["S"], env["N"]
+    m, ns = 512, 1024
+    fx = _highs_fixture()[f"{m}x{ns}_seed0_variant0"]
+    lp = bench_lp.dense_lp(m, ns, 0, 0)
+    for engine, bk in ((N.ENGINE_REVISED, 0), (N.ENGINE_TABLEAU, 32)):
+        st = [lp[k].copy() for k in ("x", "B", "N", "N_side")]
+        sol = S.GpuPrimalSimplexSolver.new(None, ctx=env["ctx"], engine=engine, block_k=bk, ratio=N.RATIO_HARRIS, tie_rule=N.TIES_CANONICAL)
+        res, _ = sol.solve_with_initial(m, m + ns, lp["A"], lp["c"], lp["b"], lp["kind"], lp["lb"], lp["ub"], *st)
+        assert res.status == N.OPTIMAL
+        obj = float(lp["c"] @ st[0])
+        assert _rel(obj, fx["obj"]) < 1e-9
+        assert np.abs(lp["A"] @ st[0] - lp["b"]).max() <= 1e-8 * np.abs(lp["b"]).max()
