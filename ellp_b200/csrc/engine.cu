@@ -1773,45 +1773,54 @@ int ellp_b200_primal_solve_batch(ellp_b200_ctx* ctx, const ellp_batch* bt, const
     CUDA_TRY(cudaStreamWaitEvent(cs, ctx->ev0, 0));  // the copies start after whatever was queued on the compute stream
     // three streams: H2D of chunk c + 1 (cs) and D2H of chunk c - 1 (ds) run under the kernel of chunk c (ks); the chunks use
     // disjoint regions of the device buffers, so the only dependencies are H2D(c) -> kernel(c) -> D2H(c)
-    auto h2d = [&](int c) -> int {
-        const size_t l0 = (size_t)c * per, cnt = std::min<size_t>(per, (size_t)bt->nlp - l0);
-        CUDA_TRY(cudaMemcpyAsync(B.A + l0 * m * n, bt->A + l0 * m * n, sizeof(double) * cnt * m * n, cudaMemcpyHostToDevice, cs));
-        CUDA_TRY(cudaMemcpyAsync(B.c + l0 * n, bt->c + l0 * n, sizeof(double) * cnt * n, cudaMemcpyHostToDevice, cs));
-        CUDA_TRY(cudaMemcpyAsync(B.b + l0 * m, bt->b + l0 * m, sizeof(double) * cnt * m, cudaMemcpyHostToDevice, cs));
-        CUDA_TRY(cudaMemcpyAsync(B.lb + l0 * n, bt->lb + l0 * n, sizeof(double) * cnt * n, cudaMemcpyHostToDevice, cs));
-        CUDA_TRY(cudaMemcpyAsync(B.ub + l0 * n, bt->ub + l0 * n, sizeof(double) * cnt * n, cudaMemcpyHostToDevice, cs));
-        CUDA_TRY(cudaMemcpyAsync(B.kind + l0 * n, bt->kind + l0 * n, cnt * n, cudaMemcpyHostToDevice, cs));
-        CUDA_TRY(cudaEventRecord(ctx->chunk_ev[2 * c], cs));
+    // the copies read / write the CALLER's buffers asynchronously: on any failure the three streams are drained before returning, so
+    // that no DMA is still in flight when the caller gets its buffers back
+    const int used = (bt->nlp + per - 1) / per;
+    auto pipeline = [&]() -> int {
+        auto h2d = [&](int c) -> int {
+            const size_t l0 = (size_t)c * per, cnt = std::min<size_t>(per, (size_t)bt->nlp - l0);
+            CUDA_TRY(cudaMemcpyAsync(B.A + l0 * m * n, bt->A + l0 * m * n, sizeof(double) * cnt * m * n, cudaMemcpyHostToDevice, cs));
+            CUDA_TRY(cudaMemcpyAsync(B.c + l0 * n, bt->c + l0 * n, sizeof(double) * cnt * n, cudaMemcpyHostToDevice, cs));
+            CUDA_TRY(cudaMemcpyAsync(B.b + l0 * m, bt->b + l0 * m, sizeof(double) * cnt * m, cudaMemcpyHostToDevice, cs));
+            CUDA_TRY(cudaMemcpyAsync(B.lb + l0 * n, bt->lb + l0 * n, sizeof(double) * cnt * n, cudaMemcpyHostToDevice, cs));
+            CUDA_TRY(cudaMemcpyAsync(B.ub + l0 * n, bt->ub + l0 * n, sizeof(double) * cnt * n, cudaMemcpyHostToDevice, cs));
+            CUDA_TRY(cudaMemcpyAsync(B.kind + l0 * n, bt->kind + l0 * n, cnt * n, cudaMemcpyHostToDevice, cs));
+            CUDA_TRY(cudaEventRecord(ctx->chunk_ev[2 * c], cs));
+            return ELLP_OK;
+        };
+        if (int rc = h2d(0)) return rc;
+        for (int c = 0; c < used; ++c) {
+            const size_t l0 = (size_t)c * per, cnt = std::min<size_t>(per, (size_t)bt->nlp - l0);
+            CUDA_TRY(cudaStreamWaitEvent(ks, ctx->chunk_ev[2 * c], 0));
+            BatchArgs a{};
+            a.nlp = (int)cnt; a.m = B.m; a.n0 = B.n0; a.nc = B.nc; a.ld = B.ld;
+            a.mode = 0;
+            a.tie_rule = o->tie_rule;
+            a.trace_cap = B.trace_cap;
+            a.max_iter = o->max_iter;
+            a.A = B.A + l0 * m * n; a.c = B.c + l0 * n; a.b = B.b + l0 * m; a.kind = B.kind + l0 * n; a.lb = B.lb + l0 * n; a.ub = B.ub + l0 * n;
+            a.x = B.x + l0 * nc; a.B = B.B + l0 * m; a.N = B.N + l0 * n; a.Ns = B.Ns + l0 * n;
+            a.status = B.status + l0; a.obj = B.obj + l0; a.iters = B.iters + 2 * l0; a.err = B.err + l0;
+            a.trace = B.trace ? B.trace + l0 * B.trace_cap : nullptr; a.trace_len = B.trace_len + l0;
+            const int grid = (int)std::min<size_t>(cnt, (size_t)sms * std::max(1, per_sm));
+            k_batch_primal<<<grid, kBatchThreads, smem, ks>>>(a);
+            ctx->launches++;
+            CUDA_TRY(cudaEventRecord(ctx->chunk_ev[2 * c + 1], ks));
+            if (c + 1 < used) { if (int rc = h2d(c + 1)) return rc; }
+            CUDA_TRY(cudaStreamWaitEvent(ds, ctx->chunk_ev[2 * c + 1], 0));
+            if (res->status) CUDA_TRY(cudaMemcpyAsync(res->status + l0, B.status + l0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, ds));
+            if (res->obj) CUDA_TRY(cudaMemcpyAsync(res->obj + l0, B.obj + l0, sizeof(double) * cnt, cudaMemcpyDeviceToHost, ds));
+            if (res->iters) CUDA_TRY(cudaMemcpyAsync(res->iters + 2 * l0, B.iters + 2 * l0, sizeof(int32_t) * 2 * cnt, cudaMemcpyDeviceToHost, ds));
+            if (res->err) CUDA_TRY(cudaMemcpyAsync(res->err + l0, B.err + l0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, ds));
+            if (res->x) CUDA_TRY(cudaMemcpyAsync(res->x + l0 * nc, B.x + l0 * nc, sizeof(double) * cnt * nc, cudaMemcpyDeviceToHost, ds));
+            if (res->trace_len) CUDA_TRY(cudaMemcpyAsync(res->trace_len + l0, B.trace_len + l0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, ds));
+            if (res->trace && B.trace) CUDA_TRY(cudaMemcpyAsync(res->trace + l0 * B.trace_cap, B.trace + l0 * B.trace_cap, sizeof(ellp_trace_rec) * cnt * B.trace_cap, cudaMemcpyDeviceToHost, ds));
+        }
         return ELLP_OK;
     };
-    const int used = (bt->nlp + per - 1) / per;
-    if (int rc = h2d(0)) return rc;
-    for (int c = 0; c < used; ++c) {
-        const size_t l0 = (size_t)c * per, cnt = std::min<size_t>(per, (size_t)bt->nlp - l0);
-        CUDA_TRY(cudaStreamWaitEvent(ks, ctx->chunk_ev[2 * c], 0));
-        BatchArgs a{};
-        a.nlp = (int)cnt; a.m = B.m; a.n0 = B.n0; a.nc = B.nc; a.ld = B.ld;
-        a.mode = 0;
-        a.tie_rule = o->tie_rule;
-        a.trace_cap = B.trace_cap;
-        a.max_iter = o->max_iter;
-        a.A = B.A + l0 * m * n; a.c = B.c + l0 * n; a.b = B.b + l0 * m; a.kind = B.kind + l0 * n; a.lb = B.lb + l0 * n; a.ub = B.ub + l0 * n;
-        a.x = B.x + l0 * nc; a.B = B.B + l0 * m; a.N = B.N + l0 * n; a.Ns = B.Ns + l0 * n;
-        a.status = B.status + l0; a.obj = B.obj + l0; a.iters = B.iters + 2 * l0; a.err = B.err + l0;
-        a.trace = B.trace ? B.trace + l0 * B.trace_cap : nullptr; a.trace_len = B.trace_len + l0;
-        const int grid = (int)std::min<size_t>(cnt, (size_t)sms * std::max(1, per_sm));
-        k_batch_primal<<<grid, kBatchThreads, smem, ks>>>(a);
-        ctx->launches++;
-        CUDA_TRY(cudaEventRecord(ctx->chunk_ev[2 * c + 1], ks));
-        if (c + 1 < used) { if (int rc = h2d(c + 1)) return rc; }
-        CUDA_TRY(cudaStreamWaitEvent(ds, ctx->chunk_ev[2 * c + 1], 0));
-        if (res->status) CUDA_TRY(cudaMemcpyAsync(res->status + l0, B.status + l0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, ds));
-        if (res->obj) CUDA_TRY(cudaMemcpyAsync(res->obj + l0, B.obj + l0, sizeof(double) * cnt, cudaMemcpyDeviceToHost, ds));
-        if (res->iters) CUDA_TRY(cudaMemcpyAsync(res->iters + 2 * l0, B.iters + 2 * l0, sizeof(int32_t) * 2 * cnt, cudaMemcpyDeviceToHost, ds));
-        if (res->err) CUDA_TRY(cudaMemcpyAsync(res->err + l0, B.err + l0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, ds));
-        if (res->x) CUDA_TRY(cudaMemcpyAsync(res->x + l0 * nc, B.x + l0 * nc, sizeof(double) * cnt * nc, cudaMemcpyDeviceToHost, ds));
-        if (res->trace_len) CUDA_TRY(cudaMemcpyAsync(res->trace_len + l0, B.trace_len + l0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, ds));
-        if (res->trace && B.trace) CUDA_TRY(cudaMemcpyAsync(res->trace + l0 * B.trace_cap, B.trace + l0 * B.trace_cap, sizeof(ellp_trace_rec) * cnt * B.trace_cap, cudaMemcpyDeviceToHost, ds));
+    if (int rc = pipeline()) {
+        cudaStreamSynchronize(ks); cudaStreamSynchronize(cs); cudaStreamSynchronize(ds);
+        return rc;
     }
     CUDA_TRY(cudaEventRecord(ctx->ev1, ks));
     CUDA_TRY(cudaStreamSynchronize(ks));
