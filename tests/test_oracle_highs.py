@@ -77,3 +77,21 @@ def test_oracle_agrees_with_highs_on_random_lps(seed):
             assert r.status_name == "Infeasible", (seed, which, r.status_name)
         elif hs.status == 3:
             assert r.status_name in ("Unbounded", "Infeasible"), (seed, which, r.status_name)  # HiGHS may call an infeasible LP unbounded (dual ray)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_oracle_agrees_with_highs_on_the_dense_generator_lp(variant):
+    """the bench generator's dense LP (numpy twin, 256 x 512) solved to optimality by the oracle's restatement of
+    solve_with_initial (slack start; primal for `A x <= b`, dual for `A x >= b`) against HiGHS (tests/golden/highs_dense_lp.json)."""
+    import json, os
+    import bench_lp
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "highs_dense_lp.json")))
+    m, ns = 256, 512
+    key = f"{m}x{ns}_seed0_variant{variant}"
+    lp = bench_lp.dense_lp(m, ns, 0, variant)
+    st = [lp[k].copy() for k in ("x", "B", "N", "N_side")] + ([lp["y"].copy(), lp["d"].copy()] if variant else [])
+    r = O.solve_with_initial(O.DUAL if variant else O.PRIMAL, m, m + ns, lp["A"], lp["c"], lp["b"], lp["kind"], lp["lb"], lp["ub"], *st, max_iter=100000)
+    assert r.status == O.OPTIMAL == fx[key]["status"]
+    obj = float(lp["c"] @ st[0])
+    assert abs(obj - fx[key]["obj"]) <= 1e-9 * max(1.0, abs(fx[key]["obj"]))
+    assert np.abs(lp["A"] @ st[0] - lp["b"]).max() <= 1e-9 * np.abs(lp["b"]).max()
