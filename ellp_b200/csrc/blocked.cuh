@@ -542,4 +542,127 @@ __global__ void __launch_bounds__(kFlush4Threads, 1) k_blk_flush4(double* __rest
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K3b, version 5: k_blk_flush4 with the warp's 32 x 32 register tile cut into NSPLIT parts by column tiles and software-pipelined
+// inside the warp.  ncu on version 4 (profiles/r02_ncu_full_blk_flush4_k56_summary.txt): 75.6 % DMMA active, and the largest stall
+// is long_scoreboard (5.3 warps per issue cycle): a warp issues its 16 tile loads and waits for ALL of them before its first DMMA,
+// so a scheduler regularly has fewer than the ~3 warps in their DMMA phase that the fp64 tensor pipe needs.  Here part p of step
+// s + 1 is requested right after part p of step s was stored, and the DMMAs of the OTHER parts of step s run while it travels:
+// no warp ever waits on HBM with nothing to issue.  Same registers (one 32 x 32 tile per warp), same ring, same per-element
+// accumulation order as versions 3 / 4 (the stored tableau is bit-identical to theirs).
+// ------------------------------------------------------------------------------------------------
+template <bool STREAM, int NSPLIT>
+__global__ void __launch_bounds__(kFlush4Threads, 1) k_blk_flush5(double* __restrict__ T, int64_t ld, int R, int C, const double* __restrict__ U,
+                                                                  const double* __restrict__ V, int64_t ldv, int cnt, int col_steps, int stages) {
+    constexpr int CTS = 4 / NSPLIT;  // column tiles (of 8 columns) per part
+    extern __shared__ __align__(16) double blk_smem[];
+    const int K4 = (cnt + 3) & ~3;
+    double* sU = blk_smem;                         // sU[j][row] = -U[row0 + row, j]
+    double* sVr = blk_smem + K4 * kFlushSU;        // ring: sV[stage][j][col] = V[j, col0 + col]
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(sVr + (size_t)stages * K4 * kFlush4SV);
+    unsigned long long* empty = full + 3;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * kFlushRows;
+    const int wr = (warp & 3) * 32, wc = ((warp >> 2) & 3) * 32;
+    const int fq = lane >> 2, fk = lane & 3;
+    const int ksteps = K4 >> 2;
+    const int64_t step0 = (int64_t)blockIdx.y * col_steps;
+    const int64_t steps_total = (C + kFlush4Cols - 1) / kFlush4Cols;
+    const int nsteps = (int)max((int64_t)0, min((int64_t)col_steps, steps_total - step0));
+    if (nsteps == 0) return;
+    const unsigned tile_bytes = (unsigned)cnt * kFlush4Cols * (unsigned)sizeof(double);
+    if (tid == 0) {
+        for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 16); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    double2 acc[NSPLIT][CTS][4];  // [part][column tile][row tile]
+    auto load_part = [&](double2 (&a)[CTS][4], int s, int part) {
+        const int64_t col0 = (step0 + s) * kFlush4Cols + wc + part * (CTS * 8);
+#pragma unroll
+        for (int ct = 0; ct < CTS; ++ct) {
+            const int64_t c = col0 + ct * 8 + fq;
+#pragma unroll
+            for (int rt = 0; rt < 4; ++rt) {
+                const int64_t r = row0 + wr + rt * 8 + 2 * fk;
+                if (c < C && r < R) {
+                    const double* p = T + c * ld + r;
+                    a[ct][rt] = STREAM ? ld_f64x2_stream(p) : ld_f64x2(p);
+                } else {
+                    a[ct][rt] = make_double2(0., 0.);
+                }
+            }
+        }
+    };
+    auto store_part = [&](const double2 (&a)[CTS][4], int s, int part) {
+        const int64_t col0 = (step0 + s) * kFlush4Cols + wc + part * (CTS * 8);
+#pragma unroll
+        for (int ct = 0; ct < CTS; ++ct) {
+            const int64_t c = col0 + ct * 8 + fq;
+#pragma unroll
+            for (int rt = 0; rt < 4; ++rt) {
+                const int64_t r = row0 + wr + rt * 8 + 2 * fk;
+                if (c < C && r < R) {
+                    double* p = T + c * ld + r;
+                    if (STREAM) st_f64x2_stream(p, a[ct][rt]);
+                    else st_f64x2(p, a[ct][rt]);
+                }
+            }
+        }
+    };
+    if (warp < 16) {  // the first tile travels while -U is staged
+#pragma unroll
+        for (int p = 0; p < NSPLIT; ++p) load_part(acc[p], 0, p);
+    }
+    for (int e = tid; e < K4 * kFlushRows; e += kFlush4Threads) {
+        const int j = e >> 7, i = e & (kFlushRows - 1);
+        sU[j * kFlushSU + i] = (j < cnt && row0 + i < R) ? -U[(int64_t)j * ld + row0 + i] : 0.;
+    }
+    for (int e = tid; e < stages * (K4 - cnt) * kFlush4SV; e += kFlush4Threads) {  // rows cnt .. K4-1 are never copied: zero them once
+        const int slot = e / ((K4 - cnt) * kFlush4SV), rem = e - slot * (K4 - cnt) * kFlush4SV;
+        sVr[(size_t)slot * K4 * kFlush4SV + (size_t)cnt * kFlush4SV + rem] = 0.;
+    }
+    __syncthreads();  // the only block-wide barrier
+    if (warp == 16) {  // producer: V tile of step t -> ring slot t % stages, one 1 KB row per lane and copy
+        for (int t = 0; t < nsteps; ++t) {
+            const int slot = t % stages, use = t / stages;
+            if (lane == 0) {
+                if (use > 0) mbar_wait(&empty[slot], (unsigned)((use - 1) & 1));
+                mbar_arrive_expect_tx(&full[slot], tile_bytes);
+            }
+            __syncwarp();
+            double* dst = sVr + (size_t)slot * K4 * kFlush4SV;
+            const double* src = V + (step0 + t) * kFlush4Cols;
+            for (int j = lane; j < cnt; j += 32) bulk_g2s(dst + j * kFlush4SV, src + (int64_t)j * ldv, kFlush4Cols * (unsigned)sizeof(double), &full[slot]);
+        }
+        return;
+    }
+    for (int s = 0; s < nsteps; ++s) {
+        const int slot = s % stages;
+        mbar_wait(&full[slot], (unsigned)((s / stages) & 1));
+        const double* sV = sVr + (size_t)slot * K4 * kFlush4SV;
+#pragma unroll
+        for (int p = 0; p < NSPLIT; ++p) {
+#pragma unroll 2
+            for (int ks = 0; ks < ksteps; ++ks) {
+                double a[CTS], b[4];
+                const int j = ks * 4 + fk;
+#pragma unroll
+                for (int ct = 0; ct < CTS; ++ct) a[ct] = sV[j * kFlush4SV + wc + (p * CTS + ct) * 8 + fq];
+#pragma unroll
+                for (int rt = 0; rt < 4; ++rt) b[rt] = sU[j * kFlushSU + wr + rt * 8 + fq];
+#pragma unroll
+                for (int ct = 0; ct < CTS; ++ct)
+#pragma unroll
+                    for (int rt = 0; rt < 4; ++rt) dmma_m8n8k4(acc[p][ct][rt].x, acc[p][ct][rt].y, a[ct], b[rt]);
+            }
+            if (p == NSPLIT - 1) {  // this warp no longer reads the slot
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[slot]);
+            }
+            store_part(acc[p], s, p);
+            if (s + 1 < nsteps) load_part(acc[p], s + 1, p);  // lands behind the DMMAs of the other parts
+        }
+    }
+}
+
 }  // namespace ellp

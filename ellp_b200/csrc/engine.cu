@@ -409,12 +409,13 @@ void launch_rankk(ellp_b200_ctx* ctx, double* E, int64_t ld, int R, int C, const
     // stages fit next to -U), the register-prefetching kernel below (HBM-bound) and at k > 56 (only two wide stages would fit)
     if (kern == 0) kern = (cnt >= ctx->flush4_min_k && cnt <= 56) ? 4 : 3;
     const bool base_ok = (ldv % 2 == 0) && ((reinterpret_cast<uintptr_t>(V) & 15) == 0);
-    if (kern == 4 && !(base_ok && (int64_t)((C + kFlush4Cols - 1) / kFlush4Cols) * kFlush4Cols <= ldv)) kern = 3;
+    const bool wide = kern == 4 || kern == 5 || kern == 6;  // 128-column steps, 16 consumer warps (5 / 6: tile pipelined in 2 / 4 parts)
+    if (wide && !(base_ok && (int64_t)((C + kFlush4Cols - 1) / kFlush4Cols) * kFlush4Cols <= ldv)) kern = 3;
     if (kern == 3 && !(base_ok && (int64_t)((C + kFlushCols - 1) / kFlushCols) * kFlushCols <= ldv)) kern = 1;
     if (kern == 2) kern = 1;
-    const int cols_per_step = kern == 4 ? kFlush4Cols : kFlushCols;
+    const int cols_per_step = kern >= 4 ? kFlush4Cols : kFlushCols;
     const int steps_total = (C + cols_per_step - 1) / cols_per_step;
-    const size_t smem = kern == 4 ? blk_flush4_smem_bytes(K4) : (kern == 3 ? blk_flush3_smem_bytes(K4) : blk_flush_smem_bytes(K4));
+    const size_t smem = kern >= 4 ? blk_flush4_smem_bytes(K4) : (kern == 3 ? blk_flush3_smem_bytes(K4) : blk_flush_smem_bytes(K4));
     int col_steps = std::max(1, std::min(kern == 1 ? ctx->flush_col_steps : ctx->flush2_col_steps, steps_total));
     if (kern != 1) {  // one CTA per SM: keep at least ~6 waves of CTAs so the last partial wave stays small (narrow shards)
         const int64_t row_blocks = (R + kFlushRows - 1) / kFlushRows;
@@ -422,7 +423,16 @@ void launch_rankk(ellp_b200_ctx* ctx, double* E, int64_t ld, int R, int C, const
     }
     dim3 grid((unsigned)((R + kFlushRows - 1) / kFlushRows), (unsigned)((steps_total + col_steps - 1) / col_steps));
     const bool stream = (double)R * C * 8.0 > (double)ctx->rank1_stream_min_mb * 1048576.0;
-    if (kern == 4) {
+    if (kern == 5 || kern == 6) {
+        const int stages = blk_flush4_stages(K4);
+        if (kern == 5) {
+            if (stream) LAUNCH_SMEM((k_blk_flush5<true, 2>), grid, kFlush4Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps, stages);
+            else LAUNCH_SMEM((k_blk_flush5<false, 2>), grid, kFlush4Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps, stages);
+        } else {
+            if (stream) LAUNCH_SMEM((k_blk_flush5<true, 4>), grid, kFlush4Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps, stages);
+            else LAUNCH_SMEM((k_blk_flush5<false, 4>), grid, kFlush4Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps, stages);
+        }
+    } else if (kern == 4) {
         const int stages = blk_flush4_stages(K4);
         if (stream) LAUNCH_SMEM(k_blk_flush4<true>, grid, kFlush4Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps, stages);
         else LAUNCH_SMEM(k_blk_flush4<false>, grid, kFlush4Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps, stages);
@@ -445,6 +455,10 @@ int flush_attrs(ellp_b200_ctx* ctx) {
     const int smem4 = (int)std::max(blk_flush4_smem_bytes(kBlkMax), blk_flush4_smem_bytes(40));
     CUDA_TRY(cudaFuncSetAttribute(k_blk_flush4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
     CUDA_TRY(cudaFuncSetAttribute(k_blk_flush4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
+    CUDA_TRY(cudaFuncSetAttribute((k_blk_flush5<true, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
+    CUDA_TRY(cudaFuncSetAttribute((k_blk_flush5<false, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
+    CUDA_TRY(cudaFuncSetAttribute((k_blk_flush5<true, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
+    CUDA_TRY(cudaFuncSetAttribute((k_blk_flush5<false, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
     ctx->flush_attrs_set = true;
     return ELLP_OK;
 }

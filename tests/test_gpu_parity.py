@@ -575,6 +575,32 @@ def test_rankk_update_matches_numpy_and_sequential_rank1(env, R, C_, k):
     assert (np.abs(got - want) <= 4 * np.finfo(float).eps * scale * max(1, k)).all()
 
 
+@pytest.mark.parametrize("R,C_,k", [(128, 128, 4), (130, 259, 17), (513, 1000, 40), (1024, 2048, 56), (640, 4100, 64), (2050, 333, 48)])
+def test_rankk_update_kernel_variants_are_bit_identical(env, R, C_, k):
+    """Every version of the rank-k row reduction (tuning key "flush_kernel": 1 = two CTAs per SM, 3 = register prefetch + bulk-copy
+    ring, 4 = 16 consumer warps, 5 / 6 = 16 warps with the warp tile pipelined in 2 / 4 parts) accumulates the k products of an
+    element in the same order on the same DMMA shape, so the stored tableaus are equal bit for bit -- switching the kernel can
+    never change a pivot decision."""
+    N, ctx = env["N"], env["ctx"]
+    rng = np.random.default_rng(R * 31 + C_ * 7 + k)
+    E = np.asfortranarray(rng.standard_normal((R, C_)))
+    U = np.asfortranarray(rng.standard_normal((R, k)))
+    V = np.ascontiguousarray(rng.standard_normal((k, C_)))
+    out = {}
+    try:
+        for kern in (1, 3, 4, 5, 6):
+            ctx.set_tuning("flush_kernel", kern)
+            got = E.copy(order="F")
+            ctx.check(N.lib.ellp_b200_rankk_update(ctx.h, N.ptr(got), R, C_, R, N.ptr(U), N.ptr(V), k))
+            out[kern] = got
+    finally:
+        ctx.set_tuning("flush_kernel", 0)
+    scale = np.abs(E) + np.abs(U) @ np.abs(V)
+    assert (np.abs(out[4] - (E - U @ V)) <= 4 * np.finfo(float).eps * scale * k).all()
+    for kern in (1, 3, 5, 6):
+        np.testing.assert_array_equal(out[kern], out[4], err_msg=f"flush_kernel {kern} vs 4")
+
+
 @pytest.mark.parametrize("seed,m,n,tie,bk", [(0, 24, 40, 0, 2), (1, 64, 128, 0, 7), (2, 64, 128, 1, 32), (3, 132, 190, 0, 64), (5, 260, 515, 0, 32)])
 def test_blocked_tableau_engine_matches_oracle_trace(env, seed, m, n, tie, bk):
     """ellp_opts::block_k > 1: identical pivot sequence, basis and point as the oracle (and hence as the rank-1 engine)."""
