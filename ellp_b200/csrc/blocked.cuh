@@ -443,9 +443,23 @@ constexpr int kFlush4Cols = 128;
 constexpr int kFlush4SV = kFlush4Cols + 4;
 constexpr int kFlush4Threads = 544;  // 16 consumer warps + 1 producer warp
 inline int blk_flush4_stages(int K4) { return K4 <= 40 ? 3 : 2; }
+inline size_t blk_flush4_smem_bytes_st(int K4, int stages) { return sizeof(double) * (size_t)K4 * (kFlushSU + stages * kFlush4SV) + 16 * 3; }
 inline size_t blk_flush4_smem_bytes(int K4) { return sizeof(double) * (size_t)K4 * (kFlushSU + blk_flush4_stages(K4) * kFlush4SV) + 16 * 3; }
 
-template <bool STREAM>
+// tile access modes of versions 4 / 5 (template parameter STREAM): 0 = default caching, 1 = evict-first loads and stores (.cs),
+// 2 = loads that bypass L1 (.cg) + evict-first stores, 3 = .cg loads + .cg stores
+template <int MODE> __device__ __forceinline__ double2 ld_tile(const double* p) {
+    if (MODE == 1) return __ldcs(reinterpret_cast<const double2*>(p));
+    if (MODE >= 2) return __ldcg(reinterpret_cast<const double2*>(p));
+    return *reinterpret_cast<const double2*>(p);
+}
+template <int MODE> __device__ __forceinline__ void st_tile(double* p, double2 v) {
+    if (MODE == 1 || MODE == 2) __stcs(reinterpret_cast<double2*>(p), v);
+    else if (MODE == 3) __stcg(reinterpret_cast<double2*>(p), v);
+    else *reinterpret_cast<double2*>(p) = v;
+}
+
+template <int STREAM>
 __global__ void __launch_bounds__(kFlush4Threads, 1) k_blk_flush4(double* __restrict__ T, int64_t ld, int R, int C, const double* __restrict__ U,
                                                                   const double* __restrict__ V, int64_t ldv, int cnt, int col_steps, int stages) {
     extern __shared__ __align__(16) double blk_smem[];
@@ -502,7 +516,7 @@ __global__ void __launch_bounds__(kFlush4Threads, 1) k_blk_flush4(double* __rest
                 const int64_t r = row0 + wr + rt * 8 + 2 * fk;
                 if (c < C && r < R) {
                     const double* p = T + c * ld + r;
-                    acc[ct][rt] = STREAM ? ld_f64x2_stream(p) : ld_f64x2(p);
+                    acc[ct][rt] = ld_tile<STREAM>(p);
                 } else {
                     acc[ct][rt] = make_double2(0., 0.);
                 }
@@ -534,8 +548,7 @@ __global__ void __launch_bounds__(kFlush4Threads, 1) k_blk_flush4(double* __rest
                 const int64_t r = row0 + wr + rt * 8 + 2 * fk;
                 if (c < C && r < R) {
                     double* p = T + c * ld + r;
-                    if (STREAM) st_f64x2_stream(p, acc[ct][rt]);
-                    else st_f64x2(p, acc[ct][rt]);
+                    st_tile<STREAM>(p, acc[ct][rt]);
                 }
             }
         }
@@ -551,7 +564,7 @@ __global__ void __launch_bounds__(kFlush4Threads, 1) k_blk_flush4(double* __rest
 // no warp ever waits on HBM with nothing to issue.  Same registers (one 32 x 32 tile per warp), same ring, same per-element
 // accumulation order as versions 3 / 4 (the stored tableau is bit-identical to theirs).
 // ------------------------------------------------------------------------------------------------
-template <bool STREAM, int NSPLIT>
+template <int STREAM, int NSPLIT>
 __global__ void __launch_bounds__(kFlush4Threads, 1) k_blk_flush5(double* __restrict__ T, int64_t ld, int R, int C, const double* __restrict__ U,
                                                                   const double* __restrict__ V, int64_t ldv, int cnt, int col_steps, int stages) {
     constexpr int CTS = 4 / NSPLIT;  // column tiles (of 8 columns) per part
@@ -586,7 +599,7 @@ __global__ void __launch_bounds__(kFlush4Threads, 1) k_blk_flush5(double* __rest
                 const int64_t r = row0 + wr + rt * 8 + 2 * fk;
                 if (c < C && r < R) {
                     const double* p = T + c * ld + r;
-                    a[ct][rt] = STREAM ? ld_f64x2_stream(p) : ld_f64x2(p);
+                    a[ct][rt] = ld_tile<STREAM>(p);
                 } else {
                     a[ct][rt] = make_double2(0., 0.);
                 }
@@ -603,8 +616,7 @@ __global__ void __launch_bounds__(kFlush4Threads, 1) k_blk_flush5(double* __rest
                 const int64_t r = row0 + wr + rt * 8 + 2 * fk;
                 if (c < C && r < R) {
                     double* p = T + c * ld + r;
-                    if (STREAM) st_f64x2_stream(p, a[ct][rt]);
-                    else st_f64x2(p, a[ct][rt]);
+                    st_tile<STREAM>(p, a[ct][rt]);
                 }
             }
         }
@@ -663,6 +675,162 @@ __global__ void __launch_bounds__(kFlush4Threads, 1) k_blk_flush5(double* __rest
             if (s + 1 < nsteps) load_part(acc[p], s + 1, p);  // lands behind the DMMAs of the other parts
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3b, version 6: the 16-consumer-warp kernel WITHOUT a producer warp.  512 threads instead of 544 lift the register cap from 96 to
+// 128 per thread: versions 4 / 5 spill (56 - 80 bytes), and their spill reloads (LDL) sit on the same scoreboards as the
+// outstanding tile loads -- ncu's source page of version 4 shows 28 % of all stall samples as long_scoreboard on integer
+// instructions that only consume a reloaded spill (profiles/r02_ncu_full_blk_flush4_k56_summary.txt), i.e. a warp waits for its
+// whole T tile before it even polls the ring, and in version 5 the reloads inside the pipelined loop cancel the overlap.
+// The ring is refilled by whichever consumer warp is the LAST to finish the DMMAs of a step (a shared-memory arrival counter per
+// slot replaces the `empty` mbarriers): that warp re-arms full[slot] and issues the bulk copies of step s + stages.
+// NSPLIT = 1: one 32 x 32 register tile per warp, loaded as a whole (version 4's schedule); NSPLIT = 2: tile pipelined in two
+// halves (version 5's schedule).  Interior tiles take a path without bounds predicates.
+// Same DMMA shape and per-element accumulation order as every other version (bit-identical tableau).
+// ------------------------------------------------------------------------------------------------
+constexpr int kFlush6Threads = 512;
+inline size_t blk_flush6_smem_bytes(int K4, int stages) { return sizeof(double) * (size_t)K4 * (kFlushSU + stages * kFlush4SV) + 48; }
+
+template <int STREAM, int NSPLIT, bool FULL>
+__device__ __forceinline__ void flush6_body(double* __restrict__ T, int64_t ld, int R, int C, const double* __restrict__ V, int64_t ldv, int cnt,
+                                            int K4, int stages, int nsteps, int64_t step0, int64_t row0, const double* sU, double* sVr,
+                                            unsigned long long* full, unsigned* arrived) {
+    constexpr int CTS = 4 / NSPLIT;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wr = (warp & 3) * 32, wc = (warp >> 2) * 32;
+    const int fq = lane >> 2, fk = lane & 3;
+    const int ksteps = K4 >> 2;
+    const unsigned tile_bytes = (unsigned)cnt * kFlush4Cols * (unsigned)sizeof(double);
+    const int64_t r_lane = row0 + wr + 2 * fk;                    // first row of this lane's accumulator pairs
+    double* tp = T + (step0 * kFlush4Cols + wc + fq) * ld + r_lane;  // element (row r_lane, column col0 + wc + fq) of step 0
+    const int64_t cstride = 8 * ld, sstride = (int64_t)kFlush4Cols * ld;
+    double2 acc[NSPLIT][CTS][4];  // [part][column tile][row tile]
+    auto load_part = [&](double2 (&a)[CTS][4], int s, int part) {
+        const double* base = tp + (int64_t)s * sstride + (int64_t)(part * CTS) * cstride;
+#pragma unroll
+        for (int ct = 0; ct < CTS; ++ct) {
+#pragma unroll
+            for (int rt = 0; rt < 4; ++rt) {
+                if (FULL) {
+                    a[ct][rt] = ld_tile<STREAM>(base + ct * cstride + rt * 8);
+                } else {
+                    const int64_t c = (step0 + s) * kFlush4Cols + wc + (part * CTS + ct) * 8 + fq, r = r_lane + rt * 8;
+                    a[ct][rt] = (c < C && r < R) ? ld_tile<STREAM>(base + ct * cstride + rt * 8) : make_double2(0., 0.);
+                }
+            }
+        }
+    };
+    auto store_part = [&](const double2 (&a)[CTS][4], int s, int part) {
+        double* base = tp + (int64_t)s * sstride + (int64_t)(part * CTS) * cstride;
+#pragma unroll
+        for (int ct = 0; ct < CTS; ++ct) {
+#pragma unroll
+            for (int rt = 0; rt < 4; ++rt) {
+                if (FULL) {
+                    st_tile<STREAM>(base + ct * cstride + rt * 8, a[ct][rt]);
+                } else {
+                    const int64_t c = (step0 + s) * kFlush4Cols + wc + (part * CTS + ct) * 8 + fq, r = r_lane + rt * 8;
+                    if (c < C && r < R) st_tile<STREAM>(base + ct * cstride + rt * 8, a[ct][rt]);
+                }
+            }
+        }
+    };
+#pragma unroll
+    for (int p = 0; p < NSPLIT; ++p) load_part(acc[p], 0, p);
+    for (int s = 0; s < nsteps; ++s) {
+        const int slot = s % stages;
+        mbar_wait(&full[slot], (unsigned)((s / stages) & 1));
+        const double* sV = sVr + (size_t)slot * K4 * kFlush4SV;
+#pragma unroll
+        for (int p = 0; p < NSPLIT; ++p) {
+#pragma unroll 2
+            for (int ks = 0; ks < ksteps; ++ks) {
+                double a[CTS], b[4];
+                const int j = ks * 4 + fk;
+#pragma unroll
+                for (int ct = 0; ct < CTS; ++ct) a[ct] = sV[j * kFlush4SV + wc + (p * CTS + ct) * 8 + fq];
+#pragma unroll
+                for (int rt = 0; rt < 4; ++rt) b[rt] = sU[j * kFlushSU + wr + rt * 8 + fq];
+#pragma unroll
+                for (int ct = 0; ct < CTS; ++ct)
+#pragma unroll
+                    for (int rt = 0; rt < 4; ++rt) dmma_m8n8k4(acc[p][ct][rt].x, acc[p][ct][rt].y, a[ct], b[rt]);
+            }
+            if (p == NSPLIT - 1) {
+                // this warp no longer reads the slot; the last of the 16 warps to get here refills it with the tile of step s + stages
+                __syncwarp();
+                unsigned last = 0;
+                if (lane == 0) {
+                    __threadfence_block();
+                    last = (atomicAdd(&arrived[slot], 1u) == 15u) ? 1u : 0u;
+                }
+                last = __shfl_sync(0xffffffffu, last, 0);
+                const int t = s + stages;
+                if (last && t < nsteps) {
+                    // every lane issues its rows: a single-thread loop was measured 4 % slower (the refill sits on the critical path: with
+                    // two stages the tile of step s + 2 is requested when the slowest warp leaves step s)
+                    if (lane == 0) {
+                        arrived[slot] = 0u;  // nobody arrives on this slot again before the copies below have completed full[slot]
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        mbar_arrive_expect_tx(&full[slot], tile_bytes);
+                    }
+                    __syncwarp();
+                    double* dst = sVr + (size_t)slot * K4 * kFlush4SV;
+                    const double* src = V + (step0 + t) * kFlush4Cols;
+                    for (int j = lane; j < cnt; j += 32) bulk_g2s(dst + j * kFlush4SV, src + (int64_t)j * ldv, kFlush4Cols * (unsigned)sizeof(double), &full[slot]);
+                }
+            }
+            store_part(acc[p], s, p);
+            if (s + 1 < nsteps) load_part(acc[p], s + 1, p);
+        }
+    }
+}
+
+template <int STREAM, int NSPLIT>
+__global__ void __launch_bounds__(kFlush6Threads, 1) k_blk_flush6(double* __restrict__ T, int64_t ld, int R, int C, const double* __restrict__ U,
+                                                                  const double* __restrict__ V, int64_t ldv, int cnt, int col_steps, int stages) {
+    extern __shared__ __align__(16) double blk_smem[];
+    const int K4 = (cnt + 3) & ~3;
+    double* sU = blk_smem;                         // sU[j][row] = -U[row0 + row, j]
+    double* sVr = blk_smem + K4 * kFlushSU;        // ring: sV[stage][j][col] = V[j, col0 + col]
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(sVr + (size_t)stages * K4 * kFlush4SV);
+    unsigned* arrived = reinterpret_cast<unsigned*>(full + 3);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * kFlushRows;
+    const int64_t step0 = (int64_t)blockIdx.y * col_steps;
+    const int64_t steps_total = (C + kFlush4Cols - 1) / kFlush4Cols;
+    const int nsteps = (int)max((int64_t)0, min((int64_t)col_steps, steps_total - step0));
+    if (nsteps == 0) return;
+    if (tid == 0) {
+        for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); arrived[i] = 0u; }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int e = tid; e < K4 * kFlushRows; e += kFlush6Threads) {
+        const int j = e >> 7, i = e & (kFlushRows - 1);
+        sU[j * kFlushSU + i] = (j < cnt && row0 + i < R) ? -U[(int64_t)j * ld + row0 + i] : 0.;
+    }
+    for (int e = tid; e < stages * (K4 - cnt) * kFlush4SV; e += kFlush6Threads) {  // rows cnt .. K4-1 are never copied: zero them once
+        const int slot = e / ((K4 - cnt) * kFlush4SV), rem = e - slot * (K4 - cnt) * kFlush4SV;
+        sVr[(size_t)slot * K4 * kFlush4SV + (size_t)cnt * kFlush4SV + rem] = 0.;
+    }
+    __syncthreads();  // the only block-wide barrier
+    if (warp == 0) {  // initial fill of the ring
+        const unsigned tile_bytes = (unsigned)cnt * kFlush4Cols * (unsigned)sizeof(double);
+        for (int t = 0; t < stages && t < nsteps; ++t) {
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive_expect_tx(&full[t], tile_bytes);
+            }
+            __syncwarp();
+            double* dst = sVr + (size_t)t * K4 * kFlush4SV;
+            const double* src = V + (step0 + t) * kFlush4Cols;
+            for (int j = lane; j < cnt; j += 32) bulk_g2s(dst + j * kFlush4SV, src + (int64_t)j * ldv, kFlush4Cols * (unsigned)sizeof(double), &full[t]);
+        }
+    }
+    const bool interior = row0 + kFlushRows <= R && (step0 + nsteps) * kFlush4Cols <= C;
+    if (interior) flush6_body<STREAM, NSPLIT, true>(T, ld, R, C, V, ldv, cnt, K4, stages, nsteps, step0, row0, sU, sVr, full, arrived);
+    else flush6_body<STREAM, NSPLIT, false>(T, ld, R, C, V, ldv, cnt, K4, stages, nsteps, step0, row0, sU, sVr, full, arrived);
 }
 
 }  // namespace ellp

@@ -114,6 +114,8 @@ struct ellp_b200_ctx {
     int flush_kernel = 0;         // tuning: 0 = auto (4 for k >= flush4_min_k, else 3), 1 = k_blk_flush (2 CTAs/SM, also the fallback for an unpadded V),
                                   // 3 = k_blk_flush3 (register prefetch + bulk-copy ring), 4 = k_blk_flush4 (16 consumer warps, tensor-bound regime)
     int flush4_min_k = 40;
+    int flush_ld = -1;            // tuning key "flush_ld": tile access mode of versions 4 / 5 (-1 = auto, see ld_tile in blocked.cuh)
+    int flush_stages = 0;         // tuning key "flush_stages": ring depth of versions 4 / 5 (0 = blk_flush4_stages)
     bool flush_attrs_set = false;
     int flush2_col_steps = 32;    // column steps per CTA of k_blk_flush3 / k_blk_flush4
     int flush_waves = 6;          // tuning key "flush_waves": keep at least this many waves of CTAs (narrow shards); 0 = take flush2_col_steps as given.
@@ -401,7 +403,8 @@ int gemv_grid(int ncols) { return std::max(1, std::min((ncols + 7) / 8, 148 * 32
 
 // One launch of the rank-k row reduction E -= U V (K3b).  Kernel choice (tuning key "flush_kernel"): 3 = bulk-copy /
 // mbarrier ring, one CTA per SM (needs V rows padded to whole tiles, 16-byte aligned); 4 = the same ring with 16 consumer warps;
-// 1 = two CTAs per SM without register prefetch (any V).
+// 1 = two CTAs per SM without register prefetch (any V); 5 / 6 = version 4 with the warp tile pipelined in 2 / 4 parts; 7 / 8 = the
+// producer-less 512-thread kernel (k_blk_flush6) with the schedule of version 4 / 5.
 void launch_rankk(ellp_b200_ctx* ctx, double* E, int64_t ld, int R, int C, const double* U, const double* V, int64_t ldv, int cnt) {
     const int K4 = (cnt + 3) & ~3;
     int kern = ctx->flush_kernel;
@@ -409,7 +412,7 @@ void launch_rankk(ellp_b200_ctx* ctx, double* E, int64_t ld, int R, int C, const
     // stages fit next to -U), the register-prefetching kernel below (HBM-bound) and at k > 56 (only two wide stages would fit)
     if (kern == 0) kern = (cnt >= ctx->flush4_min_k && cnt <= 56) ? 4 : 3;
     const bool base_ok = (ldv % 2 == 0) && ((reinterpret_cast<uintptr_t>(V) & 15) == 0);
-    const bool wide = kern == 4 || kern == 5 || kern == 6;  // 128-column steps, 16 consumer warps (5 / 6: tile pipelined in 2 / 4 parts)
+    const bool wide = kern >= 4;  // 128-column steps, 16 consumer warps (5 / 6: tile pipelined in 2 / 4 parts; 7 / 8: no producer warp, 128 registers)
     if (wide && !(base_ok && (int64_t)((C + kFlush4Cols - 1) / kFlush4Cols) * kFlush4Cols <= ldv)) kern = 3;
     if (kern == 3 && !(base_ok && (int64_t)((C + kFlushCols - 1) / kFlushCols) * kFlushCols <= ldv)) kern = 1;
     if (kern == 2) kern = 1;
@@ -423,19 +426,42 @@ void launch_rankk(ellp_b200_ctx* ctx, double* E, int64_t ld, int R, int C, const
     }
     dim3 grid((unsigned)((R + kFlushRows - 1) / kFlushRows), (unsigned)((steps_total + col_steps - 1) / col_steps));
     const bool stream = (double)R * C * 8.0 > (double)ctx->rank1_stream_min_mb * 1048576.0;
-    if (kern == 5 || kern == 6) {
-        const int stages = blk_flush4_stages(K4);
-        if (kern == 5) {
-            if (stream) LAUNCH_SMEM((k_blk_flush5<true, 2>), grid, kFlush4Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps, stages);
-            else LAUNCH_SMEM((k_blk_flush5<false, 2>), grid, kFlush4Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps, stages);
-        } else {
-            if (stream) LAUNCH_SMEM((k_blk_flush5<true, 4>), grid, kFlush4Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps, stages);
-            else LAUNCH_SMEM((k_blk_flush5<false, 4>), grid, kFlush4Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps, stages);
+    // auto, second part (profiles/r02_flush5_sweep.jsonl): the producer-less kernel with the tile pipelined in two halves wins where a CTA
+    // is short (narrow shards: <= 16 column steps per CTA, 27.9 vs 24.4 TFLOP/s at 32768 x 4096) and near the HBM / tensor crossover
+    // (k < 48: 24.9 vs 22.5 at k = 40); on the full 32768 x 32768 tableau at k = 48 .. 56 version 4 stays ahead (27.5 vs 26.6)
+    if (ctx->flush_kernel == 0 && kern == 4 && (col_steps <= 16 || cnt < 48)) kern = 8;
+    if (kern >= 4) {
+        // tile access mode (tuning key "flush_ld"): -1 = auto (evict-first when the matrix exceeds L2, default caching otherwise)
+        const int mode = ctx->flush_ld >= 0 ? ctx->flush_ld : (stream ? 1 : 0);
+        int stages = blk_flush4_stages(K4);
+        if (ctx->flush_stages > 0 && blk_flush4_smem_bytes_st(K4, ctx->flush_stages) <= (size_t)227 * 1024) stages = std::min(3, ctx->flush_stages);
+        const size_t smem_w = blk_flush4_smem_bytes_st(K4, stages);
+#define ELLP_FLUSH_WIDE(KERNEL)                                                                                              \
+        switch (mode) {                                                                                                      \
+            case 0: LAUNCH_SMEM((KERNEL(0)), grid, kFlush4Threads, smem_w, E, ld, R, C, U, V, ldv, cnt, col_steps, stages); break; \
+            case 2: LAUNCH_SMEM((KERNEL(2)), grid, kFlush4Threads, smem_w, E, ld, R, C, U, V, ldv, cnt, col_steps, stages); break; \
+            case 3: LAUNCH_SMEM((KERNEL(3)), grid, kFlush4Threads, smem_w, E, ld, R, C, U, V, ldv, cnt, col_steps, stages); break; \
+            default: LAUNCH_SMEM((KERNEL(1)), grid, kFlush4Threads, smem_w, E, ld, R, C, U, V, ldv, cnt, col_steps, stages); break; \
         }
-    } else if (kern == 4) {
-        const int stages = blk_flush4_stages(K4);
-        if (stream) LAUNCH_SMEM(k_blk_flush4<true>, grid, kFlush4Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps, stages);
-        else LAUNCH_SMEM(k_blk_flush4<false>, grid, kFlush4Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps, stages);
+#define ELLP_K4(M) k_blk_flush4<M>
+#define ELLP_K5(M) k_blk_flush5<M, 2>
+#define ELLP_K6(M) k_blk_flush5<M, 4>
+        if (kern == 7 || kern == 8) {
+            const int md = mode ? 1 : 0;
+            if (kern == 7) {
+                if (md) LAUNCH_SMEM((k_blk_flush6<1, 1>), grid, kFlush6Threads, smem_w, E, ld, R, C, U, V, ldv, cnt, col_steps, stages);
+                else LAUNCH_SMEM((k_blk_flush6<0, 1>), grid, kFlush6Threads, smem_w, E, ld, R, C, U, V, ldv, cnt, col_steps, stages);
+            } else {
+                if (md) LAUNCH_SMEM((k_blk_flush6<1, 2>), grid, kFlush6Threads, smem_w, E, ld, R, C, U, V, ldv, cnt, col_steps, stages);
+                else LAUNCH_SMEM((k_blk_flush6<0, 2>), grid, kFlush6Threads, smem_w, E, ld, R, C, U, V, ldv, cnt, col_steps, stages);
+            }
+        } else if (kern == 4) { ELLP_FLUSH_WIDE(ELLP_K4) }
+        else if (kern == 5) { ELLP_FLUSH_WIDE(ELLP_K5) }
+        else { ELLP_FLUSH_WIDE(ELLP_K6) }
+#undef ELLP_K4
+#undef ELLP_K5
+#undef ELLP_K6
+#undef ELLP_FLUSH_WIDE
     } else if (kern == 3) {
         if (stream) LAUNCH_SMEM(k_blk_flush3<true>, grid, kFlush3Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
         else LAUNCH_SMEM(k_blk_flush3<false>, grid, kFlush3Threads, smem, E, ld, R, C, U, V, ldv, cnt, col_steps);
@@ -452,13 +478,13 @@ int flush_attrs(ellp_b200_ctx* ctx) {
     CUDA_TRY(cudaFuncSetAttribute(k_blk_flush<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     CUDA_TRY(cudaFuncSetAttribute(k_blk_flush3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush3_smem_bytes(kBlkMax)));
     CUDA_TRY(cudaFuncSetAttribute(k_blk_flush3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk_flush3_smem_bytes(kBlkMax)));
-    const int smem4 = (int)std::max(blk_flush4_smem_bytes(kBlkMax), blk_flush4_smem_bytes(40));
-    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
-    CUDA_TRY(cudaFuncSetAttribute(k_blk_flush4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
-    CUDA_TRY(cudaFuncSetAttribute((k_blk_flush5<true, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
-    CUDA_TRY(cudaFuncSetAttribute((k_blk_flush5<false, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
-    CUDA_TRY(cudaFuncSetAttribute((k_blk_flush5<true, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
-    CUDA_TRY(cudaFuncSetAttribute((k_blk_flush5<false, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
+    const int smem4 = 227 * 1024;  // versions 4 / 5: the ring depth is a tuning parameter, allow the whole carve-out
+#define ELLP_ATTR(K) CUDA_TRY(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4))
+    ELLP_ATTR(k_blk_flush4<0>); ELLP_ATTR(k_blk_flush4<1>); ELLP_ATTR(k_blk_flush4<2>); ELLP_ATTR(k_blk_flush4<3>);
+    ELLP_ATTR((k_blk_flush5<0, 2>)); ELLP_ATTR((k_blk_flush5<1, 2>)); ELLP_ATTR((k_blk_flush5<2, 2>)); ELLP_ATTR((k_blk_flush5<3, 2>));
+    ELLP_ATTR((k_blk_flush5<0, 4>)); ELLP_ATTR((k_blk_flush5<1, 4>)); ELLP_ATTR((k_blk_flush5<2, 4>)); ELLP_ATTR((k_blk_flush5<3, 4>));
+    ELLP_ATTR((k_blk_flush6<0, 1>)); ELLP_ATTR((k_blk_flush6<1, 1>)); ELLP_ATTR((k_blk_flush6<0, 2>)); ELLP_ATTR((k_blk_flush6<1, 2>));
+#undef ELLP_ATTR
     ctx->flush_attrs_set = true;
     return ELLP_OK;
 }
@@ -1115,6 +1141,7 @@ int ellp_b200_create(int device, ellp_b200_ctx** out) {
         delete ctx;
         return ELLP_E_CUDA;
     }
+    cudaDeviceSynchronize();  // the memset above ran on the legacy stream; ctx->stream is non-blocking
     std::memset(ctx->h_st, 0, sizeof(PivotState));
     if (cudaFuncSetAttribute(k_select_primal, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmemBytes) != cudaSuccess ||
         cudaFuncSetAttribute(k_ratio_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmemBytes) != cudaSuccess) {
@@ -1164,6 +1191,8 @@ int ellp_b200_set_tuning(ellp_b200_ctx* ctx, const char* key, int value) {
     else if (!std::strcmp(key, "flush_kernel")) ctx->flush_kernel = value;
     else if (!std::strcmp(key, "flush_waves")) ctx->flush_waves = value;
     else if (!std::strcmp(key, "flush4_min_k")) ctx->flush4_min_k = value;
+    else if (!std::strcmp(key, "flush_ld")) ctx->flush_ld = value;
+    else if (!std::strcmp(key, "flush_stages")) ctx->flush_stages = value;
     else if (!std::strcmp(key, "coop_pivots")) ctx->coop_pivots = value;
     else if (!std::strcmp(key, "cuda_graphs")) ctx->use_graphs = value;
     else if (!std::strcmp(key, "small_path")) ctx->small_path = value;
@@ -1181,6 +1210,7 @@ int ellp_b200_set_tuning(ellp_b200_ctx* ctx, const char* key, int value) {
         if (value > 0) {
             CUDA_TRY(cudaMalloc(&ctx->tlog, sizeof(long long) * kTlogStamps * (size_t)value));
             CUDA_TRY(cudaMemset(ctx->tlog, 0, sizeof(long long) * kTlogStamps * (size_t)value));
+            CUDA_TRY(cudaDeviceSynchronize());  // legacy-stream memset vs. the non-blocking ctx->stream
             ctx->tlog_cap = value;
             ctx->tlog_seq0 = ctx->xseq;
         }
@@ -2297,6 +2327,7 @@ int ellp_b200_rank1_update(ellp_b200_ctx* ctx, double* E, int64_t R, int64_t C, 
     CUDA_TRY(cudaMalloc(&da, sizeof(double) * R));
     CUDA_TRY(cudaMemcpy(dE, E, sizeof(double) * ld * C, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(da, alpha, sizeof(double) * R, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaDeviceSynchronize());  // the copies above ran on the legacy stream; ctx->stream is non-blocking and would not wait for them
     int rc = ellp_b200_rank1_update_dev(ctx, dE, R, C, ld, da, r, 1, nullptr);
     if (rc == ELLP_OK) CUDA_TRY(cudaMemcpy(E, dE, sizeof(double) * ld * C, cudaMemcpyDeviceToHost));
     cudaFree(dE);
@@ -2339,6 +2370,7 @@ int ellp_b200_rankk_update(ellp_b200_ctx* ctx, double* E, int64_t R, int64_t C, 
     CUDA_TRY(cudaMemcpy2D(dE, sizeof(double) * ldp, E, sizeof(double) * ld, sizeof(double) * R, C, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy2D(dU, sizeof(double) * ldp, U, sizeof(double) * R, sizeof(double) * R, k, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy2D(dV, sizeof(double) * ldvp, V, sizeof(double) * C, sizeof(double) * C, k, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaDeviceSynchronize());  // the copies above ran on the legacy stream; ctx->stream is non-blocking and would not wait for them
     int rc = ellp_b200_rankk_update_dev(ctx, dE, R, C, ldp, dU, dV, ldvp, k, 1, nullptr);
     if (rc == ELLP_OK) CUDA_TRY(cudaMemcpy2D(E, sizeof(double) * ld, dE, sizeof(double) * ldp, sizeof(double) * R, C, cudaMemcpyDeviceToHost));
     cudaFree(dE); cudaFree(dU); cudaFree(dV);
@@ -2363,6 +2395,7 @@ int ellp_b200_gemv_t(ellp_b200_ctx* ctx, const double* M, int64_t R, int64_t C, 
         CUDA_TRY(cudaMalloc(&dc, sizeof(int32_t) * ncols));
         CUDA_TRY(cudaMemcpy(dc, cols, sizeof(int32_t) * ncols, cudaMemcpyHostToDevice));
     }
+    CUDA_TRY(cudaDeviceSynchronize());  // the copies above ran on the legacy stream; ctx->stream is non-blocking and would not wait for them
     LAUNCH(k_gemv_t<EPI_PLAIN>, gemv_grid((int)ncols), 256, dM, ldp, dc, (int)ncols, dv, dy, (const double*)nullptr,
            (const uint8_t*)nullptr, (double*)nullptr, (PivotState*)nullptr, 0);
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -2387,6 +2420,7 @@ int ellp_b200_gemv_n(ellp_b200_ctx* ctx, const double* M, int64_t R, int64_t C, 
     CUDA_TRY(cudaMemset(dM, 0, sizeof(double) * ldp * C));
     CUDA_TRY(cudaMemcpy2D(dM, sizeof(double) * ldp, M, sizeof(double) * ld, sizeof(double) * R, C, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(dv, v, sizeof(double) * C, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaDeviceSynchronize());  // the copies above ran on the legacy stream; ctx->stream is non-blocking and would not wait for them
     dim3 grid((unsigned)((ldp + 255) / 256), (unsigned)KS);
     LAUNCH(k_gemv_n_partial, grid, 128, dM, ldp, (int)R, (int)C, dv, dp, kc);
     LAUNCH(k_sum_partials, (unsigned)((R + 255) / 256), 256, dp, ldp, (int)R, KS, dy);
@@ -2407,6 +2441,7 @@ int ellp_b200_refactor_bench(ellp_b200_ctx* ctx, int32_t m, uint64_t seed, int32
     std::vector<int32_t> B((size_t)m);
     for (int i = 0; i < m; ++i) B[i] = i;  // basis = the m dense structural columns
     CUDA_TRY(cudaMemcpy(ctx->lp.Bv, B.data(), sizeof(int32_t) * m, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaDeviceSynchronize());  // the copies above ran on the legacy stream; ctx->stream is non-blocking and would not wait for them
     std::memset(ctx->h_st, 0, sizeof(PivotState));
     if (int rc = write_state(ctx)) return rc;
     const int saved = ctx->refactor_mode;
@@ -2444,6 +2479,7 @@ int ellp_b200_invert(ellp_b200_ctx* ctx, const double* Bmat, int64_t m, double* 
     if (int rc = write_state(ctx)) return rc;
     if (int rc = refactor(ctx, nullptr)) return rc;
     const DevLP& lp = ctx->lp;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // the copy below runs on the legacy stream, which does not wait for ctx->stream
     CUDA_TRY(cudaMemcpy2D(Binv, sizeof(double) * m, lp.Binv, sizeof(double) * lp.ld, sizeof(double) * m, m, cudaMemcpyDeviceToHost));
     return ELLP_OK;
 }
