@@ -133,9 +133,28 @@ __device__ __forceinline__ double warp_min_any(double v) {
     return __longlong_as_double((long long)((km >> 63) ? (km & 0x7fffffffffffffffull) : ~km));
 }
 
+// Cross-warp combine of the per-warp partials in shared memory: 16 lanes load one partial each and the warp reduces them with REDUX.
+// (Round 1 had every thread fold all 16 partials serially: fp64 max / min have no native instruction, each step is DSETP + 2 FSEL,
+// and those replicated folds were 35 % of all instructions of the kernel -- ncu source page, profiles/r02_k6_batch_ncu_summary.txt.)
+__device__ __forceinline__ double cta_max_nonneg(const double* sh_w, int lane) {
+    return warp_max_nonneg(lane < kBatchThreads / 32 ? sh_w[lane] : 0.);
+}
+__device__ __forceinline__ double cta_min_any(const double* sh_w, int lane) {
+    return warp_min_any(lane < kBatchThreads / 32 ? sh_w[lane] : CUDART_INF);
+}
+__device__ __forceinline__ void cta_counts(const int (*sh_c)[3], int lane, int& nF, int& nBand, int& idxF) {
+    const bool on = lane < kBatchThreads / 32;
+    nF = __reduce_add_sync(0xffffffffu, on ? sh_c[lane][0] : 0);
+    nBand = __reduce_add_sync(0xffffffffu, on ? sh_c[lane][1] : 0);
+    idxF = __reduce_min_sync(0xffffffffu, on ? sh_c[lane][2] : 0x7fffffff);
+}
+
 // One solve_with_initial on the condensed shared-memory tableau (primal :160-235).  Returns the SolutionStatus; all
 // threads of the CTA call it and receive the same value.  dn must hold the reduced costs of the current phase on entry.
-__device__ int batch_run_phase(const BatchSmem& s, int m, int n0, int ld, uint64_t max_iter, int tie_rule, int phase_tag,
+// MCT / N0CT > 0: rows / nonbasic columns known at compile time (the 64 x 192 shape of BASELINE.json configs[3]): the rank-1 sweep
+// unrolls completely with immediate shared-memory offsets (4 instructions per element instead of ~10).
+template <int MCT, int N0CT>
+__device__ int batch_run_phase(const BatchSmem& s, int m_rt, int n0_rt, int ld_rt, uint64_t max_iter, int tie_rule, int phase_tag,
                                ellp_trace_rec* trace, int trace_cap, int* trace_len, double* obj_running, int* iters_out,
                                int* err_out) {
     __shared__ int sh_i[8];      // 0 q_pos, 2 side, 3 nb, 4 status (kRunning while pivoting), 5 err
@@ -144,6 +163,7 @@ __device__ int batch_run_phase(const BatchSmem& s, int m, int n0, int ld, uint64
     __shared__ int sh_c[kBatchThreads / 32][3];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned full = 0xffffffffu;
+    const int m = MCT > 0 ? MCT : m_rt, n0 = N0CT > 0 ? N0CT : n0_rt, ld = MCT > 0 ? ((MCT % 2 == 0) ? MCT + 1 : MCT) : ld_rt;
     // thread -> (row, column group) map of the rank-1 update: no division inside the sweep
     const int groups = (m <= kBatchThreads) ? kBatchThreads / m : 0;
     const int my_row = (groups > 0) ? tid % m : 0;
@@ -171,9 +191,7 @@ __device__ int batch_run_phase(const BatchSmem& s, int m, int n0, int ld, uint64
         kloc = warp_max_nonneg(kloc);
         if (lane == 0) sh_w[warp] = kloc;
         __syncthreads();
-        double kmax = sh_w[0];
-#pragma unroll
-        for (int w = 1; w < kBatchThreads / 32; ++w) kmax = fmax(kmax, sh_w[w]);
+        const double kmax = cta_max_nonneg(sh_w, lane);
         if (kmax == 0.) {  // no candidate: optimal (:289-292); uniform across the CTA
             if (tid == 0) sh_i[4] = ELLP_OPTIMAL;
             __syncthreads();
@@ -195,9 +213,8 @@ __device__ int batch_run_phase(const BatchSmem& s, int m, int n0, int ld, uint64
         __syncthreads();
         int q_pos, q_var;
         {
-            int nF = 0, nBand = 0, idxF = 0x7fffffff;
-#pragma unroll
-            for (int w = 0; w < kBatchThreads / 32; ++w) { nF += sh_c[w][0]; nBand += sh_c[w][1]; idxF = min(idxF, sh_c[w][2]); }
+            int nF, nBand, idxF;
+            cta_counts(sh_c, lane, nF, nBand, idxF);
             if (tie_rule == ELLP_TIES_REFERENCE && nF == 1 && nBand == 0) {
                 q_pos = idxF;
             } else {
@@ -268,9 +285,7 @@ __device__ int batch_run_phase(const BatchSmem& s, int m, int n0, int ld, uint64
         lloc = warp_min_any(lloc);
         if (lane == 0) sh_w[warp] = lloc;
         __syncthreads();
-        double lmin = sh_w[0];
-#pragma unroll
-        for (int w = 1; w < kBatchThreads / 32; ++w) lmin = fmin(lmin, sh_w[w]);
+        const double lmin = cta_min_any(sh_w, lane);
         double lambda;
         {
             const int kq = s.kind[q_var];  // :305-311
@@ -293,9 +308,7 @@ __device__ int batch_run_phase(const BatchSmem& s, int m, int n0, int ld, uint64
                 idxF = __reduce_min_sync(full, idxF);
                 if (lane == 0) { sh_c[warp][0] = nF; sh_c[warp][1] = nBand; sh_c[warp][2] = idxF; }
                 __syncthreads();
-                nF = 0; nBand = 0; idxF = 0x7fffffff;
-#pragma unroll
-                for (int w = 0; w < kBatchThreads / 32; ++w) { nF += sh_c[w][0]; nBand += sh_c[w][1]; idxF = min(idxF, sh_c[w][2]); }
+                cta_counts(sh_c, lane, nF, nBand, idxF);
                 const int f0 = (lambda < L + kEps) ? 1 : 0;
                 const int band0 = (!f0 && lambda < L + 2. * kEps) ? 1 : 0;
                 if (nF + f0 == 1 && nBand + band0 == 0) {
@@ -367,6 +380,9 @@ __device__ int batch_run_phase(const BatchSmem& s, int m, int n0, int ld, uint64
         if (nb >= 0) {
             const double alpha_r = s.dcol[nb];
             for (int j = tid; j < n0; j += kBatchThreads) s.prow[j] = ((j == q_pos) ? 1. : s.T[(size_t)j * ld + nb]) / alpha_r;
+            // the entering position's column restarts from the (implicit) unit column e_r of the leaving variable: zeros outside row r
+            // (its old content lives in dcol; the row gather above skips it), so that the sweep below needs no per-element select
+            for (int i = tid; i < m; i += kBatchThreads) s.T[(size_t)q_pos * ld + i] = 0.;
         }
         __syncthreads();
         if (tid == 0) {
@@ -400,13 +416,24 @@ __device__ int batch_run_phase(const BatchSmem& s, int m, int n0, int ld, uint64
         if (nb >= 0) {
             if (groups > 0) {
                 if (my_group < groups) {
+                    // uniform sweep t = fma(-alpha_i, p_j, t) (the entering column was zeroed above); the thread of row r then overwrites
+                    // its own elements with the scaled pivot row -- same values as the per-element selects of round 1
                     const double na = -s.dcol[my_row];
-                    const bool is_r = (my_row == nb);
-                    for (int j = my_group; j < n0; j += groups) {
-                        const double p = s.prow[j];
-                        double* t = s.T + (size_t)j * ld + my_row;
-                        const double told = (j == q_pos) ? 0. : *t;
-                        *t = is_r ? p : fma(na, p, told);
+                    double* __restrict__ t = s.T + (size_t)my_group * ld + my_row;
+                    const double* __restrict__ pp = s.prow + my_group;
+                    if (MCT > 0 && N0CT > 0) {
+                        constexpr int G = MCT > 0 ? kBatchThreads / MCT : 1, LD = (MCT % 2 == 0) ? MCT + 1 : MCT, IT = (N0CT + G - 1) / G;
+#pragma unroll
+                        for (int u = 0; u < IT; ++u)
+                            if (N0CT % G == 0 || my_group + u * G < N0CT) t[u * G * LD] = fma(na, pp[u * G], t[u * G * LD]);
+                    } else {
+                        const int tstep = groups * ld;
+#pragma unroll 4
+                        for (int j = my_group; j < n0; j += groups) { *t = fma(na, *pp, *t); t += tstep; pp += groups; }
+                    }
+                    if (my_row == nb) {
+                        double* tr = s.T + (size_t)my_group * ld + my_row;
+                        for (int j = my_group; j < n0; j += groups) { *tr = s.prow[j]; tr += groups * ld; }
                     }
                 }
             } else {
@@ -431,6 +458,7 @@ __device__ int batch_run_phase(const BatchSmem& s, int m, int n0, int ld, uint64
     return status;
 }
 
+template <int MCT, int N0CT>
 __global__ void __launch_bounds__(kBatchThreads, 2) k_batch_primal(BatchArgs a) {
     extern __shared__ __align__(16) unsigned char batch_smem[];
     __shared__ int sh_tl;
@@ -488,7 +516,7 @@ __global__ void __launch_bounds__(kBatchThreads, 2) k_batch_primal(BatchArgs a) 
         batch_reduced_costs(s, c, m, n0, ld, 0);
         if (tid == 0) { double o = 0.; for (int i = 0; i < m; ++i) o += s.x[n0 + i]; sh_obj = o; }
         __syncthreads();
-        int status = batch_run_phase(s, m, n0, ld, a.max_iter, a.tie_rule, 0, trace, a.trace_cap, &sh_tl, &sh_obj, &sh_it[0], &sh_err);
+        int status = batch_run_phase<MCT, N0CT>(s, m, n0, ld, a.max_iter, a.tie_rule, 0, trace, a.trace_cap, &sh_tl, &sh_obj, &sh_it[0], &sh_err);
         int result = -1;
         if (status == ELLP_OPTIMAL) {  // primal_simplex_solver.rs:41-52
             if (tid == 0) { double o = 0.; for (int j = n0; j < nc; ++j) o += s.x[j]; sh_obj = o; }
@@ -509,7 +537,7 @@ __global__ void __launch_bounds__(kBatchThreads, 2) k_batch_primal(BatchArgs a) 
             batch_reduced_costs(s, c, m, n0, ld, 1);
             if (tid == 0) { double o = 0.; for (int j = 0; j < n0; ++j) o += c[j] * s.x[j]; sh_obj = o; }
             __syncthreads();
-            status = batch_run_phase(s, m, n0, ld, a.max_iter, a.tie_rule, 1, trace, a.trace_cap, &sh_tl, &sh_obj, &sh_it[1], &sh_err);
+            status = batch_run_phase<MCT, N0CT>(s, m, n0, ld, a.max_iter, a.tie_rule, 1, trace, a.trace_cap, &sh_tl, &sh_obj, &sh_it[1], &sh_err);
             if (tid == 0) {
                 double o = 0.;
                 for (int j = 0; j < n0; ++j) o += c[j] * s.x[j];  // Solution::obj() = c . x (artificial costs are 0)

@@ -1700,6 +1700,13 @@ int ellp_b200_batch_upload(ellp_b200_ctx* ctx, const ellp_batch* bt, int32_t tra
     return ELLP_OK;
 }
 
+// the 64 x 192 standard form of BASELINE.json configs[3] has a compile-time specialisation (fully unrolled rank-1 sweep)
+using BatchKernel = void (*)(BatchArgs);
+static BatchKernel batch_kernel_for(int m, int n0, int ld) {
+    if (m == 64 && n0 == 192 && ld == 65) return k_batch_primal<64, 192>;
+    return k_batch_primal<0, 0>;
+}
+
 int ellp_b200_batch_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_batch_result* res) {
     if (!ctx || !o || !res) return ELLP_E_ARG;
     auto& B = ctx->batch;
@@ -1707,7 +1714,8 @@ int ellp_b200_batch_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_batch_resul
     CUDA_TRY(cudaSetDevice(ctx->device));
     const size_t smem = batch_smem_bytes(B.m, B.n0, B.ld);
     if (smem > 227 * 1024) return set_err(ctx, ELLP_E_ARG, "LP too large for the shared-memory kernel (needs about (m+1)*n*8 bytes <= ~215 KB)");
-    CUDA_TRY(cudaFuncSetAttribute(k_batch_primal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const BatchKernel kern = batch_kernel_for(B.m, B.n0, B.ld);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     BatchArgs a{};
     a.nlp = B.nlp; a.m = B.m; a.n0 = B.n0; a.nc = B.nc; a.ld = B.ld;
     a.mode = 0;
@@ -1720,10 +1728,10 @@ int ellp_b200_batch_run(ellp_b200_ctx* ctx, const ellp_opts* o, ellp_batch_resul
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     int per_sm = 1;  // persistent CTAs: as many per SM as the shared-memory tableau allows (2 for 64 x 192)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_batch_primal, kBatchThreads, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBatchThreads, smem);
     const int grid = std::min(B.nlp, sms * std::max(1, per_sm));
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-    LAUNCH_SMEM(k_batch_primal, grid, kBatchThreads, smem, a);
+    LAUNCH_SMEM(kern, grid, kBatchThreads, smem, a);
     CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(cudaGetLastError());
@@ -1799,7 +1807,8 @@ int ellp_b200_primal_solve_batch(ellp_b200_ctx* ctx, const ellp_batch* bt, const
     auto& B = ctx->batch;
     const size_t smem = batch_smem_bytes(B.m, B.n0, B.ld);
     if (smem > 227 * 1024) return set_err(ctx, ELLP_E_ARG, "LP too large for the shared-memory kernel (needs about (m+1)*n*8 bytes <= ~215 KB)");
-    CUDA_TRY(cudaFuncSetAttribute(k_batch_primal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const BatchKernel kern = batch_kernel_for(B.m, B.n0, B.ld);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (!ctx->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     if (ctx->chunk_ev.size() < 2 * (size_t)nchunks) {
         const size_t old = ctx->chunk_ev.size();
@@ -1808,7 +1817,7 @@ int ellp_b200_primal_solve_batch(ellp_b200_ctx* ctx, const ellp_batch* bt, const
     }
     int sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_batch_primal, kBatchThreads, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBatchThreads, smem);
     const size_t m = (size_t)bt->m, n = (size_t)bt->n, nc = (size_t)B.nc;
     const int per = (bt->nlp + nchunks - 1) / nchunks;
     if (!ctx->d2h_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
@@ -1847,7 +1856,7 @@ int ellp_b200_primal_solve_batch(ellp_b200_ctx* ctx, const ellp_batch* bt, const
             a.status = B.status + l0; a.obj = B.obj + l0; a.iters = B.iters + 2 * l0; a.err = B.err + l0;
             a.trace = B.trace ? B.trace + l0 * B.trace_cap : nullptr; a.trace_len = B.trace_len + l0;
             const int grid = (int)std::min<size_t>(cnt, (size_t)sms * std::max(1, per_sm));
-            k_batch_primal<<<grid, kBatchThreads, smem, ks>>>(a);
+            kern<<<grid, kBatchThreads, smem, ks>>>(a);
             ctx->launches++;
             CUDA_TRY(cudaEventRecord(ctx->chunk_ev[2 * c + 1], ks));
             if (c + 1 < used) { if (int rc = h2d(c + 1)) return rc; }
