@@ -133,21 +133,9 @@ __device__ __forceinline__ double warp_min_any(double v) {
     return __longlong_as_double((long long)((km >> 63) ? (km & 0x7fffffffffffffffull) : ~km));
 }
 
-// Cross-warp combine of the per-warp partials in shared memory: 16 lanes load one partial each and the warp reduces them with REDUX.
-// (Round 1 had every thread fold all 16 partials serially: fp64 max / min have no native instruction, each step is DSETP + 2 FSEL,
-// and those replicated folds were 35 % of all instructions of the kernel -- ncu source page, profiles/r02_k6_batch_ncu_summary.txt.)
-__device__ __forceinline__ double cta_max_nonneg(const double* sh_w, int lane) {
-    return warp_max_nonneg(lane < kBatchThreads / 32 ? sh_w[lane] : 0.);
-}
-__device__ __forceinline__ double cta_min_any(const double* sh_w, int lane) {
-    return warp_min_any(lane < kBatchThreads / 32 ? sh_w[lane] : CUDART_INF);
-}
-__device__ __forceinline__ void cta_counts(const int (*sh_c)[3], int lane, int& nF, int& nBand, int& idxF) {
-    const bool on = lane < kBatchThreads / 32;
-    nF = __reduce_add_sync(0xffffffffu, on ? sh_c[lane][0] : 0);
-    nBand = __reduce_add_sync(0xffffffffu, on ? sh_c[lane][1] : 0);
-    idxF = __reduce_min_sync(0xffffffffu, on ? sh_c[lane][2] : 0x7fffffff);
-}
+// Cross-warp combines: 16 lanes load one per-warp partial each and the warp reduces them with REDUX.  (Round 1 had every thread fold
+// all 16 partials serially: fp64 max / min have no native instruction, each step is DSETP + 2 FSEL, and those replicated folds were
+// 35 % of all instructions of the kernel -- ncu source page, profiles/r02_k6_batch_ncu_summary.txt.)
 
 // One solve_with_initial on the condensed shared-memory tableau (primal :160-235).  Returns the SolutionStatus; all
 // threads of the CTA call it and receive the same value.  dn must hold the reduced costs of the current phase on entry.
@@ -159,8 +147,10 @@ __device__ int batch_run_phase(const BatchSmem& s, int m_rt, int n0_rt, int ld_r
                                int* err_out) {
     __shared__ int sh_i[8];      // 0 q_pos, 2 side, 3 nb, 4 status (kRunning while pivoting), 5 err
     __shared__ double sh_d[4];   // 1 lambda
-    __shared__ double sh_w[kBatchThreads / 32];
-    __shared__ int sh_c[kBatchThreads / 32][3];
+    // per-warp (best, second best, position) partials: separate arrays for pricing and for the ratio test, because no block barrier
+    // separates a fast warp's ratio partial from a slow warp's read of the pricing partials any more
+    __shared__ double shp1[kBatchThreads / 32], shp2[kBatchThreads / 32], shr1[kBatchThreads / 32], shr2[kBatchThreads / 32];
+    __shared__ int shpi[kBatchThreads / 32], shri[kBatchThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned full = 0xffffffffu;
     const int m = MCT > 0 ? MCT : m_rt, n0 = N0CT > 0 ? N0CT : n0_rt, ld = MCT > 0 ? ((MCT % 2 == 0) ? MCT + 1 : MCT) : ld_rt;
@@ -175,7 +165,11 @@ __device__ int batch_run_phase(const BatchSmem& s, int m_rt, int n0_rt, int ld_r
         if (pivots >= max_iter) { if (tid == 0) sh_i[4] = ELLP_MAXITER; __syncthreads(); break; }  // :163-166
         // ---- pricing (primal :253-292) by the whole CTA: keys -> CTA max -> is the maximum isolated? (exact shortcut, DESIGN.md
         // section 3); only ties / near-ties run the reference's sequential max_by fold on warp 0.
-        double kloc = 0.;  // keys are > 0; +0.0 marks "no candidate" so that bit patterns order like unsigned integers
+        // One reduction pass: every thread / warp carries (best, second best, position of the best).  The maximum is isolated --
+        // nF == 1 && nBand == 0 of the two-pass formulation -- exactly when the SECOND best fails the band test kmax - k < 2 EPS, because
+        // that test is monotone in k; this saves the count pass and its block barrier.
+        double a1 = 0., a2 = 0.;  // keys are > 0; +0.0 marks "no candidate" so that bit patterns order like unsigned integers
+        int i1 = 0;
         for (int j = tid; j < n0; j += kBatchThreads) {
             const double r = s.dn[j];
             const int side = s.Ns[j];
@@ -185,38 +179,38 @@ __device__ int batch_run_phase(const BatchSmem& s, int m_rt, int n0_rt, int ld_r
                 else if (!(r > 0.) && side == ELLP_NB_LOWER) k = -r;
                 else if (side == ELLP_NB_FREE) k = fabs(r);
             }
-            s.prow[j] = k;  // prow doubles as the key buffer
-            if (k > kloc) kloc = k;
+            s.prow[j] = k;  // prow doubles as the key buffer (read by the fold on ties)
+            if (k > a1) { a2 = a1; a1 = k; i1 = j; }
+            else if (k > a2) a2 = k;  // also k == a1: the second best then equals the best ("tie")
         }
-        kloc = warp_max_nonneg(kloc);
-        if (lane == 0) sh_w[warp] = kloc;
+        {
+            const double w1 = warp_max_nonneg(a1);
+            const bool hold = (a1 == w1);
+            const unsigned hm = __ballot_sync(full, hold);
+            double w2 = warp_max_nonneg(hold ? a2 : a1);
+            if (__popc(hm) > 1) w2 = w1;
+            const int wi = __shfl_sync(full, i1, __ffs(hm) - 1);
+            if (lane == 0) { shp1[warp] = w1; shp2[warp] = w2; shpi[warp] = wi; }
+        }
         __syncthreads();
-        const double kmax = cta_max_nonneg(sh_w, lane);
+        const bool on16 = lane < kBatchThreads / 32;
+        const double pb1 = on16 ? shp1[lane] : 0., pb2 = on16 ? shp2[lane] : 0.;
+        const int pbi = on16 ? shpi[lane] : 0;
+        const double kmax = warp_max_nonneg(pb1);
         if (kmax == 0.) {  // no candidate: optimal (:289-292); uniform across the CTA
             if (tid == 0) sh_i[4] = ELLP_OPTIMAL;
             __syncthreads();
             break;
         }
-        {
-            int nF = 0, nBand = 0, idxF = 0x7fffffff;
-            for (int j = tid; j < n0; j += kBatchThreads) {
-                const double k = s.prow[j];
-                if (k == -1.0) continue;
-                if (kmax - k < kEps) { ++nF; idxF = min(idxF, j); }
-                else if (kmax - k < 2. * kEps) ++nBand;
-            }
-            nF = __reduce_add_sync(full, nF);
-            nBand = __reduce_add_sync(full, nBand);
-            idxF = __reduce_min_sync(full, idxF);
-            if (lane == 0) { sh_c[warp][0] = nF; sh_c[warp][1] = nBand; sh_c[warp][2] = idxF; }
-        }
-        __syncthreads();
         int q_pos, q_var;
         {
-            int nF, nBand, idxF;
-            cta_counts(sh_c, lane, nF, nBand, idxF);
-            if (tie_rule == ELLP_TIES_REFERENCE && nF == 1 && nBand == 0) {
-                q_pos = idxF;
+            const bool hold = on16 && (pb1 == kmax);
+            const unsigned hm = __ballot_sync(full, hold);
+            double k2 = warp_max_nonneg(hold ? pb2 : pb1);
+            if (__popc(hm) > 1) k2 = kmax;
+            const int idx1 = __shfl_sync(full, pbi, __ffs(hm) - 1);
+            if (tie_rule == ELLP_TIES_REFERENCE && !(kmax - k2 < 2. * kEps)) {
+                q_pos = idx1;
             } else {
                 if (warp == 0) {
                     int bp = -1, bv = -1;
@@ -268,7 +262,8 @@ __device__ int batch_run_phase(const BatchSmem& s, int m_rt, int n0_rt, int ld_r
         const bool at_lower = (side_q == ELLP_NB_LOWER);
         const double rq = s.dn[q_pos];
         // ---- pivot column, direction, ratios (primal :295-367): one row per thread
-        double lloc = CUDART_INF;
+        double r1 = CUDART_INF, r2 = CUDART_INF;  // smallest / second smallest ratio of this thread's rows, position of the smallest
+        int ri = 0;
         for (int i = tid; i < m; i += kBatchThreads) {
             const double a = s.T[(size_t)q_pos * ld + i];
             s.dcol[i] = a;
@@ -278,14 +273,24 @@ __device__ int batch_run_phase(const BatchSmem& s, int m_rt, int n0_rt, int ld_r
                 const int var = s.Bv[i];
                 lam = primal_ratio(s.kind[var], s.lo[var], s.hi[var], s.x[var], d_i);
                 if (lam == 0.) lam = 0.;  // canonical +0.0
-                if (lam < lloc) lloc = lam;
+                if (lam < r1) { r2 = r1; r1 = lam; ri = i; }
+                else if (lam < r2) r2 = lam;  // also lam == r1 ("tie"); +inf ratios never enter, as in the two-pass version
             }
             s.lam[i] = lam;
         }
-        lloc = warp_min_any(lloc);
-        if (lane == 0) sh_w[warp] = lloc;
+        {
+            const double w1 = warp_min_any(r1);
+            const bool hold = (r1 == w1);
+            const unsigned hm = __ballot_sync(full, hold);
+            double w2 = warp_min_any(hold ? r2 : r1);
+            if (__popc(hm) > 1) w2 = w1;
+            const int wi = __shfl_sync(full, ri, __ffs(hm) - 1);
+            if (lane == 0) { shr1[warp] = w1; shr2[warp] = w2; shri[warp] = wi; }
+        }
         __syncthreads();
-        const double lmin = cta_min_any(sh_w, lane);
+        const double rb1 = on16 ? shr1[lane] : CUDART_INF, rb2 = on16 ? shr2[lane] : CUDART_INF;
+        const int rbi = on16 ? shri[lane] : 0;
+        const double lmin = warp_min_any(rb1);
         double lambda;
         {
             const int kq = s.kind[q_var];  // :305-311
@@ -296,24 +301,18 @@ __device__ int batch_run_phase(const BatchSmem& s, int m_rt, int n0_rt, int ld_r
             const double L = fmin(lmin, lambda);
             bool fast = !(L < CUDART_INF);  // nothing finite: lambda stays +inf
             if (!fast) {
-                int nF = 0, nBand = 0, idxF = 0x7fffffff;
-                for (int i = tid; i < m; i += kBatchThreads) {
-                    const double l = s.lam[i];
-                    if (l == kLamSkipped) continue;
-                    if (l < L + kEps) { ++nF; idxF = min(idxF, i); }
-                    else if (l < L + 2. * kEps) ++nBand;
-                }
-                nF = __reduce_add_sync(full, nF);
-                nBand = __reduce_add_sync(full, nBand);
-                idxF = __reduce_min_sync(full, idxF);
-                if (lane == 0) { sh_c[warp][0] = nF; sh_c[warp][1] = nBand; sh_c[warp][2] = idxF; }
-                __syncthreads();
-                cta_counts(sh_c, lane, nF, nBand, idxF);
-                const int f0 = (lambda < L + kEps) ? 1 : 0;
-                const int band0 = (!f0 && lambda < L + 2. * kEps) ? 1 : 0;
-                if (nF + f0 == 1 && nBand + band0 == 0) {
+                // second smallest of the multiset {ratios} + {lambda of the entering variable}: the minimum is isolated (the fold's result
+                // is known without running it) iff that second value is at least 2 EPS above L (nF + f0 == 1 && nBand + band0 == 0)
+                const bool hold = on16 && (rb1 == lmin);
+                const unsigned hm = __ballot_sync(full, hold);
+                double l2 = warp_min_any(hold ? rb2 : rb1);
+                if (__popc(hm) > 1) l2 = lmin;
+                const int idx1 = __shfl_sync(full, rbi, __ffs(hm) - 1);
+                const bool q_is_min = lambda < lmin;
+                const double second = q_is_min ? lmin : ((lambda == lmin) ? lmin : fmin(l2, lambda));
+                if (!(second < L + 2. * kEps)) {
                     fast = true;
-                    if (!f0) { nb = idxF; lambda = s.lam[idxF]; }
+                    if (!q_is_min) { nb = idx1; lambda = lmin; }
                 }
             }
             if (!fast) {  // sequential scan with its (lambda, new_basic, new_basic_index) state (primal :379-399), warp 0
