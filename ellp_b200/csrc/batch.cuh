@@ -11,6 +11,10 @@
 // Layout: the condensed tableau (nonbasic columns of B^-1 [A | artificials]) lives in shared memory, column-major with an
 // ODD leading dimension (m+1 if m is even) so that both the column sweeps of the rank-1 update and the strided pivot-row
 // gather are (almost) bank-conflict free.  The tie folds are the reference's sequential folds, evaluated by warp 0 with ballots exactly as in kernels.cuh.
+//
+// Per pivot (round 2): three block barriers -- [ratio partials] -> decision -> [x step, scaled pivot row, entering column zeroed] ->
+// rank-1 sweep + reduced costs + keys / partials of the NEXT pricing -> [loop].  Decisions are replicated in every warp (REDUX on
+// order-preserving keys over the 16 per-warp partials); bookkeeping runs on single threads of two otherwise idle warps.
 #pragma once
 #include "kernels.cuh"
 
@@ -52,7 +56,8 @@ struct BatchArgs {
 struct BatchSmem {
     double* T;      // ld x n0
     double* dn;     // n0: reduced cost per nonbasic position
-    double* prow;   // n0: scaled pivot row; doubles as the Dantzig key buffer during pricing
+    double* prow;   // n0: scaled pivot row
+    double* key;    // n0: Dantzig keys of the next pricing (written while the sweep still reads prow; read by the fold on ties)
     double* x;      // nc
     double* lo;     // nc
     double* hi;     // nc
@@ -66,7 +71,7 @@ struct BatchSmem {
 
 __host__ __device__ inline size_t batch_smem_bytes(int m, int n0, int ld) {
     const size_t nc = (size_t)n0 + m;
-    size_t d = (size_t)ld * n0 + 2 * (size_t)n0 + 3 * nc + 2 * (size_t)m;  // doubles
+    size_t d = (size_t)ld * n0 + 3 * (size_t)n0 + 3 * nc + 2 * (size_t)m;  // doubles
     size_t bytes = d * 8 + 4 * ((size_t)m + n0) + (size_t)n0 + nc;
     return (bytes + 15) / 16 * 16;
 }
@@ -78,6 +83,7 @@ __device__ inline BatchSmem batch_carve(unsigned char* base, int m, int n0, int 
     s.T = d; d += (size_t)ld * n0;
     s.dn = d; d += n0;
     s.prow = d; d += n0;
+    s.key = d; d += n0;
     s.x = d; d += nc;
     s.lo = d; d += nc;
     s.hi = d; d += nc;
@@ -160,39 +166,47 @@ __device__ int batch_run_phase(const BatchSmem& s, int m_rt, int n0_rt, int ld_r
     const int my_group = (groups > 0) ? tid / m : 0;
     uint64_t pivots = 0;
     if (tid == 0) { sh_i[4] = kRunning; sh_i[5] = 0; }
-    __syncthreads();
-    for (;;) {
-        if (pivots >= max_iter) { if (tid == 0) sh_i[4] = ELLP_MAXITER; __syncthreads(); break; }  // :163-166
-        // ---- pricing (primal :253-292) by the whole CTA: keys -> CTA max -> is the maximum isolated? (exact shortcut, DESIGN.md
-        // section 3); only ties / near-ties run the reference's sequential max_by fold on warp 0.
-        // One reduction pass: every thread / warp carries (best, second best, position of the best).  The maximum is isolated --
-        // nF == 1 && nBand == 0 of the two-pass formulation -- exactly when the SECOND best fails the band test kmax - k < 2 EPS, because
-        // that test is monotone in k; this saves the count pass and its block barrier.
+    // Pricing keys (primal :253-270) of this thread's positions and the per-warp partials (best, second best, position of the best).
+    // One reduction pass: the maximum is isolated -- nF == 1 && nBand == 0 of a two-pass formulation -- exactly when the SECOND best
+    // fails the band test kmax - k < 2 EPS, because that test is monotone in k.  Runs once before the loop and then at the END of
+    // every iteration, fused with the reduced-cost update (no separate pass, no barrier of its own); q_pos_prev / side_prev give the
+    // new bound side of the position that was just pivoted or flipped (its Ns entry is being written by another thread).
+    auto price = [&](bool update, int q_prev, int side_prev, double rq_prev, int nb_prev) {
         double a1 = 0., a2 = 0.;  // keys are > 0; +0.0 marks "no candidate" so that bit patterns order like unsigned integers
         int i1 = 0;
         for (int j = tid; j < n0; j += kBatchThreads) {
-            const double r = s.dn[j];
-            const int side = s.Ns[j];
+            double r = s.dn[j];
+            if (update) {  // reduced costs after the pivot, and row r of the tableau = the scaled pivot row
+                const double p = s.prow[j];
+                r = fma(-rq_prev, p, (j == q_prev) ? 0. : r);
+                s.dn[j] = r;
+                s.T[(size_t)j * ld + nb_prev] = p;
+            }
+            const int side = (j == q_prev) ? side_prev : s.Ns[j];
             double k = -1.0;
             if (!(fabs(r) < kEps)) {
                 if (r > 0. && side == ELLP_NB_UPPER) k = r;
                 else if (!(r > 0.) && side == ELLP_NB_LOWER) k = -r;
                 else if (side == ELLP_NB_FREE) k = fabs(r);
             }
-            s.prow[j] = k;  // prow doubles as the key buffer (read by the fold on ties)
+            s.key[j] = k;  // read by the fold on ties
             if (k > a1) { a2 = a1; a1 = k; i1 = j; }
             else if (k > a2) a2 = k;  // also k == a1: the second best then equals the best ("tie")
         }
-        {
-            const double w1 = warp_max_nonneg(a1);
-            const bool hold = (a1 == w1);
-            const unsigned hm = __ballot_sync(full, hold);
-            double w2 = warp_max_nonneg(hold ? a2 : a1);
-            if (__popc(hm) > 1) w2 = w1;
-            const int wi = __shfl_sync(full, i1, __ffs(hm) - 1);
-            if (lane == 0) { shp1[warp] = w1; shp2[warp] = w2; shpi[warp] = wi; }
-        }
-        __syncthreads();
+        const double w1 = warp_max_nonneg(a1);
+        const bool hold = (a1 == w1);
+        const unsigned hm = __ballot_sync(full, hold);
+        double w2 = warp_max_nonneg(hold ? a2 : a1);
+        if (__popc(hm) > 1) w2 = w1;
+        const int wi = __shfl_sync(full, i1, __ffs(hm) - 1);
+        if (lane == 0) { shp1[warp] = w1; shp2[warp] = w2; shpi[warp] = wi; }
+    };
+    price(false, -1, 0, 0., 0);
+    __syncthreads();
+    for (;;) {
+        if (pivots >= max_iter) { if (tid == 0) sh_i[4] = ELLP_MAXITER; __syncthreads(); break; }  // :163-166
+        // ---- pricing (primal :253-292): combine the per-warp partials left by price() -> CTA maximum -> is it isolated? (exact
+        // shortcut); only ties / near-ties run the reference's sequential max_by fold on warp 0.
         const bool on16 = lane < kBatchThreads / 32;
         const double pb1 = on16 ? shp1[lane] : 0., pb2 = on16 ? shp2[lane] : 0.;
         const int pbi = on16 ? shpi[lane] : 0;
@@ -219,7 +233,7 @@ __device__ int batch_run_phase(const BatchSmem& s, int m_rt, int n0_rt, int ld_r
                         double bk = 0.;
                         for (int c0 = 0; c0 < n0; c0 += 32) {
                             const int j = c0 + lane;
-                            const double k = (j < n0) ? s.prow[j] : -1.0;
+                            const double k = (j < n0) ? s.key[j] : -1.0;
                             const int v = (j < n0) ? s.Nv[j] : 0;
                             const bool cand = (k != -1.0);
                             unsigned rem = __ballot_sync(full, cand);
@@ -242,7 +256,7 @@ __device__ int batch_run_phase(const BatchSmem& s, int m_rt, int n0_rt, int ld_r
                         }
                     } else {  // order-free rule: largest variable index within EPS of the maximum
                         for (int j = lane; j < n0; j += 32) {
-                            const double k = s.prow[j];
+                            const double k = s.key[j];
                             if (k != -1.0 && (kmax - k < kEps) && s.Nv[j] > bv) { bv = s.Nv[j]; bp = j; }
                         }
 #pragma unroll
@@ -367,8 +381,8 @@ __device__ int batch_run_phase(const BatchSmem& s, int m_rt, int n0_rt, int ld_r
             __syncthreads();
             break;
         }
-        if (tid == 0) sh_i[2] = side_q;
         // ---- step (primal :408-417) and scaled pivot row (1 / alpha_r in the slot of the entering position)
+        const int leave_var = (nb >= 0) ? s.Bv[nb] : -1;  // read before the barrier: the swap below runs concurrently with the trace record
         if (lambda > 0.)
             for (int i = tid; i < m; i += kBatchThreads) {
                 const double a = s.dcol[i];
@@ -376,27 +390,23 @@ __device__ int batch_run_phase(const BatchSmem& s, int m_rt, int n0_rt, int ld_r
                 const int var = s.Bv[i];
                 s.x[var] = s.x[var] + lambda * d_i;
             }
+        int new_side_q;  // bound side of position q_pos after this iteration (:217-231), known to every thread
         if (nb >= 0) {
             const double alpha_r = s.dcol[nb];
+            const double d_nb = at_lower ? -alpha_r : alpha_r;
+            new_side_q = (d_nb > 0.) ? ELLP_NB_UPPER : ELLP_NB_LOWER;
             for (int j = tid; j < n0; j += kBatchThreads) s.prow[j] = ((j == q_pos) ? 1. : s.T[(size_t)j * ld + nb]) / alpha_r;
             // the entering position's column restarts from the (implicit) unit column e_r of the leaving variable: zeros outside row r
             // (its old content lives in dcol; the row gather above skips it), so that the sweep below needs no per-element select
             for (int i = tid; i < m; i += kBatchThreads) s.T[(size_t)q_pos * ld + i] = 0.;
+        } else {
+            new_side_q = (side_q == ELLP_NB_LOWER) ? ELLP_NB_UPPER : ELLP_NB_LOWER;
         }
         __syncthreads();
-        if (tid == 0) {
+        // bookkeeping by single threads of two warps that carry no reduced-cost work (warps 0 .. n0/32 do): entering value, trace
+        // record and running objective on one, the index swap / bound flip (:208-231) on the other
+        if (tid == kBatchThreads - 64) {
             if (lambda > 0.) s.x[q_var] = at_lower ? s.x[q_var] + lambda : s.x[q_var] - lambda;
-            int leave_var = -1;
-            if (nb >= 0) {  // :208-221
-                const double a = s.dcol[nb];
-                const double d_nb = at_lower ? -a : a;
-                leave_var = s.Bv[nb];
-                s.Bv[nb] = q_var;
-                s.Nv[q_pos] = leave_var;
-                s.Ns[q_pos] = (d_nb > 0.) ? ELLP_NB_UPPER : ELLP_NB_LOWER;
-            } else {  // :223-231
-                s.Ns[q_pos] = (side_q == ELLP_NB_LOWER) ? ELLP_NB_UPPER : ELLP_NB_LOWER;
-            }
             if (trace && *trace_len < trace_cap) {
                 ellp_trace_rec rec;
                 rec.phase = phase_tag;
@@ -410,13 +420,14 @@ __device__ int batch_run_phase(const BatchSmem& s, int m_rt, int n0_rt, int ld_r
             *trace_len += 1;
             *obj_running = *obj_running + rq * (at_lower ? lambda : -lambda);
         }
-        // ---- rank-1 update of the condensed tableau and of the reduced costs; the entering position's column starts from the
-        // (implicit) unit column e_r of the leaving variable, i.e. from zeros outside row r
+        if (tid == kBatchThreads - 32) {
+            if (nb >= 0) { s.Bv[nb] = q_var; s.Nv[q_pos] = leave_var; }
+            s.Ns[q_pos] = (uint8_t)new_side_q;
+        }
+        // ---- rank-1 update of the condensed tableau (rows other than r; row r = the scaled pivot row is written by price())
         if (nb >= 0) {
             if (groups > 0) {
-                if (my_group < groups) {
-                    // uniform sweep t = fma(-alpha_i, p_j, t) (the entering column was zeroed above); the thread of row r then overwrites
-                    // its own elements with the scaled pivot row -- same values as the per-element selects of round 1
+                if (my_group < groups && my_row != nb) {
                     const double na = -s.dcol[my_row];
                     double* __restrict__ t = s.T + (size_t)my_group * ld + my_row;
                     const double* __restrict__ pp = s.prow + my_group;
@@ -430,23 +441,19 @@ __device__ int batch_run_phase(const BatchSmem& s, int m_rt, int n0_rt, int ld_r
 #pragma unroll 4
                         for (int j = my_group; j < n0; j += groups) { *t = fma(na, *pp, *t); t += tstep; pp += groups; }
                     }
-                    if (my_row == nb) {
-                        double* tr = s.T + (size_t)my_group * ld + my_row;
-                        for (int j = my_group; j < n0; j += groups) { *tr = s.prow[j]; tr += groups * ld; }
-                    }
                 }
             } else {
                 const int total = m * n0;
                 for (int e = tid; e < total; e += kBatchThreads) {
                     const int j = e / m, i = e - j * m;
-                    const double p = s.prow[j];
+                    if (i == nb) continue;
                     double* t = s.T + (size_t)j * ld + i;
-                    const double told = (j == q_pos) ? 0. : *t;
-                    *t = (i == nb) ? p : fma(-s.dcol[i], p, told);
+                    *t = fma(-s.dcol[i], s.prow[j], *t);
                 }
             }
-            for (int j = tid; j < n0; j += kBatchThreads) s.dn[j] = fma(-rq, s.prow[j], (j == q_pos) ? 0. : s.dn[j]);
         }
+        // reduced costs, row r, and the keys / partials of the NEXT pricing
+        price(nb >= 0, q_pos, new_side_q, rq, nb >= 0 ? nb : 0);
         pivots += 1;
         __syncthreads();
     }
