@@ -833,4 +833,117 @@ __global__ void __launch_bounds__(kFlush6Threads, 1) k_blk_flush6(double* __rest
     else flush6_body<STREAM, NSPLIT, false>(T, ld, R, C, V, ldv, cnt, K4, stages, nsteps, step0, row0, sU, sVr, full, arrived);
 }
 
+// ------------------------------------------------------------------------------------------------
+// K3b, version 4r: version 4 with RW x 4 consumer warps (CTA tile RW*32 rows x 128 columns per step).  RW = 3 gives 12 consumer
+// warps + the producer warp = 13 warps, which the register file allocates as 16: 128 registers per thread instead of 96 (no
+// spills, fragment loads of the next k-step in flight behind the DMMAs of the current one), and 96 KB of tile loads in flight
+// instead of 128 KB next to a larger L1 (163 KB of shared memory at k = 56).  Keeps the dedicated producer warp of version 4 (the
+// refill stays off the consumers' critical path, which is what version 6 loses).  Bit-identical to the other versions.
+// ------------------------------------------------------------------------------------------------
+template <int RW> constexpr int flush4r_threads() { return (4 * RW + 1) * 32; }
+template <int RW> inline size_t blk_flush4r_smem_bytes(int K4, int stages) { return sizeof(double) * (size_t)K4 * ((RW * 32 + 4) + stages * kFlush4SV) + 48; }
+
+template <int STREAM, int RW>
+__global__ void __launch_bounds__((4 * RW + 1) * 32, 1) k_blk_flush4r(double* __restrict__ T, int64_t ld, int R, int C, const double* __restrict__ U,
+                                                                      const double* __restrict__ V, int64_t ldv, int cnt, int col_steps, int stages) {
+    constexpr int ROWS = RW * 32, SU = ROWS + 4, NCW = 4 * RW, THREADS = (NCW + 1) * 32;
+    extern __shared__ __align__(16) double blk_smem[];
+    const int K4 = (cnt + 3) & ~3;
+    double* sU = blk_smem;                    // sU[j][row] = -U[row0 + row, j]
+    double* sVr = blk_smem + K4 * SU;         // ring: sV[stage][j][col] = V[j, col0 + col]
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(sVr + (size_t)stages * K4 * kFlush4SV);
+    unsigned long long* empty = full + 3;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * ROWS;
+    const int wr = (warp % RW) * 32, wc = (warp / RW) * 32;
+    const int fq = lane >> 2, fk = lane & 3;
+    const int ksteps = K4 >> 2;
+    const int64_t step0 = (int64_t)blockIdx.y * col_steps;
+    const int64_t steps_total = (C + kFlush4Cols - 1) / kFlush4Cols;
+    const int nsteps = (int)max((int64_t)0, min((int64_t)col_steps, steps_total - step0));
+    if (nsteps == 0) return;
+    const unsigned tile_bytes = (unsigned)cnt * kFlush4Cols * (unsigned)sizeof(double);
+    if (tid == 0) {
+        for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], NCW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int e = tid; e < K4 * ROWS; e += THREADS) {
+        const int j = e / ROWS, i = e - j * ROWS;
+        sU[j * SU + i] = (j < cnt && row0 + i < R) ? -U[(int64_t)j * ld + row0 + i] : 0.;
+    }
+    for (int e = tid; e < stages * (K4 - cnt) * kFlush4SV; e += THREADS) {  // rows cnt .. K4-1 are never copied: zero them once
+        const int slot = e / ((K4 - cnt) * kFlush4SV), rem = e - slot * (K4 - cnt) * kFlush4SV;
+        sVr[(size_t)slot * K4 * kFlush4SV + (size_t)cnt * kFlush4SV + rem] = 0.;
+    }
+    __syncthreads();  // the only block-wide barrier
+    if (warp == NCW) {  // producer: V tile of step t -> ring slot t % stages, one 1 KB row per lane and copy
+        for (int t = 0; t < nsteps; ++t) {
+            const int slot = t % stages, use = t / stages;
+            if (lane == 0) {
+                if (use > 0) mbar_wait(&empty[slot], (unsigned)((use - 1) & 1));
+                mbar_arrive_expect_tx(&full[slot], tile_bytes);
+            }
+            __syncwarp();
+            double* dst = sVr + (size_t)slot * K4 * kFlush4SV;
+            const double* src = V + (step0 + t) * kFlush4Cols;
+            for (int j = lane; j < cnt; j += 32) bulk_g2s(dst + j * kFlush4SV, src + (int64_t)j * ldv, kFlush4Cols * (unsigned)sizeof(double), &full[slot]);
+        }
+        return;
+    }
+    const bool interior = row0 + ROWS <= R && (step0 + nsteps) * kFlush4Cols <= C;
+    const int64_t r_lane = row0 + wr + 2 * fk;
+    double* tp = T + (step0 * kFlush4Cols + wc + fq) * ld + r_lane;
+    const int64_t cstride = 8 * ld, sstride = (int64_t)kFlush4Cols * ld;
+    for (int s = 0; s < nsteps; ++s) {
+        double2 acc[4][4];
+        double* base = tp + (int64_t)s * sstride;
+        if (interior) {
+#pragma unroll
+            for (int ct = 0; ct < 4; ++ct)
+#pragma unroll
+                for (int rt = 0; rt < 4; ++rt) acc[ct][rt] = ld_tile<STREAM>(base + ct * cstride + rt * 8);
+        } else {
+#pragma unroll
+            for (int ct = 0; ct < 4; ++ct) {
+                const int64_t c = (step0 + s) * kFlush4Cols + wc + ct * 8 + fq;
+#pragma unroll
+                for (int rt = 0; rt < 4; ++rt)
+                    acc[ct][rt] = (c < C && r_lane + rt * 8 < R) ? ld_tile<STREAM>(base + ct * cstride + rt * 8) : make_double2(0., 0.);
+            }
+        }
+        const int slot = s % stages;
+        mbar_wait(&full[slot], (unsigned)((s / stages) & 1));
+        const double* sV = sVr + (size_t)slot * K4 * kFlush4SV;
+#pragma unroll 2
+        for (int ks = 0; ks < ksteps; ++ks) {
+            double a[4], b[4];
+            const int j = ks * 4 + fk;
+#pragma unroll
+            for (int ct = 0; ct < 4; ++ct) a[ct] = sV[j * kFlush4SV + wc + ct * 8 + fq];
+#pragma unroll
+            for (int rt = 0; rt < 4; ++rt) b[rt] = sU[j * SU + wr + rt * 8 + fq];
+#pragma unroll
+            for (int ct = 0; ct < 4; ++ct)
+#pragma unroll
+                for (int rt = 0; rt < 4; ++rt) dmma_m8n8k4(acc[ct][rt].x, acc[ct][rt].y, a[ct], b[rt]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
+        if (interior) {
+#pragma unroll
+            for (int ct = 0; ct < 4; ++ct)
+#pragma unroll
+                for (int rt = 0; rt < 4; ++rt) st_tile<STREAM>(base + ct * cstride + rt * 8, acc[ct][rt]);
+        } else {
+#pragma unroll
+            for (int ct = 0; ct < 4; ++ct) {
+                const int64_t c = (step0 + s) * kFlush4Cols + wc + ct * 8 + fq;
+#pragma unroll
+                for (int rt = 0; rt < 4; ++rt)
+                    if (c < C && r_lane + rt * 8 < R) st_tile<STREAM>(base + ct * cstride + rt * 8, acc[ct][rt]);
+            }
+        }
+    }
+}
+
 }  // namespace ellp

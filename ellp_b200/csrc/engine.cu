@@ -430,6 +430,15 @@ void launch_rankk(ellp_b200_ctx* ctx, double* E, int64_t ld, int R, int C, const
     // is short (narrow shards: <= 16 column steps per CTA, 27.9 vs 24.4 TFLOP/s at 32768 x 4096) and near the HBM / tensor crossover
     // (k < 48: 24.9 vs 22.5 at k = 40); on the full 32768 x 32768 tableau at k = 48 .. 56 version 4 stays ahead (27.5 vs 26.6)
     if (ctx->flush_kernel == 0 && kern == 4 && (col_steps <= 16 || cnt < 48)) kern = 8;
+    if (kern == 9) {  // version 4r: 3 x 4 consumer warps, CTA tile 96 rows x 128 columns
+        const int mode = ctx->flush_ld >= 0 ? (ctx->flush_ld ? 1 : 0) : (stream ? 1 : 0);
+        int stages = blk_flush4_stages(K4);
+        if (ctx->flush_stages > 0 && blk_flush4r_smem_bytes<3>(K4, ctx->flush_stages) <= (size_t)227 * 1024) stages = std::min(3, ctx->flush_stages);
+        dim3 grid9((unsigned)((R + 95) / 96), grid.y);
+        if (mode) LAUNCH_SMEM((k_blk_flush4r<1, 3>), grid9, flush4r_threads<3>(), blk_flush4r_smem_bytes<3>(K4, stages), E, ld, R, C, U, V, ldv, cnt, col_steps, stages);
+        else LAUNCH_SMEM((k_blk_flush4r<0, 3>), grid9, flush4r_threads<3>(), blk_flush4r_smem_bytes<3>(K4, stages), E, ld, R, C, U, V, ldv, cnt, col_steps, stages);
+        return;
+    }
     if (kern >= 4) {
         // tile access mode (tuning key "flush_ld"): -1 = auto (evict-first when the matrix exceeds L2, default caching otherwise)
         const int mode = ctx->flush_ld >= 0 ? ctx->flush_ld : (stream ? 1 : 0);
@@ -484,6 +493,7 @@ int flush_attrs(ellp_b200_ctx* ctx) {
     ELLP_ATTR((k_blk_flush5<0, 2>)); ELLP_ATTR((k_blk_flush5<1, 2>)); ELLP_ATTR((k_blk_flush5<2, 2>)); ELLP_ATTR((k_blk_flush5<3, 2>));
     ELLP_ATTR((k_blk_flush5<0, 4>)); ELLP_ATTR((k_blk_flush5<1, 4>)); ELLP_ATTR((k_blk_flush5<2, 4>)); ELLP_ATTR((k_blk_flush5<3, 4>));
     ELLP_ATTR((k_blk_flush6<0, 1>)); ELLP_ATTR((k_blk_flush6<1, 1>)); ELLP_ATTR((k_blk_flush6<0, 2>)); ELLP_ATTR((k_blk_flush6<1, 2>));
+    ELLP_ATTR((k_blk_flush4r<0, 3>)); ELLP_ATTR((k_blk_flush4r<1, 3>));
 #undef ELLP_ATTR
     ctx->flush_attrs_set = true;
     return ELLP_OK;

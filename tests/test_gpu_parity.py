@@ -588,7 +588,7 @@ def test_rankk_update_kernel_variants_are_bit_identical(env, R, C_, k):
     V = np.ascontiguousarray(rng.standard_normal((k, C_)))
     out = {}
     try:
-        for kern in (1, 3, 4, 5, 6, 7, 8):
+        for kern in (1, 3, 4, 5, 6, 7, 8, 9):
             ctx.set_tuning("flush_kernel", kern)
             got = E.copy(order="F")
             ctx.check(N.lib.ellp_b200_rankk_update(ctx.h, N.ptr(got), R, C_, R, N.ptr(U), N.ptr(V), k))
@@ -597,7 +597,7 @@ def test_rankk_update_kernel_variants_are_bit_identical(env, R, C_, k):
         ctx.set_tuning("flush_kernel", 0)
     scale = np.abs(E) + np.abs(U) @ np.abs(V)
     assert (np.abs(out[4] - (E - U @ V)) <= 4 * np.finfo(float).eps * scale * k).all()
-    for kern in (1, 3, 5, 6, 7, 8):
+    for kern in (1, 3, 5, 6, 7, 8, 9):
         np.testing.assert_array_equal(out[kern], out[4], err_msg=f"flush_kernel {kern} vs 4")
 
 

@@ -9,7 +9,7 @@ from ellp_b200 import _native as N
 import blk_sweep
 
 ctx = N.Context(0)
-kerns = (4, 5, 7, 8)
+kerns = (4, 5, 8, 9)
 for k in (56, 64, 48, 40):
     for kern in kerns:
         ctx.set_tuning("flush_kernel", kern)
@@ -23,7 +23,7 @@ for Cc in (4096, 8192):
         d["flush_kernel"] = kern
         print(json.dumps(d), flush=True)
 for bk in (56, 64):
-    for kern in (4, 7, 8):
+    for kern in (4, 8, 9):
         ctx.set_tuning("flush_kernel", kern)
         d = blk_sweep.loop_point(ctx, 32768, 32768, bk, 12 * bk, 32)
         d["flush_kernel"] = kern
