@@ -59,9 +59,9 @@ def _protect_stdout() -> None:
 
 WORKLOADS = {
     # BASELINE.json configs[4]: "synthetic dense LP 32768x65536 fp64, tableau column-sharded ... at 1/2/4/8 B200"
-    "dense_tableau_32768x65536": dict(m=32768, ns=32768, pivots=672, block_k=56, sample_m=1024, sample_pivots=3),
+    "dense_tableau_32768x65536": dict(m=32768, ns=32768, pivots=704, block_k=64, sample_m=1024, sample_pivots=3),
     # north_star target size: "for a 16384x32768 dense LP, the row-reduction kernel sustains >= 70% of HBM bandwidth"
-    "dense_tableau_16384x32768": dict(m=16384, ns=16384, pivots=672, block_k=48, sample_m=1024, sample_pivots=3),
+    "dense_tableau_16384x32768": dict(m=16384, ns=16384, pivots=704, block_k=64, sample_m=1024, sample_pivots=3),
     "dense_tableau_4096x12288": dict(m=4096, ns=8192, pivots=960, block_k=48, sample_m=512, sample_pivots=6),
     # BASELINE.json configs[2] shape: dense 4096x8192 (Gte rows => standard form 4096x12288), DUAL simplex, revised engine
     # (explicit basis inverse), the reference's entering / leaving rules.
@@ -70,8 +70,8 @@ WORKLOADS = {
     "dense_tableau_dual_4096x12288": dict(m=4096, ns=8192, pivots=960, block_k=48, sample_m=512, sample_pivots=6, dual=True, tableau=True),
     # ... and with dual Devex pricing (reference weights updated from the entering column, no extra pass): a step = one whole solve
     "dense_tableau_dual_devex_4096x12288": dict(m=4096, ns=8192, pivots=200, block_k=48, sample_m=512, sample_pivots=6, dual=True, tableau=True, devex=True),
-    "dense_tableau_dual_16384x32768": dict(m=16384, ns=16384, pivots=672, block_k=48, sample_m=1024, sample_pivots=3, dual=True, tableau=True),
-    "dense_tableau_dual_32768x65536": dict(m=32768, ns=32768, pivots=672, block_k=56, sample_m=1024, sample_pivots=3, dual=True, tableau=True),
+    "dense_tableau_dual_16384x32768": dict(m=16384, ns=16384, pivots=704, block_k=64, sample_m=1024, sample_pivots=3, dual=True, tableau=True),
+    "dense_tableau_dual_32768x65536": dict(m=32768, ns=32768, pivots=704, block_k=64, sample_m=1024, sample_pivots=3, dual=True, tableau=True),
     # the same LP with dual steepest edge (exact weights from the rank-1 update's epilogue) + Harris ratio test
     "dense_revised_dual_dse_4096x12288": dict(m=4096, ns=8192, pivots=200, sample_m=512, sample_pivots=6, dual=True, dse=True),
     # BASELINE.json configs[0] / configs[1]: netlib LPs of the reference's tests/benchmark_problems (fixtures in tests/golden/),

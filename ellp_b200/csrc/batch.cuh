@@ -429,14 +429,21 @@ __device__ int batch_run_phase(const BatchSmem& s, int m_rt, int n0_rt, int ld_r
             if (groups > 0) {
                 if (my_group < groups && my_row != nb) {
                     const double na = -s.dcol[my_row];
-                    double* __restrict__ t = s.T + (size_t)my_group * ld + my_row;
-                    const double* __restrict__ pp = s.prow + my_group;
-                    if (MCT > 0 && N0CT > 0) {
-                        constexpr int G = MCT > 0 ? kBatchThreads / MCT : 1, LD = (MCT % 2 == 0) ? MCT + 1 : MCT, IT = (N0CT + G - 1) / G;
+                    constexpr int G = MCT > 0 ? kBatchThreads / MCT : 1, LD = (MCT % 2 == 0) ? MCT + 1 : MCT, IT = N0CT / G;
+                    if (MCT > 0 && N0CT > 0 && N0CT % (2 * G) == 0) {
+                        // compile-time shape: column group g owns the IT consecutive columns [g*IT, (g+1)*IT) -- the pivot-row entries of
+                        // two neighbouring columns arrive in one 16-byte broadcast load, every tableau offset is an immediate
+                        double* __restrict__ t = s.T + (size_t)my_group * IT * LD + my_row;
+                        const double2* __restrict__ pp2 = reinterpret_cast<const double2*>(s.prow + my_group * IT);
 #pragma unroll
-                        for (int u = 0; u < IT; ++u)
-                            if (N0CT % G == 0 || my_group + u * G < N0CT) t[u * G * LD] = fma(na, pp[u * G], t[u * G * LD]);
+                        for (int u = 0; u < IT; u += 2) {
+                            const double2 p2 = pp2[u / 2];
+                            t[u * LD] = fma(na, p2.x, t[u * LD]);
+                            t[(u + 1) * LD] = fma(na, p2.y, t[(u + 1) * LD]);
+                        }
                     } else {
+                        double* __restrict__ t = s.T + (size_t)my_group * ld + my_row;
+                        const double* __restrict__ pp = s.prow + my_group;
                         const int tstep = groups * ld;
 #pragma unroll 4
                         for (int j = my_group; j < n0; j += groups) { *t = fma(na, *pp, *t); t += tstep; pp += groups; }

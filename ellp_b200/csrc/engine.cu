@@ -408,28 +408,39 @@ int gemv_grid(int ncols) { return std::max(1, std::min((ncols + 7) / 8, 148 * 32
 void launch_rankk(ellp_b200_ctx* ctx, double* E, int64_t ld, int R, int C, const double* U, const double* V, int64_t ldv, int cnt) {
     const int K4 = (cnt + 3) & ~3;
     int kern = ctx->flush_kernel;
-    // auto (measured at 32768^2, profiles/r01_flush_kernel_sweeps.jsonl): the 16-warp kernel wins for 40 <= k <= 56 (3 or 2 ring
-    // stages fit next to -U), the register-prefetching kernel below (HBM-bound) and at k > 56 (only two wide stages would fit)
-    if (kern == 0) kern = (cnt >= ctx->flush4_min_k && cnt <= 56) ? 4 : 3;
+    const bool automatic = (kern == 0);
+    // auto, first part (profiles/r02_flush5_sweep.jsonl, r02_flush_lowk_sweep.jsonl, 32768^2 tableau): version 4r (12 consumer warps, 128
+    // registers) is ahead of versions 3 / 4 from k = 24 on (k = 32: 22.6 vs 19.0 TFLOP/s, k = 56: 29.8 vs 27.4, k = 64: 30.8 vs 27.4 / 24.3);
+    // below that the kernels are HBM-bound and level, version 3 stays
+    if (automatic) kern = (cnt >= 24) ? 9 : 3;
     const bool base_ok = (ldv % 2 == 0) && ((reinterpret_cast<uintptr_t>(V) & 15) == 0);
-    const bool wide = kern >= 4;  // 128-column steps, 16 consumer warps (5 / 6: tile pipelined in 2 / 4 parts; 7 / 8: no producer warp, 128 registers)
+    const bool wide = kern >= 4;  // 128-column steps (4: 16 consumer warps; 5 / 6: tile pipelined in 2 / 4 parts; 7 / 8: no producer warp; 9: 12 warps)
     if (wide && !(base_ok && (int64_t)((C + kFlush4Cols - 1) / kFlush4Cols) * kFlush4Cols <= ldv)) kern = 3;
     if (kern == 3 && !(base_ok && (int64_t)((C + kFlushCols - 1) / kFlushCols) * kFlushCols <= ldv)) kern = 1;
     if (kern == 2) kern = 1;
     const int cols_per_step = kern >= 4 ? kFlush4Cols : kFlushCols;
     const int steps_total = (C + cols_per_step - 1) / cols_per_step;
     const size_t smem = kern >= 4 ? blk_flush4_smem_bytes(K4) : (kern == 3 ? blk_flush3_smem_bytes(K4) : blk_flush_smem_bytes(K4));
-    int col_steps = std::max(1, std::min(kern == 1 ? ctx->flush_col_steps : ctx->flush2_col_steps, steps_total));
-    if (kern != 1) {  // one CTA per SM: keep at least ~6 waves of CTAs so the last partial wave stays small (narrow shards)
-        const int64_t row_blocks = (R + kFlushRows - 1) / kFlushRows;
-        while (col_steps > 4 && row_blocks * ((steps_total + col_steps - 1) / col_steps) < (int64_t)ctx->flush_waves * 148) col_steps >>= 1;
-    }
+    // column steps per CTA.  One CTA per SM: keep enough waves of CTAs that the last partial wave stays small (narrow shards) -- 6 waves
+    // of 128-row CTAs (profiles/r02_flush_shard_sweep.jsonl), 4 waves of the 96-row CTAs of version 4r (32768 x 4096, k = 64: 16 steps per
+    // CTA = 684 CTAs 28.0 TFLOP/s, 8 steps 26.0, 32 steps 24.5)
+    auto plan = [&](int kn) {
+        int cs = std::max(1, std::min(kn == 1 ? ctx->flush_col_steps : ctx->flush2_col_steps, steps_total));
+        if (kn != 1) {
+            const int rows = (kn == 9) ? 96 : kFlushRows;
+            const int waves = (kn == 9) ? std::min(ctx->flush_waves, 4) : ctx->flush_waves;
+            const int64_t row_blocks = (R + rows - 1) / rows;
+            while (cs > 4 && row_blocks * ((steps_total + cs - 1) / cs) < (int64_t)waves * 148) cs >>= 1;
+        }
+        return cs;
+    };
+    int col_steps = plan(kern);
+    // auto, second part: where a CTA is short (<= 8 column steps: small tableaus such as 4096 x 8192, where it leads at every k -- k = 48:
+    // 23.1 vs 20.2 (4r) vs 17.6 (3) TFLOP/s) the producer-less kernel with the tile pipelined in two halves wins; its 203 KB of shared
+    // memory at k > 56 leave too little L1, so version 4r keeps those
+    if (automatic && kern == 9 && col_steps <= 8 && cnt <= 56) { kern = 8; col_steps = plan(8); }
     dim3 grid((unsigned)((R + kFlushRows - 1) / kFlushRows), (unsigned)((steps_total + col_steps - 1) / col_steps));
     const bool stream = (double)R * C * 8.0 > (double)ctx->rank1_stream_min_mb * 1048576.0;
-    // auto, second part (profiles/r02_flush5_sweep.jsonl): the producer-less kernel with the tile pipelined in two halves wins where a CTA
-    // is short (narrow shards: <= 16 column steps per CTA, 27.9 vs 24.4 TFLOP/s at 32768 x 4096) and near the HBM / tensor crossover
-    // (k < 48: 24.9 vs 22.5 at k = 40); on the full 32768 x 32768 tableau at k = 48 .. 56 version 4 stays ahead (27.5 vs 26.6)
-    if (ctx->flush_kernel == 0 && kern == 4 && (col_steps <= 16 || cnt < 48)) kern = 8;
     if (kern == 9) {  // version 4r: 3 x 4 consumer warps, CTA tile 96 rows x 128 columns
         const int mode = ctx->flush_ld >= 0 ? (ctx->flush_ld ? 1 : 0) : (stream ? 1 : 0);
         int stages = blk_flush4_stages(K4);

@@ -17,3 +17,6 @@ for f in ('gpurun_out/r02_flush5_sweep.jsonl', 'gpurun_out/r02_flush_lowk_sweep.
     for l in open(f):
         d = json.loads(l); print({k: d[k] for k in d if k in ('R', 'C', 'k', 'ms', 'TFLOPs', 'GBs', 'flush_kernel', 'block_k', 'pivots_per_s')})
 "
+# ncu evidence of the default command with the final kernels (each only after the plain run above exited 0)
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_ncu_launches_default_k64_32768x65536.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-other-configs > gpurun_out/ncu_default_launches2.log 2>&1; echo "ncu launches rc=$?"
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_blk_flush4r -s 2 -c 1 -o gpurun_out/r02_ncu_full_blk_flush4r python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-other-configs > gpurun_out/ncu_flush4r_full.log 2>&1; echo "ncu full rc=$?"
