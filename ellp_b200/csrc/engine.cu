@@ -111,9 +111,10 @@ struct ellp_b200_ctx {
     int blk_kmax = 0;             // slots allocated for the blocked (deferred rank-k) tableau engine; 0 = rank-1 engine only
     int blk_fill = 0;             // slots used since the last flush
     int flush_col_steps = 8;      // column steps (of 64 columns) per CTA of k_blk_flush
-    int flush_kernel = 0;         // tuning: 0 = auto (4 for k >= flush4_min_k, else 3), 1 = k_blk_flush (2 CTAs/SM, also the fallback for an unpadded V),
-                                  // 3 = k_blk_flush3 (register prefetch + bulk-copy ring), 4 = k_blk_flush4 (16 consumer warps, tensor-bound regime)
-    int flush4_min_k = 40;
+    int flush_kernel = 0;         // tuning: 0 = auto (see launch_rankk), 1 = k_blk_flush (2 CTAs/SM, also the fallback for an unpadded V),
+                                  // 3 = k_blk_flush3 (register prefetch + bulk-copy ring), 4 = k_blk_flush4 (16 consumer warps), 5 / 6 = k_blk_flush5<2 / 4>,
+                                  // 7 / 8 = k_blk_flush6<1 / 2> (no producer warp), 9 = k_blk_flush4r<3> (12 consumer warps, 128 registers)
+    int flush4_min_k = 24;        // auto: the wide kernels (versions 4r / 6) from this many pending pairs on, version 3 below
     int flush_ld = -1;            // tuning key "flush_ld": tile access mode of versions 4 / 5 (-1 = auto, see ld_tile in blocked.cuh)
     int flush_stages = 0;         // tuning key "flush_stages": ring depth of versions 4 / 5 (0 = blk_flush4_stages)
     bool flush_attrs_set = false;
@@ -412,7 +413,7 @@ void launch_rankk(ellp_b200_ctx* ctx, double* E, int64_t ld, int R, int C, const
     // auto, first part (profiles/r02_flush5_sweep.jsonl, r02_flush_lowk_sweep.jsonl, 32768^2 tableau): version 4r (12 consumer warps, 128
     // registers) is ahead of versions 3 / 4 from k = 24 on (k = 32: 22.6 vs 19.0 TFLOP/s, k = 56: 29.8 vs 27.4, k = 64: 30.8 vs 27.4 / 24.3);
     // below that the kernels are HBM-bound and level, version 3 stays
-    if (automatic) kern = (cnt >= 24) ? 9 : 3;
+    if (automatic) kern = (cnt >= ctx->flush4_min_k) ? 9 : 3;
     const bool base_ok = (ldv % 2 == 0) && ((reinterpret_cast<uintptr_t>(V) & 15) == 0);
     const bool wide = kern >= 4;  // 128-column steps (4: 16 consumer warps; 5 / 6: tile pipelined in 2 / 4 parts; 7 / 8: no producer warp; 9: 12 warps)
     if (wide && !(base_ok && (int64_t)((C + kFlush4Cols - 1) / kFlush4Cols) * kFlush4Cols <= ldv)) kern = 3;

@@ -164,7 +164,9 @@ int ellp_b200_generate_dense_ex(ellp_b200_ctx*, int32_t m, int32_t n_struct, uin
 int ellp_b200_download_std_form(ellp_b200_ctx*, double* A, double* c, double* b, uint8_t* kind, double* lb, double* ub);
 /* tuning knobs: "rank1_cols_per_cta", "rank1_stream_min_mb", "refactor_mode", "flush_col_steps", "flush_waves", "flush_kernel" (rank-k row
  * reduction: 0 = auto, 1 = k_blk_flush, 3 = k_blk_flush3, 4 = k_blk_flush4, 5 / 6 = k_blk_flush5<2 / 4>, 7 / 8 = k_blk_flush6<1 / 2>, 9 =
- * k_blk_flush4r<3>; all bit-identical), "flush_ld" (tile access mode of versions 4 .. 9, -1 = auto), "flush_stages" (ring depth, 0 = auto), "coop_pivots",
+ * k_blk_flush4r<3>; all bit-identical), "flush4_min_k" (auto: pending pairs from which the 128-column kernels take over, default 24), "flush_ld" (tile
+ * access mode of versions 4 .. 9, -1 = auto), "flush_stages" (ring depth, 0 = auto), "refactor_panel" (panel width of the blocked LU), "coop_pivots",
+ * "coop_ctas_per_sm" (CTAs per SM of the cooperative pivot kernels, 0 = occupancy query),
  * "coop_threads", "peer_exchange", "owner_ratio" (sharded primal: 1 = only the owner of the entering column runs the ratio test), "fast_upload"
  * (0 = always upload the whole A so that the tableau stays rebuildable), "residual_every" / "residual_tol_1e12" (residual-triggered rebuild of a
  * rebuildable tableau: pivots between checks of |A x - b|_inf, tolerance in units of 1e-12 relative to 1 + |b|_inf), "batch_pipeline" (0 = upload,

@@ -344,3 +344,15 @@ def test_rust_ffi_structs_mirror_the_header():
     for fn in fns:
         assert hasattr(lib, fn), fn
         assert re.search(r"\b" + fn + r"\s*\(", hdr), fn
+
+
+def test_every_tuning_key_of_the_engine_is_documented_in_the_header():
+    """ellp_b200_set_tuning accepts string keys; the header comment is their only documentation -- keep the two in step."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "ellp_b200", "csrc", "engine.cu")).read()
+    hdr = open(os.path.join(root, "include", "ellp_b200.h")).read()
+    keys = sorted(set(re.findall(r'strcmp\(key, "([a-z_0-9]+)"\)', src)))
+    assert len(keys) >= 20
+    missing = [k for k in keys if f'"{k}"' not in hdr]
+    assert not missing, f"tuning keys missing from include/ellp_b200.h: {missing}"
