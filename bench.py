@@ -692,7 +692,13 @@ def run_ours(args, wl, name):
     if bk > 1:
         k3_cols = ns
         alg_bytes = 16.0 * m * k3_cols + 8.0 * bk * (m + k3_cols)
-        kernel = "k_blk_flush (rank-%d row reduction T -= U V of the condensed %d x %d tableau, fp64 DMMA)" % (bk, m, ns)
+        try:  # the version launch_rankk's auto rule launched on this shape
+            flush_version = int(N.lib.ellp_b200_last_flush_kernel(ctx.h))
+        except Exception:
+            flush_version = 0
+        fk = {1: "k_blk_flush", 3: "k_blk_flush3", 4: "k_blk_flush4", 5: "k_blk_flush5<2>", 6: "k_blk_flush5<4>", 7: "k_blk_flush6<1>", 8: "k_blk_flush6<2>",
+              9: "k_blk_flush4r<3>"}.get(flush_version, "k_blk_flush")
+        kernel = "%s (rank-%d row reduction T -= U V of the condensed %d x %d tableau, fp64 DMMA)" % (fk, bk, m, ns)
         traffic_key = name + ":k_blk_flush"
     else:
         k3_cols = ns if tab else m  # revised engine: K3 updates the m x m basis inverse; tableau engine: the condensed tableau

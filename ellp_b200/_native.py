@@ -124,6 +124,7 @@ def _load():
         "ellp_b200_sharded_upload_nonbasic_ex": (C.c_int, [vp, C.POINTER(StdForm), C.POINTER(Point), C.c_int, vp, C.POINTER(Opts)]),
         "ellp_b200_sharded_upload": (C.c_int, [vp, C.POINTER(StdForm), C.POINTER(Point), C.POINTER(Opts)]),
         "ellp_b200_phase_log": (C.c_int, [vp, C.POINTER(C.c_int64), C.c_int32]),
+        "ellp_b200_last_flush_kernel": (C.c_int, [vp]),
         "ellp_b200_sharded_upload_nonbasic": (C.c_int, [vp, C.POINTER(StdForm), C.POINTER(Point), C.POINTER(Opts)]),
         "ellp_b200_generate_dense_ex": (C.c_int, [vp, i32, i32, u64, i32, C.POINTER(Opts)]),
         "ellp_b200_generate_dense": (C.c_int, [vp, i32, i32, u64, C.POINTER(Opts)]),

@@ -114,6 +114,7 @@ struct ellp_b200_ctx {
     int flush_kernel = 0;         // tuning: 0 = auto (see launch_rankk), 1 = k_blk_flush (2 CTAs/SM, also the fallback for an unpadded V),
                                   // 3 = k_blk_flush3 (register prefetch + bulk-copy ring), 4 = k_blk_flush4 (16 consumer warps), 5 / 6 = k_blk_flush5<2 / 4>,
                                   // 7 / 8 = k_blk_flush6<1 / 2> (no producer warp), 9 = k_blk_flush4r<3> (12 consumer warps, 128 registers)
+    int last_flush_kernel = 0;    // version launch_rankk launched last (ellp_b200_last_flush_kernel)
     int flush4_min_k = 24;        // auto: the wide kernels (versions 4r / 6) from this many pending pairs on, version 3 below
     int flush_ld = -1;            // tuning key "flush_ld": tile access mode of versions 4 / 5 (-1 = auto, see ld_tile in blocked.cuh)
     int flush_stages = 0;         // tuning key "flush_stages": ring depth of versions 4 / 5 (0 = blk_flush4_stages)
@@ -442,6 +443,7 @@ void launch_rankk(ellp_b200_ctx* ctx, double* E, int64_t ld, int R, int C, const
     if (automatic && kern == 9 && col_steps <= 8 && cnt <= 56) { kern = 8; col_steps = plan(8); }
     dim3 grid((unsigned)((R + kFlushRows - 1) / kFlushRows), (unsigned)((steps_total + col_steps - 1) / col_steps));
     const bool stream = (double)R * C * 8.0 > (double)ctx->rank1_stream_min_mb * 1048576.0;
+    ctx->last_flush_kernel = kern;
     if (kern == 9) {  // version 4r: 3 x 4 consumer warps, CTA tile 96 rows x 128 columns
         const int mode = ctx->flush_ld >= 0 ? (ctx->flush_ld ? 1 : 0) : (stream ? 1 : 0);
         int stages = blk_flush4_stages(K4);
@@ -1240,6 +1242,8 @@ int ellp_b200_set_tuning(ellp_b200_ctx* ctx, const char* key, int value) {
     else return set_err(ctx, ELLP_E_ARG, std::string("unknown tuning key ") + key);
     return ELLP_OK;
 }
+
+int ellp_b200_last_flush_kernel(ellp_b200_ctx* ctx) { return ctx ? ctx->last_flush_kernel : 0; }
 
 int ellp_b200_phase_log(ellp_b200_ctx* ctx, int64_t* out, int32_t pivots) {
     if (!ctx || !out || !ctx->tlog || pivots > ctx->tlog_cap) return ELLP_E_ARG;

@@ -193,6 +193,10 @@ def bench_main(args, wl, name, METRIC, UNIT, SEED, ClockSampler, measured_peak, 
     tt = torch.tensor([dt_local, dev_ms, rank1_ms / max(n_rank1, 1)], dtype=torch.float64, device="cuda")
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dt, dev_ms_max, k3_ms = [float(v) for v in tt.cpu()]
+    try:  # version of the row reduction that launch_rankk's auto rule picked for this shard shape (read before the parity LP below runs)
+        flush_version = int(N.lib.ellp_b200_last_flush_kernel(ctx.h))
+    except Exception:
+        flush_version = 0
     value = args.steps * P / dt
     obj_resident = float(r.obj)
 
@@ -305,7 +309,9 @@ def bench_main(args, wl, name, METRIC, UNIT, SEED, ClockSampler, measured_peak, 
         nloc = hi - lo
         if peer:
             alg_bytes = 16.0 * m * nloc + 8.0 * bk * (m + nloc)
-            kernel = "k_blk_flush (rank-%d row reduction of the local %d x %d slice of the condensed tableau, fp64 DMMA)" % (bk, m, nloc)
+            fk = {1: "k_blk_flush", 3: "k_blk_flush3", 4: "k_blk_flush4", 5: "k_blk_flush5<2>", 6: "k_blk_flush5<4>", 7: "k_blk_flush6<1>",
+                  8: "k_blk_flush6<2>", 9: "k_blk_flush4r<3>"}.get(flush_version, "k_blk_flush")
+            kernel = "%s (rank-%d row reduction of the local %d x %d slice of the condensed tableau, fp64 DMMA)" % (fk, bk, m, nloc)
         else:
             alg_bytes = 16.0 * m * nloc + 8.0 * (m + nloc)
             kernel = "k_rank1<true> on the local column shard"

@@ -175,6 +175,8 @@ int ellp_b200_set_tuning(ellp_b200_ctx*, const char* key, int value);
 /* profiling aid: after set_tuning("phase_timing", P) the fused pivot kernel logs 10 clock64() stamps per pivot (block 0,
  * thread 0; phase boundaries, see peer.cuh) for the next P pivots; this copies the first `pivots` records (10 int64 each). */
 int ellp_b200_phase_log(ellp_b200_ctx*, int64_t* out, int32_t pivots);
+/* version of the rank-k row reduction (K3b) that the last flush launched: the "flush_kernel" numbering above (0 = none yet) */
+int ellp_b200_last_flush_kernel(ellp_b200_ctx*);
 
 /* ---- K6: batches of independent small LPs (BASELINE.json configs[3]) -------------------------------------------
  * Every LP of the batch has the same standard-form shape m x n and no Free variable; LP k sits at offset k*m*n (A,
