@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(kFlush4Threads, 1) k_blk_flush5(double* __rest
 // ------------------------------------------------------------------------------------------------
 // K3b, version 6: the 16-consumer-warp kernel WITHOUT a producer warp.  512 threads instead of 544 lift the register cap from 96 to
 // 128 per thread: versions 4 / 5 spill (56 - 80 bytes), and their spill reloads (LDL) sit on the same scoreboards as the
-// outstanding tile loads -- ncu's source page of version 4 shows 28 % of all stall samples as long_scoreboard on integer
+// outstanding tile loads -- on ncu's source page of version 4 long_scoreboard is 28 % of all stall samples, two thirds of them on integer
 // instructions that only consume a reloaded spill (profiles/r02_ncu_full_blk_flush4_k56_summary.txt), i.e. a warp waits for its
 // whole T tile before it even polls the ring, and in version 5 the reloads inside the pipelined loop cancel the overlap.
 // The ring is refilled by whichever consumer warp is the LAST to finish the DMMAs of a step (a shared-memory arrival counter per
