@@ -57,7 +57,7 @@ def case_flush(ctx):
     out = []
     rng = np.random.default_rng(1)
     R, Cc = 512, 1000
-    for kern, k in ((1, 24), (3, 24), (4, 48), (3, 64)):
+    for kern, k in ((1, 24), (3, 24), (4, 48), (3, 64), (5, 56), (8, 56), (9, 64), (9, 40)):
         ctx.set_tuning("flush_kernel", kern)
         E = np.asfortranarray(rng.standard_normal((R, Cc)))
         U = np.asfortranarray(rng.standard_normal((R, k)))
